@@ -1,0 +1,38 @@
+"""Import the reference's OWN ellipsoid-half modules, unmodified, from /root/reference.
+
+ORACLE / TEST INFRASTRUCTURE -- see oracle/__init__.py.
+
+Only works in the build container (the GPU box has no /root/reference): callers must check
+``available()`` and skip otherwise.  Nothing is copied: the modules are imported from where
+they lie, with oracle/_casadi_shim on sys.path to satisfy ``from casadi import reshape``
+(reference safe_exploration/utils.py:14).
+"""
+import os
+import sys
+import warnings
+
+REFERENCE_ROOT = "/root/reference"
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_casadi_shim")
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "safe_exploration", "gp_reachability.py"))
+
+
+def load():
+    """Returns (gp_reachability, utils, utils_ellipsoid) modules of the reference."""
+    if not available():
+        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+    have_casadi = True
+    try:
+        import casadi  # noqa: F401  (a real CasADi wins if one is ever installed)
+    except ImportError:
+        have_casadi = False
+    if not have_casadi and _SHIM not in sys.path:
+        sys.path.insert(0, _SHIM)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.append(REFERENCE_ROOT)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from safe_exploration import gp_reachability, utils, utils_ellipsoid
+    return gp_reachability, utils, utils_ellipsoid
