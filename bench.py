@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Headline benchmark: ellipsoid-reachability rollouts/sec (B x H onestep calls) on N B200s.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # product arm (libsegp.so, CUDA)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # CPU arm: the reference algorithm's port
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus 8 --steps 5 --warmup 3
+
+Workload (BASELINE.json): config C4 = cart-pole, GP N=5000, H=20, n_s=4, B=65536 sharded over 8 GPUs, i.e.
+8192 candidate sequences per GPU; the same per-GPU shard is the N=1 workload (weak scaling: B = 8192 x N).
+A "step" is one pass of the hot path over the rank's batch: B_g independent H-step rollouts
+(multistep_reachability) = B_g x H one-step calls.  `value` times the device-resident path (inputs in HBM,
+CUDA events); `e2e` times the same call through the host-buffer C-ABI entry (segp_multistep_host: pinned host
+inputs, H2D + D2H inside the timed region).  Every rank prints nothing except rank 0's single JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ellipsoid_reachability_rollouts_per_sec"
+UNIT = "rollouts/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "MEASURED_PEAKS.json (of measured)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "_source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, smax, power, reasons = [], [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _oracle_model(w):
+    from oracle.gp_oracle import GPOracle
+    return GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
+                    [h["variance"] for h in w.hyp], [h["noise"] + 1e-5 + 1e-8 for h in w.hyp])
+
+
+def cpu_baseline(w, seconds_target=15.0):
+    """The vectorised float64 oracle (oracle/reach_oracle.multistep_batch: Cholesky + solve_triangular on N x B
+    panels, all host cores through BLAS) on a bounded sample of the same workload."""
+    from oracle import reach_oracle
+    ora = _oracle_model(w)
+    cores = os.cpu_count() or 1
+    sample = 8
+    t_used = 0.0
+    best = None
+    while True:
+        k_ff = w.k_ff[:sample]
+        t0 = time.perf_counter()
+        reach_oracle.multistep_batch(w.p0, ora, w.k_fb, k_ff, w.l_mu, w.l_sigma, None, w.c_safety, w.a, w.b)
+        dt = time.perf_counter() - t0
+        t_used += dt
+        best = (sample, dt)
+        if t_used > seconds_target or sample * 4 > w.k_ff.shape[0] or dt * 4 > seconds_target:
+            break
+        sample *= 4
+    return {"value": best[0] / best[1], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "{} of the workload's rollouts (H={}), vectorised float64 NumPy/SciPy oracle "
+                      "(Cholesky form), {:.2f} s".format(best[0], w.horizon, best[1])}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm for the path, one trajectory at a time
+    (multistep_reachability over SimpleGPModel.__call__ with per-dimension explicit K^-1,
+    gp_reachability.py:159-212 / gp_models_utils_casadi.py:186-193) as restated in oracle/ ("port": GPy and
+    CasADi are not installable, /root/reference does not exist on the GPU box)."""
+    if rank != 0:
+        return
+    from oracle import reach_oracle
+    from safe_exploration_b200 import workloads
+    per_step = max(1, args.ref_rollouts)
+    w = workloads.make(args.config, batch=per_step * (args.steps + args.warmup))
+    ora = _oracle_model(w)
+    ora._ensure_inv()
+    cores = os.cpu_count() or 1
+
+    def one_step(i):
+        for j in range(per_step):
+            reach_oracle.multistep_reachability(w.p0[:, None], ora, w.k_fb, w.k_ff[i * per_step + j], w.l_mu,
+                                                w.l_sigma, None, w.c_safety, 0, w.a, w.b)
+
+    for i in range(args.warmup):
+        one_step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one_step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "{} rollouts per step, one trajectory at a time, explicit-inverse form, float64 NumPy".format(per_step)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config_dict(args, w, per_step, world, "host"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def _config_dict(args, w, b_per_gpu, world, where):
+    return {"workload": "{}: {} GP N={} H={} n_s={} n_u={} kernel={}; B={} candidate sequences per GPU x {} GPU(s) "
+                        "= {} (BASELINE C4 is 65536 over 8 GPUs)".format(
+                            w.name, "cart-pole" if w.n_s == 4 else ("pendulum" if w.n_s == 2 else "synthetic 10-D"),
+                            w.n_train, w.horizon, w.n_s, w.n_u, w.kern_types[0], b_per_gpu, world, b_per_gpu * world),
+            "n_train": w.n_train, "horizon": w.horizon, "n_s": w.n_s, "n_u": w.n_u,
+            "batch_per_gpu": b_per_gpu, "global_batch": b_per_gpu * world, "parallelism": "dp{}".format(world),
+            "inputs": where,
+            "l2_policy": "inputs larger than L2: every step streams the packed factor ({} MB) and a K* block far "
+                         "above the 126 MB L2".format(int(w.n_s * w.n_train ** 2 * 4 / 1e6))}
+
+
+def run_product(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import safe_exploration_b200 as se
+    from safe_exploration_b200 import distributed as sd
+    from safe_exploration_b200 import workloads
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = workloads.CONFIGS[args.config]
+    b_per_gpu = args.batch_per_gpu or max(1, cfg[5] // cfg[6])
+    w = workloads.make(args.config, batch=b_per_gpu * world)
+    s0, s1 = sd.shard_range(b_per_gpu * world, rank, world)
+    k_ff_shard = np.ascontiguousarray(w.k_ff[s0:s1])
+
+    t_setup0 = time.perf_counter()
+    gp = sd.build_replicated_model(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, w.kern_types, w.hyp, rank, world,
+                                   src=0, device=local_rank, redundant=args.redundant_factor)
+    torch.cuda.synchronize(dev)
+    t_setup = time.perf_counter() - t_setup0
+
+    # ---------------- device-resident inputs (the `value` arm)
+    p0_d = torch.as_tensor(w.p0, device=dev)
+    kff_d = torch.as_tensor(k_ff_shard, device=dev)
+    kfb_d = torch.as_tensor(w.k_fb, device=dev)
+    rargs = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+
+    def step_device():
+        return se.rollout(gp, p0_d, kff_d, kfb_d, *rargs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        res = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = gp.get_option("launches")
+    gp.set_option("time_tri", 1)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        res = step_device()
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    tri_ns = gp.get_option("tri_ns")
+    tri_count = gp.get_option("tri_launches")
+    gp.set_option("time_tri", 0)
+    launches = gp.get_option("launches") - launches0
+    ms_max = sd.max_across_ranks(ms)
+    status_bad = int((res.status != 0).sum().item())
+    finite = bool(torch.isfinite(res.q_all).all().item())
+
+    # ---------------- end-to-end arm: host buffers through segp_multistep_host
+    kff_pin = torch.as_tensor(k_ff_shard).pin_memory()
+    kff_host = kff_pin.numpy()
+    bsz, hor = k_ff_shard.shape[0], k_ff_shard.shape[1]
+    h2d = kff_host.nbytes + w.p0.nbytes + w.k_fb.nbytes
+    d2h = 8 * bsz * hor * (w.n_s + w.n_s * w.n_s + w.n_s) + 4 * bsz
+
+    def step_host():
+        return se.rollout(gp, w.p0, kff_host, w.k_fb, *rargs)
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res_h = step_host()
+    torch.cuda.synchronize(dev)
+    t_e2e = time.perf_counter() - t0
+    t_e2e_max = sd.max_across_ranks(t_e2e)
+    if rank == 0:
+        time.sleep(0.2)
+        sampler.stop()
+    same = bool(np.array_equal(res_h.q_all, res.q_all.cpu().numpy()))
+
+    if rank != 0:
+        return
+    peaks = _peaks()
+    total_b = b_per_gpu * world
+    value = total_b * args.steps / (ms_max * 1e-3)
+    # roofline of the dominant kernel (tri_sumsq): algorithmic flop per launch = n_s * N^2 * columns of the launch
+    flop_launch = float(w.n_s) * w.n_train ** 2 * min(b_per_gpu, gp.get_option("chunk"))
+    tri_avg_s = (tri_ns / max(tri_count, 1)) * 1e-9
+    achieved = flop_launch / tri_avg_s / 1e12 if tri_avg_s > 0 else None
+    dmma = _dmma_peak(gp, local_rank)
+    bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    roofline = {"bound": "tensor", "kernel": "tri_sumsq_kernel", "pipe": "fp64 DMMA (mma.sync m8n8k4.f64)",
+                "achieved": achieved, "peak": dmma, "unit": "TFLOP/s",
+                "frac": (achieved / dmma) if (achieved and dmma) else None,
+                "peak_source": "segp_dmma_peak measured in this run: the float64 contraction cannot run on tcgen05 "
+                               "(no f64 kind); " + peaks["_source"] + " holds only bf16",
+                "bf16_peak": bf16_peak, "frac_of_bf16_peak": (achieved / bf16_peak) if achieved else None,
+                "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count,
+                "share_of_step": (tri_ns * 1e-6) / ms if ms > 0 else None,
+                "algorithmic_flop_per_launch": flop_launch, "traffic": None}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config_dict(args, w, b_per_gpu, world, "device-resident"),
+            "onestep_calls_per_sec": value * w.horizon,
+            "algorithmic_tflops": value * w.horizon * workloads.flop_per_step(w.n_s, w.n_u, w.n_train) / 1e12,
+            "e2e": {"value": total_b * e2e_steps / t_e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "api": "safe_exploration_b200.rollout -> segp_multistep_host (pinned host k_ff)",
+                    "bit_identical_to_device_arm": same},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": sampler.summary(t_wall0, t_wall1),
+            "setup_s": t_setup, "bad_status": status_bad, "all_finite": finite}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(w, args.cpu_seconds)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+def _dmma_peak(gp, device):
+    import ctypes
+    out = ctypes.c_double()
+    rc = gp._lib.segp_dmma_peak(device, 2000, ctypes.byref(out))
+    return out.value if rc == 0 else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--batch-per-gpu", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--redundant-factor", action="store_true",
+                    help="factorise on every rank instead of broadcasting the factor")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    from safe_exploration_b200 import distributed as sd
+    rank, world, local_rank = sd.init_from_env()
+    try:
+        run_product(args, rank, world, local_rank)
+    finally:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

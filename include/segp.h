@@ -1,0 +1,186 @@
+/* segp.h -- C ABI of libsegp.so: batched GP one-step posterior + ellipsoid reachability on B200.
+ *
+ * The reference (befelix/safe-exploration) is pure Python and has NO FFI for this path; the entry
+ * points below are what a ctypes binding of that path binds (INTEGRATION.md shows the stub).  Each
+ * one cites the reference interface it replaces; paths are relative to
+ * /root/reference/safe_exploration/.
+ *
+ * Conventions
+ *   - extern "C", opaque handle, int status returns (SEGP_OK == 0); no C++ / torch types.
+ *   - all arithmetic and all buffers are IEEE float64 ("double"), row-major, contiguous.
+ *   - pointers named d_* are DEVICE pointers on the handle's device; h_* are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous on that stream unless stated otherwise; one handle is not re-entrant.
+ *   - the handle owns the model buffers and its workspace; callers own every input/output buffer.
+ *   - per-trajectory failures (non-finite or non-positive variance, a zero box bound) are RETURNED in
+ *     the d_status bitmask, never raised: one diverging candidate must not kill a 65k batch.
+ */
+#ifndef SEGP_H_
+#define SEGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGP_ABI_VERSION 1
+
+/* status codes (Python wrapper maps them: INVALID->ValueError, CUDA->RuntimeError,
+ * NOT_POSDEF->numpy.linalg.LinAlgError, NOT_TRAINED->RuntimeError, UNSUPPORTED->NotImplementedError) */
+#define SEGP_OK 0
+#define SEGP_ERR_INVALID 1
+#define SEGP_ERR_CUDA 2
+#define SEGP_ERR_NOT_POSDEF 3
+#define SEGP_ERR_NOT_TRAINED 4
+#define SEGP_ERR_UNSUPPORTED 5
+
+/* kernel types, per output dimension (ssm_gpy/gp_models_utils_casadi.py:17-70, 218-231) */
+#define SEGP_KERN_RBF 0
+#define SEGP_KERN_MAT52 1
+
+/* per-trajectory status bits written to d_status */
+#define SEGP_STATUS_NONFINITE 1    /* p or Q became inf/NaN                                  */
+#define SEGP_STATUS_BAD_VARIANCE 2 /* predictive variance <= 0 or NaN (sqrt undefined)        */
+#define SEGP_STATUS_ZERO_BOUND 4   /* a box bound was <= 0: the reference asserts here
+                                      (utils_ellipsoid.py:226-228)                            */
+
+/* limits of this build */
+#define SEGP_MAX_NS 16
+#define SEGP_MAX_NU 8
+
+typedef struct segp_model segp_model;
+
+int segp_abi_version(void);
+
+/* Last error message of the calling thread ("" if none). */
+const char* segp_last_error(void);
+
+/* Create an (untrained) model handle on CUDA device `device`.
+ * Replaces SimpleGPModel.__init__ (ssm_gpy/gaussian_process.py:32-70): n_s_out independent GPs over
+ * inputs [state(n_s_in), action(n_u)]; kern_type[n_s_out] in SEGP_KERN_*. */
+int segp_create(segp_model** out, int device, int n_s_out, int n_s_in, int n_u, const int* kern_type);
+int segp_destroy(segp_model* m);
+
+/* Upload training data and hyper-parameters (HOST pointers; copies are taken).
+ * Replaces the data/hyper-parameter half of SimpleGPModel.train (ssm_gpy/gaussian_process.py:189-278):
+ * h_x [n_train x (n_s_in+n_u)], h_y [n_train x n_s_out], h_lengthscale [n_s_out x (n_s_in+n_u)] (ARD),
+ * h_variance [n_s_out] (sigma_f^2), h_noise [n_s_out] = TOTAL diagonal term added to K
+ * (GPy: Gaussian_noise.variance + noise_diag 1e-5 (gaussian_process.py:252-253) + 1e-8 jitter). */
+int segp_set_model(segp_model* m, int n_train, const double* h_x, const double* h_y,
+                   const double* h_lengthscale, const double* h_variance, const double* h_noise);
+
+/* Build K_d = k_d(X,X)+noise_d I, Cholesky-factorise it, beta_d = K_d^-1 y_d, W_d = L_d^-1 packed for
+ * the variance contraction -- all on the device in float64.  Synchronous (returns after completion).
+ * Replaces the posterior half of SimpleGPModel.train / update_model
+ * (ssm_gpy/gaussian_process.py:238-263, 396-413: GPRegression posterior, woodbury_inv/vector, pdinv).
+ * SEGP_ERR_NOT_POSDEF if a pivot is not positive (LAPACK LinAlgError in the reference). */
+int segp_factorize(segp_model* m, void* stream);
+
+/* Multi-GPU setup: the factorised state is n_buffers device buffers.  Rank `root` factorises, every
+ * rank calls segp_alloc_factor_buffers (non-root ranks instead of segp_factorize), the host broadcasts
+ * each buffer (one ncclBroadcast per buffer via torch.distributed), then non-root ranks call
+ * segp_mark_factorized.  No collective is needed afterwards. */
+int segp_alloc_factor_buffers(segp_model* m);
+int segp_num_factor_buffers(segp_model* m);
+int segp_factor_buffer(segp_model* m, int index, void** d_ptr, size_t* bytes);
+int segp_mark_factorized(segp_model* m);
+
+/* log det(K_d) per output dimension from the Cholesky factor (h_out[n_s_out], HOST).
+ * Building block of SimpleGPModel.information_gain (ssm_gpy/gaussian_process.py:621-634). */
+int segp_logdet(segp_model* m, double* h_out);
+
+/* Batched predictive posterior at d_z [n_batch x (n_s_in+n_u)]:
+ *   d_mu [n_batch x n_s_out], d_var [n_batch x n_s_out], d_jac [n_batch x n_s_out x (n_s_in+n_u)] or NULL.
+ * Replaces SimpleGPModel.predict / predictive_gradients (ssm_gpy/gaussian_process.py:546-596), the
+ * single-point SimpleGPModel.__call__ -> gp_pred_function (gp_models_utils_casadi.py:177-197, 234-288)
+ * and StateSpaceModel.predict (state_space_models.py:74-104). */
+int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
+                 void* stream);
+
+/* Shared (not per-trajectory) parameters of the reachability recursion; HOST pointers. */
+typedef struct segp_reach_params {
+    const double* h_l_mu;    /* [n_s]  Lipschitz constants of the mean gradient (gp_reachability.py:38) */
+    const double* h_l_sigma; /* [n_s]  Lipschitz constants of the std deviation (gp_reachability.py:40) */
+    double c_safety;         /* gp_reachability.py:46                                                    */
+    const double* h_a;       /* [n_s x n_s] linear prior, NULL = identity (gp_reachability.py:61-63)     */
+    const double* h_b;       /* [n_s x n_u] linear prior, NULL = zero                                    */
+    const double* h_t_z_gp;  /* [n_s_in x n_s] GP input transform or NULL (gp_reachability_casadi.py:60) */
+} segp_reach_params;
+
+/* n_batch independent H-step ellipsoid reachability recursions.
+ * Replaces multistep_reachability (gp_reachability.py:159-212) and, with horizon == 1,
+ * onestep_reachability (gp_reachability.py:19-156) -- including compute_remainder_overapproximations
+ * (utils.py:108-144), ellipsoid_from_rectangle (utils_ellipsoid.py:197-233) and sum_two_ellipsoids
+ * (utils_ellipsoid.py:63-94) -- for every trajectory at once.
+ *   d_p0      [n_s] (p0_stride 0) or [n_batch x n_s] (p0_stride n_s): initial centres
+ *   d_q0      NULL (start from a point, q_shape=None branch) or [n_s x n_s] (q0_stride 0) /
+ *             [n_batch x n_s x n_s] (q0_stride n_s*n_s): initial shape matrices
+ *   d_k_ff    [n_batch x horizon x n_u]
+ *   d_k_fb    feedback gains for steps 1..horizon-1: [(horizon-1) x n_u x n_s] shared (kfb_stride 0) or
+ *             [n_batch x (horizon-1) x n_u x n_s] (kfb_stride (horizon-1)*n_u*n_s); may be NULL if horizon==1
+ *   d_k_fb_init  gain of step 0 (only read when d_q0 != NULL): [n_u x n_s] (kfb_init_stride 0) or per trajectory
+ *   d_p_all   [n_batch x horizon x n_s]        out
+ *   d_q_all   [n_batch x horizon x n_s x n_s]  out
+ *   d_var_all [n_batch x horizon x n_s] out or NULL (predictive variances at the centres)
+ *   d_status  [n_batch] int32 out or NULL (OR of SEGP_STATUS_* over the steps) */
+int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0, long p0_stride,
+                   const double* d_q0, long q0_stride, const double* d_k_ff, const double* d_k_fb,
+                   long kfb_stride, const double* d_k_fb_init, long kfb_init_stride,
+                   const segp_reach_params* params, double* d_p_all, double* d_q_all, double* d_var_all,
+                   int32_t* d_status, void* stream);
+
+/* Same call with HOST buffers: copies inputs to the device, runs, copies results back, synchronises.
+ * This is the entry point a reference-side binding uses when it holds NumPy arrays. */
+int segp_multistep_host(segp_model* m, long n_batch, int horizon, const double* h_p0, long p0_stride,
+                        const double* h_q0, long q0_stride, const double* h_k_ff, const double* h_k_fb,
+                        long kfb_stride, const double* h_k_fb_init, long kfb_init_stride,
+                        const segp_reach_params* params, double* h_p_all, double* h_q_all, double* h_var_all,
+                        int32_t* h_status);
+
+/* One ellipsoid step for a foreign state-space model: the caller supplies the GP outputs.
+ * Replaces the body of onestep_reachability after the ssm(...) call (gp_reachability.py:75-88, 102-156).
+ *   d_mu, d_var [n_batch x n_s]; d_jac [n_batch x n_s x (n_s_in+n_u)] (ignored when d_q == NULL)
+ *   d_p [n_batch x n_s]; d_q NULL or [n_batch x n_s x n_s]; d_k_ff [n_batch x n_u];
+ *   d_k_fb [n_u x n_s] (kfb_stride 0) or [n_batch x n_u x n_s] (kfb_stride n_u*n_s), required when d_q != NULL */
+int segp_ellipsoid_step(int device, long n_batch, int n_s, int n_s_in, int n_u, const double* d_mu,
+                        const double* d_var, const double* d_jac, const double* d_p, const double* d_q,
+                        const double* d_k_ff, const double* d_k_fb, long kfb_stride,
+                        const segp_reach_params* params, double* d_p_out, double* d_q_out, int32_t* d_status,
+                        void* stream);
+
+/* Batched leaves of the ellipsoid calculus (each replaces the cited reference function, per item). */
+/* utils.py:108-144 -- d_q [n_batch x n_s x n_s], d_k_fb [n_u x n_s] (stride 0) or per item; out [n_batch x n_s] */
+int segp_remainder_overapproximations(int device, long n_batch, int n_s, int n_u, const double* d_q,
+                                      const double* d_k_fb, long kfb_stride, const double* h_l_mu,
+                                      const double* h_l_sigma, double* d_u_mu, double* d_u_sigma, void* stream);
+/* utils_ellipsoid.py:63-94 (c=None) -- p [n_batch x n], q [n_batch x n x n] */
+int segp_sum_two_ellipsoids(int device, long n_batch, int n, const double* d_p1, const double* d_q1,
+                            const double* d_p2, const double* d_q2, double* d_p, double* d_q, void* stream);
+/* utils_ellipsoid.py:197-233 -- d_ub [n_batch x n] -> d_q [n_batch x n x n]; status bit ZERO_BOUND if any ub <= 0 */
+int segp_ellipsoid_from_rectangle(int device, long n_batch, int n, const double* d_ub, double* d_q,
+                                  int32_t* d_status, void* stream);
+/* gp_reachability.py:215-250 -- p [n_items x n_s], q [n_items x n_s x n_s], h_mat [m x n_s], h_vec [m] (HOST);
+ * out d_dist [n_items x m] */
+int segp_safety_distance(int device, long n_items, int n_s, int m, const double* d_p, const double* d_q,
+                         const double* h_h_mat, const double* h_h_vec, double c_safety, double* d_dist,
+                         void* stream);
+
+/* Diagnostic: sustained FP64 tensor-pipe (DMMA m8n8k4) rate of `device` in TFLOP/s, measured by a register-only
+ * kernel (148 x 4 CTAs x 8 warps, `iters` x 64 independent DMMAs per warp).  bench.py reports tri_sumsq against it,
+ * next to the bf16 figure MEASURED_PEAKS.json carries -- tcgen05 has no f64 kind, so this is the pipe the float64
+ * contraction actually runs on. */
+int segp_dmma_peak(int device, int iters, double* tflops);
+
+/* Tuning knobs / introspection ("chunk": trajectories per workspace chunk, "panel_group", "ksplit",
+ * "time_tri": 1 = bracket every tri_sumsq launch with a CUDA-event pair on its stream (resets the counters);
+ * read-only: "launches" = kernels launched by this handle so far, "n_train_padded", "workspace_bytes",
+ * "tri_launches" / "tri_ns" = number and total device nanoseconds of the timed tri_sumsq launches). */
+int segp_set_option(segp_model* m, const char* name, long value);
+int segp_get_option(segp_model* m, const char* name, long* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGP_H_ */

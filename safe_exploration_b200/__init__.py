@@ -1,0 +1,16 @@
+"""safe_exploration_b200: the batched GP-posterior + ellipsoid-reachability hot path of
+befelix/safe-exploration, as hand-written CUDA for B200 (sm_100a) behind the reference's own plugin API.
+
+    from safe_exploration_b200 import BatchedGPSSM
+    from safe_exploration_b200.gp_reachability import onestep_reachability, multistep_reachability
+
+Importing the package does not need a GPU; constructing a model or calling any reachability function
+does, and raises otherwise (there is no CPU fallback; the CPU oracle under oracle/ is test-only).
+"""
+from . import _lib  # noqa: F401
+from .ssm import BatchedGPSSM  # noqa: F401
+from . import gp_reachability, utils, utils_ellipsoid  # noqa: F401
+from .gp_reachability import (lin_ellipsoid_safety_distance, multistep_reachability,  # noqa: F401
+                              onestep_reachability, rollout)
+
+__version__ = "0.1.0"

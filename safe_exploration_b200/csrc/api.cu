@@ -1,0 +1,898 @@
+// C ABI of libsegp.so (include/segp.h): handle management, chunked rollout driver, host-buffer entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "segp_internal.cuh"
+
+namespace segp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return SEGP_OK;
+    SEGP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+    return SEGP_OK;
+}
+template <typename T>
+static void dev_free(T*& p) {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+}
+
+}  // namespace segp
+
+using namespace segp;
+
+struct segp_model {
+    int device = 0;
+    int n_s = 0, n_in = 0, n_u = 0, dim = 0;
+    int kern[SEGP_MAX_NS] = {0};
+    // model data (host copies kept for re-factorisation / introspection)
+    int n_train = 0, n_pad = 0, nblk = 0;
+    long ntri = 0;
+    std::vector<double> h_x, h_y, h_ls, h_var, h_noise;
+    bool has_data = false, factorized = false;
+    // device model
+    double* xs = nullptr;      // [n_s][n_pad][dim] inputs scaled by 1/lengthscale
+    double* yp = nullptr;      // [n_s][n_pad] targets, zero padded
+    double* invls = nullptr;   // [n_s][dim]
+    double* var = nullptr;     // [n_s]
+    double* beta = nullptr;    // [n_s][n_pad]
+    double* wt = nullptr;      // [n_s][ntri][128*128]
+    double* logdet = nullptr;  // [n_s]
+    // workspace
+    long b_cap = 0;
+    int nsplit = 1, blocks_per_split = 1;
+    double* ks = nullptr;
+    double* mu_part = nullptr;
+    double* jac_part = nullptr;
+    double* qpart = nullptr;
+    StepParams* d_sp = nullptr;
+    size_t workspace_bytes = 0;
+    // host-entry staging (grown on demand)
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    // options
+    long opt_chunk = 8192;
+    long opt_panel_group = 16;
+    long opt_ksplit = 0;   // 0 = automatic
+    long launches = 0;
+    // optional per-launch timing of tri_sumsq (bench.py roofline): event pairs recorded on the launching stream
+    bool time_tri = false;
+    std::vector<cudaEvent_t> tri_events;
+    size_t tri_events_used = 0;
+};
+
+namespace segp {
+
+static void free_model_buffers(segp_model* m) {
+    dev_free(m->xs);
+    dev_free(m->yp);
+    dev_free(m->invls);
+    dev_free(m->var);
+    dev_free(m->beta);
+    dev_free(m->wt);
+    dev_free(m->logdet);
+    m->factorized = false;
+}
+
+static void free_workspace(segp_model* m) {
+    dev_free(m->ks);
+    dev_free(m->mu_part);
+    dev_free(m->jac_part);
+    dev_free(m->qpart);
+    m->b_cap = 0;
+    m->workspace_bytes = 0;
+}
+
+static int ensure_workspace(segp_model* m, long n_batch) {
+    long want = std::min<long>(m->opt_chunk, n_batch);
+    want = (want + TILE - 1) / TILE * TILE;
+    // split of the N-length reductions of kstar_mean_jac over blockIdx.z so small batches still fill 148 SMs
+    const long col_blocks = want / TILE;
+    int nsplit;
+    if (m->opt_ksplit > 0) {
+        nsplit = (int)std::min<long>(m->opt_ksplit, m->nblk);
+    } else {
+        const long target = 4 * 148;
+        nsplit = (int)std::max<long>(1, std::min<long>(m->nblk, (target + col_blocks * m->n_s - 1) / (col_blocks * m->n_s)));
+    }
+    const int bps = (m->nblk + nsplit - 1) / nsplit;
+    nsplit = (m->nblk + bps - 1) / bps;
+    if (want <= m->b_cap && nsplit == m->nsplit && bps == m->blocks_per_split) return SEGP_OK;
+    if (want <= m->b_cap) {
+        // same capacity, only the split changed: partial buffers are sized for nblk splits, nothing to do
+        m->nsplit = nsplit;
+        m->blocks_per_split = bps;
+        return SEGP_OK;
+    }
+    free_workspace(m);
+    const size_t n_ks = (size_t)m->n_s * m->n_pad * want;
+    const size_t n_mu = (size_t)m->nblk * m->n_s * want;
+    const size_t n_jac = n_mu * m->dim;
+    const size_t n_q = (size_t)m->n_s * m->nblk * want;
+    SEGP_CHECK(dev_alloc(&m->ks, n_ks));
+    SEGP_CHECK(dev_alloc(&m->mu_part, n_mu));
+    SEGP_CHECK(dev_alloc(&m->jac_part, n_jac));
+    SEGP_CHECK(dev_alloc(&m->qpart, n_q));
+    SEGP_CUDA_CHECK(cudaMemset(m->ks, 0, n_ks * sizeof(double)));
+    m->workspace_bytes = (n_ks + n_mu + n_jac + n_q) * sizeof(double);
+    m->b_cap = want;
+    m->nsplit = nsplit;
+    m->blocks_per_split = bps;
+    return SEGP_OK;
+}
+
+static int fill_step_params(StepParams* sp, const segp_reach_params* prm, int n_s, int n_in, int n_u) {
+    memset(sp, 0, sizeof(*sp));
+    if (prm == nullptr || prm->h_l_mu == nullptr || prm->h_l_sigma == nullptr) {
+        set_error("reach params: l_mu and l_sigma are required");
+        return SEGP_ERR_INVALID;
+    }
+    for (int i = 0; i < n_s; ++i) {
+        sp->l_mu[i] = prm->h_l_mu[i];
+        sp->l_sigma[i] = prm->h_l_sigma[i];
+    }
+    sp->c_safety = prm->c_safety;
+    for (int i = 0; i < n_s; ++i)
+        for (int j = 0; j < n_s; ++j) sp->a[i * n_s + j] = prm->h_a ? prm->h_a[i * n_s + j] : (i == j ? 1.0 : 0.0);
+    for (int i = 0; i < n_s; ++i)
+        for (int j = 0; j < n_u; ++j) sp->b[i * n_u + j] = prm->h_b ? prm->h_b[i * n_u + j] : 0.0;
+    sp->has_t = prm->h_t_z_gp != nullptr;
+    if (sp->has_t) {
+        for (int i = 0; i < n_in * n_s; ++i) sp->t[i] = prm->h_t_z_gp[i];
+    } else if (n_in != n_s) {
+        set_error("GP input state dimension %d differs from the state dimension %d: t_z_gp is required", n_in, n_s);
+        return SEGP_ERR_INVALID;
+    }
+    return SEGP_OK;
+}
+
+static int check_ready(const segp_model* m) {
+    if (m == nullptr) {
+        set_error("null model handle");
+        return SEGP_ERR_INVALID;
+    }
+    if (!m->factorized) {
+        set_error("model is not factorised (call segp_set_model + segp_factorize first)");
+        return SEGP_ERR_NOT_TRAINED;
+    }
+    return SEGP_OK;
+}
+
+static KstarArgs base_kstar_args(const segp_model* m) {
+    KstarArgs k{};
+    k.xs = m->xs;
+    k.invls = m->invls;
+    k.var = m->var;
+    k.beta = m->beta;
+    for (int d = 0; d < m->n_s; ++d) k.kern[d] = m->kern[d];
+    k.n_train = m->n_train;
+    k.n_pad = m->n_pad;
+    k.dim = m->dim;
+    k.n_in = m->n_in;
+    k.n_u = m->n_u;
+    k.n_s_state = m->n_s;
+    k.b_cap = m->b_cap;
+    k.groups_per_split = m->blocks_per_split * (TILE / 4);
+    k.ks = m->ks;
+    k.mu_part = m->mu_part;
+    k.jac_part = m->jac_part;
+    return k;
+}
+
+// tri_sumsq launch, optionally bracketed by a CUDA-event pair on the launching stream
+static int run_tri(segp_model* m, long nb, cudaStream_t st) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (m->time_tri) {
+        while (m->tri_events.size() < m->tri_events_used + 2) {
+            cudaEvent_t e;
+            SEGP_CUDA_CHECK(cudaEventCreate(&e));
+            m->tri_events.push_back(e);
+        }
+        e0 = m->tri_events[m->tri_events_used];
+        e1 = m->tri_events[m->tri_events_used + 1];
+        m->tri_events_used += 2;
+        SEGP_CUDA_CHECK(cudaEventRecord(e0, st));
+    }
+    TriArgs t{};
+    t.wt = m->wt;
+    t.ks = m->ks;
+    t.qpart = m->qpart;
+    t.nblk = m->nblk;
+    t.npanels = (int)((nb + TILE - 1) / TILE);
+    t.group = (int)std::max<long>(1, std::min<long>(m->opt_panel_group, t.npanels));
+    t.b_cap = m->b_cap;
+    t.ntri = m->ntri;
+    SEGP_CHECK(launch_tri_sumsq(t, m->n_s, st));
+    if (e1 != nullptr) SEGP_CUDA_CHECK(cudaEventRecord(e1, st));
+    return SEGP_OK;
+}
+
+}  // namespace segp
+
+// ============================================================================================== C ABI
+extern "C" {
+
+int segp_abi_version(void) { return SEGP_ABI_VERSION; }
+
+const char* segp_last_error(void) { return g_err; }
+
+int segp_create(segp_model** out, int device, int n_s_out, int n_s_in, int n_u, const int* kern_type) {
+    if (out == nullptr || kern_type == nullptr) {
+        set_error("segp_create: null argument");
+        return SEGP_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (n_s_out < 1 || n_s_out > SEGP_MAX_NS || n_s_in < 1 || n_s_in > SEGP_MAX_NS || n_u < 0 || n_u > SEGP_MAX_NU) {
+        set_error("segp_create: dimensions out of range (n_s_out=%d n_s_in=%d n_u=%d; limits %d/%d)", n_s_out, n_s_in,
+                  n_u, SEGP_MAX_NS, SEGP_MAX_NU);
+        return SEGP_ERR_INVALID;
+    }
+    for (int d = 0; d < n_s_out; ++d)
+        if (kern_type[d] != SEGP_KERN_RBF && kern_type[d] != SEGP_KERN_MAT52) {
+            set_error("segp_create: unsupported kernel type %d for output %d", kern_type[d], d);
+            return SEGP_ERR_UNSUPPORTED;
+        }
+    int ndev = 0;
+    SEGP_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_error("segp_create: no CUDA device %d (%d visible); this library has no CPU path", device, ndev);
+        return SEGP_ERR_CUDA;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("segp_create: cudaSetDevice(%d) failed", device);
+        return SEGP_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    SEGP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) {
+        set_error("segp_create: device %d is sm_%d%d; this build targets sm_100a", device, prop.major, prop.minor);
+        return SEGP_ERR_UNSUPPORTED;
+    }
+    SEGP_CHECK(tri_sumsq_init());
+    segp_model* m = new (std::nothrow) segp_model();
+    if (m == nullptr) {
+        set_error("out of host memory");
+        return SEGP_ERR_INVALID;
+    }
+    m->device = device;
+    m->n_s = n_s_out;
+    m->n_in = n_s_in;
+    m->n_u = n_u;
+    m->dim = n_s_in + n_u;
+    for (int d = 0; d < n_s_out; ++d) m->kern[d] = kern_type[d];
+    if (dev_alloc(&m->d_sp, 1) != SEGP_OK) {
+        delete m;
+        return SEGP_ERR_CUDA;
+    }
+    *out = m;
+    return SEGP_OK;
+}
+
+int segp_destroy(segp_model* m) {
+    if (m == nullptr) return SEGP_OK;
+    DeviceGuard guard(m->device);
+    cudaDeviceSynchronize();
+    free_model_buffers(m);
+    free_workspace(m);
+    dev_free(m->d_sp);
+    for (cudaEvent_t e : m->tri_events) cudaEventDestroy(e);
+    if (m->stage != nullptr) cudaFree(m->stage);
+    delete m;
+    return SEGP_OK;
+}
+
+int segp_set_model(segp_model* m, int n_train, const double* h_x, const double* h_y, const double* h_lengthscale,
+                   const double* h_variance, const double* h_noise) {
+    if (m == nullptr || h_x == nullptr || h_y == nullptr || h_lengthscale == nullptr || h_variance == nullptr ||
+        h_noise == nullptr || n_train < 1) {
+        set_error("segp_set_model: null argument or n_train < 1");
+        return SEGP_ERR_INVALID;
+    }
+    for (int d = 0; d < m->n_s; ++d) {
+        if (!(h_variance[d] > 0.0) || !(h_noise[d] >= 0.0)) {
+            set_error("segp_set_model: variance must be > 0 and noise >= 0 (output %d)", d);
+            return SEGP_ERR_INVALID;
+        }
+        for (int j = 0; j < m->dim; ++j)
+            if (!(h_lengthscale[d * m->dim + j] > 0.0)) {
+                set_error("segp_set_model: lengthscale[%d][%d] must be > 0", d, j);
+                return SEGP_ERR_INVALID;
+            }
+    }
+    DeviceGuard guard(m->device);
+    cudaDeviceSynchronize();
+    free_model_buffers(m);
+    free_workspace(m);
+    const int dim = m->dim, n_s = m->n_s;
+    m->n_train = n_train;
+    m->n_pad = (n_train + TILE - 1) / TILE * TILE;
+    m->nblk = m->n_pad / TILE;
+    m->ntri = (long)m->nblk * (m->nblk + 1) / 2;
+    m->h_x.assign(h_x, h_x + (size_t)n_train * dim);
+    m->h_y.assign(h_y, h_y + (size_t)n_train * n_s);
+    m->h_ls.assign(h_lengthscale, h_lengthscale + (size_t)n_s * dim);
+    m->h_var.assign(h_variance, h_variance + n_s);
+    m->h_noise.assign(h_noise, h_noise + n_s);
+
+    std::vector<double> xs((size_t)n_s * m->n_pad * dim, 0.0), yp((size_t)n_s * m->n_pad, 0.0), invls((size_t)n_s * dim);
+    for (int d = 0; d < n_s; ++d) {
+        for (int j = 0; j < dim; ++j) invls[d * dim + j] = 1.0 / h_lengthscale[d * dim + j];
+        for (int i = 0; i < n_train; ++i) {
+            for (int j = 0; j < dim; ++j)
+                xs[((size_t)d * m->n_pad + i) * dim + j] = h_x[(size_t)i * dim + j] * invls[d * dim + j];
+            yp[(size_t)d * m->n_pad + i] = h_y[(size_t)i * n_s + d];
+        }
+    }
+    SEGP_CHECK(dev_alloc(&m->xs, xs.size()));
+    SEGP_CHECK(dev_alloc(&m->yp, yp.size()));
+    SEGP_CHECK(dev_alloc(&m->invls, invls.size()));
+    SEGP_CHECK(dev_alloc(&m->var, (size_t)n_s));
+    SEGP_CUDA_CHECK(cudaMemcpy(m->xs, xs.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SEGP_CUDA_CHECK(cudaMemcpy(m->yp, yp.data(), yp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SEGP_CUDA_CHECK(cudaMemcpy(m->invls, invls.data(), invls.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SEGP_CUDA_CHECK(cudaMemcpy(m->var, h_variance, n_s * sizeof(double), cudaMemcpyHostToDevice));
+    m->has_data = true;
+    return SEGP_OK;
+}
+
+int segp_alloc_factor_buffers(segp_model* m) {
+    if (m == nullptr || !m->has_data) {
+        set_error("segp_alloc_factor_buffers: segp_set_model has not been called");
+        return SEGP_ERR_NOT_TRAINED;
+    }
+    DeviceGuard guard(m->device);
+    if (m->wt == nullptr) SEGP_CHECK(dev_alloc(&m->wt, (size_t)m->n_s * m->ntri * TILE * TILE));
+    if (m->beta == nullptr) SEGP_CHECK(dev_alloc(&m->beta, (size_t)m->n_s * m->n_pad));
+    if (m->logdet == nullptr) SEGP_CHECK(dev_alloc(&m->logdet, (size_t)m->n_s));
+    return SEGP_OK;
+}
+
+int segp_num_factor_buffers(segp_model* m) {
+    (void)m;
+    return 3;
+}
+
+int segp_factor_buffer(segp_model* m, int index, void** d_ptr, size_t* bytes) {
+    if (m == nullptr || d_ptr == nullptr || bytes == nullptr || m->wt == nullptr) {
+        set_error("segp_factor_buffer: buffers are not allocated");
+        return SEGP_ERR_NOT_TRAINED;
+    }
+    switch (index) {
+        case 0:
+            *d_ptr = m->wt;
+            *bytes = (size_t)m->n_s * m->ntri * TILE * TILE * sizeof(double);
+            return SEGP_OK;
+        case 1:
+            *d_ptr = m->beta;
+            *bytes = (size_t)m->n_s * m->n_pad * sizeof(double);
+            return SEGP_OK;
+        case 2:
+            *d_ptr = m->logdet;
+            *bytes = (size_t)m->n_s * sizeof(double);
+            return SEGP_OK;
+        default:
+            set_error("segp_factor_buffer: index %d out of range", index);
+            return SEGP_ERR_INVALID;
+    }
+}
+
+int segp_mark_factorized(segp_model* m) {
+    if (m == nullptr || m->wt == nullptr) {
+        set_error("segp_mark_factorized: buffers are not allocated");
+        return SEGP_ERR_NOT_TRAINED;
+    }
+    m->factorized = true;
+    return SEGP_OK;
+}
+
+int segp_factorize(segp_model* m, void* stream) {
+    if (m == nullptr || !m->has_data) {
+        set_error("segp_factorize: segp_set_model has not been called");
+        return SEGP_ERR_NOT_TRAINED;
+    }
+    DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    m->factorized = false;
+    SEGP_CHECK(segp_alloc_factor_buffers(m));
+    const size_t nn = (size_t)m->n_pad * m->n_pad;
+    const int nb64 = m->n_pad / NBLK;
+    double *kbuf = nullptr, *wbuf = nullptr, *tmp = nullptr, *diag_inv = nullptr, *u_tmp = nullptr;
+    int* d_fail = nullptr;
+    int rc = SEGP_OK;
+    std::vector<int> fails(m->n_s, 0);
+    do {
+        if ((rc = dev_alloc(&kbuf, nn)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&wbuf, nn)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&tmp, nn)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_fail, (size_t)m->n_s)) != SEGP_OK) break;
+        SetupDims sd{m->n_train, m->n_pad, m->dim};
+        for (int d = 0; d < m->n_s && rc == SEGP_OK; ++d) {
+            const double* xs_d = m->xs + (size_t)d * m->n_pad * m->dim;
+            if ((rc = launch_kmat(kbuf, xs_d, m->kern[d], m->h_var[d], m->h_noise[d], sd, st)) != SEGP_OK) break;
+            ++m->launches;
+            if ((rc = potrf_lower(kbuf, m->n_pad, diag_inv, d_fail + d, st, &m->launches)) != SEGP_OK) break;
+            if ((rc = logdet_from_chol(kbuf, m->n_train, m->n_pad, m->logdet + d, st)) != SEGP_OK) break;
+            ++m->launches;
+            if (cudaMemsetAsync(wbuf, 0, nn * sizeof(double), st) != cudaSuccess) {
+                set_error("cudaMemsetAsync failed");
+                rc = SEGP_ERR_CUDA;
+                break;
+            }
+            if ((rc = trtri_lower(kbuf, wbuf, m->n_pad, diag_inv, tmp, st, &m->launches)) != SEGP_OK) break;
+            if ((rc = solve_beta(wbuf, m->yp + (size_t)d * m->n_pad, u_tmp, m->beta + (size_t)d * m->n_pad, m->n_pad,
+                                 st)) != SEGP_OK)
+                break;
+            m->launches += 3;
+            if ((rc = pack_w(wbuf, m->wt + (size_t)d * m->ntri * TILE * TILE, m->n_pad, st)) != SEGP_OK) break;
+            ++m->launches;
+        }
+        if (rc != SEGP_OK) break;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(fails.data(), d_fail, m->n_s * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("segp_factorize: %s", cudaGetErrorString(e));
+            rc = SEGP_ERR_CUDA;
+            break;
+        }
+        for (int d = 0; d < m->n_s; ++d)
+            if (fails[d] != 0) {
+                set_error("segp_factorize: K + noise I is not positive definite for output %d (pivot %d)", d,
+                          fails[d] - 1);
+                rc = SEGP_ERR_NOT_POSDEF;
+                break;
+            }
+    } while (0);
+    cudaStreamSynchronize(st);
+    dev_free(kbuf);
+    dev_free(wbuf);
+    dev_free(tmp);
+    dev_free(diag_inv);
+    dev_free(u_tmp);
+    dev_free(d_fail);
+    if (rc == SEGP_OK) m->factorized = true;
+    return rc;
+}
+
+int segp_logdet(segp_model* m, double* h_out) {
+    SEGP_CHECK(check_ready(m));
+    DeviceGuard guard(m->device);
+    SEGP_CUDA_CHECK(cudaMemcpy(h_out, m->logdet, m->n_s * sizeof(double), cudaMemcpyDeviceToHost));
+    return SEGP_OK;
+}
+
+int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
+                 void* stream) {
+    SEGP_CHECK(check_ready(m));
+    if (n_batch < 0 || (n_batch > 0 && (d_z == nullptr || d_mu == nullptr || d_var == nullptr))) {
+        set_error("segp_predict: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    if (n_batch == 0) return SEGP_OK;
+    DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SEGP_CHECK(ensure_workspace(m, n_batch));
+    for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
+        const long nb = std::min<long>(m->b_cap, n_batch - c0);
+        KstarArgs k = base_kstar_args(m);
+        k.z = d_z + c0 * m->dim;
+        k.n_batch = nb;
+        SEGP_CHECK(launch_kstar(k, m->n_s, m->nsplit, st));
+        SEGP_CHECK(run_tri(m, nb, st));
+        FinalizeArgs f{};
+        f.mu_part = m->mu_part;
+        f.jac_part = m->jac_part;
+        f.qpart = m->qpart;
+        f.gp_var = m->var;
+        f.invls = m->invls;
+        f.nsplit = m->nsplit;
+        f.nblk = m->nblk;
+        f.n_s = m->n_s;
+        f.dim = m->dim;
+        f.b_cap = m->b_cap;
+        f.n_batch = nb;
+        f.mu = d_mu + c0 * m->n_s;
+        f.var = d_var + c0 * m->n_s;
+        f.jac = d_jac ? d_jac + c0 * m->n_s * m->dim : nullptr;
+        SEGP_CHECK(launch_finalize_predict(f, st));
+        m->launches += 3;
+    }
+    return SEGP_OK;
+}
+
+int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0, long p0_stride, const double* d_q0,
+                   long q0_stride, const double* d_k_ff, const double* d_k_fb, long kfb_stride,
+                   const double* d_k_fb_init, long kfb_init_stride, const segp_reach_params* params, double* d_p_all,
+                   double* d_q_all, double* d_var_all, int32_t* d_status, void* stream) {
+    SEGP_CHECK(check_ready(m));
+    if (n_batch < 0 || horizon < 1) {
+        set_error("segp_multistep: n_batch >= 0 and horizon >= 1 required");
+        return SEGP_ERR_INVALID;
+    }
+    if (n_batch == 0) return SEGP_OK;
+    if (d_p0 == nullptr || d_k_ff == nullptr || d_p_all == nullptr || d_q_all == nullptr) {
+        set_error("segp_multistep: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    if (horizon > 1 && d_k_fb == nullptr) {
+        set_error("segp_multistep: k_fb is required for horizon > 1");
+        return SEGP_ERR_INVALID;
+    }
+    if (d_q0 != nullptr && d_k_fb_init == nullptr) {
+        set_error("segp_multistep: k_fb_init is required when an initial shape matrix q_0 is given");
+        return SEGP_ERR_INVALID;
+    }
+    StepParams sp;
+    SEGP_CHECK(fill_step_params(&sp, params, m->n_s, m->n_in, m->n_u));
+    DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SEGP_CHECK(ensure_workspace(m, n_batch));
+    SEGP_CUDA_CHECK(cudaMemcpyAsync(m->d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, st));
+    if (d_status != nullptr) SEGP_CUDA_CHECK(cudaMemsetAsync(d_status, 0, n_batch * sizeof(int32_t), st));
+
+    const int n_s = m->n_s, n_u = m->n_u;
+    const long hs = (long)horizon * n_s, hss = (long)horizon * n_s * n_s;
+    for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
+        const long nb = std::min<long>(m->b_cap, n_batch - c0);
+        for (int t = 0; t < horizon; ++t) {
+            const double* p_in = (t == 0) ? d_p0 + c0 * p0_stride : d_p_all + c0 * hs + (long)(t - 1) * n_s;
+            const long p_in_stride = (t == 0) ? p0_stride : hs;
+            const double* kff = d_k_ff + (c0 * horizon + t) * n_u;
+            KstarArgs k = base_kstar_args(m);
+            k.z = nullptr;
+            k.p = p_in;
+            k.p_stride = p_in_stride;
+            k.kff = kff;
+            k.kff_stride = (long)horizon * n_u;
+            k.sp = m->d_sp;
+            k.n_batch = nb;
+            SEGP_CHECK(launch_kstar(k, n_s, m->nsplit, st));
+            SEGP_CHECK(run_tri(m, nb, st));
+
+            StepArgs s{};
+            s.mu_part = m->mu_part;
+            s.jac_part = m->jac_part;
+            s.qpart = m->qpart;
+            s.gp_var = m->var;
+            s.invls = m->invls;
+            s.nsplit = m->nsplit;
+            s.nblk = m->nblk;
+            s.b_cap = m->b_cap;
+            s.p = p_in;
+            s.p_stride = p_in_stride;
+            if (t == 0) {
+                s.q = d_q0 ? d_q0 + c0 * q0_stride : nullptr;
+                s.q_stride = q0_stride;
+                s.kfb = d_k_fb_init ? d_k_fb_init + c0 * kfb_init_stride : nullptr;
+                s.kfb_stride = kfb_init_stride;
+            } else {
+                s.q = d_q_all + c0 * hss + (long)(t - 1) * n_s * n_s;
+                s.q_stride = hss;
+                s.kfb = d_k_fb + c0 * kfb_stride + (long)(t - 1) * n_u * n_s;
+                s.kfb_stride = kfb_stride;
+            }
+            s.kff = kff;
+            s.kff_stride = (long)horizon * n_u;
+            s.sp = m->d_sp;
+            s.p_out = d_p_all + c0 * hs + (long)t * n_s;
+            s.p_out_stride = hs;
+            s.q_out = d_q_all + c0 * hss + (long)t * n_s * n_s;
+            s.q_out_stride = hss;
+            s.var_out = d_var_all ? d_var_all + c0 * hs + (long)t * n_s : nullptr;
+            s.var_out_stride = hs;
+            s.status = d_status ? d_status + c0 : nullptr;
+            s.n_batch = nb;
+            s.n_s = n_s;
+            s.n_in = m->n_in;
+            s.n_u = n_u;
+            SEGP_CHECK(launch_ellipsoid_step(s, st));
+            m->launches += 3;
+        }
+    }
+    return SEGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- host entry
+static int ensure_stage(segp_model* m, size_t bytes) {
+    if (bytes <= m->stage_bytes) return SEGP_OK;
+    if (m->stage != nullptr) cudaFree(m->stage);
+    m->stage = nullptr;
+    m->stage_bytes = 0;
+    SEGP_CUDA_CHECK(cudaMalloc(&m->stage, bytes));
+    m->stage_bytes = bytes;
+    return SEGP_OK;
+}
+
+int segp_multistep_host(segp_model* m, long n_batch, int horizon, const double* h_p0, long p0_stride,
+                        const double* h_q0, long q0_stride, const double* h_k_ff, const double* h_k_fb,
+                        long kfb_stride, const double* h_k_fb_init, long kfb_init_stride,
+                        const segp_reach_params* params, double* h_p_all, double* h_q_all, double* h_var_all,
+                        int32_t* h_status) {
+    SEGP_CHECK(check_ready(m));
+    if (n_batch < 0 || horizon < 1) {
+        set_error("segp_multistep_host: n_batch >= 0 and horizon >= 1 required");
+        return SEGP_ERR_INVALID;
+    }
+    if (n_batch == 0) return SEGP_OK;
+    if (h_p0 == nullptr || h_k_ff == nullptr || h_p_all == nullptr || h_q_all == nullptr) {
+        set_error("segp_multistep_host: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(m->device);
+    const int n_s = m->n_s, n_u = m->n_u;
+    auto al = [](size_t v) { return (v + 31) / 32 * 32; };   // in doubles, keeps 256-byte alignment
+    const size_t n_p0 = p0_stride ? (size_t)n_batch * n_s : n_s;
+    const size_t n_q0 = h_q0 ? (q0_stride ? (size_t)n_batch * n_s * n_s : (size_t)n_s * n_s) : 0;
+    const size_t n_kff = (size_t)n_batch * horizon * n_u;
+    const size_t n_kfb1 = (size_t)std::max(horizon - 1, 0) * n_u * n_s;
+    const size_t n_kfb = h_k_fb ? (kfb_stride ? (size_t)n_batch * n_kfb1 : n_kfb1) : 0;
+    const size_t n_kfbi = h_k_fb_init ? (kfb_init_stride ? (size_t)n_batch * n_u * n_s : (size_t)n_u * n_s) : 0;
+    const size_t n_pall = (size_t)n_batch * horizon * n_s;
+    const size_t n_qall = n_pall * n_s;
+    const size_t n_stat = (size_t)(n_batch + 1) / 2;   // int32 pairs in double units
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        const size_t o = off;
+        off += al(std::max<size_t>(n, 1));
+        return o;
+    };
+    const size_t o_p0 = take(n_p0), o_q0 = take(n_q0), o_kff = take(n_kff), o_kfb = take(n_kfb), o_kfbi = take(n_kfbi),
+                 o_pall = take(n_pall), o_qall = take(n_qall), o_var = take(n_pall), o_stat = take(n_stat);
+    SEGP_CHECK(ensure_stage(m, off * sizeof(double)));
+    double* base = static_cast<double*>(m->stage);
+    cudaStream_t st = nullptr;
+    auto up = [&](size_t o, const double* src, size_t n) -> cudaError_t {
+        if (n == 0 || src == nullptr) return cudaSuccess;
+        return cudaMemcpyAsync(base + o, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    };
+    SEGP_CUDA_CHECK(up(o_p0, h_p0, n_p0));
+    SEGP_CUDA_CHECK(up(o_q0, h_q0, n_q0));
+    SEGP_CUDA_CHECK(up(o_kff, h_k_ff, n_kff));
+    SEGP_CUDA_CHECK(up(o_kfb, h_k_fb, n_kfb));
+    SEGP_CUDA_CHECK(up(o_kfbi, h_k_fb_init, n_kfbi));
+    int32_t* d_stat = reinterpret_cast<int32_t*>(base + o_stat);
+    SEGP_CHECK(segp_multistep(m, n_batch, horizon, base + o_p0, p0_stride, h_q0 ? base + o_q0 : nullptr, q0_stride,
+                              base + o_kff, h_k_fb ? base + o_kfb : nullptr, kfb_stride,
+                              h_k_fb_init ? base + o_kfbi : nullptr, kfb_init_stride, params, base + o_pall,
+                              base + o_qall, h_var_all ? base + o_var : nullptr, h_status ? d_stat : nullptr, st));
+    SEGP_CUDA_CHECK(cudaMemcpyAsync(h_p_all, base + o_pall, n_pall * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SEGP_CUDA_CHECK(cudaMemcpyAsync(h_q_all, base + o_qall, n_qall * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_var_all != nullptr)
+        SEGP_CUDA_CHECK(cudaMemcpyAsync(h_var_all, base + o_var, n_pall * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_status != nullptr)
+        SEGP_CUDA_CHECK(cudaMemcpyAsync(h_status, d_stat, n_batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SEGP_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SEGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- handle-free leaves
+namespace {
+struct TempParams {
+    StepParams* d = nullptr;
+    cudaStream_t st;
+    explicit TempParams(cudaStream_t s) : st(s) {}
+    int upload(const StepParams& sp) {
+        SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d), sizeof(StepParams), st));
+        SEGP_CUDA_CHECK(cudaMemcpyAsync(d, &sp, sizeof(sp), cudaMemcpyHostToDevice, st));
+        return SEGP_OK;
+    }
+    ~TempParams() {
+        if (d != nullptr) cudaFreeAsync(d, st);
+    }
+};
+int check_dims(int n_s, int n_in, int n_u) {
+    if (n_s < 1 || n_s > SEGP_MAX_NS || n_in < 1 || n_in > SEGP_MAX_NS || n_u < 0 || n_u > SEGP_MAX_NU) {
+        set_error("dimensions out of range (n_s=%d n_in=%d n_u=%d; limits %d/%d)", n_s, n_in, n_u, SEGP_MAX_NS,
+                  SEGP_MAX_NU);
+        return SEGP_ERR_INVALID;
+    }
+    return SEGP_OK;
+}
+}  // namespace
+
+int segp_ellipsoid_step(int device, long n_batch, int n_s, int n_s_in, int n_u, const double* d_mu,
+                        const double* d_var, const double* d_jac, const double* d_p, const double* d_q,
+                        const double* d_k_ff, const double* d_k_fb, long kfb_stride, const segp_reach_params* params,
+                        double* d_p_out, double* d_q_out, int32_t* d_status, void* stream) {
+    SEGP_CHECK(check_dims(n_s, n_s_in, n_u));
+    if (n_batch <= 0) return n_batch == 0 ? SEGP_OK : SEGP_ERR_INVALID;
+    if (d_mu == nullptr || d_var == nullptr || d_p == nullptr || d_k_ff == nullptr || d_p_out == nullptr ||
+        d_q_out == nullptr || (d_q != nullptr && (d_jac == nullptr || d_k_fb == nullptr))) {
+        set_error("segp_ellipsoid_step: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    StepParams sp;
+    SEGP_CHECK(fill_step_params(&sp, params, n_s, n_s_in, n_u));
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TempParams tp(st);
+    SEGP_CHECK(tp.upload(sp));
+    if (d_status != nullptr) SEGP_CUDA_CHECK(cudaMemsetAsync(d_status, 0, n_batch * sizeof(int32_t), st));
+    StepArgs s{};
+    s.mu_d = d_mu;
+    s.var_d = d_var;
+    s.jac_d = d_jac;
+    s.p = d_p;
+    s.p_stride = n_s;
+    s.q = d_q;
+    s.q_stride = (long)n_s * n_s;
+    s.kff = d_k_ff;
+    s.kff_stride = n_u;
+    s.kfb = d_k_fb;
+    s.kfb_stride = kfb_stride;
+    s.sp = tp.d;
+    s.p_out = d_p_out;
+    s.p_out_stride = n_s;
+    s.q_out = d_q_out;
+    s.q_out_stride = (long)n_s * n_s;
+    s.status = d_status;
+    s.n_batch = n_batch;
+    s.n_s = n_s;
+    s.n_in = n_s_in;
+    s.n_u = n_u;
+    return launch_ellipsoid_step(s, st);
+}
+
+int segp_remainder_overapproximations(int device, long n_batch, int n_s, int n_u, const double* d_q,
+                                      const double* d_k_fb, long kfb_stride, const double* h_l_mu,
+                                      const double* h_l_sigma, double* d_u_mu, double* d_u_sigma, void* stream) {
+    SEGP_CHECK(check_dims(n_s, n_s, n_u));
+    if (n_batch <= 0) return n_batch == 0 ? SEGP_OK : SEGP_ERR_INVALID;
+    if (d_q == nullptr || d_k_fb == nullptr || h_l_mu == nullptr || h_l_sigma == nullptr || d_u_mu == nullptr ||
+        d_u_sigma == nullptr) {
+        set_error("segp_remainder_overapproximations: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    segp_reach_params prm{h_l_mu, h_l_sigma, 1.0, nullptr, nullptr, nullptr};
+    StepParams sp;
+    SEGP_CHECK(fill_step_params(&sp, &prm, n_s, n_s, n_u));
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TempParams tp(st);
+    SEGP_CHECK(tp.upload(sp));
+    return launch_remainder(n_batch, n_s, n_u, d_q, d_k_fb, kfb_stride, tp.d, d_u_mu, d_u_sigma, st);
+}
+
+int segp_sum_two_ellipsoids(int device, long n_batch, int n, const double* d_p1, const double* d_q1,
+                            const double* d_p2, const double* d_q2, double* d_p, double* d_q, void* stream) {
+    if (n_batch <= 0) return n_batch == 0 ? SEGP_OK : SEGP_ERR_INVALID;
+    if (n < 1 || d_p1 == nullptr || d_q1 == nullptr || d_p2 == nullptr || d_q2 == nullptr || d_p == nullptr ||
+        d_q == nullptr) {
+        set_error("segp_sum_two_ellipsoids: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    return launch_sum_two(n_batch, n, d_p1, d_q1, d_p2, d_q2, d_p, d_q, static_cast<cudaStream_t>(stream));
+}
+
+int segp_ellipsoid_from_rectangle(int device, long n_batch, int n, const double* d_ub, double* d_q, int32_t* d_status,
+                                  void* stream) {
+    if (n_batch <= 0) return n_batch == 0 ? SEGP_OK : SEGP_ERR_INVALID;
+    if (n < 1 || d_ub == nullptr || d_q == nullptr) {
+        set_error("segp_ellipsoid_from_rectangle: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    return launch_from_rectangle(n_batch, n, d_ub, d_q, d_status, static_cast<cudaStream_t>(stream));
+}
+
+int segp_safety_distance(int device, long n_items, int n_s, int m, const double* d_p, const double* d_q,
+                         const double* h_h_mat, const double* h_h_vec, double c_safety, double* d_dist, void* stream) {
+    if (n_items <= 0) return n_items == 0 ? SEGP_OK : SEGP_ERR_INVALID;
+    if (n_s < 1 || m < 1 || d_p == nullptr || d_q == nullptr || h_h_mat == nullptr || h_h_vec == nullptr ||
+        d_dist == nullptr) {
+        set_error("segp_safety_distance: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* d_h = nullptr;
+    const size_t n_h = (size_t)m * n_s + m;
+    SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_h), n_h * sizeof(double), st));
+    cudaError_t e = cudaMemcpyAsync(d_h, h_h_mat, (size_t)m * n_s * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_h + (size_t)m * n_s, h_h_vec, m * sizeof(double), cudaMemcpyHostToDevice, st);
+    int rc = SEGP_OK;
+    if (e != cudaSuccess) {
+        set_error("segp_safety_distance: %s", cudaGetErrorString(e));
+        rc = SEGP_ERR_CUDA;
+    } else {
+        rc = launch_safety_distance(n_items, n_s, m, d_p, d_q, d_h, d_h + (size_t)m * n_s, c_safety, d_dist, st);
+    }
+    cudaFreeAsync(d_h, st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- options
+int segp_set_option(segp_model* m, const char* name, long value) {
+    if (m == nullptr || name == nullptr) {
+        set_error("segp_set_option: null argument");
+        return SEGP_ERR_INVALID;
+    }
+    if (strcmp(name, "chunk") == 0 && value >= TILE) {
+        DeviceGuard guard(m->device);
+        cudaDeviceSynchronize();
+        free_workspace(m);
+        m->opt_chunk = (value + TILE - 1) / TILE * TILE;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "panel_group") == 0 && value >= 1) {
+        m->opt_panel_group = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "ksplit") == 0 && value >= 0) {
+        m->opt_ksplit = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "time_tri") == 0) {
+        m->time_tri = value != 0;
+        if (m->time_tri) m->tri_events_used = 0;
+        return SEGP_OK;
+    }
+    set_error("segp_set_option: unknown option or bad value: %s=%ld", name, value);
+    return SEGP_ERR_INVALID;
+}
+
+int segp_get_option(segp_model* m, const char* name, long* value) {
+    if (m == nullptr || name == nullptr || value == nullptr) {
+        set_error("segp_get_option: null argument");
+        return SEGP_ERR_INVALID;
+    }
+    if (strcmp(name, "chunk") == 0) *value = m->opt_chunk;
+    else if (strcmp(name, "panel_group") == 0) *value = m->opt_panel_group;
+    else if (strcmp(name, "ksplit") == 0) *value = m->opt_ksplit;
+    else if (strcmp(name, "launches") == 0) *value = m->launches;
+    else if (strcmp(name, "n_train_padded") == 0) *value = m->n_pad;
+    else if (strcmp(name, "workspace_bytes") == 0) *value = (long)m->workspace_bytes;
+    else if (strcmp(name, "tri_launches") == 0) *value = (long)(m->tri_events_used / 2);
+    else if (strcmp(name, "tri_ns") == 0) {
+        // total device time of the tri_sumsq launches recorded since time_tri was switched on
+        DeviceGuard guard(m->device);
+        SEGP_CUDA_CHECK(cudaDeviceSynchronize());
+        double total_ms = 0.0;
+        for (size_t i = 0; i + 1 < m->tri_events_used; i += 2) {
+            float ms = 0.f;
+            SEGP_CUDA_CHECK(cudaEventElapsedTime(&ms, m->tri_events[i], m->tri_events[i + 1]));
+            total_ms += ms;
+        }
+        *value = (long)(total_ms * 1e6);
+    }
+    else {
+        set_error("segp_get_option: unknown option %s", name);
+        return SEGP_ERR_INVALID;
+    }
+    return SEGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,482 @@
+// Per-trajectory ellipsoid calculus, one thread per trajectory, float64 in registers:
+//   ellipsoid_step   body of onestep_reachability after the ssm(...) call (gp_reachability.py:75-88 point branch,
+//                    :102-156 set branch), with compute_remainder_overapproximations (utils.py:108-144),
+//                    ellipsoid_from_rectangle (utils_ellipsoid.py:197-233) and both sum_two_ellipsoids
+//                    (utils_ellipsoid.py:63-94) fused; optional GP-input transform (gp_reachability_casadi.py:60-98).
+//                    In the fused path it also finishes the GP posterior: fixed-order reduction of the mean /
+//                    Jacobian / |L^-1 k*|^2 partials written by kstar_mean_jac and tri_sumsq.
+//   remainder, sum_two, from_rectangle, safety_distance : the batched leaves behind the Python mirrors of
+//                    utils.py / utils_ellipsoid.py / gp_reachability.py:215-250.
+// The reference takes max eig(Q (I + K^T K)) with a general eigen-solver (utils.py:133-134); Q B is similar to the
+// symmetric C^T Q C with B = C C^T, so a cyclic Jacobi iteration on that gives the same spectrum.
+#include <math.h>
+
+#include "segp_internal.cuh"
+
+namespace segp {
+
+// Small state dimensions are fully unrolled into registers; larger ones keep rolled loops over local-memory arrays
+// (the ellipsoid algebra is O(n_s^3) per trajectory-step against O(n_s N^2) for the GP, so it never matters).
+__host__ __device__ constexpr int unroll_factor(int n) { return n <= 4 ? 32 : 1; }
+
+// largest eigenvalue of Q (I + K^T K), Q symmetric positive semi-definite (n x n), K (n_u x n)
+template <int N, int NU>
+__device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const double (&kfb)[NU][N], int n, int nu) {
+    constexpr int UF = unroll_factor(N);
+    double bm[N][N];
+#pragma unroll UF
+    for (int i = 0; i < N; ++i)
+#pragma unroll UF
+        for (int j = 0; j < N; ++j) {
+            double acc = (i == j) ? 1.0 : 0.0;
+            if (i < n && j < n) {
+#pragma unroll UF
+                for (int u = 0; u < NU; ++u)
+                    if (u < nu) acc = fma(kfb[u][i], kfb[u][j], acc);
+            }
+            bm[i][j] = acc;
+        }
+    // Cholesky B = C C^T (B >= I, always positive definite), in place, lower
+#pragma unroll UF
+    for (int j = 0; j < N; ++j) {
+        if (j < n) {
+            double d = bm[j][j];
+#pragma unroll UF
+            for (int k = 0; k < N; ++k)
+                if (k < j) d = fma(-bm[j][k], bm[j][k], d);
+            d = sqrt(d);
+            bm[j][j] = d;
+            const double inv = 1.0 / d;
+#pragma unroll UF
+            for (int i = 0; i < N; ++i) {
+                if (i > j && i < n) {
+                    double s = bm[i][j];
+#pragma unroll UF
+                    for (int k = 0; k < N; ++k)
+                        if (k < j) s = fma(-bm[i][k], bm[j][k], s);
+                    bm[i][j] = s * inv;
+                }
+            }
+        }
+    }
+    // M = C^T Q C ; first T = Q C (T[i][j] = sum_{k>=j} Q[i][k] C[k][j])
+    double t[N][N];
+#pragma unroll UF
+    for (int i = 0; i < N; ++i)
+#pragma unroll UF
+        for (int j = 0; j < N; ++j) {
+            double acc = 0.0;
+#pragma unroll UF
+            for (int k = 0; k < N; ++k)
+                if (k >= j && k < n && i < n) acc = fma(0.5 * (q[i][k] + q[k][i]), bm[k][j], acc);
+            t[i][j] = acc;
+        }
+    double m[N][N];
+#pragma unroll UF
+    for (int i = 0; i < N; ++i)
+#pragma unroll UF
+        for (int j = 0; j < N; ++j) {
+            double acc = 0.0;
+            if (j >= i) {
+#pragma unroll UF
+                for (int k = 0; k < N; ++k)
+                    if (k >= i && k < n) acc = fma(bm[k][i], t[k][j], acc);
+            }
+            m[i][j] = acc;
+        }
+#pragma unroll UF
+    for (int i = 0; i < N; ++i)
+#pragma unroll UF
+        for (int j = 0; j < N; ++j)
+            if (j < i) m[i][j] = m[j][i];
+    // cyclic Jacobi on the symmetric M (eigenvalues only)
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, dg = 0.0;
+#pragma unroll UF
+        for (int i = 0; i < N; ++i) {
+            dg = fma(m[i][i], m[i][i], dg);
+#pragma unroll UF
+            for (int j = 0; j < N; ++j)
+                if (j > i) off = fma(m[i][j], m[i][j], off);
+        }
+        if (!(off > 1e-26 * dg)) break;   // relative off-diagonal norm < 1e-13; also exits on NaN / all-zero
+#pragma unroll UF
+        for (int p = 0; p < N; ++p) {
+#pragma unroll UF
+            for (int r = 0; r < N; ++r) {
+                if (r > p && r < n) {
+                    const double apq = m[p][r];
+                    if (apq != 0.0) {
+                        const double theta = (m[r][r] - m[p][p]) / (2.0 * apq);
+                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                        const double cs = 1.0 / sqrt(fma(tt, tt, 1.0));
+                        const double sn = tt * cs;
+#pragma unroll UF
+                        for (int k = 0; k < N; ++k) {
+                            const double akp = m[k][p], akr = m[k][r];
+                            m[k][p] = cs * akp - sn * akr;
+                            m[k][r] = sn * akp + cs * akr;
+                        }
+#pragma unroll UF
+                        for (int k = 0; k < N; ++k) {
+                            const double apk = m[p][k], ark = m[r][k];
+                            m[p][k] = cs * apk - sn * ark;
+                            m[r][k] = sn * apk + cs * ark;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    double lam = m[0][0];
+#pragma unroll UF
+    for (int i = 1; i < N; ++i)
+        if (i < n) lam = fmax(lam, m[i][i]);
+    return lam;
+}
+
+// =========================================================================================== ellipsoid_step
+// NS/NU are compile-time capacities; n_s/n_u the run-time sizes (equal for the specialised instances).
+template <int NS, int NU>
+__global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
+    constexpr int UF = unroll_factor(NS);
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.n_batch) return;
+    const int n_s = a.n_s, n_u = a.n_u, n_in = a.n_in;
+    const int dim = n_in + n_u;
+    const StepParams* __restrict__ sp = a.sp;
+    int32_t status = 0;
+
+    // ---- GP posterior at the centre
+    double mu[NS], var[NS];
+#pragma unroll UF
+    for (int d = 0; d < NS; ++d) {
+        mu[d] = 0.0;
+        var[d] = 0.0;
+        if (d < n_s) {
+            if (a.mu_part != nullptr) {
+                double m = 0.0;
+                for (int s = 0; s < a.nsplit; ++s) m += a.mu_part[((long)s * n_s + d) * a.b_cap + b];
+                double qf = 0.0;
+                for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
+                mu[d] = m;
+                var[d] = a.gp_var[d] - qf;
+            } else {
+                mu[d] = a.mu_d[b * n_s + d];
+                var[d] = a.var_d[b * n_s + d];
+            }
+            if (a.var_out != nullptr) a.var_out[b * a.var_out_stride + d] = var[d];
+            if (!(var[d] > 0.0)) status |= SEGP_STATUS_BAD_VARIANCE;
+        }
+    }
+
+    double p[NS], u[NU];
+#pragma unroll UF
+    for (int i = 0; i < NS; ++i) p[i] = (i < n_s) ? a.p[b * a.p_stride + i] : 0.0;
+#pragma unroll UF
+    for (int i = 0; i < NU; ++i) u[i] = (i < n_u) ? a.kff[b * a.kff_stride + i] : 0.0;
+
+    // p_lin = mu + A p + B k_ff   (gp_reachability.py:82-83, :115)
+    double p1[NS];
+#pragma unroll UF
+    for (int i = 0; i < NS; ++i) {
+        double acc = mu[i];
+        if (i < n_s) {
+#pragma unroll UF
+            for (int k = 0; k < NS; ++k)
+                if (k < n_s) acc = fma(sp->a[i * n_s + k], p[k], acc);
+#pragma unroll UF
+            for (int k = 0; k < NU; ++k)
+                if (k < n_u) acc = fma(sp->b[i * n_u + k], u[k], acc);
+        }
+        p1[i] = acc;
+    }
+    const double c = sp->c_safety;
+    double q1[NS][NS];
+
+    if (a.q == nullptr) {
+        // ---- point branch (gp_reachability.py:65-88): Q1 = diag(n_s (c sigma_d)^2)
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i)
+#pragma unroll UF
+            for (int j = 0; j < NS; ++j) q1[i][j] = 0.0;
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i)
+            if (i < n_s) {
+                const double bound = c * sqrt(var[i]);
+                if (!(bound > 0.0)) status |= SEGP_STATUS_ZERO_BOUND;
+                q1[i][i] = (double)n_s * bound * bound;
+            }
+    } else {
+        // ---- set branch (gp_reachability.py:89-156)
+        double q[NS][NS], kfb[NU][NS];
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i)
+#pragma unroll UF
+            for (int j = 0; j < NS; ++j) q[i][j] = (i < n_s && j < n_s) ? a.q[b * a.q_stride + i * n_s + j] : 0.0;
+#pragma unroll UF
+        for (int i = 0; i < NU; ++i)
+#pragma unroll UF
+            for (int j = 0; j < NS; ++j)
+                kfb[i][j] = (i < n_u && j < n_s) ? a.kfb[b * a.kfb_stride + i * n_s + j] : 0.0;
+
+        // H = A + A_mu + (B_mu + B) K_fb ; A_mu = J[:, :n_in] (T), B_mu = J[:, n_in:]
+        double h[NS][NS];
+#pragma unroll UF
+        for (int d = 0; d < NS; ++d) {
+            if (d < n_s) {
+                // Jacobian row d: jrow[j], j < dim
+                double jrow[NS + NU];
+#pragma unroll UF
+                for (int j = 0; j < NS + NU; ++j) {
+                    jrow[j] = 0.0;
+                    if (j < dim) {
+                        if (a.mu_part != nullptr) {
+                            double acc = 0.0;
+                            for (int s = 0; s < a.nsplit; ++s)
+                                acc += a.jac_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
+                            jrow[j] = -acc * a.invls[d * dim + j];
+                        } else {
+                            jrow[j] = a.jac_d[(b * n_s + d) * dim + j];
+                        }
+                    }
+                }
+#pragma unroll UF
+                for (int j = 0; j < NS; ++j) {
+                    if (j < n_s) {
+                        double acc = sp->a[d * n_s + j];
+                        if (sp->has_t) {
+                            for (int i = 0; i < n_in; ++i) {
+                                double ji = 0.0;
+#pragma unroll UF
+                                for (int jj = 0; jj < NS + NU; ++jj)
+                                    if (jj == i) ji = jrow[jj];
+                                acc = fma(ji, sp->t[i * n_s + j], acc);
+                            }
+                        } else {
+                            acc += jrow[j];
+                        }
+#pragma unroll UF
+                        for (int k = 0; k < NU; ++k) {
+                            if (k < n_u) {
+                                double jb = 0.0;
+#pragma unroll UF
+                                for (int jj = 0; jj < NS + NU; ++jj)
+                                    if (jj == n_in + k) jb = jrow[jj];
+                                acc = fma(jb + sp->b[d * n_u + k], kfb[k][j], acc);
+                            }
+                        }
+                        h[d][j] = acc;
+                    } else {
+                        h[d][j] = 0.0;
+                    }
+                }
+            } else {
+#pragma unroll UF
+                for (int j = 0; j < NS; ++j) h[d][j] = 0.0;
+            }
+        }
+        // Q0 = H Q H^T
+        double hq[NS][NS];
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i)
+#pragma unroll UF
+            for (int j = 0; j < NS; ++j) {
+                double acc = 0.0;
+#pragma unroll UF
+                for (int k = 0; k < NS; ++k) acc = fma(h[i][k], q[k][j], acc);
+                hq[i][j] = acc;
+            }
+        double tr0 = 0.0;
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i)
+#pragma unroll UF
+            for (int j = 0; j < NS; ++j) {
+                double acc = 0.0;
+#pragma unroll UF
+                for (int k = 0; k < NS; ++k) acc = fma(hq[i][k], h[j][k], acc);
+                q1[i][j] = acc;
+                if (i == j) tr0 += acc;
+            }
+        // remainder boxes (utils.py:129-142)
+        const double r2 = lambda_max_qb<NS, NU>(q, kfb, n_s, n_u);
+        const double r1 = sqrt(r2);
+        double tr_sig = 0.0, tr_mu = 0.0;
+        double d_sig[NS], d_mu[NS];
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i) {
+            d_sig[i] = d_mu[i] = 0.0;
+            if (i < n_s) {
+                const double ub_mu = sp->l_mu[i] * r2;
+                const double ub_sig = sp->l_sigma[i] * r1;
+                const double bs = c * (sqrt(var[i]) + ub_sig);
+                if (!(bs > 0.0) || !(ub_mu > 0.0)) status |= SEGP_STATUS_ZERO_BOUND;
+                d_sig[i] = (double)n_s * bs * bs;
+                d_mu[i] = (double)n_s * ub_mu * ub_mu;
+                tr_sig += d_sig[i];
+                tr_mu += d_mu[i];
+            }
+        }
+        // (0, Q_L) = Q_sigma (+) Q_mu ; (p1, Q1) = (0, Q_L) (+) (p0, Q0)     (utils_ellipsoid.py:88-94)
+        const double c1 = sqrt(tr_sig / tr_mu);
+        double tr_l = 0.0;
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i) {
+            d_sig[i] = (1.0 + 1.0 / c1) * d_sig[i] + (1.0 + c1) * d_mu[i];
+            tr_l += d_sig[i];
+        }
+        const double c2 = sqrt(tr_l / tr0);
+        const double f_l = 1.0 + 1.0 / c2, f_0 = 1.0 + c2;
+#pragma unroll UF
+        for (int i = 0; i < NS; ++i)
+#pragma unroll UF
+            for (int j = 0; j < NS; ++j) q1[i][j] = f_0 * q1[i][j] + ((i == j) ? f_l * d_sig[i] : 0.0);
+    }
+
+    bool finite = true;
+#pragma unroll UF
+    for (int i = 0; i < NS; ++i) {
+        if (i < n_s) {
+            a.p_out[b * a.p_out_stride + i] = p1[i];
+            finite = finite && isfinite(p1[i]);
+#pragma unroll UF
+            for (int j = 0; j < NS; ++j)
+                if (j < n_s) {
+                    a.q_out[b * a.q_out_stride + i * n_s + j] = q1[i][j];
+                    finite = finite && isfinite(q1[i][j]);
+                }
+        }
+    }
+    if (!finite) status |= SEGP_STATUS_NONFINITE;
+    if (a.status != nullptr && status != 0) atomicOr(&a.status[b], status);
+}
+
+int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
+    const int threads = 64;
+    const unsigned grid = (unsigned)((a.n_batch + threads - 1) / threads);
+    if (a.n_s == 2 && a.n_u == 1)
+        ellipsoid_step_kernel<2, 1><<<grid, threads, 0, st>>>(a);
+    else if (a.n_s == 4 && a.n_u == 1)
+        ellipsoid_step_kernel<4, 1><<<grid, threads, 0, st>>>(a);
+    else if (a.n_s <= 4 && a.n_u <= 2)
+        ellipsoid_step_kernel<4, 2><<<grid, threads, 0, st>>>(a);
+    else
+        ellipsoid_step_kernel<SEGP_MAX_NS, SEGP_MAX_NU><<<grid, threads, 0, st>>>(a);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== batched leaves
+template <int NS, int NU>
+__global__ void remainder_kernel(long n_batch, int n_s, int n_u, const double* __restrict__ q,
+                                 const double* __restrict__ kfb, long kfb_stride, const StepParams* __restrict__ sp,
+                                 double* __restrict__ u_mu, double* __restrict__ u_sigma) {
+    constexpr int UF = unroll_factor(NS);
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch) return;
+    double qm[NS][NS], k[NU][NS];
+#pragma unroll UF
+    for (int i = 0; i < NS; ++i)
+#pragma unroll UF
+        for (int j = 0; j < NS; ++j) qm[i][j] = (i < n_s && j < n_s) ? q[b * n_s * n_s + i * n_s + j] : 0.0;
+#pragma unroll UF
+    for (int i = 0; i < NU; ++i)
+#pragma unroll UF
+        for (int j = 0; j < NS; ++j) k[i][j] = (i < n_u && j < n_s) ? kfb[b * kfb_stride + i * n_s + j] : 0.0;
+    const double r2 = lambda_max_qb<NS, NU>(qm, k, n_s, n_u);
+    const double r1 = sqrt(r2);
+    for (int i = 0; i < n_s; ++i) {
+        u_mu[b * n_s + i] = sp->l_mu[i] * r2;
+        u_sigma[b * n_s + i] = sp->l_sigma[i] * r1;
+    }
+}
+
+int launch_remainder(long n_batch, int n_s, int n_u, const double* q, const double* kfb, long kfb_stride,
+                     const StepParams* sp, double* u_mu, double* u_sigma, cudaStream_t st) {
+    const int threads = 64;
+    const unsigned grid = (unsigned)((n_batch + threads - 1) / threads);
+    if (n_s <= 4 && n_u <= 2)
+        remainder_kernel<4, 2><<<grid, threads, 0, st>>>(n_batch, n_s, n_u, q, kfb, kfb_stride, sp, u_mu, u_sigma);
+    else
+        remainder_kernel<SEGP_MAX_NS, SEGP_MAX_NU>
+            <<<grid, threads, 0, st>>>(n_batch, n_s, n_u, q, kfb, kfb_stride, sp, u_mu, u_sigma);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// utils_ellipsoid.py:63-94 with c = sqrt(tr Q1 / tr Q2)
+__global__ void sum_two_kernel(long n_batch, int n, const double* __restrict__ p1, const double* __restrict__ q1,
+                               const double* __restrict__ p2, const double* __restrict__ q2, double* __restrict__ p,
+                               double* __restrict__ q) {
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch) return;
+    const double* a1 = q1 + b * n * n;
+    const double* a2 = q2 + b * n * n;
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+        t1 += a1[i * n + i];
+        t2 += a2[i * n + i];
+    }
+    const double c = sqrt(t1 / t2);
+    const double f1 = 1.0 + 1.0 / c, f2 = 1.0 + c;
+    for (int i = 0; i < n * n; ++i) q[b * n * n + i] = f1 * a1[i] + f2 * a2[i];
+    for (int i = 0; i < n; ++i) p[b * n + i] = p1[b * n + i] + p2[b * n + i];
+}
+
+int launch_sum_two(long n_batch, int n, const double* p1, const double* q1, const double* p2, const double* q2,
+                   double* p, double* q, cudaStream_t st) {
+    sum_two_kernel<<<(unsigned)((n_batch + 127) / 128), 128, 0, st>>>(n_batch, n, p1, q1, p2, q2, p, q);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// utils_ellipsoid.py:197-233
+__global__ void from_rectangle_kernel(long n_batch, int n, const double* __restrict__ ub, double* __restrict__ q,
+                                      int32_t* __restrict__ status) {
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch) return;
+    int32_t st = 0;
+    for (int i = 0; i < n; ++i) {
+        const double v = ub[b * n + i];
+        if (!(v > 0.0)) st |= SEGP_STATUS_ZERO_BOUND;
+        for (int j = 0; j < n; ++j) q[b * n * n + i * n + j] = (i == j) ? (double)n * v * v : 0.0;
+    }
+    if (status != nullptr) status[b] = st;
+}
+
+int launch_from_rectangle(long n_batch, int n, const double* ub, double* q, int32_t* status, cudaStream_t st) {
+    from_rectangle_kernel<<<(unsigned)((n_batch + 127) / 128), 128, 0, st>>>(n_batch, n, ub, q, status);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// gp_reachability.py:215-250: d = h_mat p + c sqrt(diag(h_mat Q h_mat^T)) - h_vec ; one thread per (item, constraint)
+__global__ void safety_distance_kernel(long n_items, int n_s, int m, const double* __restrict__ p,
+                                       const double* __restrict__ q, const double* __restrict__ hmat,
+                                       const double* __restrict__ hvec, double c, double* __restrict__ dist) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_items * m) return;
+    const long b = idx / m;
+    const int r = (int)(idx % m);
+    const double* hr = hmat + (long)r * n_s;
+    const double* qb = q + b * n_s * n_s;
+    double dc = 0.0, ds = 0.0;
+    for (int i = 0; i < n_s; ++i) {
+        dc = fma(hr[i], p[b * n_s + i], dc);
+        double acc = 0.0;
+        for (int j = 0; j < n_s; ++j) acc = fma(qb[i * n_s + j], hr[j], acc);
+        ds = fma(hr[i], acc, ds);
+    }
+    dist[idx] = dc + c * sqrt(ds) - hvec[r];
+}
+
+int launch_safety_distance(long n_items, int n_s, int m, const double* p, const double* q, const double* hmat,
+                           const double* hvec, double c, double* dist, cudaStream_t st) {
+    const long total = n_items * m;
+    safety_distance_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(n_items, n_s, m, p, q, hmat, hvec, c,
+                                                                           dist);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+}  // namespace segp

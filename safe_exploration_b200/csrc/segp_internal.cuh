@@ -1,0 +1,160 @@
+// Internal declarations shared by the libsegp translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "segp.h"
+
+namespace segp {
+
+constexpr int TILE = 128;   // tile edge of the variance contraction; N is padded to a multiple of it
+constexpr int KC = 16;      // k-depth of one pipeline stage of tri_sumsq
+constexpr int NBLK = 64;    // block size of the setup factorisation kernels
+constexpr int MAX_D = SEGP_MAX_NS + SEGP_MAX_NU;
+
+void set_error(const char* fmt, ...);
+
+#define SEGP_CUDA_CHECK(expr)                                                                       \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            ::segp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,    \
+                              __LINE__);                                                            \
+            return SEGP_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+#define SEGP_CHECK(expr)             \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != SEGP_OK) return rc__; \
+    } while (0)
+
+// Shared reachability parameters, resident in device memory (uploaded once per call).
+struct StepParams {
+    double a[SEGP_MAX_NS * SEGP_MAX_NS];     // row-major n_s x n_s
+    double b[SEGP_MAX_NS * SEGP_MAX_NU];     // row-major n_s x n_u
+    double t[SEGP_MAX_NS * SEGP_MAX_NS];     // row-major n_in x n_s (only if has_t)
+    double l_mu[SEGP_MAX_NS];
+    double l_sigma[SEGP_MAX_NS];
+    double c_safety;
+    int has_t;
+    int pad_;
+};
+
+// ---------------------------------------------------------------- kernel-matrix block + mean/Jacobian partials
+struct KstarArgs {
+    const double* xs;       // [n_s][Np][D]  training inputs scaled by 1/lengthscale_d
+    const double* invls;    // [n_s][D]
+    const double* var;      // [n_s]
+    const double* beta;     // [n_s][Np]     zero padded
+    int kern[SEGP_MAX_NS];
+    int n_train, n_pad, dim, n_in, n_u, n_s_state;
+    const double* z;        // direct inputs [B x D] (predict) or NULL
+    const double* p;        // state centres (used when z == NULL), n_s_state per trajectory
+    long p_stride;
+    const double* kff;      // feed-forward controls, n_u per trajectory
+    long kff_stride;
+    const StepParams* sp;   // for t_z_gp (may be NULL when z != NULL)
+    long n_batch, b_cap;
+    int groups_per_split;   // 4-row groups handled by one blockIdx.z
+    double* ks;             // [n_s][Np/4][b_cap][4]
+    double* mu_part;        // [nsplit][n_s][b_cap]
+    double* jac_part;       // [nsplit][n_s][D][b_cap]   (scaled coordinates, sign not yet applied)
+};
+int launch_kstar(const KstarArgs& a, int n_s, int nsplit, cudaStream_t st);
+
+// ---------------------------------------------------------------- variance contraction  |W K*|^2 column sums
+struct TriArgs {
+    const double* wt;   // [n_s][ntri][32][128][4]   packed tiles of W = L^-1 (lower block triangle)
+    const double* ks;   // [n_s][Np/4][b_cap][4]
+    double* qpart;      // [n_s][nblk][b_cap]
+    int nblk;           // Np / 128
+    int npanels;        // ceil(B / 128)
+    int group;          // panels per L2 group
+    long b_cap;
+    long ntri;          // nblk (nblk+1) / 2
+};
+int launch_tri_sumsq(const TriArgs& a, int n_s, cudaStream_t st);
+int tri_sumsq_init();   // sets the dynamic shared memory attribute once per device
+
+// ---------------------------------------------------------------- posterior finalise / ellipsoid step
+struct StepArgs {
+    // GP outputs as partials (fused path) ...
+    const double* mu_part;
+    const double* jac_part;
+    const double* qpart;
+    const double* gp_var;   // [n_s] signal variances
+    const double* invls;    // [n_s][D]
+    int nsplit, nblk;
+    long b_cap;
+    // ... or given directly (foreign state-space model): [B x n_s], [B x n_s], [B x n_s x D]
+    const double* mu_d;
+    const double* var_d;
+    const double* jac_d;
+    // state
+    const double* p;
+    long p_stride;
+    const double* q;        // NULL -> point branch
+    long q_stride;
+    const double* kff;
+    long kff_stride;
+    const double* kfb;
+    long kfb_stride;
+    const StepParams* sp;
+    double* p_out;
+    long p_out_stride;
+    double* q_out;
+    long q_out_stride;
+    double* var_out;        // may be NULL
+    long var_out_stride;
+    int32_t* status;        // may be NULL
+    long n_batch;
+    int n_s, n_in, n_u;
+};
+int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st);
+
+struct FinalizeArgs {
+    const double* mu_part;
+    const double* jac_part;
+    const double* qpart;
+    const double* gp_var;
+    const double* invls;
+    int nsplit, nblk, n_s, dim;
+    long b_cap, n_batch;
+    double* mu;    // [B x n_s]
+    double* var;   // [B x n_s]
+    double* jac;   // [B x n_s x D] or NULL
+};
+int launch_finalize_predict(const FinalizeArgs& a, cudaStream_t st);
+
+int launch_remainder(long n_batch, int n_s, int n_u, const double* q, const double* kfb, long kfb_stride,
+                     const StepParams* sp, double* u_mu, double* u_sigma, cudaStream_t st);
+int launch_sum_two(long n_batch, int n, const double* p1, const double* q1, const double* p2, const double* q2,
+                   double* p, double* q, cudaStream_t st);
+int launch_from_rectangle(long n_batch, int n, const double* ub, double* q, int32_t* status, cudaStream_t st);
+int launch_safety_distance(long n_items, int n_s, int m, const double* p, const double* q, const double* hmat,
+                           const double* hvec, double c, double* dist, cudaStream_t st);
+
+// ---------------------------------------------------------------- setup (factorisation), all float64 on device
+struct SetupDims {
+    int n_train, n_pad, dim;
+};
+// K[d] (n_pad x n_pad row-major) = k_d(X,X) + noise I; identity on the padded diagonal.
+int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, cudaStream_t st);
+// in-place blocked Cholesky (lower) of a (n_pad x n_pad); diag_inv gets the inverses of the 64x64 diagonal blocks;
+// *d_fail (device int) is set to 1+pivot index on a non-positive pivot.
+int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_t st, long* launches);
+// w (zero-initialised n_pad x n_pad) = inverse of the lower factor l; tmp is 64 x n_pad scratch.
+int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, double* tmp, cudaStream_t st,
+                long* launches);
+// beta = W^T (W y)
+int solve_beta(const double* w, const double* y, double* u_tmp, double* beta, int n_pad, cudaStream_t st);
+// pack W into [ntri][32][128][4] tiles
+int pack_w(const double* w, double* wt, int n_pad, cudaStream_t st);
+// logdet = 2 sum log L_ii over the first n_train rows (single block reduction into *d_out)
+int logdet_from_chol(const double* l, int n_train, int n_pad, double* d_out, cudaStream_t st);
+
+}  // namespace segp

@@ -1,0 +1,478 @@
+// Model setup on the device, all float64 (runs once per model update, off the rollout loop):
+//   kmat        K_d = k_d(X,X) + noise_d I                    (ssm_gpy/gaussian_process.py:247 GPRegression)
+//   potrf_lower blocked right-looking Cholesky, 64-wide panels, trailing update on the FP64 tensor pipe (DMMA)
+//   trtri_lower W_d = L_d^-1 by recursive doubling: [[W11,0],[-W22 L21 W11, W22]]   (GPy posterior.woodbury_inv
+//               is W^T W; ssm_gpy/gaussian_process.py:258-259, 406-409 pdinv)
+//   solve_beta  beta_d = W^T (W y_d)                          (posterior.woodbury_vector, :261)
+//   pack_w      W -> 128x128 tiles in DMMA fragment order for tri_sumsq
+//   logdet      2 sum log L_ii                                (information_gain, :621-634)
+// The factorisation must be float64: cond(K + noise I) ~ N s_f^2 / noise ~ 1e6..1e8 at the benchmark sizes.
+#include <math.h>
+
+#include "segp_internal.cuh"
+
+namespace segp {
+
+// =========================================================================================== kmat
+__global__ void kmat_kernel(double* __restrict__ k, const double* __restrict__ xs, int kern, double var, double noise,
+                            int n_train, int n_pad, int dim) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n_pad) return;
+    double v;
+    if (i >= n_train || j >= n_train) {
+        v = (i == j) ? 1.0 : 0.0;
+    } else if (i == j) {
+        v = var + noise;
+    } else {
+        double r2 = 0.0;
+        for (int c = 0; c < dim; ++c) {
+            const double df = xs[(long)i * dim + c] - xs[(long)j * dim + c];
+            r2 = fma(df, df, r2);
+        }
+        if (kern == SEGP_KERN_RBF) {
+            v = var * exp(-0.5 * r2);
+        } else {
+            const double sqrt5 = 2.23606797749978969641;
+            const double rr = sqrt(r2);
+            v = var * (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * exp(-sqrt5 * rr);
+        }
+    }
+    k[(long)i * n_pad + j] = v;
+}
+
+int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, cudaStream_t st) {
+    dim3 grid((unsigned)((s.n_pad + 127) / 128), (unsigned)s.n_pad);
+    kmat_kernel<<<grid, 128, 0, st>>>(k, xs_d, kern, var, noise, s.n_train, s.n_pad, s.dim);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== gemm64 (DMMA)
+// C[z] (M_z x N) = alpha * A[z] (M_z x K) * op(B[z]) + beta * C[z];  all row-major, all dims multiples of 64.
+//   TRANS_B: B is N x K (C = A B^T), else B is K x N.
+//   flags  GEMM_A_LOWER: A[i,k] == 0 for k > i   -> k loop stops at the row tile's end
+//          GEMM_B_LOWER: B[k,n] == 0 for k < n   -> k loop starts at the column tile's start (non-transposed B)
+//          GEMM_C_LOWER: only tiles on or below the diagonal are computed (syrk)
+//   batch  blockIdx.z: every pointer advances by z * zstride elements; M_z = min(M, m_total - z * zrows).
+// 64x64 tile, 4 warps (2x2) of 32x32 = 4x4 DMMA m8n8k4 tiles; operands staged in shared memory in fragment order
+// [k/4][row][k%4] so every fragment is one conflict-free LDS.64; global loads are register-prefetched one chunk ahead.
+constexpr int GEMM_A_LOWER = 1;
+constexpr int GEMM_B_LOWER = 2;
+constexpr int GEMM_C_LOWER = 4;
+constexpr int GT = 64;    // tile edge
+constexpr int GK = 16;    // k chunk
+
+struct GemmArgs {
+    const double* a;
+    const double* b;
+    double* c;
+    long lda, ldb, ldc;
+    int m, n, k;
+    double alpha, beta;
+    int flags;
+    long zstride_a, zstride_b, zstride_c;
+    int m_total, zrows;
+};
+
+__device__ __forceinline__ void dmma884_s(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool TRANS_B>
+__global__ void __launch_bounds__(128) gemm64_kernel(const GemmArgs g) {
+    const int z = blockIdx.z;
+    const int m_z = min(g.m, g.m_total - z * g.zrows);
+    const int row0 = blockIdx.y * GT;
+    const int col0 = blockIdx.x * GT;
+    if (row0 >= m_z) return;
+    if ((g.flags & GEMM_C_LOWER) && col0 > row0) return;
+    const double* __restrict__ A = g.a + (long)z * g.zstride_a;
+    const double* __restrict__ B = g.b + (long)z * g.zstride_b;
+    double* __restrict__ C = g.c + (long)z * g.zstride_c;
+
+    int k_begin = 0, k_end = g.k;
+    if (g.flags & GEMM_A_LOWER) k_end = min(k_end, row0 + GT);
+    if (g.flags & GEMM_B_LOWER) k_begin = col0;
+
+    __shared__ __align__(16) double s_a[GK * GT];   // [k/4][row][k%4]
+    __shared__ __align__(16) double s_b[GK * GT];   // [k/4][col][k%4]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const int frag = (lane >> 2) * 4 + (lane & 3);
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // register staging of one chunk: A: 2 x (row, kgroup) items of 4 doubles; B likewise
+    double ra[2][4], rb[2][4];
+    auto load_chunk = [&](int k0) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int item = tid + it * 128;        // 0..255
+            const int r = item >> 2, kg = item & 3;
+            const double2* src = reinterpret_cast<const double2*>(A + (long)(row0 + r) * g.lda + k0 + kg * 4);
+            const double2 v0 = src[0], v1 = src[1];
+            ra[it][0] = v0.x; ra[it][1] = v0.y; ra[it][2] = v1.x; ra[it][3] = v1.y;
+        }
+        if (TRANS_B) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int item = tid + it * 128;
+                const int r = item >> 2, kg = item & 3;
+                const double2* src = reinterpret_cast<const double2*>(B + (long)(col0 + r) * g.ldb + k0 + kg * 4);
+                const double2 v0 = src[0], v1 = src[1];
+                rb[it][0] = v0.x; rb[it][1] = v0.y; rb[it][2] = v1.x; rb[it][3] = v1.y;
+            }
+        } else {
+            // item = (kgroup, column pair): 4 x 32 = 128 items, one per thread; two columns x four k each
+            const int kg = tid >> 5, cp = tid & 31;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const double2 v =
+                    *reinterpret_cast<const double2*>(B + (long)(k0 + kg * 4 + kk) * g.ldb + col0 + cp * 2);
+                rb[0][kk] = v.x;
+                rb[1][kk] = v.y;
+            }
+        }
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int item = tid + it * 128;
+            const int r = item >> 2, kg = item & 3;
+            double2* dst = reinterpret_cast<double2*>(s_a + (kg * GT + r) * 4);
+            dst[0] = make_double2(ra[it][0], ra[it][1]);
+            dst[1] = make_double2(ra[it][2], ra[it][3]);
+        }
+        if (TRANS_B) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int item = tid + it * 128;
+                const int r = item >> 2, kg = item & 3;
+                double2* dst = reinterpret_cast<double2*>(s_b + (kg * GT + r) * 4);
+                dst[0] = make_double2(rb[it][0], rb[it][1]);
+                dst[1] = make_double2(rb[it][2], rb[it][3]);
+            }
+        } else {
+            const int kg = tid >> 5, cp = tid & 31;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                double2* dst = reinterpret_cast<double2*>(s_b + (kg * GT + cp * 2 + cc) * 4);
+                dst[0] = make_double2(rb[cc][0], rb[cc][1]);
+                dst[1] = make_double2(rb[cc][2], rb[cc][3]);
+            }
+        }
+    };
+
+    if (k_begin < k_end) load_chunk(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += GK) {
+        store_chunk();
+        __syncthreads();
+        if (k0 + GK < k_end) load_chunk(k0 + GK);
+#pragma unroll
+        for (int kk = 0; kk < GK / 4; ++kk) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = s_a[(kk * GT + wr + i * 8) * 4 + frag];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = s_b[(kk * GT + wc + j * 8) * 4 + frag];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884_s(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+    // epilogue: thread holds rows wr + i*8 + lane/4, columns wc + j*8 + (lane%4)*2 + {0,1}
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + wr + i * 8 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cidx = col0 + wc + j * 8 + (lane & 3) * 2;
+            double2* dst = reinterpret_cast<double2*>(C + (long)r * g.ldc + cidx);
+            double2 out = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+            if (g.beta != 0.0) {
+                const double2 old = *dst;
+                out.x = fma(g.beta, old.x, out.x);
+                out.y = fma(g.beta, old.y, out.y);
+            }
+            *dst = out;
+        }
+    }
+}
+
+static int launch_gemm64(const GemmArgs& g, bool trans_b, int batch, cudaStream_t st) {
+    if (g.m <= 0 || g.n <= 0 || batch <= 0) return SEGP_OK;
+    dim3 grid((unsigned)(g.n / GT), (unsigned)(g.m / GT), (unsigned)batch);
+    if (trans_b)
+        gemm64_kernel<true><<<grid, 128, 0, st>>>(g);
+    else
+        gemm64_kernel<false><<<grid, 128, 0, st>>>(g);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== potrf
+// Diagonal block: unblocked Cholesky of the 64x64 block in shared memory + its explicit inverse.
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ a, int n_pad, int kb,
+                                                        double* __restrict__ diag_inv, int* __restrict__ fail) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double(*s)[NBLK + 1] = reinterpret_cast<double(*)[NBLK + 1]>(dyn_smem);
+    double(*x)[NBLK + 1] = s + NBLK;
+    __shared__ int s_fail;
+    const int tid = threadIdx.x;
+    double* blk = a + ((long)kb * NBLK) * n_pad + (long)kb * NBLK;
+    if (tid == 0) s_fail = 0;
+    for (int idx = tid; idx < NBLK * NBLK; idx += 256) {
+        const int r = idx / NBLK, c = idx % NBLK;
+        s[r][c] = (c <= r) ? blk[(long)r * n_pad + c] : 0.0;
+    }
+    __syncthreads();
+    const int row = tid & 63, part = tid >> 6;
+    for (int j = 0; j < NBLK; ++j) {
+        if (tid == 0) {
+            const double d = s[j][j];
+            if (!(d > 0.0)) {
+                s_fail = kb * NBLK + j + 1;
+                s[j][j] = 1.0;
+            } else {
+                s[j][j] = sqrt(d);
+            }
+        }
+        __syncthreads();
+        if (tid > j && tid < NBLK) s[tid][j] /= s[j][j];
+        __syncthreads();
+        if (row > j) {
+            const double lij = s[row][j];
+            for (int k = j + 1 + part; k <= row; k += 4) s[row][k] = fma(-lij, s[k][j], s[row][k]);
+        }
+        __syncthreads();
+    }
+    // inverse, one column per thread (forward substitution)
+    if (tid < NBLK) {
+        const int c = tid;
+        for (int i = 0; i < c; ++i) x[i][c] = 0.0;
+        x[c][c] = 1.0 / s[c][c];
+        for (int i = c + 1; i < NBLK; ++i) {
+            double acc = 0.0;
+            for (int k = c; k < i; ++k) acc = fma(s[i][k], x[k][c], acc);
+            x[i][c] = -acc / s[i][i];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NBLK * NBLK; idx += 256) {
+        const int r = idx / NBLK, c = idx % NBLK;
+        if (c <= r) blk[(long)r * n_pad + c] = s[r][c];
+        diag_inv[(long)kb * NBLK * NBLK + idx] = x[r][c];
+    }
+    if (tid == 0 && s_fail != 0) atomicCAS(fail, 0, s_fail);
+}
+
+// Panel: A[i,k] <- A[i,k] * Linv_kk^T for the row blocks i > k (64 rows per CTA).
+__global__ void __launch_bounds__(256) panel_trsm_kernel(double* __restrict__ a, int n_pad, int kb,
+                                                         const double* __restrict__ diag_inv) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double(*s_a)[NBLK + 1] = reinterpret_cast<double(*)[NBLK + 1]>(dyn_smem);
+    double(*s_l)[NBLK + 1] = s_a + NBLK;
+    const int tid = threadIdx.x;
+    const long row0 = ((long)kb + 1 + blockIdx.x) * NBLK;
+    double* blk = a + row0 * n_pad + (long)kb * NBLK;
+    const double* li = diag_inv + (long)kb * NBLK * NBLK;
+    for (int idx = tid; idx < NBLK * NBLK; idx += 256) {
+        const int r = idx / NBLK, c = idx % NBLK;
+        s_a[r][c] = blk[(long)r * n_pad + c];
+        s_l[r][c] = li[idx];
+    }
+    __syncthreads();
+    // out[r][c] = sum_{m <= c} A[r][m] * Linv[c][m]
+    const int c = tid & 63;
+    for (int r = tid >> 6; r < NBLK; r += 4) {
+        double acc = 0.0;
+        for (int m = 0; m <= c; ++m) acc = fma(s_a[r][m], s_l[c][m], acc);
+        blk[(long)r * n_pad + c] = acc;
+    }
+}
+
+int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_t st, long* launches) {
+    const int nb = n_pad / NBLK;
+    constexpr int kBlockSmem = 2 * NBLK * (NBLK + 1) * (int)sizeof(double);
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmem));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmem));
+    SEGP_CUDA_CHECK(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+    for (int kb = 0; kb < nb; ++kb) {
+        potf2_inv_kernel<<<1, 256, kBlockSmem, st>>>(a, n_pad, kb, diag_inv, d_fail);
+        ++*launches;
+        const int rem = nb - kb - 1;
+        if (rem <= 0) break;
+        panel_trsm_kernel<<<rem, 256, kBlockSmem, st>>>(a, n_pad, kb, diag_inv);
+        ++*launches;
+        // trailing update: A22 -= A21 A21^T (lower tiles only)
+        GemmArgs g{};
+        const long off = ((long)kb + 1) * NBLK;
+        g.a = a + off * n_pad + (long)kb * NBLK;
+        g.b = g.a;
+        g.c = a + off * n_pad + off;
+        g.lda = g.ldb = g.ldc = n_pad;
+        g.m = g.n = rem * NBLK;
+        g.k = NBLK;
+        g.alpha = -1.0;
+        g.beta = 1.0;
+        g.flags = GEMM_C_LOWER;
+        g.m_total = g.m;
+        g.zrows = 0;
+        SEGP_CHECK(launch_gemm64(g, true, 1, st));
+        ++*launches;
+    }
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== trtri
+__global__ void copy_diag_inv_kernel(double* __restrict__ w, int n_pad, const double* __restrict__ diag_inv) {
+    const int kb = blockIdx.x;
+    double* blk = w + ((long)kb * NBLK) * n_pad + (long)kb * NBLK;
+    for (int idx = threadIdx.x; idx < NBLK * NBLK; idx += blockDim.x)
+        blk[(long)(idx / NBLK) * n_pad + (idx % NBLK)] = diag_inv[(long)kb * NBLK * NBLK + idx];
+}
+
+int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, double* tmp, cudaStream_t st,
+                long* launches) {
+    const int nb = n_pad / NBLK;
+    copy_diag_inv_kernel<<<nb, 256, 0, st>>>(w, n_pad, diag_inv);
+    ++*launches;
+    // level with block size s merges diagonal blocks [r0, r0+s) and [r0+s, r0+2s) (clipped at n_pad):
+    //   T   = L21 W11      (W11 lower)       -> tmp, at the coordinates of the (2,1) block
+    //   W21 = -W22 T       (W22 lower)
+    for (long s = NBLK; s < n_pad; s *= 2) {
+        const int pairs = (int)((n_pad - s + 2 * s - 1) / (2 * s));   // pairs whose second block is non-empty
+        GemmArgs g{};
+        g.lda = g.ldb = g.ldc = n_pad;
+        g.m = (int)s;
+        g.n = (int)s;
+        g.k = (int)s;
+        g.zstride_a = g.zstride_b = g.zstride_c = 2 * s * ((long)n_pad + 1);
+        g.m_total = (int)(n_pad - s);
+        g.zrows = (int)(2 * s);
+        // T = L21 * W11
+        g.a = l + s * n_pad;
+        g.b = w;
+        g.c = tmp + s * n_pad;
+        g.alpha = 1.0;
+        g.beta = 0.0;
+        g.flags = GEMM_B_LOWER;
+        SEGP_CHECK(launch_gemm64(g, false, pairs, st));
+        ++*launches;
+        // W21 = -W22 * T   (K = rows of the second block; the A_LOWER trim bounds the k loop by the row tile)
+        g.a = w + s * n_pad + s;
+        g.b = tmp + s * n_pad;
+        g.c = w + s * n_pad;
+        g.alpha = -1.0;
+        g.beta = 0.0;
+        g.flags = GEMM_A_LOWER;
+        SEGP_CHECK(launch_gemm64(g, false, pairs, st));
+        ++*launches;
+    }
+    return SEGP_OK;
+}
+
+// =========================================================================================== beta = W^T (W y)
+// u = W y : one warp per row (W lower: columns 0..row)
+__global__ void wy_kernel(const double* __restrict__ w, const double* __restrict__ y, double* __restrict__ u,
+                          int n_pad) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    double acc = 0.0;
+    const double* wr = w + (long)row * n_pad;
+    for (int c = lane; c <= row; c += 32) acc = fma(wr[c], y[c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) u[row] = acc;
+}
+// beta = W^T u : one thread per column, rows split over blockIdx.y with a fixed-order second pass
+__global__ void wtu_partial_kernel(const double* __restrict__ w, const double* __restrict__ u,
+                                   double* __restrict__ part, int n_pad, int rows_per_split) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_pad) return;
+    const int r0 = blockIdx.y * rows_per_split;
+    const int r1 = min(n_pad, r0 + rows_per_split);
+    double acc = 0.0;
+    for (int r = max(r0, c); r < r1; ++r) acc = fma(w[(long)r * n_pad + c], u[r], acc);
+    part[(long)blockIdx.y * n_pad + c] = acc;
+}
+__global__ void wtu_reduce_kernel(const double* __restrict__ part, double* __restrict__ beta, int n_pad, int nsplit) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_pad) return;
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s) acc += part[(long)s * n_pad + c];
+    beta[c] = acc;
+}
+
+int solve_beta(const double* w, const double* y, double* u_tmp, double* beta, int n_pad, cudaStream_t st) {
+    // u_tmp: (1 + nsplit) * n_pad doubles
+    const int nsplit = 32;
+    const int rows_per_split = (n_pad + nsplit - 1) / nsplit;
+    wy_kernel<<<(n_pad + 7) / 8, 256, 0, st>>>(w, y, u_tmp, n_pad);
+    dim3 grid((unsigned)((n_pad + 127) / 128), nsplit);
+    wtu_partial_kernel<<<grid, 128, 0, st>>>(w, u_tmp, u_tmp + n_pad, n_pad, rows_per_split);
+    wtu_reduce_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(u_tmp + n_pad, beta, n_pad, nsplit);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== pack_w
+// wt[tile(bi,bj)][k/4][row][k%4], tile index bi (bi+1)/2 + bj for bj <= bi; k indexes the columns of W.
+__global__ void pack_w_kernel(const double* __restrict__ w, double* __restrict__ wt, int n_pad) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const long tile = (long)bi * (bi + 1) / 2 + bj;
+    double* dst = wt + tile * (TILE * TILE);
+    const double* src = w + ((long)bi * TILE) * n_pad + (long)bj * TILE;
+    for (int item = threadIdx.x; item < TILE * (TILE / 4); item += blockDim.x) {
+        const int kg = item & 31;      // fastest over k-groups: coalesced reads of a W row
+        const int r = item >> 5;
+        const double2* s2 = reinterpret_cast<const double2*>(src + (long)r * n_pad + kg * 4);
+        double2* d2 = reinterpret_cast<double2*>(dst + ((long)kg * TILE + r) * 4);
+        d2[0] = s2[0];
+        d2[1] = s2[1];
+    }
+}
+
+int pack_w(const double* w, double* wt, int n_pad, cudaStream_t st) {
+    const int nblk = n_pad / TILE;
+    dim3 grid((unsigned)nblk, (unsigned)nblk);
+    pack_w_kernel<<<grid, 256, 0, st>>>(w, wt, n_pad);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== logdet
+__global__ void logdet_kernel(const double* __restrict__ l, int n_train, int n_pad, double* __restrict__ out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_train; i += 256) acc += log(l[(long)i * n_pad + i]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = 2.0 * s[0];
+}
+
+int logdet_from_chol(const double* l, int n_train, int n_pad, double* d_out, cudaStream_t st) {
+    logdet_kernel<<<1, 256, 0, st>>>(l, n_train, n_pad, d_out);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+}  // namespace segp

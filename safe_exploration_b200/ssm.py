@@ -1,0 +1,364 @@
+"""BatchedGPSSM: the state-space-model plugin of the reference, backed by libsegp.so on a B200.
+
+Mirrors, for the hot path only, the surface of
+
+* ``StateSpaceModel`` (reference safe_exploration/state_space_models.py:14-211):
+  ``num_states``, ``num_actions``, ``predict(states, actions, jacobians, full_cov)``, ``__call__``,
+  ``linearize_predict``, ``update_model``;
+* ``SimpleGPModel`` (reference safe_exploration/ssm_gpy/gaussian_process.py:15-634):
+  ``n_s_out / n_s_in / n_u``, ``train``, ``update_model``, GPy-style ``predict(x_new,
+  compute_gradients=...)``, ``predictive_gradients``, ``to_dict / from_dict``, ``information_gain``,
+  ``x_train / y_train / z / beta / hyp / kern_types / gp_trained``.
+
+What is different, on purpose:
+
+* every entry point accepts a batch (the reference's ``__call__`` raises for more than one input,
+  ssm_gpy/gaussian_process.py:142-143);
+* hyper-parameters are explicit inputs (``hyp``), never optimised here: hyper-parameter optimisation is
+  GPy's L-BFGS and is out of scope; ``opt_hyp=True`` raises NotImplementedError;
+* the model lives on the GPU; there is no CPU path: constructing a model without a CUDA device raises.
+
+The arithmetic is float64 end to end (the reference is float64; the predictive variance cancels 3-4
+digits).
+"""
+import ctypes
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["BatchedGPSSM"]
+
+_GPY_JITTER = 1e-8        # ExactGaussianInference adds 1e-8 to the diagonal of K
+_GPY_DEFAULT_NOISE = 1.0  # GPRegression default Gaussian_noise.variance
+
+
+def _default_hyp(n_s_out, dim):
+    """GPy defaults (lengthscale 1, variance 1, Gaussian noise 1), i.e. what SimpleGPModel yields for
+    train(..., opt_hyp=False) (reference test/test_safempc.py:56-69)."""
+    return [{"lengthscale": np.ones(dim), "variance": 1.0, "noise": _GPY_DEFAULT_NOISE} for _ in range(n_s_out)]
+
+
+class BatchedGPSSM(object):
+    """n_s_out independent exact GPs over inputs [state (n_s_in), action (n_u)], evaluated in batch on the GPU.
+
+    Parameters
+    ----------
+    n_s_out, n_s_in, n_u : int
+        As SimpleGPModel.__init__ (ssm_gpy/gaussian_process.py:32-33).
+    X : (N, n_s_in+n_u), y : (N, n_s_out), optional
+        Training data; if both are given and ``train`` is true the model is factorised immediately.
+    kern_types : list[str], optional
+        "rbf" | "mat52" per output dimension (default "rbf").  The composite "lin_rbf"/"lin_mat52"
+        kernels of the reference are not on this path yet: NotImplementedError.
+    hyp : list[dict], optional
+        Per output dimension ``{"lengthscale": (D,) or scalar, "variance": float, "noise": float}``
+        (the reference's hyp dicts, ssm_gpy/gaussian_process.py:494-518, plus the Gaussian noise
+        variance GPy keeps on the likelihood).  Defaults are GPy's defaults.
+    device : int or torch.device, optional
+        CUDA device (default: current).
+    """
+
+    has_jacobian = True
+    has_reverse = False
+
+    def __init__(self, n_s_out, n_s_in, n_u, X=None, y=None, m=None, kern_types=None, hyp=None, train=True,
+                 Z=None, device=None, noise_diag=1e-5):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self._lib = _lib.load()
+        if m is not None or Z is not None:
+            raise NotImplementedError("subset-of-data selection (m) and inducing points (Z) are not on this path; "
+                                      "pass the training set to use (SURVEY.md section 2: out of scope)")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.n_s_out = int(n_s_out)
+        self.n_s_in = int(n_s_in)
+        self.n_u = int(n_u)
+        self.num_states = self.n_s_out
+        self.num_actions = self.n_u
+        self.dim_in = self.n_s_in + self.n_u
+        self.kern_types = list(kern_types) if kern_types is not None else ["rbf"] * self.n_s_out
+        if len(self.kern_types) != self.n_s_out:
+            raise ValueError("kern_types needs one entry per output dimension")
+        for k in self.kern_types:
+            if k not in _lib.KERN_IDS:
+                if k in ("lin_rbf", "lin_mat52", "lin"):
+                    raise NotImplementedError("kernel '{}' is not on the B200 path yet".format(k))
+                raise ValueError("kernel type '{}' not supported".format(k))
+        self.hyp = self._normalise_hyp(hyp)
+        self.noise_diag = float(noise_diag)
+        self.gp_trained = False
+        self.x_train = None
+        self.y_train = None
+        self.z = None
+        self.m = None
+        self._handle = ctypes.c_void_p()
+        kern_ids = (ctypes.c_int * self.n_s_out)(*[_lib.KERN_IDS[k] for k in self.kern_types])
+        _lib.check(self._lib.segp_create(ctypes.byref(self._handle), self.device.index, self.n_s_out, self.n_s_in,
+                                         self.n_u, kern_ids))
+        if X is not None and y is not None and train:
+            self.train(X, y)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            self._lib.segp_destroy(h)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ hyper-parameters
+    def _normalise_hyp(self, hyp):
+        if hyp is None:
+            return _default_hyp(self.n_s_out, self.dim_in)
+        if len(hyp) != self.n_s_out:
+            raise ValueError("hyp needs one dict per output dimension")
+        out = []
+        for h in hyp:
+            ls = np.asarray(h.get("lengthscale", 1.0), dtype=np.float64).reshape(-1)
+            if ls.size == 1:
+                ls = np.full(self.dim_in, float(ls[0]))
+            if ls.size != self.dim_in:
+                raise ValueError("lengthscale needs {} entries".format(self.dim_in))
+            out.append({"lengthscale": ls.copy(), "variance": float(np.asarray(h.get("variance", 1.0)).reshape(-1)[0]),
+                        "noise": float(np.asarray(h.get("noise", _GPY_DEFAULT_NOISE)).reshape(-1)[0])})
+        return out
+
+    def total_noise(self):
+        """Diagonal term added to K per output dimension: Gaussian noise + noise_diag
+        (ssm_gpy/gaussian_process.py:252-253) + GPy's 1e-8 jitter."""
+        return np.array([h["noise"] + self.noise_diag + _GPY_JITTER for h in self.hyp])
+
+    # ------------------------------------------------------------------ training (posterior only)
+    def train(self, X, y, m=None, opt_hyp=False, noise_diag=None, Z=None, choose_data=True, hyp=None):
+        """Posterior half of SimpleGPModel.train (ssm_gpy/gaussian_process.py:238-263): per output dimension
+        K_d + noise I -> Cholesky -> beta, L^-1, all on the GPU.  Hyper-parameters stay fixed."""
+        if opt_hyp:
+            raise NotImplementedError("hyper-parameter optimisation is out of scope for the B200 path; "
+                                      "pass fixed hyper-parameters via hyp=")
+        if m is not None or Z is not None:
+            raise NotImplementedError("subset-of-data selection is out of scope; pass the subset as X, y")
+        if hyp is not None:
+            self.hyp = self._normalise_hyp(hyp)
+        if noise_diag is not None:
+            self.noise_diag = float(noise_diag)
+        x_h = _lib.host_f64(X)
+        y_h = _lib.host_f64(y)
+        if x_h.ndim != 2 or x_h.shape[1] != self.dim_in:
+            raise ValueError("X must be N x {}".format(self.dim_in))
+        if y_h.ndim != 2 or y_h.shape != (x_h.shape[0], self.n_s_out):
+            raise ValueError("y must be N x {}".format(self.n_s_out))
+        ls = _lib.host_f64(np.stack([h["lengthscale"] for h in self.hyp]))
+        var = _lib.host_f64([h["variance"] for h in self.hyp])
+        noise = _lib.host_f64(self.total_noise())
+        self.gp_trained = False
+        _lib.check(self._lib.segp_set_model(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
+                                            _lib.dbl_ptr(ls), _lib.dbl_ptr(var), _lib.dbl_ptr(noise)))
+        self.x_train = x_h
+        self.y_train = y_h
+        self.z = x_h
+        self._factorize()
+
+    def _factorize(self):
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.segp_factorize(self._handle, _lib.current_stream(self.device)))
+        self.gp_trained = True
+
+    def update_model(self, x, y, opt_hyp=False, replace_old=True, noise_diag=None, choose_data=True):
+        """SimpleGPModel.update_model (ssm_gpy/gaussian_process.py:347-419) without re-optimisation:
+        replace or append the data and refactorise."""
+        if opt_hyp:
+            raise NotImplementedError("hyper-parameter optimisation is out of scope for the B200 path")
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        if not replace_old and self.x_train is not None:
+            x = np.vstack((self.x_train, x))
+            y = np.vstack((self.y_train, y))
+        self.train(x, y, noise_diag=noise_diag)
+
+    # ------------------------------------------------------------------ multi-GPU: one broadcast of the factor
+    def factor_buffers(self):
+        """The device buffers that make up the factorised state, as uint8 torch views (for broadcast)."""
+        _lib.check(self._lib.segp_alloc_factor_buffers(self._handle))
+        out = []
+        for i in range(self._lib.segp_num_factor_buffers(self._handle)):
+            ptr = ctypes.c_void_p()
+            nbytes = ctypes.c_size_t()
+            _lib.check(self._lib.segp_factor_buffer(self._handle, i, ctypes.byref(ptr), ctypes.byref(nbytes)))
+            out.append((ptr.value, nbytes.value))
+        return out
+
+    def set_data_only(self, X, y):
+        """Upload data + hyper-parameters without factorising (non-root ranks before the broadcast)."""
+        x_h = _lib.host_f64(X)
+        y_h = _lib.host_f64(y)
+        ls = _lib.host_f64(np.stack([h["lengthscale"] for h in self.hyp]))
+        var = _lib.host_f64([h["variance"] for h in self.hyp])
+        noise = _lib.host_f64(self.total_noise())
+        _lib.check(self._lib.segp_set_model(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
+                                            _lib.dbl_ptr(ls), _lib.dbl_ptr(var), _lib.dbl_ptr(noise)))
+        self.x_train, self.y_train, self.z = x_h, y_h, x_h
+        self.gp_trained = False
+
+    def mark_factorized(self):
+        _lib.check(self._lib.segp_mark_factorized(self._handle))
+        self.gp_trained = True
+
+    # ------------------------------------------------------------------ prediction
+    def _as_device_inputs(self, states, actions):
+        torch = self._torch
+        if actions is None:
+            z = states
+        else:
+            if torch.is_tensor(states) or torch.is_tensor(actions):
+                states = torch.as_tensor(states, dtype=torch.float64, device=self.device)
+                actions = torch.as_tensor(actions, dtype=torch.float64, device=self.device)
+                z = torch.cat((states.reshape(-1, self.n_s_in), actions.reshape(-1, self.n_u)), dim=1)
+            else:
+                z = np.hstack((np.asarray(states, dtype=np.float64).reshape(-1, self.n_s_in),
+                               np.asarray(actions, dtype=np.float64).reshape(-1, self.n_u)))
+        was_tensor = torch.is_tensor(z)
+        z_d = torch.as_tensor(z, dtype=torch.float64, device=self.device).reshape(-1, self.dim_in).contiguous()
+        return z_d, was_tensor
+
+    def predict_device(self, z, jacobians=False):
+        """Device-resident predict: z (T, D) float64 CUDA tensor -> (mu (T,n_s), var (T,n_s)[, jac (T,n_s,D)])."""
+        torch = self._torch
+        if not self.gp_trained:
+            raise RuntimeError("model is not trained")
+        assert z.is_cuda and z.dtype == torch.float64 and z.dim() == 2 and z.shape[1] == self.dim_in
+        z = z.contiguous()
+        t = z.shape[0]
+        mu = torch.empty((t, self.n_s_out), dtype=torch.float64, device=self.device)
+        var = torch.empty((t, self.n_s_out), dtype=torch.float64, device=self.device)
+        jac = torch.empty((t, self.n_s_out, self.dim_in), dtype=torch.float64, device=self.device) if jacobians else None
+        _lib.check(self._lib.segp_predict(self._handle, t, _lib.dev_ptr(z), _lib.dev_ptr(mu), _lib.dev_ptr(var),
+                                          _lib.dev_ptr(jac), _lib.current_stream(self.device)))
+        return (mu, var, jac) if jacobians else (mu, var)
+
+    def predict(self, states, actions=None, jacobians=False, full_cov=False, quantiles=None,
+                compute_gradients=False):
+        """Both reference spellings:
+
+        * ``predict(states (T,n_s), actions (T,n_u), jacobians=False, full_cov=False)``
+          (StateSpaceModel.predict, state_space_models.py:74-104) -> ``(mean (T,n_s), var (T,n_s)[, jac_mean])``;
+        * ``predict(x_new (T,D), compute_gradients=False)`` (SimpleGPModel.predict,
+          ssm_gpy/gaussian_process.py:546-568) -> ``(mu, var[, grad_mu (T,n_s,D)])``.
+
+        NumPy in -> NumPy out; CUDA tensors in -> CUDA tensors out."""
+        if full_cov:
+            raise NotImplementedError("full covariance between test points is not on this path")
+        if quantiles is not None:
+            raise NotImplementedError()       # as the reference, ssm_gpy/gaussian_process.py:561
+        want_jac = bool(jacobians or compute_gradients)
+        z_d, was_tensor = self._as_device_inputs(states, actions)
+        out = self.predict_device(z_d, want_jac)
+        if was_tensor:
+            return out
+        return tuple(o.cpu().numpy() for o in out)
+
+    def predictive_gradients(self, x_new, grad_sigma=False):
+        """ssm_gpy/gaussian_process.py:570-596: d mean / d input, (T, n_s_out, D)."""
+        if grad_sigma:
+            raise NotImplementedError("Gradient of sigma not implemented")
+        return self.predict(x_new, compute_gradients=True)[2]
+
+    def __call__(self, states, actions):
+        """The exact triple onestep_reachability unpacks (gp_reachability.py:74,101) for a single input:
+        ``(mu (n_s,1), var (n_s,1), jac (n_s,D))`` (SimpleGPModel.__call__ -> predict_casadi_symbolic,
+        ssm_gpy/gaussian_process.py:135-175).  For T > 1 inputs the batch triple
+        ``(mu (T,n_s), var (T,n_s), jac (T,n_s,D))`` is returned instead of raising."""
+        mu, var, jac = self.predict(states, actions, jacobians=True)
+        if mu.shape[0] == 1:
+            if self._torch.is_tensor(mu):
+                return mu.t(), var.t(), jac[0]
+            return mu.T, var.T, jac[0]
+        return mu, var, jac
+
+    def linearize_predict(self, states, actions, jacobians=False, full_cov=False):
+        raise NotImplementedError("Taylor-linearised prediction is a 'next' row (SURVEY.md section 8 f2)")
+
+    def get_forward_model_casadi(self, linearize_mu=True):
+        raise NotImplementedError("the CasADi/IPOPT bridge is what the batched sampling path replaces "
+                                  "(SURVEY.md section 2); use safe_exploration_b200.gp_reachability")
+
+    # ------------------------------------------------------------------ introspection
+    @property
+    def beta(self):
+        """(N, n_s_out) = K^-1 y per output dimension (posterior.woodbury_vector)."""
+        if not self.gp_trained:
+            return None
+        ptr, nbytes = self.factor_buffers()[1]
+        n_pad = nbytes // 8 // self.n_s_out
+        host = np.empty((self.n_s_out, n_pad))
+        self._torch.cuda.synchronize(self.device)
+        _cudart_memcpy_d2h(self._torch, host, ptr, nbytes, self.device)
+        return np.ascontiguousarray(host[:, :self.x_train.shape[0]].T)
+
+    def log_det_k(self):
+        """log det (K_d + noise_d I) per output dimension, from the Cholesky factor."""
+        out = np.empty(self.n_s_out)
+        _lib.check(self._lib.segp_logdet(self._handle, _lib.dbl_ptr(out)))
+        return out
+
+    def information_gain(self, x=None):
+        """ssm_gpy/gaussian_process.py:621-634: log det(I + K / noise_var) per output dimension, for the
+        training inputs.  log det(I + K/s) = log det(K + s I) - N log s, taken from the factor when the
+        model's own diagonal term equals the Gaussian noise; the small noise_diag/jitter shift is part of
+        the factorised matrix here (documented difference, relative size 1e-5 / noise)."""
+        if x is not None:
+            raise NotImplementedError("information gain for foreign inputs is a 'next' row (SURVEY.md 8 f4)")
+        n = self.x_train.shape[0]
+        tot = self.total_noise()
+        return list(self.log_det_k() - n * np.log(tot))
+
+    def to_dict(self):
+        """ssm_gpy/gaussian_process.py:177-187 (inv_K is not materialised on this path)."""
+        return {"x": self.x_train, "y": self.y_train, "kern_types": self.kern_types, "hyp": self.hyp,
+                "beta": self.beta, "inv_K": None, "n_s_in": self.n_s_in, "n_s_out": self.n_s_out, "n_u": self.n_u}
+
+    @classmethod
+    def from_dict(cls, gp_dict, device=None):
+        """ssm_gpy/gaussian_process.py:72-133."""
+        x = gp_dict.get("x")
+        y = gp_dict.get("y")
+        if x is None or y is None:
+            warnings.warn("no data in gp_dict: the model is instantiated untrained")
+        if "prior_model" in gp_dict and x is not None:
+            y = y - gp_dict["prior_model"](x)
+        return cls(gp_dict["n_s_out"], gp_dict["n_s_in"], gp_dict["n_u"], x, y, None, gp_dict.get("kern_types"),
+                   gp_dict.get("hyp"), gp_dict.get("train", True), None, device)
+
+    def set_option(self, name, value):
+        _lib.check(self._lib.segp_set_option(self._handle, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = ctypes.c_long()
+        _lib.check(self._lib.segp_get_option(self._handle, name.encode(), ctypes.byref(v)))
+        return v.value
+
+
+def _cudart_memcpy_d2h(torch, host, dev_ptr, nbytes, device):
+    """Copy raw device memory into a NumPy array through a uint8 torch view of the pointer."""
+    view = _tensor_from_ptr(torch, dev_ptr, nbytes, device)
+    host.view(np.uint8).reshape(-1)[:] = view.cpu().numpy()
+
+
+def _tensor_from_ptr(torch, dev_ptr, nbytes, device):
+    """uint8 CUDA tensor aliasing [dev_ptr, dev_ptr+nbytes) via the CUDA array interface."""
+
+    class _Holder(object):
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(dev_ptr), False),
+                                  "version": 2}
+    return torch.as_tensor(h, device=device)

@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: sharding, the factor broadcast helper and the
+arg-best exchange.  The data path itself has no collective."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from safe_exploration_b200 import distributed as sd
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 8, 4096, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [sd.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a0, a1), (b0, b1) in zip(spans[:-1], spans[1:]):
+                assert a1 == b0
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sd.shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = sd.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    # "factor" buffers: rank 0 holds the truth, the others receive it with one broadcast per buffer
+    rng = np.random.RandomState(0)
+    truth = [rng.randn(64, 64), rng.randn(128), rng.randn(2)]
+    bufs = [torch.from_numpy(t.copy()) if rank == 0 else torch.zeros(t.shape, dtype=torch.float64) for t in truth]
+    sd.broadcast_buffers(bufs, src=0)
+    ok = all(np.array_equal(b.numpy(), t) for b, t in zip(bufs, truth))
+    # sharded candidates: every rank scores its shard, the best of all ranks is agreed on
+    total = 1001
+    cost = np.random.RandomState(1).rand(total)
+    cost[3] = np.nan                                        # a diverged candidate must never win
+    s0, s1 = sd.shard_range(total, rank, world)
+    local = cost[s0:s1]
+    j = int(np.nanargmin(local))
+    best_cost, best_idx, best_rank = sd.argmin_across_ranks(local[j], s0 + j)
+    ok = ok and best_idx == int(np.nanargmin(cost)) and abs(best_cost - np.nanmin(cost)) == 0.0
+    ok = ok and sd.max_across_ranks(float(rank + 1)) == float(world)
+    dist.barrier()
+    with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_broadcast_and_argmin_world_size_2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(str(tmp_path), "ok%d" % r)).read() == "1"

@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> ctypes -> C ABI of libsegp.so) against
+
+* the golden vectors the reference's own functions produced (tests/golden/, oracle/make_golden.py),
+* the float64 CPU oracle (oracle/) on the same seeded inputs, at sizes the oracle finishes in seconds,
+* size-independent properties at the benchmark sizes.
+
+Tolerance: BASELINE.json's rtol 1e-4 on predictive mean/variance and on (p, Q), with the reference's own
+atol (1e-6 on GP outputs, test/test_gp_models.py:22-23; 1e-5 on ellipsoids, test_gp_reachability_casadi.py:25-26)
+scaled to the data.  The float64 pipeline is in practice ~1e-9 or better, and the tests assert a much tighter
+bound (RTOL_TIGHT) where conditioning allows so regressions show up long before the 1e-4 gate.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4          # the gate of BASELINE.json
+RTOL_TIGHT = 1e-7    # what the float64 path is expected to deliver on (p, Q)
+
+
+@pytest.fixture(scope="module")
+def se():
+    import safe_exploration_b200 as pkg
+    pkg._lib.load()
+    return pkg
+
+
+def _make_models(se, x, y, n_s_in, n_u, kern_types, ls, var, noise_total):
+    from oracle.gp_oracle import GPOracle
+    # the product adds noise_diag + jitter itself; subtract them so both sides factorise the same matrix
+    hyp = [{"lengthscale": ls[d], "variance": float(var[d]), "noise": float(noise_total[d]) - 1e-5 - 1e-8}
+           for d in range(len(var))]
+    gp = se.BatchedGPSSM(y.shape[1], n_s_in, n_u, x, y, kern_types=kern_types, hyp=hyp)
+    ora = GPOracle(x, y, kern_types, ls, var, gp.total_noise())
+    return gp, ora
+
+
+def _gp_from_golden(se, g, n_u=1):
+    kern = [str(k) for k in g["kern_types"]]
+    n_s = g["y_train"].shape[1]
+    return _make_models(se, g["x_train"], g["y_train"], n_s, g["x_train"].shape[1] - n_s, kern, g["lengthscale"],
+                        g["variance"], g["noise"])
+
+
+def _assert_close(got, want, rtol, atol_scale=1e-9, what=""):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    atol = atol_scale * max(1.0, float(np.max(np.abs(want))))
+    err = np.max(np.abs(got - want) / (atol / rtol + np.abs(want))) if want.size else 0.0
+    assert np.allclose(got, want, rtol=rtol, atol=atol), "{}: max scaled rel err {:.3e}".format(what, err)
+
+
+# =========================================================================== golden vectors (reference outputs)
+def test_golden_invpend_c1(se, golden_dir):
+    """BASELINE config C1: N=50, H=5, reference fixture data, point start."""
+    g = np.load(os.path.join(golden_dir, "invpend_c1.npz"))
+    gp, _ = _gp_from_golden(se, g)
+    c = float(g["c_safety"])
+    # batched call
+    p_new, q_new, p_all, q_all = se.multistep_reachability(g["p0"], gp, g["k_fb"], g["k_ff"], g["l_mu"],
+                                                           g["l_sigma"], None, c)
+    _assert_close(p_all, g["p_all"], RTOL_TIGHT, what="p_all")
+    _assert_close(q_all, g["q_all"], RTOL_TIGHT, what="q_all")
+    assert np.array_equal(p_new, p_all[:, -1]) and np.array_equal(q_new, q_all[:, -1])
+    # the reference's un-batched call shape
+    for i in range(g["k_ff"].shape[0]):
+        p_n, q_n, p_a, q_a = se.multistep_reachability(g["p0"][:, None], gp, g["k_fb"], g["k_ff"][i], g["l_mu"],
+                                                       g["l_sigma"], None, c)
+        assert p_n.shape == (2, 1) and q_n.shape == (2, 2) and p_a.shape == (5, 2) and q_a.shape == (5, 2, 2)
+        _assert_close(p_a, g["p_all"][i], RTOL_TIGHT)
+        _assert_close(q_a, g["q_all"][i], RTOL_TIGHT)
+
+
+def test_golden_invpend_reach_test(se, golden_dir):
+    """The reference's test_gp_reachability_casadi.py recipe: onestep (both branches, with and without the
+    linear prior), multistep T=3 with per-step gains, safety distance."""
+    g = np.load(os.path.join(golden_dir, "invpend_reach_test.npz"))
+    gp, _ = _gp_from_golden(se, g)
+    c = float(g["c_safety"])
+    for tag, a, b in (("lin", g["a"], g["b"]), ("nolin", None, None)):
+        p1, q1 = se.onestep_reachability(g["p"], gp, g["k_ff"], g["l_mu"], g["l_sigma"], g["q"], g["k_fb"], c, 0,
+                                         a=a, b=b)
+        assert p1.shape == (2, 1) and q1.shape == (2, 2)
+        _assert_close(p1, g["p1_set_" + tag], RTOL_TIGHT, what="p1 set " + tag)
+        _assert_close(q1, g["q1_set_" + tag], RTOL_TIGHT, what="q1 set " + tag)
+        p1, q1 = se.onestep_reachability(g["p"], gp, g["k_ff"], g["l_mu"], g["l_sigma"], None, g["k_fb"], c, 0,
+                                         a=a, b=b)
+        _assert_close(p1, g["p1_point_" + tag], RTOL_TIGHT, what="p1 point " + tag)
+        _assert_close(q1, g["q1_point_" + tag], RTOL_TIGHT, what="q1 point " + tag)
+    _, _, p_all, q_all = se.multistep_reachability(g["p"], gp, g["k_fb_multi"], g["k_ff_multi"], g["l_mu"],
+                                                   g["l_sigma"], None, c, 0, g["a"], g["b"], None)
+    _assert_close(p_all, g["p_all"], RTOL_TIGHT, what="multistep p_all")
+    _assert_close(q_all, g["q_all"], RTOL_TIGHT, what="multistep q_all")
+    dist = se.lin_ellipsoid_safety_distance(g["p_all"][-1][:, None], g["q_all"][-1], g["h_mat"], g["h_vec"], c)
+    assert dist.shape == g["dist"].shape
+    _assert_close(dist, g["dist"], 1e-10, what="safety distance")
+    dist_b = se.lin_ellipsoid_safety_distance(g["p_all"], g["q_all"], g["h_mat"], g["h_vec"], c)
+    _assert_close(dist_b[-1], g["dist"][:, 0], 1e-10)
+
+
+def test_golden_cartpole(se, golden_dir):
+    """Cart-pole fixture, mixed rbf / mat52 kernels, per-trajectory gains; with and without q_0."""
+    g = np.load(os.path.join(golden_dir, "cartpole.npz"))
+    gp, _ = _gp_from_golden(se, g)
+    _, _, p_all, q_all = se.multistep_reachability(g["p0"], gp, g["k_fb"], g["k_ff"], g["l_mu"], g["l_sigma"], None,
+                                                   2.0, 0, g["a"], g["b"])
+    _assert_close(p_all, g["p_all"], RTOL_TIGHT, what="p_all")
+    _assert_close(q_all, g["q_all"], RTOL_TIGHT, what="q_all")
+    _, _, p_all, q_all = se.multistep_reachability(g["p0"], gp, g["k_fb"], g["k_ff"], g["l_mu"], g["l_sigma"],
+                                                   g["q0"], 1.5, 0, g["a"], g["b"], g["k_fb_init"])
+    _assert_close(p_all, g["p_all_q0"], RTOL_TIGHT, what="p_all q0")
+    _assert_close(q_all, g["q_all_q0"], RTOL_TIGHT, what="q_all q0")
+
+
+def test_golden_ellipsoid_algebra(se, golden_dir):
+    """Reference outputs of compute_remainder_overapproximations (test_utils_casadi.py inputs, n_s up to 8),
+    sum_two_ellipsoids and ellipsoid_from_rectangle, plus the literal cases of test_utils_ellipsoid.py."""
+    from safe_exploration_b200.utils import compute_remainder_overapproximations
+    from safe_exploration_b200.utils_ellipsoid import ellipsoid_from_rectangle, sum_two_ellipsoids
+    g = np.load(os.path.join(golden_dir, "ellipsoid_algebra.npz"))
+    for tag in ("t_1", "t_2", "t_3", "t_4"):
+        u_mu, u_sig = compute_remainder_overapproximations(g[tag + "_q"], g[tag + "_k_fb"], g[tag + "_l_mu"],
+                                                           g[tag + "_l_sigma"])
+        _assert_close(u_mu, g[tag + "_u_mu"], 1e-11, what=tag + " u_mu")
+        _assert_close(u_sig, g[tag + "_u_sigma"], 1e-11, what=tag + " u_sigma")
+    for i in range(3):
+        p, q = sum_two_ellipsoids(g["s%d_p1" % i], g["s%d_q1" % i], g["s%d_p2" % i], g["s%d_q2" % i])
+        assert p.shape == g["s%d_p" % i].shape
+        _assert_close(p, g["s%d_p" % i], 1e-13)
+        _assert_close(q, g["s%d_q" % i], 1e-13)
+        _assert_close(ellipsoid_from_rectangle(g["s%d_ub" % i]), g["s%d_qrect" % i], 1e-14)
+    for tag in ("rectangle", "cube"):
+        _assert_close(ellipsoid_from_rectangle(g["rect_" + tag + "_ub"]), g["rect_" + tag + "_q"], 1e-14)
+    with pytest.raises(AssertionError):          # reference test/test_utils_ellipsoid.py:28-33
+        ellipsoid_from_rectangle([0.6, -0.3])
+    # batched leaves
+    qs = np.stack([g["t_2_q"], 2.0 * g["t_2_q"]])
+    um, us = compute_remainder_overapproximations(qs, g["t_2_k_fb"], g["t_2_l_mu"], g["t_2_l_sigma"])
+    _assert_close(um[0], g["t_2_u_mu"], 1e-11)
+    _assert_close(um[1], 2.0 * g["t_2_u_mu"], 1e-11)
+    _assert_close(us[1], np.sqrt(2.0) * g["t_2_u_sigma"], 1e-11)
+
+
+# =========================================================================== GP posterior vs the oracle
+@pytest.mark.parametrize("n,n_s,n_u,kerns,t", [
+    (50, 2, 1, ["rbf", "mat52"], 1),
+    (128, 3, 2, ["mat52", "rbf", "rbf"], 127),
+    (300, 4, 1, ["rbf", "mat52", "mat52", "rbf"], 129),
+    (700, 2, 1, ["rbf", "rbf"], 1000),
+])
+def test_predict_matches_oracle(se, n, n_s, n_u, kerns, t):
+    rng = np.random.RandomState(n + t)
+    dim = n_s + n_u
+    x = rng.uniform(-1, 1, size=(n, dim))
+    y = np.tanh(x @ rng.randn(dim, n_s)) + 0.05 * rng.randn(n, n_s)
+    ls = rng.uniform(0.7, 2.0, size=(n_s, dim))
+    var = rng.uniform(0.5, 1.5, size=n_s)
+    noise = rng.uniform(0.01, 0.05, size=n_s)
+    gp, ora = _make_models(se, x, y, n_s, n_u, kerns, ls, var, noise)
+    z = rng.uniform(-1, 1, size=(t, dim))
+    mu, sig2, jac = gp.predict(z, compute_gradients=True)
+    mu_o, var_o, jac_o = ora.predict_batch(z)
+    assert mu.shape == (t, n_s) and sig2.shape == (t, n_s) and jac.shape == (t, n_s, dim)
+    _assert_close(mu, mu_o, RTOL, atol_scale=1e-6, what="mean")       # the gate
+    _assert_close(sig2, var_o, RTOL, atol_scale=1e-6, what="variance")
+    _assert_close(mu, mu_o, 1e-6, atol_scale=1e-9, what="mean (tight)")
+    _assert_close(sig2, var_o, 1e-6, atol_scale=1e-10, what="variance (tight)")
+    _assert_close(jac, jac_o, 1e-6, atol_scale=1e-8, what="jacobian")
+    # ABC spelling and the single-point __call__ triple (gp_reachability.py:74,101)
+    mu2, var2 = gp.predict(z[:, :n_s], z[:, n_s:])
+    assert np.array_equal(mu2, mu) and np.array_equal(var2, sig2)
+    m1, v1, j1 = gp(z[:1, :n_s], z[:1, n_s:])
+    assert m1.shape == (n_s, 1) and v1.shape == (n_s, 1) and j1.shape == (n_s, dim)
+    _assert_close(m1[:, 0], mu_o[0], 1e-6, atol_scale=1e-9)
+    # beta and log-determinant of the factorisation
+    _assert_close(gp.beta, ora.beta, 1e-6, atol_scale=1e-7, what="beta")
+    logdet_o = np.array([2.0 * np.sum(np.log(np.diag(l))) for l in ora.chol])
+    _assert_close(gp.log_det_k(), logdet_o, 1e-10, what="logdet")
+    gp.close()
+
+
+def test_predict_at_training_inputs_identity(se):
+    """Size-independent property that checks potrf + trtri without an oracle: at a training input,
+    mean_i = y_i - noise * beta_i (K beta = y - noise beta)."""
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C3", batch=1)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    idx = np.arange(0, w.n_train, 7)
+    mu, var = gp.predict(w.x_train[idx])
+    want = w.y_train[idx] - gp.total_noise()[None, :] * gp.beta[idx]
+    _assert_close(mu, want, 1e-6, atol_scale=1e-8, what="mean at training inputs")
+    assert np.all(var > 0) and np.all(var < gp.total_noise()[None, :])
+    gp.close()
+
+
+# =========================================================================== rollouts vs the batch oracle
+def _rollout_vs_oracle(se, w, t_z_gp=None, q0=None, k_fb_init=None, per_traj_kfb=False, rtol=RTOL_TIGHT):
+    from oracle import reach_oracle
+    from oracle.gp_oracle import GPOracle
+    n_in = w.n_s if t_z_gp is None else t_z_gp.shape[0]
+    x = w.x_train if t_z_gp is None else np.hstack((w.x_train[:, :w.n_s] @ t_z_gp.T, w.x_train[:, w.n_s:]))
+    hyp = w.hyp if t_z_gp is None else [
+        {"lengthscale": np.concatenate((h["lengthscale"][:n_in], h["lengthscale"][w.n_s:])), "variance": h["variance"],
+         "noise": h["noise"]} for h in w.hyp]
+    gp = se.BatchedGPSSM(w.n_s, n_in, w.n_u, x, w.y_train, kern_types=w.kern_types, hyp=hyp)
+    ora = GPOracle(x, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in hyp]),
+                   [h["variance"] for h in hyp], gp.total_noise())
+    k_fb = w.k_fb
+    if per_traj_kfb:
+        rng = np.random.RandomState(5)
+        k_fb = w.k_fb[None] * (1.0 + 0.05 * rng.randn(w.batch, 1, 1, 1))
+    res = se.rollout(gp, w.p0, w.k_ff, k_fb, w.l_mu, w.l_sigma, q0, k_fb_init, w.c_safety, w.a, w.b, t_z_gp)
+    p_o, q_o, v_o = reach_oracle.multistep_batch(w.p0, ora, k_fb, w.k_ff, w.l_mu, w.l_sigma, q0, w.c_safety, w.a, w.b,
+                                                 k_fb_init, t_z_gp)
+    assert np.all(res.status == 0)
+    assert np.all(np.isfinite(q_o))
+    _assert_close(res.var_all, v_o, RTOL, atol_scale=1e-6, what="variance (gate)")
+    _assert_close(res.p_all, p_o, RTOL, atol_scale=1e-5, what="p_all (gate)")
+    _assert_close(res.q_all, q_o, RTOL, atol_scale=1e-5, what="q_all (gate)")
+    _assert_close(res.var_all, v_o, 1e-6, atol_scale=1e-10, what="variance (tight)")
+    _assert_close(res.p_all, p_o, rtol, what="p_all (tight)")
+    _assert_close(res.q_all, q_o, rtol, what="q_all (tight)")
+    return gp, res
+
+
+def test_rollout_c2_full_size(se):
+    """BASELINE config C2 (pendulum, N=500, H=10) on 512 of its candidates, every step of every trajectory."""
+    from safe_exploration_b200 import workloads
+    gp, _ = _rollout_vs_oracle(se, workloads.make("C2", batch=512))
+    gp.close()
+
+
+def test_rollout_c3_model_size(se):
+    """BASELINE config C3 (cart-pole, Matern-5/2, N=2000, H=15) on 192 candidates (ragged vs the 128 tile)."""
+    from safe_exploration_b200 import workloads
+    gp, _ = _rollout_vs_oracle(se, workloads.make("C3", batch=192), rtol=1e-6)
+    gp.close()
+
+
+def test_rollout_c5_shape_reduced(se):
+    """The 10-D / 3-action shape of C5 (generic n_s path of the ellipsoid kernel) at N=600, H=6."""
+    from safe_exploration_b200 import workloads
+    gp, _ = _rollout_vs_oracle(se, workloads.make("C5", batch=70, n_train=600, horizon=6), rtol=1e-6)
+    gp.close()
+
+
+def test_rollout_with_q0_per_trajectory_gains_and_input_transform(se):
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C3", batch=33, n_train=400, horizon=5)
+    q0 = 1e-3 * np.array([[2., .3, 0., .1], [.3, 1., .2, 0.], [0., .2, 1.5, .4], [.1, 0., .4, 1.]])
+    gp, _ = _rollout_vs_oracle(se, w, q0=q0, k_fb_init=w.k_fb[0], per_traj_kfb=True, rtol=1e-6)
+    gp.close()
+    # GP sees only (vel, theta, omega): t_z_gp drops the cart position (reference defaultconfig_episode.py:44)
+    t = np.eye(4)[1:]
+    gp, _ = _rollout_vs_oracle(se, w, t_z_gp=t, rtol=1e-6)
+    gp.close()
+
+
+def test_rollout_is_deterministic_chunk_and_order_invariant(se):
+    """Bit-exact properties: same call twice; chunk size 128 vs default; reversed candidate order; device
+    tensors vs host buffers."""
+    import torch
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C2", batch=300)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    args = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    r1 = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
+    r2 = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
+    assert np.array_equal(r1.q_all, r2.q_all) and np.array_equal(r1.p_all, r2.p_all)
+    gp.set_option("chunk", 128)
+    r3 = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
+    assert np.array_equal(r1.q_all, r3.q_all) and np.array_equal(r1.p_all, r3.p_all)
+    gp.set_option("chunk", 8192)
+    r4 = se.rollout(gp, w.p0, w.k_ff[::-1].copy(), w.k_fb, *args)
+    assert np.array_equal(r1.q_all, r4.q_all[::-1]) and np.array_equal(r1.var_all, r4.var_all[::-1])
+    dev = gp.device
+    r5 = se.rollout(gp, torch.as_tensor(w.p0, device=dev), torch.as_tensor(w.k_ff, device=dev),
+                    torch.as_tensor(w.k_fb, device=dev), *args)
+    assert np.array_equal(r5.q_all.cpu().numpy(), r1.q_all) and np.array_equal(r5.p_all.cpu().numpy(), r1.p_all)
+    assert int(r5.status.abs().sum().item()) == 0
+    assert gp.get_option("launches") > 0
+    gp.close()
+
+
+def test_multistep_first_step_equals_onestep_and_horizon_prefix(se):
+    """Structural property at any size: the first H' steps of an H-step rollout equal an H'-step rollout, and
+    step t+1 equals onestep_reachability applied to step t's ellipsoid."""
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C3", batch=40, n_train=500, horizon=6)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    _, _, p_all, q_all = se.multistep_reachability(w.p0, gp, w.k_fb, w.k_ff, w.l_mu, w.l_sigma, None, w.c_safety, 0,
+                                                   w.a, w.b)
+    _, _, p3, q3 = se.multistep_reachability(w.p0, gp, w.k_fb[:2], w.k_ff[:, :3], w.l_mu, w.l_sigma, None,
+                                             w.c_safety, 0, w.a, w.b)
+    assert np.array_equal(p3, p_all[:, :3]) and np.array_equal(q3, q_all[:, :3])
+    p1, q1 = se.onestep_reachability(p_all[:, 2], gp, w.k_ff[:, 3], w.l_mu, w.l_sigma, q_all[:, 2], w.k_fb[2],
+                                     w.c_safety, 0, w.a, w.b)
+    assert np.array_equal(p1, p_all[:, 3]) and np.array_equal(q1, q_all[:, 3])
+    gp.close()
+
+
+def test_foreign_ssm_uses_ellipsoid_step(se):
+    """Any callable with the reference's plugin signature works: here the CPU oracle GP is the 'foreign' model and
+    only the ellipsoid algebra runs on the GPU."""
+    from oracle import reach_oracle
+    from oracle.gp_oracle import GPOracle
+    rng = np.random.RandomState(3)
+    n_s, n_u, n = 3, 2, 40
+    x = rng.uniform(-1, 1, size=(n, n_s + n_u))
+    y = np.tanh(x @ rng.randn(n_s + n_u, n_s))
+    ora = GPOracle(x, y, ["rbf", "mat52", "rbf"], rng.uniform(0.7, 2, size=(n_s, n_s + n_u)),
+                   rng.uniform(0.5, 1.5, size=n_s), rng.uniform(0.01, 0.05, size=n_s))
+    m = rng.randn(n_s, n_s)
+    q = 0.05 * (m @ m.T + 0.1 * np.eye(n_s))
+    p = 0.1 * rng.randn(n_s, 1)
+    k_fb = 0.5 * rng.randn(n_u, n_s)
+    k_ff = 0.2 * rng.randn(n_u, 1)
+    l_mu = rng.uniform(1e-3, 5e-2, n_s)
+    l_sig = rng.uniform(1e-3, 5e-2, n_s)
+    a = np.eye(n_s) + 0.1 * rng.randn(n_s, n_s)
+    b = rng.randn(n_s, n_u)
+    for qq in (q, None):
+        p1, q1 = se.onestep_reachability(p, ora, k_ff, l_mu, l_sig, qq, k_fb, 1.7, 0, a, b)
+        po, qo = reach_oracle.onestep_reachability(p, ora, k_ff, l_mu, l_sig, qq, k_fb, 1.7, 0, a, b)
+        _assert_close(p1, po, 1e-12)
+        _assert_close(q1, qo, 1e-11)
+    hor = 4
+    kfb = 0.5 * rng.randn(hor - 1, n_u, n_s)
+    kff = 0.2 * rng.randn(hor, n_u)
+    _, _, pa, qa = se.multistep_reachability(p, ora, kfb, kff, l_mu, l_sig, None, 2.0, 0, a, b, None)
+    _, _, pa_o, qa_o = reach_oracle.multistep_reachability(p, ora, kfb, kff, l_mu, l_sig, None, 2.0, 0, a, b, None)
+    _assert_close(pa, pa_o, 1e-10)
+    _assert_close(qa, qa_o, 1e-10)
+
+
+# =========================================================================== error behaviour
+def test_error_mapping_and_status_flags(se):
+    from safe_exploration_b200 import workloads
+    rng = np.random.RandomState(0)
+    x = rng.uniform(-1, 1, size=(30, 3))
+    y = rng.randn(30, 2)
+    # a non-finite kernel matrix has no Cholesky factor -> LinAlgError, as numpy/LAPACK raise in the reference
+    xd = x.copy()
+    xd[7, 1] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        se.BatchedGPSSM(2, 2, 1, xd, y)
+    with pytest.raises(NotImplementedError):
+        se.BatchedGPSSM(2, 2, 1, x, y, kern_types=["lin_rbf", "rbf"])
+    with pytest.raises(ValueError):
+        se.BatchedGPSSM(2, 2, 1, x, y, kern_types=["rbf", "nope"])
+    gp = se.BatchedGPSSM(2, 2, 1)
+    with pytest.raises(RuntimeError):
+        gp.predict(x)
+    with pytest.raises(NotImplementedError):
+        gp.update_model(x, y, opt_hyp=True)
+    gp.update_model(x, y)
+    gp.update_model(x[:5] + 0.3, y[:5], replace_old=False)
+    assert gp.x_train.shape[0] == 35
+    # zero Lipschitz constant -> the reference's ellipsoid_from_rectangle assertion; batch mode flags it instead
+    w = workloads.make("C2", batch=5, n_train=60, horizon=3)
+    gp2 = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    res = se.rollout(gp2, w.p0, w.k_ff, w.k_fb, np.zeros(2), w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    assert np.all(res.status & se._lib.STATUS_ZERO_BOUND)
+    with pytest.raises(AssertionError):
+        se.multistep_reachability(w.p0[:, None], gp2, w.k_fb, w.k_ff[0], np.zeros(2), w.l_sigma, None, w.c_safety)
+    with pytest.raises(ValueError):
+        se.rollout(gp2, w.p0, w.k_ff[:, :, :0], w.k_fb, w.l_mu, w.l_sigma)
+    # empty batch is a no-op
+    res = se.rollout(gp2, w.p0, w.k_ff[:0], w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    assert res.p_all.shape == (0, 3, 2)
+    gp.close()
+    gp2.close()
