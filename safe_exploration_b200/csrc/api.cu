@@ -66,10 +66,15 @@ struct segp_model {
     double* beta = nullptr;    // [n_s][n_pad]
     double* wt = nullptr;      // [n_s][ntri][128*128]
     double* logdet = nullptr;  // [n_s]
+    int8_t* wi8 = nullptr;     // [n_s][nblk (nblk+1)][I8_S][I8_A_TILE] digit planes of W (tcgen05 path)
+    double* rowfac = nullptr;  // [n_s][n_pad] per-row factors of the digit planes
     // workspace
     long b_cap = 0;
     int nsplit = 1, blocks_per_split = 1;
-    double* ks = nullptr;
+    double* ks = nullptr;      // fp64 K* block (DMMA path)
+    int8_t* ki8 = nullptr;     // digit planes of the K* block (tcgen05 path)
+    long npanel_cap = 0;
+    bool ws_i8 = false;        // which of ks / ki8 the current workspace holds
     double* mu_part = nullptr;
     double* jac_part = nullptr;
     double* qpart = nullptr;
@@ -82,6 +87,7 @@ struct segp_model {
     long opt_chunk = 8192;
     long opt_panel_group = 16;
     long opt_ksplit = 0;   // 0 = automatic
+    long opt_tri_mode = -1;   // -1 = automatic (int8 tcgen05 when n_pad <= I8_MAX_NPAD), 0 = fp64 DMMA, 1 = int8 tcgen05
     long launches = 0;
     // optional per-launch timing of tri_sumsq (bench.py roofline): event pairs recorded on the launching stream
     bool time_tri = false;
@@ -99,11 +105,15 @@ static void free_model_buffers(segp_model* m) {
     dev_free(m->beta);
     dev_free(m->wt);
     dev_free(m->logdet);
+    dev_free(m->wi8);
+    dev_free(m->rowfac);
     m->factorized = false;
 }
 
 static void free_workspace(segp_model* m) {
     dev_free(m->ks);
+    dev_free(m->ki8);
+    m->npanel_cap = 0;
     dev_free(m->mu_part);
     dev_free(m->jac_part);
     dev_free(m->qpart);
@@ -111,9 +121,21 @@ static void free_workspace(segp_model* m) {
     m->workspace_bytes = 0;
 }
 
+static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD; }
+static bool use_i8(const segp_model* m) {
+    return m->opt_tri_mode == 1 || (m->opt_tri_mode < 0 && i8_capable(m));
+}
+
 static int ensure_workspace(segp_model* m, long n_batch) {
+    constexpr long ALIGN = 384;   // lcm of the DMMA tile (128 columns) and the tcgen05 panel (96 columns)
     long want = std::min<long>(m->opt_chunk, n_batch);
-    want = (want + TILE - 1) / TILE * TILE;
+    want = (want + ALIGN - 1) / ALIGN * ALIGN;
+    const bool i8 = use_i8(m);
+    if (i8 && m->wi8 == nullptr) {
+        set_error("tri_mode=1 (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", I8_MAX_NPAD, m->n_pad);
+        return SEGP_ERR_UNSUPPORTED;
+    }
+    if (i8 != m->ws_i8 && m->b_cap > 0) free_workspace(m);
     // split of the N-length reductions of kstar_mean_jac over blockIdx.z so small batches still fill 148 SMs
     const long col_blocks = want / TILE;
     int nsplit;
@@ -133,17 +155,23 @@ static int ensure_workspace(segp_model* m, long n_batch) {
         return SEGP_OK;
     }
     free_workspace(m);
-    const size_t n_ks = (size_t)m->n_s * m->n_pad * want;
+    const size_t n_ks = i8 ? 0 : (size_t)m->n_s * m->n_pad * want;
+    const long npanel_cap = want / I8_N;
+    const size_t n_ki8 = i8 ? (size_t)m->n_s * npanel_cap * (m->n_pad / I8_KB) * (I8_S * I8_B_TILE) : 0;
     const size_t n_mu = (size_t)m->nblk * m->n_s * want;
     const size_t n_jac = n_mu * m->dim;
     const size_t n_q = (size_t)m->n_s * m->nblk * want;
     SEGP_CHECK(dev_alloc(&m->ks, n_ks));
+    SEGP_CHECK(dev_alloc(&m->ki8, n_ki8));
     SEGP_CHECK(dev_alloc(&m->mu_part, n_mu));
     SEGP_CHECK(dev_alloc(&m->jac_part, n_jac));
     SEGP_CHECK(dev_alloc(&m->qpart, n_q));
-    SEGP_CUDA_CHECK(cudaMemset(m->ks, 0, n_ks * sizeof(double)));
-    m->workspace_bytes = (n_ks + n_mu + n_jac + n_q) * sizeof(double);
+    if (n_ks > 0) SEGP_CUDA_CHECK(cudaMemset(m->ks, 0, n_ks * sizeof(double)));
+    if (n_ki8 > 0) SEGP_CUDA_CHECK(cudaMemset(m->ki8, 0, n_ki8));
+    m->workspace_bytes = (n_ks + n_mu + n_jac + n_q) * sizeof(double) + n_ki8;
     m->b_cap = want;
+    m->npanel_cap = npanel_cap;
+    m->ws_i8 = i8;
     m->nsplit = nsplit;
     m->blocks_per_split = bps;
     return SEGP_OK;
@@ -207,7 +235,20 @@ static KstarArgs base_kstar_args(const segp_model* m) {
     return k;
 }
 
-// tri_sumsq launch, optionally bracketed by a CUDA-event pair on the launching stream
+// K* block (+ mean / Jacobian partials) in the operand format of the active contraction kernel
+static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st) {
+    if (m->ws_i8) {
+        KstarI8Args k8{};
+        k8.k = k;
+        k8.ki8 = m->ki8;
+        k8.npanel_cap = m->npanel_cap;
+        return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
+    }
+    return launch_kstar(k, m->n_s, m->nsplit, st);
+}
+
+// variance contraction launch (tri_i8 on tcgen05 or tri_sumsq on the DMMA pipe), optionally bracketed by a
+// CUDA-event pair on the launching stream
 static int run_tri(segp_model* m, long nb, cudaStream_t st) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->time_tri) {
@@ -221,16 +262,31 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st) {
         m->tri_events_used += 2;
         SEGP_CUDA_CHECK(cudaEventRecord(e0, st));
     }
-    TriArgs t{};
-    t.wt = m->wt;
-    t.ks = m->ks;
-    t.qpart = m->qpart;
-    t.nblk = m->nblk;
-    t.npanels = (int)((nb + TILE - 1) / TILE);
-    t.group = (int)std::max<long>(1, std::min<long>(m->opt_panel_group, t.npanels));
-    t.b_cap = m->b_cap;
-    t.ntri = m->ntri;
-    SEGP_CHECK(launch_tri_sumsq(t, m->n_s, st));
+    if (m->ws_i8) {
+        TriI8Args t{};
+        t.wi8 = m->wi8;
+        t.rowfac = m->rowfac;
+        t.ki8 = m->ki8;
+        t.qpart = m->qpart;
+        t.nblk = m->nblk;
+        t.npanels = (int)((nb + I8_N - 1) / I8_N);
+        t.npanel_cap = m->npanel_cap;
+        t.b_cap = m->b_cap;
+        t.dbg = nullptr;
+        t.fix_bi = -1;
+        SEGP_CHECK(launch_tri_i8(t, m->n_s, st));
+    } else {
+        TriArgs t{};
+        t.wt = m->wt;
+        t.ks = m->ks;
+        t.qpart = m->qpart;
+        t.nblk = m->nblk;
+        t.npanels = (int)((nb + TILE - 1) / TILE);
+        t.group = (int)std::max<long>(1, std::min<long>(m->opt_panel_group, t.npanels));
+        t.b_cap = m->b_cap;
+        t.ntri = m->ntri;
+        SEGP_CHECK(launch_tri_sumsq(t, m->n_s, st));
+    }
     if (e1 != nullptr) SEGP_CUDA_CHECK(cudaEventRecord(e1, st));
     return SEGP_OK;
 }
@@ -278,6 +334,7 @@ int segp_create(segp_model** out, int device, int n_s_out, int n_s_in, int n_u, 
         return SEGP_ERR_UNSUPPORTED;
     }
     SEGP_CHECK(tri_sumsq_init());
+    SEGP_CHECK(tri_i8_init());
     segp_model* m = new (std::nothrow) segp_model();
     if (m == nullptr) {
         set_error("out of host memory");
@@ -373,12 +430,17 @@ int segp_alloc_factor_buffers(segp_model* m) {
     if (m->wt == nullptr) SEGP_CHECK(dev_alloc(&m->wt, (size_t)m->n_s * m->ntri * TILE * TILE));
     if (m->beta == nullptr) SEGP_CHECK(dev_alloc(&m->beta, (size_t)m->n_s * m->n_pad));
     if (m->logdet == nullptr) SEGP_CHECK(dev_alloc(&m->logdet, (size_t)m->n_s));
+    if (i8_capable(m)) {
+        if (m->wi8 == nullptr)
+            SEGP_CHECK(dev_alloc(&m->wi8, (size_t)m->n_s * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE)));
+        if (m->rowfac == nullptr) SEGP_CHECK(dev_alloc(&m->rowfac, (size_t)m->n_s * m->n_pad));
+    }
     return SEGP_OK;
 }
 
 int segp_num_factor_buffers(segp_model* m) {
-    (void)m;
-    return 3;
+    if (m == nullptr) return 0;
+    return i8_capable(m) ? 5 : 3;
 }
 
 int segp_factor_buffer(segp_model* m, int index, void** d_ptr, size_t* bytes) {
@@ -399,6 +461,20 @@ int segp_factor_buffer(segp_model* m, int index, void** d_ptr, size_t* bytes) {
             *d_ptr = m->logdet;
             *bytes = (size_t)m->n_s * sizeof(double);
             return SEGP_OK;
+        case 3:
+            if (m->wi8 != nullptr) {
+                *d_ptr = m->wi8;
+                *bytes = (size_t)m->n_s * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE);
+                return SEGP_OK;
+            }
+            [[fallthrough]];
+        case 4:
+            if (index == 4 && m->rowfac != nullptr) {
+                *d_ptr = m->rowfac;
+                *bytes = (size_t)m->n_s * m->n_pad * sizeof(double);
+                return SEGP_OK;
+            }
+            [[fallthrough]];
         default:
             set_error("segp_factor_buffer: index %d out of range", index);
             return SEGP_ERR_INVALID;
@@ -456,6 +532,12 @@ int segp_factorize(segp_model* m, void* stream) {
             m->launches += 3;
             if ((rc = pack_w(wbuf, m->wt + (size_t)d * m->ntri * TILE * TILE, m->n_pad, st)) != SEGP_OK) break;
             ++m->launches;
+            if (m->wi8 != nullptr) {
+                if ((rc = pack_w_i8(wbuf, m->wi8 + (size_t)d * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE),
+                                    m->rowfac + (size_t)d * m->n_pad, m->h_var[d], m->n_pad, st)) != SEGP_OK)
+                    break;
+                m->launches += 2;
+            }
         }
         if (rc != SEGP_OK) break;
         cudaError_t e = cudaStreamSynchronize(st);
@@ -508,7 +590,7 @@ int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, d
         KstarArgs k = base_kstar_args(m);
         k.z = d_z + c0 * m->dim;
         k.n_batch = nb;
-        SEGP_CHECK(launch_kstar(k, m->n_s, m->nsplit, st));
+        SEGP_CHECK(run_kstar(m, k, st));
         SEGP_CHECK(run_tri(m, nb, st));
         FinalizeArgs f{};
         f.mu_part = m->mu_part;
@@ -577,7 +659,7 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
             k.kff_stride = (long)horizon * n_u;
             k.sp = m->d_sp;
             k.n_batch = nb;
-            SEGP_CHECK(launch_kstar(k, n_s, m->nsplit, st));
+            SEGP_CHECK(run_kstar(m, k, st));
             SEGP_CHECK(run_tri(m, nb, st));
 
             StepArgs s{};
@@ -834,6 +916,98 @@ int segp_safety_distance(int device, long n_items, int n_s, int m, const double*
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------- tcgen05 diagnostics
+int segp_i8_peak(int device, int umma_n, int iters, double* tops) {
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("segp_i8_peak: cudaSetDevice(%d) failed", device);
+        return SEGP_ERR_CUDA;
+    }
+    return i8_peak(umma_n, iters, tops);
+}
+
+int segp_i8_selftest(int device, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc, double* h_colsum) {
+    if (k_blocks < 1 || k_blocks > 64 || h_a == nullptr || h_b == nullptr || h_acc == nullptr || h_colsum == nullptr) {
+        set_error("segp_i8_selftest: bad argument");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("segp_i8_selftest: cudaSetDevice(%d) failed", device);
+        return SEGP_ERR_CUDA;
+    }
+    SEGP_CHECK(tri_i8_init());
+    // one tile: block row bi = k_blocks - 1 of a (128 k_blocks)-point model, panel 0; K = 128 k_blocks
+    const int bi = k_blocks - 1, nblk = k_blocks, kdim = TILE * k_blocks, nkb = 2 * k_blocks;
+    const size_t a_bytes = (size_t)nblk * (nblk + 1) * (I8_S * I8_A_TILE);
+    const size_t b_bytes = (size_t)nkb * (I8_S * I8_B_TILE);
+    std::vector<int8_t> a_img(a_bytes, 0), b_img(b_bytes, 0);
+    // same image format as pack_w_i8_kernel / kstar_i8_kernel: [k-block][plane][row][64 B, SWIZZLE_64B]
+    for (int kb = 0; kb < nkb; ++kb)
+        for (int pl = 0; pl < I8_S; ++pl) {
+            int8_t* at = a_img.data() + ((size_t)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE) + (size_t)pl * I8_A_TILE;
+            int8_t* bt = b_img.data() + (size_t)kb * (I8_S * I8_B_TILE) + (size_t)pl * I8_B_TILE;
+            for (int k = 0; k < I8_KB; ++k) {
+                for (int r = 0; r < TILE; ++r) {
+                    const int off = r * I8_KB + ((((k >> 4) ^ ((r >> 1) & 3)) << 4) | (k & 15));
+                    at[off] = h_a[((size_t)pl * TILE + r) * kdim + (size_t)kb * I8_KB + k];
+                }
+                for (int r = 0; r < I8_N; ++r) {
+                    const int off = r * I8_KB + ((((k >> 4) ^ ((r >> 1) & 3)) << 4) | (k & 15));
+                    bt[off] = h_b[((size_t)pl * I8_N + r) * kdim + (size_t)kb * I8_KB + k];
+                }
+            }
+        }
+    int8_t *d_a = nullptr, *d_b = nullptr;
+    double *d_rf = nullptr, *d_q = nullptr;
+    int32_t* d_dbg = nullptr;
+    const size_t n_dbg = (size_t)I8_S * TILE * I8_N;
+    int rc = SEGP_OK;
+    do {
+        if ((rc = dev_alloc(&d_a, a_bytes)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_b, b_bytes)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_rf, (size_t)kdim)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_q, (size_t)nblk * I8_N)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_dbg, n_dbg)) != SEGP_OK) break;
+        std::vector<double> ones((size_t)kdim, 1.0);
+        cudaError_t e = cudaMemcpy(d_a, a_img.data(), a_bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_b, b_img.data(), b_bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_rf, ones.data(), kdim * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(d_q, 0, (size_t)nblk * I8_N * sizeof(double));
+        if (e != cudaSuccess) {
+            set_error("segp_i8_selftest: %s", cudaGetErrorString(e));
+            rc = SEGP_ERR_CUDA;
+            break;
+        }
+        TriI8Args t{};
+        t.wi8 = d_a;
+        t.rowfac = d_rf;
+        t.ki8 = d_b;
+        t.qpart = d_q;
+        t.nblk = nblk;
+        t.npanels = 1;
+        t.npanel_cap = 1;
+        t.b_cap = I8_N;
+        t.dbg = d_dbg;
+        t.fix_bi = bi;
+        if ((rc = launch_tri_i8(t, 1, nullptr)) != SEGP_OK) break;
+        e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(h_acc, d_dbg, n_dbg * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(h_colsum, d_q + (size_t)bi * I8_N, I8_N * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("segp_i8_selftest: %s", cudaGetErrorString(e));
+            rc = SEGP_ERR_CUDA;
+        }
+    } while (0);
+    dev_free(d_a);
+    dev_free(d_b);
+    dev_free(d_rf);
+    dev_free(d_q);
+    dev_free(d_dbg);
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------- options
 int segp_set_option(segp_model* m, const char* name, long value) {
     if (m == nullptr || name == nullptr) {
@@ -855,6 +1029,14 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_ksplit = value;
         return SEGP_OK;
     }
+    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 1) {
+        if (value == 1 && m->has_data && !i8_capable(m)) {
+            set_error("tri_mode=1 (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", I8_MAX_NPAD, m->n_pad);
+            return SEGP_ERR_UNSUPPORTED;
+        }
+        m->opt_tri_mode = value;
+        return SEGP_OK;
+    }
     if (strcmp(name, "time_tri") == 0) {
         m->time_tri = value != 0;
         if (m->time_tri) m->tri_events_used = 0;
@@ -872,6 +1054,8 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     if (strcmp(name, "chunk") == 0) *value = m->opt_chunk;
     else if (strcmp(name, "panel_group") == 0) *value = m->opt_panel_group;
     else if (strcmp(name, "ksplit") == 0) *value = m->opt_ksplit;
+    else if (strcmp(name, "tri_mode") == 0) *value = m->opt_tri_mode;
+    else if (strcmp(name, "tri_mode_effective") == 0) *value = use_i8(m) ? 1 : 0;
     else if (strcmp(name, "launches") == 0) *value = m->launches;
     else if (strcmp(name, "n_train_padded") == 0) *value = m->n_pad;
     else if (strcmp(name, "workspace_bytes") == 0) *value = (long)m->workspace_bytes;

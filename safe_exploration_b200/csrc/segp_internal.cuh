@@ -80,6 +80,44 @@ struct TriArgs {
 int launch_tri_sumsq(const TriArgs& a, int n_s, cudaStream_t st);
 int tri_sumsq_init();   // sets the dynamic shared memory attribute once per device
 
+// ---------------------------------------------------------------- the same contraction on tcgen05 (int8 slices)
+// Ozaki-style error-free splitting: every row of W and every column of K* is scaled into [-1,1] and written as
+// I8_S balanced base-254 digits (int8, |digit| <= 127); digit planes are multiplied pairwise on the int8 tensor
+// pipe (tcgen05.mma kind::i8, exact int32 accumulation in TMEM), digit pairs (a,c) with a+c < I8_S only, one
+// TMEM accumulator per diagonal a+c; the epilogue recombines the diagonals exactly in int64 (Horner, base 254),
+// converts once to float64, squares and column-sums.  See DESIGN.md section 4.
+constexpr int I8_S = 5;        // digit planes per operand  -> 15 int8 products, ~2^-39 relative resolution
+constexpr int I8_N = 96;       // trajectories per panel (UMMA N); I8_S * I8_N = 480 <= 512 TMEM columns
+constexpr int I8_KB = 64;      // bytes (= training points) per k-block row: one SWIZZLE_64B atom
+constexpr int I8_A_TILE = TILE * I8_KB;    // 8192 B: 128 rows of W x 64 k, one digit plane, swizzled smem image
+constexpr int I8_B_TILE = I8_N * I8_KB;    // 6144 B: 96 trajectories x 64 k
+constexpr long I8_MAX_NPAD = 16384;        // int32 accumulators: 5 * 127^2 * n_pad < 2^31 and the int64 Horner bound
+constexpr double I8_BASE0 = 127.0;         // first digit scale
+constexpr double I8_BASE = 254.0;          // following digits
+
+struct KstarI8Args {
+    KstarArgs k;            // model, inputs and mean/Jacobian partial outputs (k.ks unused)
+    int8_t* ki8;            // [n_s][npanel_cap][n_pad/64][I8_S][I8_B_TILE]
+    long npanel_cap;
+};
+int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st);
+
+struct TriI8Args {
+    const int8_t* wi8;      // [n_s][nblk (nblk+1) k-blocks][I8_S][I8_A_TILE]   (block row bi starts at bi (bi+1))
+    const double* rowfac;   // [n_s][n_pad]   rowmax_i * var_d / (127^2 254^(S-1))
+    const int8_t* ki8;      // as above
+    double* qpart;          // [n_s][nblk][b_cap]
+    int nblk, npanels;
+    long npanel_cap, b_cap;
+    int32_t* dbg;           // optional raw accumulators [I8_S][128][I8_N] of tile (0, fix_bi, 0)
+    int fix_bi;             // >= 0: single-tile self-test mode
+};
+int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);
+int tri_i8_init();
+// W (n_pad x n_pad fp64, lower) -> digit planes + row factors for output dimension d
+int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int n_pad, cudaStream_t st);
+int i8_peak(int umma_n, int iters, double* tops);
+
 // ---------------------------------------------------------------- posterior finalise / ellipsoid step
 struct StepArgs {
     // GP outputs as partials (fused path) ...

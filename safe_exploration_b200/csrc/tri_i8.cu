@@ -1,0 +1,587 @@
+// The variance contraction |L_d^-1 K*_d[:,b]|^2 on the 5th-generation tensor cores (tcgen05, int8 -> int32 in TMEM).
+//
+// Why int8 and not bf16/tf32: sigma^2 = k** - |L^-1 k*|^2 cancels ~4 digits on the benchmark models, so the
+// contraction needs ~2^-36 relative accuracy -- out of reach of any fp32-accumulating pipe.
+// Integer accumulation is exact, so an error-free splitting (Ozaki scheme) recovers float64-grade results from
+// int8 products: every row of W = L^-1 and every column of K* is scaled into [-1, 1] and written as I8_S balanced
+// base-254 digits; the digit planes are multiplied pairwise (a + c < I8_S: 15 products) by tcgen05.mma kind::i8,
+// one TMEM accumulator per diagonal a + c, and the epilogue recombines the diagonals exactly in int64 before the
+// single conversion to float64.  Replaces, like tri_sumsq, `sum2(mtimes(k*, K^-1) * k*)` of
+// ssm_gpy/gp_models_utils_casadi.py:190-193 / GPy predict_noiseless.
+//
+//   pack_w_i8      W_d (fp64)            -> digit planes as SWIZZLE_64B shared-memory images + per-row factors
+//   kstar_i8       K*_d[i,b] (fp64 exp)  -> digit planes (same image format), fused with the mean / Jacobian sums
+//   tri_i8         per (d, block row, 96-trajectory panel): bulk-copy ring -> tcgen05.mma -> TMEM -> column sums
+//   i8_peak        register/shared-only issue loop that measures the int8 tensor-pipe rate (roofline denominator)
+#include <math.h>
+
+#include "segp_internal.cuh"
+
+namespace segp {
+
+// =========================================================================================== digits
+// r in [-1, 1]  ->  r ~= d0/127 + d1/(127 254) + ... ; |d_a| <= 127, remainder below 0.5 / (127 254^(S-1)).
+__device__ __forceinline__ void split_digits(double r, int (&dg)[I8_S]) {
+    double x = r * I8_BASE0;
+    double q = rint(x);
+    dg[0] = (int)q;
+    double res = x - q;
+#pragma unroll
+    for (int a = 1; a < I8_S; ++a) {
+        x = res * I8_BASE;
+        q = rint(x);
+        dg[a] = (int)q;
+        res = x - q;
+    }
+}
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_64B tile image (rows of 64 bytes, 16-byte chunks
+// XOR-ed with address bits [7,9) = (row >> 1) & 3)
+__host__ __device__ __forceinline__ int sw64_offset(int row, int k) {
+    return row * I8_KB + ((((k >> 4) ^ ((row >> 1) & 3)) << 4) | (k & 15));
+}
+
+// =========================================================================================== pack_w_i8
+__global__ void w_rowmax_kernel(const double* __restrict__ w, double* __restrict__ rowmax, int n_pad) {
+    __shared__ double s[256];
+    const int i = blockIdx.x;
+    double m = 0.0;
+    for (int j = threadIdx.x; j <= i; j += 256) m = fmax(m, fabs(w[(long)i * n_pad + j]));
+    s[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rowmax[i] = s[0];
+}
+
+__global__ void __launch_bounds__(TILE) pack_w_i8_kernel(const double* __restrict__ w, const double* __restrict__ rowmax,
+                                                         int8_t* __restrict__ wi8, double* __restrict__ rowfac,
+                                                         double var, int n_pad) {
+    const int kb = blockIdx.x, bi = blockIdx.y;
+    if (kb >= 2 * (bi + 1)) return;
+    const int r = threadIdx.x;
+    const long row = (long)bi * TILE + r;
+    const double rm = rowmax[row];
+    const double inv = rm > 0.0 ? 1.0 / rm : 0.0;
+    if (kb == 0) {
+        double f = rm * var / (I8_BASE0 * I8_BASE0);
+#pragma unroll
+        for (int a = 1; a < I8_S; ++a) f /= I8_BASE;
+        rowfac[row] = f;
+    }
+    const double* src = w + row * n_pad + (long)kb * I8_KB;
+    int8_t* dst = wi8 + ((long)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE);
+#pragma unroll 1
+    for (int c = 0; c < I8_KB / 16; ++c) {
+        uint32_t pk[I8_S][4];
+#pragma unroll
+        for (int a = 0; a < I8_S; ++a) pk[a][0] = pk[a][1] = pk[a][2] = pk[a][3] = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const long col = (long)kb * I8_KB + c * 16 + j;
+            const double v = (col <= row) ? src[c * 16 + j] : 0.0;   // strictly lower + diagonal only
+            int dg[I8_S];
+            split_digits(v * inv, dg);
+#pragma unroll
+            for (int a = 0; a < I8_S; ++a) pk[a][j >> 2] |= (uint32_t)(dg[a] & 0xff) << ((j & 3) * 8);
+        }
+        const int off = sw64_offset(r, c * 16);
+#pragma unroll
+        for (int a = 0; a < I8_S; ++a)
+            *reinterpret_cast<uint4*>(dst + (long)a * I8_A_TILE + off) = make_uint4(pk[a][0], pk[a][1], pk[a][2], pk[a][3]);
+    }
+}
+
+int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int n_pad, cudaStream_t st) {
+    const int nblk = n_pad / TILE;
+    double* rowmax = nullptr;
+    SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rowmax), (size_t)n_pad * sizeof(double), st));
+    w_rowmax_kernel<<<n_pad, 256, 0, st>>>(w, rowmax, n_pad);
+    dim3 grid((unsigned)(2 * nblk), (unsigned)nblk);
+    pack_w_i8_kernel<<<grid, TILE, 0, st>>>(w, rowmax, wi8_d, rowfac_d, var, n_pad);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(rowmax, st);
+    SEGP_CUDA_CHECK(e);
+    return SEGP_OK;
+}
+
+// =========================================================================================== kstar_i8
+// One block = one 96-trajectory panel (thread = trajectory = one row of the B tile images), blockIdx.y = output
+// dimension, blockIdx.z = split of the training points.  Same arithmetic as kstar_mean_jac (predict.cu); the kernel
+// value leaves as I8_S digit bytes instead of one double.
+template <int D_T>
+__global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
+    const KstarArgs& a = aa.k;
+    constexpr int DM = D_T > 0 ? D_T : MAX_D;
+    const int dim = D_T > 0 ? D_T : a.dim;
+    const int d = blockIdx.y;
+    const int split = blockIdx.z;
+    const int trow = threadIdx.x;
+    const long b = (long)blockIdx.x * I8_N + trow;
+    const bool active = b < a.n_batch;
+
+    __shared__ double s_x[TILE * DM];
+    __shared__ double s_beta[TILE];
+
+    double zs[DM];
+#pragma unroll
+    for (int j = 0; j < DM; ++j) zs[j] = 0.0;
+    if (active) {
+        if (a.z != nullptr) {
+#pragma unroll
+            for (int j = 0; j < DM; ++j)
+                if (j < dim) zs[j] = a.z[b * dim + j];
+        } else {
+            const double* p = a.p + b * a.p_stride;
+            const double* u = a.kff + b * a.kff_stride;
+            if (a.sp != nullptr && a.sp->has_t) {
+                for (int i = 0; i < a.n_in; ++i) {
+                    double acc = 0.0;
+                    for (int k = 0; k < a.n_s_state; ++k) acc += a.sp->t[i * a.n_s_state + k] * p[k];
+#pragma unroll
+                    for (int j = 0; j < DM; ++j)
+                        if (j == i) zs[j] = acc;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < DM; ++j)
+                    if (j < a.n_in) zs[j] = p[j];
+            }
+#pragma unroll
+            for (int j = 0; j < DM; ++j)
+                if (j >= a.n_in && j < dim) zs[j] = u[j - a.n_in];
+        }
+#pragma unroll
+        for (int j = 0; j < DM; ++j)
+            if (j < dim) zs[j] *= a.invls[d * dim + j];
+    }
+
+    double mu = 0.0;
+    double jac[DM];
+#pragma unroll
+    for (int j = 0; j < DM; ++j) jac[j] = 0.0;
+
+    const int kern = a.kern[d];
+    const double var = a.var[d];
+    const int nkb = a.n_pad / I8_KB;
+    const int row_begin = split * a.groups_per_split * 4;
+    const int row_end = min(row_begin + a.groups_per_split * 4, a.n_pad);
+    const double sqrt5 = 2.23606797749978969641;
+    int8_t* panel_base = aa.ki8 + (((long)d * aa.npanel_cap + blockIdx.x) * nkb) * (long)(I8_S * I8_B_TILE);
+
+    for (int row0 = row_begin; row0 < row_end; row0 += TILE) {
+        __syncthreads();
+        const double* src = a.xs + ((long)d * a.n_pad + row0) * dim;
+        for (int idx = threadIdx.x; idx < TILE * dim; idx += I8_N) s_x[idx] = src[idx];
+        for (int idx = threadIdx.x; idx < TILE; idx += I8_N) s_beta[idx] = a.beta[(long)d * a.n_pad + row0 + idx];
+        __syncthreads();
+#pragma unroll 1
+        for (int r = 0; r < TILE; r += 16) {
+            uint32_t pk[I8_S][4];
+#pragma unroll
+            for (int s = 0; s < I8_S; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
+#pragma unroll
+            for (int qd = 0; qd < 16; ++qd) {
+                const double* xr = s_x + (r + qd) * dim;
+                double diff[DM];
+                double r2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < DM; ++j) {
+                    diff[j] = 0.0;
+                    if (j < dim) {
+                        diff[j] = zs[j] - xr[j];
+                        r2 = fma(diff[j], diff[j], r2);
+                    }
+                }
+                double unit, g;   // k / var  and  (dk/dr2-type factor) / var
+                if (kern == SEGP_KERN_RBF) {
+                    unit = exp(-0.5 * r2);
+                    g = unit;
+                } else {
+                    const double rr = sqrt(r2);
+                    const double e = exp(-sqrt5 * rr);
+                    unit = (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * e;
+                    g = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
+                }
+                if (row0 + r + qd >= a.n_train || !active) unit = 0.0;   // padded rows / columns: zero digits
+                const double bt = s_beta[r + qd] * var;
+                mu = fma(bt, unit, mu);
+                const double w = bt * g;
+#pragma unroll
+                for (int j = 0; j < DM; ++j)
+                    if (j < dim) jac[j] = fma(w, diff[j], jac[j]);
+                int dg[I8_S];
+                split_digits(unit, dg);
+#pragma unroll
+                for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
+            }
+            const int kglob = row0 + r;
+            int8_t* tile0 = panel_base + (long)(kglob >> 6) * (I8_S * I8_B_TILE) + sw64_offset(trow, kglob & 63);
+#pragma unroll
+            for (int s = 0; s < I8_S; ++s)
+                *reinterpret_cast<uint4*>(tile0 + (long)s * I8_B_TILE) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+        }
+    }
+    if (active) {
+        const int n_s = gridDim.y;
+        a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
+#pragma unroll
+        for (int j = 0; j < DM; ++j)
+            if (j < dim) a.jac_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = jac[j];
+    }
+}
+
+int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st) {
+    dim3 grid((unsigned)((a.k.n_batch + I8_N - 1) / I8_N), (unsigned)n_s, (unsigned)nsplit);
+    dim3 block(I8_N);
+    switch (a.k.dim) {
+#define SEGP_KS8_CASE(D) \
+    case D:              \
+        kstar_i8_kernel<D><<<grid, block, 0, st>>>(a); \
+        break;
+        SEGP_KS8_CASE(2)
+        SEGP_KS8_CASE(3)
+        SEGP_KS8_CASE(4)
+        SEGP_KS8_CASE(5)
+        SEGP_KS8_CASE(6)
+        SEGP_KS8_CASE(7)
+        SEGP_KS8_CASE(8)
+        SEGP_KS8_CASE(13)
+#undef SEGP_KS8_CASE
+        default:
+            kstar_i8_kernel<0><<<grid, block, 0, st>>>(a);
+    }
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== PTX helpers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "I8_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra I8_WAIT_DONE;\n"
+        "bra I8_WAIT_LOOP;\n"
+        "I8_WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// all prior tcgen05.mma of this thread complete -> one arrival on the mbarrier
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = 128, N from idesc, K = 32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major SWIZZLE_64B operand descriptor: start address >> 4, LBO unused (0), SBO = 8 rows x 64 B = 512 B,
+// descriptor version 1 (sm_100), layout type 4 (SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// instruction descriptor, kind::i8: D = s32, A = B = signed int8, both K-major, dense, no saturation
+__host__ __device__ constexpr uint32_t make_i8_idesc(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// 32 lanes x 32 consecutive 32-bit columns of this warp's TMEM quadrant -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// =========================================================================================== tri_i8
+constexpr int I8_STAGES = 3;
+constexpr int I8_STAGE_BYTES = I8_S * (I8_A_TILE + I8_B_TILE);   // 71680
+constexpr int I8_THREADS = 192;                                  // producer, MMA issuer, 4 epilogue warps
+constexpr int I8_TMEM_COLS = 512;
+constexpr size_t I8_SMEM = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 /* alignment slack */ + 4 * I8_N * 8 + 128;
+constexpr int I8_PANEL_GROUP = 24;   // panels whose K* digit planes (24 x 2.5 MB at N = 5000) stay L2-resident
+
+__global__ void __launch_bounds__(I8_THREADS, 1) tri_i8_kernel(const TriI8Args a) {
+    // ---- tile decode: (d, panel group) outer, block row descending (heavy first), panel inner
+    int d, bi, panel;
+    if (a.fix_bi >= 0) {
+        d = 0;
+        bi = a.fix_bi;
+        panel = 0;
+    } else {
+        const int tiles_per_group = I8_PANEL_GROUP * a.nblk;
+        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        const long gid = blockIdx.x / tiles_per_group;
+        const int r = blockIdx.x % tiles_per_group;
+        d = (int)(gid / npg);
+        const int pg = (int)(gid % npg);
+        bi = a.nblk - 1 - r / I8_PANEL_GROUP;
+        panel = pg * I8_PANEL_GROUP + r % I8_PANEL_GROUP;
+        if (panel >= a.npanels) return;
+    }
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_addr(smem_raw);
+    const uint32_t stage0 = (raw + 1023u) & ~1023u;                    // SWIZZLE images need aligned tile bases
+    unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)I8_STAGES * I8_STAGE_BYTES;
+    double* s_col = reinterpret_cast<double*>(tail);                   // [4][I8_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 4 * I8_N);     // full[3], empty[3], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 1);
+    const uint32_t bar0 = smem_addr(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (I8_STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (2 * I8_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
+                     "n"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nk = 2 * (bi + 1);   // k-blocks of 64 training points: columns 0 .. 128 (bi + 1) of the block row
+    const int nkb_total = a.nblk * 2;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer: two bulk copies per stage
+        if (lane == 0) {
+            const int8_t* wsrc = a.wi8 + ((long)d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (I8_S * I8_A_TILE);
+            const int8_t* ksrc = a.ki8 + (((long)d * a.npanel_cap + panel) * nkb_total) * (long)(I8_S * I8_B_TILE);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % I8_STAGES;
+                if (it >= I8_STAGES) mbar_wait(empty_bar(s), (uint32_t)((it / I8_STAGES - 1) & 1));
+                const uint32_t dst = stage0 + (uint32_t)s * I8_STAGE_BYTES;
+                mbar_expect_tx(full_bar(s), I8_STAGE_BYTES);
+                bulk_g2s(dst, wsrc + (long)it * (I8_S * I8_A_TILE), I8_S * I8_A_TILE, full_bar(s));
+                bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * I8_B_TILE, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_i8_idesc(TILE, I8_N);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % I8_STAGES;
+                mbar_wait(full_bar(s), (uint32_t)((it / I8_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t sa = stage0 + (uint32_t)s * I8_STAGE_BYTES;
+                const uint32_t sb = sa + I8_S * I8_A_TILE;
+#pragma unroll
+                for (int ks = 0; ks < I8_KB / 32; ++ks) {
+#pragma unroll
+                    for (int pa = 0; pa < I8_S; ++pa) {
+                        const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
+#pragma unroll
+                        for (int pc = 0; pc < I8_S - pa; ++pc) {
+                            const uint64_t bdesc = make_sw64_desc(sb + pc * I8_B_TILE + ks * 32);
+                            // diagonal pa + pc accumulates in TMEM columns [(pa+pc) N, (pa+pc+1) N)
+                            tc_mma_i8(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, idesc,
+                                      (uint32_t)((it | ks | pa) != 0));
+                        }
+                    }
+                }
+                tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+            }
+            tc_commit(tmem_full_bar);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: 4 warps, one TMEM quadrant each
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const double rf = a.rowfac[((long)d * a.nblk + bi) * TILE + row];
+        mbar_wait(tmem_full_bar, 0u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = 0; chunk < I8_N / 32; ++chunk) {
+            long long acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0;
+#pragma unroll
+            for (int dg = 0; dg < I8_S; ++dg) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dg * I8_N + chunk * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = acc[j] * 254 + (long long)(int)v[j];   // exact: |acc| < 2^63
+                if (a.dbg != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a.dbg[((long)dg * TILE + row) * I8_N + chunk * 32 + j] = (int)v[j];
+                }
+            }
+            double vals[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const double x = (double)acc[j] * rf;
+                vals[j] = x * x;
+            }
+            // transpose-reduce over the 32 rows of the warp: after the 5 halving steps lane l holds column l
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int j = 0; j < off; ++j) {
+                    const double keep = up ? vals[j + off] : vals[j];
+                    const double give = up ? vals[j] : vals[j + off];
+                    vals[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+                }
+            }
+            s_col[q * I8_N + chunk * 32 + lane] = vals[0];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int c = threadIdx.x - 64;
+        if (c < I8_N) {
+            const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
+            const long bcol = (long)panel * I8_N + c;
+            if (bcol < a.b_cap) a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+int tri_i8_init() {
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
+    return SEGP_OK;
+}
+
+int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st) {
+    long nblocks = 1;
+    if (a.fix_bi < 0) {
+        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        nblocks = (long)n_s * npg * I8_PANEL_GROUP * a.nblk;
+    }
+    if (nblocks <= 0 || nblocks > 2147483647L) {
+        set_error("tri_i8: grid of %ld tiles out of range", nblocks);
+        return SEGP_ERR_INVALID;
+    }
+    tri_i8_kernel<<<(unsigned)nblocks, I8_THREADS, I8_SMEM, st>>>(a);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== i8_peak
+// One CTA per SM issues `iters` back-to-back tcgen05.mma kind::i8 (M = 128, N = umma_n, K = 32) on fixed shared
+// memory tiles; no loads, no epilogue: the sustained int8 tensor-pipe rate a kernel of this shape can reach.
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int umma_n, int iters) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t raw = smem_addr(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* tiles = smem_raw + (base - raw);
+    for (int i = threadIdx.x; i < (TILE + 256) * I8_KB / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tiles)[i] = 0x01010101u;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_addr(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_slot)),
+                     "n"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // generic-proxy writes above must be visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_i8_idesc(TILE, umma_n);
+        const uint64_t adesc0 = make_sw64_desc(base);
+        const uint64_t bdesc0 = make_sw64_desc(base + I8_A_TILE);
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t koff = (uint32_t)(it & 1) * 2u;                  // alternate the two k-steps of the tile
+            const uint32_t col = (umma_n <= 256 && (it & 2)) ? 256u : 0u;   // and two accumulators
+            tc_mma_i8(tmem_base + col, adesc0 + koff, bdesc0 + koff, idesc, (uint32_t)(it > 3));
+        }
+        tc_commit(smem_addr(&bar));
+        mbar_wait(smem_addr(&bar), 0u);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+int i8_peak(int umma_n, int iters, double* tops) {
+    if (umma_n < 16 || umma_n > 256 || umma_n % 16 != 0 || iters < 1 || tops == nullptr) {
+        set_error("i8_peak: umma_n must be a multiple of 16 in [16, 256]");
+        return SEGP_ERR_INVALID;
+    }
+    int dev = 0, sms = 0;
+    SEGP_CUDA_CHECK(cudaGetDevice(&dev));
+    SEGP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = (size_t)(TILE + 256) * I8_KB + 1024;
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    SEGP_CUDA_CHECK(cudaEventCreate(&e0));
+    SEGP_CUDA_CHECK(cudaEventCreate(&e1));
+    i8_peak_kernel<<<sms, 128, smem>>>(umma_n, iters);   // warm-up
+    SEGP_CUDA_CHECK(cudaEventRecord(e0));
+    i8_peak_kernel<<<sms, 128, smem>>>(umma_n, iters);
+    SEGP_CUDA_CHECK(cudaEventRecord(e1));
+    SEGP_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    SEGP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    *tops = 2.0 * TILE * umma_n * 32.0 * iters * sms / (ms * 1e-3) / 1e12;
+    return SEGP_OK;
+}
+
+}  // namespace segp

@@ -22,6 +22,7 @@ The arithmetic is float64 end to end (the reference is float64; the predictive v
 digits).
 """
 import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -29,6 +30,11 @@ import numpy as np
 from . import _lib
 
 __all__ = ["BatchedGPSSM"]
+
+# Which tensor pipe runs the variance contraction of new models (include/segp.h, option "tri_mode"):
+# -1 automatic (int8 digit planes on tcgen05 when the padded training size allows, else fp64 DMMA), 0 fp64 DMMA,
+# 1 int8 tcgen05.  Both are products of this package and both meet the rtol 1e-4 gate; tests run both.
+DEFAULT_TRI_MODE = int(os.environ.get("SEGP_TRI_MODE", "-1"))
 
 _GPY_JITTER = 1e-8        # ExactGaussianInference adds 1e-8 to the diagonal of K
 _GPY_DEFAULT_NOISE = 1.0  # GPRegression default Gaussian_noise.variance
@@ -64,7 +70,7 @@ class BatchedGPSSM(object):
     has_reverse = False
 
     def __init__(self, n_s_out, n_s_in, n_u, X=None, y=None, m=None, kern_types=None, hyp=None, train=True,
-                 Z=None, device=None, noise_diag=1e-5):
+                 Z=None, device=None, noise_diag=1e-5, tri_mode=None):
         torch = _lib.require_cuda()
         self._torch = torch
         self._lib = _lib.load()
@@ -99,6 +105,7 @@ class BatchedGPSSM(object):
         kern_ids = (ctypes.c_int * self.n_s_out)(*[_lib.KERN_IDS[k] for k in self.kern_types])
         _lib.check(self._lib.segp_create(ctypes.byref(self._handle), self.device.index, self.n_s_out, self.n_s_in,
                                          self.n_u, kern_ids))
+        self.set_option("tri_mode", DEFAULT_TRI_MODE if tri_mode is None else tri_mode)
         if X is not None and y is not None and train:
             self.train(X, y)
 

@@ -1,0 +1,107 @@
+"""GPU tests of the tcgen05 (int8 digit-plane) variance contraction, through the C ABI.
+
+* exact integer check of one tile against NumPy (descriptor / swizzle / TMEM layout),
+* predictive variance of both tensor pipes (tri_mode 0 = fp64 DMMA, 1 = int8 tcgen05) against the float64
+  oracle on models whose variance cancels 3-4 digits, at BASELINE.json's rtol 1e-4,
+* the two pipes against each other on a rollout at the C4 model size.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+I8_S, TILE, I8_N = 5, 128, 96
+
+
+@pytest.fixture(scope="module")
+def se():
+    import safe_exploration_b200 as pkg
+    pkg._lib.load()
+    return pkg
+
+
+@pytest.mark.parametrize("k_blocks", [1, 2, 5])
+def test_one_tile_exact_integers(se, k_blocks):
+    lib = se._lib.load()
+    rng = np.random.default_rng(10 + k_blocks)
+    kdim = TILE * k_blocks
+    a = rng.integers(-127, 128, size=(I8_S, TILE, kdim), dtype=np.int8)
+    b = rng.integers(-127, 128, size=(I8_S, I8_N, kdim), dtype=np.int8)
+    acc = np.zeros((I8_S, TILE, I8_N), dtype=np.int32)
+    colsum = np.zeros(I8_N, dtype=np.float64)
+    se._lib.check(lib.segp_i8_selftest(0, k_blocks, a.ctypes.data_as(ctypes.c_void_p),
+                                       b.ctypes.data_as(ctypes.c_void_p), acc.ctypes.data_as(ctypes.c_void_p),
+                                       colsum.ctypes.data_as(ctypes.c_void_p)))
+    want = np.zeros((I8_S, TILE, I8_N), dtype=np.int64)
+    a64, b64 = a.astype(np.int64), b.astype(np.int64)
+    for pa in range(I8_S):
+        for pc in range(I8_S - pa):
+            want[pa + pc] += a64[pa] @ b64[pc].T
+    assert np.abs(want).max() < 2 ** 31
+    assert np.array_equal(acc.astype(np.int64), want), "first mismatch at {}".format(
+        np.argwhere(acc.astype(np.int64) != want)[:4])
+    horner = np.zeros((TILE, I8_N), dtype=object)
+    for g in range(I8_S):
+        horner = horner * 254 + want[g].astype(object)
+    want_col = np.array([float(sum(int(v) ** 2 for v in horner[:, c])) for c in range(I8_N)])
+    assert np.allclose(colsum, want_col, rtol=1e-13, atol=0.0)
+
+
+def test_i8_peak_reports(se):
+    lib = se._lib.load()
+    for n in (96, 256):
+        tops = ctypes.c_double()
+        se._lib.check(lib.segp_i8_peak(0, n, 20000, ctypes.byref(tops)))
+        print("int8 tcgen05 peak, M=128 N=%d: %.1f TOP/s" % (n, tops.value))
+        assert tops.value > 500.0
+
+
+def _cancelling_model(se, n, n_s, n_u, kern, seed, tri_mode):
+    from oracle.gp_oracle import GPOracle
+    rng = np.random.default_rng(seed)
+    dim = n_s + n_u
+    x = rng.uniform(-1.0, 1.0, size=(n, dim))
+    y = np.sin(x @ rng.standard_normal((dim, n_s))) + 0.1 * rng.standard_normal((n, n_s))
+    ls = rng.uniform(0.8, 2.0, size=(n_s, dim))
+    var = rng.uniform(0.5, 1.5, size=n_s)
+    hyp = [{"lengthscale": ls[d], "variance": float(var[d]), "noise": 1e-2} for d in range(n_s)]
+    gp = se.BatchedGPSSM(n_s, n_s, n_u, x, y, kern_types=[kern] * n_s, hyp=hyp, tri_mode=tri_mode)
+    ora = GPOracle(x, y, [kern] * n_s, ls, var, gp.total_noise())
+    z = rng.uniform(-0.7, 0.7, size=(500, dim))
+    return gp, ora, z
+
+
+@pytest.mark.parametrize("tri_mode", [0, 1])
+@pytest.mark.parametrize("n,n_s,n_u,kern", [(1500, 2, 1, "rbf"), (3000, 4, 1, "rbf"), (2000, 3, 2, "mat52")])
+def test_predict_variance_under_cancellation(se, n, n_s, n_u, kern, tri_mode):
+    gp, ora, z = _cancelling_model(se, n, n_s, n_u, kern, 5, tri_mode)
+    assert gp.get_option("tri_mode_effective") == tri_mode
+    mu, var, jac = gp.predict(z, compute_gradients=True)
+    mu_o, var_o, jac_o = ora.predict_batch(z)
+    ratio = float(np.min(var_o / np.array([h["variance"] for h in gp.hyp])[None, :]))
+    err_v = float(np.max(np.abs(var - var_o) / np.abs(var_o)))
+    err_m = float(np.max(np.abs(mu - mu_o) / (np.abs(mu_o) + 1e-6)))
+    print("N=%d %s mode %d: min var/k** %.2e, max rel err var %.2e, mean %.2e" % (n, kern, tri_mode, ratio, err_v, err_m))
+    assert err_v < 1e-5          # gate is 1e-4; both pipes are expected near 1e-6 or better
+    assert err_m < 1e-6
+    assert np.allclose(jac, jac_o, rtol=1e-6, atol=1e-8)
+    gp.close()
+
+
+def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C4", batch=700)
+    out = {}
+    for mode in (0, 1):
+        gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp,
+                             tri_mode=mode)
+        out[mode] = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+        gp.close()
+    assert np.all(out[0].status == 0) and np.all(out[1].status == 0)
+    for name in ("var_all", "p_all", "q_all"):
+        a0, a1 = getattr(out[0], name), getattr(out[1], name)
+        err = float(np.max(np.abs(a1 - a0) / (np.abs(a0) + 1e-12 * np.abs(a0).max())))
+        print("C4 model, %s: int8 vs fp64 pipe max rel diff %.2e" % (name, err))
+        assert err < 2e-5
