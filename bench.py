@@ -194,6 +194,7 @@ def run_product(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (the product has no CPU path)")
+    se.ssm.DEFAULT_TRI_MODE = args.tri_mode
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     cfg = workloads.CONFIGS[args.config]
@@ -284,20 +285,56 @@ def run_product(args, rank, world, local_rank):
     flop_launch = float(w.n_s) * w.n_train ** 2 * min(b_per_gpu, gp.get_option("chunk"))
     tri_avg_s = (tri_ns / max(tri_count, 1)) * 1e-9
     achieved = flop_launch / tri_avg_s / 1e12 if tri_avg_s > 0 else None
-    dmma = _dmma_peak(gp, local_rank)
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    roofline = {"bound": "tensor", "kernel": "tri_sumsq_kernel", "pipe": "fp64 DMMA (mma.sync m8n8k4.f64)",
-                "achieved": achieved, "peak": dmma, "unit": "TFLOP/s",
-                "frac": (achieved / dmma) if (achieved and dmma) else None,
-                "peak_source": "segp_dmma_peak measured in this run: the float64 contraction cannot run on tcgen05 "
-                               "(no f64 kind); " + peaks["_source"] + " holds only bf16",
-                "bf16_peak": bf16_peak, "frac_of_bf16_peak": (achieved / bf16_peak) if achieved else None,
-                "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count,
-                "share_of_step": (tri_ns * 1e-6) / ms if ms > 0 else None,
-                "algorithmic_flop_per_launch": flop_launch, "traffic": None}
+    share = (tri_ns * 1e-6) / ms if ms > 0 else None
+    mode = gp.get_option("tri_mode_effective")
+    if mode in (1, 2):
+        # tri_i8: 15 int8 digit-plane products per algorithmic multiply-add, exact int32 accumulation in TMEM.
+        # `achieved` is ALGORITHMIC flop/s (n_s N^2 B per launch); `peak` is the measured bf16 figure of
+        # MEASURED_PEAKS.json, so `frac` is the algorithmic fraction of the bf16 tensor peak: error-free splitting
+        # caps it at 2/15 (int8 runs at twice the bf16 rate, 15 products).  `pipe_*` say how busy the int8 pipe
+        # actually was: executed int8 op/s (padding and all 15 products counted) against the int8 rate measured
+        # in this run by segp_i8_peak (same instruction shape, no loads).
+        cols = min(b_per_gpu, gp.get_option("chunk"))
+        n_pad = gp.get_option("n_train_padded")
+        nblk = n_pad // 128
+        panels = -(-cols // 96)
+        if mode == 2:   # block-row pairs: the upper row of a pair also runs over the lower row's diagonal block
+            kblocks = sum(2 * (min(2 * bp + 1, nblk - 1) + 1) for bp in range((nblk + 1) // 2))
+        else:
+            kblocks = nblk * (nblk + 1) // 2
+        executed = 2.0 * 15 * w.n_s * (128 * 128 * kblocks) * panels * 96
+        i8_96, i8_256 = _i8_peak(gp, local_rank, 96), _i8_peak(gp, local_rank, 256)
+        pipe_tops = executed / tri_avg_s / 1e12 if tri_avg_s > 0 else None
+        roofline = {"bound": "tensor", "kernel": "tri_i8x2_kernel" if mode == 2 else "tri_i8_kernel",
+                    "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, " + ("cta_group::2 M=256" if mode == 2 else "M=128")
+                            + " N=96 K=32, int32 accumulators in TMEM); "
+                            "float64-grade result from 5 x 5 balanced base-254 digit planes, 15 products",
+                    "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": (achieved / bf16_peak) if achieved else None,
+                    "peak_source": peaks["_source"] + " bf16_tflops_sustained; algorithmic flop against the bf16 "
+                                   "peak, ceiling 2/15 = 0.133 for the 15-product int8 splitting",
+                    "frac_of_splitting_ceiling": (achieved / (bf16_peak * 2.0 / 15.0)) if achieved else None,
+                    "pipe_executed_tops": pipe_tops, "pipe_peak_tops_n96": i8_96, "pipe_peak_tops_n256": i8_256,
+                    "pipe_frac_of_n96_peak": (pipe_tops / i8_96) if (pipe_tops and i8_96) else None,
+                    "pipe_frac_of_2x_bf16_peak": (pipe_tops / (2.0 * bf16_peak)) if pipe_tops else None,
+                    "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
+                    "algorithmic_flop_per_launch": flop_launch, "traffic": None}
+    else:
+        dmma = _dmma_peak(gp, local_rank)
+        roofline = {"bound": "tensor", "kernel": "tri_sumsq_kernel", "pipe": "fp64 DMMA (mma.sync m8n8k4.f64)",
+                    "achieved": achieved, "peak": dmma, "unit": "TFLOP/s",
+                    "frac": (achieved / dmma) if (achieved and dmma) else None,
+                    "peak_source": "segp_dmma_peak measured in this run (fp64 DMMA pipe; tri_mode=0); "
+                                   + peaks["_source"] + " holds only bf16",
+                    "bf16_peak": bf16_peak, "frac_of_bf16_peak": (achieved / bf16_peak) if achieved else None,
+                    "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
+                    "algorithmic_flop_per_launch": flop_launch, "traffic": None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "tri_mode": {0: "fp64 DMMA", 1: "int8 digit planes on tcgen05 (single CTA), float64 recombination",
+                         2: "int8 digit planes on tcgen05 (CTA pairs), float64 recombination"}[mode],
             "config": _config_dict(args, w, b_per_gpu, world, "device-resident"),
             "onestep_calls_per_sec": value * w.horizon,
             "algorithmic_tflops": value * w.horizon * workloads.flop_per_step(w.n_s, w.n_u, w.n_train) / 1e12,
@@ -313,6 +350,13 @@ def run_product(args, rank, world, local_rank):
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
+
+
+def _i8_peak(gp, device, umma_n):
+    import ctypes
+    out = ctypes.c_double()
+    rc = gp._lib.segp_i8_peak(device, umma_n, 20000, ctypes.byref(out))
+    return out.value if rc == 0 else None
 
 
 def _dmma_peak(gp, device):
@@ -334,6 +378,9 @@ def main():
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="variance contraction pipe: -1 auto (2 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
+                         "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2)")
     ap.add_argument("--redundant-factor", action="store_true",
                     help="factorise on every rank instead of broadcasting the factor")
     args = ap.parse_args()

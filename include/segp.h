@@ -178,18 +178,20 @@ int segp_dmma_peak(int device, int iters, double* tflops);
  * contraction kernel (tri_i8) against, next to twice the measured bf16 figure of MEASURED_PEAKS.json. */
 int segp_i8_peak(int device, int umma_n, int iters, double* tops);
 
-/* Diagnostic: run ONE tile of the tcgen05 contraction kernel on caller-supplied digit planes and return the raw
+/* Diagnostic: run ONE tile of a tcgen05 contraction kernel on caller-supplied digit planes and return the raw
  * TMEM accumulators, so descriptor / swizzle / TMEM-layout errors show up as exact integer mismatches.
- *   h_a [5][128][K] int8, h_b [5][96][K] int8 with K = 128 * k_blocks (HOST)
- *   h_acc [5][128][96] int32: h_acc[g] = sum over planes a + c == g of A_a B_c^T
- *   h_colsum [96]: sum over rows of (sum_g h_acc[g] * 254^(4-g))^2 as float64 */
-int segp_i8_selftest(int device, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
+ *   variant 1: single-CTA kernel (M = 128 rows); variant 2: CTA-pair kernel (cta_group::2, M = 256 rows; k_blocks
+ *   even; rows 0..127 are the upper block row, whose last 128 columns are outside its k-range and read as zero)
+ *   h_a [5][M][K] int8, h_b [5][96][K] int8 with K = 128 * k_blocks (HOST)
+ *   h_acc [5][M][96] int32: h_acc[g] = sum over planes a + c == g of A_a B_c^T
+ *   h_colsum [M/128][96]: per block row, sum over rows of (sum_g h_acc[g] * 254^(4-g))^2 as float64 */
+int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum);
 
 /* Tuning knobs / introspection ("chunk": trajectories per workspace chunk, "panel_group", "ksplit",
- * "tri_mode": which pipe runs the variance contraction: -1 = automatic (default: int8 tcgen05 when the padded
- *   training size is <= 16384, else fp64 DMMA), 0 = fp64 DMMA (mma.sync m8n8k4.f64), 1 = int8 digit planes on
- *   tcgen05; read-only "tri_mode_effective";
+ * "tri_mode": which pipe runs the variance contraction: -1 = automatic (default: 2 when the padded training
+ *   size is <= 16384, else 0), 0 = fp64 DMMA (mma.sync m8n8k4.f64), 1 = int8 digit planes on tcgen05, one CTA per
+ *   tile, 2 = the same on CTA pairs (tcgen05.mma.cta_group::2, M = 256); read-only "tri_mode_effective";
  * "time_tri": 1 = bracket every tri_sumsq launch with a CUDA-event pair on its stream (resets the counters);
  * read-only: "launches" = kernels launched by this handle so far, "n_train_padded", "workspace_bytes",
  * "tri_launches" / "tri_ns" = number and total device nanoseconds of the timed tri_sumsq launches). */

@@ -74,7 +74,8 @@ struct segp_model {
     double* ks = nullptr;      // fp64 K* block (DMMA path)
     int8_t* ki8 = nullptr;     // digit planes of the K* block (tcgen05 path)
     long npanel_cap = 0;
-    bool ws_i8 = false;        // which of ks / ki8 the current workspace holds
+    int ws_mode = 0;           // tri mode the current workspace is laid out for (0 fp64 ks, 1 ki8, 2 ki8 split halves)
+    int8_t* i8zero = nullptr;  // I8_S * I8_A_TILE zero bytes (pair kernel)
     double* mu_part = nullptr;
     double* jac_part = nullptr;
     double* qpart = nullptr;
@@ -87,7 +88,8 @@ struct segp_model {
     long opt_chunk = 8192;
     long opt_panel_group = 16;
     long opt_ksplit = 0;   // 0 = automatic
-    long opt_tri_mode = -1;   // -1 = automatic (int8 tcgen05 when n_pad <= I8_MAX_NPAD), 0 = fp64 DMMA, 1 = int8 tcgen05
+    long opt_tri_mode = -1;   // -1 = automatic (2 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
+                              // 1 = int8 tcgen05 single CTA, 2 = int8 tcgen05 CTA pair (cta_group::2)
     long launches = 0;
     // optional per-launch timing of tri_sumsq (bench.py roofline): event pairs recorded on the launching stream
     bool time_tri = false;
@@ -107,6 +109,7 @@ static void free_model_buffers(segp_model* m) {
     dev_free(m->logdet);
     dev_free(m->wi8);
     dev_free(m->rowfac);
+    dev_free(m->i8zero);
     m->factorized = false;
 }
 
@@ -122,20 +125,23 @@ static void free_workspace(segp_model* m) {
 }
 
 static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD; }
-static bool use_i8(const segp_model* m) {
-    return m->opt_tri_mode == 1 || (m->opt_tri_mode < 0 && i8_capable(m));
+static int tri_mode(const segp_model* m) {
+    if (m->opt_tri_mode >= 0) return (int)m->opt_tri_mode;
+    return i8_capable(m) ? 2 : 0;
 }
 
 static int ensure_workspace(segp_model* m, long n_batch) {
     constexpr long ALIGN = 384;   // lcm of the DMMA tile (128 columns) and the tcgen05 panel (96 columns)
     long want = std::min<long>(m->opt_chunk, n_batch);
     want = (want + ALIGN - 1) / ALIGN * ALIGN;
-    const bool i8 = use_i8(m);
+    const int mode = tri_mode(m);
+    const bool i8 = mode != 0;
     if (i8 && m->wi8 == nullptr) {
-        set_error("tri_mode=1 (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", I8_MAX_NPAD, m->n_pad);
+        set_error("tri_mode=%d (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", mode, I8_MAX_NPAD,
+                  m->n_pad);
         return SEGP_ERR_UNSUPPORTED;
     }
-    if (i8 != m->ws_i8 && m->b_cap > 0) free_workspace(m);
+    if (mode != m->ws_mode && m->b_cap > 0) free_workspace(m);
     // split of the N-length reductions of kstar_mean_jac over blockIdx.z so small batches still fill 148 SMs
     const long col_blocks = want / TILE;
     int nsplit;
@@ -171,7 +177,7 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     m->workspace_bytes = (n_ks + n_mu + n_jac + n_q) * sizeof(double) + n_ki8;
     m->b_cap = want;
     m->npanel_cap = npanel_cap;
-    m->ws_i8 = i8;
+    m->ws_mode = mode;
     m->nsplit = nsplit;
     m->blocks_per_split = bps;
     return SEGP_OK;
@@ -237,11 +243,12 @@ static KstarArgs base_kstar_args(const segp_model* m) {
 
 // K* block (+ mean / Jacobian partials) in the operand format of the active contraction kernel
 static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st) {
-    if (m->ws_i8) {
+    if (m->ws_mode != 0) {
         KstarI8Args k8{};
         k8.k = k;
         k8.ki8 = m->ki8;
         k8.npanel_cap = m->npanel_cap;
+        k8.split_halves = m->ws_mode == 2;
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
     }
     return launch_kstar(k, m->n_s, m->nsplit, st);
@@ -262,7 +269,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st) {
         m->tri_events_used += 2;
         SEGP_CUDA_CHECK(cudaEventRecord(e0, st));
     }
-    if (m->ws_i8) {
+    if (m->ws_mode != 0) {
         TriI8Args t{};
         t.wi8 = m->wi8;
         t.rowfac = m->rowfac;
@@ -274,7 +281,8 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st) {
         t.b_cap = m->b_cap;
         t.dbg = nullptr;
         t.fix_bi = -1;
-        SEGP_CHECK(launch_tri_i8(t, m->n_s, st));
+        t.zero_a = m->i8zero;
+        SEGP_CHECK(m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st) : launch_tri_i8(t, m->n_s, st));
     } else {
         TriArgs t{};
         t.wt = m->wt;
@@ -434,6 +442,10 @@ int segp_alloc_factor_buffers(segp_model* m) {
         if (m->wi8 == nullptr)
             SEGP_CHECK(dev_alloc(&m->wi8, (size_t)m->n_s * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE)));
         if (m->rowfac == nullptr) SEGP_CHECK(dev_alloc(&m->rowfac, (size_t)m->n_s * m->n_pad));
+        if (m->i8zero == nullptr) {
+            SEGP_CHECK(dev_alloc(&m->i8zero, (size_t)I8_S * I8_A_TILE));
+            SEGP_CUDA_CHECK(cudaMemset(m->i8zero, 0, (size_t)I8_S * I8_A_TILE));
+        }
     }
     return SEGP_OK;
 }
@@ -926,9 +938,11 @@ int segp_i8_peak(int device, int umma_n, int iters, double* tops) {
     return i8_peak(umma_n, iters, tops);
 }
 
-int segp_i8_selftest(int device, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc, double* h_colsum) {
-    if (k_blocks < 1 || k_blocks > 64 || h_a == nullptr || h_b == nullptr || h_acc == nullptr || h_colsum == nullptr) {
-        set_error("segp_i8_selftest: bad argument");
+int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
+                     double* h_colsum) {
+    if ((variant != 1 && variant != 2) || k_blocks < 1 || k_blocks > 64 || (variant == 2 && (k_blocks & 1)) ||
+        h_a == nullptr || h_b == nullptr || h_acc == nullptr || h_colsum == nullptr) {
+        set_error("segp_i8_selftest: bad argument (variant 1|2, k_blocks in [1,64], even for variant 2)");
         return SEGP_ERR_INVALID;
     }
     DeviceGuard guard(device);
@@ -937,41 +951,55 @@ int segp_i8_selftest(int device, int k_blocks, const int8_t* h_a, const int8_t* 
         return SEGP_ERR_CUDA;
     }
     SEGP_CHECK(tri_i8_init());
-    // one tile: block row bi = k_blocks - 1 of a (128 k_blocks)-point model, panel 0; K = 128 k_blocks
-    const int bi = k_blocks - 1, nblk = k_blocks, kdim = TILE * k_blocks, nkb = 2 * k_blocks;
+    // one tile of a (128 k_blocks)-point model, panel 0, K = 128 k_blocks:
+    //   variant 1: block row k_blocks - 1 (128 rows);  variant 2: block rows k_blocks - 2 and k_blocks - 1 (256 rows),
+    //   where the upper block row sees zeros in the last 128 columns (its own k-range ends one block earlier)
+    const int nblk = k_blocks, kdim = TILE * k_blocks, nkb = 2 * k_blocks;
+    const int rows = variant == 2 ? 2 * TILE : TILE;
+    const int bi0 = variant == 2 ? k_blocks - 2 : k_blocks - 1;
     const size_t a_bytes = (size_t)nblk * (nblk + 1) * (I8_S * I8_A_TILE);
     const size_t b_bytes = (size_t)nkb * (I8_S * I8_B_TILE);
     std::vector<int8_t> a_img(a_bytes, 0), b_img(b_bytes, 0);
-    // same image format as pack_w_i8_kernel / kstar_i8_kernel: [k-block][plane][row][64 B, SWIZZLE_64B]
-    for (int kb = 0; kb < nkb; ++kb)
-        for (int pl = 0; pl < I8_S; ++pl) {
-            int8_t* at = a_img.data() + ((size_t)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE) + (size_t)pl * I8_A_TILE;
-            int8_t* bt = b_img.data() + (size_t)kb * (I8_S * I8_B_TILE) + (size_t)pl * I8_B_TILE;
-            for (int k = 0; k < I8_KB; ++k) {
-                for (int r = 0; r < TILE; ++r) {
-                    const int off = r * I8_KB + ((((k >> 4) ^ ((r >> 1) & 3)) << 4) | (k & 15));
-                    at[off] = h_a[((size_t)pl * TILE + r) * kdim + (size_t)kb * I8_KB + k];
-                }
-                for (int r = 0; r < I8_N; ++r) {
-                    const int off = r * I8_KB + ((((k >> 4) ^ ((r >> 1) & 3)) << 4) | (k & 15));
-                    bt[off] = h_b[((size_t)pl * I8_N + r) * kdim + (size_t)kb * I8_KB + k];
-                }
+    auto sw = [](int r, int k) { return r * I8_KB + ((((k >> 4) ^ ((r >> 1) & 3)) << 4) | (k & 15)); };
+    // same image formats as pack_w_i8_kernel / kstar_i8_kernel
+    for (int rb = 0; rb < rows / TILE; ++rb) {
+        const int bi = bi0 + rb;
+        for (int kb = 0; kb < 2 * (bi + 1); ++kb)
+            for (int pl = 0; pl < I8_S; ++pl) {
+                int8_t* at = a_img.data() + ((size_t)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE) + (size_t)pl * I8_A_TILE;
+                for (int k = 0; k < I8_KB; ++k)
+                    for (int r = 0; r < TILE; ++r)
+                        at[sw(r, k)] = h_a[((size_t)pl * rows + rb * TILE + r) * kdim + (size_t)kb * I8_KB + k];
             }
-        }
-    int8_t *d_a = nullptr, *d_b = nullptr;
+    }
+    for (int kb = 0; kb < nkb; ++kb)
+        for (int pl = 0; pl < I8_S; ++pl)
+            for (int k = 0; k < I8_KB; ++k)
+                for (int r = 0; r < I8_N; ++r) {
+                    const int8_t v = h_b[((size_t)pl * I8_N + r) * kdim + (size_t)kb * I8_KB + k];
+                    int8_t* kbase = b_img.data() + (size_t)kb * (I8_S * I8_B_TILE);
+                    if (variant == 2)
+                        kbase[(size_t)(r / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) + (size_t)pl * (I8_B_TILE / 2) +
+                              sw(r % (I8_N / 2), k)] = v;
+                    else
+                        kbase[(size_t)pl * I8_B_TILE + sw(r, k)] = v;
+                }
+    int8_t *d_a = nullptr, *d_b = nullptr, *d_zero = nullptr;
     double *d_rf = nullptr, *d_q = nullptr;
     int32_t* d_dbg = nullptr;
-    const size_t n_dbg = (size_t)I8_S * TILE * I8_N;
+    const size_t n_dbg = (size_t)I8_S * rows * I8_N;
     int rc = SEGP_OK;
     do {
         if ((rc = dev_alloc(&d_a, a_bytes)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_b, b_bytes)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_zero, (size_t)I8_S * I8_A_TILE)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_rf, (size_t)kdim)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_q, (size_t)nblk * I8_N)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_dbg, n_dbg)) != SEGP_OK) break;
         std::vector<double> ones((size_t)kdim, 1.0);
         cudaError_t e = cudaMemcpy(d_a, a_img.data(), a_bytes, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(d_b, b_img.data(), b_bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(d_zero, 0, (size_t)I8_S * I8_A_TILE);
         if (e == cudaSuccess) e = cudaMemcpy(d_rf, ones.data(), kdim * sizeof(double), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemset(d_q, 0, (size_t)nblk * I8_N * sizeof(double));
         if (e != cudaSuccess) {
@@ -989,12 +1017,14 @@ int segp_i8_selftest(int device, int k_blocks, const int8_t* h_a, const int8_t* 
         t.npanel_cap = 1;
         t.b_cap = I8_N;
         t.dbg = d_dbg;
-        t.fix_bi = bi;
-        if ((rc = launch_tri_i8(t, 1, nullptr)) != SEGP_OK) break;
+        t.zero_a = d_zero;
+        t.fix_bi = variant == 2 ? bi0 / 2 : bi0;
+        if ((rc = (variant == 2 ? launch_tri_i8x2(t, 1, nullptr) : launch_tri_i8(t, 1, nullptr))) != SEGP_OK) break;
         e = cudaDeviceSynchronize();
         if (e == cudaSuccess) e = cudaMemcpy(h_acc, d_dbg, n_dbg * sizeof(int32_t), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess)
-            e = cudaMemcpy(h_colsum, d_q + (size_t)bi * I8_N, I8_N * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)   // column sums of the block row(s): [rows / 128][96]
+            e = cudaMemcpy(h_colsum, d_q + (size_t)bi0 * I8_N, (size_t)(rows / TILE) * I8_N * sizeof(double),
+                           cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {
             set_error("segp_i8_selftest: %s", cudaGetErrorString(e));
             rc = SEGP_ERR_CUDA;
@@ -1002,6 +1032,7 @@ int segp_i8_selftest(int device, int k_blocks, const int8_t* h_a, const int8_t* 
     } while (0);
     dev_free(d_a);
     dev_free(d_b);
+    dev_free(d_zero);
     dev_free(d_rf);
     dev_free(d_q);
     dev_free(d_dbg);
@@ -1029,9 +1060,10 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_ksplit = value;
         return SEGP_OK;
     }
-    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 1) {
-        if (value == 1 && m->has_data && !i8_capable(m)) {
-            set_error("tri_mode=1 (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", I8_MAX_NPAD, m->n_pad);
+    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 2) {
+        if (value >= 1 && m->has_data && !i8_capable(m)) {
+            set_error("tri_mode=%ld (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", value, I8_MAX_NPAD,
+                      m->n_pad);
             return SEGP_ERR_UNSUPPORTED;
         }
         m->opt_tri_mode = value;
@@ -1055,7 +1087,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "panel_group") == 0) *value = m->opt_panel_group;
     else if (strcmp(name, "ksplit") == 0) *value = m->opt_ksplit;
     else if (strcmp(name, "tri_mode") == 0) *value = m->opt_tri_mode;
-    else if (strcmp(name, "tri_mode_effective") == 0) *value = use_i8(m) ? 1 : 0;
+    else if (strcmp(name, "tri_mode_effective") == 0) *value = tri_mode(m);
     else if (strcmp(name, "launches") == 0) *value = m->launches;
     else if (strcmp(name, "n_train_padded") == 0) *value = m->n_pad;
     else if (strcmp(name, "workspace_bytes") == 0) *value = (long)m->workspace_bytes;

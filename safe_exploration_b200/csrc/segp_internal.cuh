@@ -97,8 +97,11 @@ constexpr double I8_BASE = 254.0;          // following digits
 
 struct KstarI8Args {
     KstarArgs k;            // model, inputs and mean/Jacobian partial outputs (k.ks unused)
-    int8_t* ki8;            // [n_s][npanel_cap][n_pad/64][I8_S][I8_B_TILE]
+    int8_t* ki8;            // [n_s][npanel_cap][n_pad/64][I8_S][I8_B_TILE]           (split_halves == 0)
+                            // [n_s][npanel_cap][n_pad/64][2][I8_S][I8_B_TILE / 2]    (split_halves == 1: the two
+                            //   48-trajectory halves a CTA pair loads separately for cta_group::2 MMAs)
     long npanel_cap;
+    int split_halves;
 };
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st);
 
@@ -109,10 +112,13 @@ struct TriI8Args {
     double* qpart;          // [n_s][nblk][b_cap]
     int nblk, npanels;
     long npanel_cap, b_cap;
-    int32_t* dbg;           // optional raw accumulators [I8_S][128][I8_N] of tile (0, fix_bi, 0)
-    int fix_bi;             // >= 0: single-tile self-test mode
+    int32_t* dbg;           // optional raw accumulators [I8_S][128 (256 for the pair kernel)][I8_N] of one tile
+    int fix_bi;             // >= 0: single-tile self-test mode (block row, or block-row pair for the pair kernel)
+    const int8_t* zero_a;   // pair kernel: I8_S * I8_A_TILE zero bytes (k-blocks right of the upper block row's diagonal)
 };
 int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);
+// CTA-pair variant: cta_group::2 MMAs, M = 256 (two block rows), each CTA stages its own A rows and half of B
+int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st);
 int tri_i8_init();
 // W (n_pad x n_pad fp64, lower) -> digit planes + row factors for output dimension d
 int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int n_pad, cudaStream_t st);

@@ -218,10 +218,17 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
                 for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
             }
             const int kglob = row0 + r;
-            int8_t* tile0 = panel_base + (long)(kglob >> 6) * (I8_S * I8_B_TILE) + sw64_offset(trow, kglob & 63);
+            int8_t* tile0 = panel_base + (long)(kglob >> 6) * (I8_S * I8_B_TILE);
+            long plane_stride = I8_B_TILE;
+            if (aa.split_halves) {   // [half][plane][48 x 64]: 48 rows keep the 8-row swizzle period intact
+                tile0 += (long)(trow / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) + sw64_offset(trow % (I8_N / 2), kglob & 63);
+                plane_stride = I8_B_TILE / 2;
+            } else {
+                tile0 += sw64_offset(trow, kglob & 63);
+            }
 #pragma unroll
             for (int s = 0; s < I8_S; ++s)
-                *reinterpret_cast<uint4*>(tile0 + (long)s * I8_B_TILE) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+                *reinterpret_cast<uint4*>(tile0 + (long)s * plane_stride) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
         }
     }
     if (active) {
@@ -489,10 +496,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) tri_i8_kernel(const TriI8Args a
     }
 }
 
-int tri_i8_init() {
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
-    return SEGP_OK;
-}
+int tri_i8_init();
 
 int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st) {
     long nblocks = 1;
@@ -506,6 +510,267 @@ int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st) {
     }
     tri_i8_kernel<<<(unsigned)nblocks, I8_THREADS, I8_SMEM, st>>>(a);
     SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== tri_i8x2 (CTA pair)
+// Two CTAs on one TPC (cluster of 2) compute two adjacent block rows (2 bp, 2 bp + 1) x one 96-trajectory panel with
+// tcgen05.mma.cta_group::2, M = 256: every CTA stages its OWN 128 rows of W (5 planes, 40 KB per k-block) and only
+// HALF of the K* panel (48 trajectories, 15 KB); the tensor cores of the pair read both halves.  Against the
+// single-CTA kernel this cuts the shared-memory operand traffic per MMA from 7 KB to 5.5 KB per SM (below the
+// 128 B/clk that capped the N = 96 shape at 84 % of the int8 peak) and the L2 -> SM fill from 70 to 55 KB per k-block.
+// The upper block row's k-range is one diagonal block (two k-blocks) shorter; it reads zero tiles there (2.4 % extra
+// MMA work at N = 5000).  Barriers: local full (own bulk copies) + relay of the peer's full barrier to the leader,
+// empty / tmem_full by multicast tcgen05.commit to both CTAs.
+constexpr int X2_STAGES = 4;
+constexpr int X2_STAGE_BYTES = I8_S * (I8_A_TILE + I8_B_TILE / 2);   // 56320
+constexpr size_t X2_SMEM = (size_t)X2_STAGES * X2_STAGE_BYTES + 1024 + 4 * I8_N * 8 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(local_bar),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "I8C_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra I8C_WAIT_DONE;\n"
+        "bra I8C_WAIT_LOOP;\n"
+        "I8C_WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i8x2_kernel(const TriI8Args a) {
+    const uint32_t rank = cluster_ctarank();
+    const int npairs = (a.nblk + 1) / 2;
+    // ---- tile decode (per cluster): (d, panel group) outer, pair descending (heavy first), panel inner
+    int d, bp, panel;
+    bool skip = false;
+    if (a.fix_bi >= 0) {
+        d = 0;
+        bp = a.fix_bi;
+        panel = 0;
+    } else {
+        const int cid = blockIdx.x >> 1;
+        const int tiles_per_group = I8_PANEL_GROUP * npairs;
+        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        const int gid = cid / tiles_per_group;
+        const int r = cid % tiles_per_group;
+        d = gid / npg;
+        const int pg = gid % npg;
+        bp = npairs - 1 - r / I8_PANEL_GROUP;
+        panel = pg * I8_PANEL_GROUP + r % I8_PANEL_GROUP;
+        skip = panel >= a.npanels;
+    }
+    if (skip) return;   // both CTAs of the cluster take the same decision
+    const int bi = 2 * bp + (int)rank;             // this CTA's block row
+    const bool has_rows = bi < a.nblk;             // odd nblk: the last pair's second CTA only feeds its B half
+    const int bi_hi = min(2 * bp + 1, a.nblk - 1);
+    const int nk = 2 * (bi_hi + 1);                // k-blocks of the pair
+    const int nk_own = has_rows ? 2 * (bi + 1) : 0;   // beyond: zero tiles
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_addr(smem_raw);
+    const uint32_t stage0 = (raw + 1023u) & ~1023u;
+    unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)X2_STAGES * X2_STAGE_BYTES;
+    double* s_col = reinterpret_cast<double*>(tail);                   // [4][I8_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 4 * I8_N);     // full[4], peer_full[4], empty[4], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * X2_STAGES + 1);
+    const uint32_t bar0 = smem_addr(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto peer_full_bar = [&](int s) { return bar0 + 8u * (X2_STAGES + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * X2_STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (3 * X2_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < X2_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(peer_full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
+                     "n"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();   // barriers of both CTAs initialised, TMEM of both allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer: own W rows + own half of K*
+        if (lane == 0) {
+            const int8_t* wsrc = a.wi8 + ((long)d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (I8_S * I8_A_TILE);
+            const int8_t* ksrc = a.ki8 + (((long)d * a.npanel_cap + panel) * (a.nblk * 2)) * (long)(I8_S * I8_B_TILE) +
+                                 (long)rank * (I8_S * (I8_B_TILE / 2));
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % X2_STAGES;
+                if (it >= X2_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((it / X2_STAGES - 1) & 1));
+                const uint32_t dst = stage0 + (uint32_t)s * X2_STAGE_BYTES;
+                mbar_expect_tx(full_bar(s), X2_STAGE_BYTES);
+                const int8_t* asrc = it < nk_own ? wsrc + (long)it * (I8_S * I8_A_TILE) : a.zero_a;
+                bulk_g2s(dst, asrc, I8_S * I8_A_TILE, full_bar(s));
+                bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * (I8_B_TILE / 2), full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            if (rank == 1) {
+                // -------------------------------------------------------------- relay: my stage landed -> tell the leader
+                for (int it = 0; it < nk; ++it) {
+                    const int s = it % X2_STAGES;
+                    mbar_wait(full_bar(s), (uint32_t)((it / X2_STAGES) & 1));
+                    mbar_arrive_remote(peer_full_bar(s), 0u);
+                }
+            } else {
+                // -------------------------------------------------------------- MMA issuer of the pair
+                constexpr uint32_t idesc = make_i8_idesc(2 * TILE, I8_N);
+                for (int it = 0; it < nk; ++it) {
+                    const int s = it % X2_STAGES;
+                    const uint32_t par = (uint32_t)((it / X2_STAGES) & 1);
+                    mbar_wait(full_bar(s), par);
+                    mbar_wait_cluster(peer_full_bar(s), par);
+                    tc_fence_after();
+                    const uint32_t sa = stage0 + (uint32_t)s * X2_STAGE_BYTES;
+                    const uint32_t sb = sa + I8_S * I8_A_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < I8_KB / 32; ++ks) {
+#pragma unroll
+                        for (int pa = 0; pa < I8_S; ++pa) {
+                            const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
+#pragma unroll
+                            for (int pc = 0; pc < I8_S - pa; ++pc) {
+                                const uint64_t bdesc = make_sw64_desc(sb + pc * (I8_B_TILE / 2) + ks * 32);
+                                tc_mma_i8_pair(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, idesc,
+                                               (uint32_t)((it | ks | pa) != 0));
+                            }
+                        }
+                    }
+                    tc_commit_pair(empty_bar(s));
+                }
+                tc_commit_pair(tmem_full_bar);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: own 128 rows, as in tri_i8
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const double rf = has_rows ? a.rowfac[((long)d * a.nblk + bi) * TILE + row] : 0.0;
+        mbar_wait_cluster(tmem_full_bar, 0u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = 0; chunk < I8_N / 32; ++chunk) {
+            long long acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0;
+#pragma unroll
+            for (int dg = 0; dg < I8_S; ++dg) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dg * I8_N + chunk * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = acc[j] * 254 + (long long)(int)v[j];
+                if (a.dbg != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        a.dbg[((long)dg * 2 * TILE + rank * TILE + row) * I8_N + chunk * 32 + j] = (int)v[j];
+                }
+            }
+            double vals[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const double x = (double)acc[j] * rf;
+                vals[j] = x * x;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int j = 0; j < off; ++j) {
+                    const double keep = up ? vals[j + off] : vals[j];
+                    const double give = up ? vals[j] : vals[j + off];
+                    vals[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+                }
+            }
+            s_col[q * I8_N + chunk * 32 + lane] = vals[0];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int c = threadIdx.x - 64;
+        if (c < I8_N && has_rows) {
+            const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
+            const long bcol = (long)panel * I8_N + c;
+            if (bcol < a.b_cap) a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();   // the peer may still read this CTA's shared memory / signal its barriers until here
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st) {
+    long nclusters = 1;
+    if (a.fix_bi < 0) {
+        const int npairs = (a.nblk + 1) / 2;
+        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        nclusters = (long)n_s * npg * I8_PANEL_GROUP * npairs;
+    }
+    if (nclusters <= 0 || 2 * nclusters > 2147483647L) {
+        set_error("tri_i8x2: grid of %ld cluster tiles out of range", nclusters);
+        return SEGP_ERR_INVALID;
+    }
+    tri_i8x2_kernel<<<(unsigned)(2 * nclusters), I8_THREADS, X2_SMEM, st>>>(a);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+int tri_i8_init() {
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     return SEGP_OK;
 }
 

@@ -3,7 +3,9 @@
 * exact integer check of one tile against NumPy (descriptor / swizzle / TMEM layout),
 * predictive variance of both tensor pipes (tri_mode 0 = fp64 DMMA, 1 = int8 tcgen05) against the float64
   oracle on models whose variance cancels 3-4 digits, at BASELINE.json's rtol 1e-4,
-* the two pipes against each other on a rollout at the C4 model size.
+* the pipes against each other on a rollout at the C4 model size (N = 5000 pads to 40 block rows; the odd
+  block-row count of the CTA-pair kernel is covered by the N = 1500 / 3000 predict cases: 12 and 24 ... and N = 2000
+  pads to 16; see test_pair_kernel_odd_block_rows).
 """
 import ctypes
 
@@ -22,19 +24,23 @@ def se():
     return pkg
 
 
-@pytest.mark.parametrize("k_blocks", [1, 2, 5])
-def test_one_tile_exact_integers(se, k_blocks):
+@pytest.mark.parametrize("variant,k_blocks", [(1, 1), (1, 2), (1, 5), (2, 2), (2, 4), (2, 6)])
+def test_one_tile_exact_integers(se, variant, k_blocks):
+    """variant 1: single-CTA kernel, 128 rows; variant 2: CTA pair (cta_group::2), 256 rows."""
     lib = se._lib.load()
-    rng = np.random.default_rng(10 + k_blocks)
+    rng = np.random.default_rng(10 * variant + k_blocks)
     kdim = TILE * k_blocks
-    a = rng.integers(-127, 128, size=(I8_S, TILE, kdim), dtype=np.int8)
+    rows = TILE * variant
+    a = rng.integers(-127, 128, size=(I8_S, rows, kdim), dtype=np.int8)
+    if variant == 2:
+        a[:, :TILE, kdim - TILE:] = 0      # the upper block row ends one diagonal block earlier
     b = rng.integers(-127, 128, size=(I8_S, I8_N, kdim), dtype=np.int8)
-    acc = np.zeros((I8_S, TILE, I8_N), dtype=np.int32)
-    colsum = np.zeros(I8_N, dtype=np.float64)
-    se._lib.check(lib.segp_i8_selftest(0, k_blocks, a.ctypes.data_as(ctypes.c_void_p),
+    acc = np.zeros((I8_S, rows, I8_N), dtype=np.int32)
+    colsum = np.zeros((variant, I8_N), dtype=np.float64)
+    se._lib.check(lib.segp_i8_selftest(0, variant, k_blocks, a.ctypes.data_as(ctypes.c_void_p),
                                        b.ctypes.data_as(ctypes.c_void_p), acc.ctypes.data_as(ctypes.c_void_p),
                                        colsum.ctypes.data_as(ctypes.c_void_p)))
-    want = np.zeros((I8_S, TILE, I8_N), dtype=np.int64)
+    want = np.zeros((I8_S, rows, I8_N), dtype=np.int64)
     a64, b64 = a.astype(np.int64), b.astype(np.int64)
     for pa in range(I8_S):
         for pc in range(I8_S - pa):
@@ -42,11 +48,13 @@ def test_one_tile_exact_integers(se, k_blocks):
     assert np.abs(want).max() < 2 ** 31
     assert np.array_equal(acc.astype(np.int64), want), "first mismatch at {}".format(
         np.argwhere(acc.astype(np.int64) != want)[:4])
-    horner = np.zeros((TILE, I8_N), dtype=object)
+    horner = np.zeros((rows, I8_N), dtype=object)
     for g in range(I8_S):
         horner = horner * 254 + want[g].astype(object)
-    want_col = np.array([float(sum(int(v) ** 2 for v in horner[:, c])) for c in range(I8_N)])
-    assert np.allclose(colsum, want_col, rtol=1e-13, atol=0.0)
+    for rb in range(variant):
+        want_col = np.array([float(sum(int(v) ** 2 for v in horner[rb * TILE:(rb + 1) * TILE, c]))
+                             for c in range(I8_N)])
+        assert np.allclose(colsum[rb], want_col, rtol=1e-13, atol=0.0)
 
 
 def test_i8_peak_reports(se):
@@ -73,7 +81,7 @@ def _cancelling_model(se, n, n_s, n_u, kern, seed, tri_mode):
     return gp, ora, z
 
 
-@pytest.mark.parametrize("tri_mode", [0, 1])
+@pytest.mark.parametrize("tri_mode", [0, 1, 2])
 @pytest.mark.parametrize("n,n_s,n_u,kern", [(1500, 2, 1, "rbf"), (3000, 4, 1, "rbf"), (2000, 3, 2, "mat52")])
 def test_predict_variance_under_cancellation(se, n, n_s, n_u, kern, tri_mode):
     gp, ora, z = _cancelling_model(se, n, n_s, n_u, kern, 5, tri_mode)
@@ -94,14 +102,27 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
     from safe_exploration_b200 import workloads
     w = workloads.make("C4", batch=700)
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp,
                              tri_mode=mode)
         out[mode] = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
         gp.close()
-    assert np.all(out[0].status == 0) and np.all(out[1].status == 0)
+    assert all(np.all(o.status == 0) for o in out.values())
+    # the two tcgen05 kernels execute the same exact integer arithmetic: identical bits
+    assert np.array_equal(out[1].q_all, out[2].q_all) and np.array_equal(out[1].var_all, out[2].var_all)
     for name in ("var_all", "p_all", "q_all"):
-        a0, a1 = getattr(out[0], name), getattr(out[1], name)
+        a0, a1 = getattr(out[0], name), getattr(out[2], name)
         err = float(np.max(np.abs(a1 - a0) / (np.abs(a0) + 1e-12 * np.abs(a0).max())))
         print("C4 model, %s: int8 vs fp64 pipe max rel diff %.2e" % (name, err))
         assert err < 2e-5
+
+
+def test_pair_kernel_odd_block_rows(se):
+    """N = 1100 pads to 9 block rows: the last CTA pair has only one real block row."""
+    gp, ora, z = _cancelling_model(se, 1100, 2, 1, "rbf", 9, 2)
+    assert gp.get_option("n_train_padded") == 1152
+    mu, var, _ = gp.predict(z, compute_gradients=True)
+    mu_o, var_o, _ = ora.predict_batch(z)
+    assert float(np.max(np.abs(var - var_o) / np.abs(var_o))) < 1e-5
+    assert float(np.max(np.abs(mu - mu_o) / (np.abs(mu_o) + 1e-6))) < 1e-6
+    gp.close()
