@@ -231,6 +231,8 @@ def run_product(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    if os.environ.get("SEGP_I8_ABLATE"):
+        gp.set_option("i8_ablate", int(os.environ["SEGP_I8_ABLATE"]))   # profiling experiments only
     launches0 = gp.get_option("launches")
     gp.set_option("time_tri", 1)
     ev0 = torch.cuda.Event(enable_timing=True)

@@ -90,6 +90,7 @@ struct segp_model {
     long opt_ksplit = 0;   // 0 = automatic
     long opt_tri_mode = -1;   // -1 = automatic (2 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
                               // 1 = int8 tcgen05 single CTA, 2 = int8 tcgen05 CTA pair (cta_group::2)
+    long opt_i8_ablate = 0;   // profiling only, see TriI8Args::ablate
     long launches = 0;
     // optional per-launch timing of tri_sumsq (bench.py roofline): event pairs recorded on the launching stream
     bool time_tri = false;
@@ -148,7 +149,7 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     if (m->opt_ksplit > 0) {
         nsplit = (int)std::min<long>(m->opt_ksplit, m->nblk);
     } else {
-        const long target = 4 * 148;
+        const long target = 16 * 148;   // ~48 warps per SM for the (latency-bound, fp64) K* kernels
         nsplit = (int)std::max<long>(1, std::min<long>(m->nblk, (target + col_blocks * m->n_s - 1) / (col_blocks * m->n_s)));
     }
     const int bps = (m->nblk + nsplit - 1) / nsplit;
@@ -282,6 +283,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st) {
         t.dbg = nullptr;
         t.fix_bi = -1;
         t.zero_a = m->i8zero;
+        t.ablate = (int)m->opt_i8_ablate;
         SEGP_CHECK(m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st) : launch_tri_i8(t, m->n_s, st));
     } else {
         TriArgs t{};
@@ -1067,6 +1069,10 @@ int segp_set_option(segp_model* m, const char* name, long value) {
             return SEGP_ERR_UNSUPPORTED;
         }
         m->opt_tri_mode = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "i8_ablate") == 0) {
+        m->opt_i8_ablate = value;
         return SEGP_OK;
     }
     if (strcmp(name, "time_tri") == 0) {

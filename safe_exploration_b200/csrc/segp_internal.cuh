@@ -114,6 +114,7 @@ struct TriI8Args {
     long npanel_cap, b_cap;
     int32_t* dbg;           // optional raw accumulators [I8_S][128 (256 for the pair kernel)][I8_N] of one tile
     int fix_bi;             // >= 0: single-tile self-test mode (block row, or block-row pair for the pair kernel)
+    int ablate;             // profiling only (pair kernel): 1 = no bulk copies, 2 = no MMAs, 4 = no epilogue math
     const int8_t* zero_a;   // pair kernel: I8_S * I8_A_TILE zero bytes (k-blocks right of the upper block row's diagonal)
 };
 int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);

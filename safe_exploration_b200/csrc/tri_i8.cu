@@ -35,6 +35,28 @@ __device__ __forceinline__ void split_digits(double r, int (&dg)[I8_S]) {
     }
 }
 
+// Same representation for u in [0, 1] (kernel values), with two float64 roundings instead of five and the digit
+// arithmetic on the integer pipes: u 127 254^4 ~= hi 254^2 + lo, hi = rn(u 127 254^2) in [0, 8193532],
+// lo = rn(frac 254^2) in [-32258, 32258], then balanced base-254 digits of hi (3) and lo (2).
+__device__ __forceinline__ void split_digits_unit(double u, int (&dg)[I8_S]) {
+    static_assert(I8_S == 5, "digit layout below is for 5 planes");
+    const double x = u * (I8_BASE0 * I8_BASE * I8_BASE);
+    const int hi = __double2int_rn(x);
+    const int lo = __double2int_rn((x - (double)hi) * (I8_BASE * I8_BASE));
+    // balanced remainder: v = 254 q + d, d in [-127, 126]; offsets keep the dividends non-negative
+    const unsigned lo_s = (unsigned)(lo + 127 + 254 * 128);
+    const unsigned q3 = lo_s / 254u;
+    dg[4] = (int)(lo_s - q3 * 254u) - 127;
+    dg[3] = (int)q3 - 128;
+    const unsigned hi_s = (unsigned)(hi + 127);
+    const unsigned q1 = hi_s / 254u;
+    dg[2] = (int)(hi_s - q1 * 254u) - 127;
+    const unsigned q1_s = q1 + 127u;
+    const unsigned q0 = q1_s / 254u;
+    dg[1] = (int)(q1_s - q0 * 254u) - 127;
+    dg[0] = (int)q0;
+}
+
 // byte offset of element (row, k) inside a K-major SWIZZLE_64B tile image (rows of 64 bytes, 16-byte chunks
 // XOR-ed with address bits [7,9) = (row >> 1) & 3)
 __host__ __device__ __forceinline__ int sw64_offset(int row, int k) {
@@ -213,7 +235,7 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
                 for (int j = 0; j < DM; ++j)
                     if (j < dim) jac[j] = fma(w, diff[j], jac[j]);
                 int dg[I8_S];
-                split_digits(unit, dg);
+                split_digits_unit(unit, dg);
 #pragma unroll
                 for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
             }
@@ -333,6 +355,70 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// =========================================================================================== epilogue helper
+// One warp, its 32 accumulator rows, 32 columns [col0, col0 + 32): recombine the I8_S diagonals
+//   v = sum_g C_g 254^(S-1-g)   as   ((C0 254 + C1) 254^2 + (C2 254 + C3)) 254 + C4
+// -- the two inner brackets exactly in int64 (one IMAD.WIDE each), the outer two steps as float64 FMAs (relative
+// error 2^-53, far below the 2^-39 resolution of the digits) -- scale by the row factor, square, and transpose-
+// reduce over the 32 rows: after the 5 halving steps lane l returns the sum of column col0 + l.
+__device__ __forceinline__ double i8_epilogue_chunk(uint32_t tmem_quadrant_base, int col0, double rf, int lane,
+                                                    int32_t* dbg_row, long dbg_plane_stride) {
+    static_assert(I8_S == 5, "recombination below is written for 5 diagonals");
+    uint32_t v[32];
+    long long t01[32], t23[32];
+    tmem_ld32(tmem_quadrant_base + (uint32_t)(0 * I8_N + col0), v);
+    if (dbg_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbg_row[0 * dbg_plane_stride + col0 + j] = (int)v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t01[j] = (long long)(int)v[j] * 254;
+    tmem_ld32(tmem_quadrant_base + (uint32_t)(1 * I8_N + col0), v);
+    if (dbg_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbg_row[1 * dbg_plane_stride + col0 + j] = (int)v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t01[j] += (long long)(int)v[j];
+    tmem_ld32(tmem_quadrant_base + (uint32_t)(2 * I8_N + col0), v);
+    if (dbg_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbg_row[2 * dbg_plane_stride + col0 + j] = (int)v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t23[j] = (long long)(int)v[j] * 254;
+    tmem_ld32(tmem_quadrant_base + (uint32_t)(3 * I8_N + col0), v);
+    if (dbg_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbg_row[3 * dbg_plane_stride + col0 + j] = (int)v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t23[j] += (long long)(int)v[j];
+    tmem_ld32(tmem_quadrant_base + (uint32_t)(4 * I8_N + col0), v);
+    if (dbg_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbg_row[4 * dbg_plane_stride + col0 + j] = (int)v[j];
+    }
+    double vals[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double hi = fma((double)t01[j], I8_BASE * I8_BASE, (double)t23[j]);
+        const double x = fma(hi, I8_BASE, (double)(int)v[j]) * rf;
+        vals[j] = x * x;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const double keep = up ? vals[j + off] : vals[j];
+            const double give = up ? vals[j] : vals[j + off];
+            vals[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+        }
+    }
+    return vals[0];
+}
+
 // =========================================================================================== tri_i8
 constexpr int I8_STAGES = 3;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_TILE + I8_B_TILE);   // 71680
@@ -445,41 +531,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) tri_i8_kernel(const TriI8Args a
         const double rf = a.rowfac[((long)d * a.nblk + bi) * TILE + row];
         mbar_wait(tmem_full_bar, 0u);
         tc_fence_after();
+        int32_t* dbg_row = a.dbg != nullptr ? a.dbg + (long)row * I8_N : nullptr;
 #pragma unroll 1
-        for (int chunk = 0; chunk < I8_N / 32; ++chunk) {
-            long long acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0;
-#pragma unroll
-            for (int dg = 0; dg < I8_S; ++dg) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dg * I8_N + chunk * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = acc[j] * 254 + (long long)(int)v[j];   // exact: |acc| < 2^63
-                if (a.dbg != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) a.dbg[((long)dg * TILE + row) * I8_N + chunk * 32 + j] = (int)v[j];
-                }
-            }
-            double vals[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const double x = (double)acc[j] * rf;
-                vals[j] = x * x;
-            }
-            // transpose-reduce over the 32 rows of the warp: after the 5 halving steps lane l holds column l
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int j = 0; j < off; ++j) {
-                    const double keep = up ? vals[j + off] : vals[j];
-                    const double give = up ? vals[j] : vals[j + off];
-                    vals[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
-                }
-            }
-            s_col[q * I8_N + chunk * 32 + lane] = vals[0];
-        }
+        for (int chunk = 0; chunk < I8_N / 32; ++chunk)
+            s_col[q * I8_N + chunk * 32 + lane] = i8_epilogue_chunk(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf,
+                                                                    lane, dbg_row, (long)TILE * I8_N);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int c = threadIdx.x - 64;
         if (c < I8_N) {
@@ -551,7 +607,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "I8C_WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra I8C_WAIT_DONE;\n"
         "bra I8C_WAIT_LOOP;\n"
         "I8C_WAIT_DONE:\n"
@@ -650,6 +706,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i
                 const int s = it % X2_STAGES;
                 if (it >= X2_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((it / X2_STAGES - 1) & 1));
                 const uint32_t dst = stage0 + (uint32_t)s * X2_STAGE_BYTES;
+                if (a.ablate & 1) {
+                    mbar_expect_tx(full_bar(s), 0);
+                    continue;
+                }
                 mbar_expect_tx(full_bar(s), X2_STAGE_BYTES);
                 const int8_t* asrc = it < nk_own ? wsrc + (long)it * (I8_S * I8_A_TILE) : a.zero_a;
                 bulk_g2s(dst, asrc, I8_S * I8_A_TILE, full_bar(s));
@@ -678,6 +738,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i
                     const uint32_t sb = sa + I8_S * I8_A_TILE;
 #pragma unroll
                     for (int ks = 0; ks < I8_KB / 32; ++ks) {
+                        if (a.ablate & 2) break;
 #pragma unroll
                         for (int pa = 0; pa < I8_S; ++pa) {
                             const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
@@ -701,41 +762,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i
         const double rf = has_rows ? a.rowfac[((long)d * a.nblk + bi) * TILE + row] : 0.0;
         mbar_wait_cluster(tmem_full_bar, 0u);
         tc_fence_after();
+        int32_t* dbg_row = a.dbg != nullptr ? a.dbg + ((long)rank * TILE + row) * I8_N : nullptr;
 #pragma unroll 1
-        for (int chunk = 0; chunk < I8_N / 32; ++chunk) {
-            long long acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0;
-#pragma unroll
-            for (int dg = 0; dg < I8_S; ++dg) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dg * I8_N + chunk * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = acc[j] * 254 + (long long)(int)v[j];
-                if (a.dbg != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        a.dbg[((long)dg * 2 * TILE + rank * TILE + row) * I8_N + chunk * 32 + j] = (int)v[j];
-                }
-            }
-            double vals[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const double x = (double)acc[j] * rf;
-                vals[j] = x * x;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int j = 0; j < off; ++j) {
-                    const double keep = up ? vals[j + off] : vals[j];
-                    const double give = up ? vals[j] : vals[j + off];
-                    vals[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
-                }
-            }
-            s_col[q * I8_N + chunk * 32 + lane] = vals[0];
-        }
+        for (int chunk = 0; chunk < ((a.ablate & 4) ? 0 : I8_N / 32); ++chunk)
+            s_col[q * I8_N + chunk * 32 + lane] = i8_epilogue_chunk(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf,
+                                                                    lane, dbg_row, (long)2 * TILE * I8_N);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int c = threadIdx.x - 64;
         if (c < I8_N && has_rows) {
