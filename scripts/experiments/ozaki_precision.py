@@ -57,3 +57,9 @@ for d in range(min(w.n_s, 2)):
             rel = np.abs(var_o - var) / np.abs(var)
             print("   bits %d slices %d (products %2d): var rel err max %.2e median %.2e" % (
                 bits, s, s * (s + 1) // 2, rel.max(), np.median(rel)))
+    # fp32-accumulating pipelines for comparison (what any floating tcgen05 kind delivers at best): float32
+    # operands, products and sums
+    v32 = (W.astype(np.float32) @ ks.astype(np.float32)).astype(np.float64)
+    var32 = hyp["variance"] - np.sum(v32 * v32, axis=0)
+    rel = np.abs(var32 - var) / np.abs(var)
+    print("   float32 operands + float32 accumulation: var rel err max %.2e median %.2e" % (rel.max(), np.median(rel)))
