@@ -27,6 +27,15 @@ def se():
     return pkg
 
 
+@pytest.fixture(autouse=True, params=[0, 2], ids=["fp64-dmma", "int8-tcgen05"])
+def _tri_mode(request, se):
+    """Every parity test runs on both tensor pipes of the variance contraction (include/segp.h, "tri_mode")."""
+    old = se.ssm.DEFAULT_TRI_MODE
+    se.ssm.DEFAULT_TRI_MODE = request.param
+    yield request.param
+    se.ssm.DEFAULT_TRI_MODE = old
+
+
 def _make_models(se, x, y, n_s_in, n_u, kern_types, ls, var, noise_total):
     from oracle.gp_oracle import GPOracle
     # the product adds noise_diag + jitter itself; subtract them so both sides factorise the same matrix
