@@ -50,14 +50,16 @@ def test_no_cpp_or_torch_types_cross_the_boundary():
         assert banned not in re.sub(r"/\*.*?\*/", "", src, flags=re.S)
 
 
-def test_library_is_sm100a_sass_with_dmma_and_bulk_copies():
-    """The shipped binary holds sm_100a SASS: the FP64 tensor-pipe instruction (DMMA) of the variance
-    contraction and TMA bulk copies (UBLKCP) with mbarrier transactions (SYNCS)."""
+def test_library_is_sm100a_sass_with_tcgen05_dmma_and_bulk_copies():
+    """The shipped binary holds sm_100a SASS: tcgen05 int8 MMAs (UTCIMMA) with TMEM loads (LDTM) for the variance
+    contraction, the FP64 tensor-pipe instruction (DMMA) of its float64 variant and of the factorisation, and TMA
+    bulk copies (UBLKCP) with mbarrier transactions (SYNCS)."""
     from safe_exploration_b200 import build
     out = subprocess.run(["cuobjdump", "-sass", build.LIB_PATH], capture_output=True, text=True)
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout
+    assert "UTCIMMA" in out.stdout and "LDTM" in out.stdout
     assert "DMMA" in out.stdout
     assert "UBLKCP" in out.stdout and "SYNCS" in out.stdout
 
