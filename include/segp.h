@@ -49,6 +49,7 @@ extern "C" {
 /* limits of this build */
 #define SEGP_MAX_NS 16
 #define SEGP_MAX_NU 8
+#define SEGP_MAX_CONSTR 64 /* rows of one constraint polytope (segp_score_rollouts) */
 
 typedef struct segp_model segp_model;
 
@@ -166,6 +167,49 @@ int segp_ellipsoid_from_rectangle(int device, long n_batch, int n, const double*
 int segp_safety_distance(int device, long n_items, int n_s, int m, const double* d_p, const double* d_q,
                          const double* h_h_mat, const double* h_h_vec, double c_safety, double* d_dist,
                          void* stream);
+
+/* ---- scoring of rolled-out candidates: what SimpleSafeMPC assembles symbolically around the reachability call ---- */
+#define SEGP_COST_EXPLORATION 0 /* - sum_t sqrt(sum_d (var_d(t) + eps_noise))  (safempc_simple.py:303-305)       */
+#define SEGP_COST_QUADRATIC 1   /* sum_t (p_t - x_ref)^T Wx (p_t - x_ref) + u_t^T Wu u_t                          */
+
+typedef struct segp_score_params {
+    const double* h_u_min;     /* [n_u] control bounds or NULL (ctrl_bounds[:,0], safempc_simple.py:488-532)       */
+    const double* h_u_max;     /* [n_u]                                                                            */
+    int m_obs;                 /* rows of the obstacle polytope h_mat_obs x <= h_obs (0 = none), steps 0..H-2      */
+    const double* h_mat_obs;   /* [m_obs x n_s]  (safempc_simple.py:369-378)                                       */
+    const double* h_obs;       /* [m_obs]                                                                          */
+    int m_safe;                /* rows of the terminal safe-set polytope, step H-1 (safempc_simple.py:380-389)     */
+    const double* h_mat_safe;  /* [m_safe x n_s]                                                                   */
+    const double* h_safe;      /* [m_safe]                                                                         */
+    double c_safety;           /* factor on the ellipsoid support term; the reference passes 1 here                */
+    double eps_constraints;    /* feasible iff every g < eps_constraints (1e-5, safempc_simple.py:913)             */
+    int cost_type;             /* SEGP_COST_*                                                                      */
+    double eps_noise;          /* exploration cost                                                                 */
+    const double* h_wx;        /* [n_s x n_s], quadratic cost                                                      */
+    const double* h_wu;        /* [n_u x n_u]                                                                      */
+    const double* h_x_ref;     /* [n_s] or NULL (origin)                                                           */
+} segp_score_params;
+
+/* Number of constraint values per candidate: (has_ctrl ? 2 n_u H : 0) + (H-1) m_obs + m_safe. */
+int segp_score_num_constraints(int horizon, int n_u, const segp_score_params* params);
+
+/* Constraint values, feasibility and cost of n_batch rolled-out candidates (outputs of segp_multistep).
+ * Replaces generate_safety_constraints (safempc_simple.py:317-392), _generate_control_constraint (:488-532),
+ * eval_safety_constraints (:911-942) and the default generate_cost_function (:286-315), per candidate.
+ *   d_p_all [B x H x n_s], d_q_all [B x H x n_s x n_s], d_var_all [B x H x n_s] (exploration cost; else may be NULL)
+ *   d_k_ff [B x H x n_u] (row 0 is u_0), d_k_fb [(H-1) x n_u x n_s] (kfb_stride 0) or per candidate
+ *   d_status [B] int32 from the rollout or NULL: a candidate with a non-zero status is infeasible
+ *   out: d_cost [B], d_feasible [B] int32, d_violation [B] (max constraint value), d_g [B x n_g] or NULL */
+int segp_score_rollouts(int device, long n_batch, int horizon, int n_s, int n_u, const double* d_p_all,
+                        const double* d_q_all, const double* d_var_all, const double* d_k_ff, const double* d_k_fb,
+                        long kfb_stride, const int32_t* d_status, const segp_score_params* params, double* d_cost,
+                        int32_t* d_feasible, double* d_violation, double* d_g, void* stream);
+
+/* Lowest-cost feasible candidate (or, if none is feasible, the least-violating one, *h_feasible = 0); synchronous.
+ * Replaces the IPOPT solve + feasibility test of SimpleSafeMPC.solve/_get_solution (:672-742, 874-904) on the
+ * sampling path.  *h_index = -1 if n_batch == 0 or every candidate is NaN. */
+int segp_argbest(int device, long n_batch, const double* d_cost, const int32_t* d_feasible, const double* d_violation,
+                 long* h_index, double* h_cost, double* h_violation, int* h_feasible, void* stream);
 
 /* Diagnostic: sustained FP64 tensor-pipe (DMMA m8n8k4) rate of `device` in TFLOP/s, measured by a register-only
  * kernel (148 x 4 CTAs x 8 warps, `iters` x 64 independent DMMAs per warp).  bench.py reports tri_sumsq against it,

@@ -38,6 +38,17 @@ class ReachParams(ctypes.Structure):
                 ("h_a", _c_double_p), ("h_b", _c_double_p), ("h_t_z_gp", _c_double_p)]
 
 
+class ScoreParams(ctypes.Structure):
+    """struct segp_score_params (include/segp.h)."""
+    _fields_ = [("h_u_min", _c_double_p), ("h_u_max", _c_double_p), ("m_obs", _int), ("h_mat_obs", _c_double_p),
+                ("h_obs", _c_double_p), ("m_safe", _int), ("h_mat_safe", _c_double_p), ("h_safe", _c_double_p),
+                ("c_safety", _dbl), ("eps_constraints", _dbl), ("cost_type", _int), ("eps_noise", _dbl),
+                ("h_wx", _c_double_p), ("h_wu", _c_double_p), ("h_x_ref", _c_double_p)]
+
+
+COST_EXPLORATION = 0
+COST_QUADRATIC = 1
+
 # name -> (restype, argtypes); kept in one table so tests can check it against include/segp.h
 PROTOTYPES = {
     "segp_abi_version": (_int, []),
@@ -63,6 +74,11 @@ PROTOTYPES = {
     "segp_sum_two_ellipsoids": (_int, [_int, _long, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "segp_ellipsoid_from_rectangle": (_int, [_int, _long, _int, _vp, _vp, _vp, _vp]),
     "segp_safety_distance": (_int, [_int, _long, _int, _int, _vp, _vp, _c_double_p, _c_double_p, _dbl, _vp, _vp]),
+    "segp_score_num_constraints": (_int, [_int, _int, ctypes.POINTER(ScoreParams)]),
+    "segp_score_rollouts": (_int, [_int, _long, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _long, _vp,
+                                   ctypes.POINTER(ScoreParams), _vp, _vp, _vp, _vp, _vp]),
+    "segp_argbest": (_int, [_int, _long, _vp, _vp, _vp, ctypes.POINTER(_long), ctypes.POINTER(_dbl),
+                            ctypes.POINTER(_dbl), ctypes.POINTER(_int), _vp]),
     "segp_dmma_peak": (_int, [_int, _int, ctypes.POINTER(_dbl)]),
     "segp_i8_peak": (_int, [_int, _int, _int, ctypes.POINTER(_dbl)]),
     "segp_i8_selftest": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),

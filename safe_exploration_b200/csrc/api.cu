@@ -930,6 +930,146 @@ int segp_safety_distance(int device, long n_items, int n_s, int m, const double*
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------- scoring
+static int fill_score_params(ScoreParams* sp, const segp_score_params* prm, int n_s, int n_u) {
+    memset(sp, 0, sizeof(*sp));
+    if (prm == nullptr) {
+        set_error("score params: null");
+        return SEGP_ERR_INVALID;
+    }
+    if (prm->m_obs < 0 || prm->m_obs > SEGP_MAX_CONSTR || prm->m_safe < 0 || prm->m_safe > SEGP_MAX_CONSTR) {
+        set_error("score params: polytopes are limited to %d rows (m_obs=%d, m_safe=%d)", SEGP_MAX_CONSTR, prm->m_obs,
+                  prm->m_safe);
+        return SEGP_ERR_INVALID;
+    }
+    if ((prm->m_obs > 0 && (prm->h_mat_obs == nullptr || prm->h_obs == nullptr)) ||
+        (prm->m_safe > 0 && (prm->h_mat_safe == nullptr || prm->h_safe == nullptr)) ||
+        ((prm->h_u_min == nullptr) != (prm->h_u_max == nullptr))) {
+        set_error("score params: inconsistent null pointers");
+        return SEGP_ERR_INVALID;
+    }
+    sp->has_ctrl = prm->h_u_min != nullptr;
+    for (int j = 0; j < n_u && sp->has_ctrl; ++j) {
+        sp->u_min[j] = prm->h_u_min[j];
+        sp->u_max[j] = prm->h_u_max[j];
+    }
+    sp->m_obs = prm->m_obs;
+    sp->m_safe = prm->m_safe;
+    for (int i = 0; i < prm->m_obs * n_s; ++i) sp->h_mat_obs[i] = prm->h_mat_obs[i];
+    for (int i = 0; i < prm->m_obs; ++i) sp->h_obs[i] = prm->h_obs[i];
+    for (int i = 0; i < prm->m_safe * n_s; ++i) sp->h_mat_safe[i] = prm->h_mat_safe[i];
+    for (int i = 0; i < prm->m_safe; ++i) sp->h_safe[i] = prm->h_safe[i];
+    sp->c_safety = prm->c_safety;
+    sp->eps_constraints = prm->eps_constraints;
+    sp->eps_noise = prm->eps_noise;
+    sp->cost_type = prm->cost_type;
+    if (prm->cost_type == SEGP_COST_QUADRATIC) {
+        if (prm->h_wx == nullptr || prm->h_wu == nullptr) {
+            set_error("score params: the quadratic cost needs h_wx and h_wu");
+            return SEGP_ERR_INVALID;
+        }
+        for (int i = 0; i < n_s * n_s; ++i) sp->wx[i] = prm->h_wx[i];
+        for (int i = 0; i < n_u * n_u; ++i) sp->wu[i] = prm->h_wu[i];
+        for (int i = 0; i < n_s; ++i) sp->x_ref[i] = prm->h_x_ref ? prm->h_x_ref[i] : 0.0;
+    } else if (prm->cost_type != SEGP_COST_EXPLORATION) {
+        set_error("score params: unknown cost type %d", prm->cost_type);
+        return SEGP_ERR_INVALID;
+    }
+    return SEGP_OK;
+}
+
+int segp_score_num_constraints(int horizon, int n_u, const segp_score_params* params) {
+    if (params == nullptr || horizon < 1) return -1;
+    return (params->h_u_min != nullptr ? 2 * n_u * horizon : 0) + (horizon - 1) * params->m_obs + params->m_safe;
+}
+
+int segp_score_rollouts(int device, long n_batch, int horizon, int n_s, int n_u, const double* d_p_all,
+                        const double* d_q_all, const double* d_var_all, const double* d_k_ff, const double* d_k_fb,
+                        long kfb_stride, const int32_t* d_status, const segp_score_params* params, double* d_cost,
+                        int32_t* d_feasible, double* d_violation, double* d_g, void* stream) {
+    SEGP_CHECK(check_dims(n_s, n_s, n_u));
+    if (n_batch <= 0 || horizon < 1) return (n_batch == 0 && horizon >= 1) ? SEGP_OK : SEGP_ERR_INVALID;
+    ScoreParams sp;
+    SEGP_CHECK(fill_score_params(&sp, params, n_s, n_u));
+    if (d_p_all == nullptr || d_q_all == nullptr || d_k_ff == nullptr || d_cost == nullptr || d_feasible == nullptr ||
+        d_violation == nullptr || (sp.cost_type == SEGP_COST_EXPLORATION && d_var_all == nullptr) ||
+        (sp.has_ctrl && horizon > 1 && d_k_fb == nullptr)) {
+        set_error("segp_score_rollouts: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScoreParams* d_sp = nullptr;
+    SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_sp), sizeof(ScoreParams), st));
+    cudaError_t e = cudaMemcpyAsync(d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, st);
+    int rc = SEGP_OK;
+    if (e != cudaSuccess) {
+        set_error("segp_score_rollouts: %s", cudaGetErrorString(e));
+        rc = SEGP_ERR_CUDA;
+    } else {
+        // the host copy `sp` must outlive the asynchronous upload: pageable memory is staged by the runtime before
+        // cudaMemcpyAsync returns, so this is safe
+        ScoreArgs a{};
+        a.p_all = d_p_all;
+        a.q_all = d_q_all;
+        a.var_all = d_var_all;
+        a.kff = d_k_ff;
+        a.kfb = d_k_fb;
+        a.kfb_stride = kfb_stride;
+        a.status = d_status;
+        a.sp = d_sp;
+        a.cost = d_cost;
+        a.feasible = d_feasible;
+        a.violation = d_violation;
+        a.g = d_g;
+        a.n_batch = n_batch;
+        a.horizon = horizon;
+        a.n_s = n_s;
+        a.n_u = n_u;
+        a.n_g = segp_score_num_constraints(horizon, n_u, params);
+        rc = launch_score(a, st);
+    }
+    cudaFreeAsync(d_sp, st);
+    return rc;
+}
+
+int segp_argbest(int device, long n_batch, const double* d_cost, const int32_t* d_feasible, const double* d_violation,
+                 long* h_index, double* h_cost, double* h_violation, int* h_feasible, void* stream) {
+    if (h_index == nullptr) {
+        set_error("segp_argbest: null output");
+        return SEGP_ERR_INVALID;
+    }
+    *h_index = -1;
+    if (h_feasible) *h_feasible = 0;
+    if (n_batch <= 0) return n_batch == 0 ? SEGP_OK : SEGP_ERR_INVALID;
+    if (d_cost == nullptr || d_feasible == nullptr || d_violation == nullptr) {
+        set_error("segp_argbest: null buffer");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BestCandidate* d_out = nullptr;
+    SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_out), sizeof(BestCandidate), st));
+    int rc = launch_argbest(n_batch, d_cost, d_feasible, d_violation, d_out, st);
+    BestCandidate out{};
+    if (rc == SEGP_OK) {
+        cudaError_t e = cudaMemcpyAsync(&out, d_out, sizeof(out), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("segp_argbest: %s", cudaGetErrorString(e));
+            rc = SEGP_ERR_CUDA;
+        }
+    }
+    cudaFreeAsync(d_out, st);
+    if (rc == SEGP_OK) {
+        *h_index = out.index;
+        if (h_cost) *h_cost = out.cost;
+        if (h_violation) *h_violation = out.violation;
+        if (h_feasible) *h_feasible = out.feasible;
+    }
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------- tcgen05 diagnostics
 int segp_i8_peak(int device, int umma_n, int iters, double* tops) {
     DeviceGuard guard(device);

@@ -183,6 +183,41 @@ int launch_from_rectangle(long n_batch, int n, const double* ub, double* q, int3
 int launch_safety_distance(long n_items, int n_s, int m, const double* p, const double* q, const double* hmat,
                            const double* hvec, double c, double* dist, cudaStream_t st);
 
+// ---------------------------------------------------------------- candidate scoring (constraints, cost, arg-best)
+struct ScoreParams {
+    double u_min[SEGP_MAX_NU], u_max[SEGP_MAX_NU];
+    double h_mat_obs[SEGP_MAX_CONSTR * SEGP_MAX_NS], h_obs[SEGP_MAX_CONSTR];
+    double h_mat_safe[SEGP_MAX_CONSTR * SEGP_MAX_NS], h_safe[SEGP_MAX_CONSTR];
+    double wx[SEGP_MAX_NS * SEGP_MAX_NS], wu[SEGP_MAX_NU * SEGP_MAX_NU], x_ref[SEGP_MAX_NS];
+    double c_safety, eps_constraints, eps_noise;
+    int has_ctrl, m_obs, m_safe, cost_type;
+};
+struct ScoreArgs {
+    const double* p_all;      // [B][H][n_s]
+    const double* q_all;      // [B][H][n_s][n_s]
+    const double* var_all;    // [B][H][n_s]  (exploration cost only)
+    const double* kff;        // [B][H][n_u]
+    const double* kfb;        // [(B)][H-1][n_u][n_s]
+    long kfb_stride;
+    const int32_t* status;    // [B] or NULL
+    const ScoreParams* sp;
+    double* cost;             // [B]
+    int32_t* feasible;        // [B]
+    double* violation;        // [B]
+    double* g;                // [B][n_g] or NULL
+    long n_batch;
+    int horizon, n_s, n_u, n_g;
+};
+struct BestCandidate {
+    long index;
+    int feasible;
+    int pad_;
+    double cost, violation;
+};
+int launch_score(const ScoreArgs& a, cudaStream_t st);
+int launch_argbest(long n, const double* cost, const int32_t* feasible, const double* violation, BestCandidate* out,
+                   cudaStream_t st);
+
 // ---------------------------------------------------------------- setup (factorisation), all float64 on device
 struct SetupDims {
     int n_train, n_pad, dim;

@@ -1,0 +1,407 @@
+"""Sampling SafeMPC: B candidate control sequences rolled out, scored and ranked on the GPU.
+
+The reference solves, at every control step, one nonlinear program with CasADi/IPOPT whose objective and
+constraints are symbolic functions of ONE ellipsoid trajectory (reference safe_exploration/safempc_simple.py:
+163-284 ``init_solver``, :672-742 ``solve``).  On this path the same quantities are evaluated for B candidate
+feed-forward sequences at once (``rollout`` -> ``score_rollouts`` -> ``best_candidate``), which is what
+BASELINE.json's north star asks for ("the sequential CasADi/IPOPT path is replaced on this path by massively
+parallel sampling rollouts").
+
+* ``score_rollouts``    constraint values, feasibility and cost per candidate: generate_safety_constraints
+                        (safempc_simple.py:317-392), _generate_control_constraint (:488-532),
+                        eval_safety_constraints (:911-942), default generate_cost_function (:286-315)
+* ``best_candidate``    arg-best on the device, across ranks if torch.distributed is initialised
+* ``SamplingSafeMPC``   the SimpleSafeMPC surface (constructor arguments, ``get_action``, ``solve``,
+                        ``update_model``, ``get_old_solution``, ``eval_safety_constraints``, n_fail fallback
+                        logic :874-904, solution shifting :1027-1108) over a cross-entropy style sampler.
+
+The decision variables are the reference's: u_0 and the feed-forward controls k_ff (n_safe-1, n_u); the
+feedback gains k_fb are parameters (LQR of the linear prior, get_lqr_feedback :569-597), as in ``solve``.
+"""
+import collections
+import ctypes
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .gp_reachability import rollout
+from .ssm import BatchedGPSSM
+
+__all__ = ["score_rollouts", "best_candidate", "SamplingSafeMPC", "ScoreResult"]
+
+ScoreResult = collections.namedtuple("ScoreResult", ["cost", "feasible", "violation", "g"])
+
+ATTR_NAMES_ENV = ['l_mu', 'l_sigma', 'h_mat_safe', 'h_safe', 'lin_model', 'ctrl_bounds', 'safe_policy',
+                  'h_mat_obs', 'h_obs']                                           # safempc_simple.py:22-23
+DEFAULT_OPT_ENV = {'ctrl_bounds': None, 'safe_policy': None, 'lin_model': None, 'h_mat_obs': None,
+                   'h_obs': None}                                                 # safempc_simple.py:24-25
+
+
+def _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, cost, wx, wu, x_ref,
+                  eps_constraints, eps_noise, c_safety):
+    keep = []
+
+    def hp(x, shape):
+        if x is None:
+            return None
+        arr = _lib.host_f64(x, shape)
+        keep.append(arr)
+        return _lib.dbl_ptr(arr)
+
+    u_min = u_max = None
+    if ctrl_bounds is not None:
+        cb = _lib.host_f64(ctrl_bounds, (n_u, 2))
+        u_min, u_max = hp(cb[:, 0].copy(), (n_u,)), hp(cb[:, 1].copy(), (n_u,))
+    m_obs = 0 if h_mat_obs is None else int(np.shape(h_mat_obs)[0])
+    m_safe = int(np.shape(h_mat_safe)[0])
+    if cost not in ("exploration", "quadratic"):
+        raise ValueError("cost must be 'exploration' or 'quadratic'")
+    prm = _lib.ScoreParams(
+        u_min, u_max, m_obs, hp(h_mat_obs, (m_obs, n_s)) if m_obs else None, hp(h_obs, (m_obs,)) if m_obs else None,
+        m_safe, hp(h_mat_safe, (m_safe, n_s)), hp(h_safe, (m_safe,)), float(c_safety), float(eps_constraints),
+        _lib.COST_EXPLORATION if cost == "exploration" else _lib.COST_QUADRATIC, float(eps_noise),
+        hp(wx, (n_s, n_s)) if cost == "quadratic" else None, hp(wu, (n_u, n_u)) if cost == "quadratic" else None,
+        hp(x_ref, (n_s,)) if (cost == "quadratic" and x_ref is not None) else None)
+    return prm, keep
+
+
+def score_rollouts(res, k_ff, k_fb, h_mat_safe, h_safe, ctrl_bounds=None, h_mat_obs=None, h_obs=None,
+                   cost="exploration", wx=None, wu=None, x_ref=None, eps_constraints=1e-5, eps_noise=0.0,
+                   c_safety=1.0, want_g=False):
+    """Score the candidates of a RolloutResult (device tensors or NumPy arrays; the result has the same kind).
+
+    res        RolloutResult of ``rollout`` for k_ff (B,H,n_u) and k_fb ((H-1),n_u,n_s) or (B,H-1,n_u,n_s)
+    Returns ScoreResult(cost (B,), feasible (B,) int32, violation (B,) = max constraint value, g (B,n_g) | None);
+    a candidate is feasible iff every constraint value is < eps_constraints and its rollout status is 0.
+    Constraint order (safempc_simple.py:317-392): [u_0 - u_max, u_min - u_0], then per step i = 0..H-2 the 2 n_u
+    control distances, then per step i = 0..H-2 the m_obs obstacle distances, then the m_safe terminal distances.
+    """
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    on_device = torch.is_tensor(res.p_all)
+    dev = res.p_all.device if on_device else torch.device("cuda", torch.cuda.current_device())
+
+    def prep(x):
+        if x is None:
+            return None
+        return torch.as_tensor(np.ascontiguousarray(x) if not torch.is_tensor(x) else x, dtype=torch.float64,
+                               device=dev).contiguous()
+
+    p_all, q_all, var_all, kff_d = prep(res.p_all), prep(res.q_all), prep(res.var_all), prep(k_ff)
+    bsz, hor, n_s = (int(v) for v in p_all.shape)
+    n_u = int(kff_d.shape[2])
+    kfb_d = prep(k_fb) if hor > 1 else None
+    per = (hor - 1) * n_u * n_s
+    kfb_stride = 0 if (kfb_d is None or kfb_d.numel() == per) else per
+    status = res.status
+    if status is not None:
+        status = torch.as_tensor(status, device=dev).to(torch.int32).contiguous()
+    if cost == "exploration" and var_all is None:
+        raise ValueError("the exploration cost needs the predictive variances (rollout(..., want_var=True))")
+    prm, keep = _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, cost, wx, wu, x_ref,
+                              eps_constraints, eps_noise, c_safety)
+    n_g = lib.segp_score_num_constraints(hor, n_u, ctypes.byref(prm))
+    cost_d = torch.empty((bsz,), dtype=torch.float64, device=dev)
+    feas_d = torch.empty((bsz,), dtype=torch.int32, device=dev)
+    viol_d = torch.empty((bsz,), dtype=torch.float64, device=dev)
+    g_d = torch.empty((bsz, n_g), dtype=torch.float64, device=dev) if want_g else None
+    _lib.check(lib.segp_score_rollouts(dev.index, bsz, hor, n_s, n_u, _lib.dev_ptr(p_all), _lib.dev_ptr(q_all),
+                                       _lib.dev_ptr(var_all), _lib.dev_ptr(kff_d), _lib.dev_ptr(kfb_d), kfb_stride,
+                                       _lib.dev_ptr(status), ctypes.byref(prm), _lib.dev_ptr(cost_d),
+                                       _lib.dev_ptr(feas_d), _lib.dev_ptr(viol_d), _lib.dev_ptr(g_d),
+                                       _lib.current_stream(dev)))
+    if on_device:
+        return ScoreResult(cost_d, feas_d, viol_d, g_d)
+    return ScoreResult(cost_d.cpu().numpy(), feas_d.cpu().numpy(), viol_d.cpu().numpy(),
+                       None if g_d is None else g_d.cpu().numpy())
+
+
+def best_candidate(score, index_offset=0, group=None):
+    """(index, cost, violation, feasible) of the best candidate: lowest cost among the feasible ones, else the
+    least-violating one (feasible False).  With torch.distributed initialised the result is the best over all
+    ranks (``index_offset`` = first global index of this rank's shard) and every rank returns the same tuple."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = score.cost.device if torch.is_tensor(score.cost) else torch.device("cuda", torch.cuda.current_device())
+    cost_d = torch.as_tensor(score.cost, dtype=torch.float64, device=dev).contiguous()
+    feas_d = torch.as_tensor(score.feasible, device=dev).to(torch.int32).contiguous()
+    viol_d = torch.as_tensor(score.violation, dtype=torch.float64, device=dev).contiguous()
+    idx, c, v, f = ctypes.c_long(-1), ctypes.c_double(np.inf), ctypes.c_double(np.inf), ctypes.c_int(0)
+    _lib.check(lib.segp_argbest(dev.index, int(cost_d.numel()), _lib.dev_ptr(cost_d), _lib.dev_ptr(feas_d),
+                                _lib.dev_ptr(viol_d), ctypes.byref(idx), ctypes.byref(c), ctypes.byref(v),
+                                ctypes.byref(f), _lib.current_stream(dev)))
+    local = (idx.value + index_offset if idx.value >= 0 else -1, c.value, v.value, bool(f.value))
+    return _best_across_ranks(local, group)
+
+
+def _best_across_ranks(local, group=None):
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    devc = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor([float(local[0]), local[1], local[2], float(local[3])], dtype=torch.float64, device=devc)
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    rows = [tuple(float(x) for x in v) for v in allv]
+    rows = [r for r in rows if r[0] >= 0]
+    if not rows:
+        return (-1, np.inf, np.inf, False)
+    # feasible first, then lowest cost (feasible) / lowest violation (infeasible), then lowest index
+    rows.sort(key=lambda r: (-r[3], r[1] if r[3] else r[2], r[0]))
+    r = rows[0]
+    return (int(r[0]), r[1], r[2], bool(r[3]))
+
+
+def _dlqr(a, b, q, r):
+    """Discrete LQR gain, u = -k x (reference utils.dlqr, utils.py:20-35)."""
+    import scipy.linalg as sla
+    x = sla.solve_discrete_are(a, b, q, r)
+    return np.linalg.solve(b.T @ x @ b + r, b.T @ x @ a)
+
+
+class SamplingSafeMPC(object):
+    """SimpleSafeMPC with the IPOPT solve replaced by GPU sampling (safempc_simple.py:28-161 constructor).
+
+    Parameters as the reference: ``n_safe, ssm, opt_env, wx_cost, wu_cost, beta_safety=2.5, rhc=True,
+    safe_policy=None, lin_trafo_gp_input=None, verbosity=0``; ``ssm`` must be a BatchedGPSSM.  Sampler options:
+    ``n_samples`` candidates per iteration, ``n_iter`` refinement iterations (the sampling distribution is refit to
+    the ``n_elite`` best feasible candidates), ``sigma0`` initial standard deviation of the control noise in units
+    of the control range, ``seed``.  ``cost`` is "exploration" (the reference's default cost) or "quadratic".
+    """
+
+    def __init__(self, n_safe, ssm, opt_env, wx_cost, wu_cost, beta_safety=2.5, rhc=True, safe_policy=None,
+                 lin_trafo_gp_input=None, verbosity=0, n_samples=4096, n_iter=2, n_elite=64, sigma0=0.25,
+                 cost="exploration", x_ref=None, seed=0):
+        if not isinstance(ssm, BatchedGPSSM):
+            raise TypeError("SamplingSafeMPC needs a BatchedGPSSM")
+        self.rhc = rhc
+        self.ssm = ssm
+        self.n_safe = int(n_safe)
+        self.n_fail = self.n_safe          # no backup strategy yet (safempc_simple.py:75)
+        self.n_s = ssm.num_states
+        self.n_u = ssm.num_actions
+        self.safe_policy = safe_policy
+        for name in ATTR_NAMES_ENV:        # _set_attributes_from_dict (safempc_simple.py:1003-1016)
+            if name in opt_env:
+                setattr(self, name, opt_env[name])
+            elif name in DEFAULT_OPT_ENV:
+                setattr(self, name, DEFAULT_OPT_ENV[name])
+            else:
+                raise ValueError("Mandatory attribute {} missing in opt_env".format(name))
+        if safe_policy is not None:
+            self.safe_policy = safe_policy
+        self.lin_trafo_gp_input = lin_trafo_gp_input
+        self.m_obs = 0 if self.h_mat_obs is None else np.shape(self.h_mat_obs)[0]
+        if self.h_mat_obs is not None:
+            assert np.shape(self.h_mat_obs)[1] == self.n_s, " Wrong shape of obstacle matrix"
+            assert np.shape(self.h_obs) == (self.m_obs, 1), \
+                " Shapes of obstacle linear inequality matrix/vector must match "
+        self.m_safe, n_s_safe = np.shape(self.h_mat_safe)
+        assert n_s_safe == self.n_s, " Wrong shape of safety matrix"
+        assert np.shape(self.h_safe) == (self.m_safe, 1), \
+            " Shapes of safety linear inequality matrix/vector must match "
+        self.has_ctrl_bounds = self.ctrl_bounds is not None
+        if self.has_ctrl_bounds:
+            assert np.shape(self.ctrl_bounds) == (self.n_u, 2), "control bounds need to be of shape n_u x 2"
+        self.wx_cost = np.asarray(wx_cost, dtype=np.float64)
+        self.wu_cost = np.asarray(wu_cost, dtype=np.float64)
+        self.wx_feedback = self.wx_cost
+        self.wu_feedback = 1 * self.wu_cost
+        self.beta_safety = beta_safety
+        self.verbosity = verbosity
+        self.lin_prior = False
+        self.a = np.eye(self.n_s)
+        self.b = np.zeros((self.n_s, self.n_u))
+        if self.lin_model is not None:
+            self.a, self.b = (np.asarray(m, dtype=np.float64) for m in self.lin_model)
+            self.lin_prior = True
+            if self.safe_policy is None:
+                k = self.get_lqr_feedback().reshape(self.n_u, self.n_s)
+                self.safe_policy = lambda x: np.dot(k, x)
+        if self.safe_policy is None:
+            warnings.warn("No SafePolicy!")
+        self.n_samples, self.n_iter, self.n_elite = int(n_samples), int(n_iter), int(n_elite)
+        self.sigma0 = float(sigma0)
+        self.cost = cost
+        self.x_ref = x_ref
+        self._rng = np.random.default_rng(seed)
+        self.solver_initialized = True     # nothing to build: kept for callers that check it
+        self.k_ff_safe = None              # (n_safe-1, n_u) of the last feasible solution
+        self.k_fb_safe_all = None          # (n_safe-1, n_u*n_s)
+        self.p_safe = None                 # (n_safe, n_s)
+        self.u_apply = None
+
+    # ------------------------------------------------------------------ reference helpers
+    def init_solver(self, cost_func=None, opt_x0=False, init_uncertainty=False):
+        """Nothing to compile on this path (safempc_simple.py:163-284 builds the NLP here)."""
+        if cost_func is not None or opt_x0 or init_uncertainty:
+            raise NotImplementedError("custom cost functions, opt_x0 and init_uncertainty are not on the sampling path")
+        self.solver_initialized = True
+
+    def get_lqr_feedback(self, x_0=None, u_0=None):
+        """safempc_simple.py:569-597: k_fb = -dlqr(a, b, wx_feedback, wu_feedback), as a (1, n_s*n_u) row."""
+        if not self.lin_prior:
+            raise NotImplementedError("Cannot compute feed-back matrices without prior model")
+        return (-_dlqr(self.a, self.b, self.wx_feedback, self.wu_feedback)).reshape((1, self.n_s * self.n_u))
+
+    def eval_prior(self, state, action):
+        """safempc_simple.py:552-566"""
+        return np.dot(state, self.a.T) + np.dot(action, self.b.T)
+
+    def _rollout(self, p_0, k_ff, k_fb):
+        return rollout(self.ssm, p_0, k_ff, k_fb, self.l_mu, self.l_sigma, None, None, self.beta_safety, self.a,
+                       self.b, self.lin_trafo_gp_input)
+
+    def _score(self, res, k_ff, k_fb, want_g=False):
+        return score_rollouts(res, k_ff, k_fb, self.h_mat_safe, self.h_safe, self.ctrl_bounds, self.h_mat_obs,
+                              self.h_obs, cost=self.cost, wx=self.wx_cost, wu=self.wu_cost, x_ref=self.x_ref,
+                              want_g=want_g)
+
+    def get_safety_trajectory_openloop(self, x_0, u_0, k_fb=None, k_ff=None, q_0=None, k_fb_0=None):
+        """safempc_simple.py:599-637 for one control sequence -> (p_all, q_all, var_all)."""
+        if q_0 is not None:
+            raise NotImplementedError("init_uncertainty is not on the sampling path")
+        k_fb = self.k_fb_safe_all if k_fb is None else k_fb
+        k_ff = self.k_ff_safe if k_ff is None else k_ff
+        if k_fb is None or k_ff is None:
+            return None, None, None
+        seq = np.vstack((np.reshape(u_0, (1, self.n_u)), np.reshape(k_ff, (self.n_safe - 1, self.n_u))))
+        res = self._rollout(np.reshape(x_0, (self.n_s,)), seq[None], np.reshape(k_fb, (self.n_safe - 1, self.n_u, self.n_s)))
+        return res.p_all[0], res.q_all[0], res.var_all[0]
+
+    def eval_safety_constraints(self, p_all, q_all, ubg_term=0., lbg_term=-np.inf, ubg_interm=0.,
+                                lbg_interm=-np.inf, terminal_only=False, eps_constraints=1e-5):
+        """safempc_simple.py:911-942 (terminal constraint; like the reference, the "intermediate" values are
+        evaluated on the LAST ellipsoid with the TERMINAL polytope, :101-103, 932)."""
+        from .gp_reachability import lin_ellipsoid_safety_distance
+        q_last = np.reshape(q_all[-1], (self.n_s, self.n_s))
+        g_term = lin_ellipsoid_safety_distance(np.reshape(p_all[-1], (self.n_s, 1)), q_last, self.h_mat_safe,
+                                               self.h_safe)
+        feasible = bool(np.all(lbg_term - eps_constraints < g_term) and np.all(g_term < ubg_term + eps_constraints))
+        if terminal_only or self.h_mat_obs is None:
+            return feasible, g_term
+        g_interm = g_term
+        feasible_interm = bool(np.all(lbg_interm - eps_constraints < g_interm)
+                               and np.all(g_interm < ubg_interm + eps_constraints))
+        return feasible and feasible_interm, np.vstack((g_term, g_interm))
+
+    # ------------------------------------------------------------------ the sampler
+    def _init_controls(self):
+        """Mean of the sampling distribution: the shifted previous solution if there is a fresh one
+        (_get_init_controls, safempc_simple.py:1027-1108), else zeros."""
+        k_fb_lqr = self.get_lqr_feedback()
+        if self.n_fail == 0 and self.k_ff_safe is not None and self.n_safe > 1:
+            k_ff_old = np.vstack((np.reshape(self.u_apply, (1, self.n_u)), self.k_ff_safe))   # (n_safe, n_u)
+            mean = np.vstack((k_ff_old[1:], k_ff_old[-1:]))                                      # shift, repeat last
+            k_fb = np.vstack((self.k_fb_safe_all[1:], self.k_fb_safe_all[-1:])) if self.n_safe > 2 \
+                else np.copy(self.k_fb_safe_all)
+        else:
+            mean = np.zeros((self.n_safe, self.n_u))
+            k_fb = np.tile(k_fb_lqr, (max(self.n_safe - 1, 1), 1))[:self.n_safe - 1]
+        return mean, k_fb
+
+    def solve(self, p_0, u_0=None, k_ff_all_0=None, k_fb_safe=None, sol_verbose=False):
+        """One MPC step (safempc_simple.py:672-742, 742-909): sample, roll out, score, rank, fall back.
+
+        Returns ``(x_0, u_apply, success)`` or, with sol_verbose, ``(x_0, u_apply, feasible, success,
+        k_fb_safe, k_ff_all, p_safe, q_safe)`` like the reference (without the CasADi solution object).
+        """
+        p_0 = np.reshape(np.asarray(p_0, dtype=np.float64), (self.n_s,))
+        mean, k_fb_init = self._init_controls()
+        if u_0 is not None:
+            mean[0] = np.reshape(u_0, (self.n_u,))
+        if k_ff_all_0 is not None and self.n_safe > 1:
+            mean[1:] = np.reshape(k_ff_all_0, (self.n_safe - 1, self.n_u))
+        k_fb = k_fb_init if k_fb_safe is None else np.reshape(k_fb_safe, (self.n_safe - 1, self.n_u * self.n_s))
+        k_fb3 = np.reshape(k_fb, (self.n_safe - 1, self.n_u, self.n_s))
+        if self.has_ctrl_bounds:
+            lo, hi = self.ctrl_bounds[:, 0], self.ctrl_bounds[:, 1]
+        else:
+            lo, hi = -np.ones(self.n_u), np.ones(self.n_u)
+        std = np.tile(self.sigma0 * (hi - lo), (self.n_safe, 1))
+        best = None
+        for _ in range(max(self.n_iter, 1)):
+            cand = mean[None] + std[None] * self._rng.standard_normal((self.n_samples, self.n_safe, self.n_u))
+            cand[0] = mean                                      # the current mean is always a candidate
+            # u_0 is applied at a point (no feedback term), so clipping it to the bounds loses nothing; the later
+            # feed-forward terms need head-room for the feedback part and are left to the constraint check
+            cand[:, 0] = np.clip(cand[:, 0], lo, hi)
+            res = self._rollout(p_0, cand, k_fb3)
+            sc = self._score(res, cand, k_fb3)
+            idx, cost, viol, feas = best_candidate(sc)
+            if idx >= 0 and (best is None or (feas, -cost if feas else -viol) > (best[3], -best[1] if best[3] else -best[2])):
+                best = (cand[idx].copy(), cost, viol, feas, res.p_all[idx].copy(), res.q_all[idx].copy())
+            order = np.lexsort((np.where(sc.feasible > 0, sc.cost, sc.violation), -sc.feasible))
+            elite = cand[order[:min(self.n_elite, self.n_samples)]]
+            mean = elite.mean(axis=0)
+            std = np.maximum(elite.std(axis=0), 1e-3 * (hi - lo))
+        feasible = bool(best is not None and best[3])
+        success = True
+        k_ff_all = p_safe = q_safe = k_fb_out = None
+        if feasible:
+            seq, _, _, _, p_safe, q_safe = best
+            u_apply = seq[0].copy()
+            k_ff_all = seq[1:].copy()
+            k_fb_out = np.copy(k_fb)
+            self.n_fail = 0
+            if self.rhc:
+                self.k_ff_safe = k_ff_all
+                self.p_safe = p_safe
+                self.k_fb_safe_all = k_fb_out
+                self.u_apply = u_apply
+        else:
+            self.n_fail += 1
+            if self.n_fail >= self.n_safe:
+                # too many infeasible steps: safe controller (safempc_simple.py:887-893)
+                u_apply = np.reshape(self.safe_policy(p_0), (self.n_u,))
+                k_ff_all = u_apply
+            else:
+                u_apply = np.reshape(self.get_old_solution(p_0), (self.n_u,))
+                k_ff_all = u_apply
+        if sol_verbose:
+            return p_0[:, None], u_apply, feasible, success, k_fb_out, k_ff_all, p_safe, q_safe
+        return p_0[:, None], u_apply, success
+
+    def get_action(self, x0_mu, lqr_only=False, sol_verbose=False):
+        """safempc_simple.py:639-670"""
+        if lqr_only:
+            return self.safe_policy(x0_mu), False
+        x0 = np.asarray(x0_mu, dtype=np.float64).reshape(self.n_s)
+        if sol_verbose:
+            _, u_apply, feasible, success, k_fb_apply, k_ff_all, p_all, q_all = self.solve(x0, sol_verbose=True)
+            return u_apply.reshape(self.n_u, ), feasible, success, k_fb_apply, k_ff_all, p_all, q_all
+        _, u_apply, success = self.solve(x0)
+        return u_apply.reshape(self.n_u, ), success
+
+    def get_old_solution(self, x, k=None, get_ctrl_traj=False):
+        """Shift the last feasible solution (safempc_simple.py:944-1001): u = k_ff[k-1] + K_fb[k-1] (x - p[k-1])."""
+        if self.n_fail > self.n_safe or self.k_ff_safe is None:
+            warnings.warn("There are no previous solution to be applied. Returning None")
+            return None
+        k = self.n_fail if k is None else k
+        if k < 1:
+            warnings.warn("Have to shift at least one timestep back")
+            return None
+        k_fb_old = np.reshape(self.k_fb_safe_all[k - 1], (self.n_u, self.n_s))
+        k_ff = self.k_ff_safe[k - 1]
+        p_safe = self.p_safe[k - 1]
+        u_apply = k_ff + k_fb_old @ (np.reshape(x, (self.n_s,)) - p_safe)       # utils.feedback_ctrl
+        if get_ctrl_traj:
+            if k < self.n_safe:
+                return (u_apply, self.k_fb_safe_all[k:], np.vstack((u_apply, self.k_ff_safe[k + 1:])), self.p_safe[k:])
+            return u_apply, None, u_apply, None
+        return u_apply
+
+    def update_model(self, x, y, opt_hyp=False, replace_old=True, reinitialize_solver=True):
+        """safempc_simple.py:1111-1140: the GP learns the residual to the linear prior."""
+        x = np.asarray(x, dtype=np.float64)
+        n_train = x.shape[0]
+        x_s = x[:, :self.n_s].reshape((n_train, self.n_s))
+        x_u = x[:, self.n_s:].reshape((n_train, self.n_u))
+        y_prior = self.eval_prior(x_s, x_u)
+        x_trafo = x_s if self.lin_trafo_gp_input is None else x_s @ np.asarray(self.lin_trafo_gp_input).T
+        self.ssm.update_model(np.hstack((x_trafo, x_u)), np.asarray(y, dtype=np.float64) - y_prior, opt_hyp,
+                              replace_old)

@@ -65,3 +65,34 @@ def test_broadcast_and_argmin_world_size_2(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert open(os.path.join(str(tmp_path), "ok%d" % r)).read() == "1"
+
+
+def _best_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from safe_exploration_b200.safempc_sampling import _best_across_ranks
+    # rank 0: infeasible but tiny violation; rank 1: feasible with a larger cost -> feasible wins
+    local = (3, -1.0, 0.2, False) if rank == 0 else (8192 + 5, 7.0, -0.1, True)
+    res1 = _best_across_ranks(local)
+    # both feasible: lowest cost wins; equal cost: lowest index
+    res2 = _best_across_ranks((10 + rank, 2.0, -0.5, True))
+    # nobody has a candidate
+    res3 = _best_across_ranks((-1, float("inf"), float("inf"), False))
+    with open(os.path.join(out_dir, "best_%d.txt" % rank), "w") as f:
+        f.write(repr((res1, res2, res3)))
+    dist.destroy_process_group()
+
+
+def test_best_candidate_across_ranks_world_size_2(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29600 + os.getpid() % 200
+    mp.spawn(_best_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    outs = [eval(open(os.path.join(str(tmp_path), "best_%d.txt" % r)).read(), {"inf": float("inf")}) for r in range(2)]
+    assert outs[0] == outs[1]
+    res1, res2, res3 = outs[0]
+    assert res1 == (8197, 7.0, -0.1, True)
+    assert res2 == (10, 2.0, -0.5, True)
+    assert res3[0] == -1 and res3[3] is False

@@ -1,0 +1,168 @@
+"""GPU tests of the scoring kernels and the sampling SafeMPC driver, through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def se():
+    import safe_exploration_b200 as pkg
+    pkg._lib.load()
+    return pkg
+
+
+def _model_and_rollout(se, name="C2", n_train=300, horizon=6, batch=257):
+    from safe_exploration_b200 import workloads
+    w = workloads.make(name, batch=batch, n_train=n_train, horizon=horizon)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    res = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    return w, gp, res
+
+
+@pytest.mark.parametrize("name,per_candidate_gain", [("C2", False), ("C3", True)])
+def test_score_matches_oracle(se, name, per_candidate_gain):
+    from oracle import score_oracle
+    w, gp, res = _model_and_rollout(se, name)
+    rng = np.random.default_rng(4)
+    k_fb = w.k_fb
+    if per_candidate_gain:
+        k_fb = w.k_fb[None] + 0.01 * rng.standard_normal((w.k_ff.shape[0],) + w.k_fb.shape)
+        res = se.rollout(gp, w.p0, w.k_ff, k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    h_obs = rng.standard_normal((3, w.n_s))
+    # thresholds from the data (constraint values with all bounds at zero), so that each family of constraints
+    # rejects a share of the candidates and the batch mixes feasible and infeasible ones
+    zero_cb = np.zeros((w.n_u, 2))
+    _, _, _, g0 = score_oracle.score_batch(res.p_all, res.q_all, res.var_all, w.k_ff, k_fb, zero_cb, h_obs,
+                                           np.zeros((3, 1)), w.h_mat, np.zeros((2 * w.n_s, 1)))
+    n_c = 2 * w.n_u * w.k_ff.shape[1]
+    n_o = 3 * (w.k_ff.shape[1] - 1)
+    u_abs = float(np.quantile(g0[:, :n_c].max(axis=1), 0.8))
+    cb = np.stack((-u_abs * np.ones(w.n_u), u_abs * np.ones(w.n_u)), axis=1)
+    h_obs_v = float(np.quantile(g0[:, n_c:n_c + n_o].max(axis=1), 0.8)) * np.ones((3, 1))
+    h_safe_v = float(np.quantile(g0[:, n_c + n_o:].max(axis=1), 0.8)) * np.ones((2 * w.n_s, 1))
+    for cost, kw in (("exploration", {}), ("quadratic", {"wx": np.diag(np.arange(1, w.n_s + 1.0)),
+                                                         "wu": 0.5 * np.eye(w.n_u), "x_ref": 0.1 * np.ones(w.n_s)})):
+        sc = se.score_rollouts(res, w.k_ff, k_fb, w.h_mat, h_safe_v, cb, h_obs, h_obs_v, cost=cost, want_g=True, **kw)
+        c_o, f_o, v_o, g_o = score_oracle.score_batch(res.p_all, res.q_all, res.var_all, w.k_ff, k_fb, cb, h_obs,
+                                                      h_obs_v, w.h_mat, h_safe_v, cost=cost, **kw)
+        assert sc.g.shape == g_o.shape
+        assert np.allclose(sc.g, g_o, rtol=1e-12, atol=1e-13)
+        assert np.allclose(sc.cost, c_o, rtol=1e-12, atol=1e-13)
+        assert np.allclose(sc.violation, v_o, rtol=1e-12, atol=1e-13)
+        assert np.array_equal(sc.feasible.astype(bool), f_o)
+        assert 0 < f_o.sum() < f_o.size, "test case should mix feasible and infeasible candidates"
+        idx, c, v, f = se.best_candidate(sc)
+        want = int(np.flatnonzero(f_o)[np.argmin(c_o[f_o])])
+        assert f and idx == want and np.isclose(c, c_o[want]) and np.isclose(v, v_o[want])
+    # without control bounds / obstacles only the terminal rows remain
+    sc = se.score_rollouts(res, w.k_ff, k_fb, w.h_mat, h_safe_v, want_g=True)
+    assert sc.g.shape[1] == 2 * w.n_s
+    gp.close()
+
+
+def test_best_candidate_without_feasible_and_with_bad_status(se):
+    w, gp, res = _model_and_rollout(se, batch=64)
+    tight = 1e-4 * np.ones((2 * w.n_s, 1))          # nobody fits
+    sc = se.score_rollouts(res, w.k_ff, w.k_fb, w.h_mat, tight)
+    assert sc.feasible.sum() == 0
+    idx, c, v, f = se.best_candidate(sc)
+    assert not f and idx == int(np.argmin(sc.violation)) and np.isclose(v, sc.violation.min())
+    # a candidate whose rollout reported a failure is never feasible, however good its numbers look
+    loose = 10.0 * np.ones((2 * w.n_s, 1))
+    status = res.status.copy()
+    sc0 = se.score_rollouts(res, w.k_ff, w.k_fb, w.h_mat, loose)
+    best0 = se.best_candidate(sc0)[0]
+    status[best0] = 1
+    sc1 = se.score_rollouts(res._replace(status=status), w.k_ff, w.k_fb, w.h_mat, loose)
+    assert sc0.feasible.all() and sc1.feasible[best0] == 0 and sc1.feasible.sum() == 63
+    assert se.best_candidate(sc1)[0] != best0
+    gp.close()
+
+
+def test_score_device_tensors_match_host_arrays(se):
+    import torch
+    w, gp, res = _model_and_rollout(se, batch=100)
+    dev = gp.device
+    kff_d = torch.as_tensor(w.k_ff, device=dev)
+    res_d = se.rollout(gp, torch.as_tensor(w.p0, device=dev), kff_d, torch.as_tensor(w.k_fb, device=dev), w.l_mu,
+                       w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    safe_v = 0.3 * np.ones((2 * w.n_s, 1))
+    sc_d = se.score_rollouts(res_d, kff_d, torch.as_tensor(w.k_fb, device=dev), w.h_mat, safe_v)
+    sc_h = se.score_rollouts(res, w.k_ff, w.k_fb, w.h_mat, safe_v)
+    assert torch.is_tensor(sc_d.cost) and sc_d.cost.is_cuda
+    assert np.array_equal(sc_d.cost.cpu().numpy(), sc_h.cost)
+    assert np.array_equal(sc_d.feasible.cpu().numpy(), sc_h.feasible)
+    assert se.best_candidate(sc_d) == se.best_candidate(sc_h)
+    gp.close()
+
+
+def _pendulum_mpc(se, n_safe=4, h_safe_bound=0.5, **kw):
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C2", batch=8, n_train=200, horizon=n_safe)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    opt_env = {"l_mu": w.l_mu, "l_sigma": w.l_sigma, "h_mat_safe": w.h_mat,
+               "h_safe": h_safe_bound * np.ones((2 * w.n_s, 1)), "lin_model": (w.a, w.b),
+               "ctrl_bounds": np.array([[-1.0, 1.0]])}
+    mpc = se.SamplingSafeMPC(n_safe, gp, opt_env, np.eye(w.n_s), np.eye(w.n_u), beta_safety=2.0, n_samples=512,
+                             n_iter=2, n_elite=32, seed=1, **kw)
+    return w, gp, mpc
+
+
+def test_sampling_mpc_returns_a_feasible_action_and_its_certificate(se):
+    from oracle import reach_oracle, score_oracle
+    from oracle.gp_oracle import GPOracle
+    w, gp, mpc = _pendulum_mpc(se)
+    x0 = np.array([0.02, -0.03])
+    u, feasible, success, k_fb, k_ff_all, p_safe, q_safe = mpc.get_action(x0, sol_verbose=True)
+    assert feasible and success and u.shape == (w.n_u,) and -1.0 <= u[0] <= 1.0
+    assert k_ff_all.shape == (3, w.n_u) and p_safe.shape == (4, w.n_s) and q_safe.shape == (4, w.n_s, w.n_s)
+    assert mpc.n_fail == 0
+    # certificate: the returned plan, re-evaluated by the CPU oracle, satisfies every constraint
+    ora = GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
+                   [h["variance"] for h in w.hyp], gp.total_noise())
+    seq = np.vstack((u[None], k_ff_all))
+    p_o, q_o, v_o = reach_oracle.multistep_batch(x0, ora, k_fb.reshape(3, w.n_u, w.n_s), seq[None], w.l_mu, w.l_sigma,
+                                                 None, 2.0, w.a, w.b)
+    assert np.allclose(p_o[0], p_safe, rtol=1e-6, atol=1e-9) and np.allclose(q_o[0], q_safe, rtol=1e-6, atol=1e-9)
+    g = score_oracle.constraints_one(p_o[0], q_o[0], seq, k_fb.reshape(3, w.n_u, w.n_s), mpc.ctrl_bounds, None, None,
+                                     mpc.h_mat_safe, mpc.h_safe)
+    assert np.all(g < 1e-5)
+    feas2, g_term = mpc.eval_safety_constraints(p_safe, q_safe)
+    assert feas2 and g_term.shape == (2 * w.n_s, 1)
+    # receding horizon: the next call starts from the shifted plan and stays feasible
+    u2, success2 = mpc.get_action(p_safe[0])
+    assert success2 and mpc.n_fail == 0 and u2.shape == (w.n_u,)
+    # lqr_only short-cut of the reference
+    u_lqr, fail = mpc.get_action(x0, lqr_only=True)
+    assert np.allclose(u_lqr, mpc.get_lqr_feedback().reshape(w.n_u, w.n_s) @ x0) and fail is False
+    gp.close()
+
+
+def test_sampling_mpc_falls_back_like_the_reference(se):
+    """Infeasible problem: first the shifted old solution (n_fail < n_safe), then the safe policy."""
+    w, gp, mpc = _pendulum_mpc(se)
+    x0 = np.array([0.02, -0.03])
+    u, feasible, *_ = mpc.get_action(x0, sol_verbose=True)
+    assert feasible
+    old = (mpc.k_ff_safe.copy(), mpc.k_fb_safe_all.copy(), mpc.p_safe.copy())
+    mpc.h_safe = 1e-6 * np.ones_like(mpc.h_safe)        # now nothing is feasible
+    x1 = old[2][0] + 1e-3
+    u1, feasible1, *_ = mpc.get_action(x1, sol_verbose=True)
+    assert not feasible1 and mpc.n_fail == 1
+    want = old[0][0] + old[1][0].reshape(w.n_u, w.n_s) @ (x1 - old[2][0])      # feedback_ctrl on the old plan
+    assert np.allclose(u1, want)
+    for _ in range(3):
+        u_k, feasible_k, *_ = mpc.get_action(x1, sol_verbose=True)
+    assert mpc.n_fail == 4 and np.allclose(u_k, mpc.safe_policy(x1))
+    gp.close()
+
+
+def test_sampling_mpc_update_model_subtracts_the_prior(se):
+    w, gp, mpc = _pendulum_mpc(se)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-0.5, 0.5, size=(50, w.n_s + w.n_u))
+    y = x[:, :w.n_s] @ w.a.T + x[:, w.n_s:] @ w.b.T + 0.01
+    mpc.update_model(x, y, replace_old=True)
+    assert gp.x_train.shape == (50, w.n_s + w.n_u) and np.allclose(gp.y_train, 0.01)
+    gp.close()

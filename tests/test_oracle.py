@@ -192,3 +192,49 @@ def test_oracle_equals_reference_functions_live():
         _, _, pa_r, qa_r = reach.multistep_reachability(p, gp, kfb, kff, l_mu, l_sig, None, 2.0, 0, a, b, None)
         pb, qb, _ = reach_oracle.multistep_batch(p, gp, kfb, kff[None], l_mu, l_sig, None, 2.0, a, b)
         assert np.allclose(pb[0], np.real(pa_r), rtol=1e-9) and np.allclose(qb[0], np.real(qa_r), rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------- scoring oracle (SafeMPC assembly)
+def _random_candidates(rng, bsz, hor, n_s, n_u):
+    p_all = 0.3 * rng.standard_normal((bsz, hor, n_s))
+    m = 0.2 * rng.standard_normal((bsz, hor, n_s, n_s))
+    q_all = m @ np.swapaxes(m, -1, -2) + 1e-3 * np.eye(n_s)
+    var_all = rng.uniform(1e-4, 1e-2, size=(bsz, hor, n_s))
+    k_ff = 0.5 * rng.standard_normal((bsz, hor, n_u))
+    k_fb = rng.standard_normal((hor - 1, n_u, n_s))
+    return p_all, q_all, var_all, k_ff, k_fb
+
+
+def test_score_oracle_known_answer_and_reference_distance():
+    """Hand-computable case + the assembly evaluated with the reference's own lin_ellipsoid_safety_distance."""
+    from oracle import ref_loader, score_oracle
+    # one candidate, H=2, n_s=2, n_u=1: Q = diag(0.04, 0.09), K = [1, 0] -> sqrt(K Q K^T) = 0.2
+    p_all = np.array([[0.1, -0.2], [0.3, 0.4]])
+    q_all = np.array([np.diag([0.04, 0.09]), np.diag([0.01, 0.16])])
+    k_ff = np.array([[0.5], [-0.25]])
+    k_fb = np.array([[[1.0, 0.0]]])
+    cb = np.array([[-1.0, 1.0]])
+    h_mat = np.vstack((np.eye(2), -np.eye(2)))
+    h_vec = np.ones((4, 1))
+    g = score_oracle.constraints_one(p_all, q_all, k_ff, k_fb, cb, h_mat, h_vec, h_mat, h_vec)
+    want = np.array([0.5 - 1.0, -1.0 - 0.5,                      # u_0 bounds
+                     -0.25 + 0.2 - 1.0, 0.25 + 0.2 - 1.0,        # step-1 control through the ellipsoid
+                     0.1 + 0.2 - 1, -0.2 + 0.3 - 1, -0.1 + 0.2 - 1, 0.2 + 0.3 - 1,     # obstacle polytope, ellipsoid 0
+                     0.3 + 0.1 - 1, 0.4 + 0.4 - 1, -0.3 + 0.1 - 1, -0.4 + 0.4 - 1])    # terminal polytope, ellipsoid 1
+    assert np.allclose(g, want, rtol=0, atol=1e-15)
+    assert np.isclose(score_oracle.exploration_cost_one(np.array([[0.04, 0.05], [0.16, 0.09]])), -(0.3 + 0.5))
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    gp_reach, _, _ = ref_loader.load()
+    rng = np.random.default_rng(3)
+    p, q, v, kff, kfb = _random_candidates(rng, 5, 4, 3, 2)
+    cb = np.array([[-1.0, 1.0], [-0.5, 0.7]])
+    h_obs = rng.standard_normal((5, 3))
+    c_own, f_own, v_own, g_own = score_oracle.score_batch(p, q, v, kff, kfb, cb, h_obs, np.ones((5, 1)), h_obs[:2],
+                                                          np.ones((2, 1)))
+    c_ref, f_ref, v_ref, g_ref = score_oracle.score_batch(p, q, v, kff, kfb, cb, h_obs, np.ones((5, 1)), h_obs[:2],
+                                                          np.ones((2, 1)),
+                                                          dist_fn=gp_reach.lin_ellipsoid_safety_distance)
+    assert g_own.shape == (5, 2 * 2 * 4 + 3 * 5 + 2)
+    assert np.allclose(g_own, np.real(g_ref), rtol=1e-14, atol=1e-15)
+    assert np.array_equal(f_own, f_ref)
