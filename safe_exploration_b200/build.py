@@ -42,7 +42,8 @@ def _stale(target, deps):
 
 
 def _compile_one(nvcc, src, obj, log):
-    cmd = [nvcc] + ARCH_FLAGS + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
+    extra = os.environ.get("SEGP_EXTRA_NVCC_FLAGS", "").split()   # tuning experiments only (e.g. -DSEGP_KS_UNROLL=16)
+    cmd = [nvcc] + ARCH_FLAGS + NVCC_FLAGS + extra + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -133,6 +133,91 @@ int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int 
 // One block = one 96-trajectory panel (thread = trajectory = one row of the B tile images), blockIdx.y = output
 // dimension, blockIdx.z = split of the training points.  Same arithmetic as kstar_mean_jac (predict.cu); the kernel
 // value leaves as I8_S digit bytes instead of one double.
+// exp(x) for x <= 0 without branches: x = (64 m + j) ln2/64 + r, |r| <= ln2/128, exp(x) = 2^m 2^(j/64) e^r with a
+// 64-entry table in shared memory and a degree-5 polynomial (remainder 3.5e-17 relative).  ~1.5 ulp; 10 FP64
+// instructions instead of ~17 plus a slow-path branch for the library exp, and it schedules across unrolled points.
+__device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict__ s_tab) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double t = fma(x, 92.33248261689366, MAGIC);
+    const int n = __double2loint(t);
+    const double nd = t - MAGIC;
+    double r = fma(nd, -0.01083042469326756, x);    // ln2/64, high part (32 significant bits: nd * hi is exact)
+    r = fma(nd, -2.9815858269852933e-12, r);        // low part
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = s_tab[n & 63] * p;
+    const double scaled = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+    return x < -700.0 ? 0.0 : scaled;
+}
+
+// 128 staged training points against one trajectory: kernel values -> digit bytes, mean / Jacobian sums.
+template <int DM, int KERN, int UNR>
+__device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, const double* __restrict__ s_beta,
+                                              const double* __restrict__ s_tab,
+                                              const double (&zs)[DM], int dim, double var, int row0, int n_train,
+                                              bool active, int8_t* __restrict__ kb_base, int rowp, long plane_stride,
+                                              double& mu, double (&jac)[DM]) {
+    const double sqrt5 = 2.23606797749978969641;
+    // UNR independent points per iteration (8 or 16): ILP against code size / registers
+    static_assert(UNR == 8 || UNR == 16, "unroll");
+#pragma unroll 1
+    for (int r = 0; r < TILE; r += UNR) {
+        uint32_t pk[I8_S][UNR / 4];
+#pragma unroll
+        for (int s = 0; s < I8_S; ++s)
+#pragma unroll
+            for (int q4 = 0; q4 < UNR / 4; ++q4) pk[s][q4] = 0u;
+#pragma unroll
+        for (int qd = 0; qd < UNR; ++qd) {
+            const double* xr = s_x + (r + qd) * dim;
+            double diff[DM];
+            double r2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < DM; ++j) {
+                diff[j] = 0.0;
+                if (j < dim) {
+                    diff[j] = zs[j] - xr[j];
+                    r2 = fma(diff[j], diff[j], r2);
+                }
+            }
+            double unit, g;   // k / var  and  (dk/dr2-type factor) / var
+            if (KERN == SEGP_KERN_RBF) {
+                unit = exp_neg_tab(-0.5 * r2, s_tab);
+                g = unit;
+            } else {
+                const double rr = sqrt(r2);
+                const double e = exp_neg_tab(-sqrt5 * rr, s_tab);
+                unit = (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * e;
+                g = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
+            }
+            if (row0 + r + qd >= n_train || !active) unit = 0.0;   // padded rows / columns: zero digits
+            const double bt = s_beta[r + qd] * var;
+            mu = fma(bt, unit, mu);
+            const double w = bt * g;
+#pragma unroll
+            for (int j = 0; j < DM; ++j)
+                if (j < dim) jac[j] = fma(w, diff[j], jac[j]);
+            int dg[I8_S];
+            split_digits_unit(unit, dg);
+#pragma unroll
+            for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
+        }
+        const int kglob = row0 + r;
+        int8_t* dst = kb_base + (long)(kglob >> 6) * (I8_S * I8_B_TILE) + sw64_offset(rowp, kglob & 63);
+#pragma unroll
+        for (int s = 0; s < I8_S; ++s) {
+            if (UNR == 16)
+                *reinterpret_cast<uint4*>(dst + (long)s * plane_stride) =
+                    make_uint4(pk[s][0], pk[s][1], pk[s][UNR / 4 - 2], pk[s][UNR / 4 - 1]);
+            else
+                *reinterpret_cast<uint2*>(dst + (long)s * plane_stride) = make_uint2(pk[s][0], pk[s][1]);
+        }
+    }
+}
+
 template <int D_T>
 __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
     const KstarArgs& a = aa.k;
@@ -146,7 +231,9 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
 
     __shared__ double s_x[TILE * DM];
     __shared__ double s_beta[TILE];
-
+    __shared__ double s_tab[64];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));   // visible after the first
+                                                                                           // __syncthreads below
     double zs[DM];
 #pragma unroll
     for (int j = 0; j < DM; ++j) zs[j] = 0.0;
@@ -190,8 +277,12 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
     const int nkb = a.n_pad / I8_KB;
     const int row_begin = split * a.groups_per_split * 4;
     const int row_end = min(row_begin + a.groups_per_split * 4, a.n_pad);
-    const double sqrt5 = 2.23606797749978969641;
     int8_t* panel_base = aa.ki8 + (((long)d * aa.npanel_cap + blockIdx.x) * nkb) * (long)(I8_S * I8_B_TILE);
+
+    // destination of this trajectory's bytes inside a k-block image
+    const int rowp = aa.split_halves ? trow % (I8_N / 2) : trow;
+    const long half_off = aa.split_halves ? (long)(trow / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) : 0;
+    const long plane_stride = aa.split_halves ? I8_B_TILE / 2 : I8_B_TILE;
 
     for (int row0 = row_begin; row0 < row_end; row0 += TILE) {
         __syncthreads();
@@ -199,59 +290,16 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
         for (int idx = threadIdx.x; idx < TILE * dim; idx += I8_N) s_x[idx] = src[idx];
         for (int idx = threadIdx.x; idx < TILE; idx += I8_N) s_beta[idx] = a.beta[(long)d * a.n_pad + row0 + idx];
         __syncthreads();
-#pragma unroll 1
-        for (int r = 0; r < TILE; r += 16) {
-            uint32_t pk[I8_S][4];
-#pragma unroll
-            for (int s = 0; s < I8_S; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
-#pragma unroll
-            for (int qd = 0; qd < 16; ++qd) {
-                const double* xr = s_x + (r + qd) * dim;
-                double diff[DM];
-                double r2 = 0.0;
-#pragma unroll
-                for (int j = 0; j < DM; ++j) {
-                    diff[j] = 0.0;
-                    if (j < dim) {
-                        diff[j] = zs[j] - xr[j];
-                        r2 = fma(diff[j], diff[j], r2);
-                    }
-                }
-                double unit, g;   // k / var  and  (dk/dr2-type factor) / var
-                if (kern == SEGP_KERN_RBF) {
-                    unit = exp(-0.5 * r2);
-                    g = unit;
-                } else {
-                    const double rr = sqrt(r2);
-                    const double e = exp(-sqrt5 * rr);
-                    unit = (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * e;
-                    g = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
-                }
-                if (row0 + r + qd >= a.n_train || !active) unit = 0.0;   // padded rows / columns: zero digits
-                const double bt = s_beta[r + qd] * var;
-                mu = fma(bt, unit, mu);
-                const double w = bt * g;
-#pragma unroll
-                for (int j = 0; j < DM; ++j)
-                    if (j < dim) jac[j] = fma(w, diff[j], jac[j]);
-                int dg[I8_S];
-                split_digits_unit(unit, dg);
-#pragma unroll
-                for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
-            }
-            const int kglob = row0 + r;
-            int8_t* tile0 = panel_base + (long)(kglob >> 6) * (I8_S * I8_B_TILE);
-            long plane_stride = I8_B_TILE;
-            if (aa.split_halves) {   // [half][plane][48 x 64]: 48 rows keep the 8-row swizzle period intact
-                tile0 += (long)(trow / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) + sw64_offset(trow % (I8_N / 2), kglob & 63);
-                plane_stride = I8_B_TILE / 2;
-            } else {
-                tile0 += sw64_offset(trow, kglob & 63);
-            }
-#pragma unroll
-            for (int s = 0; s < I8_S; ++s)
-                *reinterpret_cast<uint4*>(tile0 + (long)s * plane_stride) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
-        }
+        int8_t* kb_base = panel_base + half_off;
+        // One loop body per kernel type: with both types inlined the 16-point body was 52 KB of SASS and stalled on
+        // instruction fetch (ncu: no_instruction 1.1 per issue).  16 independent points per iteration are needed
+        // to cover the FP64 latency (a 4-point body ran 40 % slower).
+        if (kern == SEGP_KERN_RBF)
+            kstar_i8_rows<DM, SEGP_KERN_RBF, 16>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active, kb_base,
+                                                 rowp, plane_stride, mu, jac);
+        else
+            kstar_i8_rows<DM, SEGP_KERN_MAT52, 8>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active, kb_base,
+                                                  rowp, plane_stride, mu, jac);
     }
     if (active) {
         const int n_s = gridDim.y;
