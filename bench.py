@@ -233,6 +233,8 @@ def run_product(args, rank, world, local_rank):
         time.sleep(0.3)
     if os.environ.get("SEGP_I8_ABLATE"):
         gp.set_option("i8_ablate", int(os.environ["SEGP_I8_ABLATE"]))   # profiling experiments only
+    if os.environ.get("SEGP_I8_PROF"):
+        gp.set_option("i8_prof", 1)
     launches0 = gp.get_option("launches")
     gp.set_option("time_tri", 1)
     ev0 = torch.cuda.Event(enable_timing=True)
@@ -278,6 +280,17 @@ def run_product(args, rank, world, local_rank):
         sampler.stop()
     same = bool(np.array_equal(res_h.q_all, res.q_all.cpu().numpy()))
 
+    if os.environ.get("SEGP_I8_PROF") and rank == 0:
+        from safe_exploration_b200.ssm import _tensor_from_ptr
+        torch.cuda.synchronize(dev)
+        view = _tensor_from_ptr(torch, gp.get_option("i8_prof_ptr"), 128 * 8 * 8, gp.device)
+        prof = view.cpu().numpy().view(np.int64).reshape(128, 8)
+        prof = prof[prof[:, 4] > 0]
+        sys.stderr.write("i8_prof (last launch; MMA thread of each cluster): clusters %d\n" % len(prof))
+        for name, col in (("total", 0), ("wait_full", 1), ("wait_peer", 2), ("wait_tmem_empty", 3), ("tiles", 4),
+                          ("stages", 5)):
+            c = prof[:, col]
+            sys.stderr.write("  %-16s min %10d  median %10d  max %10d\n" % (name, c.min(), np.median(c), c.max()))
     if rank != 0:
         return
     peaks = _peaks()
@@ -290,7 +303,7 @@ def run_product(args, rank, world, local_rank):
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     share = (tri_ns * 1e-6) / ms if ms > 0 else None
     mode = gp.get_option("tri_mode_effective")
-    if mode in (1, 2):
+    if mode in (1, 2, 3):
         # tri_i8: 15 int8 digit-plane products per algorithmic multiply-add, exact int32 accumulation in TMEM.
         # `achieved` is ALGORITHMIC flop/s (n_s N^2 B per launch); `peak` is the measured bf16 figure of
         # MEASURED_PEAKS.json, so `frac` is the algorithmic fraction of the bf16 tensor peak: error-free splitting
@@ -301,15 +314,15 @@ def run_product(args, rank, world, local_rank):
         n_pad = gp.get_option("n_train_padded")
         nblk = n_pad // 128
         panels = -(-cols // 96)
-        if mode == 2:   # block-row pairs: the upper row of a pair also runs over the lower row's diagonal block
+        if mode >= 2:   # block-row pairs: the upper row of a pair also runs over the lower row's diagonal block
             kblocks = sum(2 * (min(2 * bp + 1, nblk - 1) + 1) for bp in range((nblk + 1) // 2))
         else:
             kblocks = nblk * (nblk + 1) // 2
         executed = 2.0 * 15 * w.n_s * (128 * 128 * kblocks) * panels * 96
         i8_96, i8_256 = _i8_peak(gp, local_rank, 96), _i8_peak(gp, local_rank, 256)
         pipe_tops = executed / tri_avg_s / 1e12 if tri_avg_s > 0 else None
-        roofline = {"bound": "tensor", "kernel": "tri_i8x2_kernel" if mode == 2 else "tri_i8_kernel",
-                    "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, " + ("cta_group::2 M=256" if mode == 2 else "M=128")
+        roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 2: "tri_i8x2_kernel", 3: "tri_i8x2p_kernel"}[mode],
+                    "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, " + ("cta_group::2 M=256" if mode >= 2 else "M=128")
                             + " N=96 K=32, int32 accumulators in TMEM); "
                             "float64-grade result from 5 x 5 balanced base-254 digit planes, 15 products",
                     "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
@@ -336,7 +349,8 @@ def run_product(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "tri_mode": {0: "fp64 DMMA", 1: "int8 digit planes on tcgen05 (single CTA), float64 recombination",
-                         2: "int8 digit planes on tcgen05 (CTA pairs), float64 recombination"}[mode],
+                         2: "int8 digit planes on tcgen05 (CTA pairs), float64 recombination",
+                         3: "int8 digit planes on tcgen05 (persistent CTA pairs), float64 recombination"}[mode],
             "config": _config_dict(args, w, b_per_gpu, world, "device-resident"),
             "onestep_calls_per_sec": value * w.horizon,
             "algorithmic_tflops": value * w.horizon * workloads.flop_per_step(w.n_s, w.n_u, w.n_train) / 1e12,
@@ -380,9 +394,9 @@ def main():
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2],
+    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
                     help="variance contraction pipe: -1 auto (2 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
-                         "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2)")
+                         "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs")
     ap.add_argument("--redundant-factor", action="store_true",
                     help="factorise on every rank instead of broadcasting the factor")
     args = ap.parse_args()

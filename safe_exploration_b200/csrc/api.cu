@@ -91,6 +91,7 @@ struct segp_model {
     long opt_tri_mode = -1;   // -1 = automatic (2 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
                               // 1 = int8 tcgen05 single CTA, 2 = int8 tcgen05 CTA pair (cta_group::2)
     long opt_i8_ablate = 0;   // profiling only, see TriI8Args::ablate
+    long long* i8_prof = nullptr;   // profiling only: [128][8] counters of the persistent kernel's MMA threads
     long launches = 0;
     // optional per-launch timing of tri_sumsq (bench.py roofline): event pairs recorded on the launching stream
     bool time_tri = false;
@@ -249,7 +250,7 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st) {
         k8.k = k;
         k8.ki8 = m->ki8;
         k8.npanel_cap = m->npanel_cap;
-        k8.split_halves = m->ws_mode == 2;
+        k8.split_halves = m->ws_mode >= 2;
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
     }
     return launch_kstar(k, m->n_s, m->nsplit, st);
@@ -284,7 +285,10 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st) {
         t.fix_bi = -1;
         t.zero_a = m->i8zero;
         t.ablate = (int)m->opt_i8_ablate;
-        SEGP_CHECK(m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st) : launch_tri_i8(t, m->n_s, st));
+        t.prof = m->i8_prof;
+        SEGP_CHECK(m->ws_mode == 3   ? launch_tri_i8x2p(t, m->n_s, st)
+                   : m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st)
+                                     : launch_tri_i8(t, m->n_s, st));
     } else {
         TriArgs t{};
         t.wt = m->wt;
@@ -371,6 +375,7 @@ int segp_destroy(segp_model* m) {
     free_model_buffers(m);
     free_workspace(m);
     dev_free(m->d_sp);
+    dev_free(m->i8_prof);
     for (cudaEvent_t e : m->tri_events) cudaEventDestroy(e);
     if (m->stage != nullptr) cudaFree(m->stage);
     delete m;
@@ -1082,7 +1087,7 @@ int segp_i8_peak(int device, int umma_n, int iters, double* tops) {
 
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum) {
-    if ((variant != 1 && variant != 2) || k_blocks < 1 || k_blocks > 64 || (variant == 2 && (k_blocks & 1)) ||
+    if ((variant < 1 || variant > 3) || k_blocks < 1 || k_blocks > 64 || (variant >= 2 && (k_blocks & 1)) ||
         h_a == nullptr || h_b == nullptr || h_acc == nullptr || h_colsum == nullptr) {
         set_error("segp_i8_selftest: bad argument (variant 1|2, k_blocks in [1,64], even for variant 2)");
         return SEGP_ERR_INVALID;
@@ -1097,8 +1102,8 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
     //   variant 1: block row k_blocks - 1 (128 rows);  variant 2: block rows k_blocks - 2 and k_blocks - 1 (256 rows),
     //   where the upper block row sees zeros in the last 128 columns (its own k-range ends one block earlier)
     const int nblk = k_blocks, kdim = TILE * k_blocks, nkb = 2 * k_blocks;
-    const int rows = variant == 2 ? 2 * TILE : TILE;
-    const int bi0 = variant == 2 ? k_blocks - 2 : k_blocks - 1;
+    const int rows = variant >= 2 ? 2 * TILE : TILE;
+    const int bi0 = variant >= 2 ? k_blocks - 2 : k_blocks - 1;
     const size_t a_bytes = (size_t)nblk * (nblk + 1) * (I8_S * I8_A_TILE);
     const size_t b_bytes = (size_t)nkb * (I8_S * I8_B_TILE);
     std::vector<int8_t> a_img(a_bytes, 0), b_img(b_bytes, 0);
@@ -1120,7 +1125,7 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
                 for (int r = 0; r < I8_N; ++r) {
                     const int8_t v = h_b[((size_t)pl * I8_N + r) * kdim + (size_t)kb * I8_KB + k];
                     int8_t* kbase = b_img.data() + (size_t)kb * (I8_S * I8_B_TILE);
-                    if (variant == 2)
+                    if (variant >= 2)
                         kbase[(size_t)(r / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) + (size_t)pl * (I8_B_TILE / 2) +
                               sw(r % (I8_N / 2), k)] = v;
                     else
@@ -1160,8 +1165,11 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
         t.b_cap = I8_N;
         t.dbg = d_dbg;
         t.zero_a = d_zero;
-        t.fix_bi = variant == 2 ? bi0 / 2 : bi0;
-        if ((rc = (variant == 2 ? launch_tri_i8x2(t, 1, nullptr) : launch_tri_i8(t, 1, nullptr))) != SEGP_OK) break;
+        t.fix_bi = variant >= 2 ? bi0 / 2 : bi0;
+        if ((rc = (variant == 3   ? launch_tri_i8x2p(t, 1, nullptr)
+                   : variant == 2 ? launch_tri_i8x2(t, 1, nullptr)
+                                  : launch_tri_i8(t, 1, nullptr))) != SEGP_OK)
+            break;
         e = cudaDeviceSynchronize();
         if (e == cudaSuccess) e = cudaMemcpy(h_acc, d_dbg, n_dbg * sizeof(int32_t), cudaMemcpyDeviceToHost);
         if (e == cudaSuccess)   // column sums of the block row(s): [rows / 128][96]
@@ -1202,7 +1210,7 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_ksplit = value;
         return SEGP_OK;
     }
-    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 2) {
+    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 3) {
         if (value >= 1 && m->has_data && !i8_capable(m)) {
             set_error("tri_mode=%ld (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", value, I8_MAX_NPAD,
                       m->n_pad);
@@ -1213,6 +1221,17 @@ int segp_set_option(segp_model* m, const char* name, long value) {
     }
     if (strcmp(name, "i8_ablate") == 0) {
         m->opt_i8_ablate = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "i8_prof") == 0) {   // 1: allocate the counter buffer; 0: release it
+        DeviceGuard guard(m->device);
+        if (value != 0 && m->i8_prof == nullptr) {
+            SEGP_CHECK(dev_alloc(&m->i8_prof, (size_t)128 * 8));
+            SEGP_CUDA_CHECK(cudaMemset(m->i8_prof, 0, 128 * 8 * sizeof(long long)));
+        } else if (value == 0) {
+            cudaDeviceSynchronize();
+            dev_free(m->i8_prof);
+        }
         return SEGP_OK;
     }
     if (strcmp(name, "time_tri") == 0) {
@@ -1233,6 +1252,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "panel_group") == 0) *value = m->opt_panel_group;
     else if (strcmp(name, "ksplit") == 0) *value = m->opt_ksplit;
     else if (strcmp(name, "tri_mode") == 0) *value = m->opt_tri_mode;
+    else if (strcmp(name, "i8_prof_ptr") == 0) *value = (long)(uintptr_t)m->i8_prof;
     else if (strcmp(name, "tri_mode_effective") == 0) *value = tri_mode(m);
     else if (strcmp(name, "launches") == 0) *value = m->launches;
     else if (strcmp(name, "n_train_padded") == 0) *value = m->n_pad;

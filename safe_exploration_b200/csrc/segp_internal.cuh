@@ -114,12 +114,15 @@ struct TriI8Args {
     long npanel_cap, b_cap;
     int32_t* dbg;           // optional raw accumulators [I8_S][128 (256 for the pair kernel)][I8_N] of one tile
     int fix_bi;             // >= 0: single-tile self-test mode (block row, or block-row pair for the pair kernel)
+    long long* prof;        // profiling only (persistent kernel): [cluster][8] clock64 counters of the MMA thread
     int ablate;             // profiling only (pair kernel): 1 = no bulk copies, 2 = no MMAs, 4 = no epilogue math
     const int8_t* zero_a;   // pair kernel: I8_S * I8_A_TILE zero bytes (k-blocks right of the upper block row's diagonal)
 };
 int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);
 // CTA-pair variant: cta_group::2 MMAs, M = 256 (two block rows), each CTA stages its own A rows and half of B
 int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st);
+// persistent CTA-pair variant: one resident pair per TPC walks a static tile list
+int launch_tri_i8x2p(const TriI8Args& a, int n_s, cudaStream_t st);
 int tri_i8_init();
 // W (n_pad x n_pad fp64, lower) -> digit planes + row factors for output dimension d
 int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int n_pad, cudaStream_t st);

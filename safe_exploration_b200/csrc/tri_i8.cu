@@ -15,6 +15,8 @@
 //   i8_peak        register/shared-only issue loop that measures the int8 tensor-pipe rate (roofline denominator)
 #include <math.h>
 
+#include <algorithm>
+
 #include "segp_internal.cuh"
 
 namespace segp {
@@ -831,6 +833,265 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i
     }
 }
 
+// =========================================================================================== tri_i8x2p (persistent)
+// Same tiles, same arithmetic, same barriers as tri_i8x2, but ONE resident CTA pair per TPC walks a static list of
+// tiles (heavy-first order, boustrophedon over the clusters so every cluster gets the same mix of long and short
+// tiles): TMEM allocation, barrier initialisation and the cluster handshakes happen once per kernel instead of once per
+// tile, the producer runs ahead into the next tile while the epilogue of the current one drains TMEM, and no cluster
+// launch latency sits between tiles (the per-tile overhead of tri_i8x2 was ~14k clocks, 18 % of the MMA time at C4).
+// One more barrier: tmem_empty (leader CTA, 2 arrivals = the epilogues of both CTAs) gates the first MMA of the next tile.
+struct X2Tile {
+    int d, bp, panel;
+};
+__device__ __forceinline__ bool x2_decode_tile(const TriI8Args& a, long t, int npairs, X2Tile& out) {
+    if (a.fix_bi >= 0) {
+        out.d = 0;
+        out.bp = a.fix_bi;
+        out.panel = 0;
+        return t == 0;
+    }
+    const int tiles_per_group = I8_PANEL_GROUP * npairs;
+    const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+    const long gid = t / tiles_per_group;
+    const int r = (int)(t % tiles_per_group);
+    out.d = (int)(gid / npg);
+    const int pg = (int)(gid % npg);
+    out.bp = npairs - 1 - r / I8_PANEL_GROUP;
+    out.panel = pg * I8_PANEL_GROUP + r % I8_PANEL_GROUP;
+    return out.panel < a.npanels;
+}
+// tile index of round `rr` for cluster `c` of `nc`: even rounds left to right, odd rounds right to left
+__device__ __forceinline__ long x2_tile_of_round(long rr, int c, int nc) {
+    return rr * nc + ((rr & 1) ? (nc - 1 - c) : c);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+    tri_i8x2p_kernel(const TriI8Args a, const long n_tiles) {
+    const uint32_t rank = cluster_ctarank();
+    const int npairs = (a.nblk + 1) / 2;
+    const int cluster = blockIdx.x >> 1;
+    const int nclusters = gridDim.x >> 1;
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_addr(smem_raw);
+    const uint32_t stage0 = (raw + 1023u) & ~1023u;
+    unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)X2_STAGES * X2_STAGE_BYTES;
+    double* s_col = reinterpret_cast<double*>(tail);                   // [4][I8_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 4 * I8_N);     // full[4], peer_full[4], empty[4], tmem_full, tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * X2_STAGES + 2);
+    const uint32_t bar0 = smem_addr(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto peer_full_bar = [&](int s) { return bar0 + 8u * (X2_STAGES + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * X2_STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (3 * X2_STAGES);
+    const uint32_t tmem_empty_bar = bar0 + 8u * (3 * X2_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < X2_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(peer_full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
+                     "n"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            long g = 0;   // running k-block counter: ring stage g % 4, phase (g / 4) & 1
+            for (long rr = 0;; ++rr) {
+                const long t = x2_tile_of_round(rr, cluster, nclusters);
+                if (rr * nclusters >= n_tiles) break;
+                X2Tile tl;
+                if (t >= n_tiles || !x2_decode_tile(a, t, npairs, tl)) continue;
+                const int bi = 2 * tl.bp + (int)rank;
+                const bool has_rows = bi < a.nblk;
+                const int bi_hi = min(2 * tl.bp + 1, a.nblk - 1);
+                const int nk = 2 * (bi_hi + 1);
+                const int nk_own = has_rows ? 2 * (bi + 1) : 0;
+                const int8_t* wsrc =
+                    a.wi8 + ((long)tl.d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (I8_S * I8_A_TILE);
+                const int8_t* ksrc = a.ki8 +
+                                     (((long)tl.d * a.npanel_cap + tl.panel) * (a.nblk * 2)) * (long)(I8_S * I8_B_TILE) +
+                                     (long)rank * (I8_S * (I8_B_TILE / 2));
+                for (int it = 0; it < nk; ++it, ++g) {
+                    const int s = (int)(g % X2_STAGES);
+                    if (g >= X2_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((g / X2_STAGES - 1) & 1));
+                    const uint32_t dst = stage0 + (uint32_t)s * X2_STAGE_BYTES;
+                    if (a.ablate & 1) {
+                        mbar_expect_tx(full_bar(s), 0);
+                        continue;
+                    }
+                    mbar_expect_tx(full_bar(s), X2_STAGE_BYTES);
+                    const int8_t* asrc = it < nk_own ? wsrc + (long)it * (I8_S * I8_A_TILE) : a.zero_a;
+                    bulk_g2s(dst, asrc, I8_S * I8_A_TILE, full_bar(s));
+                    bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * (I8_B_TILE / 2),
+                             full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            long g = 0;
+            long ti = 0;   // tiles done by this cluster: phase of the tmem barriers
+            constexpr uint32_t idesc = make_i8_idesc(2 * TILE, I8_N);
+            const bool prof = a.prof != nullptr && rank == 0;
+            long long t_start = 0, t_full = 0, t_peer = 0, t_tmem = 0, c0 = 0;
+            if (prof) t_start = clock64();
+            for (long rr = 0;; ++rr) {
+                const long t = x2_tile_of_round(rr, cluster, nclusters);
+                if (rr * nclusters >= n_tiles) break;
+                X2Tile tl;
+                if (t >= n_tiles || !x2_decode_tile(a, t, npairs, tl)) continue;
+                const int bi_hi = min(2 * tl.bp + 1, a.nblk - 1);
+                const int nk = 2 * (bi_hi + 1);
+                if (rank == 1) {
+                    // ---------------------------------------------------------- relay my full barriers to the leader
+                    for (int it = 0; it < nk; ++it, ++g) {
+                        const int s = (int)(g % X2_STAGES);
+                        mbar_wait(full_bar(s), (uint32_t)((g / X2_STAGES) & 1));
+                        mbar_arrive_remote(peer_full_bar(s), 0u);
+                    }
+                    continue;
+                }
+                // -------------------------------------------------------------- MMA issuer of the pair
+                if (ti > 0) {   // both epilogues have drained the accumulators of the previous tile
+                    if (prof) c0 = clock64();
+                    mbar_wait_cluster(tmem_empty_bar, (uint32_t)((ti - 1) & 1));
+                    if (prof) t_tmem += clock64() - c0;
+                    tc_fence_after();
+                }
+                for (int it = 0; it < nk; ++it, ++g) {
+                    const int s = (int)(g % X2_STAGES);
+                    const uint32_t par = (uint32_t)((g / X2_STAGES) & 1);
+                    if (prof) c0 = clock64();
+                    mbar_wait(full_bar(s), par);
+                    if (prof) {
+                        const long long c1 = clock64();
+                        t_full += c1 - c0;
+                        c0 = c1;
+                    }
+                    mbar_wait_cluster(peer_full_bar(s), par);
+                    if (prof) t_peer += clock64() - c0;
+                    tc_fence_after();
+                    const uint32_t sa = stage0 + (uint32_t)s * X2_STAGE_BYTES;
+                    const uint32_t sb = sa + I8_S * I8_A_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < I8_KB / 32; ++ks) {
+                        if (a.ablate & 2) break;
+#pragma unroll
+                        for (int pa = 0; pa < I8_S; ++pa) {
+                            const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
+#pragma unroll
+                            for (int pc = 0; pc < I8_S - pa; ++pc) {
+                                const uint64_t bdesc = make_sw64_desc(sb + pc * (I8_B_TILE / 2) + ks * 32);
+                                tc_mma_i8_pair(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, idesc,
+                                               (uint32_t)((it | ks | pa) != 0));
+                            }
+                        }
+                    }
+                    tc_commit_pair(empty_bar(s));
+                }
+                tc_commit_pair(tmem_full_bar);
+                ++ti;
+            }
+            if (prof) {
+                long long* o = a.prof + (long)cluster * 8;
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                o[0] = clock64() - t_start;
+                o[1] = t_full;
+                o[2] = t_peer;
+                o[3] = t_tmem;
+                o[4] = ti;
+                o[5] = g;
+                o[6] = (long long)smid;
+                o[7] = 0;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        long ti = 0;
+        for (long rr = 0;; ++rr) {
+            const long t = x2_tile_of_round(rr, cluster, nclusters);
+            if (rr * nclusters >= n_tiles) break;
+            X2Tile tl;
+            if (t >= n_tiles || !x2_decode_tile(a, t, npairs, tl)) continue;
+            const int bi = 2 * tl.bp + (int)rank;
+            const bool has_rows = bi < a.nblk;
+            const double rf = has_rows ? a.rowfac[((long)tl.d * a.nblk + bi) * TILE + row] : 0.0;
+            mbar_wait_cluster(tmem_full_bar, (uint32_t)(ti & 1));
+            tc_fence_after();
+            int32_t* dbg_row = a.dbg != nullptr ? a.dbg + ((long)rank * TILE + row) * I8_N : nullptr;
+#pragma unroll 1
+            for (int chunk = 0; chunk < ((a.ablate & 4) ? 0 : I8_N / 32); ++chunk)
+                s_col[q * I8_N + chunk * 32 + lane] = i8_epilogue_chunk(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32,
+                                                                        rf, lane, dbg_row, (long)2 * TILE * I8_N);
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // all four quadrants read: TMEM may be overwritten
+            if (threadIdx.x == 64) {
+                if (rank == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar) : "memory");
+                else
+                    mbar_arrive_remote(tmem_empty_bar, 0u);
+            }
+            const int c = threadIdx.x - 64;
+            if (c < I8_N && has_rows) {
+                const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
+                const long bcol = (long)tl.panel * I8_N + c;
+                if (bcol < a.b_cap) a.qpart[((long)tl.d * a.nblk + bi) * a.b_cap + bcol] = sum;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // s_col is free for the next tile
+            ++ti;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+int launch_tri_i8x2p(const TriI8Args& a, int n_s, cudaStream_t st) {
+    long n_tiles = 1;
+    if (a.fix_bi < 0) {
+        const int npairs = (a.nblk + 1) / 2;
+        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        n_tiles = (long)n_s * npg * I8_PANEL_GROUP * npairs;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        SEGP_CUDA_CHECK(cudaGetDevice(&dev));
+        SEGP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (n_tiles <= 0) {
+        set_error("tri_i8x2p: no tiles");
+        return SEGP_ERR_INVALID;
+    }
+    const long nclusters = std::min<long>(std::max(sms / 2, 1), n_tiles);
+    tri_i8x2p_kernel<<<(unsigned)(2 * nclusters), I8_THREADS, X2_SMEM, st>>>(a, n_tiles);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
 int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st) {
     long nclusters = 1;
     if (a.fix_bi < 0) {
@@ -850,6 +1111,7 @@ int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st) {
 int tri_i8_init() {
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     return SEGP_OK;
 }
 

@@ -24,19 +24,19 @@ def se():
     return pkg
 
 
-@pytest.mark.parametrize("variant,k_blocks", [(1, 1), (1, 2), (1, 5), (2, 2), (2, 4), (2, 6)])
+@pytest.mark.parametrize("variant,k_blocks", [(1, 1), (1, 2), (1, 5), (2, 2), (2, 4), (2, 6), (3, 2), (3, 6)])
 def test_one_tile_exact_integers(se, variant, k_blocks):
-    """variant 1: single-CTA kernel, 128 rows; variant 2: CTA pair (cta_group::2), 256 rows."""
+    """variant 1: single-CTA kernel, 128 rows; variant 2: CTA pair (cta_group::2), 256 rows; 3: persistent pair."""
     lib = se._lib.load()
     rng = np.random.default_rng(10 * variant + k_blocks)
     kdim = TILE * k_blocks
-    rows = TILE * variant
+    rows = TILE * min(variant, 2)
     a = rng.integers(-127, 128, size=(I8_S, rows, kdim), dtype=np.int8)
-    if variant == 2:
+    if variant >= 2:
         a[:, :TILE, kdim - TILE:] = 0      # the upper block row ends one diagonal block earlier
     b = rng.integers(-127, 128, size=(I8_S, I8_N, kdim), dtype=np.int8)
     acc = np.zeros((I8_S, rows, I8_N), dtype=np.int32)
-    colsum = np.zeros((variant, I8_N), dtype=np.float64)
+    colsum = np.zeros((rows // TILE, I8_N), dtype=np.float64)
     se._lib.check(lib.segp_i8_selftest(0, variant, k_blocks, a.ctypes.data_as(ctypes.c_void_p),
                                        b.ctypes.data_as(ctypes.c_void_p), acc.ctypes.data_as(ctypes.c_void_p),
                                        colsum.ctypes.data_as(ctypes.c_void_p)))
@@ -51,7 +51,7 @@ def test_one_tile_exact_integers(se, variant, k_blocks):
     horner = np.zeros((rows, I8_N), dtype=object)
     for g in range(I8_S):
         horner = horner * 254 + want[g].astype(object)
-    for rb in range(variant):
+    for rb in range(rows // TILE):
         want_col = np.array([float(sum(int(v) ** 2 for v in horner[rb * TILE:(rb + 1) * TILE, c]))
                              for c in range(I8_N)])
         assert np.allclose(colsum[rb], want_col, rtol=1e-13, atol=0.0)
@@ -81,7 +81,7 @@ def _cancelling_model(se, n, n_s, n_u, kern, seed, tri_mode):
     return gp, ora, z
 
 
-@pytest.mark.parametrize("tri_mode", [0, 1, 2])
+@pytest.mark.parametrize("tri_mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,n_s,n_u,kern", [(1500, 2, 1, "rbf"), (3000, 4, 1, "rbf"), (2000, 3, 2, "mat52")])
 def test_predict_variance_under_cancellation(se, n, n_s, n_u, kern, tri_mode):
     gp, ora, z = _cancelling_model(se, n, n_s, n_u, kern, 5, tri_mode)
@@ -102,7 +102,7 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
     from safe_exploration_b200 import workloads
     w = workloads.make("C4", batch=700)
     out = {}
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp,
                              tri_mode=mode)
         out[mode] = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
@@ -110,6 +110,7 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
     assert all(np.all(o.status == 0) for o in out.values())
     # the two tcgen05 kernels execute the same exact integer arithmetic: identical bits
     assert np.array_equal(out[1].q_all, out[2].q_all) and np.array_equal(out[1].var_all, out[2].var_all)
+    assert np.array_equal(out[3].q_all, out[2].q_all) and np.array_equal(out[3].var_all, out[2].var_all)
     for name in ("var_all", "p_all", "q_all"):
         a0, a1 = getattr(out[0], name), getattr(out[2], name)
         err = float(np.max(np.abs(a1 - a0) / (np.abs(a0) + 1e-12 * np.abs(a0).max())))
@@ -119,10 +120,11 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
 
 def test_pair_kernel_odd_block_rows(se):
     """N = 1100 pads to 9 block rows: the last CTA pair has only one real block row."""
-    gp, ora, z = _cancelling_model(se, 1100, 2, 1, "rbf", 9, 2)
-    assert gp.get_option("n_train_padded") == 1152
-    mu, var, _ = gp.predict(z, compute_gradients=True)
-    mu_o, var_o, _ = ora.predict_batch(z)
-    assert float(np.max(np.abs(var - var_o) / np.abs(var_o))) < 1e-5
-    assert float(np.max(np.abs(mu - mu_o) / (np.abs(mu_o) + 1e-6))) < 1e-6
-    gp.close()
+    for mode in (2, 3):
+        gp, ora, z = _cancelling_model(se, 1100, 2, 1, "rbf", 9, mode)
+        assert gp.get_option("n_train_padded") == 1152
+        mu, var, _ = gp.predict(z, compute_gradients=True)
+        mu_o, var_o, _ = ora.predict_batch(z)
+        assert float(np.max(np.abs(var - var_o) / np.abs(var_o))) < 1e-5
+        assert float(np.max(np.abs(mu - mu_o) / (np.abs(mu_o) + 1e-6))) < 1e-6
+        gp.close()
