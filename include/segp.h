@@ -100,6 +100,13 @@ int segp_logdet(segp_model* m, double* h_out);
 int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
                  void* stream);
 
+/* what the n_s x n_s matrix carried along a rollout means */
+#define SEGP_PROP_ELLIPSOID 0       /* ellipsoid shape matrix Q, gp_reachability.py:19-156 (default)                */
+#define SEGP_PROP_TAYLOR 1          /* Gaussian covariance, first-order Taylor: one_step_taylor,
+                                       uncertainty_propagation_casadi.py:11-87 / multi_step_taylor_symbolic :90-148   */
+#define SEGP_PROP_MEAN_EQUIVALENT 2 /* Gaussian covariance, mean-equivalent: one_step_mean_equivalent :210-283 /
+                                       mean_equivalent_multistep :151-207                                              */
+
 /* Shared (not per-trajectory) parameters of the reachability recursion; HOST pointers. */
 typedef struct segp_reach_params {
     const double* h_l_mu;    /* [n_s]  Lipschitz constants of the mean gradient (gp_reachability.py:38) */
@@ -108,6 +115,8 @@ typedef struct segp_reach_params {
     const double* h_a;       /* [n_s x n_s] linear prior, NULL = identity (gp_reachability.py:61-63)     */
     const double* h_b;       /* [n_s x n_u] linear prior, NULL = zero                                    */
     const double* h_t_z_gp;  /* [n_s_in x n_s] GP input transform or NULL (gp_reachability_casadi.py:60) */
+    int propagation;         /* SEGP_PROP_*; with TAYLOR / MEAN_EQUIVALENT d_q0 / d_q_all hold covariances, l_mu,
+                                l_sigma and c_safety are ignored (pass zeros)                                    */
 } segp_reach_params;
 
 /* n_batch independent H-step ellipsoid reachability recursions.

@@ -23,6 +23,11 @@ reach_oracle.py  float64 NumPy restatement of the ellipsoid half (reference
                  unmodified functions (imported through ref_loader.py) and the
                  reference's known-answer tests; golden vectors produced by the
                  reference code are committed under tests/golden/.
+score_oracle.py  restatement of the SafeMPC constraint / cost assembly (safempc_simple.py:286-392,
+                 488-532, 911-942) around the pinned safety distance.
+uprop_oracle.py  closed-form batch restatement of uncertainty_propagation_casadi.py:11-283.
+                 PINNED against the reference's own functions (live through the NumPy-backed
+                 CasADi shim, and tests/golden/uncertainty_propagation.npz).
 ref_loader.py    imports the reference's own gp_reachability / utils /
                  utils_ellipsoid from /root/reference (this container only)
                  through a one-function ``casadi.reshape`` stand-in.

@@ -1,11 +1,16 @@
-"""One-function stand-in for the ``casadi`` module (ORACLE / TEST INFRASTRUCTURE).
+"""Minimal NumPy-backed stand-in for the ``casadi`` module (ORACLE / TEST INFRASTRUCTURE).
 
-The reference's ``safe_exploration/utils.py:14`` does ``from casadi import reshape``
-at import time although none of the NumPy hot-path functions use it.  CasADi is not
-installable in this image, so ``oracle/ref_loader.py`` puts this directory on
-``sys.path`` to let the reference's own ``gp_reachability.py`` / ``utils.py`` /
-``utils_ellipsoid.py`` import unmodified.  CasADi reshapes are column-major.
+CasADi is not installable in this image.  ``oracle/ref_loader.py`` puts this directory on ``sys.path`` so that the
+reference's own modules import UNMODIFIED and run on NumPy arrays:
+
+* ``safe_exploration/utils.py:14`` does ``from casadi import reshape`` at import time (none of the NumPy hot-path
+  functions use it): ``reshape`` (column-major, like CasADi);
+* ``safe_exploration/uncertainty_propagation_casadi.py:8`` does ``from casadi import *`` and then uses ``mtimes``,
+  ``vertcat``, ``horzcat``, ``diag``, ``MX.eye``, ``MX.zeros`` and -- through CasADi's own star export -- ``np``.
+
+Only numeric evaluation is provided; nothing symbolic.
 """
+import numpy as np
 import numpy as _np
 
 
@@ -13,3 +18,45 @@ def reshape(x, *shape):
     if len(shape) == 1:
         shape = shape[0]
     return _np.reshape(_np.asarray(x), shape, order="F")
+
+
+def mtimes(*args):
+    if len(args) == 1 and isinstance(args[0], (list, tuple)):
+        args = tuple(args[0])
+    out = _np.asarray(args[0])
+    for m in args[1:]:
+        out = _np.dot(out, _np.asarray(m))
+    return out
+
+
+def vertcat(*args):
+    return _np.vstack([_np.atleast_2d(_np.asarray(a)) for a in args])
+
+
+def horzcat(*args):
+    return _np.hstack([_np.atleast_2d(_np.asarray(a)) for a in args])
+
+
+def diag(x):
+    """CasADi semantics: a vector (n x 1 or 1 x n) gives the diagonal matrix, a matrix gives its diagonal (n x 1)."""
+    x = _np.asarray(x)
+    if x.ndim <= 1 or 1 in x.shape:
+        return _np.diag(x.reshape(-1))
+    return _np.diag(x).reshape(-1, 1)
+
+
+class MX(object):
+    @staticmethod
+    def eye(n):
+        return _np.eye(n)
+
+    @staticmethod
+    def zeros(*shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        if len(shape) == 1:
+            shape = (shape[0], 1)
+        return _np.zeros(shape)
+
+
+SX = MX

@@ -172,9 +172,49 @@ def golden_ellipsoid_algebra(utils, uell):
     np.savez(os.path.join(OUT, "ellipsoid_algebra.npz"), **out)
 
 
+def golden_uncertainty_propagation():
+    """Outputs of the reference's own multi_step_taylor_symbolic / mean_equivalent_multistep
+    (uncertainty_propagation_casadi.py, run numerically through the NumPy-backed CasADi shim) on the cart-pole
+    fixture, with and without the linear prior and the GP-input transform."""
+    up = ref_loader.load_uncertainty_propagation()
+    d = np.load(os.path.join(REF_TEST, "data_cartpole.npz"))
+    x, y = d["X"][:80], d["y"][:80]
+    n_s, n_u, hor, bsz = y.shape[1], x.shape[1] - y.shape[1], 5, 6
+    rng = np.random.RandomState(11)
+    ls = rng.uniform(0.8, 2.5, size=(n_s, n_s + n_u))
+    var = rng.uniform(0.5, 1.5, size=n_s)
+    noise = np.full(n_s, 0.05 + 1e-5 + 1e-8)
+    kern = ["rbf", "mat52", "rbf", "mat52"][:n_s]
+    gp = GPOracle(x, y, kern, ls, var, noise)
+    a = np.eye(n_s) + 0.05 * rng.randn(n_s, n_s)
+    b = 0.1 * rng.randn(n_s, n_u)
+    mu0 = 0.1 * rng.randn(bsz, n_s)
+    k_ff = 0.2 * rng.randn(bsz, hor, n_u)
+    k_fb = 0.3 * rng.randn(bsz, hor - 1, n_u, n_s)
+    out = dict(x_train=x, y_train=y, kern_types=np.array(kern), lengthscale=ls, variance=var, noise=noise, a=a, b=b,
+               mu0=mu0, k_ff=k_ff, k_fb=k_fb)
+    # GP on a reduced input (drop the first state, as the reference's cart-pole configs do)
+    t_mat = np.eye(n_s)[1:]
+    gp_t = GPOracle(x[:, 1:], y, kern, ls[:, 1:], var, noise)
+    out["t_mat"] = t_mat
+    for tag, fn in (("taylor", up.multi_step_taylor_symbolic), ("meaneq", up.mean_equivalent_multistep)):
+        for pr, (aa, bb, model, tm) in (("lin", (a, b, gp, None)), ("nolin", (None, None, gp, None)),
+                                        ("trafo", (a, b, gp_t, t_mat))):
+            mu_all = np.empty((bsz, hor, n_s))
+            sig_all = np.empty((bsz, hor, n_s, n_s))
+            for i in range(bsz):
+                m, sg, _ = fn(mu0[i].reshape(n_s, 1), model, k_ff[i], k_fb[i], None, aa, bb, tm)
+                mu_all[i] = np.asarray(m, dtype=np.float64)
+                sig_all[i] = np.asarray(sg, dtype=np.float64).reshape(hor, n_s, n_s)
+            out["mu_%s_%s" % (tag, pr)] = mu_all
+            out["sigma_%s_%s" % (tag, pr)] = sig_all
+    np.savez(os.path.join(OUT, "uncertainty_propagation.npz"), **out)
+
+
 def main():
     reach, utils, uell = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    golden_uncertainty_propagation()
     golden_invpend_c1(reach)
     golden_invpend_reach_test(reach)
     golden_cartpole(reach)

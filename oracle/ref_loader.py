@@ -19,8 +19,7 @@ def available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "safe_exploration", "gp_reachability.py"))
 
 
-def load():
-    """Returns (gp_reachability, utils, utils_ellipsoid) modules of the reference."""
+def _prepare_path():
     if not available():
         raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
     have_casadi = True
@@ -32,7 +31,22 @@ def load():
         sys.path.insert(0, _SHIM)
     if REFERENCE_ROOT not in sys.path:
         sys.path.append(REFERENCE_ROOT)
+
+
+def load():
+    """Returns (gp_reachability, utils, utils_ellipsoid) modules of the reference."""
+    _prepare_path()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         from safe_exploration import gp_reachability, utils, utils_ellipsoid
     return gp_reachability, utils, utils_ellipsoid
+
+
+def load_uncertainty_propagation():
+    """The reference's uncertainty_propagation_casadi module (one_step_taylor, multi_step_taylor_symbolic,
+    one_step_mean_equivalent, mean_equivalent_multistep), evaluated numerically through the NumPy-backed shim."""
+    _prepare_path()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from safe_exploration import uncertainty_propagation_casadi
+    return uncertainty_propagation_casadi

@@ -9,7 +9,7 @@ does, and raises otherwise (there is no CPU fallback; the CPU oracle under oracl
 """
 from . import _lib  # noqa: F401
 from .ssm import BatchedGPSSM  # noqa: F401
-from . import gp_reachability, safempc_sampling, utils, utils_ellipsoid  # noqa: F401
+from . import gp_reachability, safempc_sampling, uncertainty_propagation, utils, utils_ellipsoid  # noqa: F401
 from .safempc_sampling import SamplingSafeMPC, best_candidate, score_rollouts  # noqa: F401
 from .gp_reachability import (lin_ellipsoid_safety_distance, multistep_reachability,  # noqa: F401
                               onestep_reachability, rollout)

@@ -35,7 +35,12 @@ _dbl = ctypes.c_double
 class ReachParams(ctypes.Structure):
     """struct segp_reach_params (include/segp.h)."""
     _fields_ = [("h_l_mu", _c_double_p), ("h_l_sigma", _c_double_p), ("c_safety", _dbl),
-                ("h_a", _c_double_p), ("h_b", _c_double_p), ("h_t_z_gp", _c_double_p)]
+                ("h_a", _c_double_p), ("h_b", _c_double_p), ("h_t_z_gp", _c_double_p), ("propagation", _int)]
+
+
+PROP_ELLIPSOID = 0
+PROP_TAYLOR = 1
+PROP_MEAN_EQUIVALENT = 2
 
 
 class ScoreParams(ctypes.Structure):
@@ -162,7 +167,7 @@ def current_stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def make_reach_params(l_mu, l_sigma, c_safety, a, b, t_z_gp, n_s, n_u, n_in):
+def make_reach_params(l_mu, l_sigma, c_safety, a, b, t_z_gp, n_s, n_u, n_in, propagation=0):
     """Build the shared-parameter struct; returns (struct, keepalive list)."""
     l_mu = host_f64(l_mu, (n_s,))
     l_sigma = host_f64(l_sigma, (n_s,))
@@ -179,5 +184,6 @@ def make_reach_params(l_mu, l_sigma, c_safety, a, b, t_z_gp, n_s, n_u, n_in):
     if t_z_gp is not None:
         t_h = host_f64(t_z_gp, (n_in, n_s))
         keep.append(t_h)
-    prm = ReachParams(dbl_ptr(l_mu), dbl_ptr(l_sigma), float(c_safety), dbl_ptr(a_h), dbl_ptr(b_h), dbl_ptr(t_h))
+    prm = ReachParams(dbl_ptr(l_mu), dbl_ptr(l_sigma), float(c_safety), dbl_ptr(a_h), dbl_ptr(b_h), dbl_ptr(t_h),
+                      int(propagation))
     return prm, keep

@@ -200,6 +200,11 @@ static int fill_step_params(StepParams* sp, const segp_reach_params* prm, int n_
         for (int j = 0; j < n_s; ++j) sp->a[i * n_s + j] = prm->h_a ? prm->h_a[i * n_s + j] : (i == j ? 1.0 : 0.0);
     for (int i = 0; i < n_s; ++i)
         for (int j = 0; j < n_u; ++j) sp->b[i * n_u + j] = prm->h_b ? prm->h_b[i * n_u + j] : 0.0;
+    if (prm->propagation < SEGP_PROP_ELLIPSOID || prm->propagation > SEGP_PROP_MEAN_EQUIVALENT) {
+        set_error("reach params: unknown propagation mode %d", prm->propagation);
+        return SEGP_ERR_INVALID;
+    }
+    sp->prop_mode = prm->propagation;
     sp->has_t = prm->h_t_z_gp != nullptr;
     if (sp->has_t) {
         for (int i = 0; i < n_in * n_s; ++i) sp->t[i] = prm->h_t_z_gp[i];
@@ -875,7 +880,7 @@ int segp_remainder_overapproximations(int device, long n_batch, int n_s, int n_u
         set_error("segp_remainder_overapproximations: null buffer");
         return SEGP_ERR_INVALID;
     }
-    segp_reach_params prm{h_l_mu, h_l_sigma, 1.0, nullptr, nullptr, nullptr};
+    segp_reach_params prm{h_l_mu, h_l_sigma, 1.0, nullptr, nullptr, nullptr, SEGP_PROP_ELLIPSOID};
     StepParams sp;
     SEGP_CHECK(fill_step_params(&sp, &prm, n_s, n_s, n_u));
     DeviceGuard guard(device);

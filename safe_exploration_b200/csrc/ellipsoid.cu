@@ -192,10 +192,12 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
         p1[i] = acc;
     }
     const double c = sp->c_safety;
+    const int mode = sp->prop_mode;   // 0 ellipsoid reachability, 1 Taylor, 2 mean-equivalent Gaussian propagation
     double q1[NS][NS];
 
     if (a.q == nullptr) {
-        // ---- point branch (gp_reachability.py:65-88): Q1 = diag(n_s (c sigma_d)^2)
+        // ---- point branch (gp_reachability.py:65-88): Q1 = diag(n_s (c sigma_d)^2);
+        //      Gaussian propagation (uncertainty_propagation_casadi.py:52-57, 256-261): Sigma1 = diag(sigma_d^2)
 #pragma unroll UF
         for (int i = 0; i < NS; ++i)
 #pragma unroll UF
@@ -203,9 +205,13 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
 #pragma unroll UF
         for (int i = 0; i < NS; ++i)
             if (i < n_s) {
-                const double bound = c * sqrt(var[i]);
-                if (!(bound > 0.0)) status |= SEGP_STATUS_ZERO_BOUND;
-                q1[i][i] = (double)n_s * bound * bound;
+                if (mode != SEGP_PROP_ELLIPSOID) {
+                    q1[i][i] = var[i];
+                } else {
+                    const double bound = c * sqrt(var[i]);
+                    if (!(bound > 0.0)) status |= SEGP_STATUS_ZERO_BOUND;
+                    q1[i][i] = (double)n_s * bound * bound;
+                }
             }
     } else {
         // ---- set branch (gp_reachability.py:89-156)
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
                         } else {
                             jrow[j] = a.jac_d[(b * n_s + d) * dim + j];
                         }
+                        if (mode == SEGP_PROP_MEAN_EQUIVALENT) jrow[j] = 0.0;   // no linearisation term
                     }
                 }
 #pragma unroll UF
@@ -298,6 +305,15 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
                 q1[i][j] = acc;
                 if (i == j) tr0 += acc;
             }
+        if (mode != SEGP_PROP_ELLIPSOID) {
+            // Gaussian propagation: [A B I] Sigma_all [A B I]^T of uncertainty_propagation_casadi.py:59-87 (Taylor)
+            // and :263-283 (mean equivalent) collapses to H Sigma H^T + diag(sigma^2) with the H above
+            // (H = A + B K for the mean-equivalent variant): with F = [I; K], Sigma_z = F Sigma F^T and
+            // Sigma_zg = Sigma_z J^T, so every block carries the factor F Sigma F^T.
+#pragma unroll UF
+            for (int i = 0; i < NS; ++i)
+                if (i < n_s) q1[i][i] += var[i];
+        } else {
         // remainder boxes (utils.py:129-142)
         const double r2 = lambda_max_qb<NS, NU>(q, kfb, n_s, n_u);
         const double r1 = sqrt(r2);
@@ -331,6 +347,7 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
         for (int i = 0; i < NS; ++i)
 #pragma unroll UF
             for (int j = 0; j < NS; ++j) q1[i][j] = f_0 * q1[i][j] + ((i == j) ? f_l * d_sig[i] : 0.0);
+        }
     }
 
     bool finite = true;

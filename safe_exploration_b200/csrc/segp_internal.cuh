@@ -41,7 +41,7 @@ struct StepParams {
     double l_sigma[SEGP_MAX_NS];
     double c_safety;
     int has_t;
-    int pad_;
+    int prop_mode;   // SEGP_PROP_*
 };
 
 // ---------------------------------------------------------------- kernel-matrix block + mean/Jacobian partials

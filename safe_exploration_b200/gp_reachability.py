@@ -45,7 +45,7 @@ def _is_tensor(x):
 
 
 def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safety=1., a=None, b=None,
-            t_z_gp=None, want_var=True):
+            t_z_gp=None, want_var=True, propagation=0):
     """B independent H-step reachability recursions in one call (the batched core behind
     multistep_reachability).
 
@@ -56,6 +56,8 @@ def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safe
     q_0       None | (n_s,n_s) shared | (B,n_s,n_s);  k_fb_init (n_u,n_s) | (B,n_u,n_s), needed with q_0
     NumPy inputs use host buffers through segp_multistep_host and return NumPy; CUDA float64 tensors stay
     on the device (segp_multistep, asynchronous on the current stream) and return tensors.
+    propagation  0 ellipsoid reachability (default); 1 / 2: q_all holds Gaussian covariances propagated by the
+              first-order Taylor / mean-equivalent scheme (see uncertainty_propagation.py); l_mu, l_sigma, c_safety unused
     Returns RolloutResult(p_all (B,H,n_s), q_all (B,H,n_s,n_s), var_all (B,H,n_s) | None, status (B,) int32).
     """
     if not isinstance(gp, BatchedGPSSM):
@@ -65,7 +67,7 @@ def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safe
     lib = gp._lib
     n_s, n_u, n_in = gp.n_s_out, gp.n_u, gp.n_s_in
     on_device = _is_tensor(k_ff)
-    prm, keep = _lib.make_reach_params(l_mu, l_sigma, c_safety, a, b, t_z_gp, n_s, n_u, n_in)
+    prm, keep = _lib.make_reach_params(l_mu, l_sigma, c_safety, a, b, t_z_gp, n_s, n_u, n_in, propagation)
     if on_device:
         torch = gp._torch
         dev = gp.device

@@ -381,3 +381,45 @@ def test_error_mapping_and_status_flags(se):
     assert res.p_all.shape == (0, 3, 2)
     gp.close()
     gp2.close()
+
+
+# =========================================================================== Gaussian uncertainty propagation (8 f2)
+def test_golden_uncertainty_propagation(se, golden_dir):
+    """multi_step_taylor_symbolic / mean_equivalent_multistep against outputs of the reference's own functions."""
+    from safe_exploration_b200 import uncertainty_propagation as up
+    g = np.load(os.path.join(golden_dir, "uncertainty_propagation.npz"))
+    kern = [str(k) for k in g["kern_types"]]
+    n_s = g["y_train"].shape[1]
+    n_u = g["x_train"].shape[1] - n_s
+
+    def model(reduced):
+        x = g["x_train"][:, 1:] if reduced else g["x_train"]
+        ls = g["lengthscale"][:, 1:] if reduced else g["lengthscale"]
+        gp, _ = _make_models(se, x, g["y_train"], n_s - 1 if reduced else n_s, n_u, kern, ls, g["variance"], g["noise"])
+        return gp
+
+    for tag, fn, one in (("taylor", up.multi_step_taylor_symbolic, up.one_step_taylor),
+                         ("meaneq", up.mean_equivalent_multistep, up.one_step_mean_equivalent)):
+        for pr, (a, b, red, tm) in (("lin", (g["a"], g["b"], False, None)), ("nolin", (None, None, False, None)),
+                                    ("trafo", (g["a"], g["b"], True, g["t_mat"]))):
+            gp = model(red)
+            mu, sig, var = fn(g["mu0"], gp, g["k_ff"], g["k_fb"], None, a, b, tm)      # batched call
+            _assert_close(mu, g["mu_%s_%s" % (tag, pr)], RTOL_TIGHT, what="mu " + tag + pr)
+            _assert_close(sig, g["sigma_%s_%s" % (tag, pr)], RTOL_TIGHT, atol_scale=1e-10, what="sigma " + tag + pr)
+            assert var.shape == mu.shape
+            # the reference's un-batched call shape, one trajectory
+            hor = g["k_ff"].shape[1]
+            m1, s1, third = fn(g["mu0"][0][:, None], gp, g["k_ff"][0], g["k_fb"][0], None, a, b, tm)
+            assert m1.shape == (hor, n_s) and s1.shape == (hor, n_s * n_s)
+            assert third.shape == ((1 + (hor - 1) * n_s, n_s) if tag == "taylor" else (hor, n_s))
+            _assert_close(m1, g["mu_%s_%s" % (tag, pr)][0], RTOL_TIGHT)
+            _assert_close(s1.reshape(hor, n_s, n_s), g["sigma_%s_%s" % (tag, pr)][0], RTOL_TIGHT, atol_scale=1e-10)
+            # one step with an input covariance equals the second step of the trajectory
+            mu_n, sig_n, _ = one(m1[0][:, None], gp, g["k_ff"][0][1][:, None], s1[0].reshape(n_s, n_s), g["k_fb"][0][0],
+                                 a, b, tm)
+            assert mu_n.shape == (n_s, 1) and sig_n.shape == (n_s, n_s)
+            _assert_close(mu_n[:, 0], m1[1], 1e-12)
+            _assert_close(sig_n, s1[1].reshape(n_s, n_s), 1e-12)
+            gp.close()
+    with pytest.raises(NotImplementedError):
+        up.multi_step_taylor_symbolic(g["mu0"][0][:, None], model(False), g["k_ff"][0], g["k_fb"][0], np.eye(n_s))

@@ -238,3 +238,49 @@ def test_score_oracle_known_answer_and_reference_distance():
     assert g_own.shape == (5, 2 * 2 * 4 + 3 * 5 + 2)
     assert np.allclose(g_own, np.real(g_ref), rtol=1e-14, atol=1e-15)
     assert np.array_equal(f_own, f_ref)
+
+
+# ---------------------------------------------------------------------------------- Gaussian uncertainty propagation
+def _uprop_gp(g, reduced=False):
+    from oracle.gp_oracle import GPOracle
+    kern = [str(k) for k in g["kern_types"]]
+    if reduced:
+        return GPOracle(g["x_train"][:, 1:], g["y_train"], kern, g["lengthscale"][:, 1:], g["variance"], g["noise"])
+    return GPOracle(g["x_train"], g["y_train"], kern, g["lengthscale"], g["variance"], g["noise"])
+
+
+def test_golden_uncertainty_propagation_batch_oracle(golden_dir):
+    """Closed-form batch oracle == outputs of the reference's multi_step_taylor_symbolic / mean_equivalent_multistep."""
+    from oracle import uprop_oracle
+    g = np.load(os.path.join(golden_dir, "uncertainty_propagation.npz"))
+    for tag, taylor in (("taylor", True), ("meaneq", False)):
+        for pr, (a, b, red, tm) in (("lin", (g["a"], g["b"], False, None)), ("nolin", (None, None, False, None)),
+                                    ("trafo", (g["a"], g["b"], True, g["t_mat"]))):
+            mu, sig, _ = uprop_oracle.multistep_batch(g["mu0"], _uprop_gp(g, red), g["k_ff"], g["k_fb"], a, b, tm,
+                                                      taylor)
+            assert np.allclose(mu, g["mu_%s_%s" % (tag, pr)], rtol=1e-10, atol=1e-12)
+            assert np.allclose(sig, g["sigma_%s_%s" % (tag, pr)], rtol=1e-9, atol=1e-13)
+
+
+def test_uncertainty_propagation_oracle_equals_reference_live():
+    from oracle import ref_loader, uprop_oracle
+    from oracle.gp_oracle import GPOracle
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    up = ref_loader.load_uncertainty_propagation()
+    rng = np.random.default_rng(21)
+    n_s, n_u, n, hor = 3, 2, 40, 4
+    x = rng.uniform(-1, 1, (n, n_s + n_u))
+    y = np.sin(x @ rng.standard_normal((n_s + n_u, n_s)))
+    gp = GPOracle(x, y, ["rbf", "mat52", "rbf"], rng.uniform(0.8, 2, (n_s, n_s + n_u)), rng.uniform(.5, 1.5, n_s),
+                  np.full(n_s, 0.01))
+    a = np.eye(n_s) + 0.1 * rng.standard_normal((n_s, n_s))
+    b = 0.3 * rng.standard_normal((n_s, n_u))
+    k_ff = 0.1 * rng.standard_normal((hor, n_u))
+    k_fb = 0.2 * rng.standard_normal((hor - 1, n_u, n_s))
+    mu0 = 0.1 * rng.standard_normal((n_s, 1))
+    for fn, taylor in ((up.multi_step_taylor_symbolic, True), (up.mean_equivalent_multistep, False)):
+        m_ref, s_ref, _ = fn(mu0, gp, k_ff, k_fb, None, a, b)
+        m, s, _ = uprop_oracle.multistep_batch(mu0[:, 0], gp, k_ff[None], k_fb, a, b, None, taylor)
+        assert np.allclose(m[0], m_ref, rtol=1e-12, atol=1e-14)
+        assert np.allclose(s[0].reshape(hor, -1), s_ref, rtol=1e-10, atol=1e-14)
