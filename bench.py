@@ -334,7 +334,7 @@ def run_product(args, rank, world, local_rank):
                     "pipe_frac_of_n96_peak": (pipe_tops / i8_96) if (pipe_tops and i8_96) else None,
                     "pipe_frac_of_2x_bf16_peak": (pipe_tops / (2.0 * bf16_peak)) if pipe_tops else None,
                     "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
-                    "algorithmic_flop_per_launch": flop_launch, "traffic": None}
+                    "algorithmic_flop_per_launch": flop_launch, "traffic": _traffic(args.config, mode)}
     else:
         dmma = _dmma_peak(gp, local_rank)
         roofline = {"bound": "tensor", "kernel": "tri_sumsq_kernel", "pipe": "fp64 DMMA (mma.sync m8n8k4.f64)",
@@ -344,7 +344,7 @@ def run_product(args, rank, world, local_rank):
                                    + peaks["_source"] + " holds only bf16",
                     "bf16_peak": bf16_peak, "frac_of_bf16_peak": (achieved / bf16_peak) if achieved else None,
                     "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
-                    "algorithmic_flop_per_launch": flop_launch, "traffic": None}
+                    "algorithmic_flop_per_launch": flop_launch, "traffic": _traffic(args.config, mode)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -366,6 +366,16 @@ def run_product(args, rank, world, local_rank):
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
+
+
+def _traffic(config, mode):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum), or None for configurations that were not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get("{}:tri_mode{}".format(config, mode))
 
 
 def _i8_peak(gp, device, umma_n):
