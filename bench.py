@@ -414,6 +414,12 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly ONE line (rank 0's JSON): anything a library prints on file descriptor 1 meanwhile
+    # (NCCL's version banner, for one) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
