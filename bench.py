@@ -303,7 +303,7 @@ def run_product(args, rank, world, local_rank):
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     share = (tri_ns * 1e-6) / ms if ms > 0 else None
     mode = gp.get_option("tri_mode_effective")
-    if mode in (1, 2, 3):
+    if mode in (1, 2, 3, 4):
         # tri_i8: 15 int8 digit-plane products per algorithmic multiply-add, exact int32 accumulation in TMEM.
         # `achieved` is ALGORITHMIC flop/s (n_s N^2 B per launch); `peak` is the measured bf16 figure of
         # MEASURED_PEAKS.json, so `frac` is the algorithmic fraction of the bf16 tensor peak: error-free splitting
@@ -314,15 +314,15 @@ def run_product(args, rank, world, local_rank):
         n_pad = gp.get_option("n_train_padded")
         nblk = n_pad // 128
         panels = -(-cols // 96)
-        if mode >= 2:   # block-row pairs: the upper row of a pair also runs over the lower row's diagonal block
+        if mode in (2, 3):   # block-row pairs: the upper row of a pair also runs over the lower row's diagonal block
             kblocks = sum(2 * (min(2 * bp + 1, nblk - 1) + 1) for bp in range((nblk + 1) // 2))
         else:
             kblocks = nblk * (nblk + 1) // 2
         executed = 2.0 * 15 * w.n_s * (128 * 128 * kblocks) * panels * 96
         i8_96, i8_256 = _i8_peak(gp, local_rank, 96), _i8_peak(gp, local_rank, 256)
         pipe_tops = executed / tri_avg_s / 1e12 if tri_avg_s > 0 else None
-        roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 2: "tri_i8x2_kernel", 3: "tri_i8x2p_kernel"}[mode],
-                    "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, " + ("cta_group::2 M=256" if mode >= 2 else "M=128")
+        roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 2: "tri_i8x2_kernel", 3: "tri_i8x2p_kernel", 4: "tri_i8m_kernel"}[mode],
+                    "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, " + ("cta_group::2 M=256" if mode in (2, 3) else "M=128")
                             + " N=96 K=32, int32 accumulators in TMEM); "
                             "float64-grade result from 5 x 5 balanced base-254 digit planes, 15 products",
                     "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
@@ -350,7 +350,9 @@ def run_product(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "tri_mode": {0: "fp64 DMMA", 1: "int8 digit planes on tcgen05 (single CTA), float64 recombination",
                          2: "int8 digit planes on tcgen05 (CTA pairs), float64 recombination",
-                         3: "int8 digit planes on tcgen05 (persistent CTA pairs), float64 recombination"}[mode],
+                         3: "int8 digit planes on tcgen05 (persistent CTA pairs), float64 recombination",
+                         4: "int8 digit planes on tcgen05 (single-CTA MMAs, W multicast over CTA pairs), float64 "
+                            "recombination"}[mode],
             "config": _config_dict(args, w, b_per_gpu, world, "device-resident"),
             "onestep_calls_per_sec": value * w.horizon,
             "algorithmic_tflops": value * w.horizon * workloads.flop_per_step(w.n_s, w.n_u, w.n_train) / 1e12,
@@ -404,7 +406,7 @@ def main():
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
+    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4],
                     help="variance contraction pipe: -1 auto (2 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
                          "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs")
     ap.add_argument("--redundant-factor", action="store_true",

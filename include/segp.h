@@ -230,6 +230,10 @@ int segp_dmma_peak(int device, int iters, double* tflops);
  * back by one thread per SM from fixed shared-memory tiles) in TOP/s: the denominator bench.py reports the int8
  * contraction kernel (tri_i8) against, next to twice the measured bf16 figure of MEASURED_PEAKS.json. */
 int segp_i8_peak(int device, int umma_n, int iters, double* tops);
+/* Same with a choice of issue pattern: 0 = two accumulators alternating (segp_i8_peak), 1 = one accumulator back to
+ * back, 2 = the 15 digit-plane products of tri_i8 in plane-major order (accumulator changes every instruction),
+ * 3 = the same products in diagonal-major order (umma_n must be 96 for 2 and 3). */
+int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double* tops);
 
 /* Diagnostic: run ONE tile of a tcgen05 contraction kernel on caller-supplied digit planes and return the raw
  * TMEM accumulators, so descriptor / swizzle / TMEM-layout errors show up as exact integer mismatches.

@@ -86,6 +86,7 @@ PROTOTYPES = {
                             ctypes.POINTER(_dbl), ctypes.POINTER(_int), _vp]),
     "segp_dmma_peak": (_int, [_int, _int, ctypes.POINTER(_dbl)]),
     "segp_i8_peak": (_int, [_int, _int, _int, ctypes.POINTER(_dbl)]),
+    "segp_i8_peak_pattern": (_int, [_int, _int, _int, _int, ctypes.POINTER(_dbl)]),
     "segp_i8_selftest": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
     "segp_set_option": (_int, [_vp, ctypes.c_char_p, _long]),
     "segp_get_option": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_long)]),

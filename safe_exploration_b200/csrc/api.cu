@@ -255,7 +255,7 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st) {
         k8.k = k;
         k8.ki8 = m->ki8;
         k8.npanel_cap = m->npanel_cap;
-        k8.split_halves = m->ws_mode >= 2;
+        k8.split_halves = m->ws_mode == 2 || m->ws_mode == 3;
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
     }
     return launch_kstar(k, m->n_s, m->nsplit, st);
@@ -291,7 +291,8 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st) {
         t.zero_a = m->i8zero;
         t.ablate = (int)m->opt_i8_ablate;
         t.prof = m->i8_prof;
-        SEGP_CHECK(m->ws_mode == 3   ? launch_tri_i8x2p(t, m->n_s, st)
+        SEGP_CHECK(m->ws_mode == 4   ? launch_tri_i8m(t, m->n_s, st)
+                   : m->ws_mode == 3 ? launch_tri_i8x2p(t, m->n_s, st)
                    : m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st)
                                      : launch_tri_i8(t, m->n_s, st));
     } else {
@@ -1087,7 +1088,16 @@ int segp_i8_peak(int device, int umma_n, int iters, double* tops) {
         set_error("segp_i8_peak: cudaSetDevice(%d) failed", device);
         return SEGP_ERR_CUDA;
     }
-    return i8_peak(umma_n, iters, tops);
+    return i8_peak(umma_n, iters, 0, tops);
+}
+
+int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double* tops) {
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("segp_i8_peak_pattern: cudaSetDevice(%d) failed", device);
+        return SEGP_ERR_CUDA;
+    }
+    return i8_peak(umma_n, iters, pattern, tops);
 }
 
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
@@ -1215,7 +1225,7 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_ksplit = value;
         return SEGP_OK;
     }
-    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 3) {
+    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 4) {
         if (value >= 1 && m->has_data && !i8_capable(m)) {
             set_error("tri_mode=%ld (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", value, I8_MAX_NPAD,
                       m->n_pad);

@@ -121,12 +121,14 @@ struct TriI8Args {
 int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);
 // CTA-pair variant: cta_group::2 MMAs, M = 256 (two block rows), each CTA stages its own A rows and half of B
 int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st);
+// single-CTA MMAs, two CTAs per cluster share one block row of W through multicast bulk copies
+int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st);
 // persistent CTA-pair variant: one resident pair per TPC walks a static tile list
 int launch_tri_i8x2p(const TriI8Args& a, int n_s, cudaStream_t st);
 int tri_i8_init();
 // W (n_pad x n_pad fp64, lower) -> digit planes + row factors for output dimension d
 int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int n_pad, cudaStream_t st);
-int i8_peak(int umma_n, int iters, double* tops);
+int i8_peak(int umma_n, int iters, int pattern, double* tops);
 
 // ---------------------------------------------------------------- posterior finalise / ellipsoid step
 struct StepArgs {

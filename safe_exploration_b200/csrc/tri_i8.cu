@@ -833,6 +833,163 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i
     }
 }
 
+// =========================================================================================== tri_i8m (multicast)
+// The single-CTA tile of tri_i8 (M = 128, N = 96: 58.6 clocks per MMA, bound by the 4 KB + 3 KB shared-memory operand
+// read at ~122 B/clk, see segp_i8_peak_pattern) with the L2 -> SM fill cut from 70 to 50 KB per k-block: two CTAs of a
+// cluster work on the SAME block row of W and adjacent trajectory panels, each fetches half of the 40 KB W stage and
+// multicasts it into both shared memories, and its own 30 KB K* stage.  (The cta_group::2 pair kernel needs only
+// 55 KB per k-block as well, but its MMAs take ~71 clocks: every MMA pulls the peer's half of K* across the SM pair.)
+// Barriers: full (own expect_tx of the whole 70 KB; bytes arrive from both producers), empty with 2 arrivals (both
+// MMA threads commit with the cluster multicast mask: a stage is rewritten only when both CTAs have consumed it).
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                   uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i8m_kernel(const TriI8Args a) {
+    const uint32_t rank = cluster_ctarank();
+    constexpr int PG2 = I8_PANEL_GROUP / 2;   // panel pairs per L2 group
+    int d, bi, panel;
+    {
+        const int cid = blockIdx.x >> 1;
+        const int tiles_per_group = PG2 * a.nblk;
+        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        const int gid = cid / tiles_per_group;
+        const int r = cid % tiles_per_group;
+        d = gid / npg;
+        const int pg = gid % npg;
+        bi = a.nblk - 1 - r / PG2;
+        panel = pg * I8_PANEL_GROUP + 2 * (r % PG2) + (int)rank;
+        if (panel - (int)rank >= a.npanels) return;   // the whole cluster is past the last panel
+    }
+    const bool valid = panel < a.npanels;             // odd panel count: the last cluster's second CTA only helps loading
+    const int panel_ld = valid ? panel : panel - 1;
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_addr(smem_raw);
+    const uint32_t stage0 = (raw + 1023u) & ~1023u;
+    unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)I8_STAGES * I8_STAGE_BYTES;
+    double* s_col = reinterpret_cast<double*>(tail);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 4 * I8_N);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 1);
+    const uint32_t bar0 = smem_addr(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (I8_STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (2 * I8_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 2);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
+                     "n"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nk = 2 * (bi + 1);
+    const int nkb_total = a.nblk * 2;
+    constexpr uint32_t A_HALF = I8_S * I8_A_TILE / 2;   // 20480 B
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int8_t* wsrc = a.wi8 + ((long)d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (I8_S * I8_A_TILE) +
+                                 (long)rank * A_HALF;
+            const int8_t* ksrc = a.ki8 + (((long)d * a.npanel_cap + panel_ld) * nkb_total) * (long)(I8_S * I8_B_TILE);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % I8_STAGES;
+                if (it >= I8_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((it / I8_STAGES - 1) & 1));
+                const uint32_t dst = stage0 + (uint32_t)s * I8_STAGE_BYTES;
+                mbar_expect_tx(full_bar(s), I8_STAGE_BYTES);
+                bulk_g2s_multicast(dst + rank * A_HALF, wsrc + (long)it * (I8_S * I8_A_TILE), A_HALF, full_bar(s),
+                                   (uint16_t)3);
+                bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * I8_B_TILE, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_i8_idesc(TILE, I8_N);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % I8_STAGES;
+                mbar_wait_cluster(full_bar(s), (uint32_t)((it / I8_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t sa = stage0 + (uint32_t)s * I8_STAGE_BYTES;
+                const uint32_t sb = sa + I8_S * I8_A_TILE;
+#pragma unroll
+                for (int ks = 0; ks < I8_KB / 32; ++ks) {
+#pragma unroll
+                    for (int pa = 0; pa < I8_S; ++pa) {
+                        const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
+#pragma unroll
+                        for (int pc = 0; pc < I8_S - pa; ++pc) {
+                            const uint64_t bdesc = make_sw64_desc(sb + pc * I8_B_TILE + ks * 32);
+                            tc_mma_i8(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, idesc,
+                                      (uint32_t)((it | ks | pa) != 0));
+                        }
+                    }
+                }
+                tc_commit_multicast(empty_bar(s), (uint16_t)3);   // one of the two arrivals on BOTH CTAs' empty barriers
+            }
+            tc_commit(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const double rf = a.rowfac[((long)d * a.nblk + bi) * TILE + row];
+        mbar_wait(tmem_full_bar, 0u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = 0; chunk < I8_N / 32; ++chunk)
+            s_col[q * I8_N + chunk * 32 + lane] =
+                i8_epilogue_chunk(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane, nullptr, 0);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int c = threadIdx.x - 64;
+        if (c < I8_N && valid) {
+            const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
+            const long bcol = (long)panel * I8_N + c;
+            if (bcol < a.b_cap) a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();   // the peer may multicast into this shared memory / signal these barriers until it is done too
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
+    const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+    const long nclusters = (long)n_s * npg * (I8_PANEL_GROUP / 2) * a.nblk;
+    if (nclusters <= 0 || 2 * nclusters > 2147483647L) {
+        set_error("tri_i8m: grid of %ld cluster tiles out of range", nclusters);
+        return SEGP_ERR_INVALID;
+    }
+    tri_i8m_kernel<<<(unsigned)(2 * nclusters), I8_THREADS, I8_SMEM, st>>>(a);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
 // =========================================================================================== tri_i8x2p (persistent)
 // Same tiles, same arithmetic, same barriers as tri_i8x2, but ONE resident CTA pair per TPC walks a static list of
 // tiles (heavy-first order, boustrophedon over the clusters so every cluster gets the same mix of long and short
@@ -1112,20 +1269,21 @@ int tri_i8_init() {
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
     return SEGP_OK;
 }
 
 // =========================================================================================== i8_peak
 // One CTA per SM issues `iters` back-to-back tcgen05.mma kind::i8 (M = 128, N = umma_n, K = 32) on fixed shared
 // memory tiles; no loads, no epilogue: the sustained int8 tensor-pipe rate a kernel of this shape can reach.
-__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int umma_n, int iters) {
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int umma_n, int iters, int pattern) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const uint32_t raw = smem_addr(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* tiles = smem_raw + (base - raw);
-    for (int i = threadIdx.x; i < (TILE + 256) * I8_KB / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tiles)[i] = 0x01010101u;
+    for (int i = threadIdx.x; i < I8_STAGE_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tiles)[i] = 0x01010101u;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(smem_addr(&bar), 1);
@@ -1147,10 +1305,43 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int umma_n, int iters) 
         const uint32_t idesc = make_i8_idesc(TILE, umma_n);
         const uint64_t adesc0 = make_sw64_desc(base);
         const uint64_t bdesc0 = make_sw64_desc(base + I8_A_TILE);
-        for (int it = 0; it < iters; ++it) {
-            const uint32_t koff = (uint32_t)(it & 1) * 2u;                  // alternate the two k-steps of the tile
-            const uint32_t col = (umma_n <= 256 && (it & 2)) ? 256u : 0u;   // and two accumulators
-            tc_mma_i8(tmem_base + col, adesc0 + koff, bdesc0 + koff, idesc, (uint32_t)(it > 3));
+        if (pattern == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t koff = (uint32_t)(it & 1) * 2u;                  // alternate the two k-steps of the tile
+                const uint32_t col = (umma_n <= 256 && (it & 2)) ? 256u : 0u;   // and two accumulators
+                tc_mma_i8(tmem_base + col, adesc0 + koff, bdesc0 + koff, idesc, (uint32_t)(it > 3));
+            }
+        } else if (pattern == 1) {   // one accumulator, back to back
+            for (int it = 0; it < iters; ++it)
+                tc_mma_i8(tmem_base, adesc0 + (uint32_t)(it & 1) * 2u, bdesc0 + (uint32_t)(it & 1) * 2u, idesc,
+                          (uint32_t)(it > 0));
+        } else {
+            // the 15 digit-plane products of tri_i8 on its real stage layout (N must be I8_N):
+            // pattern 2 = plane-major order (pa outer, pc inner: the accumulator changes every instruction),
+            // pattern 3 = diagonal-major order (all products of one accumulator back to back)
+            for (int it = 0; it < iters; it += 30) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    if (pattern == 2) {
+#pragma unroll
+                        for (int pa = 0; pa < I8_S; ++pa)
+#pragma unroll
+                            for (int pc = 0; pc < I8_S - pa; ++pc)
+                                tc_mma_i8(tmem_base + (uint32_t)((pa + pc) * I8_N),
+                                          make_sw64_desc(base + pa * I8_A_TILE + ks * 32),
+                                          make_sw64_desc(base + I8_S * I8_A_TILE + pc * I8_B_TILE + ks * 32), idesc,
+                                          (uint32_t)((it | ks | pa) != 0));
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < I8_S; ++g)
+#pragma unroll
+                            for (int pa = 0; pa <= g; ++pa)
+                                tc_mma_i8(tmem_base + (uint32_t)(g * I8_N), make_sw64_desc(base + pa * I8_A_TILE + ks * 32),
+                                          make_sw64_desc(base + I8_S * I8_A_TILE + (g - pa) * I8_B_TILE + ks * 32), idesc,
+                                          (uint32_t)((it | ks | pa) != 0));
+                    }
+                }
+            }
         }
         tc_commit(smem_addr(&bar));
         mbar_wait(smem_addr(&bar), 0u);
@@ -1163,22 +1354,24 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int umma_n, int iters) 
     }
 }
 
-int i8_peak(int umma_n, int iters, double* tops) {
-    if (umma_n < 16 || umma_n > 256 || umma_n % 16 != 0 || iters < 1 || tops == nullptr) {
-        set_error("i8_peak: umma_n must be a multiple of 16 in [16, 256]");
+int i8_peak(int umma_n, int iters, int pattern, double* tops) {
+    if (umma_n < 16 || umma_n > 256 || umma_n % 16 != 0 || iters < 1 || tops == nullptr || pattern < 0 || pattern > 3 ||
+        (pattern >= 2 && umma_n != I8_N)) {
+        set_error("i8_peak: umma_n must be a multiple of 16 in [16, 256] (96 for patterns 2, 3), pattern in [0, 3]");
         return SEGP_ERR_INVALID;
     }
+    if (pattern >= 2) iters = (iters + 29) / 30 * 30;
     int dev = 0, sms = 0;
     SEGP_CUDA_CHECK(cudaGetDevice(&dev));
     SEGP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = (size_t)(TILE + 256) * I8_KB + 1024;
+    const size_t smem = (size_t)I8_STAGE_BYTES + 1024;
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     SEGP_CUDA_CHECK(cudaEventCreate(&e0));
     SEGP_CUDA_CHECK(cudaEventCreate(&e1));
-    i8_peak_kernel<<<sms, 128, smem>>>(umma_n, iters);   // warm-up
+    i8_peak_kernel<<<sms, 128, smem>>>(umma_n, iters, pattern);   // warm-up
     SEGP_CUDA_CHECK(cudaEventRecord(e0));
-    i8_peak_kernel<<<sms, 128, smem>>>(umma_n, iters);
+    i8_peak_kernel<<<sms, 128, smem>>>(umma_n, iters, pattern);
     SEGP_CUDA_CHECK(cudaEventRecord(e1));
     SEGP_CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;
