@@ -88,8 +88,9 @@ struct segp_model {
     long opt_chunk = 8192;
     long opt_panel_group = 16;
     long opt_ksplit = 0;   // 0 = automatic
-    long opt_tri_mode = -1;   // -1 = automatic (2 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
-                              // 1 = int8 tcgen05 single CTA, 2 = int8 tcgen05 CTA pair (cta_group::2)
+    long opt_tri_mode = -1;   // -1 = automatic (4 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
+                              // 1 = int8 tcgen05 single CTA, 2 = CTA pair (cta_group::2), 3 = persistent CTA pair,
+                              // 4 = single-CTA MMAs over two K* planes at once, W multicast over a CTA pair
     long opt_i8_ablate = 0;   // profiling only, see TriI8Args::ablate
     long long* i8_prof = nullptr;   // profiling only: [128][8] counters of the persistent kernel's MMA threads
     long launches = 0;
@@ -129,7 +130,7 @@ static void free_workspace(segp_model* m) {
 static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD; }
 static int tri_mode(const segp_model* m) {
     if (m->opt_tri_mode >= 0) return (int)m->opt_tri_mode;
-    return i8_capable(m) ? 2 : 0;
+    return i8_capable(m) ? 4 : 0;
 }
 
 static int ensure_workspace(segp_model* m, long n_batch) {

@@ -27,7 +27,7 @@ def se():
     return pkg
 
 
-@pytest.fixture(autouse=True, params=[0, 2], ids=["fp64-dmma", "int8-tcgen05"])
+@pytest.fixture(autouse=True, params=[0, 4], ids=["fp64-dmma", "int8-tcgen05"])
 def _tri_mode(request, se):
     """Every parity test runs on both tensor pipes of the variance contraction (include/segp.h, "tri_mode")."""
     old = se.ssm.DEFAULT_TRI_MODE

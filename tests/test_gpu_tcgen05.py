@@ -113,7 +113,7 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
     assert np.array_equal(out[3].q_all, out[2].q_all) and np.array_equal(out[3].var_all, out[2].var_all)
     assert np.array_equal(out[4].q_all, out[2].q_all) and np.array_equal(out[4].var_all, out[2].var_all)
     for name in ("var_all", "p_all", "q_all"):
-        a0, a1 = getattr(out[0], name), getattr(out[2], name)
+        a0, a1 = getattr(out[0], name), getattr(out[4], name)
         err = float(np.max(np.abs(a1 - a0) / (np.abs(a0) + 1e-12 * np.abs(a0).max())))
         print("C4 model, %s: int8 vs fp64 pipe max rel diff %.2e" % (name, err))
         assert err < 2e-5
