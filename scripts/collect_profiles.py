@@ -44,20 +44,22 @@ if __name__ == "__main__":
             shutil.copy(src, os.path.join(DST, name + ".json"))
     shutil.copy(os.path.join(SRC, "launches_c4.csv"), os.path.join(DST, "launches_c4_ncu.csv"))
     launches(os.path.join(SRC, "launches_c4.csv"), os.path.join(DST, "launches_c4_summary.txt"),
-             "ncu launch list, bench.py --steps 1 --warmup 1 --e2e-steps 1 (C4, B=8192/GPU, default tri_mode 2), "
+             "ncu launch list, bench.py --steps 1 --warmup 1 --e2e-steps 1 (C4, B=8192/GPU, default tri_mode 4), "
              "rollout kernels only")
     cmd = "ncu --set full --clock-control none --import-source on -k regex:%s -s 2 -c 1 (bench.py C4, B=8192, N=5000, n_s=4)"
-    for rep, pat, out in (("prof_tri_i8x2_c4.ncu-rep", "tri_i8x2", "tri_i8x2_c4_ncu_full.txt"),
+    for rep, pat, out in (("prof_tri_i8m_c4.ncu-rep", "tri_i8m", "tri_i8m_c4_ncu_full.txt"),
+                          ("prof_tri_i8x2_c4.ncu-rep", "tri_i8x2", "tri_i8x2_c4_ncu_full.txt"),
                           ("prof_kstar_i8_c4.ncu-rep", "kstar_i8", "kstar_i8_c4_ncu_full.txt"),
                           ("prof_ellipsoid_c4.ncu-rep", "ellipsoid_step", "ellipsoid_step_c4_ncu_full.txt")):
-        ncu_summary(os.path.join(SRC, rep), cmd % pat, os.path.join(DST, out))
-    tri = open(os.path.join(DST, "tri_i8x2_c4_ncu_full.txt")).read()
+        if os.path.exists(os.path.join(SRC, rep)):
+            ncu_summary(os.path.join(SRC, rep), cmd % pat, os.path.join(DST, out))
+    tri = open(os.path.join(DST, "tri_i8m_c4_ncu_full.txt")).read()
     rd = [l for l in tri.splitlines() if l.startswith("dram__bytes_read.sum,")][0].split(",")
     wr = [l for l in tri.splitlines() if l.startswith("dram__bytes_write.sum,")][0].split(",")
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     total = float(rd[2]) * scale[rd[1].strip()] + float(wr[2]) * scale[wr[1].strip()]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     t = json.load(open(tpath))
-    t["C4:tri_mode2"] = int(total)
+    t["C4:tri_mode4"] = int(total)
     json.dump(t, open(tpath, "w"), indent=1)
-    print("traffic C4 tri_mode2:", int(total))
+    print("traffic C4 tri_mode4:", int(total))
