@@ -208,6 +208,7 @@ def run_product(args, rank, world, local_rank):
                                    src=0, device=local_rank, redundant=args.redundant_factor)
     torch.cuda.synchronize(dev)
     t_setup = time.perf_counter() - t_setup0
+    gp.set_option("overlap", 1 if args.overlap else 0)
 
     # ---------------- device-resident inputs (the `value` arm)
     p0_d = torch.as_tensor(w.p0, device=dev)
@@ -263,8 +264,10 @@ def run_product(args, rank, world, local_rank):
     h2d = kff_host.nbytes + w.p0.nbytes + w.k_fb.nbytes
     d2h = 8 * bsz * hor * (w.n_s + w.n_s * w.n_s + w.n_s) + 4 * bsz
 
+    out_pin = se.pinned_result(gp, bsz, hor)   # page-locked result buffers, allocated once, as the input is
+
     def step_host():
-        return se.rollout(gp, w.p0, kff_host, w.k_fb, *rargs)
+        return se.rollout(gp, w.p0, kff_host, w.k_fb, *rargs, out=out_pin)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     step_host()
@@ -297,7 +300,9 @@ def run_product(args, rank, world, local_rank):
     total_b = b_per_gpu * world
     value = total_b * args.steps / (ms_max * 1e-3)
     # roofline of the dominant kernel (tri_sumsq): algorithmic flop per launch = n_s * N^2 * columns of the launch
-    flop_launch = float(w.n_s) * w.n_train ** 2 * min(b_per_gpu, gp.get_option("chunk"))
+    # (with the pipelined driver a chunk is contracted as two half-chunk launches: the per-launch figures are the
+    # timed region's totals divided by the number of launches actually timed)
+    flop_launch = float(w.n_s) * w.n_train ** 2 * b_per_gpu * w.horizon * args.steps / max(tri_count, 1)
     tri_avg_s = (tri_ns / max(tri_count, 1)) * 1e-9
     achieved = flop_launch / tri_avg_s / 1e12 if tri_avg_s > 0 else None
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
@@ -310,10 +315,12 @@ def run_product(args, rank, world, local_rank):
         # caps it at 2/15 (int8 runs at twice the bf16 rate, 15 products).  `pipe_*` say how busy the int8 pipe
         # actually was: executed int8 op/s (padding and all 15 products counted) against the int8 rate measured
         # in this run by segp_i8_peak (same instruction shape, no loads).
-        cols = min(b_per_gpu, gp.get_option("chunk"))
+        chunk = gp.get_option("chunk")
         n_pad = gp.get_option("n_train_padded")
         nblk = n_pad // 128
-        panels = -(-cols // 96)
+        # 96-trajectory panels contracted per launch, averaged the same way (padding of the last panel counted)
+        panels = sum(-(-min(chunk, b_per_gpu - c0) // 96) for c0 in range(0, b_per_gpu, chunk)) \
+            * w.horizon * args.steps / max(tri_count, 1)
         if mode in (2, 3):   # block-row pairs: the upper row of a pair also runs over the lower row's diagonal block
             kblocks = sum(2 * (min(2 * bp + 1, nblk - 1) + 1) for bp in range((nblk + 1) // 2))
         else:
@@ -358,9 +365,11 @@ def run_product(args, rank, world, local_rank):
             "algorithmic_tflops": value * w.horizon * workloads.flop_per_step(w.n_s, w.n_u, w.n_train) / 1e12,
             "e2e": {"value": total_b * e2e_steps / t_e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "api": "safe_exploration_b200.rollout -> segp_multistep_host (pinned host k_ff)",
+                    "api": "safe_exploration_b200.rollout(out=pinned_result(...)) -> segp_multistep_host (pinned host k_ff and result buffers)",
                     "bit_identical_to_device_arm": same},
             "gpu_launches": int(launches), "roofline": roofline,
+            "schedule": ("two half-chunks software-pipelined over two streams (K*/ellipsoid kernels of one half under "
+                         "the contraction of the other)" if gp.get_option("overlap") and mode == 4 else "serial"),
             "clocks": sampler.summary(t_wall0, t_wall1),
             "setup_s": t_setup, "bad_status": status_bad, "all_finite": finite}
     if world == 1 and not args.no_cpu_baseline:
@@ -406,6 +415,9 @@ def main():
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="two-stream half-chunk pipeline instead of the serial kstar -> tri -> ellipsoid schedule "
+                         "(bit-identical; measured no faster, see DESIGN.md)")
     ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4],
                     help="variance contraction pipe: -1 auto (2 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
                          "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs")

@@ -91,6 +91,12 @@ struct segp_model {
     long opt_tri_mode = -1;   // -1 = automatic (4 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
                               // 1 = int8 tcgen05 single CTA, 2 = CTA pair (cta_group::2), 3 = persistent CTA pair,
                               // 4 = single-CTA MMAs over two K* planes at once, W multicast over a CTA pair
+    long opt_overlap = 0;     // 1 = software-pipeline two half-chunks over two internal streams (tri_mode 4 only): the
+                              // FP64-bound K* kernel of one half is issued under the tensor-bound contraction of the
+                              // other.  Bit-identical, measured no faster at C3/C4/C5 (the 15k-CTA contraction grid is
+                              // dispatched ahead of the K* blocks and the GPU is power-capped): off by default
+    cudaStream_t s_hi = nullptr, s_lo = nullptr;   // internal streams of the pipelined driver (created on first use)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ks[2] = {nullptr, nullptr}, ev_tri[2] = {nullptr, nullptr};
     long opt_i8_ablate = 0;   // profiling only, see TriI8Args::ablate
     long long* i8_prof = nullptr;   // profiling only: [128][8] counters of the persistent kernel's MMA threads
     long launches = 0;
@@ -250,13 +256,14 @@ static KstarArgs base_kstar_args(const segp_model* m) {
 }
 
 // K* block (+ mean / Jacobian partials) in the operand format of the active contraction kernel
-static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st) {
+static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int panel0 = 0) {
     if (m->ws_mode != 0) {
         KstarI8Args k8{};
         k8.k = k;
         k8.ki8 = m->ki8;
         k8.npanel_cap = m->npanel_cap;
         k8.split_halves = m->ws_mode == 2 || m->ws_mode == 3;
+        k8.panel0 = panel0;
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
     }
     return launch_kstar(k, m->n_s, m->nsplit, st);
@@ -264,7 +271,7 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st) {
 
 // variance contraction launch (tri_i8 on tcgen05 or tri_sumsq on the DMMA pipe), optionally bracketed by a
 // CUDA-event pair on the launching stream
-static int run_tri(segp_model* m, long nb, cudaStream_t st) {
+static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->time_tri) {
         while (m->tri_events.size() < m->tri_events_used + 2) {
@@ -285,6 +292,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st) {
         t.qpart = m->qpart;
         t.nblk = m->nblk;
         t.npanels = (int)((nb + I8_N - 1) / I8_N);
+        t.panel0 = panel0;   // != 0 only from the pipelined driver (ws_mode 4)
         t.npanel_cap = m->npanel_cap;
         t.b_cap = m->b_cap;
         t.dbg = nullptr;
@@ -384,6 +392,10 @@ int segp_destroy(segp_model* m) {
     dev_free(m->d_sp);
     dev_free(m->i8_prof);
     for (cudaEvent_t e : m->tri_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_ks[0], m->ev_ks[1], m->ev_tri[0], m->ev_tri[1]})
+        if (e != nullptr) cudaEventDestroy(e);
+    if (m->s_hi != nullptr) cudaStreamDestroy(m->s_hi);
+    if (m->s_lo != nullptr) cudaStreamDestroy(m->s_lo);
     if (m->stage != nullptr) cudaFree(m->stage);
     delete m;
     return SEGP_OK;
@@ -671,62 +683,117 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
 
     const int n_s = m->n_s, n_u = m->n_u;
     const long hs = (long)horizon * n_s, hss = (long)horizon * n_s * n_s;
+    // argument blocks of step t for the trajectories [b0, b1) of the chunk starting at c0 (indices inside the
+    // kernels are relative to the chunk; b1 / the panel range end bound the launch)
+    auto kstar_args = [&](long c0, int t, long b1) {
+        KstarArgs k = base_kstar_args(m);
+        k.z = nullptr;
+        k.p = (t == 0) ? d_p0 + c0 * p0_stride : d_p_all + c0 * hs + (long)(t - 1) * n_s;
+        k.p_stride = (t == 0) ? p0_stride : hs;
+        k.kff = d_k_ff + (c0 * horizon + t) * n_u;
+        k.kff_stride = (long)horizon * n_u;
+        k.sp = m->d_sp;
+        k.n_batch = b1;
+        return k;
+    };
+    auto step_args = [&](long c0, int t, long b0, long b1) {
+        StepArgs s{};
+        s.mu_part = m->mu_part;
+        s.jac_part = m->jac_part;
+        s.qpart = m->qpart;
+        s.gp_var = m->var;
+        s.invls = m->invls;
+        s.nsplit = m->nsplit;
+        s.nblk = m->nblk;
+        s.b_cap = m->b_cap;
+        s.p = (t == 0) ? d_p0 + c0 * p0_stride : d_p_all + c0 * hs + (long)(t - 1) * n_s;
+        s.p_stride = (t == 0) ? p0_stride : hs;
+        if (t == 0) {
+            s.q = d_q0 ? d_q0 + c0 * q0_stride : nullptr;
+            s.q_stride = q0_stride;
+            s.kfb = d_k_fb_init ? d_k_fb_init + c0 * kfb_init_stride : nullptr;
+            s.kfb_stride = kfb_init_stride;
+        } else {
+            s.q = d_q_all + c0 * hss + (long)(t - 1) * n_s * n_s;
+            s.q_stride = hss;
+            s.kfb = d_k_fb + c0 * kfb_stride + (long)(t - 1) * n_u * n_s;
+            s.kfb_stride = kfb_stride;
+        }
+        s.kff = d_k_ff + (c0 * horizon + t) * n_u;
+        s.kff_stride = (long)horizon * n_u;
+        s.sp = m->d_sp;
+        s.p_out = d_p_all + c0 * hs + (long)t * n_s;
+        s.p_out_stride = hs;
+        s.q_out = d_q_all + c0 * hss + (long)t * n_s * n_s;
+        s.q_out_stride = hss;
+        s.var_out = d_var_all ? d_var_all + c0 * hs + (long)t * n_s : nullptr;
+        s.var_out_stride = hs;
+        s.status = d_status ? d_status + c0 : nullptr;
+        s.b0 = b0;
+        s.n_batch = b1;
+        s.n_s = n_s;
+        s.n_in = m->n_in;
+        s.n_u = n_u;
+        return s;
+    };
+
+    bool forked = false;
     for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
         const long nb = std::min<long>(m->b_cap, n_batch - c0);
-        for (int t = 0; t < horizon; ++t) {
-            const double* p_in = (t == 0) ? d_p0 + c0 * p0_stride : d_p_all + c0 * hs + (long)(t - 1) * n_s;
-            const long p_in_stride = (t == 0) ? p0_stride : hs;
-            const double* kff = d_k_ff + (c0 * horizon + t) * n_u;
-            KstarArgs k = base_kstar_args(m);
-            k.z = nullptr;
-            k.p = p_in;
-            k.p_stride = p_in_stride;
-            k.kff = kff;
-            k.kff_stride = (long)horizon * n_u;
-            k.sp = m->d_sp;
-            k.n_batch = nb;
-            SEGP_CHECK(run_kstar(m, k, st));
-            SEGP_CHECK(run_tri(m, nb, st));
-
-            StepArgs s{};
-            s.mu_part = m->mu_part;
-            s.jac_part = m->jac_part;
-            s.qpart = m->qpart;
-            s.gp_var = m->var;
-            s.invls = m->invls;
-            s.nsplit = m->nsplit;
-            s.nblk = m->nblk;
-            s.b_cap = m->b_cap;
-            s.p = p_in;
-            s.p_stride = p_in_stride;
-            if (t == 0) {
-                s.q = d_q0 ? d_q0 + c0 * q0_stride : nullptr;
-                s.q_stride = q0_stride;
-                s.kfb = d_k_fb_init ? d_k_fb_init + c0 * kfb_init_stride : nullptr;
-                s.kfb_stride = kfb_init_stride;
-            } else {
-                s.q = d_q_all + c0 * hss + (long)(t - 1) * n_s * n_s;
-                s.q_stride = hss;
-                s.kfb = d_k_fb + c0 * kfb_stride + (long)(t - 1) * n_u * n_s;
-                s.kfb_stride = kfb_stride;
+        const int npanels = (int)((nb + I8_N - 1) / I8_N);
+        // Two half-chunks, software-pipelined over two internal streams: all contractions on the high-priority
+        // stream, back to back (tensor pipe), the K* / ellipsoid kernels of the OTHER half under them on the
+        // low-priority stream (FP64 pipe).  Within a half the order kstar -> tri -> ellipsoid -> kstar(t+1) is kept by
+        // events; the halves touch disjoint panel ranges of the workspace.  Same kernels, same arithmetic, same
+        // fixed-order reductions: results are bit-identical to the serial schedule.
+        const bool pipelined = m->ws_mode == 4 && m->opt_overlap != 0 && npanels >= 48 && m->n_pad >= 1024;
+        if (!pipelined) {
+            cudaStream_t s1 = forked ? m->s_lo : st;
+            for (int t = 0; t < horizon; ++t) {
+                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, nb), s1));
+                SEGP_CHECK(run_tri(m, nb, s1));
+                SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t, 0, nb), s1));
+                m->launches += 3;
             }
-            s.kff = kff;
-            s.kff_stride = (long)horizon * n_u;
-            s.sp = m->d_sp;
-            s.p_out = d_p_all + c0 * hs + (long)t * n_s;
-            s.p_out_stride = hs;
-            s.q_out = d_q_all + c0 * hss + (long)t * n_s * n_s;
-            s.q_out_stride = hss;
-            s.var_out = d_var_all ? d_var_all + c0 * hs + (long)t * n_s : nullptr;
-            s.var_out_stride = hs;
-            s.status = d_status ? d_status + c0 : nullptr;
-            s.n_batch = nb;
-            s.n_s = n_s;
-            s.n_in = m->n_in;
-            s.n_u = n_u;
-            SEGP_CHECK(launch_ellipsoid_step(s, st));
-            m->launches += 3;
+            continue;
         }
+        if (m->s_hi == nullptr) {
+            int least = 0, greatest = 0;
+            SEGP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            SEGP_CUDA_CHECK(cudaStreamCreateWithPriority(&m->s_hi, cudaStreamNonBlocking, greatest));
+            SEGP_CUDA_CHECK(cudaStreamCreateWithPriority(&m->s_lo, cudaStreamNonBlocking, least));
+            for (cudaEvent_t* e : {&m->ev_fork, &m->ev_join, &m->ev_ks[0], &m->ev_ks[1], &m->ev_tri[0], &m->ev_tri[1]})
+                SEGP_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+        if (!forked) {
+            SEGP_CUDA_CHECK(cudaEventRecord(m->ev_fork, st));
+            SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_hi, m->ev_fork, 0));
+            SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_lo, m->ev_fork, 0));
+            forked = true;
+        }
+        const int pa = ((npanels / 2 + 1) / 2) * 2;   // even, so the cluster pairs of the first half are complete
+        const int p_begin[2] = {0, pa}, p_end[2] = {pa, npanels};
+        const long b_begin[2] = {0, (long)pa * I8_N}, b_end[2] = {std::min<long>((long)pa * I8_N, nb), nb};
+        for (int t = 0; t <= horizon; ++t) {
+            for (int h = 0; h < 2; ++h) {
+                if (t > 0) {
+                    SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_lo, m->ev_tri[h], 0));
+                    SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t - 1, b_begin[h], b_end[h]), m->s_lo));
+                    ++m->launches;
+                }
+                if (t == horizon) continue;
+                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, b_end[h]), m->s_lo, p_begin[h]));
+                SEGP_CUDA_CHECK(cudaEventRecord(m->ev_ks[h], m->s_lo));
+                SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_hi, m->ev_ks[h], 0));
+                SEGP_CHECK(run_tri(m, (long)p_end[h] * I8_N, m->s_hi, p_begin[h]));
+                SEGP_CUDA_CHECK(cudaEventRecord(m->ev_tri[h], m->s_hi));
+                m->launches += 2;
+            }
+        }
+    }
+    if (forked) {   // everything issued on s_hi has been waited for by s_lo
+        SEGP_CUDA_CHECK(cudaEventRecord(m->ev_join, m->s_lo));
+        SEGP_CUDA_CHECK(cudaStreamWaitEvent(st, m->ev_join, 0));
     }
     return SEGP_OK;
 }
@@ -1235,6 +1302,10 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_tri_mode = value;
         return SEGP_OK;
     }
+    if (strcmp(name, "overlap") == 0 && (value == 0 || value == 1)) {
+        m->opt_overlap = value;
+        return SEGP_OK;
+    }
     if (strcmp(name, "i8_ablate") == 0) {
         m->opt_i8_ablate = value;
         return SEGP_OK;
@@ -1268,6 +1339,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "panel_group") == 0) *value = m->opt_panel_group;
     else if (strcmp(name, "ksplit") == 0) *value = m->opt_ksplit;
     else if (strcmp(name, "tri_mode") == 0) *value = m->opt_tri_mode;
+    else if (strcmp(name, "overlap") == 0) *value = m->opt_overlap;
     else if (strcmp(name, "i8_prof_ptr") == 0) *value = (long)(uintptr_t)m->i8_prof;
     else if (strcmp(name, "tri_mode_effective") == 0) *value = tri_mode(m);
     else if (strcmp(name, "launches") == 0) *value = m->launches;

@@ -140,7 +140,7 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
 template <int NS, int NU>
 __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
     constexpr int UF = unroll_factor(NS);
-    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long b = a.b0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.n_batch) return;
     const int n_s = a.n_s, n_u = a.n_u, n_in = a.n_in;
     const int dim = n_in + n_u;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
 
 int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
     const int threads = 64;
-    const unsigned grid = (unsigned)((a.n_batch + threads - 1) / threads);
+    const unsigned grid = (unsigned)((a.n_batch - a.b0 + threads - 1) / threads);
     if (a.n_s == 2 && a.n_u == 1)
         ellipsoid_step_kernel<2, 1><<<grid, threads, 0, st>>>(a);
     else if (a.n_s == 4 && a.n_u == 1)

@@ -102,6 +102,7 @@ struct KstarI8Args {
                             //   48-trajectory halves a CTA pair loads separately for cta_group::2 MMAs)
     long npanel_cap;
     int split_halves;
+    int panel0;             // first panel of this launch (blockIdx.x counts from it): sub-chunk pipelining
 };
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st);
 
@@ -110,7 +111,8 @@ struct TriI8Args {
     const double* rowfac;   // [n_s][n_pad]   rowmax_i * var_d / (127^2 254^(S-1))
     const int8_t* ki8;      // as above
     double* qpart;          // [n_s][nblk][b_cap]
-    int nblk, npanels;
+    int nblk, npanels;      // npanels = END of the panel range of this launch, panel0 its begin (tri_i8m only; else 0)
+    int panel0;
     long npanel_cap, b_cap;
     int32_t* dbg;           // optional raw accumulators [I8_S][128 (256 for the pair kernel)][I8_N] of one tile
     int fix_bi;             // >= 0: single-tile self-test mode (block row, or block-row pair for the pair kernel)
@@ -161,7 +163,8 @@ struct StepArgs {
     double* var_out;        // may be NULL
     long var_out_stride;
     int32_t* status;        // may be NULL
-    long n_batch;
+    long n_batch;           // END of the trajectory range of this launch, b0 its begin (all indices are absolute)
+    long b0;
     int n_s, n_in, n_u;
 };
 int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st);

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
     const int d = blockIdx.y;
     const int split = blockIdx.z;
     const int trow = threadIdx.x;
-    const long b = (long)blockIdx.x * I8_N + trow;
+    const int panel = aa.panel0 + (int)blockIdx.x;
+    const long b = (long)panel * I8_N + trow;
     const bool active = b < a.n_batch;
 
     __shared__ double s_x[TILE * DM];
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
     const int nkb = a.n_pad / I8_KB;
     const int row_begin = split * a.groups_per_split * 4;
     const int row_end = min(row_begin + a.groups_per_split * 4, a.n_pad);
-    int8_t* panel_base = aa.ki8 + (((long)d * aa.npanel_cap + blockIdx.x) * nkb) * (long)(I8_S * I8_B_TILE);
+    int8_t* panel_base = aa.ki8 + (((long)d * aa.npanel_cap + panel) * nkb) * (long)(I8_S * I8_B_TILE);
 
     // destination of this trajectory's bytes inside a k-block image
     const int rowp = aa.split_halves ? trow % (I8_N / 2) : trow;
@@ -313,7 +314,8 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
 }
 
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st) {
-    dim3 grid((unsigned)((a.k.n_batch + I8_N - 1) / I8_N), (unsigned)n_s, (unsigned)nsplit);
+    // panels [panel0, ceil(n_batch / 96)): n_batch is the END of the trajectory range
+    dim3 grid((unsigned)((a.k.n_batch + I8_N - 1) / I8_N - a.panel0), (unsigned)n_s, (unsigned)nsplit);
     dim3 block(I8_N);
     switch (a.k.dim) {
 #define SEGP_KS8_CASE(D) \
@@ -467,6 +469,48 @@ __device__ __forceinline__ double i8_epilogue_chunk(uint32_t tmem_quadrant_base,
         }
     }
     return vals[0];
+}
+
+// Same recombination, same roundings, for the 12-warp epilogue of tri_i8m (one 32-column chunk per warp, three warps
+// per TMEM lane quadrant, so the TMEM round trips of one warp hide behind the arithmetic of the other two):
+//   * Horner entirely in float64:  a = C0; a = a 254 + C_g (g = 1..4).  The first three steps are exact (|a| < 2^47),
+//     the fourth rounds the exact value t01 254^2 + t23 once and the fifth rounds once more -- the same two
+//     roundings as i8_epilogue_chunk, hence bit-identical column sums;
+//   * int32 -> float64 without I2F (a quarter-rate conversion, and the int64 flavour is slower still): the bit pattern
+//     0x43300000:(x ^ 0x80000000) is 2^52 + 2^31 + x exactly, one full-rate DADD removes the bias;
+//   * 64 + 32 live registers instead of 192, which is what lets 448 threads fit the register file.
+__device__ __forceinline__ double i8_cvt_s32(uint32_t x) {
+    return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+}
+__device__ __forceinline__ double i8_epilogue_chunk_fast(uint32_t tmem_quadrant_base, int col0, double rf, int lane) {
+    static_assert(I8_S == 5, "recombination below is written for 5 diagonals");
+    uint32_t v[32];
+    double acc[32];
+    tmem_ld32(tmem_quadrant_base + (uint32_t)(0 * I8_N + col0), v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = i8_cvt_s32(v[j]);
+#pragma unroll
+    for (int g = 1; g < I8_S; ++g) {
+        tmem_ld32(tmem_quadrant_base + (uint32_t)(g * I8_N + col0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fma(acc[j], I8_BASE, i8_cvt_s32(v[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double x = acc[j] * rf;
+        acc[j] = x * x;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const double keep = up ? acc[j + off] : acc[j];
+            const double give = up ? acc[j] : acc[j + off];
+            acc[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+        }
+    }
+    return acc[0];
 }
 
 // =========================================================================================== tri_i8
@@ -855,20 +899,23 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask)
                  : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i8m_kernel(const TriI8Args a) {
+constexpr int I8M_EPI_WARPS = 4 * (I8_N / 32);            // one warp per (TMEM lane quadrant, 32-column chunk)
+constexpr int I8M_THREADS = 64 + 32 * I8M_EPI_WARPS;      // producer, MMA issuer, 12 epilogue warps = 448
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8m_kernel(const TriI8Args a) {
     const uint32_t rank = cluster_ctarank();
     constexpr int PG2 = I8_PANEL_GROUP / 2;   // panel pairs per L2 group
     int d, bi, panel;
     {
         const int cid = blockIdx.x >> 1;
         const int tiles_per_group = PG2 * a.nblk;
-        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        const int npg = (a.npanels - a.panel0 + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
         const int gid = cid / tiles_per_group;
         const int r = cid % tiles_per_group;
         d = gid / npg;
         const int pg = gid % npg;
         bi = a.nblk - 1 - r / PG2;
-        panel = pg * I8_PANEL_GROUP + 2 * (r % PG2) + (int)rank;
+        panel = a.panel0 + pg * I8_PANEL_GROUP + 2 * (r % PG2) + (int)rank;
         if (panel - (int)rank >= a.npanels) return;   // the whole cluster is past the last panel
     }
     const bool valid = panel < a.npanels;             // odd panel count: the last cluster's second CTA only helps loading
@@ -961,16 +1008,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i
             tc_commit(tmem_full_bar);
         }
     } else {
+        // The epilogue is exposed (480 of the 512 TMEM columns hold accumulators: no second buffer for the next tile's
+        // MMAs), so it is spread over 12 warps: warp -> (lane quadrant warp % 4 -- the hardware's TMEM access rule --,
+        // 32-column chunk (warp - 2) / 4).
         const int q = warp & 3;
+        const int chunk = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const double rf = a.rowfac[((long)d * a.nblk + bi) * TILE + row];
         mbar_wait(tmem_full_bar, 0u);
         tc_fence_after();
-#pragma unroll 1
-        for (int chunk = 0; chunk < I8_N / 32; ++chunk)
-            s_col[q * I8_N + chunk * 32 + lane] =
-                i8_epilogue_chunk(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane, nullptr, 0);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        s_col[q * I8_N + chunk * 32 + lane] =
+            i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * I8M_EPI_WARPS) : "memory");
         const int c = threadIdx.x - 64;
         if (c < I8_N && valid) {
             const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
@@ -987,13 +1036,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i
 }
 
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
-    const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+    const int npg = (a.npanels - a.panel0 + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
     const long nclusters = (long)n_s * npg * (I8_PANEL_GROUP / 2) * a.nblk;
     if (nclusters <= 0 || 2 * nclusters > 2147483647L) {
         set_error("tri_i8m: grid of %ld cluster tiles out of range", nclusters);
         return SEGP_ERR_INVALID;
     }
-    tri_i8m_kernel<<<(unsigned)(2 * nclusters), I8_THREADS, I8_SMEM, st>>>(a);
+    tri_i8m_kernel<<<(unsigned)(2 * nclusters), I8M_THREADS, I8_SMEM, st>>>(a);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }

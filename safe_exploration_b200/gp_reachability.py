@@ -30,7 +30,7 @@ import numpy as np
 from . import _lib
 from .ssm import BatchedGPSSM
 
-__all__ = ["onestep_reachability", "multistep_reachability", "lin_ellipsoid_safety_distance", "rollout",
+__all__ = ["onestep_reachability", "multistep_reachability", "lin_ellipsoid_safety_distance", "rollout", "pinned_result",
            "RolloutResult"]
 
 RolloutResult = collections.namedtuple("RolloutResult", ["p_all", "q_all", "var_all", "status"])
@@ -44,8 +44,23 @@ def _is_tensor(x):
         return False
 
 
+def pinned_result(gp, batch, horizon, want_var=True):
+    """Page-locked host buffers for `rollout(..., out=...)`: a RolloutResult of NumPy views of pinned memory, to be
+    allocated once and reused across calls (the device->host copy of a result into pageable NumPy memory costs ~5 %
+    of a C4 call; page-locking per call would cost as much again)."""
+    torch = gp._torch
+    n_s = gp.n_s_out
+
+    def pin(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
+    return RolloutResult(pin((batch, horizon, n_s), torch.float64), pin((batch, horizon, n_s, n_s), torch.float64),
+                         pin((batch, horizon, n_s), torch.float64) if want_var else None,
+                         pin((batch,), torch.int32))
+
+
 def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safety=1., a=None, b=None,
-            t_z_gp=None, want_var=True, propagation=0):
+            t_z_gp=None, want_var=True, propagation=0, out=None):
     """B independent H-step reachability recursions in one call (the batched core behind
     multistep_reachability).
 
@@ -58,6 +73,7 @@ def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safe
     on the device (segp_multistep, asynchronous on the current stream) and return tensors.
     propagation  0 ellipsoid reachability (default); 1 / 2: q_all holds Gaussian covariances propagated by the
               first-order Taylor / mean-equivalent scheme (see uncertainty_propagation.py); l_mu, l_sigma, c_safety unused
+    out       optional RolloutResult of host arrays to write into (host path only; see pinned_result)
     Returns RolloutResult(p_all (B,H,n_s), q_all (B,H,n_s,n_s), var_all (B,H,n_s) | None, status (B,) int32).
     """
     if not isinstance(gp, BatchedGPSSM):
@@ -120,10 +136,19 @@ def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safe
     kfb_stride = 0 if (kfb_h is None or kfb_h.size == per) else per
     kfbi_h = _lib.host_f64(k_fb_init).reshape(-1) if k_fb_init is not None else None
     kfbi_stride = 0 if (kfbi_h is None or kfbi_h.size == n_u * n_s) else n_u * n_s
-    p_all = np.empty((bsz, hor, n_s))
-    q_all = np.empty((bsz, hor, n_s, n_s))
-    var_all = np.empty((bsz, hor, n_s)) if want_var else None
-    status = np.zeros((bsz,), dtype=np.int32)
+    if out is not None:
+        p_all, q_all, var_all, status = out.p_all, out.q_all, (out.var_all if want_var else None), out.status
+        for arr, shape, dt in ((p_all, (bsz, hor, n_s), np.float64), (q_all, (bsz, hor, n_s, n_s), np.float64),
+                               (var_all, (bsz, hor, n_s), np.float64), (status, (bsz,), np.int32)):
+            if arr is not None and (arr.shape != shape or arr.dtype != dt or not arr.flags["C_CONTIGUOUS"]):
+                raise ValueError("out buffers must be C-contiguous {} arrays of shape {}".format(np.dtype(dt), shape))
+        if want_var and var_all is None:
+            raise ValueError("out.var_all is required when want_var is true")
+    else:
+        p_all = np.empty((bsz, hor, n_s))
+        q_all = np.empty((bsz, hor, n_s, n_s))
+        var_all = np.empty((bsz, hor, n_s)) if want_var else None
+        status = np.zeros((bsz,), dtype=np.int32)
 
     def hp(x):
         return None if x is None else x.ctypes.data
