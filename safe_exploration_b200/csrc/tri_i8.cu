@@ -42,9 +42,14 @@ __device__ __forceinline__ void split_digits(double r, int (&dg)[I8_S]) {
 // lo = rn(frac 254^2) in [-32258, 32258], then balanced base-254 digits of hi (3) and lo (2).
 __device__ __forceinline__ void split_digits_unit(double u, int (&dg)[I8_S]) {
     static_assert(I8_S == 5, "digit layout below is for 5 planes");
+    // round-to-nearest-even through the 1.5 2^52 trick (the integer lands in the low mantissa word): the same values
+    // as __double2int_rn / (double)hi, without the quarter-rate F2I / I2F conversions
+    const double MAGIC = 6755399441055744.0;
     const double x = u * (I8_BASE0 * I8_BASE * I8_BASE);
-    const int hi = __double2int_rn(x);
-    const int lo = __double2int_rn((x - (double)hi) * (I8_BASE * I8_BASE));
+    const double th = x + MAGIC;
+    const int hi = __double2loint(th);
+    const double tl = (x - (th - MAGIC)) * (I8_BASE * I8_BASE) + MAGIC;
+    const int lo = __double2loint(tl);
     // balanced remainder: v = 254 q + d, d in [-127, 126]; offsets keep the dividends non-negative
     const unsigned lo_s = (unsigned)(lo + 127 + 254 * 128);
     const unsigned q3 = lo_s / 254u;
@@ -196,7 +201,7 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
                 g = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
             }
             if (row0 + r + qd >= n_train || !active) unit = 0.0;   // padded rows / columns: zero digits
-            const double bt = s_beta[r + qd] * var;
+            const double bt = s_beta[r + qd];   // beta_i sigma_f^2 (multiplied once while staging)
             mu = fma(bt, unit, mu);
             const double w = bt * g;
 #pragma unroll
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
         __syncthreads();
         const double* src = a.xs + ((long)d * a.n_pad + row0) * dim;
         for (int idx = threadIdx.x; idx < TILE * dim; idx += I8_N) s_x[idx] = src[idx];
-        for (int idx = threadIdx.x; idx < TILE; idx += I8_N) s_beta[idx] = a.beta[(long)d * a.n_pad + row0 + idx];
+        for (int idx = threadIdx.x; idx < TILE; idx += I8_N) s_beta[idx] = a.beta[(long)d * a.n_pad + row0 + idx] * var;
         __syncthreads();
         int8_t* kb_base = panel_base + half_off;
         // One loop body per kernel type: with both types inlined the 16-point body was 52 KB of SASS and stalled on

@@ -4,8 +4,8 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 for c in C4 C3 C5; do
   st=5; [ $c = C5 ] && st=3
-  timeout 600 python bench.py --config $c --steps $st --warmup 3 --no-cpu-baseline > gpurun_out/ov_${c}_overlap.json 2> gpurun_out/ov_${c}_overlap.err
-  timeout 600 python bench.py --config $c --steps $st --warmup 3 --no-cpu-baseline --no-overlap > gpurun_out/ov_${c}_serial.json 2> gpurun_out/ov_${c}_serial.err
+  timeout 600 python bench.py --config $c --steps $st --warmup 3 --no-cpu-baseline > gpurun_out/ov_${c}_serial.json 2> gpurun_out/ov_${c}_serial.err
+  timeout 600 python bench.py --config $c --steps $st --warmup 3 --no-cpu-baseline --overlap > gpurun_out/ov_${c}_overlap.json 2> gpurun_out/ov_${c}_overlap.err
 done
 python - <<'PY'
 import json

@@ -3,7 +3,7 @@ set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline $QUICK_ARGS > gpurun_out/q_C4_a.json 2> gpurun_out/q_C4_a.err
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-overlap $QUICK_ARGS > gpurun_out/q_C4_b.json 2> gpurun_out/q_C4_b.err
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --overlap $QUICK_ARGS > gpurun_out/q_C4_b.json 2> gpurun_out/q_C4_b.err
 python - <<'PY'
 import json
 for k in ("a","b"):
