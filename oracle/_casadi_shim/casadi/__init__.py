@@ -8,6 +8,10 @@ reference's own modules import UNMODIFIED and run on NumPy arrays:
 * ``safe_exploration/uncertainty_propagation_casadi.py:8`` does ``from casadi import *`` and then uses ``mtimes``,
   ``vertcat``, ``horzcat``, ``diag``, ``MX.eye``, ``MX.zeros`` and -- through CasADi's own star export -- ``np``.
 
+* ``safe_exploration/ssm_gpy/gp_models_utils_casadi.py:13-14`` imports ``mtimes, exp, sum2, repmat, Function, sqrt,
+  vertcat, horzcat, SX, reshape``; its kernels, ``_unscaled_dist`` and ``gp_pred`` then evaluate on NumPy arrays
+  (``gp_pred_function`` builds a symbolic ``Function`` and is not usable).
+
 Only numeric evaluation is provided; nothing symbolic.
 """
 import numpy as np
@@ -46,6 +50,11 @@ def diag(x):
 
 
 class MX(object):
+    """``MX.eye(n)`` / ``MX.zeros(n[, m])`` / ``SX(n)`` (an n x 1 matrix of zeros, ssm_gpy/gp_models_utils_casadi.py:24)."""
+
+    def __new__(cls, *shape):
+        return cls.zeros(*shape)
+
     @staticmethod
     def eye(n):
         return _np.eye(n)
@@ -60,3 +69,32 @@ class MX(object):
 
 
 SX = MX
+
+
+# ---- what ssm_gpy/gp_models_utils_casadi.py:13-14 imports (kernels, _unscaled_dist, gp_pred), numerically
+def exp(x):
+    return _np.exp(_np.asarray(x, dtype=float))
+
+
+def sqrt(x):
+    return _np.sqrt(_np.asarray(x, dtype=float))
+
+
+def sum2(x):
+    """Row sums as a column (CasADi: sum over the second dimension)."""
+    return _np.sum(_np.atleast_2d(_np.asarray(x)), axis=1, keepdims=True)
+
+
+def sum1(x):
+    return _np.sum(_np.atleast_2d(_np.asarray(x)), axis=0, keepdims=True)
+
+
+def repmat(x, n, m=1):
+    return _np.tile(_np.atleast_2d(_np.asarray(x)), (int(n), int(m)))
+
+
+class Function(object):
+    """Symbolic function objects cannot be built numerically: gp_pred_function is not usable through this shim."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("casadi.Function is not available in the NumPy-backed shim")

@@ -211,9 +211,72 @@ def golden_uncertainty_propagation():
     np.savez(os.path.join(OUT, "uncertainty_propagation.npz"), **out)
 
 
+GP_CASES = (
+    # name, fixture, N, kernels per output dimension
+    ("pend_rbf_mat52", "invpend_data.npz", 60, ["rbf", "mat52"]),
+    ("pend_composite", "invpend_data.npz", 70, ["lin_rbf", "lin_mat52"]),
+    ("cart_mixed", "data_cartpole.npz", 130, ["rbf", "lin_mat52", "mat52", "lin_rbf"]),
+)
+
+
+def gp_case_hyp(kern, dim, rng):
+    """Fixed hyper-parameters in the reference's own dict layout (ssm_gpy/gaussian_process.py:515-538)."""
+    if kern in ("rbf", "mat52"):
+        return {"lengthscale": rng.uniform(0.7, 2.5, size=dim), "variance": float(rng.uniform(0.5, 1.5))}
+    st = "rbf" if kern == "lin_rbf" else "mat52"
+    return {"prod.%s.lengthscale" % st: np.array([rng.uniform(0.6, 1.8)]),
+            "prod.%s.variance" % st: float(rng.uniform(0.5, 1.5)),
+            "prod.linear.variances": np.array([rng.uniform(0.3, 1.2)]),
+            "linear.variances": rng.uniform(0.05, 0.6, size=dim)}
+
+
+def golden_gp_pred():
+    """Kernel rows, prior variances, predictive means and variances from the reference's OWN functions
+    (ssm_gpy/gp_models_utils_casadi.py: _k_rbf, _k_mat52, _k_lin_rbf, _k_lin_mat52 through _get_kernel_function, and
+    gp_pred :177-197 -- the arithmetic SimpleGPModel.__call__ executes), evaluated numerically through the NumPy-backed
+    CasADi shim.  The posterior state handed to gp_pred is what SimpleGPModel.train stores
+    (ssm_gpy/gaussian_process.py:258-263): inv_K = (K + noise I)^-1 and beta = inv_K y, with K from the same reference
+    kernel function (diagonal from its diag_only branch; the off-diagonal branch takes sqrt of a rounded-negative
+    r^2 there) and the inverse by LAPACK."""
+    g = ref_loader.load_gp_utils()
+    out = {}
+    for name, fixture, n, kerns in GP_CASES:
+        d = np.load(os.path.join(REF_TEST, fixture), allow_pickle=True)
+        x, y = np.asarray(d["X"][:n], dtype=np.float64), np.asarray(d["y"][:n], dtype=np.float64)
+        n_s, dim = y.shape[1], x.shape[1]
+        rng = np.random.RandomState(len(name) * 7 + n)
+        z = np.vstack((x[:4] + 0.05 * rng.randn(4, dim), rng.uniform(-1.0, 1.0, size=(12, dim)) * np.abs(x).max(axis=0)))
+        noise = rng.uniform(0.01, 0.05, size=n_s) + 1e-5 + 1e-8
+        out[name + "/x_train"], out[name + "/y_train"], out[name + "/z"] = x, y, z
+        out[name + "/noise"], out[name + "/kern_types"] = noise, np.array(kerns)
+        mu = np.empty((z.shape[0], n_s))
+        var = np.empty((z.shape[0], n_s))
+        prior = np.empty((z.shape[0], n_s))
+        kst = np.empty((n_s, z.shape[0], n))
+        for i, kern in enumerate(kerns):
+            hyp = gp_case_hyp(kern, dim, rng)
+            for k, v in hyp.items():
+                out["%s/hyp%d/%s" % (name, i, k)] = np.asarray(v)
+            kfun = g._get_kernel_function(kern, hyp)
+            with np.errstate(invalid="ignore"):
+                kmat = np.asarray(kfun(x, y=x), dtype=np.float64)
+            kmat = 0.5 * (kmat + kmat.T)
+            kmat[np.diag_indices(n)] = np.asarray(kfun(x, diag_only=True), dtype=np.float64).reshape(-1) + noise[i]
+            inv_k = np.linalg.inv(kmat)
+            inv_k = 0.5 * (inv_k + inv_k.T)
+            beta = inv_k @ y[:, i:i + 1]
+            m, v = g.gp_pred(z, kfun, beta, x, inv_k)
+            mu[:, i], var[:, i] = np.asarray(m).reshape(-1), np.asarray(v).reshape(-1)
+            prior[:, i] = np.asarray(kfun(z, diag_only=True), dtype=np.float64).reshape(-1)
+            kst[i] = np.asarray(kfun(z, y=x), dtype=np.float64)
+        out[name + "/mu"], out[name + "/var"], out[name + "/prior"], out[name + "/kstar"] = mu, var, prior, kst
+    np.savez(os.path.join(OUT, "gp_pred_reference.npz"), **out)
+
+
 def main():
     reach, utils, uell = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    golden_gp_pred()
     golden_uncertainty_propagation()
     golden_invpend_c1(reach)
     golden_invpend_reach_test(reach)

@@ -50,3 +50,18 @@ def load_uncertainty_propagation():
         warnings.simplefilter("ignore")
         from safe_exploration import uncertainty_propagation_casadi
     return uncertainty_propagation_casadi
+
+
+def load_gp_utils():
+    """The reference's ssm_gpy/gp_models_utils_casadi.py (kernel functions _k_rbf / _k_mat52 / _k_lin / _k_lin_rbf /
+    _k_lin_mat52, _unscaled_dist, gp_pred), loaded BY FILE -- the ssm_gpy package __init__ needs GPy, the module itself
+    only NumPy and CasADi -- and evaluated numerically through the NumPy-backed shim."""
+    import importlib.util
+    _prepare_path()
+    path = os.path.join(REFERENCE_ROOT, "safe_exploration", "ssm_gpy", "gp_models_utils_casadi.py")
+    spec = importlib.util.spec_from_file_location("_ref_gp_models_utils_casadi", path)
+    mod = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    return mod

@@ -3,9 +3,12 @@
 * ellipsoid half: against the reference's OWN functions when /root/reference is present (build
   container), against the committed golden vectors the reference produced (everywhere), and against
   the reference's known-answer tests (reference test/test_utils_ellipsoid.py:13-94).
-* GP half: GPy/CasADi are absent, so it is pinned by identities (explicit-inverse form == Cholesky
-  form, analytic Jacobian == finite differences, K K^-1 = I), with the reference's own acceptance
-  tolerances r_tol=1e-4 / a_tol=1e-6 (reference test/test_gp_models.py:22-23) as the loosest bound.
+* GP half: kernel rows, k(x,x), predictive mean and variance against the reference's OWN
+  ssm_gpy/gp_models_utils_casadi.py functions (kernels incl. the composite lin_* ones, gp_pred), run through the
+  NumPy-backed CasADi shim -- live in the build container and as golden vectors everywhere; the posterior state GPy
+  would compute (K^-1, K^-1 y) and the closed-form Jacobian by identities (explicit-inverse form == Cholesky form,
+  analytic Jacobian == finite differences, K K^-1 = I), with the reference's own acceptance tolerances
+  r_tol=1e-4 / a_tol=1e-6 (reference test/test_gp_models.py:22-23) as the loosest bound.
 """
 import os
 
@@ -160,6 +163,70 @@ def test_golden_cartpole_batch_oracle(golden_dir):
                                                1.5, g["a"], g["b"], g["k_fb_init"])
     assert np.allclose(p_b, g["p_all_q0"], rtol=1e-7, atol=1e-10)
     assert np.allclose(q_b, g["q_all_q0"], rtol=1e-7, atol=1e-10)
+
+
+# ------------------------------------------------------------------ GP half pinned by the reference's own functions
+GP_GOLDEN_CASES = ("pend_rbf_mat52", "pend_composite", "cart_mixed")
+
+
+def gp_from_gp_golden(g, name):
+    """(GPOracle, kern_types, hyp list in the reference's dict layout) of one case of gp_pred_reference.npz."""
+    kerns = [str(k) for k in g[name + "/kern_types"]]
+    pre = name + "/hyp"
+    hyp = [{k[len(pre) + 2:]: g[k] for k in g.files if k.startswith("%s%d/" % (pre, i))} for i in range(len(kerns))]
+    x = g[name + "/x_train"]
+    ls, var, pl, lin = gp_oracle.vectors_from_reference_hyp(kerns, hyp, x.shape[1])
+    ora = gp_oracle.GPOracle(x, g[name + "/y_train"], kerns, ls, var, g[name + "/noise"], prod_linear=pl, linear=lin)
+    return ora, kerns, hyp
+
+
+@pytest.mark.parametrize("name", GP_GOLDEN_CASES)
+def test_golden_gp_pred_reference(golden_dir, name):
+    """Kernel rows, k(z,z), predictive mean and variance produced by the reference's gp_models_utils_casadi.py
+    (_k_rbf/_k_mat52/_k_lin_rbf/_k_lin_mat52 + gp_pred) -- the oracle must reproduce them."""
+    g = np.load(os.path.join(golden_dir, "gp_pred_reference.npz"))
+    ora, kerns, _ = gp_from_gp_golden(g, name)
+    z = g[name + "/z"]
+    for d in range(len(kerns)):
+        assert np.allclose(ora.kstar(d, z), g[name + "/kstar"][d], rtol=1e-12, atol=1e-14)
+        assert np.allclose(ora.prior_var(d, z), g[name + "/prior"][:, d], rtol=1e-13)
+    for form in ("explicit", "chol"):
+        mu, var = ora.predict(z, form=form)
+        assert np.allclose(mu, g[name + "/mu"], rtol=1e-8, atol=1e-10)
+        assert np.allclose(var, g[name + "/var"], rtol=1e-7, atol=1e-11)
+    assert np.allclose(ora.jacobian(z), ora.jacobian_fd(z), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_gp_oracle_equals_reference_gp_utils_live():
+    """The same comparison live, on fresh random inputs, for every kernel type and both composite semantics' building
+    blocks (_k_lin on all columns is the GPy Linear(ARD) kernel)."""
+    ref = ref_loader.load_gp_utils()
+    rng = np.random.RandomState(3)
+    n, dim, t = 35, 4, 9
+    x = rng.uniform(-1.5, 1.5, size=(n, dim))
+    z = rng.uniform(-1.5, 1.5, size=(t, dim))
+    y = rng.randn(n, 4)
+    kerns = ["rbf", "mat52", "lin_rbf", "lin_mat52"]
+    hyp = [{"lengthscale": rng.uniform(0.5, 2, dim), "variance": 1.3},
+           {"lengthscale": rng.uniform(0.5, 2, dim), "variance": 0.6},
+           {"prod.rbf.lengthscale": np.array([0.9]), "prod.rbf.variance": 1.1, "prod.linear.variances": np.array([0.7]),
+            "linear.variances": rng.uniform(0.1, 0.5, dim)},
+           {"prod.mat52.lengthscale": np.array([1.4]), "prod.mat52.variance": 0.8,
+            "prod.linear.variances": np.array([1.2]), "linear.variances": rng.uniform(0.1, 0.5, dim)}]
+    ls, var, pl, lin = gp_oracle.vectors_from_reference_hyp(kerns, hyp, dim)
+    ora = gp_oracle.GPOracle(x, y, kerns, ls, var, np.full(4, 0.02), prod_linear=pl, linear=lin)
+    ora._ensure_inv()
+    assert np.allclose(gp_oracle.unscaled_dist(z, x), ref._unscaled_dist(z, x), rtol=1e-12)
+    assert np.allclose(gp_oracle.k_lin(z, x, lin[2]), ref._k_lin(z, x, lin[2]), rtol=1e-13, atol=1e-15)
+    for d, k in enumerate(kerns):
+        kfun = ref._get_kernel_function(k, hyp[d])
+        assert np.allclose(ora.kstar(d, z), kfun(z, y=x), rtol=1e-12, atol=1e-14)
+        assert np.allclose(ora.prior_var(d, z), np.asarray(kfun(z, diag_only=True)).reshape(-1), rtol=1e-13)
+        m_r, v_r = ref.gp_pred(z, kfun, ora.beta[:, d:d + 1], x, ora.inv_K[d])
+        m_o, v_o = ora.predict(z, form="explicit")
+        assert np.allclose(m_o[:, d], np.asarray(m_r).reshape(-1), rtol=1e-11, atol=1e-13)
+        assert np.allclose(v_o[:, d], np.asarray(v_r).reshape(-1), rtol=1e-9, atol=1e-13)
 
 
 # ------------------------------------------------------------------ live against the reference (build container only)
