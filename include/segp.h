@@ -39,6 +39,13 @@ extern "C" {
 /* kernel types, per output dimension (ssm_gpy/gp_models_utils_casadi.py:17-70, 218-231) */
 #define SEGP_KERN_RBF 0
 #define SEGP_KERN_MAT52 1
+/* composite kernels of the journal configs, k = k_lin(product term) * k_stationary + k_lin(all inputs)
+ * (_k_lin_rbf / _k_lin_mat52 / _k_lin, gp_models_utils_casadi.py:73-157; GPy objects gaussian_process.py:469-474),
+ * evaluated as  k(x,y) = (sum_j a_j x_j y_j) s_f^2 phi(|(x - y) / l|) + sum_j v_j x_j y_j  with the vectors a, v of
+ * segp_set_linear_terms.  They run the variance contraction in float64 on the DMMA pipe (tri_mode 0): kernel values
+ * are unbounded, the int8 digit planes of the tcgen05 path assume k / s_f^2 in [0, 1]. */
+#define SEGP_KERN_LIN_RBF 2
+#define SEGP_KERN_LIN_MAT52 3
 
 /* per-trajectory status bits written to d_status */
 #define SEGP_STATUS_NONFINITE 1    /* p or Q became inf/NaN                                  */
@@ -72,6 +79,15 @@ int segp_destroy(segp_model* m);
 int segp_set_model(segp_model* m, int n_train, const double* h_x, const double* h_y,
                    const double* h_lengthscale, const double* h_variance, const double* h_noise);
 
+/* Linear terms of the composite kernels (HOST pointers, copies are taken); call after segp_set_model and before
+ * segp_factorize whenever an output uses SEGP_KERN_LIN_*.  h_prod_linear [n_s_out x (n_s_in+n_u)]: weights a_j of the
+ * linear factor of the product term; h_linear [n_s_out x (n_s_in+n_u)]: variances v_j of the additive linear kernel
+ * (hyper-parameters "prod.linear.variances" / "linear.variances", gaussian_process.py:523-538).  Rows of
+ * non-composite outputs are ignored.  For a composite output, h_lengthscale of segp_set_model may hold +inf for
+ * input dimensions that do not enter the stationary factor: the CasADi form of the reference uses input column 1
+ * only (gp_models_utils_casadi.py:82-95), the GPy kernel object all columns. */
+int segp_set_linear_terms(segp_model* m, const double* h_prod_linear, const double* h_linear);
+
 /* Build K_d = k_d(X,X)+noise_d I, Cholesky-factorise it, beta_d = K_d^-1 y_d, W_d = L_d^-1 packed for
  * the variance contraction -- all on the device in float64.  Synchronous (returns after completion).
  * Replaces the posterior half of SimpleGPModel.train / update_model
@@ -91,6 +107,20 @@ int segp_mark_factorized(segp_model* m);
 /* log det(K_d) per output dimension from the Cholesky factor (h_out[n_s_out], HOST).
  * Building block of SimpleGPModel.information_gain (ssm_gpy/gaussian_process.py:621-634). */
 int segp_logdet(segp_model* m, double* h_out);
+
+/* Greedy maximum-predicted-variance selection of m of the n rows of h_x (HOST pointers; synchronous): at every step
+ * the row with the largest predictive variance, summed over the output dimensions, of the GPs conditioned on the rows
+ * chosen so far (fixed hyper-parameters; ties to the lowest index; starts from the empty set).
+ * Replaces the selection loop of SimpleGPModel.choose_datapoints_maxvar (ssm_gpy/gaussian_process.py:320-343:
+ * predict over the pool, argmax of the summed variance, set_XY) without its k-means / random initial set and
+ * without hyper-parameter re-optimisation.  h_noise [n_s_out] is the diagonal term of the conditioning (> 0);
+ * h_prod_linear / h_linear as in segp_set_linear_terms (NULL unless a kernel is composite).
+ * h_index [m] int32 out: selected rows in selection order; h_score [m] out or NULL: the summed variance of each
+ * row at the moment it was selected. */
+int segp_select_maxvar(int device, int n, int n_s_out, int dim, const int* kern_type, const double* h_x,
+                       const double* h_lengthscale, const double* h_variance, const double* h_noise,
+                       const double* h_prod_linear, const double* h_linear, int m, int32_t* h_index, double* h_score,
+                       void* stream);
 
 /* Batched predictive posterior at d_z [n_batch x (n_s_in+n_u)]:
  *   d_mu [n_batch x n_s_out], d_var [n_batch x n_s_out], d_jac [n_batch x n_s_out x (n_s_in+n_u)] or NULL.

@@ -153,6 +153,18 @@ def vectors_from_reference_hyp(kern_types, hyp, dim, semantics="casadi"):
     return ls, var, pl, lin
 
 
+def golden_gp_case(g, name):
+    """(GPOracle, kern_types, hyp dicts in the reference's layout) of one case of tests/golden/gp_pred_reference.npz
+    (written by oracle/make_golden.golden_gp_pred)."""
+    kerns = [str(k) for k in g[name + "/kern_types"]]
+    pre = name + "/hyp"
+    hyp = [{k[len(pre) + 2:]: g[k] for k in g.files if k.startswith("%s%d/" % (pre, i))} for i in range(len(kerns))]
+    x = g[name + "/x_train"]
+    ls, var, pl, lin = vectors_from_reference_hyp(kerns, hyp, x.shape[1])
+    ora = GPOracle(x, g[name + "/y_train"], kerns, ls, var, g[name + "/noise"], prod_linear=pl, linear=lin)
+    return ora, kerns, hyp
+
+
 class GPOracle(object):
     """n_s independent exact GPs sharing the training inputs (SimpleGPModel posterior state).
 

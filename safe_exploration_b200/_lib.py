@@ -18,7 +18,8 @@ SEGP_ERR_NOT_POSDEF = 3
 SEGP_ERR_NOT_TRAINED = 4
 SEGP_ERR_UNSUPPORTED = 5
 
-KERN_IDS = {"rbf": 0, "mat52": 1}
+KERN_IDS = {"rbf": 0, "mat52": 1, "lin_rbf": 2, "lin_mat52": 3}
+COMPOSITE_KERNELS = ("lin_rbf", "lin_mat52")
 
 STATUS_NONFINITE = 1
 STATUS_BAD_VARIANCE = 2
@@ -61,12 +62,15 @@ PROTOTYPES = {
     "segp_create": (_int, [ctypes.POINTER(_vp), _int, _int, _int, _int, _c_int_p]),
     "segp_destroy": (_int, [_vp]),
     "segp_set_model": (_int, [_vp, _int, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p]),
+    "segp_set_linear_terms": (_int, [_vp, _c_double_p, _c_double_p]),
     "segp_factorize": (_int, [_vp, _vp]),
     "segp_alloc_factor_buffers": (_int, [_vp]),
     "segp_num_factor_buffers": (_int, [_vp]),
     "segp_factor_buffer": (_int, [_vp, _int, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t)]),
     "segp_mark_factorized": (_int, [_vp]),
     "segp_logdet": (_int, [_vp, _c_double_p]),
+    "segp_select_maxvar": (_int, [_int, _int, _int, _int, _c_int_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
+                                  _c_double_p, _c_double_p, _int, _c_int_p, _c_double_p, _vp]),
     "segp_predict": (_int, [_vp, _long, _vp, _vp, _vp, _vp, _vp]),
     "segp_multistep": (_int, [_vp, _long, _int, _vp, _long, _vp, _long, _vp, _vp, _long, _vp, _long,
                               ctypes.POINTER(ReachParams), _vp, _vp, _vp, _vp, _vp]),

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libsegp.so")
 
-SOURCES = ["api.cu", "predict.cu", "setup.cu", "ellipsoid.cu", "diag.cu", "tri_i8.cu", "score.cu"]
+SOURCES = ["api.cu", "predict.cu", "setup.cu", "ellipsoid.cu", "diag.cu", "tri_i8.cu", "score.cu", "select.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

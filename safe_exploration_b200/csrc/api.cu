@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -66,6 +67,15 @@ struct segp_model {
     double* beta = nullptr;    // [n_s][n_pad]
     double* wt = nullptr;      // [n_s][ntri][128*128]
     double* logdet = nullptr;  // [n_s]
+    // composite (linear x stationary + linear) kernels: segp_set_linear_terms
+    bool has_composite = false, has_linear_terms = false;
+    std::vector<double> h_plin, h_lin;
+    double* xraw = nullptr;    // [n_pad][dim] unscaled inputs
+    double* plin = nullptr;    // [n_s][dim]
+    double* lin = nullptr;     // [n_s][dim]
+    double* xtb = nullptr;     // [n_s][dim] X^T beta_d
+    double* jac2_part = nullptr;   // workspace: additive Jacobian partials
+    double* kss = nullptr;         // workspace: [n_s][b_cap] prior variances
     int8_t* wi8 = nullptr;     // [n_s][nblk (nblk+1)][I8_S][I8_A_TILE] digit planes of W (tcgen05 path)
     double* rowfac = nullptr;  // [n_s][n_pad] per-row factors of the digit planes
     // workspace
@@ -119,6 +129,11 @@ static void free_model_buffers(segp_model* m) {
     dev_free(m->wi8);
     dev_free(m->rowfac);
     dev_free(m->i8zero);
+    dev_free(m->xraw);
+    dev_free(m->plin);
+    dev_free(m->lin);
+    dev_free(m->xtb);
+    m->has_linear_terms = false;
     m->factorized = false;
 }
 
@@ -129,12 +144,16 @@ static void free_workspace(segp_model* m) {
     dev_free(m->mu_part);
     dev_free(m->jac_part);
     dev_free(m->qpart);
+    dev_free(m->jac2_part);
+    dev_free(m->kss);
     m->b_cap = 0;
     m->workspace_bytes = 0;
 }
 
-static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD; }
+// the int8 digit planes assume kernel values in [0, s_f^2]: composite kernels (unbounded linear terms) run in float64
+static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD && !m->has_composite; }
 static int tri_mode(const segp_model* m) {
+    if (m->has_composite) return 0;
     if (m->opt_tri_mode >= 0) return (int)m->opt_tri_mode;
     return i8_capable(m) ? 4 : 0;
 }
@@ -181,6 +200,10 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     SEGP_CHECK(dev_alloc(&m->mu_part, n_mu));
     SEGP_CHECK(dev_alloc(&m->jac_part, n_jac));
     SEGP_CHECK(dev_alloc(&m->qpart, n_q));
+    if (m->has_composite) {
+        SEGP_CHECK(dev_alloc(&m->jac2_part, n_jac));
+        SEGP_CHECK(dev_alloc(&m->kss, (size_t)m->n_s * want));
+    }
     if (n_ks > 0) SEGP_CUDA_CHECK(cudaMemset(m->ks, 0, n_ks * sizeof(double)));
     if (n_ki8 > 0) SEGP_CUDA_CHECK(cudaMemset(m->ki8, 0, n_ki8));
     m->workspace_bytes = (n_ks + n_mu + n_jac + n_q) * sizeof(double) + n_ki8;
@@ -252,6 +275,14 @@ static KstarArgs base_kstar_args(const segp_model* m) {
     k.ks = m->ks;
     k.mu_part = m->mu_part;
     k.jac_part = m->jac_part;
+    if (m->has_composite) {
+        k.xraw = m->xraw;
+        k.plin = m->plin;
+        k.lin = m->lin;
+        k.xtb = m->xtb;
+        k.jac2_part = m->jac2_part;
+        k.kss = m->kss;
+    }
     return k;
 }
 
@@ -341,7 +372,7 @@ int segp_create(segp_model** out, int device, int n_s_out, int n_s_in, int n_u, 
         return SEGP_ERR_INVALID;
     }
     for (int d = 0; d < n_s_out; ++d)
-        if (kern_type[d] != SEGP_KERN_RBF && kern_type[d] != SEGP_KERN_MAT52) {
+        if (kern_type[d] < SEGP_KERN_RBF || kern_type[d] > SEGP_KERN_LIN_MAT52) {
             set_error("segp_create: unsupported kernel type %d for output %d", kern_type[d], d);
             return SEGP_ERR_UNSUPPORTED;
         }
@@ -374,7 +405,10 @@ int segp_create(segp_model** out, int device, int n_s_out, int n_s_in, int n_u, 
     m->n_in = n_s_in;
     m->n_u = n_u;
     m->dim = n_s_in + n_u;
-    for (int d = 0; d < n_s_out; ++d) m->kern[d] = kern_type[d];
+    for (int d = 0; d < n_s_out; ++d) {
+        m->kern[d] = kern_type[d];
+        if (kern_is_composite(kern_type[d])) m->has_composite = true;
+    }
     if (dev_alloc(&m->d_sp, 1) != SEGP_OK) {
         delete m;
         return SEGP_ERR_CUDA;
@@ -413,11 +447,14 @@ int segp_set_model(segp_model* m, int n_train, const double* h_x, const double* 
             set_error("segp_set_model: variance must be > 0 and noise >= 0 (output %d)", d);
             return SEGP_ERR_INVALID;
         }
-        for (int j = 0; j < m->dim; ++j)
-            if (!(h_lengthscale[d * m->dim + j] > 0.0)) {
-                set_error("segp_set_model: lengthscale[%d][%d] must be > 0", d, j);
+        for (int j = 0; j < m->dim; ++j) {
+            const double l = h_lengthscale[d * m->dim + j];
+            if (!(l > 0.0) || (std::isinf(l) && !kern_is_composite(m->kern[d]))) {
+                set_error("segp_set_model: lengthscale[%d][%d] must be > 0 (and finite unless the kernel is composite)",
+                          d, j);
                 return SEGP_ERR_INVALID;
             }
+        }
     }
     DeviceGuard guard(m->device);
     cudaDeviceSynchronize();
@@ -451,7 +488,57 @@ int segp_set_model(segp_model* m, int n_train, const double* h_x, const double* 
     SEGP_CUDA_CHECK(cudaMemcpy(m->yp, yp.data(), yp.size() * sizeof(double), cudaMemcpyHostToDevice));
     SEGP_CUDA_CHECK(cudaMemcpy(m->invls, invls.data(), invls.size() * sizeof(double), cudaMemcpyHostToDevice));
     SEGP_CUDA_CHECK(cudaMemcpy(m->var, h_variance, n_s * sizeof(double), cudaMemcpyHostToDevice));
+    if (m->has_composite) {
+        std::vector<double> xraw((size_t)m->n_pad * dim, 0.0);
+        std::copy(h_x, h_x + (size_t)n_train * dim, xraw.begin());
+        SEGP_CHECK(dev_alloc(&m->xraw, xraw.size()));
+        SEGP_CUDA_CHECK(cudaMemcpy(m->xraw, xraw.data(), xraw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     m->has_data = true;
+    return SEGP_OK;
+}
+
+int segp_set_linear_terms(segp_model* m, const double* h_prod_linear, const double* h_linear) {
+    if (m == nullptr || h_prod_linear == nullptr || h_linear == nullptr) {
+        set_error("segp_set_linear_terms: null argument");
+        return SEGP_ERR_INVALID;
+    }
+    if (!m->has_data) {
+        set_error("segp_set_linear_terms: call segp_set_model first");
+        return SEGP_ERR_NOT_TRAINED;
+    }
+    if (!m->has_composite) return SEGP_OK;   // nothing uses them
+    const size_t n = (size_t)m->n_s * m->dim;
+    for (int d = 0; d < m->n_s; ++d)
+        for (int j = 0; j < m->dim && kern_is_composite(m->kern[d]); ++j)
+            if (!(h_prod_linear[d * m->dim + j] >= 0.0) || !(h_linear[d * m->dim + j] >= 0.0)) {
+                set_error("segp_set_linear_terms: weights of output %d must be >= 0", d);
+                return SEGP_ERR_INVALID;
+            }
+    DeviceGuard guard(m->device);
+    m->h_plin.assign(h_prod_linear, h_prod_linear + n);
+    m->h_lin.assign(h_linear, h_linear + n);
+    for (int d = 0; d < m->n_s; ++d)
+        if (!kern_is_composite(m->kern[d]))
+            for (int j = 0; j < m->dim; ++j) m->h_plin[d * m->dim + j] = m->h_lin[d * m->dim + j] = 0.0;
+    if (m->plin == nullptr) SEGP_CHECK(dev_alloc(&m->plin, n));
+    if (m->lin == nullptr) SEGP_CHECK(dev_alloc(&m->lin, n));
+    if (m->xtb == nullptr) SEGP_CHECK(dev_alloc(&m->xtb, n));
+    SEGP_CUDA_CHECK(cudaMemcpy(m->plin, m->h_plin.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    SEGP_CUDA_CHECK(cudaMemcpy(m->lin, m->h_lin.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    SEGP_CUDA_CHECK(cudaMemset(m->xtb, 0, n * sizeof(double)));
+    m->has_linear_terms = true;
+    m->factorized = false;
+    return SEGP_OK;
+}
+
+// X^T beta_d for the composite outputs (after beta is known: factorisation, or the broadcast of the factor buffers)
+static int compute_xtb(segp_model* m, cudaStream_t st) {
+    for (int d = 0; d < m->n_s; ++d)
+        if (kern_is_composite(m->kern[d])) {
+            SEGP_CHECK(launch_xtb(m->xraw, m->beta + (size_t)d * m->n_pad, m->xtb + (size_t)d * m->dim, m->n_pad, m->dim, st));
+            ++m->launches;
+        }
     return SEGP_OK;
 }
 
@@ -524,6 +611,15 @@ int segp_mark_factorized(segp_model* m) {
         set_error("segp_mark_factorized: buffers are not allocated");
         return SEGP_ERR_NOT_TRAINED;
     }
+    if (m->has_composite) {
+        if (!m->has_linear_terms) {
+            set_error("segp_mark_factorized: composite kernel without linear terms (call segp_set_linear_terms)");
+            return SEGP_ERR_INVALID;
+        }
+        DeviceGuard guard(m->device);
+        SEGP_CHECK(compute_xtb(m, nullptr));
+        SEGP_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+    }
     m->factorized = true;
     return SEGP_OK;
 }
@@ -532,6 +628,10 @@ int segp_factorize(segp_model* m, void* stream) {
     if (m == nullptr || !m->has_data) {
         set_error("segp_factorize: segp_set_model has not been called");
         return SEGP_ERR_NOT_TRAINED;
+    }
+    if (m->has_composite && !m->has_linear_terms) {
+        set_error("segp_factorize: composite kernel without linear terms (call segp_set_linear_terms)");
+        return SEGP_ERR_INVALID;
     }
     DeviceGuard guard(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -553,7 +653,11 @@ int segp_factorize(segp_model* m, void* stream) {
         SetupDims sd{m->n_train, m->n_pad, m->dim};
         for (int d = 0; d < m->n_s && rc == SEGP_OK; ++d) {
             const double* xs_d = m->xs + (size_t)d * m->n_pad * m->dim;
-            if ((rc = launch_kmat(kbuf, xs_d, m->kern[d], m->h_var[d], m->h_noise[d], sd, st)) != SEGP_OK) break;
+            const bool comp = kern_is_composite(m->kern[d]);
+            if ((rc = launch_kmat(kbuf, xs_d, m->kern[d], m->h_var[d], m->h_noise[d], sd, comp ? m->xraw : nullptr,
+                                  comp ? m->plin + (size_t)d * m->dim : nullptr,
+                                  comp ? m->lin + (size_t)d * m->dim : nullptr, st)) != SEGP_OK)
+                break;
             ++m->launches;
             if ((rc = potrf_lower(kbuf, m->n_pad, diag_inv, d_fail + d, st, &m->launches)) != SEGP_OK) break;
             if ((rc = logdet_from_chol(kbuf, m->n_train, m->n_pad, m->logdet + d, st)) != SEGP_OK) break;
@@ -578,6 +682,7 @@ int segp_factorize(segp_model* m, void* stream) {
             }
         }
         if (rc != SEGP_OK) break;
+        if (m->has_composite && (rc = compute_xtb(m, st)) != SEGP_OK) break;
         cudaError_t e = cudaStreamSynchronize(st);
         if (e == cudaSuccess)
             e = cudaMemcpy(fails.data(), d_fail, m->n_s * sizeof(int), cudaMemcpyDeviceToHost);
@@ -636,6 +741,8 @@ int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, d
         f.qpart = m->qpart;
         f.gp_var = m->var;
         f.invls = m->invls;
+        f.jac2_part = m->jac2_part;
+        f.kss = m->kss;
         f.nsplit = m->nsplit;
         f.nblk = m->nblk;
         f.n_s = m->n_s;
@@ -703,6 +810,8 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         s.qpart = m->qpart;
         s.gp_var = m->var;
         s.invls = m->invls;
+        s.jac2_part = m->jac2_part;
+        s.kss = m->kss;
         s.nsplit = m->nsplit;
         s.nblk = m->nblk;
         s.b_cap = m->b_cap;
@@ -1294,6 +1403,10 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         return SEGP_OK;
     }
     if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 4) {
+        if (value >= 1 && m->has_composite) {
+            set_error("tri_mode=%ld (int8 tcgen05) is not available with composite (lin_*) kernels: float64 only", value);
+            return SEGP_ERR_UNSUPPORTED;
+        }
         if (value >= 1 && m->has_data && !i8_capable(m)) {
             set_error("tri_mode=%ld (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", value, I8_MAX_NPAD,
                       m->n_pad);

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
                 double qf = 0.0;
                 for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
                 mu[d] = m;
-                var[d] = a.gp_var[d] - qf;
+                var[d] = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;
             } else {
                 mu[d] = a.mu_d[b * n_s + d];
                 var[d] = a.var_d[b * n_s + d];
@@ -242,6 +242,12 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
                             for (int s = 0; s < a.nsplit; ++s)
                                 acc += a.jac_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
                             jrow[j] = -acc * a.invls[d * dim + j];
+                            if (a.jac2_part != nullptr) {   // composite kernels: additive terms, final form
+                                double add = 0.0;
+                                for (int s = 0; s < a.nsplit; ++s)
+                                    add += a.jac2_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
+                                jrow[j] += add;
+                            }
                         } else {
                             jrow[j] = a.jac_d[(b * n_s + d) * dim + j];
                         }

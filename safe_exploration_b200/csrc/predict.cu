@@ -20,6 +20,98 @@ namespace segp {
 // =========================================================================================== kstar_mean_jac
 constexpr int KS_THREADS = 128;
 
+// Composite kernels  k(z, x_i) = lp_i stat_i + ll_i  with  lp_i = sum_j a_j z_j x_ij,  ll_i = sum_j v_j z_j x_ij,
+// stat_i = s_f^2 phi(|s (z - x_i)|)  (_k_lin_rbf / _k_lin_mat52, gp_models_utils_casadi.py:73-129).  Same outputs as
+// the stationary path (kernel block in the DMMA operand layout, mean partial) plus
+//   jac_part  [j] = sum_i beta_i lp_i g_i s_j (z_j - x_ij)          (finalised as -s_j * ., like the stationary part)
+//   jac2_part [j] = a_j sum_i beta_i stat_i x_ij  +  v_j (X^T beta)_j          (added as is)
+//   kss           = s_f^2 sum_j a_j z_j^2 + sum_j v_j z_j^2                      (prior variance k(z, z))
+// i.e. d k / d z_j = a_j x_ij stat_i - lp_i g_i s_j^2 (z_j - x_ij) + v_j x_ij.  Small models only (journal configs:
+// N of a few hundred): one training point per iteration, raw inputs read through the cache.
+template <int DM>
+__device__ __forceinline__ void kstar_composite(const KstarArgs& a, const double (&z)[DM], int dim, int d, int split,
+                                                long b, bool active) {
+    if (!active) return;
+    const int kern = a.kern[d];
+    const double var = a.var[d];
+    const double sqrt5 = 2.23606797749978969641;
+    const double* __restrict__ pl = a.plin + d * dim;
+    const double* __restrict__ lv = a.lin + d * dim;
+    double zs[DM], za[DM], zv[DM], jac[DM], jac2[DM];
+    double kss = 0.0, kss_lin = 0.0;
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+        zs[j] = za[j] = zv[j] = jac[j] = jac2[j] = 0.0;
+        if (j < dim) {
+            zs[j] = z[j] * a.invls[d * dim + j];
+            za[j] = z[j] * pl[j];
+            zv[j] = z[j] * lv[j];
+            kss = fma(za[j], z[j], kss);
+            kss_lin = fma(zv[j], z[j], kss_lin);
+        }
+    }
+    double mu = 0.0;
+    const int ngroups = a.n_pad / 4;
+    const int g0 = split * a.groups_per_split;
+    const int g1 = min(g0 + a.groups_per_split, ngroups);
+    for (int g = g0; g < g1; ++g) {
+        double kv[4];
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const int row = g * 4 + qd;
+            const double* __restrict__ xsr = a.xs + ((long)d * a.n_pad + row) * dim;
+            const double* __restrict__ xr = a.xraw + (long)row * dim;
+            double diff[DM];
+            double r2 = 0.0, lp = 0.0, ll = 0.0;
+#pragma unroll
+            for (int j = 0; j < DM; ++j) {
+                diff[j] = 0.0;
+                if (j < dim) {
+                    diff[j] = zs[j] - xsr[j];
+                    r2 = fma(diff[j], diff[j], r2);
+                    lp = fma(za[j], xr[j], lp);
+                    ll = fma(zv[j], xr[j], ll);
+                }
+            }
+            double stat, gg;
+            if (kern == SEGP_KERN_LIN_RBF) {
+                stat = var * exp(-0.5 * r2);
+                gg = stat;
+            } else {
+                const double rr = sqrt(r2);
+                const double e = var * exp(-sqrt5 * rr);
+                stat = (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * e;
+                gg = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
+            }
+            double kval = fma(lp, stat, ll);
+            if (row >= a.n_train) kval = 0.0;
+            const double bt = a.beta[(long)d * a.n_pad + row];   // zero on padded rows
+            mu = fma(bt, kval, mu);
+            const double w = bt * lp * gg, w2 = bt * stat;
+#pragma unroll
+            for (int j = 0; j < DM; ++j)
+                if (j < dim) {
+                    jac[j] = fma(w, diff[j], jac[j]);
+                    jac2[j] = fma(w2, xr[j], jac2[j]);
+                }
+            kv[qd] = kval;
+        }
+        double2* dst = reinterpret_cast<double2*>(a.ks + (((long)d * ngroups + g) * a.b_cap + b) * 4);
+        dst[0] = make_double2(kv[0], kv[1]);
+        dst[1] = make_double2(kv[2], kv[3]);
+    }
+    const int n_s = gridDim.y;
+    a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
+#pragma unroll
+    for (int j = 0; j < DM; ++j)
+        if (j < dim) {
+            a.jac_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = jac[j];
+            a.jac2_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] =
+                pl[j] * jac2[j] + (split == 0 ? lv[j] * a.xtb[d * dim + j] : 0.0);
+        }
+    if (split == 0) a.kss[(long)d * a.b_cap + b] = fma(var, kss, kss_lin);
+}
+
 template <int D_T>
 __global__ void __launch_bounds__(KS_THREADS) kstar_mean_jac_kernel(const KstarArgs a) {
     constexpr int DM = D_T > 0 ? D_T : MAX_D;
@@ -60,6 +152,14 @@ __global__ void __launch_bounds__(KS_THREADS) kstar_mean_jac_kernel(const KstarA
             for (int j = 0; j < DM; ++j)
                 if (j >= a.n_in && j < dim) zs[j] = u[j - a.n_in];
         }
+    }
+    const int kern = a.kern[d];
+    const double var = a.var[d];
+    if (kern_is_composite(kern)) {   // block-uniform branch: the composite kernels take their own (simple) path
+        kstar_composite<DM>(a, zs, dim, d, split, b, active);
+        return;
+    }
+    if (active) {
 #pragma unroll
         for (int j = 0; j < DM; ++j)
             if (j < dim) zs[j] *= a.invls[d * dim + j];
@@ -70,8 +170,6 @@ __global__ void __launch_bounds__(KS_THREADS) kstar_mean_jac_kernel(const KstarA
 #pragma unroll
     for (int j = 0; j < DM; ++j) jac[j] = 0.0;
 
-    const int kern = a.kern[d];
-    const double var = a.var[d];
     const int ngroups = a.n_pad / 4;
     const int g0 = split * a.groups_per_split;
     const int g1 = min(g0 + a.groups_per_split, ngroups);
@@ -131,7 +229,11 @@ __global__ void __launch_bounds__(KS_THREADS) kstar_mean_jac_kernel(const KstarA
         a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
 #pragma unroll
         for (int j = 0; j < DM; ++j)
-            if (j < dim) a.jac_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = jac[j];
+            if (j < dim) {
+                a.jac_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = jac[j];
+                if (a.jac2_part != nullptr) a.jac2_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = 0.0;
+            }
+        if (a.kss != nullptr && split == 0) a.kss[(long)d * a.b_cap + b] = var;
     }
 }
 
@@ -344,13 +446,16 @@ __global__ void finalize_predict_kernel(const FinalizeArgs a) {
         double qf = 0.0;
         for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
         a.mu[b * a.n_s + d] = mu;
-        a.var[b * a.n_s + d] = a.gp_var[d] - qf;
+        a.var[b * a.n_s + d] = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;
         if (a.jac != nullptr) {
             for (int j = 0; j < a.dim; ++j) {
-                double acc = 0.0;
-                for (int s = 0; s < a.nsplit; ++s)
-                    acc += a.jac_part[(((long)s * a.n_s + d) * a.dim + j) * a.b_cap + b];
-                a.jac[(b * a.n_s + d) * a.dim + j] = -acc * a.invls[d * a.dim + j];
+                double acc = 0.0, add = 0.0;
+                for (int s = 0; s < a.nsplit; ++s) {
+                    const long idx = (((long)s * a.n_s + d) * a.dim + j) * a.b_cap + b;
+                    acc += a.jac_part[idx];
+                    if (a.jac2_part != nullptr) add += a.jac2_part[idx];
+                }
+                a.jac[(b * a.n_s + d) * a.dim + j] = fma(-acc, a.invls[d * a.dim + j], add);
             }
         }
     }

@@ -63,7 +63,15 @@ struct KstarArgs {
     double* ks;             // [n_s][Np/4][b_cap][4]
     double* mu_part;        // [nsplit][n_s][b_cap]
     double* jac_part;       // [nsplit][n_s][D][b_cap]   (scaled coordinates, sign not yet applied)
+    // composite (linear x stationary + linear) kernels only; all NULL otherwise
+    const double* xraw;     // [Np][D] unscaled training inputs, zero padded
+    const double* plin;     // [n_s][D] product-linear weights a_j
+    const double* lin;      // [n_s][D] linear variances v_j
+    const double* xtb;      // [n_s][D] X^T beta_d (the z-independent part of the Jacobian of the linear kernel)
+    double* jac2_part;      // [nsplit][n_s][D][b_cap]   additive Jacobian terms, final form
+    double* kss;            // [n_s][b_cap]  prior variance k_d(z_b, z_b)
 };
+__host__ __device__ inline bool kern_is_composite(int k) { return k == SEGP_KERN_LIN_RBF || k == SEGP_KERN_LIN_MAT52; }
 int launch_kstar(const KstarArgs& a, int n_s, int nsplit, cudaStream_t st);
 
 // ---------------------------------------------------------------- variance contraction  |W K*|^2 column sums
@@ -140,6 +148,8 @@ struct StepArgs {
     const double* qpart;
     const double* gp_var;   // [n_s] signal variances
     const double* invls;    // [n_s][D]
+    const double* jac2_part;   // composite kernels: additive Jacobian partials (else NULL)
+    const double* kss;         // composite kernels: per-trajectory prior variance [n_s][b_cap] (else NULL: gp_var)
     int nsplit, nblk;
     long b_cap;
     // ... or given directly (foreign state-space model): [B x n_s], [B x n_s], [B x n_s x D]
@@ -175,6 +185,8 @@ struct FinalizeArgs {
     const double* qpart;
     const double* gp_var;
     const double* invls;
+    const double* jac2_part;   // composite kernels only (else NULL)
+    const double* kss;
     int nsplit, nblk, n_s, dim;
     long b_cap, n_batch;
     double* mu;    // [B x n_s]
@@ -231,7 +243,11 @@ struct SetupDims {
     int n_train, n_pad, dim;
 };
 // K[d] (n_pad x n_pad row-major) = k_d(X,X) + noise I; identity on the padded diagonal.
-int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, cudaStream_t st);
+// composite kernels: xraw [n_pad][dim] unscaled inputs, plin_d / lin_d [dim] device vectors (else NULL)
+int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, const double* xraw,
+                const double* plin_d, const double* lin_d, cudaStream_t st);
+// xtb[j] = sum_i beta[i] xraw[i][j]  (fixed-order block reduction)
+int launch_xtb(const double* xraw, const double* beta, double* xtb, int n_pad, int dim, cudaStream_t st);
 // in-place blocked Cholesky (lower) of a (n_pad x n_pad); diag_inv gets the inverses of the 64x64 diagonal blocks;
 // *d_fail (device int) is set to 1+pivot index on a non-positive pivot.
 int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_t st, long* launches);

@@ -15,14 +15,16 @@ namespace segp {
 
 // =========================================================================================== kmat
 __global__ void kmat_kernel(double* __restrict__ k, const double* __restrict__ xs, int kern, double var, double noise,
-                            int n_train, int n_pad, int dim) {
+                            int n_train, int n_pad, int dim, const double* __restrict__ xraw,
+                            const double* __restrict__ plin, const double* __restrict__ lin) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= n_pad) return;
+    const bool composite = kern_is_composite(kern);
     double v;
     if (i >= n_train || j >= n_train) {
         v = (i == j) ? 1.0 : 0.0;
-    } else if (i == j) {
+    } else if (i == j && !composite) {
         v = var + noise;
     } else {
         double r2 = 0.0;
@@ -30,20 +32,57 @@ __global__ void kmat_kernel(double* __restrict__ k, const double* __restrict__ x
             const double df = xs[(long)i * dim + c] - xs[(long)j * dim + c];
             r2 = fma(df, df, r2);
         }
-        if (kern == SEGP_KERN_RBF) {
+        if (kern == SEGP_KERN_RBF || kern == SEGP_KERN_LIN_RBF) {
             v = var * exp(-0.5 * r2);
         } else {
             const double sqrt5 = 2.23606797749978969641;
             const double rr = sqrt(r2);
             v = var * (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * exp(-sqrt5 * rr);
         }
+        if (composite) {   // (sum a x_i x_j) k_stat + sum v x_i x_j   (_k_lin_rbf / _k_lin_mat52)
+            double lp = 0.0, ll = 0.0;
+            for (int c = 0; c < dim; ++c) {
+                const double xx = xraw[(long)i * dim + c] * xraw[(long)j * dim + c];
+                lp = fma(plin[c], xx, lp);
+                ll = fma(lin[c], xx, ll);
+            }
+            v = fma(lp, v, ll);
+            if (i == j) v += noise;
+        }
     }
     k[(long)i * n_pad + j] = v;
 }
 
-int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, cudaStream_t st) {
+int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, const double* xraw,
+                const double* plin_d, const double* lin_d, cudaStream_t st) {
+    if (kern_is_composite(kern) && (xraw == nullptr || plin_d == nullptr || lin_d == nullptr)) {
+        set_error("composite kernel without linear terms (call segp_set_linear_terms)");
+        return SEGP_ERR_INVALID;
+    }
     dim3 grid((unsigned)((s.n_pad + 127) / 128), (unsigned)s.n_pad);
-    kmat_kernel<<<grid, 128, 0, st>>>(k, xs_d, kern, var, noise, s.n_train, s.n_pad, s.dim);
+    kmat_kernel<<<grid, 128, 0, st>>>(k, xs_d, kern, var, noise, s.n_train, s.n_pad, s.dim, xraw, plin_d, lin_d);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// xtb[j] = sum_i beta[i] xraw[i][j]: one block per input dimension, fixed-order tree reduction
+__global__ void __launch_bounds__(256) xtb_kernel(const double* __restrict__ xraw, const double* __restrict__ beta,
+                                                  double* __restrict__ xtb, int n_pad, int dim) {
+    __shared__ double s[256];
+    const int j = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_pad; i += 256) acc = fma(beta[i], xraw[(long)i * dim + j], acc);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) xtb[j] = s[0];
+}
+
+int launch_xtb(const double* xraw, const double* beta, double* xtb, int n_pad, int dim, cudaStream_t st) {
+    xtb_kernel<<<dim, 256, 0, st>>>(xraw, beta, xtb, n_pad, dim);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }

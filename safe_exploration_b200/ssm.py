@@ -41,10 +41,50 @@ _GPY_JITTER = 1e-8        # ExactGaussianInference adds 1e-8 to the diagonal of 
 _GPY_DEFAULT_NOISE = 1.0  # GPRegression default Gaussian_noise.variance
 
 
-def _default_hyp(n_s_out, dim):
+def _default_hyp(n_s_out, dim, kern_types=None):
     """GPy defaults (lengthscale 1, variance 1, Gaussian noise 1), i.e. what SimpleGPModel yields for
     train(..., opt_hyp=False) (reference test/test_safempc.py:56-69)."""
-    return [{"lengthscale": np.ones(dim), "variance": 1.0, "noise": _GPY_DEFAULT_NOISE} for _ in range(n_s_out)]
+    out = []
+    for d in range(n_s_out):
+        k = kern_types[d] if kern_types is not None else "rbf"
+        if k in _lib.COMPOSITE_KERNELS:
+            st = "rbf" if k == "lin_rbf" else "mat52"
+            out.append({"prod.%s.lengthscale" % st: np.ones(1), "prod.%s.variance" % st: 1.0,
+                        "prod.linear.variances": np.ones(1), "linear.variances": np.ones(dim),
+                        "noise": _GPY_DEFAULT_NOISE})
+        else:
+            out.append({"lengthscale": np.ones(dim), "variance": 1.0, "noise": _GPY_DEFAULT_NOISE})
+    return out
+
+
+def _composite_vectors(kern_type, hyp, dim, semantics):
+    """Inverse length-scales s_j, product-linear weights a_j, linear variances v_j and the stationary variance of
+    the general form  k(x,y) = (sum_j a_j x_j y_j) s_f^2 phi(|s (x - y)|) + sum_j v_j x_j y_j  for the reference's
+    composite kernels.  semantics "casadi": the product term sees input column 1 only, what the hot path evaluates
+    (_k_lin_rbf / _k_lin_mat52, ssm_gpy/gp_models_utils_casadi.py:73-129); "gpy": the kernel object GPy is given,
+    Linear(D) * RBF(D) + Linear(D, ARD) on all columns (ssm_gpy/gaussian_process.py:469-474)."""
+    st = "rbf" if kern_type == "lin_rbf" else "mat52"
+    ls = float(np.asarray(hyp["prod.%s.lengthscale" % st]).reshape(-1)[0])
+    var = float(np.asarray(hyp["prod.%s.variance" % st]).reshape(-1)[0])
+    plv = float(np.asarray(hyp["prod.linear.variances"]).reshape(-1)[0])
+    lv = np.asarray(hyp["linear.variances"], dtype=np.float64).reshape(-1)
+    if lv.size == 1:
+        lv = np.full(dim, lv[0])
+    if lv.size != dim:
+        raise ValueError("linear.variances needs {} entries".format(dim))
+    if semantics == "casadi":
+        if dim < 2:
+            raise ValueError("the CasADi form of the composite kernels uses input column 1")
+        s = np.zeros(dim)
+        s[1] = 1.0 / ls
+        a = np.zeros(dim)
+        a[1] = plv
+    elif semantics == "gpy":
+        s = np.full(dim, 1.0 / ls)
+        a = np.full(dim, plv)
+    else:
+        raise ValueError("composite_semantics must be 'casadi' or 'gpy'")
+    return s, a, lv, var
 
 
 class BatchedGPSSM(object):
@@ -57,12 +97,17 @@ class BatchedGPSSM(object):
     X : (N, n_s_in+n_u), y : (N, n_s_out), optional
         Training data; if both are given and ``train`` is true the model is factorised immediately.
     kern_types : list[str], optional
-        "rbf" | "mat52" per output dimension (default "rbf").  The composite "lin_rbf"/"lin_mat52"
-        kernels of the reference are not on this path yet: NotImplementedError.
+        "rbf" | "mat52" | "lin_rbf" | "lin_mat52" per output dimension (default "rbf").  The composite kernels
+         run the variance contraction in float64 (tri_mode 0).
     hyp : list[dict], optional
-        Per output dimension ``{"lengthscale": (D,) or scalar, "variance": float, "noise": float}``
-        (the reference's hyp dicts, ssm_gpy/gaussian_process.py:494-518, plus the Gaussian noise
-        variance GPy keeps on the likelihood).  Defaults are GPy's defaults.
+        Per output dimension ``{"lengthscale": (D,) or scalar, "variance": float, "noise": float}``; for the composite
+        kernels ``{"prod.rbf.lengthscale" | "prod.mat52.lengthscale", "prod.*.variance", "prod.linear.variances",
+        "linear.variances" (D,), "noise"}`` (the reference's hyp dicts, ssm_gpy/gaussian_process.py:494-538, plus the
+        Gaussian noise variance GPy keeps on the likelihood).  Defaults are GPy's defaults.
+    composite_semantics : "casadi" | "gpy"
+        Which of the reference's two (inconsistent) definitions of the composite kernels to use for BOTH the
+        factorised matrix and the kernel rows: the CasADi functions the hot path evaluates (product term on input
+        column 1 only; default) or the GPy kernel object (all columns).
     device : int or torch.device, optional
         CUDA device (default: current).
     """
@@ -71,7 +116,7 @@ class BatchedGPSSM(object):
     has_reverse = False
 
     def __init__(self, n_s_out, n_s_in, n_u, X=None, y=None, m=None, kern_types=None, hyp=None, train=True,
-                 Z=None, device=None, noise_diag=1e-5, tri_mode=None):
+                 Z=None, device=None, noise_diag=1e-5, tri_mode=None, composite_semantics="casadi"):
         torch = _lib.require_cuda()
         self._torch = torch
         self._lib = _lib.load()
@@ -92,9 +137,11 @@ class BatchedGPSSM(object):
             raise ValueError("kern_types needs one entry per output dimension")
         for k in self.kern_types:
             if k not in _lib.KERN_IDS:
-                if k in ("lin_rbf", "lin_mat52", "lin"):
-                    raise NotImplementedError("kernel '{}' is not on the B200 path yet".format(k))
-                raise ValueError("kernel type '{}' not supported".format(k))
+                raise ValueError("kernel type '{}' not supported".format(k))     # as gaussian_process.py:476-478
+        self.has_composite = any(k in _lib.COMPOSITE_KERNELS for k in self.kern_types)
+        if composite_semantics not in ("casadi", "gpy"):
+            raise ValueError("composite_semantics must be 'casadi' or 'gpy'")
+        self.composite_semantics = composite_semantics
         self.hyp = self._normalise_hyp(hyp)
         self.noise_diag = float(noise_diag)
         self.gp_trained = False
@@ -106,7 +153,9 @@ class BatchedGPSSM(object):
         kern_ids = (ctypes.c_int * self.n_s_out)(*[_lib.KERN_IDS[k] for k in self.kern_types])
         _lib.check(self._lib.segp_create(ctypes.byref(self._handle), self.device.index, self.n_s_out, self.n_s_in,
                                          self.n_u, kern_ids))
-        self.set_option("tri_mode", DEFAULT_TRI_MODE if tri_mode is None else tri_mode)
+        if tri_mode is None:
+            tri_mode = 0 if self.has_composite else DEFAULT_TRI_MODE
+        self.set_option("tri_mode", tri_mode)
         if X is not None and y is not None and train:
             self.train(X, y)
 
@@ -126,11 +175,17 @@ class BatchedGPSSM(object):
     # ------------------------------------------------------------------ hyper-parameters
     def _normalise_hyp(self, hyp):
         if hyp is None:
-            return _default_hyp(self.n_s_out, self.dim_in)
+            return _default_hyp(self.n_s_out, self.dim_in, self.kern_types)
         if len(hyp) != self.n_s_out:
             raise ValueError("hyp needs one dict per output dimension")
         out = []
-        for h in hyp:
+        for k, h in zip(self.kern_types, hyp):
+            if k in _lib.COMPOSITE_KERNELS:
+                hc = {key: np.asarray(val, dtype=np.float64).copy() for key, val in h.items() if key != "noise"}
+                _composite_vectors(k, hc, self.dim_in, self.composite_semantics)      # validates keys and sizes
+                hc["noise"] = float(np.asarray(h.get("noise", _GPY_DEFAULT_NOISE)).reshape(-1)[0])
+                out.append(hc)
+                continue
             ls = np.asarray(h.get("lengthscale", 1.0), dtype=np.float64).reshape(-1)
             if ls.size == 1:
                 ls = np.full(self.dim_in, float(ls[0]))
@@ -139,6 +194,31 @@ class BatchedGPSSM(object):
             out.append({"lengthscale": ls.copy(), "variance": float(np.asarray(h.get("variance", 1.0)).reshape(-1)[0]),
                         "noise": float(np.asarray(h.get("noise", _GPY_DEFAULT_NOISE)).reshape(-1)[0])})
         return out
+
+    def _model_arrays(self):
+        """(lengthscale (n_s, D) with inf where a composite kernel ignores a dimension, variance (n_s,),
+        prod_linear (n_s, D), linear (n_s, D)) -- the arguments of segp_set_model / segp_set_linear_terms."""
+        ls = np.ones((self.n_s_out, self.dim_in))
+        var = np.ones(self.n_s_out)
+        pl = np.zeros((self.n_s_out, self.dim_in))
+        lin = np.zeros((self.n_s_out, self.dim_in))
+        for d, (k, h) in enumerate(zip(self.kern_types, self.hyp)):
+            if k in _lib.COMPOSITE_KERNELS:
+                s, a, v, va = _composite_vectors(k, h, self.dim_in, self.composite_semantics)
+                with np.errstate(divide="ignore"):
+                    ls[d] = 1.0 / s
+                var[d], pl[d], lin[d] = va, a, v
+            else:
+                ls[d], var[d] = h["lengthscale"], h["variance"]
+        return ls, var, pl, lin
+
+    def _upload(self, x_h, y_h):
+        ls, var, pl, lin = (_lib.host_f64(v) for v in self._model_arrays())
+        noise = _lib.host_f64(self.total_noise())
+        _lib.check(self._lib.segp_set_model(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
+                                            _lib.dbl_ptr(ls), _lib.dbl_ptr(var), _lib.dbl_ptr(noise)))
+        if self.has_composite:
+            _lib.check(self._lib.segp_set_linear_terms(self._handle, _lib.dbl_ptr(pl), _lib.dbl_ptr(lin)))
 
     def total_noise(self):
         """Diagonal term added to K per output dimension: Gaussian noise + noise_diag
@@ -164,12 +244,8 @@ class BatchedGPSSM(object):
             raise ValueError("X must be N x {}".format(self.dim_in))
         if y_h.ndim != 2 or y_h.shape != (x_h.shape[0], self.n_s_out):
             raise ValueError("y must be N x {}".format(self.n_s_out))
-        ls = _lib.host_f64(np.stack([h["lengthscale"] for h in self.hyp]))
-        var = _lib.host_f64([h["variance"] for h in self.hyp])
-        noise = _lib.host_f64(self.total_noise())
         self.gp_trained = False
-        _lib.check(self._lib.segp_set_model(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
-                                            _lib.dbl_ptr(ls), _lib.dbl_ptr(var), _lib.dbl_ptr(noise)))
+        self._upload(x_h, y_h)
         self.x_train = x_h
         self.y_train = y_h
         self.z = x_h
@@ -208,11 +284,7 @@ class BatchedGPSSM(object):
         """Upload data + hyper-parameters without factorising (non-root ranks before the broadcast)."""
         x_h = _lib.host_f64(X)
         y_h = _lib.host_f64(y)
-        ls = _lib.host_f64(np.stack([h["lengthscale"] for h in self.hyp]))
-        var = _lib.host_f64([h["variance"] for h in self.hyp])
-        noise = _lib.host_f64(self.total_noise())
-        _lib.check(self._lib.segp_set_model(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
-                                            _lib.dbl_ptr(ls), _lib.dbl_ptr(var), _lib.dbl_ptr(noise)))
+        self._upload(x_h, y_h)
         self.x_train, self.y_train, self.z = x_h, y_h, x_h
         self.gp_trained = False
 
@@ -318,15 +390,65 @@ class BatchedGPSSM(object):
         return out
 
     def information_gain(self, x=None):
-        """ssm_gpy/gaussian_process.py:621-634: log det(I + K / noise_var) per output dimension, for the
-        training inputs.  log det(I + K/s) = log det(K + s I) - N log s, taken from the factor when the
-        model's own diagonal term equals the Gaussian noise; the small noise_diag/jitter shift is part of
-        the factorised matrix here (documented difference, relative size 1e-5 / noise)."""
-        if x is not None:
-            raise NotImplementedError("information gain for foreign inputs is a 'next' row (SURVEY.md 8 f4)")
-        n = self.x_train.shape[0]
-        tot = self.total_noise()
-        return list(self.log_det_k() - n * np.log(tot))
+        """ssm_gpy/gaussian_process.py:621-634: log det(I + K / noise_var) per output dimension.
+        log det(I + K/s) = log det(K + s I) - n log s, from the Cholesky factor on the device.  The diagonal term s is
+        the one this model factorises (Gaussian noise + noise_diag + GPy jitter, relative shift 1e-5 / noise against
+        the reference's bare Gaussian noise: documented difference).
+
+        x=None (the reference's only working case: it reads the TRAINING kernel matrix ``posterior._K`` whatever x
+        is, :631-632): the training inputs, from the model's own factor.  A foreign x (n, D): K(x, x) is built and
+        factorised on the device with the same hyper-parameters."""
+        if x is None:
+            n = self.x_train.shape[0]
+            return list(self.log_det_k() - n * np.log(self.total_noise()))
+        x = _lib.host_f64(x)
+        if x.ndim != 2 or x.shape[1] != self.dim_in:
+            raise ValueError("x must be n x {}".format(self.dim_in))
+        tmp = BatchedGPSSM(self.n_s_out, self.n_s_in, self.n_u, None, None, None, self.kern_types, self.hyp, False,
+                           None, self.device.index, self.noise_diag, 0, self.composite_semantics)
+        try:
+            tmp.train(x, np.zeros((x.shape[0], self.n_s_out)))
+            return list(tmp.log_det_k() - x.shape[0] * np.log(self.total_noise()))
+        finally:
+            tmp.close()
+
+    def select_maxvar(self, x, m):
+        """Indices (m,) and scores (m,) of the greedy maximum-predicted-variance selection among the rows of x
+        (segp_select_maxvar: partial Cholesky factors on the device, fixed hyper-parameters of this model)."""
+        x = _lib.host_f64(x)
+        if x.ndim != 2 or x.shape[1] != self.dim_in:
+            raise ValueError("x must be n x {}".format(self.dim_in))
+        m = int(m)
+        if m < 1 or m > x.shape[0]:
+            raise ValueError("1 <= m <= n required")
+        ls, var, pl, lin = (_lib.host_f64(v) for v in self._model_arrays())
+        noise = _lib.host_f64(self.total_noise())
+        kern_ids = (ctypes.c_int * self.n_s_out)(*[_lib.KERN_IDS[k] for k in self.kern_types])
+        idx = np.empty(m, dtype=np.int32)
+        score = np.empty(m)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.segp_select_maxvar(
+                self.device.index, x.shape[0], self.n_s_out, self.dim_in, kern_ids, _lib.dbl_ptr(x), _lib.dbl_ptr(ls),
+                _lib.dbl_ptr(var), _lib.dbl_ptr(noise), _lib.dbl_ptr(pl) if self.has_composite else None,
+                _lib.dbl_ptr(lin) if self.has_composite else None, m,
+                idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _lib.dbl_ptr(score),
+                _lib.current_stream(self.device)))
+        return idx.astype(np.int64), score
+
+    def choose_datapoints_maxvar(self, x, y, m, k=10, min_ratio_k=0.25, n_reopt_gp=1):
+        """SimpleGPModel.choose_datapoints_maxvar (ssm_gpy/gaussian_process.py:280-345): pick m of the n data points
+        by the maximum-predicted-variance criterion; returns (x_chosen, y_chosen) in selection order.
+
+        Same criterion and loop (:320-343), run on the device.  Differences, on purpose: the initial set is empty
+        instead of k random representatives of a k-means clustering (:303-318, non-deterministic), and the
+        hyper-parameters stay fixed (the reference re-optimises them on the pool every (m-k)/(n_reopt_gp+1) steps,
+        :327-330; GPy's optimiser is out of scope).  k, min_ratio_k, n_reopt_gp are accepted and ignored."""
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        if x.shape[0] <= m:          # less data than the subset: the whole set (:295-296)
+            return x, y
+        idx, _ = self.select_maxvar(x, m)
+        return x[idx], y[idx]
 
     def to_dict(self):
         """ssm_gpy/gaussian_process.py:177-187 (inv_K is not materialised on this path)."""

@@ -204,6 +204,108 @@ def test_predict_at_training_inputs_identity(se):
     gp.close()
 
 
+@pytest.mark.parametrize("name", ["pend_rbf_mat52", "pend_composite", "cart_mixed"])
+def test_golden_gp_pred_reference(se, golden_dir, name):
+    """Predictive mean / variance the reference's OWN gp_models_utils_casadi.py functions produced (kernels incl. the
+    composite lin_rbf / lin_mat52 ones, gp_pred; oracle/make_golden.golden_gp_pred) against segp_predict, and the
+    mean Jacobian against the oracle's closed form."""
+    from oracle import gp_oracle
+    g = np.load(os.path.join(golden_dir, "gp_pred_reference.npz"))
+    ora, kerns, hyp = gp_oracle.golden_gp_case(g, name)
+    x, y, z = g[name + "/x_train"], g[name + "/y_train"], g[name + "/z"]
+    n_s = y.shape[1]
+    hyp = [dict(h, noise=float(g[name + "/noise"][d]) - 1e-5 - 1e-8) for d, h in enumerate(hyp)]
+    gp = se.BatchedGPSSM(n_s, n_s, x.shape[1] - n_s, x, y, kern_types=kerns, hyp=hyp)
+    assert np.allclose(gp.total_noise(), g[name + "/noise"], rtol=1e-13)
+    mu, var, jac = gp.predict(z, compute_gradients=True)
+    _assert_close(mu, g[name + "/mu"], RTOL, atol_scale=1e-6, what="mean (gate)")
+    _assert_close(var, g[name + "/var"], RTOL, atol_scale=1e-6, what="variance (gate)")
+    _assert_close(mu, g[name + "/mu"], 1e-7, what="mean")
+    _assert_close(var, g[name + "/var"], 1e-6, atol_scale=1e-9, what="variance")
+    _assert_close(jac, ora.jacobian(z), 1e-7, what="jacobian")
+    if any(k.startswith("lin_") for k in kerns):
+        assert gp.get_option("tri_mode_effective") == 0          # composite kernels: float64 contraction only
+        with pytest.raises(NotImplementedError):
+            gp.set_option("tri_mode", 4)
+    gp.close()
+
+
+def test_rollout_composite_kernels_vs_oracle(se):
+    """H-step reachability with the journal configs' kernel structure (lin_mat52 / lin_rbf mixed with plain ones),
+    both definitions of the composite kernels (CasADi: product term on input column 1; GPy object: all columns),
+    against the batch oracle; the two definitions must differ."""
+    from oracle import gp_oracle, reach_oracle
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C3", batch=150, n_train=300, horizon=4)
+    dim = w.n_s + w.n_u
+    rng = np.random.RandomState(4)
+    kerns = ["lin_mat52", "rbf", "lin_rbf", "mat52"]
+    hyp = []
+    for d, k in enumerate(kerns):
+        if k.startswith("lin_"):
+            st = k[4:]
+            hyp.append({"prod.%s.lengthscale" % st: np.array([rng.uniform(0.8, 1.6)]), "prod.%s.variance" % st: 0.9,
+                        "prod.linear.variances": np.array([rng.uniform(0.4, 1.0)]),
+                        "linear.variances": rng.uniform(0.05, 0.3, dim), "noise": 1e-2})
+        else:
+            hyp.append(dict(w.hyp[d]))
+    results = []
+    for sem in ("casadi", "gpy"):
+        gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=kerns, hyp=hyp,
+                             composite_semantics=sem)
+        ls, var, pl, lin = gp_oracle.vectors_from_reference_hyp(kerns, hyp, dim, semantics=sem)
+        ora = gp_oracle.GPOracle(w.x_train, w.y_train, kerns, ls, var, gp.total_noise(), prod_linear=pl, linear=lin)
+        res = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+        p_o, q_o, v_o = reach_oracle.multistep_batch(w.p0, ora, w.k_fb, w.k_ff, w.l_mu, w.l_sigma, None, w.c_safety,
+                                                     w.a, w.b)
+        assert np.all(res.status == 0) and np.all(np.isfinite(q_o))
+        _assert_close(res.var_all, v_o, 1e-6, atol_scale=1e-10, what="variance")
+        _assert_close(res.p_all, p_o, 1e-7, what="p_all")
+        _assert_close(res.q_all, q_o, 1e-6, what="q_all")
+        results.append(res.p_all)
+        gp.close()
+    assert np.max(np.abs(results[0] - results[1])) > 1e-6
+
+
+def test_select_maxvar_and_information_gain(se):
+    """SURVEY 8 f4 on the device: greedy max-predicted-variance selection against the oracle (same index sequence,
+    same scores), choose_datapoints_maxvar's surface, and information_gain for the training set and for foreign
+    inputs against numpy's slogdet."""
+    from oracle import gp_oracle, select_oracle
+    rng = np.random.default_rng(9)
+    n, n_s, n_u = 700, 3, 1
+    dim = n_s + n_u
+    x = rng.uniform(-1, 1, (n, dim))
+    y = rng.standard_normal((n, n_s))
+    kerns = ["rbf", "lin_mat52", "mat52"]
+    hyp = [{"lengthscale": rng.uniform(0.6, 1.5, dim), "variance": 1.1, "noise": 2e-2},
+           {"prod.mat52.lengthscale": np.array([0.8]), "prod.mat52.variance": 0.9,
+            "prod.linear.variances": np.array([0.7]), "linear.variances": rng.uniform(0.05, 0.3, dim), "noise": 1e-2},
+           {"lengthscale": rng.uniform(0.6, 1.5, dim), "variance": 0.6, "noise": 3e-2}]
+    gp = se.BatchedGPSSM(n_s, n_s, n_u, x[:200], y[:200], kern_types=kerns, hyp=hyp)
+    ls, var, pl, lin = gp_oracle.vectors_from_reference_hyp(kerns, hyp, dim)
+    m = 120
+    idx_o, score_o = select_oracle.greedy_maxvar(x, kerns, ls, var, gp.total_noise(), m, pl, lin)
+    idx, score = gp.select_maxvar(x, m)
+    assert np.array_equal(idx, idx_o)
+    _assert_close(score, score_o, 1e-9, what="selection scores")
+    xc, yc = gp.choose_datapoints_maxvar(x, y, m)
+    assert np.array_equal(xc, x[idx_o]) and np.array_equal(yc, y[idx_o])
+    xa, ya = gp.choose_datapoints_maxvar(x[:50], y[:50], 60)           # fewer points than m: everything
+    assert xa.shape == (50, dim) and ya.shape == (50, n_s)
+    with pytest.raises(ValueError):
+        gp.select_maxvar(x, n + 1)
+
+    def ig_ref(xx):
+        ora = gp_oracle.GPOracle(xx, np.zeros((xx.shape[0], n_s)), kerns, ls, var, gp.total_noise(), pl, lin)
+        return np.array([2.0 * np.sum(np.log(np.diag(l))) - xx.shape[0] * np.log(s)
+                         for l, s in zip(ora.chol, gp.total_noise())])
+
+    _assert_close(gp.information_gain(), ig_ref(x[:200]), 1e-9, what="information gain (training set)")
+    _assert_close(gp.information_gain(x[300:520]), ig_ref(x[300:520]), 1e-9, what="information gain (foreign x)")
+    gp.close()
+
+
 # =========================================================================== rollouts vs the batch oracle
 def _rollout_vs_oracle(se, w, t_z_gp=None, q0=None, k_fb_init=None, per_traj_kfb=False, rtol=RTOL_TIGHT):
     from oracle import reach_oracle
@@ -402,8 +504,10 @@ def test_error_mapping_and_status_flags(se):
     xd[7, 1] = np.nan
     with pytest.raises(np.linalg.LinAlgError):
         se.BatchedGPSSM(2, 2, 1, xd, y)
-    with pytest.raises(NotImplementedError):
-        se.BatchedGPSSM(2, 2, 1, x, y, kern_types=["lin_rbf", "rbf"])
+    with pytest.raises(ValueError):          # unknown kernel names, as gaussian_process.py:476-478
+        se.BatchedGPSSM(2, 2, 1, x, y, kern_types=["lin", "rbf"])
+    with pytest.raises(KeyError):            # composite kernels need the reference's prod.* / linear.* hyper-parameters
+        se.BatchedGPSSM(2, 2, 1, x, y, kern_types=["lin_rbf", "rbf"], hyp=[{"lengthscale": 1.0}, {"lengthscale": 1.0}])
     with pytest.raises(ValueError):
         se.BatchedGPSSM(2, 2, 1, x, y, kern_types=["rbf", "nope"])
     gp = se.BatchedGPSSM(2, 2, 1)

@@ -169,23 +169,12 @@ def test_golden_cartpole_batch_oracle(golden_dir):
 GP_GOLDEN_CASES = ("pend_rbf_mat52", "pend_composite", "cart_mixed")
 
 
-def gp_from_gp_golden(g, name):
-    """(GPOracle, kern_types, hyp list in the reference's dict layout) of one case of gp_pred_reference.npz."""
-    kerns = [str(k) for k in g[name + "/kern_types"]]
-    pre = name + "/hyp"
-    hyp = [{k[len(pre) + 2:]: g[k] for k in g.files if k.startswith("%s%d/" % (pre, i))} for i in range(len(kerns))]
-    x = g[name + "/x_train"]
-    ls, var, pl, lin = gp_oracle.vectors_from_reference_hyp(kerns, hyp, x.shape[1])
-    ora = gp_oracle.GPOracle(x, g[name + "/y_train"], kerns, ls, var, g[name + "/noise"], prod_linear=pl, linear=lin)
-    return ora, kerns, hyp
-
-
 @pytest.mark.parametrize("name", GP_GOLDEN_CASES)
 def test_golden_gp_pred_reference(golden_dir, name):
     """Kernel rows, k(z,z), predictive mean and variance produced by the reference's gp_models_utils_casadi.py
     (_k_rbf/_k_mat52/_k_lin_rbf/_k_lin_mat52 + gp_pred) -- the oracle must reproduce them."""
     g = np.load(os.path.join(golden_dir, "gp_pred_reference.npz"))
-    ora, kerns, _ = gp_from_gp_golden(g, name)
+    ora, kerns, _ = gp_oracle.golden_gp_case(g, name)
     z = g[name + "/z"]
     for d in range(len(kerns)):
         assert np.allclose(ora.kstar(d, z), g[name + "/kstar"][d], rtol=1e-12, atol=1e-14)
@@ -227,6 +216,30 @@ def test_gp_oracle_equals_reference_gp_utils_live():
         m_o, v_o = ora.predict(z, form="explicit")
         assert np.allclose(m_o[:, d], np.asarray(m_r).reshape(-1), rtol=1e-11, atol=1e-13)
         assert np.allclose(v_o[:, d], np.asarray(v_r).reshape(-1), rtol=1e-9, atol=1e-13)
+
+
+# ------------------------------------------------------------------ greedy max-variance selection
+def test_select_oracle_incremental_equals_brute_force():
+    """The incremental partial-Cholesky form picks, at every step, the arg-max of the GP predictive variance given
+    the points chosen so far (the criterion of choose_datapoints_maxvar, ssm_gpy/gaussian_process.py:332-333),
+    computed by a fresh Cholesky solve."""
+    from oracle import select_oracle
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, (150, 3))
+    for kerns, pl, lin in ((["rbf", "mat52"], None, None),
+                           (["lin_rbf", "mat52"], np.array([[0, .8, 0], [0, 0, 0]]), np.array([[.1, .2, .3], [0, 0, 0]]))):
+        ls = rng.uniform(0.5, 1.5, (2, 3))
+        if pl is not None:
+            ls[0] = [np.inf, 0.9, np.inf]
+        var, noise = [1.2, 0.7], [1e-2, 2e-2]
+        idx, score = select_oracle.greedy_maxvar(x, kerns, ls, var, noise, 30, pl, lin)
+        assert len(set(idx.tolist())) == 30
+        for t in (0, 1, 2, 7, 29):
+            s = select_oracle.brute_force_scores(x, kerns, ls, var, noise, idx[:t], pl, lin)
+            s[idx[:t]] = -np.inf
+            assert int(np.argmax(s)) == idx[t]
+            assert np.isclose(s[idx[t]], score[t], rtol=1e-8)
+        assert np.all(np.diff(score) <= 1e-12)          # greedy scores never increase
 
 
 # ------------------------------------------------------------------ live against the reference (build container only)
