@@ -227,9 +227,17 @@ typedef struct segp_score_params {
     const double* h_wx;        /* [n_s x n_s], quadratic cost                                                      */
     const double* h_wu;        /* [n_u x n_u]                                                                      */
     const double* h_x_ref;     /* [n_s] or NULL (origin)                                                           */
+    int layout;                /* SEGP_SCORE_SAFEMPC (0, everything above) or SEGP_SCORE_CAUTIOUS                  */
 } segp_score_params;
 
-/* Number of constraint values per candidate: (has_ctrl ? 2 n_u H : 0) + (H-1) m_obs + m_safe. */
+/* constraint layouts */
+#define SEGP_SCORE_SAFEMPC 0  /* SimpleSafeMPC.generate_safety_constraints, safempc_simple.py:317-392                */
+#define SEGP_SCORE_CAUTIOUS 1 /* CautiousMPC.generate_safety_constraints, cautious_mpc.py:337-395: the obstacle polytope
+                                 on ALL H states, no terminal set (m_safe ignored), and c_safety (beta_safety) on the
+                                 support term of the control constraints too (_generate_control_constraint :397-442)  */
+
+/* Number of constraint values per candidate: (has_ctrl ? 2 n_u H : 0) + (H-1) m_obs + m_safe
+ * (cautious layout: (has_ctrl ? 2 n_u H : 0) + H m_obs). */
 int segp_score_num_constraints(int horizon, int n_u, const segp_score_params* params);
 
 /* Constraint values, feasibility and cost of n_batch rolled-out candidates (outputs of segp_multistep).

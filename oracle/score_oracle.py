@@ -50,6 +50,30 @@ def constraints_one(p_all, q_all, k_ff, k_fb, ctrl_bounds, h_mat_obs, h_obs, h_m
     return np.concatenate(g)
 
 
+def constraints_cautious_one(p_all, q_all, k_ff, k_fb, ctrl_bounds, h_mat_obs, h_obs, beta_safety, dist_fn=None):
+    """CautiousMPC.generate_safety_constraints (cautious_mpc.py:337-395) with _generate_control_constraint (:397-442):
+    u_0 bounds; per step i = 0..H-2 the control distances of (k_ff[i+1], K_fb[i] Sigma[i] K_fb[i]^T) with
+    c_safety = beta_safety; then the obstacle distances of ALL H states with c_safety = beta_safety.  No terminal set.
+    p_all (H,n_s) means, q_all (H,n_s,n_s) covariances, k_ff (H,n_u) with row 0 = u_0, k_fb (H-1,n_u,n_s)."""
+    dist = dist_fn or reach_oracle.lin_ellipsoid_safety_distance
+    hor = p_all.shape[0]
+    n_u = k_ff.shape[1]
+    g = []
+    if ctrl_bounds is not None:
+        u_min, u_max = ctrl_bounds[:, 0], ctrl_bounds[:, 1]
+        g.append(k_ff[0] - u_max)
+        g.append(u_min - k_ff[0])
+        h_vec = np.vstack((u_max[:, None], -u_min[:, None]))
+        h_mat = np.vstack((np.eye(n_u), -np.eye(n_u)))
+        for i in range(hor - 1):
+            q_u = k_fb[i] @ q_all[i] @ k_fb[i].T
+            g.append(np.asarray(dist(k_ff[i + 1][:, None], q_u, h_mat, h_vec, beta_safety)).reshape(-1))
+    if h_mat_obs is not None:
+        for i in range(hor):
+            g.append(np.asarray(dist(p_all[i][:, None], q_all[i], h_mat_obs, h_obs, beta_safety)).reshape(-1))
+    return np.concatenate(g) if g else np.zeros(0)
+
+
 def exploration_cost_one(var_all, eps_noise=0.0):
     return -float(np.sum(np.sqrt(np.sum(var_all + eps_noise, axis=1))))
 

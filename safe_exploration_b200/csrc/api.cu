@@ -1151,6 +1151,12 @@ static int fill_score_params(ScoreParams* sp, const segp_score_params* prm, int 
     sp->eps_constraints = prm->eps_constraints;
     sp->eps_noise = prm->eps_noise;
     sp->cost_type = prm->cost_type;
+    if (prm->layout != SEGP_SCORE_SAFEMPC && prm->layout != SEGP_SCORE_CAUTIOUS) {
+        set_error("score params: unknown constraint layout %d", prm->layout);
+        return SEGP_ERR_INVALID;
+    }
+    sp->layout = prm->layout;
+    if (sp->layout == SEGP_SCORE_CAUTIOUS) sp->m_safe = 0;
     if (prm->cost_type == SEGP_COST_QUADRATIC) {
         if (prm->h_wx == nullptr || prm->h_wu == nullptr) {
             set_error("score params: the quadratic cost needs h_wx and h_wu");
@@ -1168,7 +1174,9 @@ static int fill_score_params(ScoreParams* sp, const segp_score_params* prm, int 
 
 int segp_score_num_constraints(int horizon, int n_u, const segp_score_params* params) {
     if (params == nullptr || horizon < 1) return -1;
-    return (params->h_u_min != nullptr ? 2 * n_u * horizon : 0) + (horizon - 1) * params->m_obs + params->m_safe;
+    const int ctrl = params->h_u_min != nullptr ? 2 * n_u * horizon : 0;
+    if (params->layout == SEGP_SCORE_CAUTIOUS) return ctrl + horizon * params->m_obs;
+    return ctrl + (horizon - 1) * params->m_obs + params->m_safe;
 }
 
 int segp_score_rollouts(int device, long n_batch, int horizon, int n_s, int n_u, const double* d_p_all,

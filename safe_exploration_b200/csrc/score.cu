@@ -34,6 +34,10 @@ __global__ void score_kernel(const ScoreArgs a) {
         viol = fmax(viol, v);
         if (!isfinite(v)) finite = false;
     };
+    // CautiousMPC (cautious_mpc.py:337-442): beta_safety also scales the support term of the control constraints, the
+    // obstacle polytope applies to all H states and there is no terminal set
+    const bool cautious = sp.layout == SEGP_SCORE_CAUTIOUS;
+    const double c_ctrl = cautious ? sp.c_safety : 1.0;
     // ---- control constraints
     if (sp.has_ctrl) {
         for (int j = 0; j < n_u; ++j) emit(kff[j] - sp.u_max[j]);
@@ -52,8 +56,8 @@ __global__ void score_kernel(const ScoreArgs a) {
                 }
                 sd[j] = sqrt(acc);
             }
-            for (int j = 0; j < n_u; ++j) emit(u[j] + sd[j] - sp.u_max[j]);
-            for (int j = 0; j < n_u; ++j) emit(-u[j] + sd[j] + sp.u_min[j]);
+            for (int j = 0; j < n_u; ++j) emit(u[j] + c_ctrl * sd[j] - sp.u_max[j]);
+            for (int j = 0; j < n_u; ++j) emit(-u[j] + c_ctrl * sd[j] + sp.u_min[j]);
         }
     }
     // ---- polytope constraints on the state ellipsoids
@@ -70,9 +74,11 @@ __global__ void score_kernel(const ScoreArgs a) {
             emit(hp + sp.c_safety * sqrt(hqh) - hvec[k]);
         }
     };
-    for (int i = 0; i + 1 < hor; ++i)
+    for (int i = 0; i + (cautious ? 0 : 1) < hor; ++i)
         polytope(p_all + (long)i * n_s, q_all + (long)i * n_s * n_s, sp.h_mat_obs, sp.h_obs, sp.m_obs);
-    polytope(p_all + (long)(hor - 1) * n_s, q_all + (long)(hor - 1) * n_s * n_s, sp.h_mat_safe, sp.h_safe, sp.m_safe);
+    if (!cautious)
+        polytope(p_all + (long)(hor - 1) * n_s, q_all + (long)(hor - 1) * n_s * n_s, sp.h_mat_safe, sp.h_safe,
+                 sp.m_safe);
     // ---- cost
     double cost = 0.0;
     if (sp.cost_type == SEGP_COST_EXPLORATION) {

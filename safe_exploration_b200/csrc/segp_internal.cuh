@@ -210,7 +210,7 @@ struct ScoreParams {
     double h_mat_safe[SEGP_MAX_CONSTR * SEGP_MAX_NS], h_safe[SEGP_MAX_CONSTR];
     double wx[SEGP_MAX_NS * SEGP_MAX_NS], wu[SEGP_MAX_NU * SEGP_MAX_NU], x_ref[SEGP_MAX_NS];
     double c_safety, eps_constraints, eps_noise;
-    int has_ctrl, m_obs, m_safe, cost_type;
+    int has_ctrl, m_obs, m_safe, cost_type, layout;
 };
 struct ScoreArgs {
     const double* p_all;      // [B][H][n_s]

@@ -39,7 +39,7 @@ DEFAULT_OPT_ENV = {'ctrl_bounds': None, 'safe_policy': None, 'lin_model': None, 
 
 
 def _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, cost, wx, wu, x_ref,
-                  eps_constraints, eps_noise, c_safety):
+                  eps_constraints, eps_noise, c_safety, layout="safempc"):
     keep = []
 
     def hp(x, shape):
@@ -54,21 +54,25 @@ def _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, c
         cb = _lib.host_f64(ctrl_bounds, (n_u, 2))
         u_min, u_max = hp(cb[:, 0].copy(), (n_u,)), hp(cb[:, 1].copy(), (n_u,))
     m_obs = 0 if h_mat_obs is None else int(np.shape(h_mat_obs)[0])
-    m_safe = int(np.shape(h_mat_safe)[0])
+    if layout not in ("safempc", "cautious"):
+        raise ValueError("layout must be 'safempc' or 'cautious'")
+    m_safe = int(np.shape(h_mat_safe)[0]) if (layout == "safempc" and h_mat_safe is not None) else 0
     if cost not in ("exploration", "quadratic"):
         raise ValueError("cost must be 'exploration' or 'quadratic'")
     prm = _lib.ScoreParams(
         u_min, u_max, m_obs, hp(h_mat_obs, (m_obs, n_s)) if m_obs else None, hp(h_obs, (m_obs,)) if m_obs else None,
-        m_safe, hp(h_mat_safe, (m_safe, n_s)), hp(h_safe, (m_safe,)), float(c_safety), float(eps_constraints),
+        m_safe, hp(h_mat_safe, (m_safe, n_s)) if m_safe else None, hp(h_safe, (m_safe,)) if m_safe else None,
+        float(c_safety), float(eps_constraints),
         _lib.COST_EXPLORATION if cost == "exploration" else _lib.COST_QUADRATIC, float(eps_noise),
         hp(wx, (n_s, n_s)) if cost == "quadratic" else None, hp(wu, (n_u, n_u)) if cost == "quadratic" else None,
-        hp(x_ref, (n_s,)) if (cost == "quadratic" and x_ref is not None) else None)
+        hp(x_ref, (n_s,)) if (cost == "quadratic" and x_ref is not None) else None,
+        _lib.SCORE_CAUTIOUS if layout == "cautious" else _lib.SCORE_SAFEMPC)
     return prm, keep
 
 
 def score_rollouts(res, k_ff, k_fb, h_mat_safe, h_safe, ctrl_bounds=None, h_mat_obs=None, h_obs=None,
                    cost="exploration", wx=None, wu=None, x_ref=None, eps_constraints=1e-5, eps_noise=0.0,
-                   c_safety=1.0, want_g=False):
+                   c_safety=1.0, want_g=False, layout="safempc"):
     """Score the candidates of a RolloutResult (device tensors or NumPy arrays; the result has the same kind).
 
     res        RolloutResult of ``rollout`` for k_ff (B,H,n_u) and k_fb ((H-1),n_u,n_s) or (B,H-1,n_u,n_s)
@@ -76,6 +80,9 @@ def score_rollouts(res, k_ff, k_fb, h_mat_safe, h_safe, ctrl_bounds=None, h_mat_
     a candidate is feasible iff every constraint value is < eps_constraints and its rollout status is 0.
     Constraint order (safempc_simple.py:317-392): [u_0 - u_max, u_min - u_0], then per step i = 0..H-2 the 2 n_u
     control distances, then per step i = 0..H-2 the m_obs obstacle distances, then the m_safe terminal distances.
+    layout="cautious" (CautiousMPC.generate_safety_constraints, cautious_mpc.py:337-442): the same control constraints
+    with c_safety on their support term, then the obstacle distances of ALL H states; no terminal set
+    (h_mat_safe / h_safe may be None).  q_all then holds the propagated covariances.
     """
     torch = _lib.require_cuda()
     lib = _lib.load()
@@ -100,7 +107,7 @@ def score_rollouts(res, k_ff, k_fb, h_mat_safe, h_safe, ctrl_bounds=None, h_mat_
     if cost == "exploration" and var_all is None:
         raise ValueError("the exploration cost needs the predictive variances (rollout(..., want_var=True))")
     prm, keep = _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, cost, wx, wu, x_ref,
-                              eps_constraints, eps_noise, c_safety)
+                              eps_constraints, eps_noise, c_safety, layout)
     n_g = lib.segp_score_num_constraints(hor, n_u, ctypes.byref(prm))
     cost_d = torch.empty((bsz,), dtype=torch.float64, device=dev)
     feas_d = torch.empty((bsz,), dtype=torch.int32, device=dev)

@@ -166,3 +166,83 @@ def test_sampling_mpc_update_model_subtracts_the_prior(se):
     mpc.update_model(x, y, replace_old=True)
     assert gp.x_train.shape == (50, w.n_s + w.n_u) and np.allclose(gp.y_train, 0.01)
     gp.close()
+
+
+# ---------------------------------------------------------------------------------- Cautious MPC
+def test_cautious_constraint_layout_matches_oracle(se):
+    """CautiousMPC.generate_safety_constraints (cautious_mpc.py:337-442) on propagated Gaussian covariances: the
+    device assembly (layout="cautious") against the per-candidate oracle, value by value and in the same order."""
+    from oracle import score_oracle
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C3", batch=130, n_train=250, horizon=5)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    zeros = np.zeros(w.n_s)
+    k_fb1 = w.k_fb[0]
+    k_fb_all = np.tile(k_fb1[None], (w.k_ff.shape[1] - 1, 1, 1))
+    res = se.rollout(gp, w.p0, w.k_ff, k_fb_all, zeros, zeros, None, None, 1.0, w.a, w.b, None, True, 2)
+    rng = np.random.default_rng(2)
+    h_obs = rng.standard_normal((3, w.n_s))
+    beta = 2.2
+    g0 = np.array([score_oracle.constraints_cautious_one(res.p_all[i], res.q_all[i], w.k_ff[i], k_fb_all,
+                                                          np.zeros((w.n_u, 2)), h_obs, np.zeros((3, 1)), beta)
+                   for i in range(w.k_ff.shape[0])])
+    n_c = 2 * w.n_u * w.k_ff.shape[1]
+    u_abs = float(np.quantile(g0[:, :n_c].max(axis=1), 0.8))
+    cb = np.stack((-u_abs * np.ones(w.n_u), u_abs * np.ones(w.n_u)), axis=1)
+    h_obs_v = float(np.quantile(g0[:, n_c:].max(axis=1), 0.8)) * np.ones((3, 1))
+    sc = se.score_rollouts(res, w.k_ff, k_fb_all, None, None, cb, h_obs, h_obs_v, cost="quadratic", wx=np.eye(w.n_s),
+                           wu=np.eye(w.n_u), eps_constraints=1e-6, c_safety=beta, want_g=True, layout="cautious")
+    g_o = np.array([score_oracle.constraints_cautious_one(res.p_all[i], res.q_all[i], w.k_ff[i], k_fb_all, cb, h_obs,
+                                                           h_obs_v, beta) for i in range(w.k_ff.shape[0])])
+    assert sc.g.shape == g_o.shape == (w.k_ff.shape[0], n_c + 3 * w.k_ff.shape[1])
+    assert np.allclose(sc.g, g_o, rtol=1e-12, atol=1e-13)
+    f_o = g_o.max(axis=1) < 1e-6
+    assert np.array_equal(sc.feasible.astype(bool), f_o) and 0 < f_o.sum() < f_o.size
+    gp.close()
+
+
+def _pendulum_cautious(se, obs_bound=0.6, **kw):
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C2", batch=8, n_train=200, horizon=5)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    env = {"l_mu": w.l_mu, "l_sigma": w.l_sigma, "h_mat_safe": w.h_mat, "h_safe": 0.5 * np.ones((2 * w.n_s, 1)),
+           "lin_model": (w.a, w.b), "ctrl_bounds": np.array([[-1.0, 1.0]]), "h_mat_obs": w.h_mat,
+           "h_obs": obs_bound * np.ones((2 * w.n_s, 1))}
+    mpc = se.SamplingCautiousMPC(5, gp, env, 2.0, perf_trajectory=kw.pop("perf_trajectory", "mean_equivalent"),
+                                 k_fb=w.k_fb[0], n_samples=512, n_iter=2, n_elite=32, wx_cost=np.eye(w.n_s),
+                                 wu_cost=0.1 * np.eye(w.n_u), **kw)
+    return w, gp, mpc
+
+
+@pytest.mark.parametrize("perf", ["mean_equivalent", "taylor"])
+def test_sampling_cautious_mpc_feasible_action_and_fallback(se, perf):
+    from oracle import score_oracle
+    w, gp, mpc = _pendulum_cautious(se, perf_trajectory=perf)
+    with pytest.raises(AssertionError):
+        mpc.get_action(np.zeros(w.n_s))                       # solver not initialised (cautious_mpc.py:223)
+    mpc.init_solver()
+    x0 = np.array([0.03, -0.02])
+    u, code, mu_all, sigma_all, k_ff, k_fb = mpc.get_action(x0, verbose=True)
+    assert code == 0 and u.shape == (w.n_u,) and mpc.n_fail == 0
+    assert mu_all.shape == (6, w.n_s) and np.allclose(mu_all[0], x0) and sigma_all.shape == (5, w.n_s, w.n_s)
+    # the returned plan really satisfies the reference's constraints (oracle, value by value)
+    g = score_oracle.constraints_cautious_one(mu_all[1:], sigma_all, k_ff, np.tile(k_fb[None], (4, 1, 1)),
+                                              mpc.ctrl_bounds, mpc.h_mat_obs, mpc.h_obs, mpc.beta_safety)
+    assert np.all(g < 1e-6)
+    m2, s2, v2 = mpc.f_multistep_eval(x0, k_ff, k_fb)
+    assert np.allclose(m2, mu_all[1:]) and np.allclose(s2, sigma_all)
+    # a custom cost with the reference's argument list picks a different plan
+    mpc.init_solver(lambda mu_0, u_0, mu, sig, kff, kfb, sg: np.sum((u_0 - 0.3) ** 2, axis=1))
+    u_c, code_c = mpc.get_action(x0)
+    assert code_c == 0 and abs(u_c[0] - 0.3) < 0.1
+    # infeasible problem: shifted old plan (exit code 1) T-1 times, then the feedback law (exit code 3)
+    old = mpc.k_ff_old.copy()
+    mpc.h_obs = -1.0 * np.ones_like(mpc.h_obs)
+    codes = []
+    for k in range(6):
+        u_k, code_k = mpc.get_action(x0)
+        codes.append(code_k)
+        if code_k == 1:
+            assert np.allclose(u_k, old[mpc.n_fail])
+    assert codes == [1, 1, 1, 1, 3, 3] and np.allclose(u_k, mpc.k_fb @ x0)
+    gp.close()
