@@ -209,6 +209,8 @@ def run_product(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     t_setup = time.perf_counter() - t_setup0
     gp.set_option("overlap", 1 if args.overlap else 0)
+    if args.ksplit > 0:
+        gp.set_option("ksplit", args.ksplit)
 
     # ---------------- device-resident inputs (the `value` arm)
     p0_d = torch.as_tensor(w.p0, device=dev)
@@ -419,8 +421,11 @@ def main():
                     help="two-stream half-chunk pipeline instead of the serial kstar -> tri -> ellipsoid schedule "
                          "(bit-identical; measured no faster, see DESIGN.md)")
     ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4],
-                    help="variance contraction pipe: -1 auto (2 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
-                         "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs")
+                    help="variance contraction pipe: -1 auto (4 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
+                         "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs, "
+                         "4 single-CTA MMAs over merged K* planes, W multicast over a CTA pair")
+    ap.add_argument("--ksplit", type=int, default=0,
+                    help="splits of the training points in the K* kernel (0 = automatic); tuning experiments")
     ap.add_argument("--redundant-factor", action="store_true",
                     help="factorise on every rank instead of broadcasting the factor")
     args = ap.parse_args()
