@@ -123,7 +123,7 @@ def cpu_baseline(w, seconds_target=15.0):
     while True:
         k_ff = w.k_ff[:sample]
         t0 = time.perf_counter()
-        reach_oracle.multistep_batch(w.p0, ora, w.k_fb, k_ff, w.l_mu, w.l_sigma, None, w.c_safety, w.a, w.b)
+        out = reach_oracle.multistep_batch(w.p0, ora, w.k_fb, k_ff, w.l_mu, w.l_sigma, None, w.c_safety, w.a, w.b)
         dt = time.perf_counter() - t0
         t_used += dt
         best = (sample, dt)
@@ -132,7 +132,23 @@ def cpu_baseline(w, seconds_target=15.0):
         sample *= 4
     return {"value": best[0] / best[1], "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "{} of the workload's rollouts (H={}), vectorised float64 NumPy/SciPy oracle "
-                      "(Cholesky form), {:.2f} s".format(best[0], w.horizon, best[1])}
+                      "(Cholesky form), {:.2f} s".format(best[0], w.horizon, best[1])}, out
+
+
+def parity_against_oracle(res, oracle_out):
+    """The oracle rollouts of the cpu_baseline leg are the FIRST candidates of rank 0's shard: compare the GPU result
+    of the timed arm with them at the workload's full model size (rtol gate of BASELINE.json: 1e-4)."""
+    p_o, q_o, v_o = oracle_out
+    n = p_o.shape[0]
+
+    def err(got, want):
+        got = got[:n].cpu().numpy()
+        scale = 1e-9 * max(1.0, float(np.max(np.abs(want))))
+        return float(np.max(np.abs(got - want) / (np.abs(want) + scale / 1e-4)))
+
+    e = {"p_all": err(res.p_all, p_o), "q_all": err(res.q_all, q_o), "var_all": err(res.var_all, v_o)}
+    return {"checked_rollouts": int(n), "against": "float64 oracle (oracle/reach_oracle.multistep_batch) at full model size",
+            "max_rel_err": e, "rtol_gate": 1e-4, "ok": bool(max(e.values()) < 1e-4)}
 
 
 def run_reference(args, rank, world):
@@ -310,7 +326,7 @@ def run_product(args, rank, world, local_rank):
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     share = (tri_ns * 1e-6) / ms if ms > 0 else None
     mode = gp.get_option("tri_mode_effective")
-    if mode in (1, 2, 3, 4):
+    if mode in (1, 2, 3, 4, 5):
         # tri_i8: 15 int8 digit-plane products per algorithmic multiply-add, exact int32 accumulation in TMEM.
         # `achieved` is ALGORITHMIC flop/s (n_s N^2 B per launch); `peak` is the measured bf16 figure of
         # MEASURED_PEAKS.json, so `frac` is the algorithmic fraction of the bf16 tensor peak: error-free splitting
@@ -330,7 +346,8 @@ def run_product(args, rank, world, local_rank):
         executed = 2.0 * 15 * w.n_s * (128 * 128 * kblocks) * panels * 96
         i8_96, i8_256 = _i8_peak(gp, local_rank, 96), _i8_peak(gp, local_rank, 256)
         pipe_tops = executed / tri_avg_s / 1e12 if tri_avg_s > 0 else None
-        roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 2: "tri_i8x2_kernel", 3: "tri_i8x2p_kernel", 4: "tri_i8m_kernel"}[mode],
+        roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 2: "tri_i8x2_kernel", 3: "tri_i8x2p_kernel", 4: "tri_i8m_kernel",
+                                                5: "tri_i8mp_kernel"}[mode],
                     "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, " + ("cta_group::2 M=256" if mode in (2, 3) else "M=128")
                             + " N=96 K=32, int32 accumulators in TMEM); "
                             "float64-grade result from 5 x 5 balanced base-254 digit planes, 15 products",
@@ -361,7 +378,9 @@ def run_product(args, rank, world, local_rank):
                          2: "int8 digit planes on tcgen05 (CTA pairs), float64 recombination",
                          3: "int8 digit planes on tcgen05 (persistent CTA pairs), float64 recombination",
                          4: "int8 digit planes on tcgen05 (single-CTA MMAs, W multicast over CTA pairs), float64 "
-                            "recombination"}[mode],
+                            "recombination",
+                         5: "int8 digit planes on tcgen05 (persistent clusters over folded tiles, single-CTA MMAs, W "
+                            "multicast over CTA pairs), float64 recombination"}[mode],
             "config": _config_dict(args, w, b_per_gpu, world, "device-resident"),
             "onestep_calls_per_sec": value * w.horizon,
             "algorithmic_tflops": value * w.horizon * workloads.flop_per_step(w.n_s, w.n_u, w.n_train) / 1e12,
@@ -371,11 +390,12 @@ def run_product(args, rank, world, local_rank):
                     "bit_identical_to_device_arm": same},
             "gpu_launches": int(launches), "roofline": roofline,
             "schedule": ("two half-chunks software-pipelined over two streams (K*/ellipsoid kernels of one half under "
-                         "the contraction of the other)" if gp.get_option("overlap") and mode == 4 else "serial"),
+                         "the contraction of the other)" if gp.get_option("overlap") and mode in (4, 5) else "serial"),
             "clocks": sampler.summary(t_wall0, t_wall1),
             "setup_s": t_setup, "bad_status": status_bad, "all_finite": finite}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(w, args.cpu_seconds)
+        line["cpu_baseline"], oracle_out = cpu_baseline(w, args.cpu_seconds)
+        line["parity"] = parity_against_oracle(res, oracle_out)
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
@@ -420,10 +440,11 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="two-stream half-chunk pipeline instead of the serial kstar -> tri -> ellipsoid schedule "
                          "(bit-identical; measured no faster, see DESIGN.md)")
-    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4],
+    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4, 5],
                     help="variance contraction pipe: -1 auto (4 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
                          "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs, "
-                         "4 single-CTA MMAs over merged K* planes, W multicast over a CTA pair")
+                         "4 single-CTA MMAs over merged K* planes, W multicast over a CTA pair, 5 the same as a persistent "
+                         "kernel over folded (equal-length) tiles")
     ap.add_argument("--ksplit", type=int, default=0,
                     help="splits of the training points in the K* kernel (0 = automatic); tuning experiments")
     ap.add_argument("--redundant-factor", action="store_true",

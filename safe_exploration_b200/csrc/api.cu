@@ -331,7 +331,16 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0) {
         t.zero_a = m->i8zero;
         t.ablate = (int)m->opt_i8_ablate;
         t.prof = m->i8_prof;
-        SEGP_CHECK(m->ws_mode == 4   ? launch_tri_i8m(t, m->n_s, st)
+        // Automatic mode: the persistent folded kernel where per-tile overhead matters (short tiles, enough of them to
+        // balance a static schedule: +5 % at C3), the one-cluster-per-tile kernel otherwise (C4: power-capped, +1 %
+        // at best; C5: the persistent order runs 13 % slower; C2: too few tiles) -- profiles/round1/persistent_tri_i8mp.txt
+        bool persistent = m->ws_mode == 5;
+        if (m->ws_mode == 4 && m->opt_tri_mode < 0 && t.panel0 == 0) {
+            const long ntiles = (long)m->n_s * ((m->nblk + 1) / 2) * ((t.npanels + 1) / 2);
+            persistent = m->nblk <= 32 && ntiles >= 4 * 74;
+        }
+        SEGP_CHECK(persistent        ? launch_tri_i8mp(t, m->n_s, st)
+                   : m->ws_mode == 4 ? launch_tri_i8m(t, m->n_s, st)
                    : m->ws_mode == 3 ? launch_tri_i8x2p(t, m->n_s, st)
                    : m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st)
                                      : launch_tri_i8(t, m->n_s, st));
@@ -855,7 +864,7 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         // low-priority stream (FP64 pipe).  Within a half the order kstar -> tri -> ellipsoid -> kstar(t+1) is kept by
         // events; the halves touch disjoint panel ranges of the workspace.  Same kernels, same arithmetic, same
         // fixed-order reductions: results are bit-identical to the serial schedule.
-        const bool pipelined = m->ws_mode == 4 && m->opt_overlap != 0 && npanels >= 48 && m->n_pad >= 1024;
+        const bool pipelined = (m->ws_mode == 4 || m->ws_mode == 5) && m->opt_overlap != 0 && npanels >= 48 && m->n_pad >= 1024;
         if (!pipelined) {
             cudaStream_t s1 = forked ? m->s_lo : st;
             for (int t = 0; t < horizon; ++t) {
@@ -1410,7 +1419,7 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_ksplit = value;
         return SEGP_OK;
     }
-    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 4) {
+    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 5) {
         if (value >= 1 && m->has_composite) {
             set_error("tri_mode=%ld (int8 tcgen05) is not available with composite (lin_*) kernels: float64 only", value);
             return SEGP_ERR_UNSUPPORTED;

@@ -133,6 +133,8 @@ int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);
 int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st);
 // single-CTA MMAs, two CTAs per cluster share one block row of W through multicast bulk copies
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st);
+// persistent tri_i8m: one resident cluster per TPC walks a static list of folded (equal-length) tiles
+int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st);
 // persistent CTA-pair variant: one resident pair per TPC walks a static tile list
 int launch_tri_i8x2p(const TriI8Args& a, int n_s, cudaStream_t st);
 int tri_i8_init();

@@ -1052,6 +1052,226 @@ int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
     return SEGP_OK;
 }
 
+// =========================================================================================== tri_i8mp (persistent tri_i8m)
+// Same tiles, same arithmetic, same barriers as tri_i8m, but ONE resident cluster per TPC walks a static list of
+// FOLDED tiles: a tile is (d, panel pair, fold f) and covers block rows nblk-1-f and f one after the other, so every
+// tile holds exactly 2 (nblk + 1) k-blocks and a static round-robin assignment is balanced (the persistent pair
+// kernel tri_i8x2p lost 8 % to its unequal tiles).  TMEM allocation, barrier initialisation and the cluster
+// handshakes happen once per kernel; the producer runs ahead into the next block row while the epilogue of the
+// current one drains TMEM, so the pipeline refill overlaps the (exposed) epilogue.  One more barrier: tmem_empty
+// (12 arrivals, one per epilogue warp) gates the first MMA of the next block row.  What this buys is per-tile
+// overhead: most at small N (C3: nblk = 16), little at C4/C5 where the board's power cap sets the pace.
+struct MpSub {
+    int d, bi, panel, panel_ld;
+    bool valid;
+};
+// valid tile v of [0, n_s * nfold * npairs) -> (d, fold, panel pair); order: d, panel group of 12 pairs (its K*
+// planes stay L2-resident), fold, pair -- the clusters of one round work on neighbouring block rows of one group.
+__device__ __forceinline__ void mp_decode(long v, int nfold, int npairs, int& d, int& f, int& pair) {
+    constexpr int PG2 = I8_PANEL_GROUP / 2;
+    const long per_d = (long)nfold * npairs;
+    d = (int)(v / per_d);
+    const int r = (int)(v % per_d);
+    const int full_groups = npairs / PG2;
+    const int full = full_groups * nfold * PG2;
+    if (r < full) {
+        const int pg = r / (nfold * PG2);
+        const int q = r % (nfold * PG2);
+        f = q / PG2;
+        pair = pg * PG2 + q % PG2;
+    } else {
+        const int rem = npairs - full_groups * PG2;
+        const int q = r - full;
+        f = q / rem;
+        pair = full_groups * PG2 + q % rem;
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8mp_kernel(const TriI8Args a) {
+    const uint32_t rank = cluster_ctarank();
+    const int cluster = blockIdx.x >> 1;
+    const int nclusters = gridDim.x >> 1;
+    const int nfold = (a.nblk + 1) / 2;
+    const int npairs = (a.npanels - a.panel0 + 1) / 2;
+    const long ntiles = (long)a.fix_bi * nfold * npairs;    // fix_bi carries n_s (launch_tri_i8mp)
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_addr(smem_raw);
+    const uint32_t stage0 = (raw + 1023u) & ~1023u;
+    unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)I8_STAGES * I8_STAGE_BYTES;
+    double* s_col = reinterpret_cast<double*>(tail);                        // [2][4][I8_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 2 * 4 * I8_N);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 2);
+    const uint32_t bar0 = smem_addr(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (I8_STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (2 * I8_STAGES);
+    const uint32_t tmem_empty_bar = bar0 + 8u * (2 * I8_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 2);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, I8M_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
+                     "n"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nkb_total = a.nblk * 2;
+    constexpr uint32_t A_HALF = I8_S * I8_A_TILE / 2;
+
+    // the block rows of this cluster, in order; every role walks the same sequence
+    auto sub_of = [&](long v, int which, MpSub& out) -> bool {
+        int f, pair;
+        mp_decode(v, nfold, npairs, out.d, f, pair);
+        const int bi_a = a.nblk - 1 - f;
+        if (which == 1 && bi_a == f) return false;   // odd block-row count: the middle row is alone in its tile
+        out.bi = which == 0 ? bi_a : f;
+        out.panel = a.panel0 + 2 * pair + (int)rank;
+        out.valid = out.panel < a.npanels;            // odd panel count: the second CTA of the last pair only helps loading
+        out.panel_ld = out.valid ? out.panel : out.panel - 1;
+        return true;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long it = 0;
+            for (long v = cluster; v < ntiles; v += nclusters)
+                for (int which = 0; which < 2; ++which) {
+                    MpSub t;
+                    if (!sub_of(v, which, t)) continue;
+                    const int nk = 2 * (t.bi + 1);
+                    const int8_t* wsrc = a.wi8 +
+                                         ((long)t.d * a.nblk * (a.nblk + 1) + (long)t.bi * (t.bi + 1)) * (I8_S * I8_A_TILE) +
+                                         (long)rank * A_HALF;
+                    const int8_t* ksrc =
+                        a.ki8 + (((long)t.d * a.npanel_cap + t.panel_ld) * nkb_total) * (long)(I8_S * I8_B_TILE);
+                    for (int kb = 0; kb < nk; ++kb, ++it) {
+                        const int s = (int)(it % I8_STAGES);
+                        if (it >= I8_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((it / I8_STAGES - 1) & 1));
+                        const uint32_t dst = stage0 + (uint32_t)s * I8_STAGE_BYTES;
+                        mbar_expect_tx(full_bar(s), I8_STAGE_BYTES);
+                        bulk_g2s_multicast(dst + rank * A_HALF, wsrc + (long)kb * (I8_S * I8_A_TILE), A_HALF, full_bar(s),
+                                           (uint16_t)3);
+                        bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)kb * (I8_S * I8_B_TILE), I8_S * I8_B_TILE,
+                                 full_bar(s));
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = make_i8_idesc(TILE, I8_N);
+            constexpr uint32_t idesc2 = make_i8_idesc(TILE, 2 * I8_N);
+            long it = 0;
+            uint32_t nsub = 0;
+            for (long v = cluster; v < ntiles; v += nclusters)
+                for (int which = 0; which < 2; ++which) {
+                    MpSub t;
+                    if (!sub_of(v, which, t)) continue;
+                    const int nk = 2 * (t.bi + 1);
+                    if (nsub > 0) {   // the epilogue of the previous block row has read its accumulators
+                        mbar_wait(tmem_empty_bar, (nsub - 1) & 1u);
+                        tc_fence_after();
+                    }
+                    for (int kb = 0; kb < nk; ++kb, ++it) {
+                        const int s = (int)(it % I8_STAGES);
+                        mbar_wait_cluster(full_bar(s), (uint32_t)((it / I8_STAGES) & 1));
+                        tc_fence_after();
+                        const uint32_t sa = stage0 + (uint32_t)s * I8_STAGE_BYTES;
+                        const uint32_t sb = sa + I8_S * I8_A_TILE;
+#pragma unroll
+                        for (int ks = 0; ks < I8_KB / 32; ++ks) {
+#pragma unroll
+                            for (int pa = 0; pa < I8_S; ++pa) {
+                                const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
+                                const uint32_t acc = (uint32_t)((kb | ks | pa) != 0);
+#pragma unroll
+                                for (int pc = 0; pc < I8_S - pa; pc += 2) {
+                                    const uint64_t bdesc = make_sw64_desc(sb + pc * I8_B_TILE + ks * 32);
+                                    const bool two = pc + 1 < I8_S - pa;
+                                    tc_mma_i8(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, two ? idesc2 : idesc1,
+                                              acc);
+                                }
+                            }
+                        }
+                        tc_commit_multicast(empty_bar(s), (uint16_t)3);
+                    }
+                    tc_commit(tmem_full_bar);
+                    ++nsub;
+                }
+        }
+    } else {
+        const int q = warp & 3;
+        const int chunk = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        uint32_t nsub = 0;
+        for (long v = cluster; v < ntiles; v += nclusters)
+            for (int which = 0; which < 2; ++which) {
+                MpSub t;
+                if (!sub_of(v, which, t)) continue;
+                const double rf = a.rowfac[((long)t.d * a.nblk + t.bi) * TILE + row];
+                mbar_wait(tmem_full_bar, nsub & 1u);
+                tc_fence_after();
+                const double val = i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar) : "memory");
+                double* col = s_col + (nsub & 1u) * (4 * I8_N);   // double-buffered: the next block row's epilogue may
+                col[q * I8_N + chunk * 32 + lane] = val;           // start while slow threads still read this one
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * I8M_EPI_WARPS) : "memory");
+                const int c = threadIdx.x - 64;
+                if (c < I8_N && t.valid) {
+                    const double sum = (col[c] + col[I8_N + c]) + (col[2 * I8_N + c] + col[3 * I8_N + c]);
+                    const long bcol = (long)t.panel * I8_N + c;
+                    if (bcol < a.b_cap) a.qpart[((long)t.d * a.nblk + t.bi) * a.b_cap + bcol] = sum;
+                }
+                ++nsub;
+            }
+    }
+    tc_fence_before();
+    cluster_sync_all();   // the peer may multicast into this shared memory / signal these barriers until it is done too
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+constexpr size_t I8MP_SMEM = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 /* alignment slack */ + 2 * 4 * I8_N * 8 + 128;
+
+int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st) {
+    const int nfold = (a.nblk + 1) / 2;
+    const int npairs = (a.npanels - a.panel0 + 1) / 2;
+    const long ntiles = (long)n_s * nfold * npairs;
+    if (ntiles <= 0) {
+        set_error("tri_i8mp: empty tile list");
+        return SEGP_ERR_INVALID;
+    }
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        SEGP_CUDA_CHECK(cudaGetDevice(&dev));
+        SEGP_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long nclusters = std::min<long>(ntiles, std::max(1, n_sm / 2));
+    TriI8Args b = a;
+    b.fix_bi = n_s;   // fix_bi (self-test tile selector of the other kernels) carries n_s into this one
+    tri_i8mp_kernel<<<(unsigned)(2 * nclusters), I8M_THREADS, I8MP_SMEM, st>>>(b);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
 // =========================================================================================== tri_i8x2p (persistent)
 // Same tiles, same arithmetic, same barriers as tri_i8x2, but ONE resident CTA pair per TPC walks a static list of
 // tiles (heavy-first order, boustrophedon over the clusters so every cluster gets the same mix of long and short
@@ -1332,6 +1552,7 @@ int tri_i8_init() {
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8MP_SMEM));
     return SEGP_OK;
 }
 

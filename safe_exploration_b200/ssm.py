@@ -33,7 +33,8 @@ __all__ = ["BatchedGPSSM"]
 
 # Which tensor pipe runs the variance contraction of new models (include/segp.h, option "tri_mode"):
 # -1 automatic (int8 digit planes on tcgen05 when the padded training size allows, else fp64 DMMA), 0 fp64 DMMA,
-# 1..4 the tcgen05 kernels (4, the default: single-CTA MMAs over two K* planes, W multicast over a CTA pair).  All
+# 1..5 the tcgen05 kernels (4, the default: single-CTA MMAs over two K* planes, W multicast over a CTA pair; 5: the
+# same as a persistent kernel over folded tiles).  All
 # are products of this package and all meet the rtol 1e-4 gate; tests run every one.
 DEFAULT_TRI_MODE = int(os.environ.get("SEGP_TRI_MODE", "-1"))
 

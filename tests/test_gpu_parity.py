@@ -306,6 +306,46 @@ def test_select_maxvar_and_information_gain(se):
     gp.close()
 
 
+@pytest.mark.parametrize("kerns", [["rbf", "mat52"], ["lin_rbf", "mat52"]])
+def test_factor_buffer_transplant_equals_own_factorisation(se, kerns):
+    """The multi-GPU setup path on one device: a model that only received the data (set_data_only) plus a copy of
+    another model's factor buffers (what the NCCL broadcast delivers) and mark_factorized predicts bit-identically
+    to the model that factorised -- including the composite kernels, whose X^T beta term is rebuilt from the
+    transplanted beta."""
+    from safe_exploration_b200.ssm import _tensor_from_ptr
+    import torch
+    rng = np.random.default_rng(12)
+    n, n_s, n_u = 300, 2, 1
+    dim = n_s + n_u
+    x = rng.uniform(-1, 1, (n, dim))
+    y = rng.standard_normal((n, n_s))
+    hyp = []
+    for k in kerns:
+        if k.startswith("lin_"):
+            hyp.append({"prod.rbf.lengthscale": np.array([0.9]), "prod.rbf.variance": 1.1,
+                        "prod.linear.variances": np.array([0.6]), "linear.variances": rng.uniform(0.1, 0.4, dim),
+                        "noise": 1e-2})
+        else:
+            hyp.append({"lengthscale": rng.uniform(0.7, 1.5, dim), "variance": 0.9, "noise": 2e-2})
+    gp1 = se.BatchedGPSSM(n_s, n_s, n_u, x, y, kern_types=kerns, hyp=hyp)
+    gp2 = se.BatchedGPSSM(n_s, n_s, n_u, kern_types=kerns, hyp=hyp)
+    gp2.set_data_only(x, y)
+    with pytest.raises(RuntimeError):
+        gp2.predict(x[:3])
+    b1, b2 = gp1.factor_buffers(), gp2.factor_buffers()
+    assert [nb for _, nb in b1] == [nb for _, nb in b2]
+    for (p1, nb), (p2, _) in zip(b1, b2):
+        _tensor_from_ptr(torch, p2, nb, gp2.device).copy_(_tensor_from_ptr(torch, p1, nb, gp1.device))
+    torch.cuda.synchronize()
+    gp2.mark_factorized()
+    z = rng.uniform(-1, 1, (200, dim))
+    for a, b in zip(gp1.predict(z, compute_gradients=True), gp2.predict(z, compute_gradients=True)):
+        assert np.array_equal(a, b)
+    assert np.array_equal(gp1.beta, gp2.beta)
+    gp1.close()
+    gp2.close()
+
+
 # =========================================================================== rollouts vs the batch oracle
 def _rollout_vs_oracle(se, w, t_z_gp=None, q0=None, k_fb_init=None, per_traj_kfb=False, rtol=RTOL_TIGHT):
     from oracle import reach_oracle

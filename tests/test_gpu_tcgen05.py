@@ -81,7 +81,7 @@ def _cancelling_model(se, n, n_s, n_u, kern, seed, tri_mode):
     return gp, ora, z
 
 
-@pytest.mark.parametrize("tri_mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("tri_mode", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("n,n_s,n_u,kern", [(1500, 2, 1, "rbf"), (3000, 4, 1, "rbf"), (2000, 3, 2, "mat52")])
 def test_predict_variance_under_cancellation(se, n, n_s, n_u, kern, tri_mode):
     gp, ora, z = _cancelling_model(se, n, n_s, n_u, kern, 5, tri_mode)
@@ -102,7 +102,7 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
     from safe_exploration_b200 import workloads
     w = workloads.make("C4", batch=700)
     out = {}
-    for mode in (0, 1, 2, 3, 4):
+    for mode in (0, 1, 2, 3, 4, 5):
         gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp,
                              tri_mode=mode)
         out[mode] = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
@@ -112,6 +112,7 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
     assert np.array_equal(out[1].q_all, out[2].q_all) and np.array_equal(out[1].var_all, out[2].var_all)
     assert np.array_equal(out[3].q_all, out[2].q_all) and np.array_equal(out[3].var_all, out[2].var_all)
     assert np.array_equal(out[4].q_all, out[2].q_all) and np.array_equal(out[4].var_all, out[2].var_all)
+    assert np.array_equal(out[5].q_all, out[2].q_all) and np.array_equal(out[5].var_all, out[2].var_all)
     for name in ("var_all", "p_all", "q_all"):
         a0, a1 = getattr(out[0], name), getattr(out[4], name)
         err = float(np.max(np.abs(a1 - a0) / (np.abs(a0) + 1e-12 * np.abs(a0).max())))
@@ -121,7 +122,7 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
 
 def test_pair_kernel_odd_block_rows(se):
     """N = 1100 pads to 9 block rows: the last CTA pair has only one real block row."""
-    for mode in (2, 3, 4):
+    for mode in (2, 3, 4, 5):
         gp, ora, z = _cancelling_model(se, 1100, 2, 1, "rbf", 9, mode)
         assert gp.get_option("n_train_padded") == 1152
         mu, var, _ = gp.predict(z, compute_gradients=True)
