@@ -326,6 +326,8 @@ def run_product(args, rank, world, local_rank):
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     share = (tri_ns * 1e-6) / ms if ms > 0 else None
     mode = gp.get_option("tri_mode_effective")
+    if mode == 4 and gp.get_option("tri_persistent"):
+        mode = 5   # automatic mode launched the persistent variant of the same contraction (short-tile models)
     if mode in (1, 2, 3, 4, 5):
         # tri_i8: 15 int8 digit-plane products per algorithmic multiply-add, exact int32 accumulation in TMEM.
         # `achieved` is ALGORITHMIC flop/s (n_s N^2 B per launch); `peak` is the measured bf16 figure of

@@ -288,7 +288,9 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
  *   size is <= 16384, else 0), 0 = fp64 DMMA (mma.sync m8n8k4.f64), 1..5 = int8 digit planes on tcgen05:
  *   1 one CTA per tile, 2 CTA pairs (tcgen05.mma.cta_group::2, M = 256), 3 persistent CTA pairs, 4 single-CTA MMAs
  *   spanning two K* digit planes (N = 192) with the W stage multicast over a CTA pair, 5 the same as a persistent
- *   kernel over folded (equal-length) tiles; 1..5 give bit-identical results; read-only "tri_mode_effective";
+ *   kernel over folded (equal-length) tiles (automatic mode launches it instead of 4 for models of <= 32 block rows
+ *   with enough tiles; read-only "tri_persistent" = 1 if the last launch did); 1..5 give bit-identical results;
+ *   read-only "tri_mode_effective";
  * "overlap": 1 = run a chunk as two half-chunks software-pipelined over two internal streams (tri_mode 4/5);
  * "time_tri": 1 = bracket every tri_sumsq launch with a CUDA-event pair on its stream (resets the counters);
  * read-only: "launches" = kernels launched by this handle so far, "n_train_padded", "workspace_bytes",

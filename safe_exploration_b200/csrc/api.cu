@@ -109,6 +109,7 @@ struct segp_model {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ks[2] = {nullptr, nullptr}, ev_tri[2] = {nullptr, nullptr};
     long opt_i8_ablate = 0;   // profiling only, see TriI8Args::ablate
     long long* i8_prof = nullptr;   // profiling only: [128][8] counters of the persistent kernel's MMA threads
+    bool last_tri_persistent = false;   // which tcgen05 kernel the last contraction launch used (automatic mode)
     long launches = 0;
     // optional per-launch timing of tri_sumsq (bench.py roofline): event pairs recorded on the launching stream
     bool time_tri = false;
@@ -339,6 +340,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0) {
             const long ntiles = (long)m->n_s * ((m->nblk + 1) / 2) * ((t.npanels + 1) / 2);
             persistent = m->nblk <= 32 && ntiles >= 4 * 74;
         }
+        m->last_tri_persistent = persistent;
         SEGP_CHECK(persistent        ? launch_tri_i8mp(t, m->n_s, st)
                    : m->ws_mode == 4 ? launch_tri_i8m(t, m->n_s, st)
                    : m->ws_mode == 3 ? launch_tri_i8x2p(t, m->n_s, st)
@@ -1472,6 +1474,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "overlap") == 0) *value = m->opt_overlap;
     else if (strcmp(name, "i8_prof_ptr") == 0) *value = (long)(uintptr_t)m->i8_prof;
     else if (strcmp(name, "tri_mode_effective") == 0) *value = tri_mode(m);
+    else if (strcmp(name, "tri_persistent") == 0) *value = m->last_tri_persistent ? 1 : 0;
     else if (strcmp(name, "launches") == 0) *value = m->launches;
     else if (strcmp(name, "n_train_padded") == 0) *value = m->n_pad;
     else if (strcmp(name, "workspace_bytes") == 0) *value = (long)m->workspace_bytes;
