@@ -227,6 +227,8 @@ def run_product(args, rank, world, local_rank):
     gp.set_option("overlap", 1 if args.overlap else 0)
     if args.ksplit > 0:
         gp.set_option("ksplit", args.ksplit)
+    if args.i8_panel_group > 0:
+        gp.set_option("i8_panel_group", args.i8_panel_group)
 
     # ---------------- device-resident inputs (the `value` arm)
     p0_d = torch.as_tensor(w.p0, device=dev)
@@ -447,6 +449,8 @@ def main():
                          "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs, "
                          "4 single-CTA MMAs over merged K* planes, W multicast over a CTA pair, 5 the same as a persistent "
                          "kernel over folded (equal-length) tiles")
+    ap.add_argument("--i8-panel-group", type=int, default=0,
+                    help="panels per L2 group of the tcgen05 contraction (even; 0 = automatic); tuning experiments")
     ap.add_argument("--ksplit", type=int, default=0,
                     help="splits of the training points in the K* kernel (0 = automatic); tuning experiments")
     ap.add_argument("--redundant-factor", action="store_true",

@@ -909,18 +909,19 @@ constexpr int I8M_THREADS = 64 + 32 * I8M_EPI_WARPS;      // producer, MMA issue
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8m_kernel(const TriI8Args a) {
     const uint32_t rank = cluster_ctarank();
-    constexpr int PG2 = I8_PANEL_GROUP / 2;   // panel pairs per L2 group
+    const int pgroup = a.pgroup > 0 ? a.pgroup : I8_PANEL_GROUP;   // even
+    const int PG2 = pgroup / 2;   // panel pairs per L2 group
     int d, bi, panel;
     {
         const int cid = blockIdx.x >> 1;
         const int tiles_per_group = PG2 * a.nblk;
-        const int npg = (a.npanels - a.panel0 + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
+        const int npg = (a.npanels - a.panel0 + pgroup - 1) / pgroup;
         const int gid = cid / tiles_per_group;
         const int r = cid % tiles_per_group;
         d = gid / npg;
         const int pg = gid % npg;
         bi = a.nblk - 1 - r / PG2;
-        panel = a.panel0 + pg * I8_PANEL_GROUP + 2 * (r % PG2) + (int)rank;
+        panel = a.panel0 + pg * pgroup + 2 * (r % PG2) + (int)rank;
         if (panel - (int)rank >= a.npanels) return;   // the whole cluster is past the last panel
     }
     const bool valid = panel < a.npanels;             // odd panel count: the last cluster's second CTA only helps loading
@@ -1041,8 +1042,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
 }
 
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
-    const int npg = (a.npanels - a.panel0 + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
-    const long nclusters = (long)n_s * npg * (I8_PANEL_GROUP / 2) * a.nblk;
+    const int pgroup = a.pgroup > 0 ? a.pgroup : I8_PANEL_GROUP;
+    const int npg = (a.npanels - a.panel0 + pgroup - 1) / pgroup;
+    const long nclusters = (long)n_s * npg * (pgroup / 2) * a.nblk;
     if (nclusters <= 0 || 2 * nclusters > 2147483647L) {
         set_error("tri_i8m: grid of %ld cluster tiles out of range", nclusters);
         return SEGP_ERR_INVALID;
@@ -1065,10 +1067,9 @@ struct MpSub {
     int d, bi, panel, panel_ld;
     bool valid;
 };
-// valid tile v of [0, n_s * nfold * npairs) -> (d, fold, panel pair); order: d, panel group of 12 pairs (its K*
+// valid tile v of [0, n_s * nfold * npairs) -> (d, fold, panel pair); order: d, panel group of PG2 pairs (its K*
 // planes stay L2-resident), fold, pair -- the clusters of one round work on neighbouring block rows of one group.
-__device__ __forceinline__ void mp_decode(long v, int nfold, int npairs, int& d, int& f, int& pair) {
-    constexpr int PG2 = I8_PANEL_GROUP / 2;
+__device__ __forceinline__ void mp_decode(long v, int nfold, int npairs, int PG2, int& d, int& f, int& pair) {
     const long per_d = (long)nfold * npairs;
     d = (int)(v / per_d);
     const int r = (int)(v % per_d);
@@ -1135,7 +1136,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
     // the block rows of this cluster, in order; every role walks the same sequence
     auto sub_of = [&](long v, int which, MpSub& out) -> bool {
         int f, pair;
-        mp_decode(v, nfold, npairs, out.d, f, pair);
+        mp_decode(v, nfold, npairs, (a.pgroup > 0 ? a.pgroup : I8_PANEL_GROUP) / 2, out.d, f, pair);
         const int bi_a = a.nblk - 1 - f;
         if (which == 1 && bi_a == f) return false;   // odd block-row count: the middle row is alone in its tile
         out.bi = which == 0 ? bi_a : f;
