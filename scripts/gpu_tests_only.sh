@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q $PYTEST_ARGS > gpurun_out/pytest_gpu.log 2>&1; tail -40 gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -x -q --timeout 600 ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_gpu.log 2>&1; tail -40 gpurun_out/pytest_gpu.log

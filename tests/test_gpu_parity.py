@@ -204,6 +204,45 @@ def test_predict_at_training_inputs_identity(se):
     gp.close()
 
 
+def test_model_beyond_the_int8_size_limit_runs_in_float64(se, _tri_mode):
+    """More than 16384 (padded) training points: the int32 accumulators of the digit-plane products would overflow,
+    so the model must select the float64 contraction on its own, refuse a tcgen05 mode loudly, and still satisfy the
+    training-input identity mean_i = y_i - noise beta_i (checks potrf / trtri / beta / K* / mean at that size)."""
+    if _tri_mode != 0:
+        pytest.skip("one run is enough: the model picks its pipe itself")
+    rng = np.random.default_rng(21)
+    n, dim = 16500, 3
+    x = rng.uniform(-1, 1, (n, dim))
+    y = np.sin(x @ rng.standard_normal((dim, 1))) + 0.05 * rng.standard_normal((n, 1))
+    hyp = [{"lengthscale": np.array([0.7, 0.9, 1.1]), "variance": 1.0, "noise": 5e-2}]
+    gp = se.BatchedGPSSM(1, 2, 1, x, y, kern_types=["rbf"], hyp=hyp, tri_mode=-1)
+    assert gp.get_option("n_train_padded") > 16384 and gp.get_option("tri_mode_effective") == 0
+    with pytest.raises(NotImplementedError):
+        gp.set_option("tri_mode", 4)
+    idx = np.arange(0, n, 157)
+    mu, var = gp.predict(x[idx])
+    want = y[idx] - gp.total_noise()[None, :] * gp.beta[idx]
+    _assert_close(mu, want, 1e-6, atol_scale=1e-8, what="mean at training inputs")
+    assert np.all(var > 0) and np.all(var < gp.total_noise()[None, :])
+    gp.close()
+
+
+def test_empty_and_single_candidate_batches(se):
+    """Ragged ends of the batch axis: no candidates at all, one candidate, one more than a 96-trajectory panel."""
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C2", batch=97, n_train=130, horizon=3)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    args = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    full = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
+    none = se.rollout(gp, w.p0, w.k_ff[:0], w.k_fb, *args)
+    assert none.p_all.shape == (0, 3, w.n_s) and none.q_all.shape == (0, 3, w.n_s, w.n_s) and none.status.shape == (0,)
+    one = se.rollout(gp, w.p0, w.k_ff[96:97], w.k_fb, *args)
+    assert np.array_equal(one.q_all[0], full.q_all[96]) and np.array_equal(one.p_all[0], full.p_all[96])
+    mu0, var0 = gp.predict(np.zeros((0, w.n_s + w.n_u)))
+    assert mu0.shape == (0, w.n_s) and var0.shape == (0, w.n_s)
+    gp.close()
+
+
 @pytest.mark.parametrize("name", ["pend_rbf_mat52", "pend_composite", "cart_mixed"])
 def test_golden_gp_pred_reference(se, golden_dir, name):
     """Predictive mean / variance the reference's OWN gp_models_utils_casadi.py functions produced (kernels incl. the
