@@ -95,6 +95,17 @@ int segp_set_linear_terms(segp_model* m, const double* h_prod_linear, const doub
  * SEGP_ERR_NOT_POSDEF if a pivot is not positive (LAPACK LinAlgError in the reference). */
 int segp_factorize(segp_model* m, void* stream);
 
+/* Append n_new training points (HOST pointers h_x [n_new x (n_s_in+n_u)], h_y [n_new x n_s_out]) to a factorised
+ * model and update the posterior state.  Replaces SimpleGPModel.update_model(..., replace_old=False)
+ * (ssm_gpy/gaussian_process.py:347-419: vstack + a fresh GPRegression, O(N^3)).  While the 128-padded size does not
+ * grow, only the rows of W = L^-1 from the first touched 64-row block on are recomputed --
+ * L21 = K21 W11^T, L22 L22^T = K22 - L21 L21^T, W22 = L22^-1, W21 = -W22 L21 W11, O(n_new N^2) -- then beta, the
+ * log-determinant and the packed operands are refreshed.  This needs W kept dense on the device (n_s_out x
+ * N_pad^2 doubles; option "keep_w", switched on by the first call, which therefore factorises from scratch, as
+ * does every call that grows the padded size; read-only option "append_incremental" tells which path ran).
+ * Synchronous.  SEGP_ERR_NOT_POSDEF as segp_factorize. */
+int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, void* stream);
+
 /* Multi-GPU setup: the factorised state is n_buffers device buffers.  Rank `root` factorises, every
  * rank calls segp_alloc_factor_buffers (non-root ranks instead of segp_factorize), the host broadcasts
  * each buffer (one ncclBroadcast per buffer via torch.distributed), then non-root ranks call

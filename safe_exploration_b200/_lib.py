@@ -66,6 +66,7 @@ PROTOTYPES = {
     "segp_set_model": (_int, [_vp, _int, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p]),
     "segp_set_linear_terms": (_int, [_vp, _c_double_p, _c_double_p]),
     "segp_factorize": (_int, [_vp, _vp]),
+    "segp_append": (_int, [_vp, _int, _c_double_p, _c_double_p, _vp]),
     "segp_alloc_factor_buffers": (_int, [_vp]),
     "segp_num_factor_buffers": (_int, [_vp]),
     "segp_factor_buffer": (_int, [_vp, _int, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t)]),

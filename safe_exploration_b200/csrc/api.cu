@@ -76,6 +76,9 @@ struct segp_model {
     double* xtb = nullptr;     // [n_s][dim] X^T beta_d
     double* jac2_part = nullptr;   // workspace: additive Jacobian partials
     double* kss = nullptr;         // workspace: [n_s][b_cap] prior variances
+    double* wdense = nullptr;  // [n_s][n_pad][n_pad] W = L^-1 kept dense for segp_append (only if opt_keep_w)
+    long opt_keep_w = 0;       // keep wdense after factorising (set by the first segp_append)
+    bool last_append_incremental = false;
     int8_t* wi8 = nullptr;     // [n_s][nblk (nblk+1)][I8_S][I8_A_TILE] digit planes of W (tcgen05 path)
     double* rowfac = nullptr;  // [n_s][n_pad] per-row factors of the digit planes
     // workspace
@@ -131,6 +134,7 @@ static void free_model_buffers(segp_model* m) {
     dev_free(m->wi8);
     dev_free(m->rowfac);
     dev_free(m->i8zero);
+    dev_free(m->wdense);
     dev_free(m->xraw);
     dev_free(m->plin);
     dev_free(m->lin);
@@ -660,7 +664,11 @@ int segp_factorize(segp_model* m, void* stream) {
     std::vector<int> fails(m->n_s, 0);
     do {
         if ((rc = dev_alloc(&kbuf, nn)) != SEGP_OK) break;
-        if ((rc = dev_alloc(&wbuf, nn)) != SEGP_OK) break;
+        if (m->opt_keep_w) {
+            if (m->wdense == nullptr && (rc = dev_alloc(&m->wdense, (size_t)m->n_s * nn)) != SEGP_OK) break;
+        } else if ((rc = dev_alloc(&wbuf, nn)) != SEGP_OK) {
+            break;
+        }
         if ((rc = dev_alloc(&tmp, nn)) != SEGP_OK) break;
         if ((rc = dev_alloc(&diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
         if ((rc = dev_alloc(&u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
@@ -669,6 +677,7 @@ int segp_factorize(segp_model* m, void* stream) {
         for (int d = 0; d < m->n_s && rc == SEGP_OK; ++d) {
             const double* xs_d = m->xs + (size_t)d * m->n_pad * m->dim;
             const bool comp = kern_is_composite(m->kern[d]);
+            if (m->opt_keep_w) wbuf = m->wdense + (size_t)d * nn;
             if ((rc = launch_kmat(kbuf, xs_d, m->kern[d], m->h_var[d], m->h_noise[d], sd, comp ? m->xraw : nullptr,
                                   comp ? m->plin + (size_t)d * m->dim : nullptr,
                                   comp ? m->lin + (size_t)d * m->dim : nullptr, st)) != SEGP_OK)
@@ -716,12 +725,134 @@ int segp_factorize(segp_model* m, void* stream) {
     } while (0);
     cudaStreamSynchronize(st);
     dev_free(kbuf);
-    dev_free(wbuf);
+    if (!m->opt_keep_w) dev_free(wbuf);
     dev_free(tmp);
     dev_free(diag_inv);
     dev_free(u_tmp);
     dev_free(d_fail);
     if (rc == SEGP_OK) m->factorized = true;
+    return rc;
+}
+
+int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, void* stream) {
+    SEGP_CHECK(check_ready(m));
+    if (n_new < 0 || (n_new > 0 && (h_x == nullptr || h_y == nullptr))) {
+        set_error("segp_append: null argument");
+        return SEGP_ERR_INVALID;
+    }
+    if (n_new == 0) return SEGP_OK;
+    DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int dim = m->dim, n_s = m->n_s;
+    const int n_old = m->n_train, n_tot = n_old + n_new;
+    // host copies first (copies of the arguments: h_x may alias nothing of ours, but set_model re-assigns from them)
+    std::vector<double> hx(m->h_x), hy(m->h_y);
+    hx.insert(hx.end(), h_x, h_x + (size_t)n_new * dim);
+    hy.insert(hy.end(), h_y, h_y + (size_t)n_new * n_s);
+    m->last_append_incremental = false;
+    if (m->wdense == nullptr || n_tot > m->n_pad) {
+        // no dense factor kept yet, or the padded size grows: factorise from scratch, keeping W dense from now on
+        const std::vector<double> ls(m->h_ls), var(m->h_var), noise(m->h_noise), plin(m->h_plin), lin(m->h_lin);
+        const bool had_lin = m->has_linear_terms;
+        m->opt_keep_w = 1;
+        SEGP_CHECK(segp_set_model(m, n_tot, hx.data(), hy.data(), ls.data(), var.data(), noise.data()));
+        if (had_lin) SEGP_CHECK(segp_set_linear_terms(m, plin.data(), lin.data()));
+        return segp_factorize(m, stream);
+    }
+    // ---- incremental: the padded size and every earlier row of W stay
+    SEGP_CUDA_CHECK(cudaStreamSynchronize(st));
+    m->factorized = false;
+    const int n_pad = m->n_pad;
+    const size_t nn = (size_t)n_pad * n_pad;
+    std::vector<double> rows((size_t)n_new * dim);
+    for (int d = 0; d < n_s; ++d) {
+        for (int i = 0; i < n_new; ++i)
+            for (int j = 0; j < dim; ++j) rows[(size_t)i * dim + j] = h_x[(size_t)i * dim + j] / m->h_ls[d * dim + j];
+        SEGP_CUDA_CHECK(cudaMemcpy(m->xs + ((size_t)d * n_pad + n_old) * dim, rows.data(), rows.size() * sizeof(double),
+                                   cudaMemcpyHostToDevice));
+        for (int i = 0; i < n_new; ++i) rows[i] = h_y[(size_t)i * n_s + d];
+        SEGP_CUDA_CHECK(cudaMemcpy(m->yp + (size_t)d * n_pad + n_old, rows.data(), (size_t)n_new * sizeof(double),
+                                   cudaMemcpyHostToDevice));
+    }
+    if (m->xraw != nullptr)
+        SEGP_CUDA_CHECK(cudaMemcpy(m->xraw + (size_t)n_old * dim, h_x, (size_t)n_new * dim * sizeof(double),
+                                   cudaMemcpyHostToDevice));
+    m->h_x.swap(hx);
+    m->h_y.swap(hy);
+    m->n_train = n_tot;
+    const int r0 = n_old / NBLK * NBLK;
+    const int r1 = (n_tot + NBLK - 1) / NBLK * NBLK;
+    const int sblk = r1 - r0;
+    double *krows = nullptr, *l21 = nullptr, *tbuf = nullptr, *sbuf = nullptr, *w22 = nullptr, *tmp = nullptr,
+           *diag_inv = nullptr, *u_tmp = nullptr;
+    int* d_fail = nullptr;
+    int rc = SEGP_OK;
+    std::vector<int> fails(n_s, 0);
+    do {
+        if ((rc = dev_alloc(&krows, (size_t)sblk * n_pad)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&l21, (size_t)sblk * n_pad)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&tbuf, (size_t)sblk * n_pad)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&sbuf, (size_t)sblk * sblk)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&w22, (size_t)sblk * sblk)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&tmp, (size_t)sblk * sblk)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&diag_inv, (size_t)sblk * NBLK)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&u_tmp, (size_t)33 * n_pad)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_fail, (size_t)n_s)) != SEGP_OK) break;
+        SetupDims sd{m->n_train, n_pad, dim};
+        for (int d = 0; d < n_s && rc == SEGP_OK; ++d) {
+            const bool comp = kern_is_composite(m->kern[d]);
+            double* w = m->wdense + (size_t)d * nn;
+            if ((rc = launch_kmat_rows(krows, m->xs + (size_t)d * n_pad * dim, m->kern[d], m->h_var[d], m->h_noise[d], sd,
+                                       comp ? m->xraw : nullptr, comp ? m->plin + (size_t)d * dim : nullptr,
+                                       comp ? m->lin + (size_t)d * dim : nullptr, r0, sblk, st)) != SEGP_OK)
+                break;
+            ++m->launches;
+            if ((rc = append_rows(w, n_pad, r0, sblk, krows, l21, tbuf, sbuf, w22, tmp, diag_inv, d_fail + d, st,
+                                  &m->launches)) != SEGP_OK)
+                break;
+            if ((rc = logdet_from_winv(w, m->n_train, n_pad, m->logdet + d, st)) != SEGP_OK) break;
+            if ((rc = solve_beta(w, m->yp + (size_t)d * n_pad, u_tmp, m->beta + (size_t)d * n_pad, n_pad, st)) != SEGP_OK)
+                break;
+            if ((rc = pack_w(w, m->wt + (size_t)d * m->ntri * TILE * TILE, n_pad, st)) != SEGP_OK) break;
+            m->launches += 5;
+            if (m->wi8 != nullptr) {
+                if ((rc = pack_w_i8(w, m->wi8 + (size_t)d * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE),
+                                    m->rowfac + (size_t)d * n_pad, m->h_var[d], n_pad, st)) != SEGP_OK)
+                    break;
+                m->launches += 2;
+            }
+        }
+        if (rc != SEGP_OK) break;
+        if (m->has_composite && (rc = compute_xtb(m, st)) != SEGP_OK) break;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaMemcpy(fails.data(), d_fail, n_s * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("segp_append: %s", cudaGetErrorString(e));
+            rc = SEGP_ERR_CUDA;
+            break;
+        }
+        for (int d = 0; d < n_s; ++d)
+            if (fails[d] != 0) {
+                set_error("segp_append: K + noise I is not positive definite for output %d (pivot %d)", d,
+                          r0 + fails[d] - 1);
+                rc = SEGP_ERR_NOT_POSDEF;
+                break;
+            }
+    } while (0);
+    cudaStreamSynchronize(st);
+    dev_free(krows);
+    dev_free(l21);
+    dev_free(tbuf);
+    dev_free(sbuf);
+    dev_free(w22);
+    dev_free(tmp);
+    dev_free(diag_inv);
+    dev_free(u_tmp);
+    dev_free(d_fail);
+    if (rc == SEGP_OK) {
+        m->factorized = true;
+        m->last_append_incremental = true;
+    }
     return rc;
 }
 
@@ -1446,6 +1577,15 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_overlap = value;
         return SEGP_OK;
     }
+    if (strcmp(name, "keep_w") == 0 && (value == 0 || value == 1)) {   // takes effect at the next segp_factorize
+        m->opt_keep_w = value;
+        if (value == 0) {
+            DeviceGuard guard(m->device);
+            cudaDeviceSynchronize();
+            dev_free(m->wdense);
+        }
+        return SEGP_OK;
+    }
     if (strcmp(name, "i8_ablate") == 0) {
         m->opt_i8_ablate = value;
         return SEGP_OK;
@@ -1484,6 +1624,9 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "i8_prof_ptr") == 0) *value = (long)(uintptr_t)m->i8_prof;
     else if (strcmp(name, "tri_mode_effective") == 0) *value = tri_mode(m);
     else if (strcmp(name, "tri_persistent") == 0) *value = m->last_tri_persistent ? 1 : 0;
+    else if (strcmp(name, "append_incremental") == 0) *value = m->last_append_incremental ? 1 : 0;
+    else if (strcmp(name, "keep_w") == 0) *value = m->opt_keep_w;
+    else if (strcmp(name, "n_train") == 0) *value = m->n_train;
     else if (strcmp(name, "launches") == 0) *value = m->launches;
     else if (strcmp(name, "n_train_padded") == 0) *value = m->n_pad;
     else if (strcmp(name, "workspace_bytes") == 0) *value = (long)m->workspace_bytes;

@@ -249,6 +249,13 @@ struct SetupDims {
 // composite kernels: xraw [n_pad][dim] unscaled inputs, plin_d / lin_d [dim] device vectors (else NULL)
 int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, const double* xraw,
                 const double* plin_d, const double* lin_d, cudaStream_t st);
+// rows [row0, row0 + nrows) of the same matrix into a nrows x n_pad buffer
+int launch_kmat_rows(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, const double* xraw,
+                     const double* plin_d, const double* lin_d, int row0, int nrows, cudaStream_t st);
+// incremental update of the dense W = L^-1 when rows [r0, r0 + s) of K + noise I are new (setup.cu)
+int append_rows(double* w, int n_pad, int r0, int s, const double* krows, double* l21, double* tbuf, double* sbuf,
+                double* w22, double* tmp, double* diag_inv, int* d_fail, cudaStream_t st, long* launches);
+int logdet_from_winv(const double* w, int n_train, int n_pad, double* d_out, cudaStream_t st);
 // xtb[j] = sum_i beta[i] xraw[i][j]  (fixed-order block reduction)
 int launch_xtb(const double* xraw, const double* beta, double* xtb, int n_pad, int dim, cudaStream_t st);
 // in-place blocked Cholesky (lower) of a (n_pad x n_pad); diag_inv gets the inverses of the 64x64 diagonal blocks;

@@ -16,9 +16,9 @@ namespace segp {
 // =========================================================================================== kmat
 __global__ void kmat_kernel(double* __restrict__ k, const double* __restrict__ xs, int kern, double var, double noise,
                             int n_train, int n_pad, int dim, const double* __restrict__ xraw,
-                            const double* __restrict__ plin, const double* __restrict__ lin) {
+                            const double* __restrict__ plin, const double* __restrict__ lin, int row0) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
+    const int i = row0 + blockIdx.y;   // row of the kernel matrix; row blockIdx.y of the output buffer
     if (j >= n_pad) return;
     const bool composite = kern_is_composite(kern);
     double v;
@@ -50,19 +50,24 @@ __global__ void kmat_kernel(double* __restrict__ k, const double* __restrict__ x
             if (i == j) v += noise;
         }
     }
-    k[(long)i * n_pad + j] = v;
+    k[(long)blockIdx.y * n_pad + j] = v;
 }
 
-int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, const double* xraw,
-                const double* plin_d, const double* lin_d, cudaStream_t st) {
+int launch_kmat_rows(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, const double* xraw,
+                     const double* plin_d, const double* lin_d, int row0, int nrows, cudaStream_t st) {
     if (kern_is_composite(kern) && (xraw == nullptr || plin_d == nullptr || lin_d == nullptr)) {
         set_error("composite kernel without linear terms (call segp_set_linear_terms)");
         return SEGP_ERR_INVALID;
     }
-    dim3 grid((unsigned)((s.n_pad + 127) / 128), (unsigned)s.n_pad);
-    kmat_kernel<<<grid, 128, 0, st>>>(k, xs_d, kern, var, noise, s.n_train, s.n_pad, s.dim, xraw, plin_d, lin_d);
+    dim3 grid((unsigned)((s.n_pad + 127) / 128), (unsigned)nrows);
+    kmat_kernel<<<grid, 128, 0, st>>>(k, xs_d, kern, var, noise, s.n_train, s.n_pad, s.dim, xraw, plin_d, lin_d, row0);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
+}
+
+int launch_kmat(double* k, const double* xs_d, int kern, double var, double noise, SetupDims s, const double* xraw,
+                const double* plin_d, const double* lin_d, cudaStream_t st) {
+    return launch_kmat_rows(k, xs_d, kern, var, noise, s, xraw, plin_d, lin_d, 0, s.n_pad, st);
 }
 
 // xtb[j] = sum_i beta[i] xraw[i][j]: one block per input dimension, fixed-order tree reduction
@@ -511,6 +516,102 @@ __global__ void logdet_kernel(const double* __restrict__ l, int n_train, int n_p
 int logdet_from_chol(const double* l, int n_train, int n_pad, double* d_out, cudaStream_t st) {
     logdet_kernel<<<1, 256, 0, st>>>(l, n_train, n_pad, d_out);
     SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// the same from W = L^-1 (W_ii = 1 / L_ii): -2 sum log W_ii
+__global__ void logdet_winv_kernel(const double* __restrict__ w, int n_train, int n_pad, double* __restrict__ out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_train; i += 256) acc += log(w[(long)i * n_pad + i]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = -2.0 * s[0];
+}
+
+int logdet_from_winv(const double* w, int n_train, int n_pad, double* d_out, cudaStream_t st) {
+    logdet_winv_kernel<<<1, 256, 0, st>>>(w, n_train, n_pad, d_out);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== append_rows
+// Rows [r0, r0 + s) of K + noise I are new (appended training points, re-evaluated old rows of the same 64-row blocks,
+// identity rows of the padding); rows [0, r0) and their part W11 of W = L^-1 are unchanged.  With
+//   L21 = K21 W11^T,   S = K22 - L21 L21^T = L22 L22^T,   W22 = L22^-1,   W21 = -W22 (L21 W11)
+// the rows [r0, r0 + s) of W follow in O(s N^2) instead of O(N^3) (the block form trtri_lower uses level by level).
+// r0 and s are multiples of 64; rows below r0 + s must be padding (identity).  krows: s x n_pad, rows of K + noise I.
+int append_rows(double* w, int n_pad, int r0, int s, const double* krows, double* l21, double* tbuf, double* sbuf,
+                double* w22, double* tmp, double* diag_inv, int* d_fail, cudaStream_t st, long* launches) {
+    SEGP_CUDA_CHECK(cudaMemcpy2DAsync(sbuf, (size_t)s * sizeof(double), krows + r0, (size_t)n_pad * sizeof(double),
+                                      (size_t)s * sizeof(double), (size_t)s, cudaMemcpyDeviceToDevice, st));
+    GemmArgs g{};
+    g.m_total = s;
+    g.zrows = 0;
+    if (r0 > 0) {
+        // L21 = K21 W11^T
+        g.a = krows;
+        g.b = w;
+        g.c = l21;
+        g.lda = g.ldb = g.ldc = n_pad;
+        g.m = s;
+        g.n = r0;
+        g.k = r0;
+        g.alpha = 1.0;
+        g.beta = 0.0;
+        g.flags = 0;
+        SEGP_CHECK(launch_gemm64(g, true, 1, st));
+        // S = K22 - L21 L21^T
+        g.a = l21;
+        g.b = l21;
+        g.c = sbuf;
+        g.ldc = s;
+        g.m = s;
+        g.n = s;
+        g.k = r0;
+        g.alpha = -1.0;
+        g.beta = 1.0;
+        SEGP_CHECK(launch_gemm64(g, true, 1, st));
+        *launches += 2;
+    }
+    SEGP_CHECK(potrf_lower(sbuf, s, diag_inv, d_fail, st, launches));
+    SEGP_CUDA_CHECK(cudaMemsetAsync(w22, 0, (size_t)s * s * sizeof(double), st));
+    SEGP_CHECK(trtri_lower(sbuf, w22, s, diag_inv, tmp, st, launches));
+    if (r0 > 0) {
+        // T = L21 W11 ; W21 = -W22 T
+        g.a = l21;
+        g.b = w;
+        g.c = tbuf;
+        g.lda = g.ldb = g.ldc = n_pad;
+        g.m = s;
+        g.n = r0;
+        g.k = r0;
+        g.alpha = 1.0;
+        g.beta = 0.0;
+        g.flags = GEMM_B_LOWER;
+        SEGP_CHECK(launch_gemm64(g, false, 1, st));
+        g.a = w22;
+        g.lda = s;
+        g.b = tbuf;
+        g.ldb = n_pad;
+        g.c = w + (long)r0 * n_pad;
+        g.ldc = n_pad;
+        g.m = s;
+        g.n = r0;
+        g.k = s;
+        g.alpha = -1.0;
+        g.beta = 0.0;
+        g.flags = GEMM_A_LOWER;
+        SEGP_CHECK(launch_gemm64(g, false, 1, st));
+        *launches += 2;
+    }
+    SEGP_CUDA_CHECK(cudaMemcpy2DAsync(w + (long)r0 * n_pad + r0, (size_t)n_pad * sizeof(double), w22,
+                                      (size_t)s * sizeof(double), (size_t)s * sizeof(double), (size_t)s,
+                                      cudaMemcpyDeviceToDevice, st));
     return SEGP_OK;
 }
 

@@ -265,9 +265,26 @@ class BatchedGPSSM(object):
         x = np.asarray(x, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
         if not replace_old and self.x_train is not None:
+            if self.gp_trained and (noise_diag is None or float(noise_diag) == self.noise_diag):
+                return self.append_data(x, y)
             x = np.vstack((self.x_train, x))
             y = np.vstack((self.y_train, y))
         self.train(x, y, noise_diag=noise_diag)
+
+    def append_data(self, x, y):
+        """Append training points to the factorised model (segp_append): while the padded size does not grow only the
+        trailing rows of L^-1 are recomputed, O(n_new N^2) instead of O(N^3); ``get_option("append_incremental")``
+        tells which path ran.  The first call keeps W dense on the device from then on."""
+        x_h = _lib.host_f64(x).reshape(-1, self.dim_in)
+        y_h = _lib.host_f64(y).reshape(-1, self.n_s_out)
+        if x_h.shape[0] != y_h.shape[0]:
+            raise ValueError("x and y need the same number of rows")
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.segp_append(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
+                                             _lib.current_stream(self.device)))
+        self.x_train = np.vstack((self.x_train, x_h))
+        self.y_train = np.vstack((self.y_train, y_h))
+        self.z = self.x_train
 
     # ------------------------------------------------------------------ multi-GPU: one broadcast of the factor
     def factor_buffers(self):

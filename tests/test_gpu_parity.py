@@ -227,6 +227,55 @@ def test_model_beyond_the_int8_size_limit_runs_in_float64(se, _tri_mode):
     gp.close()
 
 
+@pytest.mark.parametrize("kerns", [["rbf", "mat52"], ["lin_mat52", "rbf"]])
+def test_append_data_equals_refactorisation(se, kerns):
+    """update_model(replace_old=False) -> segp_append: appending points (1, a few, across a 64-row block, across the
+    128-row padding) must give the model a from-scratch factorisation of the concatenated data gives -- predictions,
+    Jacobians, beta, log-determinant, rollouts -- and take the incremental path whenever the padded size stays."""
+    from safe_exploration_b200 import workloads
+    rng = np.random.default_rng(33)
+    n_s, n_u = 2, 1
+    dim = n_s + n_u
+    n_all = 420
+    x = rng.uniform(-1, 1, (n_all, dim))
+    y = np.sin(x @ rng.standard_normal((dim, n_s))) + 0.05 * rng.standard_normal((n_all, n_s))
+    hyp = []
+    for k in kerns:
+        if k.startswith("lin_"):
+            hyp.append({"prod.mat52.lengthscale": np.array([0.9]), "prod.mat52.variance": 1.1,
+                        "prod.linear.variances": np.array([0.6]), "linear.variances": rng.uniform(0.1, 0.4, dim),
+                        "noise": 1e-2})
+        else:
+            hyp.append({"lengthscale": rng.uniform(0.7, 1.5, dim), "variance": 0.9, "noise": 2e-2})
+    z = rng.uniform(-1, 1, (150, dim))
+    gp = se.BatchedGPSSM(n_s, n_s, n_u, x[:290], y[:290], kern_types=kerns, hyp=hyp)
+    n = 290
+    # (points to append, incremental expected): the first call switches dense-W keeping on and refactorises
+    for add, incremental in ((1, False), (1, True), (5, True), (60, True), (27, True), (1, False), (35, True)):
+        gp.update_model(x[n:n + add], y[n:n + add], replace_old=False)
+        n += add
+        assert gp.get_option("n_train") == n and gp.x_train.shape == (n, dim)
+        assert bool(gp.get_option("append_incremental")) == incremental, (n, add)
+        ref = se.BatchedGPSSM(n_s, n_s, n_u, x[:n], y[:n], kern_types=kerns, hyp=hyp)
+        for a, b, what in zip(gp.predict(z, compute_gradients=True), ref.predict(z, compute_gradients=True),
+                              ("mean", "variance", "jacobian")):
+            _assert_close(a, b, 1e-7, atol_scale=1e-9, what="%s after appending to %d" % (what, n))
+        _assert_close(gp.beta, ref.beta, 1e-6, atol_scale=1e-8, what="beta")
+        _assert_close(gp.log_det_k(), ref.log_det_k(), 1e-10, what="log det")
+        ref.close()
+    assert n == n_all
+    # the rollouts run on the refreshed packed operands (both tensor pipes via the fixture)
+    w = workloads.make("C2", batch=64, n_train=50, horizon=3)
+    ref = se.BatchedGPSSM(n_s, n_s, n_u, x, y, kern_types=kerns, hyp=hyp)
+    args = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    r1 = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
+    r0 = se.rollout(ref, w.p0, w.k_ff, w.k_fb, *args)
+    _assert_close(r1.q_all, r0.q_all, 1e-6, what="q_all after appends")
+    _assert_close(r1.var_all, r0.var_all, 1e-6, atol_scale=1e-10, what="var_all after appends")
+    gp.close()
+    ref.close()
+
+
 def test_empty_and_single_candidate_batches(se):
     """Ragged ends of the batch axis: no candidates at all, one candidate, one more than a 96-trajectory panel."""
     from safe_exploration_b200 import workloads
