@@ -197,8 +197,21 @@ def _config_dict(args, w, b_per_gpu, world, where):
             "n_train": w.n_train, "horizon": w.horizon, "n_s": w.n_s, "n_u": w.n_u,
             "batch_per_gpu": b_per_gpu, "global_batch": b_per_gpu * world, "parallelism": "dp{}".format(world),
             "inputs": where,
-            "l2_policy": "inputs larger than L2: every step streams the packed factor ({} MB) and a K* block far "
-                         "above the 126 MB L2".format(int(w.n_s * w.n_train ** 2 * 4 / 1e6))}
+            "l2_policy": _l2_policy(w, b_per_gpu)}
+
+
+def _l2_policy(w, b_per_gpu):
+    """Working set of one H-step call against the 126 MB L2: the int8 digit planes of the factor (5 B per entry of
+    the lower block triangle) and of the K* block of one chunk (5 B per kernel value), both re-read every step."""
+    n_pad = -(-w.n_train // 128) * 128
+    factor_mb = w.n_s * (n_pad // 128) * (n_pad // 128 + 1) * 5 * 8192 / 1e6
+    kstar_mb = w.n_s * n_pad * 5 * min(b_per_gpu, 8192) / 1e6
+    if factor_mb + kstar_mb > 2 * 126:
+        return ("inputs larger than L2: every step streams the packed factor ({:.0f} MB) and a K* block of {:.0f} MB "
+                "against the 126 MB L2".format(factor_mb, kstar_mb))
+    return ("no flush: factor ({:.0f} MB) + K* block ({:.0f} MB) fit the 126 MB L2 at this configuration; the steps of a "
+            "call are dependent (step t reads what step t-1 wrote), so a flush between calls would not change what "
+            "the H-step loop sees".format(factor_mb, kstar_mb))
 
 
 def run_product(args, rank, world, local_rank):
