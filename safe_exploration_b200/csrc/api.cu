@@ -658,51 +658,87 @@ int segp_factorize(segp_model* m, void* stream) {
     SEGP_CHECK(segp_alloc_factor_buffers(m));
     const size_t nn = (size_t)m->n_pad * m->n_pad;
     const int nb64 = m->n_pad / NBLK;
-    double *kbuf = nullptr, *wbuf = nullptr, *tmp = nullptr, *diag_inv = nullptr, *u_tmp = nullptr;
+    // The output dimensions are independent factorisations and each is a chain of ~270 launches, many of them one
+    // block wide (the 64 x 64 diagonal blocks): up to FACT_SLOTS of them run concurrently on their own streams, each
+    // with its own scratch, so the latency-bound launches of one overlap the GEMMs of the others.
+    constexpr int FACT_SLOTS = 4;
+    struct Slot {
+        double *kbuf = nullptr, *wbuf = nullptr, *tmp = nullptr, *diag_inv = nullptr, *u_tmp = nullptr;
+        cudaStream_t s = nullptr;
+        cudaEvent_t done = nullptr;
+    };
+    const int nslots = std::min(m->n_s, FACT_SLOTS);
+    Slot slots[FACT_SLOTS];
+    cudaEvent_t fork = nullptr;
     int* d_fail = nullptr;
     int rc = SEGP_OK;
     std::vector<int> fails(m->n_s, 0);
     do {
-        if ((rc = dev_alloc(&kbuf, nn)) != SEGP_OK) break;
-        if (m->opt_keep_w) {
-            if (m->wdense == nullptr && (rc = dev_alloc(&m->wdense, (size_t)m->n_s * nn)) != SEGP_OK) break;
-        } else if ((rc = dev_alloc(&wbuf, nn)) != SEGP_OK) {
+        if (m->opt_keep_w && m->wdense == nullptr && (rc = dev_alloc(&m->wdense, (size_t)m->n_s * nn)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_fail, (size_t)m->n_s)) != SEGP_OK) break;
+        if (cudaMemsetAsync(d_fail, 0, m->n_s * sizeof(int), st) != cudaSuccess ||
+            cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(fork, st) != cudaSuccess) {
+            set_error("segp_factorize: stream set-up failed");
+            rc = SEGP_ERR_CUDA;
             break;
         }
-        if ((rc = dev_alloc(&tmp, nn)) != SEGP_OK) break;
-        if ((rc = dev_alloc(&diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
-        if ((rc = dev_alloc(&u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
-        if ((rc = dev_alloc(&d_fail, (size_t)m->n_s)) != SEGP_OK) break;
+        for (int i = 0; i < nslots && rc == SEGP_OK; ++i) {
+            Slot& sl = slots[i];
+            if ((rc = dev_alloc(&sl.kbuf, nn)) != SEGP_OK) break;
+            if (!m->opt_keep_w && (rc = dev_alloc(&sl.wbuf, nn)) != SEGP_OK) break;
+            if ((rc = dev_alloc(&sl.tmp, nn)) != SEGP_OK) break;
+            if ((rc = dev_alloc(&sl.diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
+            if ((rc = dev_alloc(&sl.u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
+            if (cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess ||
+                cudaStreamWaitEvent(sl.s, fork, 0) != cudaSuccess) {
+                set_error("segp_factorize: stream set-up failed");
+                rc = SEGP_ERR_CUDA;
+            }
+        }
+        if (rc != SEGP_OK) break;
         SetupDims sd{m->n_train, m->n_pad, m->dim};
         for (int d = 0; d < m->n_s && rc == SEGP_OK; ++d) {
+            Slot& sl = slots[d % nslots];   // a slot's buffers are reused in stream order
+            cudaStream_t ss = sl.s;
+            double* wbuf = m->opt_keep_w ? m->wdense + (size_t)d * nn : sl.wbuf;
             const double* xs_d = m->xs + (size_t)d * m->n_pad * m->dim;
             const bool comp = kern_is_composite(m->kern[d]);
-            if (m->opt_keep_w) wbuf = m->wdense + (size_t)d * nn;
-            if ((rc = launch_kmat(kbuf, xs_d, m->kern[d], m->h_var[d], m->h_noise[d], sd, comp ? m->xraw : nullptr,
+            if ((rc = launch_kmat(sl.kbuf, xs_d, m->kern[d], m->h_var[d], m->h_noise[d], sd, comp ? m->xraw : nullptr,
                                   comp ? m->plin + (size_t)d * m->dim : nullptr,
-                                  comp ? m->lin + (size_t)d * m->dim : nullptr, st)) != SEGP_OK)
+                                  comp ? m->lin + (size_t)d * m->dim : nullptr, ss)) != SEGP_OK)
                 break;
             ++m->launches;
-            if ((rc = potrf_lower(kbuf, m->n_pad, diag_inv, d_fail + d, st, &m->launches)) != SEGP_OK) break;
-            if ((rc = logdet_from_chol(kbuf, m->n_train, m->n_pad, m->logdet + d, st)) != SEGP_OK) break;
+            if ((rc = potrf_lower(sl.kbuf, m->n_pad, sl.diag_inv, d_fail + d, ss, &m->launches)) != SEGP_OK) break;
+            if ((rc = logdet_from_chol(sl.kbuf, m->n_train, m->n_pad, m->logdet + d, ss)) != SEGP_OK) break;
             ++m->launches;
-            if (cudaMemsetAsync(wbuf, 0, nn * sizeof(double), st) != cudaSuccess) {
+            if (cudaMemsetAsync(wbuf, 0, nn * sizeof(double), ss) != cudaSuccess) {
                 set_error("cudaMemsetAsync failed");
                 rc = SEGP_ERR_CUDA;
                 break;
             }
-            if ((rc = trtri_lower(kbuf, wbuf, m->n_pad, diag_inv, tmp, st, &m->launches)) != SEGP_OK) break;
-            if ((rc = solve_beta(wbuf, m->yp + (size_t)d * m->n_pad, u_tmp, m->beta + (size_t)d * m->n_pad, m->n_pad,
-                                 st)) != SEGP_OK)
+            if ((rc = trtri_lower(sl.kbuf, wbuf, m->n_pad, sl.diag_inv, sl.tmp, ss, &m->launches)) != SEGP_OK) break;
+            if ((rc = solve_beta(wbuf, m->yp + (size_t)d * m->n_pad, sl.u_tmp, m->beta + (size_t)d * m->n_pad, m->n_pad,
+                                 ss)) != SEGP_OK)
                 break;
             m->launches += 3;
-            if ((rc = pack_w(wbuf, m->wt + (size_t)d * m->ntri * TILE * TILE, m->n_pad, st)) != SEGP_OK) break;
+            if ((rc = pack_w(wbuf, m->wt + (size_t)d * m->ntri * TILE * TILE, m->n_pad, ss)) != SEGP_OK) break;
             ++m->launches;
             if (m->wi8 != nullptr) {
                 if ((rc = pack_w_i8(wbuf, m->wi8 + (size_t)d * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE),
-                                    m->rowfac + (size_t)d * m->n_pad, m->h_var[d], m->n_pad, st)) != SEGP_OK)
+                                    m->rowfac + (size_t)d * m->n_pad, m->h_var[d], m->n_pad, ss)) != SEGP_OK)
                     break;
                 m->launches += 2;
+            }
+        }
+        if (rc != SEGP_OK) break;
+        for (int i = 0; i < nslots; ++i) {   // join
+            if (cudaEventRecord(slots[i].done, slots[i].s) != cudaSuccess ||
+                cudaStreamWaitEvent(st, slots[i].done, 0) != cudaSuccess) {
+                set_error("segp_factorize: stream join failed");
+                rc = SEGP_ERR_CUDA;
+                break;
             }
         }
         if (rc != SEGP_OK) break;
@@ -723,12 +759,18 @@ int segp_factorize(segp_model* m, void* stream) {
                 break;
             }
     } while (0);
-    cudaStreamSynchronize(st);
-    dev_free(kbuf);
-    if (!m->opt_keep_w) dev_free(wbuf);
-    dev_free(tmp);
-    dev_free(diag_inv);
-    dev_free(u_tmp);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < FACT_SLOTS; ++i) {
+        Slot& sl = slots[i];
+        dev_free(sl.kbuf);
+        dev_free(sl.wbuf);
+        dev_free(sl.tmp);
+        dev_free(sl.diag_inv);
+        dev_free(sl.u_tmp);
+        if (sl.done != nullptr) cudaEventDestroy(sl.done);
+        if (sl.s != nullptr) cudaStreamDestroy(sl.s);
+    }
+    if (fork != nullptr) cudaEventDestroy(fork);
     dev_free(d_fail);
     if (rc == SEGP_OK) m->factorized = true;
     return rc;
