@@ -105,10 +105,13 @@ struct segp_model {
     long opt_tri_mode = -1;   // -1 = automatic (4 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
                               // 1 = int8 tcgen05 single CTA, 2 = CTA pair (cta_group::2), 3 = persistent CTA pair,
                               // 4 = single-CTA MMAs over two K* planes at once, W multicast over a CTA pair
-    long opt_overlap = 0;     // 1 = software-pipeline two half-chunks over two internal streams (tri_mode 4 only): the
-                              // FP64-bound K* kernel of one half is issued under the tensor-bound contraction of the
-                              // other.  Bit-identical, measured no faster at C3/C4/C5 (the 15k-CTA contraction grid is
-                              // dispatched ahead of the K* blocks and the GPU is power-capped): off by default
+    long opt_overlap = 0;     // 1 = software-pipeline two half-chunks over two internal streams (tri_mode 4 / 5): the
+                              // FP64-bound K* kernel of one half runs as a resident grid of small CTAs NEXT TO the
+                              // persistent contraction (tri_i8mp<4>) of the other.  Bit-identical.  The kernels do
+                              // share the SMs, but the co-resident K* kernel runs ~7x slower than alone (the
+                              // contraction saturates the shared-memory / L1 data path it also needs) and becomes the
+                              // critical path: 6 % slower than the serial schedule at C4, off by default
+                              // (profiles/round1/overlap_pipeline_c3_c4_c5.txt)
     cudaStream_t s_hi = nullptr, s_lo = nullptr;   // internal streams of the pipelined driver (created on first use)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ks[2] = {nullptr, nullptr}, ev_tri[2] = {nullptr, nullptr};
     long opt_i8_ablate = 0;   // profiling only, see TriI8Args::ablate
@@ -293,7 +296,7 @@ static KstarArgs base_kstar_args(const segp_model* m) {
 }
 
 // K* block (+ mean / Jacobian partials) in the operand format of the active contraction kernel
-static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int panel0 = 0) {
+static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int panel0 = 0, bool coresident = false) {
     if (m->ws_mode != 0) {
         KstarI8Args k8{};
         k8.k = k;
@@ -301,6 +304,7 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int pan
         k8.npanel_cap = m->npanel_cap;
         k8.split_halves = m->ws_mode == 2 || m->ws_mode == 3;
         k8.panel0 = panel0;
+        k8.resident_ctas = coresident ? 3 * 148 : 0;   // three small CTAs per SM next to the persistent contraction
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
     }
     return launch_kstar(k, m->n_s, m->nsplit, st);
@@ -308,7 +312,7 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int pan
 
 // variance contraction launch (tri_i8 on tcgen05 or tri_sumsq on the DMMA pipe), optionally bracketed by a
 // CUDA-event pair on the launching stream
-static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0) {
+static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool coresident = false) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->time_tri) {
         while (m->tri_events.size() < m->tri_events_used + 2) {
@@ -348,8 +352,9 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0) {
             const long ntiles = (long)m->n_s * ((m->nblk + 1) / 2) * ((t.npanels + 1) / 2);
             persistent = m->nblk <= 32 && ntiles >= 4 * 74;
         }
+        if (coresident) persistent = true;   // the pipelined driver needs a resident contraction grid
         m->last_tri_persistent = persistent;
-        SEGP_CHECK(persistent        ? launch_tri_i8mp(t, m->n_s, st)
+        SEGP_CHECK(persistent        ? launch_tri_i8mp(t, m->n_s, st, coresident)
                    : m->ws_mode == 4 ? launch_tri_i8m(t, m->n_s, st)
                    : m->ws_mode == 3 ? launch_tri_i8x2p(t, m->n_s, st)
                    : m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st)
@@ -1068,6 +1073,31 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
             SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_lo, m->ev_fork, 0));
             forked = true;
         }
+        // debugging aid (SEGP_TIMELINE=1): device timestamps of every launch of the first pipelined steps, on stderr
+        static const bool timeline = getenv("SEGP_TIMELINE") != nullptr;
+        struct Mark {
+            const char* what;
+            int t, h;
+            cudaEvent_t e0, e1;
+        };
+        std::vector<Mark> marks;
+        cudaEvent_t tl_base = nullptr;
+        auto mark_begin = [&](const char* what, int t, int h, cudaStream_t s) {
+            if (!timeline || t > 2) return;
+            Mark mk{what, t, h, nullptr, nullptr};
+            cudaEventCreate(&mk.e0);
+            cudaEventCreate(&mk.e1);
+            cudaEventRecord(mk.e0, s);
+            marks.push_back(mk);
+        };
+        auto mark_end = [&](int t, cudaStream_t s) {
+            if (!timeline || t > 2) return;
+            cudaEventRecord(marks.back().e1, s);
+        };
+        if (timeline) {
+            cudaEventCreate(&tl_base);
+            cudaEventRecord(tl_base, m->s_lo);
+        }
         const int pa = ((npanels / 2 + 1) / 2) * 2;   // even, so the cluster pairs of the first half are complete
         const int p_begin[2] = {0, pa}, p_end[2] = {pa, npanels};
         const long b_begin[2] = {0, (long)pa * I8_N}, b_end[2] = {std::min<long>((long)pa * I8_N, nb), nb};
@@ -1075,17 +1105,36 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
             for (int h = 0; h < 2; ++h) {
                 if (t > 0) {
                     SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_lo, m->ev_tri[h], 0));
+                    mark_begin("ell", t - 1, h, m->s_lo);
                     SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t - 1, b_begin[h], b_end[h]), m->s_lo));
+                    mark_end(t - 1, m->s_lo);
                     ++m->launches;
                 }
                 if (t == horizon) continue;
-                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, b_end[h]), m->s_lo, p_begin[h]));
+                mark_begin("kstar", t, h, m->s_lo);
+                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, b_end[h]), m->s_lo, p_begin[h], true));
+                mark_end(t, m->s_lo);
                 SEGP_CUDA_CHECK(cudaEventRecord(m->ev_ks[h], m->s_lo));
                 SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_hi, m->ev_ks[h], 0));
-                SEGP_CHECK(run_tri(m, (long)p_end[h] * I8_N, m->s_hi, p_begin[h]));
+                mark_begin("tri", t, h, m->s_hi);
+                SEGP_CHECK(run_tri(m, (long)p_end[h] * I8_N, m->s_hi, p_begin[h], true));
+                mark_end(t, m->s_hi);
                 SEGP_CUDA_CHECK(cudaEventRecord(m->ev_tri[h], m->s_hi));
                 m->launches += 2;
             }
+        }
+        if (timeline) {
+            cudaDeviceSynchronize();
+            for (const Mark& mk : marks) {
+                float t0 = 0.f, t1 = 0.f;
+                cudaEventElapsedTime(&t0, tl_base, mk.e0);
+                cudaEventElapsedTime(&t1, tl_base, mk.e1);
+                fprintf(stderr, "[segp timeline] %-5s step %d half %d: %8.3f -> %8.3f ms (%.3f)\n", mk.what, mk.t, mk.h, t0,
+                        t1, t1 - t0);
+                cudaEventDestroy(mk.e0);
+                cudaEventDestroy(mk.e1);
+            }
+            cudaEventDestroy(tl_base);
         }
     }
     if (forked) {   // everything issued on s_hi has been waited for by s_lo

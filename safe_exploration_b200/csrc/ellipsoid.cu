@@ -375,6 +375,17 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
 }
 
 int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
+    // same shared-memory carve-out preference as the contraction kernels it may run next to (pipelined driver)
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        const int mx = (int)cudaSharedmemCarveoutMaxShared;
+        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<SEGP_MAX_NS, SEGP_MAX_NU>,
+                                             cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+        carveout_set = true;
+    }
     const int threads = 64;
     const unsigned grid = (unsigned)((a.n_batch - a.b0 + threads - 1) / threads);
     if (a.n_s == 2 && a.n_u == 1)

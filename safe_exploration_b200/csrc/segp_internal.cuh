@@ -111,6 +111,7 @@ struct KstarI8Args {
     long npanel_cap;
     int split_halves;
     int panel0;             // first panel of this launch (blockIdx.x counts from it): sub-chunk pipelining
+    int resident_ctas;      // > 0: run as a resident grid of this many small CTAs looping over the work items
 };
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st);
 
@@ -135,7 +136,8 @@ int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st);
 // single-CTA MMAs, two CTAs per cluster share one block row of W through multicast bulk copies
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st);
 // persistent tri_i8m: one resident cluster per TPC walks a static list of folded (equal-length) tiles
-int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st);
+// leave_room: 4 epilogue warps instead of 12, so that two resident K* CTAs fit next to it on every SM
+int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_room = false);
 // persistent CTA-pair variant: one resident pair per TPC walks a static tile list
 int launch_tri_i8x2p(const TriI8Args& a, int n_s, cudaStream_t st);
 int tri_i8_init();

@@ -161,7 +161,7 @@ __device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict
 }
 
 // 128 staged training points against one trajectory: kernel values -> digit bytes, mean / Jacobian sums.
-template <int DM, int KERN, int UNR>
+template <int DM, int KERN, int UNR, int ROWS>
 __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, const double* __restrict__ s_beta,
                                               const double* __restrict__ s_tab,
                                               const double (&zs)[DM], int dim, double var, int row0, int n_train,
@@ -171,7 +171,7 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
     // UNR independent points per iteration (8 or 16): ILP against code size / registers
     static_assert(UNR == 8 || UNR == 16, "unroll");
 #pragma unroll 1
-    for (int r = 0; r < TILE; r += UNR) {
+    for (int r = 0; r < ROWS; r += UNR) {
         uint32_t pk[I8_S][UNR / 4];
 #pragma unroll
         for (int s = 0; s < I8_S; ++s)
@@ -225,23 +225,19 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
     }
 }
 
-template <int D_T>
-__global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
+// One work item = (96-trajectory panel, output dimension, split of the training points).  STAGE training points are
+// staged through shared memory at a time.
+template <int D_T, int STAGE>
+__device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, int d, int split, int n_s,
+                                              double* __restrict__ s_x, double* __restrict__ s_beta,
+                                              const double* __restrict__ s_tab) {
     const KstarArgs& a = aa.k;
     constexpr int DM = D_T > 0 ? D_T : MAX_D;
     const int dim = D_T > 0 ? D_T : a.dim;
-    const int d = blockIdx.y;
-    const int split = blockIdx.z;
     const int trow = threadIdx.x;
-    const int panel = aa.panel0 + (int)blockIdx.x;
     const long b = (long)panel * I8_N + trow;
     const bool active = b < a.n_batch;
 
-    __shared__ double s_x[TILE * DM];
-    __shared__ double s_beta[TILE];
-    __shared__ double s_tab[64];
-    if (threadIdx.x < 64) s_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));   // visible after the first
-                                                                                           // __syncthreads below
     double zs[DM];
 #pragma unroll
     for (int j = 0; j < DM; ++j) zs[j] = 0.0;
@@ -292,25 +288,24 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
     const long half_off = aa.split_halves ? (long)(trow / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) : 0;
     const long plane_stride = aa.split_halves ? I8_B_TILE / 2 : I8_B_TILE;
 
-    for (int row0 = row_begin; row0 < row_end; row0 += TILE) {
+    for (int row0 = row_begin; row0 < row_end; row0 += STAGE) {
         __syncthreads();
         const double* src = a.xs + ((long)d * a.n_pad + row0) * dim;
-        for (int idx = threadIdx.x; idx < TILE * dim; idx += I8_N) s_x[idx] = src[idx];
-        for (int idx = threadIdx.x; idx < TILE; idx += I8_N) s_beta[idx] = a.beta[(long)d * a.n_pad + row0 + idx] * var;
+        for (int idx = threadIdx.x; idx < STAGE * dim; idx += I8_N) s_x[idx] = src[idx];
+        for (int idx = threadIdx.x; idx < STAGE; idx += I8_N) s_beta[idx] = a.beta[(long)d * a.n_pad + row0 + idx] * var;
         __syncthreads();
         int8_t* kb_base = panel_base + half_off;
         // One loop body per kernel type: with both types inlined the 16-point body was 52 KB of SASS and stalled on
         // instruction fetch (ncu: no_instruction 1.1 per issue).  16 independent points per iteration are needed
         // to cover the FP64 latency (a 4-point body ran 40 % slower).
         if (kern == SEGP_KERN_RBF)
-            kstar_i8_rows<DM, SEGP_KERN_RBF, 16>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active, kb_base,
-                                                 rowp, plane_stride, mu, jac);
+            kstar_i8_rows<DM, SEGP_KERN_RBF, 16, STAGE>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active,
+                                                        kb_base, rowp, plane_stride, mu, jac);
         else
-            kstar_i8_rows<DM, SEGP_KERN_MAT52, 8>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active, kb_base,
-                                                  rowp, plane_stride, mu, jac);
+            kstar_i8_rows<DM, SEGP_KERN_MAT52, 8, STAGE>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active,
+                                                         kb_base, rowp, plane_stride, mu, jac);
     }
     if (active) {
-        const int n_s = gridDim.y;
         a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
 #pragma unroll
         for (int j = 0; j < DM; ++j)
@@ -318,10 +313,78 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
     }
 }
 
+template <int D_T>
+__global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
+    constexpr int DM = D_T > 0 ? D_T : MAX_D;
+    __shared__ double s_x[TILE * DM];
+    __shared__ double s_beta[TILE];
+    __shared__ double s_tab[64];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));   // visible after the first
+                                                                                           // __syncthreads of the item
+    kstar_i8_item<D_T, TILE>(aa, aa.panel0 + (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.y, s_x,
+                             s_beta, s_tab);
+}
+
+// The same work as a RESIDENT grid (a couple of small CTAs per SM looping over the items) for the pipelined driver:
+// with 16 staged points a CTA needs ~2 KB of shared memory and 96 x 88 registers, so four of them fit on an SM NEXT TO
+// a persistent contraction CTA (tri_i8mp<4>: 224 KB, 192 threads) and run under it; a resident grid leaves no pending
+// blocks that could take an SM's shared memory in the gap between two contraction kernels.
+constexpr int KS_RES_STAGE = 16;
+constexpr int KS_RES_PER_SM = 4;
+__device__ double g_exp2_tab[64];   // 2^(j/64), filled by tri_i8_init: the resident variant reads it through L1 instead of
+                                    // spending 512 B of the ~9 KB of shared memory the contraction CTA leaves per SM
+__global__ void exp2_tab_kernel() { g_exp2_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0)); }
+template <int D_T>
+__global__ void __maxnreg__(88) kstar_i8_resident_kernel(const KstarI8Args aa, int n_s, int nsplit, int npanels) {
+    static_assert(D_T > 0, "resident variant is instantiated for compile-time input dimensions only");
+    __shared__ double s_x[KS_RES_STAGE * D_T];
+    __shared__ double s_beta[KS_RES_STAGE];
+    const double* s_tab = g_exp2_tab;
+    const long n_items = (long)npanels * n_s * nsplit;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int p = (int)(item % npanels);
+        const int d = (int)((item / npanels) % n_s);
+        const int split = (int)(item / ((long)npanels * n_s));
+        kstar_i8_item<D_T, KS_RES_STAGE>(aa, aa.panel0 + p, d, split, n_s, s_x, s_beta, s_tab);
+    }
+}
+
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st) {
     // panels [panel0, ceil(n_batch / 96)): n_batch is the END of the trajectory range
-    dim3 grid((unsigned)((a.k.n_batch + I8_N - 1) / I8_N - a.panel0), (unsigned)n_s, (unsigned)nsplit);
+    const int npanels = (int)((a.k.n_batch + I8_N - 1) / I8_N) - a.panel0;
+    dim3 grid((unsigned)npanels, (unsigned)n_s, (unsigned)nsplit);
     dim3 block(I8_N);
+    if (a.resident_ctas > 0) {
+        const long n_items = (long)npanels * n_s * nsplit;
+        const unsigned ctas = (unsigned)std::min<long>(a.resident_ctas, n_items);
+        switch (a.k.dim) {
+        // The contraction CTA it has to sit next to runs with the maximum shared-memory carve-out: ask for the same one,
+        // a kernel that prefers another L1 / shared split is not scheduled onto an SM until that SM drains.
+#define SEGP_KS8R_CASE(D) \
+    case D: {             \
+        static bool carveout_set = false;                                                                        \
+        if (!carveout_set) {                                                                                     \
+            SEGP_CUDA_CHECK(cudaFuncSetAttribute(kstar_i8_resident_kernel<D>,                                     \
+                                                 cudaFuncAttributePreferredSharedMemoryCarveout,                 \
+                                                 (int)cudaSharedmemCarveoutMaxShared));                          \
+            carveout_set = true;                                                                                 \
+        }                                                                                                        \
+        kstar_i8_resident_kernel<D><<<ctas, block, 0, st>>>(a, n_s, nsplit, npanels);                             \
+        SEGP_CUDA_CHECK(cudaGetLastError());                                                                     \
+        return SEGP_OK;                                                                                          \
+    }
+            SEGP_KS8R_CASE(2)
+            SEGP_KS8R_CASE(3)
+            SEGP_KS8R_CASE(4)
+            SEGP_KS8R_CASE(5)
+            SEGP_KS8R_CASE(6)
+            SEGP_KS8R_CASE(7)
+            SEGP_KS8R_CASE(8)
+#undef SEGP_KS8R_CASE
+            default:
+                break;   // other input dimensions: the ordinary grid below
+        }
+    }
     switch (a.k.dim) {
 #define SEGP_KS8_CASE(D) \
     case D:              \
@@ -364,6 +427,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -1088,7 +1164,12 @@ __device__ __forceinline__ void mp_decode(long v, int nfold, int npairs, int PG2
     }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8mp_kernel(const TriI8Args a) {
+// EPI_WARPS = 12: one 32-column chunk per epilogue warp (448 threads, 128 registers: fills the register file);
+// EPI_WARPS = 4: one warp per TMEM lane quadrant walks the three chunks (192 threads): leaves registers and threads for
+// two resident K* CTAs per SM (kstar_i8_resident_kernel), used by the pipelined driver.
+template <int EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1) tri_i8mp_kernel(const TriI8Args a) {
+    static_assert(EPI_WARPS == 4 || EPI_WARPS == I8M_EPI_WARPS, "4 or 12 epilogue warps");
     const uint32_t rank = cluster_ctarank();
     const int cluster = blockIdx.x >> 1;
     const int nclusters = gridDim.x >> 1;
@@ -1117,7 +1198,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
             mbar_init(empty_bar(s), 2);
         }
         mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, I8M_EPI_WARPS);
+        mbar_init(tmem_empty_bar, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -1215,7 +1296,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
         }
     } else {
         const int q = warp & 3;
-        const int chunk = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         uint32_t nsub = 0;
         for (long v = cluster; v < ntiles; v += nclusters)
@@ -1223,15 +1303,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
                 MpSub t;
                 if (!sub_of(v, which, t)) continue;
                 const double rf = a.rowfac[((long)t.d * a.nblk + t.bi) * TILE + row];
-                mbar_wait(tmem_full_bar, nsub & 1u);
+                if (EPI_WARPS == 4) {   // next to resident K* CTAs: sleep between polls instead of spinning on the barrier
+                    while (!mbar_test(tmem_full_bar, nsub & 1u)) __nanosleep(512);
+                } else {
+                    mbar_wait(tmem_full_bar, nsub & 1u);
+                }
                 tc_fence_after();
-                const double val = i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+                double* col = s_col + (nsub & 1u) * (4 * I8_N);   // double-buffered: the next block row's epilogue may
+                                                                  // start while slow threads still read this one
+                if (EPI_WARPS == I8M_EPI_WARPS) {
+                    const int chunk = (warp - 2) >> 2;
+                    col[q * I8_N + chunk * 32 + lane] =
+                        i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+                } else {
+#pragma unroll 1
+                    for (int chunk = 0; chunk < I8_N / 32; ++chunk)
+                        col[q * I8_N + chunk * 32 + lane] =
+                            i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar) : "memory");
-                double* col = s_col + (nsub & 1u) * (4 * I8_N);   // double-buffered: the next block row's epilogue may
-                col[q * I8_N + chunk * 32 + lane] = val;           // start while slow threads still read this one
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * I8M_EPI_WARPS) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
                 const int c = threadIdx.x - 64;
                 if (c < I8_N && t.valid) {
                     const double sum = (col[c] + col[I8_N + c]) + (col[2 * I8_N + c] + col[3 * I8_N + c]);
@@ -1251,7 +1344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
 
 constexpr size_t I8MP_SMEM = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 /* alignment slack */ + 2 * 4 * I8_N * 8 + 128;
 
-int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st) {
+int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_room) {
     const int nfold = (a.nblk + 1) / 2;
     const int npairs = (a.npanels - a.panel0 + 1) / 2;
     const long ntiles = (long)n_s * nfold * npairs;
@@ -1268,7 +1361,10 @@ int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st) {
     const long nclusters = std::min<long>(ntiles, std::max(1, n_sm / 2));
     TriI8Args b = a;
     b.fix_bi = n_s;   // fix_bi (self-test tile selector of the other kernels) carries n_s into this one
-    tri_i8mp_kernel<<<(unsigned)(2 * nclusters), I8M_THREADS, I8MP_SMEM, st>>>(b);
+    if (leave_room)
+        tri_i8mp_kernel<4><<<(unsigned)(2 * nclusters), 64 + 32 * 4, I8MP_SMEM, st>>>(b);
+    else
+        tri_i8mp_kernel<I8M_EPI_WARPS><<<(unsigned)(2 * nclusters), I8M_THREADS, I8MP_SMEM, st>>>(b);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }
@@ -1553,7 +1649,11 @@ int tri_i8_init() {
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8MP_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel<I8M_EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)I8MP_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8MP_SMEM));
+    exp2_tab_kernel<<<1, 64>>>();   // the device's exp2, as the shared-memory tables of the other K* kernels: same bits
+    SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }
 
