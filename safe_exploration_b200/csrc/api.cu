@@ -108,8 +108,8 @@ struct segp_model {
     long opt_overlap = 0;     // 1 = software-pipeline two half-chunks over two internal streams (tri_mode 4 / 5): the
                               // FP64-bound K* kernel of one half runs as a resident grid of small CTAs NEXT TO the
                               // persistent contraction (tri_i8mp<4>) of the other.  Bit-identical.  The kernels do
-                              // share the SMs, but the co-resident K* kernel runs ~7x slower than alone (the
-                              // contraction saturates the shared-memory / L1 data path it also needs) and becomes the
+                              // share the SMs, but the co-resident K* kernel runs ~7x slower than alone (most likely
+                              // queued behind the contraction's shared-memory operand traffic) and becomes the
                               // critical path: 6 % slower than the serial schedule at C4, off by default
                               // (profiles/round1/overlap_pipeline_c3_c4_c5.txt)
     cudaStream_t s_hi = nullptr, s_lo = nullptr;   // internal streams of the pipelined driver (created on first use)
