@@ -161,7 +161,7 @@ __device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict
 }
 
 // 128 staged training points against one trajectory: kernel values -> digit bytes, mean / Jacobian sums.
-template <int DM, int KERN, int UNR, int ROWS>
+template <int DM, int KERN, int UNR, int ROWS, bool DIRECT = false>
 __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, const double* __restrict__ s_beta,
                                               const double* __restrict__ s_tab,
                                               const double (&zs)[DM], int dim, double var, int row0, int n_train,
@@ -201,7 +201,7 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
                 g = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
             }
             if (row0 + r + qd >= n_train || !active) unit = 0.0;   // padded rows / columns: zero digits
-            const double bt = s_beta[r + qd];   // beta_i sigma_f^2 (multiplied once while staging)
+            const double bt = DIRECT ? s_beta[r + qd] * var : s_beta[r + qd];   // beta_i sigma_f^2 (staged: multiplied once)
             mu = fma(bt, unit, mu);
             const double w = bt * g;
 #pragma unroll
@@ -288,7 +288,23 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
     const long half_off = aa.split_halves ? (long)(trow / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) : 0;
     const long plane_stride = aa.split_halves ? I8_B_TILE / 2 : I8_B_TILE;
 
-    for (int row0 = row_begin; row0 < row_end; row0 += STAGE) {
+    if (STAGE == 0) {
+        // no staging: every thread reads the training points straight through L1 (uniform addresses: one request per
+        // warp; the CTAs of an SM work on the same rows) -- no shared memory, no block barriers, loads of 16 points in
+        // flight per warp.  For the resident variant, whose global loads see long latencies next to the contraction.
+        for (int row0 = row_begin; row0 < row_end; row0 += TILE) {
+            const double* gx = a.xs + ((long)d * a.n_pad + row0) * dim;
+            const double* gb = a.beta + (long)d * a.n_pad + row0;
+            int8_t* kb_base = panel_base + half_off;
+            if (kern == SEGP_KERN_RBF)
+                kstar_i8_rows<DM, SEGP_KERN_RBF, 16, TILE, true>(gx, gb, s_tab, zs, dim, var, row0, a.n_train, active,
+                                                                 kb_base, rowp, plane_stride, mu, jac);
+            else
+                kstar_i8_rows<DM, SEGP_KERN_MAT52, 8, TILE, true>(gx, gb, s_tab, zs, dim, var, row0, a.n_train, active,
+                                                                  kb_base, rowp, plane_stride, mu, jac);
+        }
+    }
+    for (int row0 = row_begin; STAGE > 0 && row0 < row_end; row0 += (STAGE > 0 ? STAGE : TILE)) {
         __syncthreads();
         const double* src = a.xs + ((long)d * a.n_pad + row0) * dim;
         for (int idx = threadIdx.x; idx < STAGE * dim; idx += I8_N) s_x[idx] = src[idx];
@@ -299,11 +315,13 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
         // instruction fetch (ncu: no_instruction 1.1 per issue).  16 independent points per iteration are needed
         // to cover the FP64 latency (a 4-point body ran 40 % slower).
         if (kern == SEGP_KERN_RBF)
-            kstar_i8_rows<DM, SEGP_KERN_RBF, 16, STAGE>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active,
-                                                        kb_base, rowp, plane_stride, mu, jac);
+            kstar_i8_rows<DM, SEGP_KERN_RBF, 16, (STAGE > 0 ? STAGE : TILE)>(s_x, s_beta, s_tab, zs, dim, var, row0,
+                                                                             a.n_train, active, kb_base, rowp,
+                                                                             plane_stride, mu, jac);
         else
-            kstar_i8_rows<DM, SEGP_KERN_MAT52, 8, STAGE>(s_x, s_beta, s_tab, zs, dim, var, row0, a.n_train, active,
-                                                         kb_base, rowp, plane_stride, mu, jac);
+            kstar_i8_rows<DM, SEGP_KERN_MAT52, 8, (STAGE > 0 ? STAGE : TILE)>(s_x, s_beta, s_tab, zs, dim, var, row0,
+                                                                              a.n_train, active, kb_base, rowp,
+                                                                              plane_stride, mu, jac);
     }
     if (active) {
         a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
@@ -325,27 +343,23 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
                              s_beta, s_tab);
 }
 
-// The same work as a RESIDENT grid (a couple of small CTAs per SM looping over the items) for the pipelined driver:
-// with 16 staged points a CTA needs ~2 KB of shared memory and 96 x 88 registers, so four of them fit on an SM NEXT TO
-// a persistent contraction CTA (tri_i8mp<4>: 224 KB, 192 threads) and run under it; a resident grid leaves no pending
-// blocks that could take an SM's shared memory in the gap between two contraction kernels.
-constexpr int KS_RES_STAGE = 16;
-constexpr int KS_RES_PER_SM = 4;
+// The same work as a RESIDENT grid (a few small CTAs per SM looping over the items) for the pipelined driver: without
+// staging a CTA needs no shared memory and 96 x 88 registers, so three of them fit on an SM NEXT TO a persistent
+// contraction CTA (tri_i8mp<4>: 223 KB, 192 threads) and run beside it; a resident grid leaves no pending blocks that
+// could take an SM's shared memory in the gap between two contraction kernels.
 __device__ double g_exp2_tab[64];   // 2^(j/64), filled by tri_i8_init: the resident variant reads it through L1 instead of
                                     // spending 512 B of the ~9 KB of shared memory the contraction CTA leaves per SM
 __global__ void exp2_tab_kernel() { g_exp2_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0)); }
 template <int D_T>
 __global__ void __maxnreg__(88) kstar_i8_resident_kernel(const KstarI8Args aa, int n_s, int nsplit, int npanels) {
     static_assert(D_T > 0, "resident variant is instantiated for compile-time input dimensions only");
-    __shared__ double s_x[KS_RES_STAGE * D_T];
-    __shared__ double s_beta[KS_RES_STAGE];
     const double* s_tab = g_exp2_tab;
     const long n_items = (long)npanels * n_s * nsplit;
     for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int p = (int)(item % npanels);
         const int d = (int)((item / npanels) % n_s);
         const int split = (int)(item / ((long)npanels * n_s));
-        kstar_i8_item<D_T, KS_RES_STAGE>(aa, aa.panel0 + p, d, split, n_s, s_x, s_beta, s_tab);
+        kstar_i8_item<D_T, 0>(aa, aa.panel0 + p, d, split, n_s, nullptr, nullptr, s_tab);
     }
 }
 
