@@ -242,6 +242,8 @@ def run_product(args, rank, world, local_rank):
         gp.set_option("ksplit", args.ksplit)
     if args.i8_panel_group > 0:
         gp.set_option("i8_panel_group", args.i8_panel_group)
+    if args.i8_cluster > 0:
+        gp.set_option("i8_cluster", args.i8_cluster)
 
     # ---------------- device-resident inputs (the `value` arm)
     p0_d = torch.as_tensor(w.p0, device=dev)
@@ -464,6 +466,8 @@ def main():
                          "kernel over folded (equal-length) tiles")
     ap.add_argument("--i8-panel-group", type=int, default=0,
                     help="panels per L2 group of the tcgen05 contraction (even; 0 = automatic); tuning experiments")
+    ap.add_argument("--i8-cluster", type=int, default=0, choices=[0, 2, 4],
+                    help="CTAs per cluster of tri_i8m sharing one W stage by multicast (0 = library default)")
     ap.add_argument("--ksplit", type=int, default=0,
                     help="splits of the training points in the K* kernel (0 = automatic); tuning experiments")
     ap.add_argument("--redundant-factor", action="store_true",

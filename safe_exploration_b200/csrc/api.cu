@@ -102,6 +102,7 @@ struct segp_model {
     long opt_panel_group = 16;
     long opt_ksplit = 0;   // 0 = automatic
     long opt_i8_panel_group = 0;   // tri_i8m / tri_i8mp: panels per L2 group (even), 0 = automatic
+    long opt_i8_cluster = 2;       // tri_i8m: CTAs per cluster sharing one W stage by multicast (2 or 4)
     long opt_tri_mode = -1;   // -1 = automatic (4 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
                               // 1 = int8 tcgen05 single CTA, 2 = CTA pair (cta_group::2), 3 = persistent CTA pair,
                               // 4 = single-CTA MMAs over two K* planes at once, W multicast over a CTA pair
@@ -337,6 +338,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
         // panels per L2 group of tri_i8m / tri_i8mp (0 = 24): a sweep over 8..24 at C4 and C5 moved the launch time by
         // less than 0.5 % (scripts/gpu_pgroup.sh), so there is no automatic choice
         t.pgroup = (int)m->opt_i8_panel_group;
+        t.cluster = (int)m->opt_i8_cluster;
         t.npanel_cap = m->npanel_cap;
         t.b_cap = m->b_cap;
         t.dbg = nullptr;
@@ -1647,6 +1649,10 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_i8_panel_group = value;
         return SEGP_OK;
     }
+    if (strcmp(name, "i8_cluster") == 0 && (value == 2 || value == 4)) {
+        m->opt_i8_cluster = value;
+        return SEGP_OK;
+    }
     if (strcmp(name, "ksplit") == 0 && value >= 0) {
         m->opt_ksplit = value;
         return SEGP_OK;
@@ -1710,6 +1716,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "panel_group") == 0) *value = m->opt_panel_group;
     else if (strcmp(name, "ksplit") == 0) *value = m->opt_ksplit;
     else if (strcmp(name, "i8_panel_group") == 0) *value = m->opt_i8_panel_group;
+    else if (strcmp(name, "i8_cluster") == 0) *value = m->opt_i8_cluster;
     else if (strcmp(name, "tri_mode") == 0) *value = m->opt_tri_mode;
     else if (strcmp(name, "overlap") == 0) *value = m->opt_overlap;
     else if (strcmp(name, "i8_prof_ptr") == 0) *value = (long)(uintptr_t)m->i8_prof;

@@ -123,6 +123,7 @@ struct TriI8Args {
     int nblk, npanels;      // npanels = END of the panel range of this launch, panel0 its begin (tri_i8m only; else 0)
     int panel0;
     int pgroup;             // tri_i8m / tri_i8mp: panels per L2 group (even; 0 = 24)
+    int cluster;            // tri_i8m: CTAs per cluster sharing one W stage by multicast (2 or 4; 0 = 2)
     long npanel_cap, b_cap;
     int32_t* dbg;           // optional raw accumulators [I8_S][128 (256 for the pair kernel)][I8_N] of one tile
     int fix_bi;             // >= 0: single-tile self-test mode (block row, or block-row pair for the pair kernel)

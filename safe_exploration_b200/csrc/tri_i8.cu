@@ -997,13 +997,17 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask)
 constexpr int I8M_EPI_WARPS = 4 * (I8_N / 32);            // one warp per (TMEM lane quadrant, 32-column chunk)
 constexpr int I8M_THREADS = 64 + 32 * I8M_EPI_WARPS;      // producer, MMA issuer, 12 epilogue warps = 448
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8m_kernel(const TriI8Args a) {
+// CL = CTAs per cluster (2 or 4): the cluster works on CL adjacent panels of one block row; every CTA fetches 1/CL of
+// the W stage and multicasts it to all, so the L2 -> SM fill per CTA and k-block is 40/CL + 30 KB.
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8m_kernel(const TriI8Args a) {
+    static_assert(CL == 2 || CL == 4, "cluster of 2 or 4 CTAs");
     const uint32_t rank = cluster_ctarank();
-    const int pgroup = a.pgroup > 0 ? a.pgroup : I8_PANEL_GROUP;   // even
-    const int PG2 = pgroup / 2;   // panel pairs per L2 group
+    const int pgroup = a.pgroup > 0 ? a.pgroup : I8_PANEL_GROUP;   // multiple of CL
+    const int PG2 = pgroup / CL;   // clusters (CL adjacent panels) per L2 group
     int d, bi, panel;
     {
-        const int cid = blockIdx.x >> 1;
+        const int cid = blockIdx.x / CL;
         const int tiles_per_group = PG2 * a.nblk;
         const int npg = (a.npanels - a.panel0 + pgroup - 1) / pgroup;
         const int gid = cid / tiles_per_group;
@@ -1011,11 +1015,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
         d = gid / npg;
         const int pg = gid % npg;
         bi = a.nblk - 1 - r / PG2;
-        panel = a.panel0 + pg * pgroup + 2 * (r % PG2) + (int)rank;
+        panel = a.panel0 + pg * pgroup + CL * (r % PG2) + (int)rank;
         if (panel - (int)rank >= a.npanels) return;   // the whole cluster is past the last panel
     }
-    const bool valid = panel < a.npanels;             // odd panel count: the last cluster's second CTA only helps loading
-    const int panel_ld = valid ? panel : panel - 1;
+    const bool valid = panel < a.npanels;             // ragged panel count: the last cluster's spare CTAs only help loading
+    const int panel_ld = valid ? panel : a.npanels - 1;
 
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_addr(smem_raw);
@@ -1034,7 +1038,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
     if (threadIdx.x == 0) {
         for (int s = 0; s < I8_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 2);
+            mbar_init(empty_bar(s), CL);
         }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1052,7 +1056,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
 
     const int nk = 2 * (bi + 1);
     const int nkb_total = a.nblk * 2;
-    constexpr uint32_t A_HALF = I8_S * I8_A_TILE / 2;   // 20480 B
+    constexpr uint32_t A_HALF = I8_S * I8_A_TILE / CL;   // this CTA's share of the W stage: 20480 / 10240 B
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1065,7 +1070,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
                 const uint32_t dst = stage0 + (uint32_t)s * I8_STAGE_BYTES;
                 mbar_expect_tx(full_bar(s), I8_STAGE_BYTES);
                 bulk_g2s_multicast(dst + rank * A_HALF, wsrc + (long)it * (I8_S * I8_A_TILE), A_HALF, full_bar(s),
-                                   (uint16_t)3);
+                                   CL_MASK);
                 bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * I8_B_TILE, full_bar(s));
             }
         }
@@ -1099,7 +1104,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
                         }
                     }
                 }
-                tc_commit_multicast(empty_bar(s), (uint16_t)3);   // one of the two arrivals on BOTH CTAs' empty barriers
+                tc_commit_multicast(empty_bar(s), CL_MASK);   // one of the CL arrivals on EVERY CTA's empty barrier
             }
             tc_commit(tmem_full_bar);
         }
@@ -1132,14 +1137,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
 }
 
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
+    const int cl = a.cluster == 4 ? 4 : 2;
     const int pgroup = a.pgroup > 0 ? a.pgroup : I8_PANEL_GROUP;
+    if (pgroup % cl != 0) {
+        set_error("tri_i8m: the panel group (%d) must be a multiple of the cluster size (%d)", pgroup, cl);
+        return SEGP_ERR_INVALID;
+    }
     const int npg = (a.npanels - a.panel0 + pgroup - 1) / pgroup;
-    const long nclusters = (long)n_s * npg * (pgroup / 2) * a.nblk;
-    if (nclusters <= 0 || 2 * nclusters > 2147483647L) {
+    const long nclusters = (long)n_s * npg * (pgroup / cl) * a.nblk;
+    if (nclusters <= 0 || cl * nclusters > 2147483647L) {
         set_error("tri_i8m: grid of %ld cluster tiles out of range", nclusters);
         return SEGP_ERR_INVALID;
     }
-    tri_i8m_kernel<<<(unsigned)(2 * nclusters), I8M_THREADS, I8_SMEM, st>>>(a);
+    if (cl == 4)
+        tri_i8m_kernel<4><<<(unsigned)(4 * nclusters), I8M_THREADS, I8_SMEM, st>>>(a);
+    else
+        tri_i8m_kernel<2><<<(unsigned)(2 * nclusters), I8M_THREADS, I8_SMEM, st>>>(a);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }
@@ -1662,7 +1675,8 @@ int tri_i8_init() {
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel<I8M_EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)I8MP_SMEM));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8MP_SMEM));

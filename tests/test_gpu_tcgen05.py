@@ -107,6 +107,13 @@ def test_rollout_int8_pipe_matches_fp64_pipe_at_c4_model_size(se):
                              tri_mode=mode)
         out[mode] = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
         gp.close()
+    # tri_i8m with the W stage multicast over clusters of 4 instead of 2 CTAs (ragged: 700 candidates = 8 panels)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp, tri_mode=4)
+    gp.set_option("i8_cluster", 4)
+    out[44] = se.rollout(gp, w.p0, w.k_ff[:650], w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    gp.close()
+    assert np.array_equal(out[44].q_all, out[4].q_all[:650]) and np.array_equal(out[44].var_all, out[4].var_all[:650])
+    del out[44]
     assert all(np.all(o.status == 0) for o in out.values())
     # the two tcgen05 kernels execute the same exact integer arithmetic: identical bits
     assert np.array_equal(out[1].q_all, out[2].q_all) and np.array_equal(out[1].var_all, out[2].var_all)
