@@ -121,9 +121,8 @@ class BatchedGPSSM(object):
         torch = _lib.require_cuda()
         self._torch = torch
         self._lib = _lib.load()
-        if m is not None or Z is not None:
-            raise NotImplementedError("subset-of-data selection (m) and inducing points (Z) are not on this path; "
-                                      "pass the training set to use (SURVEY.md section 2: out of scope)")
+        if Z is not None:
+            raise NotImplementedError("inducing inputs Z (sparse GP regression) are not on this path")
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
@@ -149,7 +148,7 @@ class BatchedGPSSM(object):
         self.x_train = None
         self.y_train = None
         self.z = None
-        self.m = None
+        self.m = None if m is None else int(m)    # subset-of-data size (ssm_gpy/gaussian_process.py:36, 201-222)
         self._handle = ctypes.c_void_p()
         kern_ids = (ctypes.c_int * self.n_s_out)(*[_lib.KERN_IDS[k] for k in self.kern_types])
         _lib.check(self._lib.segp_create(ctypes.byref(self._handle), self.device.index, self.n_s_out, self.n_s_in,
@@ -233,8 +232,8 @@ class BatchedGPSSM(object):
         if opt_hyp:
             raise NotImplementedError("hyper-parameter optimisation is out of scope for the B200 path; "
                                       "pass fixed hyper-parameters via hyp=")
-        if m is not None or Z is not None:
-            raise NotImplementedError("subset-of-data selection is out of scope; pass the subset as X, y")
+        if Z is not None:
+            raise NotImplementedError("inducing inputs Z (sparse GP regression) are not on this path")
         if hyp is not None:
             self.hyp = self._normalise_hyp(hyp)
         if noise_diag is not None:
@@ -245,11 +244,25 @@ class BatchedGPSSM(object):
             raise ValueError("X must be N x {}".format(self.dim_in))
         if y_h.ndim != 2 or y_h.shape != (x_h.shape[0], self.n_s_out):
             raise ValueError("y must be N x {}".format(self.n_s_out))
+        # subset of data (ssm_gpy/gaussian_process.py:201-222): the GP conditions on m of the N points -- the
+        # max-variance selection on the device, or a random draw -- and keeps the whole set as x_train / y_train
+        m = self.m if m is None else int(m)
+        x_z, y_z = x_h, y_h
+        if m is not None:
+            if x_h.shape[0] < m:
+                warnings.warn("The desired number of datapoints is not available. Dataset consist of {} "
+                              "Datapoints! ".format(x_h.shape[0]))
+            elif x_h.shape[0] > m:
+                if choose_data:
+                    idx, _ = self.select_maxvar(x_h, m)
+                else:
+                    idx = np.random.choice(x_h.shape[0], size=m, replace=False)
+                x_z, y_z = np.ascontiguousarray(x_h[idx]), np.ascontiguousarray(y_h[idx])
         self.gp_trained = False
-        self._upload(x_h, y_h)
+        self._upload(x_z, y_z)
         self.x_train = x_h
         self.y_train = y_h
-        self.z = x_h
+        self.z = x_z
         self._factorize()
 
     def _factorize(self):
@@ -265,11 +278,11 @@ class BatchedGPSSM(object):
         x = np.asarray(x, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
         if not replace_old and self.x_train is not None:
-            if self.gp_trained and (noise_diag is None or float(noise_diag) == self.noise_diag):
+            if self.gp_trained and self.m is None and (noise_diag is None or float(noise_diag) == self.noise_diag):
                 return self.append_data(x, y)
             x = np.vstack((self.x_train, x))
             y = np.vstack((self.y_train, y))
-        self.train(x, y, noise_diag=noise_diag)
+        self.train(x, y, noise_diag=noise_diag, choose_data=choose_data)
 
     def append_data(self, x, y):
         """Append training points to the factorised model (segp_append): while the padded size does not grow only the
@@ -279,6 +292,8 @@ class BatchedGPSSM(object):
         y_h = _lib.host_f64(y).reshape(-1, self.n_s_out)
         if x_h.shape[0] != y_h.shape[0]:
             raise ValueError("x and y need the same number of rows")
+        if self.m is not None:      # subset-of-data models re-select from the whole set
+            return self.train(np.vstack((self.x_train, x_h)), np.vstack((self.y_train, y_h)))
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.segp_append(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
                                              _lib.current_stream(self.device)))
@@ -399,7 +414,7 @@ class BatchedGPSSM(object):
         host = np.empty((self.n_s_out, n_pad))
         self._torch.cuda.synchronize(self.device)
         _cudart_memcpy_d2h(self._torch, host, ptr, nbytes, self.device)
-        return np.ascontiguousarray(host[:, :self.x_train.shape[0]].T)
+        return np.ascontiguousarray(host[:, :self.z.shape[0]].T)
 
     def log_det_k(self):
         """log det (K_d + noise_d I) per output dimension, from the Cholesky factor."""
@@ -417,7 +432,7 @@ class BatchedGPSSM(object):
         is, :631-632): the training inputs, from the model's own factor.  A foreign x (n, D): K(x, x) is built and
         factorised on the device with the same hyper-parameters."""
         if x is None:
-            n = self.x_train.shape[0]
+            n = self.z.shape[0]
             return list(self.log_det_k() - n * np.log(self.total_noise()))
         x = _lib.host_f64(x)
         if x.ndim != 2 or x.shape[1] != self.dim_in:
@@ -467,6 +482,13 @@ class BatchedGPSSM(object):
             return x, y
         idx, _ = self.select_maxvar(x, m)
         return x[idx], y[idx]
+
+    def sample_from_gp(self, inp, size=10):
+        """ssm_gpy/gaussian_process.py:598-619: ``size`` samples of the (independent, full_cov=False) predictive
+        distribution per test input, (n, size, n_s_out); NumPy's global random state, like GPy."""
+        mu, var = self.predict(np.asarray(inp, dtype=np.float64))
+        std = np.sqrt(np.maximum(var, 0.0))
+        return mu[:, None, :] + std[:, None, :] * np.random.standard_normal((mu.shape[0], int(size), self.n_s_out))
 
     def to_dict(self):
         """ssm_gpy/gaussian_process.py:177-187 (inv_K is not materialised on this path)."""

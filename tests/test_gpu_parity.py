@@ -276,6 +276,48 @@ def test_append_data_equals_refactorisation(se, kerns):
     ref.close()
 
 
+def test_subset_of_data_and_sampling(se):
+    """SimpleGPModel's subset-of-data mode (ssm_gpy/gaussian_process.py:201-222, 372-392): with m given, the GP
+    conditions on m points chosen by the max-variance criterion (or at random) and keeps the whole set as x_train;
+    sample_from_gp draws from the independent predictive distributions (:598-619)."""
+    from oracle import gp_oracle, select_oracle
+    rng = np.random.default_rng(17)
+    n, n_s, n_u, m = 260, 2, 1, 90
+    dim = n_s + n_u
+    x = rng.uniform(-1, 1, (n, dim))
+    y = np.sin(x @ rng.standard_normal((dim, n_s))) + 0.05 * rng.standard_normal((n, n_s))
+    hyp = [{"lengthscale": rng.uniform(0.6, 1.4, dim), "variance": 1.0, "noise": 2e-2} for _ in range(n_s)]
+    gp = se.BatchedGPSSM(n_s, n_s, n_u, x, y, m=m, kern_types=["rbf", "mat52"], hyp=hyp)
+    ls, var, _, _ = gp_oracle.vectors_from_reference_hyp(["rbf", "mat52"], hyp, dim)
+    idx, _ = select_oracle.greedy_maxvar(x, ["rbf", "mat52"], ls, var, gp.total_noise(), m)
+    assert gp.x_train.shape == (n, dim) and gp.z.shape == (m, dim) and np.array_equal(gp.z, x[idx])
+    ref = se.BatchedGPSSM(n_s, n_s, n_u, x[idx], y[idx], kern_types=["rbf", "mat52"], hyp=hyp)
+    z = rng.uniform(-1, 1, (40, dim))
+    for a, b in zip(gp.predict(z), ref.predict(z)):
+        assert np.array_equal(a, b)
+    assert gp.beta.shape == (m, n_s) and len(gp.information_gain()) == n_s
+    # appended data: the subset is re-selected from the whole set
+    gp.update_model(x[:30] + 0.3, y[:30], replace_old=False)
+    assert gp.x_train.shape == (n + 30, dim) and gp.z.shape == (m, dim)
+    # random subset (choose_data=False): m rows of the data, reproducible through NumPy's global seed
+    np.random.seed(3)
+    gp.train(x, y, choose_data=False)
+    np.random.seed(3)
+    pick = np.random.choice(n, size=m, replace=False)
+    assert np.array_equal(gp.z, x[pick])
+    with pytest.warns(UserWarning):
+        gp.train(x[:50], y[:50])                      # fewer points than m: all of them, with the reference's warning
+    assert gp.z.shape == (50, dim)
+    np.random.seed(0)
+    smp = gp.sample_from_gp(z, size=4000)
+    mu, var_p = gp.predict(z)
+    assert smp.shape == (40, 4000, n_s)
+    assert np.allclose(smp.mean(axis=1), mu, atol=5 * np.sqrt(var_p.max() / 4000))
+    assert np.allclose(smp.var(axis=1), var_p, rtol=0.15)
+    gp.close()
+    ref.close()
+
+
 def test_empty_and_single_candidate_batches(se):
     """Ragged ends of the batch axis: no candidates at all, one candidate, one more than a 96-trajectory panel."""
     from safe_exploration_b200 import workloads
