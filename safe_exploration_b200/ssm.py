@@ -8,6 +8,7 @@ Mirrors, for the hot path only, the surface of
 * ``SimpleGPModel`` (reference safe_exploration/ssm_gpy/gaussian_process.py:15-634):
   ``n_s_out / n_s_in / n_u``, ``train``, ``update_model``, GPy-style ``predict(x_new,
   compute_gradients=...)``, ``predictive_gradients``, ``to_dict / from_dict``, ``information_gain``,
+  ``choose_datapoints_maxvar``, the subset-of-data mode (``m``), ``sample_from_gp``,
   ``x_train / y_train / z / beta / hyp / kern_types / gp_trained``.
 
 What is different, on purpose:
