@@ -105,3 +105,32 @@ def test_workloads_are_frozen_and_sized_like_baseline():
     for name in ("C2", "C3", "C5"):
         w = workloads.make(name, batch=1, n_train=16)
         assert np.max(np.abs(np.linalg.eigvals(w.a + w.b @ w.k_fb[0]))) < 1.0
+
+
+def test_ctypes_structs_match_the_c_layout(tmp_path):
+    """The ctypes mirrors of segp_reach_params / segp_score_params must have the size and field offsets the C compiler
+    gives the structs of include/segp.h (a field added on one side only would silently shift every later field)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from safe_exploration_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"segp_reach_params": _lib.ReachParams, "segp_score_params": _lib.ScoreParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "segp.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([gcc, "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
