@@ -228,7 +228,7 @@ def run_product(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     cfg = workloads.CONFIGS[args.config]
     b_per_gpu = args.batch_per_gpu or max(1, cfg[5] // cfg[6])
-    w = workloads.make(args.config, batch=b_per_gpu * world)
+    w = workloads.make(args.config, batch=b_per_gpu * world, n_train=args.n_train or None)
     s0, s1 = sd.shard_range(b_per_gpu * world, rank, world)
     k_ff_shard = np.ascontiguousarray(w.k_ff[s0:s1])
 
@@ -466,6 +466,9 @@ def main():
                          "kernel over folded (equal-length) tiles")
     ap.add_argument("--i8-panel-group", type=int, default=0,
                     help="panels per L2 group of the tcgen05 contraction (even; 0 = automatic); tuning experiments")
+    ap.add_argument("--n-train", type=int, default=0,
+                    help="override the configuration's number of training points (tuning experiments only: the line "
+                         "is then not a BASELINE configuration)")
     ap.add_argument("--i8-cluster", type=int, default=0, choices=[0, 2, 4],
                     help="CTAs per cluster of tri_i8m sharing one W stage by multicast (0 = library default)")
     ap.add_argument("--ksplit", type=int, default=0,
