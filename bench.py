@@ -6,12 +6,15 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus 8 --steps 5 --warmup 3
 
-Workload (BASELINE.json): config C4 = cart-pole, GP N=5000, H=20, n_s=4, B=65536 sharded over 8 GPUs, i.e.
-8192 candidate sequences per GPU; the same per-GPU shard is the N=1 workload (weak scaling: B = 8192 x N).
+Workload (BASELINE.json): config C4 = cart-pole, GP N=5000, H=20, n_s=4, B=65536 candidate sequences -- the
+configuration the metric is quoted on.  It fits one GPU (8 workspace chunks of 8192), so the default N=1 line runs ALL
+65536 candidates on the one GPU and N GPUs shard them (`--scaling strong`, B_g = 65536 / N: at N=8 exactly BASELINE
+C4).  `--scaling weak` keeps the 8192-candidate shard per GPU instead (B = 8192 x N; round 1's lines).
 A "step" is one pass of the hot path over the rank's batch: B_g independent H-step rollouts
 (multistep_reachability) = B_g x H one-step calls.  `value` times the device-resident path (inputs in HBM,
 CUDA events); `e2e` times the same call through the host-buffer C-ABI entry (segp_multistep_host: pinned host
-inputs, H2D + D2H inside the timed region).  Every rank prints nothing except rank 0's single JSON line.
+inputs, H2D + D2H inside the timed region) over the same number of steps.  Every rank prints nothing except rank 0's
+single JSON line.
 """
 import argparse
 import json
@@ -151,39 +154,73 @@ def parity_against_oracle(res, oracle_out):
             "max_rel_err": e, "rtol_gate": 1e-4, "ok": bool(max(e.values()) < 1e-4)}
 
 
+def _set_blas_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: give the CPU arm the host cores it is entitled to."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:   # pragma: no cover
+        pass
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(n)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm for the path, one trajectory at a time
-    (multistep_reachability over SimpleGPModel.__call__ with per-dimension explicit K^-1,
-    gp_reachability.py:159-212 / gp_models_utils_casadi.py:186-193) as restated in oracle/ ("port": GPy and
-    CasADi are not installable, /root/reference does not exist on the GPU box)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, rank 0 only (the
+    other ranks exit without work).  With oracle/_ref in place (oracle/build_ref.py: the reference's unmodified
+    gp_reachability.py / utils.py / utils_ellipsoid.py / gp_models_utils_casadi.py) the timed code IS the reference:
+    multistep_reachability (gp_reachability.py:159-212) over SimpleGPModel.__call__'s arithmetic (gp_pred,
+    gp_models_utils_casadi.py:177-197), one trajectory at a time as the reference runs it; only the posterior state
+    (GPy) and the mean Jacobian (CasADi AD) are restated (oracle/ref_ssm.py).  Without it: the oracle port."""
     if rank != 0:
         return
-    from oracle import reach_oracle
+    cores = os.cpu_count() or 1
+    _set_blas_threads(cores)
+    from oracle import reach_oracle, ref_loader
     from safe_exploration_b200 import workloads
     per_step = max(1, args.ref_rollouts)
     w = workloads.make(args.config, batch=per_step * (args.steps + args.warmup))
     ora = _oracle_model(w)
     ora._ensure_inv()
-    cores = os.cpu_count() or 1
+    kind = "port"
+    multistep = reach_oracle.multistep_reachability
+    ssm = ora
+    how = "oracle port of multistep_reachability + SimpleGPModel.__call__ (explicit-inverse form)"
+    if ref_loader.available():
+        from oracle.ref_ssm import ReferenceGP
+        ref_reach, _, _ = ref_loader.load()
+        multistep = ref_reach.multistep_reachability
+        ssm = ReferenceGP(ora, w.hyp, w.kern_types)
+        kind = "reference"
+        how = ("the reference's own multistep_reachability + gp_pred, unmodified files from {} (posterior state and "
+               "mean Jacobian restated: GPy / CasADi absent)".format(ref_loader.origin()))
 
     def one_step(i):
         for j in range(per_step):
-            reach_oracle.multistep_reachability(w.p0[:, None], ora, w.k_fb, w.k_ff[i * per_step + j], w.l_mu,
-                                                w.l_sigma, None, w.c_safety, 0, w.a, w.b)
+            multistep(w.p0[:, None], ssm, w.k_fb, w.k_ff[i * per_step + j], w.l_mu, w.l_sigma, None, w.c_safety, 0,
+                      w.a, w.b)
 
-    for i in range(args.warmup):
-        one_step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        one_step(args.warmup + i)
-    dt = time.perf_counter() - t0
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")     # the reference leaks complex128 from scipy.linalg.eig (utils.py:133-141)
+        for i in range(args.warmup):
+            one_step(i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            one_step(args.warmup + i)
+        dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = "{} rollouts per step, one trajectory at a time, explicit-inverse form, float64 NumPy".format(per_step)
+    sample = "{} rollouts per step (H={}), one trajectory at a time, float64 NumPy on {} BLAS threads: {}".format(
+        per_step, w.horizon, cores, how)
+    cfg = _config_dict(args, w, per_step, 1, "host")
+    cfg["workload"] = ("{}: GP N={} H={} n_s={} n_u={} kernel={}; CPU arm: {} rollouts per step on the host cores of "
+                       "rank 0 (launched with --gpus {}; no GPU is used)".format(
+                           w.name, w.n_train, w.horizon, w.n_s, w.n_u, w.kern_types[0], per_step, world))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": _config_dict(args, w, per_step, world, "host"),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -191,13 +228,19 @@ def run_reference(args, rank, world):
 
 def _config_dict(args, w, b_per_gpu, world, where):
     return {"workload": "{}: {} GP N={} H={} n_s={} n_u={} kernel={}; B={} candidate sequences per GPU x {} GPU(s) "
-                        "= {} (BASELINE C4 is 65536 over 8 GPUs)".format(
+                        "= {} (BASELINE {} is B={})".format(
                             w.name, "cart-pole" if w.n_s == 4 else ("pendulum" if w.n_s == 2 else "synthetic 10-D"),
-                            w.n_train, w.horizon, w.n_s, w.n_u, w.kern_types[0], b_per_gpu, world, b_per_gpu * world),
+                            w.n_train, w.horizon, w.n_s, w.n_u, w.kern_types[0], b_per_gpu, world, b_per_gpu * world,
+                            w.name, _cfg_batch(w.name)),
             "n_train": w.n_train, "horizon": w.horizon, "n_s": w.n_s, "n_u": w.n_u,
             "batch_per_gpu": b_per_gpu, "global_batch": b_per_gpu * world, "parallelism": "dp{}".format(world),
             "inputs": where,
             "l2_policy": _l2_policy(w, b_per_gpu)}
+
+
+def _cfg_batch(name):
+    from safe_exploration_b200 import workloads
+    return workloads.CONFIGS[name][5]
 
 
 def _l2_policy(w, b_per_gpu):
@@ -224,10 +267,16 @@ def run_product(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (the product has no CPU path)")
     se.ssm.DEFAULT_TRI_MODE = args.tri_mode
+    se.ssm.DEFAULT_I8_DIGITS = args.i8_digits
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     cfg = workloads.CONFIGS[args.config]
-    b_per_gpu = args.batch_per_gpu or max(1, cfg[5] // cfg[6])
+    if args.batch_per_gpu:
+        b_per_gpu = args.batch_per_gpu
+    elif args.scaling == "strong":
+        b_per_gpu = max(1, cfg[5] // world)          # the quoted configuration's B, whatever the GPU count
+    else:
+        b_per_gpu = max(1, cfg[5] // cfg[6])         # the per-GPU shard of the quoted configuration
     w = workloads.make(args.config, batch=b_per_gpu * world, n_train=args.n_train or None)
     s0, s1 = sd.shard_range(b_per_gpu * world, rank, world)
     k_ff_shard = np.ascontiguousarray(w.k_ff[s0:s1])
@@ -251,8 +300,18 @@ def run_product(args, rank, world, local_rank):
     kfb_d = torch.as_tensor(w.k_fb, device=dev)
     rargs = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
 
+    bsz_d, hor_d = k_ff_shard.shape[0], k_ff_shard.shape[1]
+    out_d = se.RolloutResult(torch.empty((bsz_d, hor_d, w.n_s), dtype=torch.float64, device=dev),
+                             torch.empty((bsz_d, hor_d, w.n_s, w.n_s), dtype=torch.float64, device=dev),
+                             torch.empty((bsz_d, hor_d, w.n_s), dtype=torch.float64, device=dev),
+                             torch.empty((bsz_d,), dtype=torch.int32, device=dev))
+    if args.no_graph:
+        gp.set_option("graph", 0)
+
     def step_device():
-        return se.rollout(gp, p0_d, kff_d, kfb_d, *rargs)
+        # the result buffers are re-used, as a sampling-MPC loop would: from the second call on the library replays the
+        # launches of a chunk as a CUDA graph
+        return se.rollout(gp, p0_d, kff_d, kfb_d, *rargs, out=out_d)
 
     def barrier():
         if world > 1:
@@ -267,8 +326,6 @@ def run_product(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    if os.environ.get("SEGP_I8_ABLATE"):
-        gp.set_option("i8_ablate", int(os.environ["SEGP_I8_ABLATE"]))   # profiling experiments only
     if os.environ.get("SEGP_I8_PROF"):
         gp.set_option("i8_prof", 1)
     launches0 = gp.get_option("launches")
@@ -304,8 +361,9 @@ def run_product(args, rank, world, local_rank):
     def step_host():
         return se.rollout(gp, w.p0, kff_host, w.k_fb, *rargs, out=out_pin)
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    step_host()
+    e2e_steps = max(1, args.e2e_steps or args.steps)      # the same number of steps as the device arm by default
+    for _ in range(2):
+        step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -343,43 +401,52 @@ def run_product(args, rank, world, local_rank):
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     share = (tri_ns * 1e-6) / ms if ms > 0 else None
     mode = gp.get_option("tri_mode_effective")
+    digits = gp.get_option("i8_digits_effective")
     if mode == 4 and gp.get_option("tri_persistent"):
         mode = 5   # automatic mode launched the persistent variant of the same contraction (short-tile models)
-    if mode in (1, 2, 3, 4, 5):
-        # tri_i8: 15 int8 digit-plane products per algorithmic multiply-add, exact int32 accumulation in TMEM.
+    rep = gp.precision_report()
+    if mode in (1, 4, 5):
+        # int8 digit planes: `products` int8 products per algorithmic multiply-add, exact int32 accumulation in TMEM.
         # `achieved` is ALGORITHMIC flop/s (n_s N^2 B per launch); `peak` is the measured bf16 figure of
         # MEASURED_PEAKS.json, so `frac` is the algorithmic fraction of the bf16 tensor peak: error-free splitting
-        # caps it at 2/15 (int8 runs at twice the bf16 rate, 15 products).  `pipe_*` say how busy the int8 pipe
-        # actually was: executed int8 op/s (padding and all 15 products counted) against the int8 rate measured
-        # in this run by segp_i8_peak (same instruction shape, no loads).
+        # caps it at 2/products (int8 runs at twice the bf16 rate).  `pipe_*` say how busy the int8 pipe actually
+        # was: executed int8 op/s (padding and all products counted) against the int8 rate measured in this run by
+        # segp_i8_peak (same instruction shape, no loads).
+        products = 10 if digits == 4 else 15
         chunk = gp.get_option("chunk")
         n_pad = gp.get_option("n_train_padded")
         nblk = n_pad // 128
         # 96-trajectory panels contracted per launch, averaged the same way (padding of the last panel counted)
         panels = sum(-(-min(chunk, b_per_gpu - c0) // 96) for c0 in range(0, b_per_gpu, chunk)) \
             * w.horizon * args.steps / max(tri_count, 1)
-        if mode in (2, 3):   # block-row pairs: the upper row of a pair also runs over the lower row's diagonal block
-            kblocks = sum(2 * (min(2 * bp + 1, nblk - 1) + 1) for bp in range((nblk + 1) // 2))
-        else:
-            kblocks = nblk * (nblk + 1) // 2
-        executed = 2.0 * 15 * w.n_s * (128 * 128 * kblocks) * panels * 96
+        kblocks = nblk * (nblk + 1) // 2
+        executed = 2.0 * products * w.n_s * (128 * 128 * kblocks) * panels * 96
         i8_96, i8_256 = _i8_peak(gp, local_rank, 96), _i8_peak(gp, local_rank, 256)
         pipe_tops = executed / tri_avg_s / 1e12 if tri_avg_s > 0 else None
-        roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 2: "tri_i8x2_kernel", 3: "tri_i8x2p_kernel", 4: "tri_i8m_kernel",
-                                                5: "tri_i8mp_kernel"}[mode],
-                    "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, " + ("cta_group::2 M=256" if mode in (2, 3) else "M=128")
-                            + " N=96 K=32, int32 accumulators in TMEM); "
-                            "float64-grade result from 5 x 5 balanced base-254 digit planes, 15 products",
+        roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 4: "tri_i8m_kernel", 5: "tri_i8mp_kernel"}[mode]
+                    + ("<split>" if digits == 4 else "<classic>"),
+                    "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, M=128 N=96/192 K=32, int32 accumulators in TMEM); "
+                            "float64-grade result from balanced base-254 digit planes, {} products ({})".format(
+                                products, "diagonal-split set, 4 x 4 digits + the diagonal's leading digit; guarded by "
+                                "the a-posteriori error estimate, flagged panels recomputed with 15 products"
+                                if digits == 4 else "5 x 5 digits"),
                     "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": (achieved / bf16_peak) if achieved else None,
                     "peak_source": peaks["_source"] + " bf16_tflops_sustained; algorithmic flop against the bf16 "
-                                   "peak, ceiling 2/15 = 0.133 for the 15-product int8 splitting",
-                    "frac_of_splitting_ceiling": (achieved / (bf16_peak * 2.0 / 15.0)) if achieved else None,
+                                   "peak, ceiling 2/{} = {:.3f} for the {}-product int8 splitting".format(
+                                       products, 2.0 / products, products),
+                    "frac_of_splitting_ceiling": (achieved / (bf16_peak * 2.0 / products)) if achieved else None,
+                    "int8_products": products,
                     "pipe_executed_tops": pipe_tops, "pipe_peak_tops_n96": i8_96, "pipe_peak_tops_n256": i8_256,
                     "pipe_frac_of_n96_peak": (pipe_tops / i8_96) if (pipe_tops and i8_96) else None,
+                    "pipe_frac_of_n256_peak": (pipe_tops / i8_256) if (pipe_tops and i8_256) else None,
                     "pipe_frac_of_2x_bf16_peak": (pipe_tops / (2.0 * bf16_peak)) if pipe_tops else None,
                     "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
-                    "algorithmic_flop_per_launch": flop_launch, "traffic": _traffic(args.config, mode)}
+                    "algorithmic_flop_per_launch": flop_launch,
+                    "traffic": _traffic(args.config, mode, digits),
+                    "traffic_source": "profiles/traffic.json: dram bytes of the committed ncu --set full capture of this "
+                                      "kernel and configuration (static; refreshed with the kernel), not measured in "
+                                      "this run"}
     else:
         dmma = _dmma_peak(gp, local_rank)
         roofline = {"bound": "tensor", "kernel": "tri_sumsq_kernel", "pipe": "fp64 DMMA (mma.sync m8n8k4.f64)",
@@ -389,7 +456,7 @@ def run_product(args, rank, world, local_rank):
                                    + peaks["_source"] + " holds only bf16",
                     "bf16_peak": bf16_peak, "frac_of_bf16_peak": (achieved / bf16_peak) if achieved else None,
                     "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
-                    "algorithmic_flop_per_launch": flop_launch, "traffic": _traffic(args.config, mode)}
+                    "algorithmic_flop_per_launch": flop_launch, "traffic": _traffic(args.config, mode, 0)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -408,6 +475,12 @@ def run_product(args, rank, world, local_rank):
                     "api": "safe_exploration_b200.rollout(out=pinned_result(...)) -> segp_multistep_host (pinned host k_ff and result buffers)",
                     "bit_identical_to_device_arm": same},
             "gpu_launches": int(launches), "roofline": roofline,
+            "precision": {"digit_set_products": (10 if digits == 4 else 15) if mode != 0 else None,
+                          "guard_rtol": rep["guard_rtol"], "guard_kappa": rep["guard_kappa"],
+                          "probe": {k: rep[k] for k in rep if k.startswith("probe_")},
+                          "panels_recomputed_with_15_products": int(rep["fallback_panels"]),
+                          "low_precision_flags": int((res.status & 8 != 0).sum().item())},
+            "cuda_graph": {"enabled": bool(gp.get_option("graph")), "graphs_cached": int(gp.get_option("graphs_cached"))},
             "schedule": ("two half-chunks software-pipelined over two streams (K*/ellipsoid kernels of one half under "
                          "the contraction of the other)" if gp.get_option("overlap") and mode in (4, 5) else "serial"),
             "clocks": sampler.summary(t_wall0, t_wall1),
@@ -420,14 +493,15 @@ def run_product(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-def _traffic(config, mode):
+def _traffic(config, mode, digits):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json:
     dram__bytes_read.sum + dram__bytes_write.sum), or None for configurations that were not captured."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
-        return json.load(f).get("{}:tri_mode{}".format(config, mode))
+        d = json.load(f)
+    return d.get("{}:tri_mode{}:digits{}".format(config, mode, digits), d.get("{}:tri_mode{}".format(config, mode)) if digits != 4 else None)
 
 
 def _i8_peak(gp, device, umma_n):
@@ -452,18 +526,24 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--batch-per-gpu", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end arm (0 = --steps)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the quoted configuration's B on every GPU count (B_g = B / N); weak: its "
+                         "per-GPU shard on every GPU (B = B_g x N)")
+    ap.add_argument("--i8-digits", type=int, default=0, choices=[0, 4, 5],
+                    help="digit set of the int8 contraction: 0 automatic (factorize-time probe), 4 = 10 products, "
+                         "5 = 15 products")
+    ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA-graph replay")
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", action="store_true",
                     help="two-stream half-chunk pipeline instead of the serial kstar -> tri -> ellipsoid schedule "
                          "(bit-identical; measured no faster, see DESIGN.md)")
-    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4, 5],
-                    help="variance contraction pipe: -1 auto (4 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
-                         "(one CTA per tile), 2 int8 tcgen05 CTA pairs (cta_group::2), 3 persistent CTA pairs, "
-                         "4 single-CTA MMAs over merged K* planes, W multicast over a CTA pair, 5 the same as a persistent "
-                         "kernel over folded (equal-length) tiles")
+    ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 4, 5],
+                    help="variance contraction pipe: -1 auto (int8 tcgen05 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
+                         "reference kernel (one CTA per tile), 4 single-CTA MMAs over merged K* planes, W multicast "
+                         "over a CTA pair, 5 the same as a persistent kernel over folded (equal-length) tiles")
     ap.add_argument("--i8-panel-group", type=int, default=0,
                     help="panels per L2 group of the tcgen05 contraction (even; 0 = automatic); tuning experiments")
     ap.add_argument("--n-train", type=int, default=0,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SEGP_ABI_VERSION 1
+#define SEGP_ABI_VERSION 2
 
 /* status codes (Python wrapper maps them: INVALID->ValueError, CUDA->RuntimeError,
  * NOT_POSDEF->numpy.linalg.LinAlgError, NOT_TRAINED->RuntimeError, UNSUPPORTED->NotImplementedError) */
@@ -52,6 +52,9 @@ extern "C" {
 #define SEGP_STATUS_BAD_VARIANCE 2 /* predictive variance <= 0 or NaN (sqrt undefined)        */
 #define SEGP_STATUS_ZERO_BOUND 4   /* a box bound was <= 0: the reference asserts here
                                       (utils_ellipsoid.py:226-228)                            */
+#define SEGP_STATUS_LOW_PRECISION 8 /* int8 tensor-core path only: the a-posteriori error estimate of the variance
+                                      contraction exceeds guard_rtol x sigma^2 even on the 15-product digit set, i.e.
+                                      sigma^2 may miss the tolerance; re-run with tri_mode 0 (float64)             */
 
 /* limits of this build */
 #define SEGP_MAX_NS 16
@@ -106,14 +109,23 @@ int segp_factorize(segp_model* m, void* stream);
  * Synchronous.  SEGP_ERR_NOT_POSDEF as segp_factorize. */
 int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, void* stream);
 
-/* Multi-GPU setup: the factorised state is n_buffers device buffers.  Rank `root` factorises, every
- * rank calls segp_alloc_factor_buffers (non-root ranks instead of segp_factorize), the host broadcasts
- * each buffer (one ncclBroadcast per buffer via torch.distributed), then non-root ranks call
- * segp_mark_factorized.  No collective is needed afterwards. */
+/* Multi-GPU setup: the factorised state is ONE device allocation (buffer 0: beta, log-determinants, the int8 digit
+ * planes of W = L^-1 with their row factors and error-model weights, and the decisions of the factorize-time probe).
+ * Rank `root` factorises, every other rank calls segp_alloc_factor_buffers instead of segp_factorize, the host
+ * broadcasts buffer 0 (one ncclBroadcast via torch.distributed), then the non-root ranks call segp_mark_factorized.
+ * No collective is needed afterwards.  Only a model that runs the float64 contraction (composite kernels, more
+ * than 16384 padded training points, tri_mode 0 / keep_fp64, or a probe that found the int8 path too coarse; option
+ * "fp64_operand_needed") has a second buffer, the float64 DMMA operand: segp_num_factor_buffers == 2 on the
+ * factorising rank; the others call segp_alloc_fp64_operand and receive buffer 1 before segp_mark_factorized. */
 int segp_alloc_factor_buffers(segp_model* m);
+int segp_alloc_fp64_operand(segp_model* m);
 int segp_num_factor_buffers(segp_model* m);
 int segp_factor_buffer(segp_model* m, int index, void** d_ptr, size_t* bytes);
 int segp_mark_factorized(segp_model* m);
+
+/* beta_d = (K_d + noise_d I)^-1 y_d, h_out [n_s_out x n_train] (HOST): posterior.woodbury_vector, what
+ * SimpleGPModel keeps as self.beta (ssm_gpy/gaussian_process.py:261). */
+int segp_beta(segp_model* m, double* h_out);
 
 /* log det(K_d) per output dimension from the Cholesky factor (h_out[n_s_out], HOST).
  * Building block of SimpleGPModel.information_gain (ssm_gpy/gaussian_process.py:621-634). */
@@ -140,6 +152,11 @@ int segp_select_maxvar(int device, int n, int n_s_out, int dim, const int* kern_
  * and StateSpaceModel.predict (state_space_models.py:74-104). */
 int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
                  void* stream);
+/* The same with a per-input status word, d_status [n_batch] int32 out or NULL: SEGP_STATUS_BAD_VARIANCE and, on the
+ * int8 tensor-core path, SEGP_STATUS_LOW_PRECISION (the reference has no counterpart: it is float64 throughout,
+ * ssm_gpy/gaussian_process.py:546-568). */
+int segp_predict_ex(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
+                    int32_t* d_status, void* stream);
 
 /* what the n_s x n_s matrix carried along a rollout means */
 #define SEGP_PROP_ELLIPSOID 0       /* ellipsoid shape matrix Q, gp_reachability.py:19-156 (default)                */
@@ -284,30 +301,50 @@ int segp_i8_peak(int device, int umma_n, int iters, double* tops);
  * 3 = the same products in diagonal-major order (umma_n must be 96 for 2 and 3). */
 int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double* tops);
 
-/* Diagnostic: run ONE tile of a tcgen05 contraction kernel on caller-supplied digit planes and return the raw
- * TMEM accumulators, so descriptor / swizzle / TMEM-layout errors show up as exact integer mismatches.
- *   variant 1: single-CTA kernel (M = 128 rows); variant 2: CTA-pair kernel (cta_group::2, M = 256 rows; k_blocks
- *   even; rows 0..127 are the upper block row, whose last 128 columns are outside its k-range and read as zero)
- *   h_a [5][M][K] int8, h_b [5][96][K] int8 with K = 128 * k_blocks (HOST)
- *   h_acc [5][M][96] int32: h_acc[g] = sum over planes a + c == g of A_a B_c^T
- *   h_colsum [M/128][96]: per block row, sum over rows of (sum_g h_acc[g] * 254^(4-g))^2 as float64 */
+/* Diagnostic: run ONE block row of a tcgen05 contraction kernel on caller-supplied digit planes, so descriptor /
+ * swizzle / TMEM-layout errors show up as exact integer mismatches.
+ *   variant 1: reference kernel (one CTA per tile); 4: production kernel tri_i8m, classic digit set (15 products);
+ *   6: tri_i8m, diagonal-split set (10 products + the diagonal's leading digit): plane 0 of h_a is that digit's plane
+ *   and may be non-zero on the diagonal (row r, column K - 128 + r) only
+ *   h_a [5][128][K] int8, h_b [5][96][K] int8 with K = 128 * k_blocks (HOST)
+ *   h_acc [5][128][96] int32 (variant 1 only): h_acc[g] = sum over planes a + c == g of A_a B_c^T
+ *   h_colsum [96]: sum over rows of (sum_g acc[g] * 254^(4-g))^2 as float64, where for variant 6
+ *                  acc[g] = sum over planes a + c == g, a >= 1 or (a == 0), c <= 4, a + c <= 4 */
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum);
 
 /* Tuning knobs / introspection ("chunk": trajectories per workspace chunk, "panel_group", "ksplit",
- * "tri_mode": which kernel runs the variance contraction: -1 = automatic (default: 4 when the padded training
- *   size is <= 16384, else 0), 0 = fp64 DMMA (mma.sync m8n8k4.f64), 1..5 = int8 digit planes on tcgen05:
- *   1 one CTA per tile, 2 CTA pairs (tcgen05.mma.cta_group::2, M = 256), 3 persistent CTA pairs, 4 single-CTA MMAs
- *   spanning two K* digit planes (N = 192) with the W stage multicast over a CTA pair, 5 the same as a persistent
- *   kernel over folded (equal-length) tiles (automatic mode launches it instead of 4 for models of <= 32 block rows
- *   with enough tiles; read-only "tri_persistent" = 1 if the last launch did); 1..5 give bit-identical results;
- *   read-only "tri_mode_effective";
+ * "tri_mode": which kernel runs the variance contraction: -1 = automatic (default: int8 digit planes on tcgen05 when
+ *   the padded training size is <= 16384, the kernels are not composite and the factorize-time probe did not find the
+ *   int8 path too coarse; else 0), 0 = fp64 DMMA (mma.sync m8n8k4.f64), 1 = int8 reference kernel (one CTA per tile,
+ *   15 products; test cross-check), 4 = tri_i8m: single-CTA MMAs spanning two K* digit planes (N = 192) with the W
+ *   stage multicast over a CTA pair, 5 = the same as a persistent kernel over folded (equal-length) tiles (automatic
+ *   mode launches it instead of 4 for models of <= 32 block rows with enough tiles; read-only "tri_persistent" = 1 if
+ *   the last launch did); read-only "tri_mode_effective";
+ * "i8_digits": digit set of the first contraction pass: 0 = automatic (the probe's choice, read-only
+ *   "i8_digits_effective"), 5 = classic set, 15 int8 products, 4 = diagonal-split set, 10 products;
+ * "guard": 1 (default) = a-posteriori precision guard: on the 10-product set, panels whose error estimate exceeds
+ *   guard_rtol x sigma^2 are recomputed on the 15-product set (read-only "fallback_panels" counts them); whatever still
+ *   exceeds it gets SEGP_STATUS_LOW_PRECISION;  "probe": 1 (default) = calibrate the error model at segp_factorize;
+ * "keep_fp64": keep the float64 operand resident after segp_factorize (else it is dropped unless needed, and a later
+ *   tri_mode 0 factorises again); read-only "fp64_operand_resident", "fp64_operand_needed", "factor_bytes";
+ * "graph": 1 (default) = replay the launches of a segp_multistep call as a CUDA graph from the second call with the
+ *   same arguments on (read-only "graphs_cached");
  * "overlap": 1 = run a chunk as two half-chunks software-pipelined over two internal streams (tri_mode 4/5);
- * "time_tri": 1 = bracket every tri_sumsq launch with a CUDA-event pair on its stream (resets the counters);
+ * "time_tri": 1 = bracket every contraction launch with a CUDA-event pair on its stream (resets the counters);
  * read-only: "launches" = kernels launched by this handle so far, "n_train_padded", "workspace_bytes",
- * "tri_launches" / "tri_ns" = number and total device nanoseconds of the timed tri_sumsq launches). */
+ * "tri_launches" / "tri_ns" = number and total device nanoseconds of the timed contraction launches). */
 int segp_set_option(segp_model* m, const char* name, long value);
 int segp_get_option(segp_model* m, const char* name, long* value);
+
+/* Real-valued parameters: "guard_rtol" (1e-4: the tolerance the precision guard protects; BASELINE.json's rtol),
+ * "guard_kappa" (6: standard deviations of the error model that must fit inside it); read-only statistics of the
+ * factorize-time probe (1024 uniform inputs over the training box against the float64 contraction, worst output
+ * dimension): "probe_ran", "probe_frac4" / "probe_frac5" (fraction the guard flags on the 10- / 15-product set),
+ * "probe_err4/5" (max abs error of |L^-1 k*|^2), "probe_rel4/5" (max error / sigma^2), "probe_ratio4/5" (max error in
+ * predicted standard deviations), "probe_rho4/5" (calibration factors applied), "probe_min_var_ratio". */
+int segp_set_param(segp_model* m, const char* name, double value);
+int segp_get_param(segp_model* m, const char* name, double* value);
 
 #ifdef __cplusplus
 }

@@ -1,22 +1,39 @@
-"""Import the reference's OWN ellipsoid-half modules, unmodified, from /root/reference.
+"""Import the reference's OWN modules of the path, unmodified.
 
 ORACLE / TEST INFRASTRUCTURE -- see oracle/__init__.py.
 
-Only works in the build container (the GPU box has no /root/reference): callers must check
-``available()`` and skip otherwise.  Nothing is copied: the modules are imported from where
-they lie, with oracle/_casadi_shim on sys.path to satisfy ``from casadi import reshape``
-(reference safe_exploration/utils.py:14).
+In the build container the modules are imported from where they lie under /root/reference; on the GPU box (no
+/root/reference) from oracle/_ref, the byte-for-byte placement oracle/build_ref.py makes at build time (git-ignored,
+travels with the snapshot).  Callers must check ``available()`` and skip otherwise.  oracle/_casadi_shim on sys.path
+satisfies ``from casadi import reshape`` (reference safe_exploration/utils.py:14).
 """
 import os
 import sys
 import warnings
 
-REFERENCE_ROOT = "/root/reference"
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_casadi_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "_casadi_shim")
+
+
+def _root():
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "safe_exploration", "gp_reachability.py")):
+            return cand
+    return None
+
+
+REFERENCE_ROOT = _root() or "/root/reference"
 
 
 def available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "safe_exploration", "gp_reachability.py"))
+
+
+def origin():
+    """'reference tree' (/root/reference) or 'oracle/_ref' (its byte-for-byte placement), or None."""
+    if not available():
+        return None
+    return "reference tree" if REFERENCE_ROOT == "/root/reference" else "oracle/_ref"
 
 
 def _prepare_path():

@@ -12,7 +12,7 @@ from .ssm import BatchedGPSSM  # noqa: F401
 from . import gp_reachability, safempc_sampling, uncertainty_propagation, utils, utils_ellipsoid  # noqa: F401
 from .safempc_sampling import SamplingSafeMPC, best_candidate, score_rollouts  # noqa: F401
 from .cautious_mpc_sampling import SamplingCautiousMPC  # noqa: F401
-from .gp_reachability import (lin_ellipsoid_safety_distance, multistep_reachability,  # noqa: F401
+from .gp_reachability import (RolloutResult, lin_ellipsoid_safety_distance, multistep_reachability,  # noqa: F401
                               onestep_reachability, pinned_result, rollout)
 
 __version__ = "0.1.0"

@@ -24,6 +24,7 @@ COMPOSITE_KERNELS = ("lin_rbf", "lin_mat52")
 STATUS_NONFINITE = 1
 STATUS_BAD_VARIANCE = 2
 STATUS_ZERO_BOUND = 4
+STATUS_LOW_PRECISION = 8
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int_p = ctypes.POINTER(ctypes.c_int)
@@ -68,13 +69,16 @@ PROTOTYPES = {
     "segp_factorize": (_int, [_vp, _vp]),
     "segp_append": (_int, [_vp, _int, _c_double_p, _c_double_p, _vp]),
     "segp_alloc_factor_buffers": (_int, [_vp]),
+    "segp_alloc_fp64_operand": (_int, [_vp]),
     "segp_num_factor_buffers": (_int, [_vp]),
     "segp_factor_buffer": (_int, [_vp, _int, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t)]),
     "segp_mark_factorized": (_int, [_vp]),
+    "segp_beta": (_int, [_vp, _c_double_p]),
     "segp_logdet": (_int, [_vp, _c_double_p]),
     "segp_select_maxvar": (_int, [_int, _int, _int, _int, _c_int_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                   _c_double_p, _c_double_p, _int, _c_int_p, _c_double_p, _vp]),
     "segp_predict": (_int, [_vp, _long, _vp, _vp, _vp, _vp, _vp]),
+    "segp_predict_ex": (_int, [_vp, _long, _vp, _vp, _vp, _vp, _vp, _vp]),
     "segp_multistep": (_int, [_vp, _long, _int, _vp, _long, _vp, _long, _vp, _vp, _long, _vp, _long,
                               ctypes.POINTER(ReachParams), _vp, _vp, _vp, _vp, _vp]),
     "segp_multistep_host": (_int, [_vp, _long, _int, _vp, _long, _vp, _long, _vp, _vp, _long, _vp, _long,
@@ -97,6 +101,8 @@ PROTOTYPES = {
     "segp_i8_selftest": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
     "segp_set_option": (_int, [_vp, ctypes.c_char_p, _long]),
     "segp_get_option": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_long)]),
+    "segp_set_param": (_int, [_vp, ctypes.c_char_p, _dbl]),
+    "segp_get_param": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_dbl)]),
 }
 
 _lib = None

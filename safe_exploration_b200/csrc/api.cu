@@ -50,6 +50,32 @@ static void dev_free(T*& p) {
 
 using namespace segp;
 
+
+namespace segp {
+constexpr int META_N = 32;      // doubles at the head of the factor arena: decisions of the factorising rank
+constexpr int PROBE_N = 1024;   // probe inputs of the factorize-time calibration of the int8 error model
+// probe statistics (read through segp_get_param "probe_*"); worst case over the output dimensions
+enum {
+    PS_RAN = 0,   // 1 if the probe ran
+    PS_FRAC4,     // fraction of probe inputs the guard flags on the 10-product set
+    PS_FRAC5,     // ... on the 15-product set
+    PS_ERR4,      // max |error of |v|^2| of the 10-product set against float64
+    PS_ERR5,
+    PS_REL4,      // max error relative to sigma^2
+    PS_REL5,
+    PS_RATIO4,    // max |error| / (predicted 1-sigma): how well the error model holds (before calibration)
+    PS_RATIO5,
+    PS_RHO4,      // calibration factor applied to the model's standard deviation (>= 1)
+    PS_RHO5,
+    PS_MINVAR,    // smallest sigma^2 / k** over the probe inputs
+    PROBE_STATS
+};
+}  // namespace segp
+
+namespace segp {
+struct GraphEntry;
+}
+
 struct segp_model {
     int device = 0;
     int n_s = 0, n_in = 0, n_u = 0, dim = 0;
@@ -64,9 +90,21 @@ struct segp_model {
     double* yp = nullptr;      // [n_s][n_pad] targets, zero padded
     double* invls = nullptr;   // [n_s][dim]
     double* var = nullptr;     // [n_s]
+    // factorised state: ONE device allocation (`arena`), so a multi-GPU setup broadcasts it with one collective
+    unsigned char* arena = nullptr;
+    size_t arena_bytes = 0;
+    double* meta = nullptr;    // [META_N] decisions of the factorising rank (digit set, float64 fallback, ...)
     double* beta = nullptr;    // [n_s][n_pad]
-    double* wt = nullptr;      // [n_s][ntri][128*128]
     double* logdet = nullptr;  // [n_s]
+    int8_t* wi8 = nullptr;     // [n_s][nblk (nblk+1)][I8_S][I8_A_TILE] digit planes of W, classic set (15 products)
+    double* rowfac = nullptr;  // [n_s][n_pad] per-row factors of the classic set
+    int8_t* wi8s = nullptr;    // [n_s][nblk (nblk+1)][I8_SS][I8_A_TILE] diagonal-split set (10 products)
+    int8_t* wm1 = nullptr;     // [n_s][nblk][2][I8_A_TILE] leading digit of the diagonal (split set)
+    double* rowfac_s = nullptr;
+    float* werr5 = nullptr;    // [n_s][n_pad] error-model variance weights of the two sets (calibrated by the probe)
+    float* werr4 = nullptr;
+    // float64 DMMA operand: only kept when the float64 contraction is (or may be) used
+    double* wt = nullptr;      // [n_s][ntri][128*128]
     // composite (linear x stationary + linear) kernels: segp_set_linear_terms
     bool has_composite = false, has_linear_terms = false;
     std::vector<double> h_plin, h_lin;
@@ -79,16 +117,26 @@ struct segp_model {
     double* wdense = nullptr;  // [n_s][n_pad][n_pad] W = L^-1 kept dense for segp_append (only if opt_keep_w)
     long opt_keep_w = 0;       // keep wdense after factorising (set by the first segp_append)
     bool last_append_incremental = false;
-    int8_t* wi8 = nullptr;     // [n_s][nblk (nblk+1)][I8_S][I8_A_TILE] digit planes of W (tcgen05 path)
-    double* rowfac = nullptr;  // [n_s][n_pad] per-row factors of the digit planes
+    // precision management of the int8 path
+    int i8_primary = 5;        // digit set of the first contraction pass: 4 (10 products) or 5 (15 products)
+    bool auto_fp64 = false;    // the probe found even the 15-product set short of guard_rtol: automatic mode runs float64
+    long opt_i8_digits = 0;    // 0 = automatic (probe), 4 / 5 = forced
+    long opt_guard = 1;        // run the a-posteriori precision guard (flag + 15-product recomputation of flagged panels)
+    long opt_probe = 1;        // calibrate the error model at factorize time (PROBE_N random inputs against float64)
+    long opt_keep_fp64 = 0;    // keep the float64 operand after factorising even when automatic mode does not need it
+    double guard_rtol = 1e-4, guard_kappa = 6.0;
+    double probe_stat[PROBE_STATS] = {0};
+    int force_mode = -2, force_digits = 0;   // probe only: overrides of the kernel selection
+    unsigned int* fallback_counter = nullptr;   // device: panels recomputed on the 15-product set so far
     // workspace
     long b_cap = 0;
     int nsplit = 1, blocks_per_split = 1;
     double* ks = nullptr;      // fp64 K* block (DMMA path)
     int8_t* ki8 = nullptr;     // digit planes of the K* block (tcgen05 path)
+    float* epart = nullptr;    // [n_s][nblk][b_cap] error-model partials (tcgen05 path)
+    int32_t* pflag = nullptr;  // [npanel_cap] panels to recompute on the 15-product set
     long npanel_cap = 0;
-    int ws_mode = 0;           // tri mode the current workspace is laid out for (0 fp64 ks, 1 ki8, 2 ki8 split halves)
-    int8_t* i8zero = nullptr;  // I8_S * I8_A_TILE zero bytes (pair kernel)
+    int ws_mode = 0;           // layout of the current workspace: 0 = fp64 ks, 1 = ki8
     double* mu_part = nullptr;
     double* jac_part = nullptr;
     double* qpart = nullptr;
@@ -97,47 +145,71 @@ struct segp_model {
     // host-entry staging (grown on demand)
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    cudaStream_t s_host = nullptr;   // stream of the host entry points
+    cudaStream_t s_cap = nullptr;    // capture stream of the CUDA-graph path
+    cudaStream_t s_copy = nullptr;   // device-to-host result copies of the host entry points
+    cudaEvent_t ev_chunk = nullptr;
     // options
     long opt_chunk = 8192;
     long opt_panel_group = 16;
     long opt_ksplit = 0;   // 0 = automatic
     long opt_i8_panel_group = 0;   // tri_i8m / tri_i8mp: panels per L2 group (even), 0 = automatic
     long opt_i8_cluster = 2;       // tri_i8m: CTAs per cluster sharing one W stage by multicast (2 or 4)
-    long opt_tri_mode = -1;   // -1 = automatic (4 when n_pad <= I8_MAX_NPAD, else 0), 0 = fp64 DMMA,
-                              // 1 = int8 tcgen05 single CTA, 2 = CTA pair (cta_group::2), 3 = persistent CTA pair,
-                              // 4 = single-CTA MMAs over two K* planes at once, W multicast over a CTA pair
+    long opt_tri_mode = -1;   // -1 = automatic (int8 tcgen05 when n_pad <= I8_MAX_NPAD, the kernels are not composite and
+                              // the probe did not ask for float64; else 0), 0 = fp64 DMMA, 1 = int8 reference kernel (one
+                              // CTA per tile, classic set; test cross-check), 4 = tri_i8m (single-CTA MMAs over two K*
+                              // planes at once, W multicast over a CTA pair), 5 = tri_i8mp (the same, persistent)
     long opt_overlap = 0;     // 1 = software-pipeline two half-chunks over two internal streams (tri_mode 4 / 5): the
                               // FP64-bound K* kernel of one half runs as a resident grid of small CTAs NEXT TO the
                               // persistent contraction (tri_i8mp<4>) of the other.  Bit-identical.  The kernels do
-                              // share the SMs, but the co-resident K* kernel runs ~7x slower than alone (most likely
-                              // queued behind the contraction's shared-memory operand traffic) and becomes the
+                              // share the SMs, but the co-resident K* kernel runs ~7x slower than alone and becomes the
                               // critical path: 6 % slower than the serial schedule at C4, off by default
                               // (profiles/round1/overlap_pipeline_c3_c4_c5.txt)
     cudaStream_t s_hi = nullptr, s_lo = nullptr;   // internal streams of the pipelined driver (created on first use)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ks[2] = {nullptr, nullptr}, ev_tri[2] = {nullptr, nullptr};
-    long opt_i8_ablate = 0;   // profiling only, see TriI8Args::ablate
     long long* i8_prof = nullptr;   // profiling only: [128][8] counters of the persistent kernel's MMA threads
     bool last_tri_persistent = false;   // which tcgen05 kernel the last contraction launch used (automatic mode)
+    int last_tri_digits = 0;
     long launches = 0;
-    // optional per-launch timing of tri_sumsq (bench.py roofline): event pairs recorded on the launching stream
+    // optional per-launch timing of the contraction (bench.py roofline): event pairs recorded on the launching stream
     bool time_tri = false;
     std::vector<cudaEvent_t> tri_events;
     size_t tri_events_used = 0;
+    // CUDA-graph cache of the rollout schedule (segp_multistep, option "graph")
+    long opt_graph = 1;
+    segp::GraphEntry* graphs = nullptr;
 };
 
 namespace segp {
 
+struct GraphEntry {
+    std::vector<unsigned char> key;
+    cudaGraphExec_t exec = nullptr;
+    long launches = 0, events = 0;
+    GraphEntry* next = nullptr;
+};
+
+static void free_graphs(segp_model* m) {
+    while (m->graphs != nullptr) {
+        GraphEntry* g = m->graphs;
+        m->graphs = g->next;
+        if (g->exec != nullptr) cudaGraphExecDestroy(g->exec);
+        delete g;
+    }
+}
+
 static void free_model_buffers(segp_model* m) {
+    free_graphs(m);
     dev_free(m->xs);
     dev_free(m->yp);
     dev_free(m->invls);
     dev_free(m->var);
-    dev_free(m->beta);
+    dev_free(m->arena);
+    m->arena_bytes = 0;
+    m->meta = m->beta = m->logdet = m->rowfac = m->rowfac_s = nullptr;
+    m->wi8 = m->wi8s = m->wm1 = nullptr;
+    m->werr5 = m->werr4 = nullptr;
     dev_free(m->wt);
-    dev_free(m->logdet);
-    dev_free(m->wi8);
-    dev_free(m->rowfac);
-    dev_free(m->i8zero);
     dev_free(m->wdense);
     dev_free(m->xraw);
     dev_free(m->plin);
@@ -148,8 +220,11 @@ static void free_model_buffers(segp_model* m) {
 }
 
 static void free_workspace(segp_model* m) {
+    free_graphs(m);
     dev_free(m->ks);
     dev_free(m->ki8);
+    dev_free(m->epart);
+    dev_free(m->pflag);
     m->npanel_cap = 0;
     dev_free(m->mu_part);
     dev_free(m->jac_part);
@@ -162,10 +237,23 @@ static void free_workspace(segp_model* m) {
 
 // the int8 digit planes assume kernel values in [0, s_f^2]: composite kernels (unbounded linear terms) run in float64
 static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD && !m->has_composite; }
+// which kernel runs the variance contraction: 0 fp64 DMMA, 1 int8 reference kernel, 4 tri_i8m, 5 tri_i8mp
 static int tri_mode(const segp_model* m) {
+    if (m->force_mode > -2) return m->force_mode == -1 ? 4 : m->force_mode;
     if (m->has_composite) return 0;
     if (m->opt_tri_mode >= 0) return (int)m->opt_tri_mode;
-    return i8_capable(m) ? 4 : 0;
+    return (i8_capable(m) && !m->auto_fp64) ? 4 : 0;
+}
+// digit set of the first contraction pass (int8 modes 4 / 5; the reference kernel knows the classic set only)
+static int tri_digits(const segp_model* m) {
+    if (m->force_digits != 0) return m->force_digits;
+    if (tri_mode(m) == 1) return 5;
+    if (m->opt_i8_digits != 0) return (int)m->opt_i8_digits;
+    return m->i8_primary;
+}
+static double guard_gs(const segp_model* m) {
+    const double r = 2.0 * m->guard_kappa / m->guard_rtol;
+    return r * r;
 }
 
 static int ensure_workspace(segp_model* m, long n_batch) {
@@ -175,11 +263,15 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     const int mode = tri_mode(m);
     const bool i8 = mode != 0;
     if (i8 && m->wi8 == nullptr) {
-        set_error("tri_mode=%d (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", mode, I8_MAX_NPAD,
-                  m->n_pad);
+        set_error("tri_mode=%d (int8 tcgen05) needs n_train_padded <= %ld and non-composite kernels; this model has %d",
+                  mode, I8_MAX_NPAD, m->n_pad);
         return SEGP_ERR_UNSUPPORTED;
     }
-    if (mode != m->ws_mode && m->b_cap > 0) free_workspace(m);
+    if (!i8 && m->wt == nullptr) {
+        set_error("internal: the float64 operand is not resident");
+        return SEGP_ERR_INVALID;
+    }
+    if ((i8 ? 1 : 0) != m->ws_mode && m->b_cap > 0) free_workspace(m);
     // split of the N-length reductions of kstar_mean_jac over blockIdx.z so small batches still fill 148 SMs
     const long col_blocks = want / TILE;
     int nsplit;
@@ -194,6 +286,7 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     if (want <= m->b_cap && nsplit == m->nsplit && bps == m->blocks_per_split) return SEGP_OK;
     if (want <= m->b_cap) {
         // same capacity, only the split changed: partial buffers are sized for nblk splits, nothing to do
+        free_graphs(m);
         m->nsplit = nsplit;
         m->blocks_per_split = bps;
         return SEGP_OK;
@@ -210,16 +303,22 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     SEGP_CHECK(dev_alloc(&m->mu_part, n_mu));
     SEGP_CHECK(dev_alloc(&m->jac_part, n_jac));
     SEGP_CHECK(dev_alloc(&m->qpart, n_q));
+    if (i8) {
+        SEGP_CHECK(dev_alloc(&m->epart, n_q));
+        SEGP_CHECK(dev_alloc(&m->pflag, (size_t)npanel_cap));
+        SEGP_CUDA_CHECK(cudaMemset(m->epart, 0, n_q * sizeof(float)));
+        SEGP_CUDA_CHECK(cudaMemset(m->pflag, 0, npanel_cap * sizeof(int32_t)));
+    }
     if (m->has_composite) {
         SEGP_CHECK(dev_alloc(&m->jac2_part, n_jac));
         SEGP_CHECK(dev_alloc(&m->kss, (size_t)m->n_s * want));
     }
     if (n_ks > 0) SEGP_CUDA_CHECK(cudaMemset(m->ks, 0, n_ks * sizeof(double)));
     if (n_ki8 > 0) SEGP_CUDA_CHECK(cudaMemset(m->ki8, 0, n_ki8));
-    m->workspace_bytes = (n_ks + n_mu + n_jac + n_q) * sizeof(double) + n_ki8;
+    m->workspace_bytes = (n_ks + n_mu + n_jac + n_q) * sizeof(double) + n_ki8 + (i8 ? n_q * sizeof(float) : 0);
     m->b_cap = want;
     m->npanel_cap = npanel_cap;
-    m->ws_mode = mode;
+    m->ws_mode = i8 ? 1 : 0;
     m->nsplit = nsplit;
     m->blocks_per_split = bps;
     return SEGP_OK;
@@ -303,7 +402,6 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int pan
         k8.k = k;
         k8.ki8 = m->ki8;
         k8.npanel_cap = m->npanel_cap;
-        k8.split_halves = m->ws_mode == 2 || m->ws_mode == 3;
         k8.panel0 = panel0;
         k8.resident_ctas = coresident ? 3 * 148 : 0;   // three small CTAs per SM next to the persistent contraction
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
@@ -311,8 +409,36 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int pan
     return launch_kstar(k, m->n_s, m->nsplit, st);
 }
 
-// variance contraction launch (tri_i8 on tcgen05 or tri_sumsq on the DMMA pipe), optionally bracketed by a
-// CUDA-event pair on the launching stream
+// argument block of an int8 contraction launch on digit set `digits`
+static TriI8Args tri_i8_args(const segp_model* m, long nb, int panel0, int digits) {
+    TriI8Args t{};
+    const bool split = digits == 4;
+    t.wi8 = split ? m->wi8s : m->wi8;
+    t.rowfac = split ? m->rowfac_s : m->rowfac;
+    t.wm1 = m->wm1;
+    t.werr = split ? m->werr4 : m->werr5;
+    t.digits = digits;
+    t.ki8 = m->ki8;
+    t.qpart = m->qpart;
+    t.epart = m->epart;
+    t.nblk = m->nblk;
+    t.npanels = (int)((nb + I8_N - 1) / I8_N);
+    t.panel0 = panel0;   // != 0 only from the pipelined driver
+    // panels per L2 group of tri_i8m / tri_i8mp (0 = 24): a sweep over 8..24 at C4 and C5 moved the launch time by
+    // less than 0.5 %, so there is no automatic choice
+    t.pgroup = (int)m->opt_i8_panel_group;
+    t.cluster = (int)m->opt_i8_cluster;
+    t.npanel_cap = m->npanel_cap;
+    t.b_cap = m->b_cap;
+    t.fix_bi = -1;
+    t.prof = m->i8_prof;
+    return t;
+}
+
+// Variance contraction of the trajectories [panel0 * 96, nb) of the current chunk: tri_sumsq on the DMMA pipe, or the
+// tcgen05 kernels on the selected digit set followed -- for the 10-product set -- by the precision guard and the
+// recomputation of the flagged panels on the 15-product set.  Optionally bracketed by a CUDA-event pair on the
+// launching stream (bench.py: the pair spans the first pass only, the kernel the roofline is quoted for).
 static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool coresident = false) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->time_tri) {
@@ -327,57 +453,66 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
         SEGP_CUDA_CHECK(cudaEventRecord(e0, st));
     }
     if (m->ws_mode != 0) {
-        TriI8Args t{};
-        t.wi8 = m->wi8;
-        t.rowfac = m->rowfac;
-        t.ki8 = m->ki8;
-        t.qpart = m->qpart;
-        t.nblk = m->nblk;
-        t.npanels = (int)((nb + I8_N - 1) / I8_N);
-        t.panel0 = panel0;   // != 0 only from the pipelined driver (ws_mode 4)
-        // panels per L2 group of tri_i8m / tri_i8mp (0 = 24): a sweep over 8..24 at C4 and C5 moved the launch time by
-        // less than 0.5 % (scripts/gpu_pgroup.sh), so there is no automatic choice
-        t.pgroup = (int)m->opt_i8_panel_group;
-        t.cluster = (int)m->opt_i8_cluster;
-        t.npanel_cap = m->npanel_cap;
-        t.b_cap = m->b_cap;
-        t.dbg = nullptr;
-        t.fix_bi = -1;
-        t.zero_a = m->i8zero;
-        t.ablate = (int)m->opt_i8_ablate;
-        t.prof = m->i8_prof;
+        const int mode = tri_mode(m);
+        const int digits = tri_digits(m);
+        TriI8Args t = tri_i8_args(m, nb, panel0, digits);
         // Automatic mode: the persistent folded kernel where per-tile overhead matters (short tiles, enough of them to
         // balance a static schedule: +5 % at C3), the one-cluster-per-tile kernel otherwise (C4: power-capped, +1 %
         // at best; C5: the persistent order runs 13 % slower; C2: too few tiles) -- profiles/round1/persistent_tri_i8mp.txt
-        bool persistent = m->ws_mode == 5;
-        if (m->ws_mode == 4 && m->opt_tri_mode < 0 && t.panel0 == 0) {
+        bool persistent = mode == 5;
+        if (mode == 4 && m->opt_tri_mode < 0 && m->force_mode == -2 && t.panel0 == 0) {
             const long ntiles = (long)m->n_s * ((m->nblk + 1) / 2) * ((t.npanels + 1) / 2);
             persistent = m->nblk <= 32 && ntiles >= 4 * 74;
         }
         if (coresident) persistent = true;   // the pipelined driver needs a resident contraction grid
         m->last_tri_persistent = persistent;
-        SEGP_CHECK(persistent        ? launch_tri_i8mp(t, m->n_s, st, coresident)
-                   : m->ws_mode == 4 ? launch_tri_i8m(t, m->n_s, st)
-                   : m->ws_mode == 3 ? launch_tri_i8x2p(t, m->n_s, st)
-                   : m->ws_mode == 2 ? launch_tri_i8x2(t, m->n_s, st)
-                                     : launch_tri_i8(t, m->n_s, st));
-    } else {
-        TriArgs t{};
-        t.wt = m->wt;
-        t.ks = m->ks;
-        t.qpart = m->qpart;
-        t.nblk = m->nblk;
-        t.npanels = (int)((nb + TILE - 1) / TILE);
-        t.group = (int)std::max<long>(1, std::min<long>(m->opt_panel_group, t.npanels));
-        t.b_cap = m->b_cap;
-        t.ntri = m->ntri;
-        SEGP_CHECK(launch_tri_sumsq(t, m->n_s, st));
+        m->last_tri_digits = digits;
+        if (mode == 1) {
+            t.epart = nullptr;   // the reference kernel has no error-model output: clear it so no stale estimate is read
+            SEGP_CUDA_CHECK(cudaMemsetAsync(m->epart, 0, (size_t)m->n_s * m->nblk * m->b_cap * sizeof(float), st));
+            SEGP_CHECK(launch_tri_i8(t, m->n_s, st));
+        } else {
+            SEGP_CHECK(persistent ? launch_tri_i8mp(t, m->n_s, st, coresident) : launch_tri_i8m(t, m->n_s, st));
+        }
+        if (e1 != nullptr) SEGP_CUDA_CHECK(cudaEventRecord(e1, st));
+        if (digits == 4 && m->opt_guard != 0 && m->force_digits == 0) {
+            GuardArgs g{};
+            g.qpart = m->qpart;
+            g.epart = m->epart;
+            g.gp_var = m->var;
+            g.nblk = m->nblk;
+            g.n_s = m->n_s;
+            g.panel0 = panel0;
+            g.b_cap = m->b_cap;
+            g.n_batch = nb;
+            g.gs = guard_gs(m);
+            g.pflag = m->pflag;
+            g.counter = m->fallback_counter;
+            SEGP_CHECK(launch_i8_guard(g, st));
+            TriI8Args t5 = tri_i8_args(m, nb, panel0, 5);
+            t5.pflag = m->pflag;
+            t5.cluster = 2;
+            SEGP_CHECK(launch_tri_i8m(t5, m->n_s, st));
+            m->launches += 2;
+        }
+        return SEGP_OK;
     }
+    TriArgs t{};
+    t.wt = m->wt;
+    t.ks = m->ks;
+    t.qpart = m->qpart;
+    t.nblk = m->nblk;
+    t.npanels = (int)((nb + TILE - 1) / TILE);
+    t.group = (int)std::max<long>(1, std::min<long>(m->opt_panel_group, t.npanels));
+    t.b_cap = m->b_cap;
+    t.ntri = m->ntri;
+    SEGP_CHECK(launch_tri_sumsq(t, m->n_s, st));
     if (e1 != nullptr) SEGP_CUDA_CHECK(cudaEventRecord(e1, st));
     return SEGP_OK;
 }
 
 }  // namespace segp
+
 
 // ============================================================================================== C ABI
 extern "C" {
@@ -435,7 +570,10 @@ int segp_create(segp_model** out, int device, int n_s_out, int n_s_in, int n_u, 
         m->kern[d] = kern_type[d];
         if (kern_is_composite(kern_type[d])) m->has_composite = true;
     }
-    if (dev_alloc(&m->d_sp, 1) != SEGP_OK) {
+    if (dev_alloc(&m->d_sp, 1) != SEGP_OK || dev_alloc(&m->fallback_counter, 1) != SEGP_OK ||
+        cudaMemset(m->fallback_counter, 0, sizeof(unsigned int)) != cudaSuccess) {
+        dev_free(m->d_sp);
+        dev_free(m->fallback_counter);
         delete m;
         return SEGP_ERR_CUDA;
     }
@@ -451,6 +589,11 @@ int segp_destroy(segp_model* m) {
     free_workspace(m);
     dev_free(m->d_sp);
     dev_free(m->i8_prof);
+    dev_free(m->fallback_counter);
+    if (m->s_host != nullptr) cudaStreamDestroy(m->s_host);
+    if (m->s_cap != nullptr) cudaStreamDestroy(m->s_cap);
+    if (m->s_copy != nullptr) cudaStreamDestroy(m->s_copy);
+    if (m->ev_chunk != nullptr) cudaEventDestroy(m->ev_chunk);
     for (cudaEvent_t e : m->tri_events) cudaEventDestroy(e);
     for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_ks[0], m->ev_ks[1], m->ev_tri[0], m->ev_tri[1]})
         if (e != nullptr) cudaEventDestroy(e);
@@ -568,87 +711,302 @@ static int compute_xtb(segp_model* m, cudaStream_t st) {
     return SEGP_OK;
 }
 
+// layout of the factor arena: [meta | beta | logdet | rowfac | rowfac_s | werr5 | werr4 | wm1 | wi8s | wi8], every part
+// 256-byte aligned; the int8 parts only when the model can run on the tcgen05 path
+static int alloc_arena(segp_model* m) {
+    if (m->arena != nullptr) return SEGP_OK;
+    const bool i8 = i8_capable(m);
+    const size_t n_rows = (size_t)m->n_s * m->n_pad;
+    const size_t n_kb = (size_t)m->n_s * m->nblk * (m->nblk + 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_meta = take(META_N * sizeof(double)), o_beta = take(n_rows * sizeof(double)),
+                 o_logdet = take((size_t)m->n_s * sizeof(double));
+    size_t o_rowfac = 0, o_rowfac_s = 0, o_werr5 = 0, o_werr4 = 0, o_wm1 = 0, o_wi8s = 0, o_wi8 = 0;
+    if (i8) {
+        o_rowfac = take(n_rows * sizeof(double));
+        o_rowfac_s = take(n_rows * sizeof(double));
+        o_werr5 = take(n_rows * sizeof(float));
+        o_werr4 = take(n_rows * sizeof(float));
+        o_wm1 = take((size_t)m->n_s * m->nblk * 2 * I8_A_TILE);
+        o_wi8s = take(n_kb * (I8_SS * I8_A_TILE));
+        o_wi8 = take(n_kb * (I8_S * I8_A_TILE));
+    }
+    SEGP_CHECK(dev_alloc(&m->arena, off));
+    SEGP_CUDA_CHECK(cudaMemset(m->arena, 0, o_beta));   // meta
+    m->arena_bytes = off;
+    m->meta = reinterpret_cast<double*>(m->arena + o_meta);
+    m->beta = reinterpret_cast<double*>(m->arena + o_beta);
+    m->logdet = reinterpret_cast<double*>(m->arena + o_logdet);
+    if (i8) {
+        m->rowfac = reinterpret_cast<double*>(m->arena + o_rowfac);
+        m->rowfac_s = reinterpret_cast<double*>(m->arena + o_rowfac_s);
+        m->werr5 = reinterpret_cast<float*>(m->arena + o_werr5);
+        m->werr4 = reinterpret_cast<float*>(m->arena + o_werr4);
+        m->wm1 = reinterpret_cast<int8_t*>(m->arena + o_wm1);
+        m->wi8s = reinterpret_cast<int8_t*>(m->arena + o_wi8s);
+        m->wi8 = reinterpret_cast<int8_t*>(m->arena + o_wi8);
+    }
+    return SEGP_OK;
+}
+
+// does this model (as configured now) ever launch the float64 contraction?
+static bool fp64_operand_needed(const segp_model* m) {
+    return !i8_capable(m) || m->auto_fp64 || m->opt_tri_mode == 0 || m->opt_keep_fp64 != 0;
+}
+
+static int write_meta(segp_model* m) {
+    double h[META_N] = {0};
+    h[0] = (double)m->i8_primary;
+    h[1] = m->auto_fp64 ? 1.0 : 0.0;
+    h[2] = m->wt != nullptr ? 1.0 : 0.0;
+    for (int i = 0; i < PROBE_STATS; ++i) h[4 + i] = m->probe_stat[i];
+    SEGP_CUDA_CHECK(cudaMemcpy(m->meta, h, sizeof(h), cudaMemcpyHostToDevice));
+    return SEGP_OK;
+}
+
+static int read_meta(segp_model* m, bool* root_has_fp64) {
+    double h[META_N];
+    SEGP_CUDA_CHECK(cudaMemcpy(h, m->meta, sizeof(h), cudaMemcpyDeviceToHost));
+    m->i8_primary = h[0] == 4.0 ? 4 : 5;
+    m->auto_fp64 = h[1] != 0.0;
+    if (root_has_fp64 != nullptr) *root_has_fp64 = h[2] != 0.0;
+    for (int i = 0; i < PROBE_STATS; ++i) m->probe_stat[i] = h[4 + i];
+    return SEGP_OK;
+}
+
 int segp_alloc_factor_buffers(segp_model* m) {
     if (m == nullptr || !m->has_data) {
         set_error("segp_alloc_factor_buffers: segp_set_model has not been called");
         return SEGP_ERR_NOT_TRAINED;
     }
     DeviceGuard guard(m->device);
-    if (m->wt == nullptr) SEGP_CHECK(dev_alloc(&m->wt, (size_t)m->n_s * m->ntri * TILE * TILE));
-    if (m->beta == nullptr) SEGP_CHECK(dev_alloc(&m->beta, (size_t)m->n_s * m->n_pad));
-    if (m->logdet == nullptr) SEGP_CHECK(dev_alloc(&m->logdet, (size_t)m->n_s));
-    if (i8_capable(m)) {
-        if (m->wi8 == nullptr)
-            SEGP_CHECK(dev_alloc(&m->wi8, (size_t)m->n_s * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE)));
-        if (m->rowfac == nullptr) SEGP_CHECK(dev_alloc(&m->rowfac, (size_t)m->n_s * m->n_pad));
-        if (m->i8zero == nullptr) {
-            SEGP_CHECK(dev_alloc(&m->i8zero, (size_t)I8_S * I8_A_TILE));
-            SEGP_CUDA_CHECK(cudaMemset(m->i8zero, 0, (size_t)I8_S * I8_A_TILE));
-        }
+    return alloc_arena(m);
+}
+
+int segp_alloc_fp64_operand(segp_model* m) {
+    if (m == nullptr || !m->has_data) {
+        set_error("segp_alloc_fp64_operand: segp_set_model has not been called");
+        return SEGP_ERR_NOT_TRAINED;
     }
+    DeviceGuard guard(m->device);
+    if (m->wt == nullptr) SEGP_CHECK(dev_alloc(&m->wt, (size_t)m->n_s * m->ntri * TILE * TILE));
     return SEGP_OK;
 }
 
 int segp_num_factor_buffers(segp_model* m) {
-    if (m == nullptr) return 0;
-    return i8_capable(m) ? 5 : 3;
+    if (m == nullptr || m->arena == nullptr) return 0;
+    return m->wt != nullptr ? 2 : 1;
 }
 
 int segp_factor_buffer(segp_model* m, int index, void** d_ptr, size_t* bytes) {
-    if (m == nullptr || d_ptr == nullptr || bytes == nullptr || m->wt == nullptr) {
+    if (m == nullptr || d_ptr == nullptr || bytes == nullptr || m->arena == nullptr) {
         set_error("segp_factor_buffer: buffers are not allocated");
         return SEGP_ERR_NOT_TRAINED;
     }
-    switch (index) {
-        case 0:
-            *d_ptr = m->wt;
-            *bytes = (size_t)m->n_s * m->ntri * TILE * TILE * sizeof(double);
-            return SEGP_OK;
-        case 1:
-            *d_ptr = m->beta;
-            *bytes = (size_t)m->n_s * m->n_pad * sizeof(double);
-            return SEGP_OK;
-        case 2:
-            *d_ptr = m->logdet;
-            *bytes = (size_t)m->n_s * sizeof(double);
-            return SEGP_OK;
-        case 3:
-            if (m->wi8 != nullptr) {
-                *d_ptr = m->wi8;
-                *bytes = (size_t)m->n_s * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE);
-                return SEGP_OK;
-            }
-            [[fallthrough]];
-        case 4:
-            if (index == 4 && m->rowfac != nullptr) {
-                *d_ptr = m->rowfac;
-                *bytes = (size_t)m->n_s * m->n_pad * sizeof(double);
-                return SEGP_OK;
-            }
-            [[fallthrough]];
-        default:
-            set_error("segp_factor_buffer: index %d out of range", index);
-            return SEGP_ERR_INVALID;
+    if (index == 0) {
+        *d_ptr = m->arena;
+        *bytes = m->arena_bytes;
+        return SEGP_OK;
     }
+    if (index == 1 && m->wt != nullptr) {
+        *d_ptr = m->wt;
+        *bytes = (size_t)m->n_s * m->ntri * TILE * TILE * sizeof(double);
+        return SEGP_OK;
+    }
+    set_error("segp_factor_buffer: index %d out of range", index);
+    return SEGP_ERR_INVALID;
 }
 
 int segp_mark_factorized(segp_model* m) {
-    if (m == nullptr || m->wt == nullptr) {
+    if (m == nullptr || m->arena == nullptr) {
         set_error("segp_mark_factorized: buffers are not allocated");
         return SEGP_ERR_NOT_TRAINED;
+    }
+    DeviceGuard guard(m->device);
+    bool root_has_fp64 = false;
+    SEGP_CHECK(read_meta(m, &root_has_fp64));
+    if (fp64_operand_needed(m) && m->wt == nullptr) {
+        set_error("segp_mark_factorized: this model runs the float64 contraction; allocate (segp_alloc_fp64_operand) "
+                  "and receive factor buffer 1 as well%s", root_has_fp64 ? "" : " (the factorising rank did not keep it: "
+                  "set tri_mode / keep_fp64 there before segp_factorize)");
+        return SEGP_ERR_INVALID;
     }
     if (m->has_composite) {
         if (!m->has_linear_terms) {
             set_error("segp_mark_factorized: composite kernel without linear terms (call segp_set_linear_terms)");
             return SEGP_ERR_INVALID;
         }
-        DeviceGuard guard(m->device);
         SEGP_CHECK(compute_xtb(m, nullptr));
         SEGP_CUDA_CHECK(cudaStreamSynchronize(nullptr));
     }
     m->factorized = true;
     return SEGP_OK;
 }
+
+// destination pointers of output dimension d inside the factor arena
+static PackI8Out pack_out(const segp_model* m, int d) {
+    PackI8Out o{};
+    const size_t kbs = (size_t)m->nblk * (m->nblk + 1);
+    o.wi8 = m->wi8 + (size_t)d * kbs * (I8_S * I8_A_TILE);
+    o.rowfac = m->rowfac + (size_t)d * m->n_pad;
+    o.wi8s = m->wi8s + (size_t)d * kbs * (I8_SS * I8_A_TILE);
+    o.wm1 = m->wm1 + (size_t)d * m->nblk * 2 * I8_A_TILE;
+    o.rowfac_s = m->rowfac_s + (size_t)d * m->n_pad;
+    o.werr5 = m->werr5 + (size_t)d * m->n_pad;
+    o.werr4 = m->werr4 + (size_t)d * m->n_pad;
+    return o;
+}
+
+// scale the error-model weights by the probe's calibration factors (standard deviation x rho -> variance x rho^2)
+static int apply_calibration(segp_model* m, cudaStream_t st) {
+    const double r4 = std::max(1.0, m->probe_stat[PS_RHO4]), r5 = std::max(1.0, m->probe_stat[PS_RHO5]);
+    const long n = (long)m->n_s * m->n_pad;
+    if (r4 > 1.0) SEGP_CHECK(launch_scale_f32(m->werr4, n, (float)(r4 * r4), st));
+    if (r5 > 1.0) SEGP_CHECK(launch_scale_f32(m->werr5, n, (float)(r5 * r5), st));
+    return SEGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- factorize-time probe
+// Calibrates the statistical error model of the int8 contraction and chooses the digit set: PROBE_N inputs drawn
+// uniformly from the bounding box of the training inputs run through the float64 contraction (reference), the
+// 15-product and the 10-product kernels.  Per output dimension the measured error of |v|^2 is compared with the
+// model's a-posteriori estimate 2 sqrt(sum_i w_i v_i^2): if any probe exceeds 4.5 predicted standard deviations the
+// weights of that digit set are inflated (rho); the digit set of the first pass is the 10-product one only when the
+// guard flags none of the probes on it (and the model is large enough for the extra launches to pay); when the guard
+// would flag more than a quarter of the probes even on the 15-product set, automatic mode runs float64.
+static int probe_pass(segp_model* m, const double* d_z, long np, int mode, int digits, cudaStream_t st,
+                      std::vector<double>& q, std::vector<double>& e) {
+    m->force_mode = mode;
+    m->force_digits = digits;
+    int rc = ensure_workspace(m, np);
+    if (rc == SEGP_OK) {
+        KstarArgs k = base_kstar_args(m);
+        k.z = d_z;
+        k.n_batch = np;
+        rc = run_kstar(m, k, st);
+    }
+    if (rc == SEGP_OK) rc = run_tri(m, np, st);
+    m->force_mode = -2;
+    m->force_digits = 0;
+    SEGP_CHECK(rc);
+    const size_t n = (size_t)m->n_s * m->nblk * m->b_cap;
+    std::vector<double> hq(n);
+    std::vector<float> he(mode != 0 ? n : 0);
+    SEGP_CUDA_CHECK(cudaStreamSynchronize(st));
+    SEGP_CUDA_CHECK(cudaMemcpy(hq.data(), m->qpart, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (mode != 0) SEGP_CUDA_CHECK(cudaMemcpy(he.data(), m->epart, n * sizeof(float), cudaMemcpyDeviceToHost));
+    q.assign((size_t)m->n_s * np, 0.0);
+    e.assign((size_t)m->n_s * np, 0.0);
+    for (int d = 0; d < m->n_s; ++d)
+        for (int i = 0; i < m->nblk; ++i) {
+            const size_t row = ((size_t)d * m->nblk + i) * m->b_cap;
+            for (long p = 0; p < np; ++p) {
+                q[(size_t)d * np + p] += hq[row + p];
+                if (mode != 0) e[(size_t)d * np + p] += (double)he[row + p];
+            }
+        }
+    return SEGP_OK;
+}
+
+static int run_probe(segp_model* m, cudaStream_t st) {
+    const long np = PROBE_N;
+    const int dim = m->dim;
+    std::vector<double> lo(dim, 1e300), hi(dim, -1e300), z((size_t)np * dim);
+    for (int i = 0; i < m->n_train; ++i)
+        for (int j = 0; j < dim; ++j) {
+            lo[j] = std::min(lo[j], m->h_x[(size_t)i * dim + j]);
+            hi[j] = std::max(hi[j], m->h_x[(size_t)i * dim + j]);
+        }
+    uint64_t state = 0x9E3779B97F4A7C15ull;
+    auto next_unit = [&state]() {   // splitmix64 -> [0, 1)
+        uint64_t x = (state += 0x9E3779B97F4A7C15ull);
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        x ^= x >> 31;
+        return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+    };
+    for (long p = 0; p < np; ++p)
+        for (int j = 0; j < dim; ++j) z[(size_t)p * dim + j] = lo[j] + (hi[j] - lo[j]) * next_unit();
+    double* d_z = nullptr;
+    SEGP_CHECK(dev_alloc(&d_z, z.size()));
+    const bool timed = m->time_tri;
+    m->time_tri = false;
+    std::vector<double> q0, e0, q5, e5, q4, e4;
+    int rc = SEGP_OK;
+    do {
+        if (cudaMemcpy(d_z, z.data(), z.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("probe: upload failed");
+            rc = SEGP_ERR_CUDA;
+            break;
+        }
+        if ((rc = probe_pass(m, d_z, np, 0, 0, st, q0, e0)) != SEGP_OK) break;
+        if ((rc = probe_pass(m, d_z, np, -1, 5, st, q5, e5)) != SEGP_OK) break;
+        if ((rc = probe_pass(m, d_z, np, -1, 4, st, q4, e4)) != SEGP_OK) break;
+    } while (0);
+    m->time_tri = timed;
+    dev_free(d_z);
+    cudaDeviceSynchronize();
+    free_workspace(m);
+    SEGP_CHECK(rc);
+
+    constexpr double KAPPA_PROBE = 4.5;
+    double* ps = m->probe_stat;
+    for (int i = 0; i < PROBE_STATS; ++i) ps[i] = 0.0;
+    ps[PS_RAN] = 1.0;
+    ps[PS_RHO4] = ps[PS_RHO5] = 1.0;
+    ps[PS_MINVAR] = 1e300;
+    for (int d = 0; d < m->n_s; ++d)
+        for (long p = 0; p < np; ++p) {
+            const size_t i = (size_t)d * np + p;
+            const double s2 = m->h_var[d] - q0[i];
+            const double err4 = std::fabs(q4[i] - q0[i]), err5 = std::fabs(q5[i] - q0[i]);
+            const double sd4 = 2.0 * std::sqrt(e4[i]), sd5 = 2.0 * std::sqrt(e5[i]);
+            ps[PS_ERR4] = std::max(ps[PS_ERR4], err4);
+            ps[PS_ERR5] = std::max(ps[PS_ERR5], err5);
+            if (s2 > 0.0) {
+                ps[PS_REL4] = std::max(ps[PS_REL4], err4 / s2);
+                ps[PS_REL5] = std::max(ps[PS_REL5], err5 / s2);
+            }
+            // the float64 reference itself carries ~1e-13 of rounding relative to k**: do not calibrate against that
+            const double floor = 1e-12 * m->h_var[d];
+            if (sd4 > 0.0 && err4 > floor) ps[PS_RATIO4] = std::max(ps[PS_RATIO4], err4 / sd4);
+            if (sd5 > 0.0 && err5 > floor) ps[PS_RATIO5] = std::max(ps[PS_RATIO5], err5 / sd5);
+            ps[PS_MINVAR] = std::min(ps[PS_MINVAR], s2 / m->h_var[d]);
+        }
+    ps[PS_RHO4] = std::max(1.0, ps[PS_RATIO4] / KAPPA_PROBE);
+    ps[PS_RHO5] = std::max(1.0, ps[PS_RATIO5] / KAPPA_PROBE);
+    // guard decisions on the probes with the calibrated model
+    const double gs = guard_gs(m);
+    long n4 = 0, n5 = 0;
+    for (long p = 0; p < np; ++p) {
+        bool f4 = false, f5 = false;
+        for (int d = 0; d < m->n_s; ++d) {
+            const size_t i = (size_t)d * np + p;
+            const double s2 = m->h_var[d] - q0[i];
+            if (!(s2 > 0.0)) {
+                f4 = f5 = true;
+                continue;
+            }
+            if (gs * ps[PS_RHO4] * ps[PS_RHO4] * e4[i] > s2 * s2) f4 = true;
+            if (gs * ps[PS_RHO5] * ps[PS_RHO5] * e5[i] > s2 * s2) f5 = true;
+        }
+        n4 += f4;
+        n5 += f5;
+    }
+    ps[PS_FRAC4] = (double)n4 / (double)np;
+    ps[PS_FRAC5] = (double)n5 / (double)np;
+    m->i8_primary = (n4 == 0 && m->n_pad >= 1024) ? 4 : 5;
+    m->auto_fp64 = ps[PS_FRAC5] > 0.25;
+    SEGP_CHECK(apply_calibration(m, st));
+    SEGP_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SEGP_OK;
+}
+
 
 int segp_factorize(segp_model* m, void* stream) {
     if (m == nullptr || !m->has_data) {
@@ -662,7 +1020,13 @@ int segp_factorize(segp_model* m, void* stream) {
     DeviceGuard guard(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     m->factorized = false;
-    SEGP_CHECK(segp_alloc_factor_buffers(m));
+    free_graphs(m);
+    SEGP_CHECK(alloc_arena(m));
+    // the float64 operand: the probe's reference, and the contraction itself where the int8 path cannot run
+    SEGP_CHECK(segp_alloc_fp64_operand(m));
+    m->i8_primary = 5;
+    m->auto_fp64 = false;
+    for (double& v : m->probe_stat) v = 0.0;
     const size_t nn = (size_t)m->n_pad * m->n_pad;
     const int nb64 = m->n_pad / NBLK;
     // The output dimensions are independent factorisations and each is a chain of ~270 launches, many of them one
@@ -733,9 +1097,7 @@ int segp_factorize(segp_model* m, void* stream) {
             if ((rc = pack_w(wbuf, m->wt + (size_t)d * m->ntri * TILE * TILE, m->n_pad, ss)) != SEGP_OK) break;
             ++m->launches;
             if (m->wi8 != nullptr) {
-                if ((rc = pack_w_i8(wbuf, m->wi8 + (size_t)d * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE),
-                                    m->rowfac + (size_t)d * m->n_pad, m->h_var[d], m->n_pad, ss)) != SEGP_OK)
-                    break;
+                if ((rc = pack_w_i8(wbuf, pack_out(m, d), m->h_var[d], m->n_pad, m->n_train, ss)) != SEGP_OK) break;
                 m->launches += 2;
             }
         }
@@ -779,8 +1141,18 @@ int segp_factorize(segp_model* m, void* stream) {
     }
     if (fork != nullptr) cudaEventDestroy(fork);
     dev_free(d_fail);
-    if (rc == SEGP_OK) m->factorized = true;
-    return rc;
+    if (rc != SEGP_OK) return rc;
+    m->factorized = true;
+    // calibrate the int8 error model and choose the digit set (needs the float64 operand as the reference)
+    if (i8_capable(m) && m->opt_probe != 0) {
+        rc = run_probe(m, st);
+        if (rc != SEGP_OK) {
+            m->factorized = false;
+            return rc;
+        }
+    }
+    if (!fp64_operand_needed(m)) dev_free(m->wt);
+    return write_meta(m);
 }
 
 int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, void* stream) {
@@ -862,12 +1234,11 @@ int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, 
             if ((rc = logdet_from_winv(w, m->n_train, n_pad, m->logdet + d, st)) != SEGP_OK) break;
             if ((rc = solve_beta(w, m->yp + (size_t)d * n_pad, u_tmp, m->beta + (size_t)d * n_pad, n_pad, st)) != SEGP_OK)
                 break;
-            if ((rc = pack_w(w, m->wt + (size_t)d * m->ntri * TILE * TILE, n_pad, st)) != SEGP_OK) break;
+            if (m->wt != nullptr && (rc = pack_w(w, m->wt + (size_t)d * m->ntri * TILE * TILE, n_pad, st)) != SEGP_OK)
+                break;
             m->launches += 5;
             if (m->wi8 != nullptr) {
-                if ((rc = pack_w_i8(w, m->wi8 + (size_t)d * m->nblk * (m->nblk + 1) * (I8_S * I8_A_TILE),
-                                    m->rowfac + (size_t)d * n_pad, m->h_var[d], n_pad, st)) != SEGP_OK)
-                    break;
+                if ((rc = pack_w_i8(w, pack_out(m, d), m->h_var[d], n_pad, m->n_train, st)) != SEGP_OK) break;
                 m->launches += 2;
             }
         }
@@ -898,11 +1269,40 @@ int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, 
     dev_free(diag_inv);
     dev_free(u_tmp);
     dev_free(d_fail);
+    if (rc == SEGP_OK && m->wi8 != nullptr) rc = apply_calibration(m, st);   // the probe's factors carry over
     if (rc == SEGP_OK) {
         m->factorized = true;
         m->last_append_incremental = true;
+        free_graphs(m);
+        return write_meta(m);
+    }
+    // The update failed half way (rows of W overwritten, data already appended): restore the model the caller had
+    // -- the old data, factorised from scratch -- so that the handle stays usable and a retry does not append twice.
+    {
+        char msg[sizeof(g_err)];
+        snprintf(msg, sizeof(msg), "%s", g_err);
+        const std::vector<double> ls(m->h_ls), var(m->h_var), noise(m->h_noise), plin(m->h_plin), lin(m->h_lin);
+        const bool had_lin = m->has_linear_terms;
+        // after the swaps above hx / hy hold the previous training set
+        if (segp_set_model(m, n_old, hx.data(), hy.data(), ls.data(), var.data(), noise.data()) == SEGP_OK &&
+            (!had_lin || segp_set_linear_terms(m, plin.data(), lin.data()) == SEGP_OK))
+            segp_factorize(m, stream);
+        set_error("%s (the previous model was restored)", msg);
     }
     return rc;
+}
+
+int segp_beta(segp_model* m, double* h_out) {
+    SEGP_CHECK(check_ready(m));
+    if (h_out == nullptr) {
+        set_error("segp_beta: null output");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(m->device);
+    for (int d = 0; d < m->n_s; ++d)
+        SEGP_CUDA_CHECK(cudaMemcpy(h_out + (size_t)d * m->n_train, m->beta + (size_t)d * m->n_pad,
+                                   (size_t)m->n_train * sizeof(double), cudaMemcpyDeviceToHost));
+    return SEGP_OK;
 }
 
 int segp_logdet(segp_model* m, double* h_out) {
@@ -912,8 +1312,19 @@ int segp_logdet(segp_model* m, double* h_out) {
     return SEGP_OK;
 }
 
-int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
-                 void* stream) {
+// make the float64 operand resident again (it is dropped after factorising when automatic mode does not need it):
+// the packed tiles come from the dense W, which is gone, so the model is factorised once more
+static int ensure_fp64_operand(segp_model* m, void* stream) {
+    if (m->wt != nullptr || tri_mode(m) != 0) return SEGP_OK;
+    const long keep = m->opt_keep_fp64;
+    m->opt_keep_fp64 = 1;
+    const int rc = segp_factorize(m, stream);
+    m->opt_keep_fp64 = keep;
+    return rc;
+}
+
+int segp_predict_ex(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
+                    int32_t* d_status, void* stream) {
     SEGP_CHECK(check_ready(m));
     if (n_batch < 0 || (n_batch > 0 && (d_z == nullptr || d_mu == nullptr || d_var == nullptr))) {
         set_error("segp_predict: null buffer");
@@ -922,6 +1333,7 @@ int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, d
     if (n_batch == 0) return SEGP_OK;
     DeviceGuard guard(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SEGP_CHECK(ensure_fp64_operand(m, stream));
     SEGP_CHECK(ensure_workspace(m, n_batch));
     for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
         const long nb = std::min<long>(m->b_cap, n_batch - c0);
@@ -938,6 +1350,9 @@ int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, d
         f.invls = m->invls;
         f.jac2_part = m->jac2_part;
         f.kss = m->kss;
+        f.epart = (m->ws_mode != 0 && m->opt_guard != 0) ? m->epart : nullptr;
+        f.guard_gs = guard_gs(m);
+        f.status = d_status ? d_status + c0 : nullptr;
         f.nsplit = m->nsplit;
         f.nblk = m->nblk;
         f.n_s = m->n_s;
@@ -951,6 +1366,11 @@ int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, d
         m->launches += 3;
     }
     return SEGP_OK;
+}
+
+int segp_predict(segp_model* m, long n_batch, const double* d_z, double* d_mu, double* d_var, double* d_jac,
+                 void* stream) {
+    return segp_predict_ex(m, n_batch, d_z, d_mu, d_var, d_jac, nullptr, stream);
 }
 
 int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0, long p0_stride, const double* d_q0,
@@ -979,9 +1399,10 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
     SEGP_CHECK(fill_step_params(&sp, params, m->n_s, m->n_in, m->n_u));
     DeviceGuard guard(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SEGP_CHECK(ensure_fp64_operand(m, stream));
     SEGP_CHECK(ensure_workspace(m, n_batch));
+    // pageable source: staged by the runtime before the call returns, and outside any captured graph
     SEGP_CUDA_CHECK(cudaMemcpyAsync(m->d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, st));
-    if (d_status != nullptr) SEGP_CUDA_CHECK(cudaMemsetAsync(d_status, 0, n_batch * sizeof(int32_t), st));
 
     const int n_s = m->n_s, n_u = m->n_u;
     const long hs = (long)horizon * n_s, hss = (long)horizon * n_s * n_s;
@@ -1007,6 +1428,8 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         s.invls = m->invls;
         s.jac2_part = m->jac2_part;
         s.kss = m->kss;
+        s.epart = (m->ws_mode != 0 && m->opt_guard != 0) ? m->epart : nullptr;
+        s.guard_gs = guard_gs(m);
         s.nsplit = m->nsplit;
         s.nblk = m->nblk;
         s.b_cap = m->b_cap;
@@ -1041,6 +1464,121 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         return s;
     };
 
+    const int npanels_first = (int)((std::min<long>(m->b_cap, n_batch) + I8_N - 1) / I8_N);
+    const bool pipelined_any = m->ws_mode != 0 && tri_mode(m) >= 4 && m->opt_overlap != 0 && npanels_first >= 48 &&
+                               m->n_pad >= 1024;
+    // The serial schedule: per chunk and step kstar -> contraction (+ guard + recomputation) -> ellipsoid step, every
+    // launch asynchronous on one stream.
+    auto issue_serial = [&](cudaStream_t s1) -> int {
+        if (d_status != nullptr) SEGP_CUDA_CHECK(cudaMemsetAsync(d_status, 0, n_batch * sizeof(int32_t), s1));
+        for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
+            const long nb = std::min<long>(m->b_cap, n_batch - c0);
+            for (int t = 0; t < horizon; ++t) {
+                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, nb), s1));
+                SEGP_CHECK(run_tri(m, nb, s1));
+                SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t, 0, nb), s1));
+                m->launches += 3;
+            }
+        }
+        return SEGP_OK;
+    };
+    if (!pipelined_any) {
+        // K5: the 3 H launches of a call are replayed as ONE CUDA graph from the second call with the same
+        // arguments on (a sampling-MPC loop re-uses its buffers); sizes where a launch costs as much as a kernel
+        // (C2: 30 launches of ~10 us of work) are otherwise launch-bound.  First sight of an argument set: direct
+        // launches; second: stream capture on an internal stream + instantiate; then cudaGraphLaunch on the caller's.
+        if (m->opt_graph == 0) return issue_serial(st);
+        struct Key {
+            long n_batch, p0_stride, q0_stride, kfb_stride, kfb_init_stride, b_cap, events_at;
+            const void *p0, *q0, *kff, *kfb, *kfbi, *p_all, *q_all, *var_all, *status;
+            int horizon, mode, digits, guard, nsplit, timed, pgroup, cluster;
+        } key;
+        memset(&key, 0, sizeof(key));
+        key.n_batch = n_batch;
+        key.p0_stride = p0_stride;
+        key.q0_stride = q0_stride;
+        key.kfb_stride = kfb_stride;
+        key.kfb_init_stride = kfb_init_stride;
+        key.b_cap = m->b_cap;
+        key.events_at = m->time_tri ? (long)m->tri_events_used : -1;
+        key.p0 = d_p0;
+        key.q0 = d_q0;
+        key.kff = d_k_ff;
+        key.kfb = d_k_fb;
+        key.kfbi = d_k_fb_init;
+        key.p_all = d_p_all;
+        key.q_all = d_q_all;
+        key.var_all = d_var_all;
+        key.status = d_status;
+        key.horizon = horizon;
+        key.mode = tri_mode(m);
+        key.digits = tri_digits(m);
+        key.guard = (int)m->opt_guard;
+        key.nsplit = m->nsplit;
+        key.timed = m->time_tri ? 1 : 0;
+        key.pgroup = (int)m->opt_i8_panel_group;
+        key.cluster = (int)m->opt_i8_cluster;
+        const unsigned char* kb = reinterpret_cast<const unsigned char*>(&key);
+        GraphEntry* g = nullptr;
+        int n_entries = 0;
+        for (GraphEntry* e = m->graphs; e != nullptr; e = e->next, ++n_entries)
+            if (e->key.size() == sizeof(key) && memcmp(e->key.data(), kb, sizeof(key)) == 0) g = e;
+        if (g != nullptr && g->exec != nullptr) {
+            SEGP_CUDA_CHECK(cudaGraphLaunch(g->exec, st));
+            m->launches += g->launches;
+            if (m->time_tri) m->tri_events_used = (size_t)key.events_at + (size_t)g->events;
+            return SEGP_OK;
+        }
+        if (g == nullptr) {   // first sight: remember the arguments, launch directly
+            if (n_entries >= 16) free_graphs(m);
+            g = new (std::nothrow) GraphEntry();
+            if (g != nullptr) {
+                g->key.assign(kb, kb + sizeof(key));
+                g->next = m->graphs;
+                m->graphs = g;
+            }
+            return issue_serial(st);
+        }
+        // second sight: capture
+        if (m->s_cap == nullptr) SEGP_CUDA_CHECK(cudaStreamCreateWithFlags(&m->s_cap, cudaStreamNonBlocking));
+        const long launches0 = m->launches;
+        const size_t events0 = m->tri_events_used;
+        if (m->time_tri)   // events are created outside the capture
+            while (m->tri_events.size() < events0 + 2 * (size_t)horizon * ((n_batch + m->b_cap - 1) / m->b_cap)) {
+                cudaEvent_t e;
+                SEGP_CUDA_CHECK(cudaEventCreate(&e));
+                m->tri_events.push_back(e);
+            }
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(m->s_cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            return issue_serial(st);
+        }
+        const int rc_issue = issue_serial(m->s_cap);
+        const cudaError_t ec = cudaStreamEndCapture(m->s_cap, &graph);
+        const long captured = m->launches - launches0;
+        const size_t captured_events = m->tri_events_used - events0;
+        m->launches = launches0;
+        m->tri_events_used = events0;
+        cudaGraphExec_t exec = nullptr;
+        if (rc_issue != SEGP_OK || ec != cudaSuccess || graph == nullptr ||
+            cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph != nullptr) cudaGraphDestroy(graph);
+            m->opt_graph = 0;   // this configuration cannot be captured: stay on direct launches
+            return issue_serial(st);
+        }
+        cudaGraphDestroy(graph);
+        g->exec = exec;
+        g->launches = captured;
+        g->events = (long)captured_events;
+        SEGP_CUDA_CHECK(cudaGraphLaunch(g->exec, st));
+        m->launches += g->launches;
+        m->tri_events_used = events0 + captured_events;
+        return SEGP_OK;
+    }
+
+    if (d_status != nullptr) SEGP_CUDA_CHECK(cudaMemsetAsync(d_status, 0, n_batch * sizeof(int32_t), st));
     bool forked = false;
     for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
         const long nb = std::min<long>(m->b_cap, n_batch - c0);
@@ -1050,7 +1588,7 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         // low-priority stream (FP64 pipe).  Within a half the order kstar -> tri -> ellipsoid -> kstar(t+1) is kept by
         // events; the halves touch disjoint panel ranges of the workspace.  Same kernels, same arithmetic, same
         // fixed-order reductions: results are bit-identical to the serial schedule.
-        const bool pipelined = (m->ws_mode == 4 || m->ws_mode == 5) && m->opt_overlap != 0 && npanels >= 48 && m->n_pad >= 1024;
+        const bool pipelined = npanels >= 48;
         if (!pipelined) {
             cudaStream_t s1 = forked ? m->s_lo : st;
             for (int t = 0; t < horizon; ++t) {
@@ -1194,7 +1732,14 @@ int segp_multistep_host(segp_model* m, long n_batch, int horizon, const double* 
                  o_pall = take(n_pall), o_qall = take(n_qall), o_var = take(n_pall), o_stat = take(n_stat);
     SEGP_CHECK(ensure_stage(m, off * sizeof(double)));
     double* base = static_cast<double*>(m->stage);
-    cudaStream_t st = nullptr;
+    // Own streams (not the legacy default stream): compute on s_host, result copies on s_copy, so the device-to-host
+    // copy of chunk i runs under the rollout of chunk i + 1 when the batch exceeds one workspace chunk.
+    if (m->s_host == nullptr) {
+        SEGP_CUDA_CHECK(cudaStreamCreateWithFlags(&m->s_host, cudaStreamNonBlocking));
+        SEGP_CUDA_CHECK(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
+        SEGP_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_chunk, cudaEventDisableTiming));
+    }
+    cudaStream_t st = m->s_host;
     auto up = [&](size_t o, const double* src, size_t n) -> cudaError_t {
         if (n == 0 || src == nullptr) return cudaSuccess;
         return cudaMemcpyAsync(base + o, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
@@ -1205,16 +1750,30 @@ int segp_multistep_host(segp_model* m, long n_batch, int horizon, const double* 
     SEGP_CUDA_CHECK(up(o_kfb, h_k_fb, n_kfb));
     SEGP_CUDA_CHECK(up(o_kfbi, h_k_fb_init, n_kfbi));
     int32_t* d_stat = reinterpret_cast<int32_t*>(base + o_stat);
-    SEGP_CHECK(segp_multistep(m, n_batch, horizon, base + o_p0, p0_stride, h_q0 ? base + o_q0 : nullptr, q0_stride,
-                              base + o_kff, h_k_fb ? base + o_kfb : nullptr, kfb_stride,
-                              h_k_fb_init ? base + o_kfbi : nullptr, kfb_init_stride, params, base + o_pall,
-                              base + o_qall, h_var_all ? base + o_var : nullptr, h_status ? d_stat : nullptr, st));
-    SEGP_CUDA_CHECK(cudaMemcpyAsync(h_p_all, base + o_pall, n_pall * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SEGP_CUDA_CHECK(cudaMemcpyAsync(h_q_all, base + o_qall, n_qall * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h_var_all != nullptr)
-        SEGP_CUDA_CHECK(cudaMemcpyAsync(h_var_all, base + o_var, n_pall * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h_status != nullptr)
-        SEGP_CUDA_CHECK(cudaMemcpyAsync(h_status, d_stat, n_batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    const long chunk = std::max<long>(1, std::min<long>(m->opt_chunk, n_batch));
+    for (long c0 = 0; c0 < n_batch; c0 += chunk) {
+        const long nb = std::min<long>(chunk, n_batch - c0);
+        const size_t hs = (size_t)horizon * n_s;
+        SEGP_CHECK(segp_multistep(m, nb, horizon, base + o_p0 + c0 * p0_stride, p0_stride,
+                                  h_q0 ? base + o_q0 + c0 * q0_stride : nullptr, q0_stride,
+                                  base + o_kff + (size_t)c0 * horizon * n_u, h_k_fb ? base + o_kfb + c0 * kfb_stride : nullptr,
+                                  kfb_stride, h_k_fb_init ? base + o_kfbi + c0 * kfb_init_stride : nullptr, kfb_init_stride,
+                                  params, base + o_pall + c0 * hs, base + o_qall + c0 * hs * n_s,
+                                  h_var_all ? base + o_var + c0 * hs : nullptr, h_status ? d_stat + c0 : nullptr, st));
+        SEGP_CUDA_CHECK(cudaEventRecord(m->ev_chunk, st));
+        SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_copy, m->ev_chunk, 0));
+        cudaStream_t sc = m->s_copy;
+        SEGP_CUDA_CHECK(cudaMemcpyAsync(h_p_all + c0 * hs, base + o_pall + c0 * hs, nb * hs * sizeof(double),
+                                        cudaMemcpyDeviceToHost, sc));
+        SEGP_CUDA_CHECK(cudaMemcpyAsync(h_q_all + c0 * hs * n_s, base + o_qall + c0 * hs * n_s, nb * hs * n_s * sizeof(double),
+                                        cudaMemcpyDeviceToHost, sc));
+        if (h_var_all != nullptr)
+            SEGP_CUDA_CHECK(cudaMemcpyAsync(h_var_all + c0 * hs, base + o_var + c0 * hs, nb * hs * sizeof(double),
+                                            cudaMemcpyDeviceToHost, sc));
+        if (h_status != nullptr)
+            SEGP_CUDA_CHECK(cudaMemcpyAsync(h_status + c0, d_stat + c0, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, sc));
+    }
+    SEGP_CUDA_CHECK(cudaStreamSynchronize(m->s_copy));
     SEGP_CUDA_CHECK(cudaStreamSynchronize(st));
     return SEGP_OK;
 }
@@ -1526,9 +2085,12 @@ int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double*
 
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum) {
-    if ((variant < 1 || variant > 3) || k_blocks < 1 || k_blocks > 64 || (variant >= 2 && (k_blocks & 1)) ||
-        h_a == nullptr || h_b == nullptr || h_acc == nullptr || h_colsum == nullptr) {
-        set_error("segp_i8_selftest: bad argument (variant 1|2, k_blocks in [1,64], even for variant 2)");
+    // variant 1: reference kernel tri_i8; 4: tri_i8m on the classic set; 6: tri_i8m on the diagonal-split set -- all on
+    // the last block row of a (128 k_blocks)-point model, one panel.  h_a holds the planes the kernel multiplies: 5
+    // (variants 1, 4) or 5 with plane 0 = the diagonal's leading digit (variant 6: non-zero on the diagonal only).
+    if ((variant != 1 && variant != 4 && variant != 6) || k_blocks < 1 || k_blocks > 64 || h_a == nullptr ||
+        h_b == nullptr || h_acc == nullptr || h_colsum == nullptr) {
+        set_error("segp_i8_selftest: bad argument (variant 1|4|6, k_blocks in [1,64])");
         return SEGP_ERR_INVALID;
     }
     DeviceGuard guard(device);
@@ -1537,57 +2099,54 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
         return SEGP_ERR_CUDA;
     }
     SEGP_CHECK(tri_i8_init());
-    // one tile of a (128 k_blocks)-point model, panel 0, K = 128 k_blocks:
-    //   variant 1: block row k_blocks - 1 (128 rows);  variant 2: block rows k_blocks - 2 and k_blocks - 1 (256 rows),
-    //   where the upper block row sees zeros in the last 128 columns (its own k-range ends one block earlier)
     const int nblk = k_blocks, kdim = TILE * k_blocks, nkb = 2 * k_blocks;
-    const int rows = variant >= 2 ? 2 * TILE : TILE;
-    const int bi0 = variant >= 2 ? k_blocks - 2 : k_blocks - 1;
-    const size_t a_bytes = (size_t)nblk * (nblk + 1) * (I8_S * I8_A_TILE);
-    const size_t b_bytes = (size_t)nkb * (I8_S * I8_B_TILE);
-    std::vector<int8_t> a_img(a_bytes, 0), b_img(b_bytes, 0);
+    const int bi = k_blocks - 1;
+    const bool split = variant == 6;
+    const int na = split ? I8_SS : I8_S;
+    const size_t a_bytes = (size_t)nblk * (nblk + 1) * (na * I8_A_TILE);
+    const size_t m1_bytes = (size_t)nblk * 2 * I8_A_TILE;
+    const size_t b_bytes = (size_t)2 * nkb * (I8_S * I8_B_TILE);   // two panels (the cluster kernels work on pairs)
+    std::vector<int8_t> a_img(a_bytes, 0), m1_img(m1_bytes, 0), b_img(b_bytes, 0);
     auto sw = [](int r, int k) { return r * I8_KB + ((((k >> 4) ^ ((r >> 1) & 3)) << 4) | (k & 15)); };
     // same image formats as pack_w_i8_kernel / kstar_i8_kernel
-    for (int rb = 0; rb < rows / TILE; ++rb) {
-        const int bi = bi0 + rb;
-        for (int kb = 0; kb < 2 * (bi + 1); ++kb)
-            for (int pl = 0; pl < I8_S; ++pl) {
-                int8_t* at = a_img.data() + ((size_t)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE) + (size_t)pl * I8_A_TILE;
-                for (int k = 0; k < I8_KB; ++k)
-                    for (int r = 0; r < TILE; ++r)
-                        at[sw(r, k)] = h_a[((size_t)pl * rows + rb * TILE + r) * kdim + (size_t)kb * I8_KB + k];
-            }
-    }
+    for (int kb = 0; kb < 2 * (bi + 1); ++kb)
+        for (int pl = 0; pl < I8_S; ++pl) {
+            int8_t* at;
+            if (!split)
+                at = a_img.data() + ((size_t)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE) + (size_t)pl * I8_A_TILE;
+            else if (pl == 0) {
+                if (kb < 2 * bi) continue;
+                at = m1_img.data() + ((size_t)bi * 2 + (kb - 2 * bi)) * I8_A_TILE;
+            } else
+                at = a_img.data() + ((size_t)bi * (bi + 1) + kb) * (I8_SS * I8_A_TILE) + (size_t)(pl - 1) * I8_A_TILE;
+            for (int k = 0; k < I8_KB; ++k)
+                for (int r = 0; r < TILE; ++r) at[sw(r, k)] = h_a[((size_t)pl * TILE + r) * kdim + (size_t)kb * I8_KB + k];
+        }
     for (int kb = 0; kb < nkb; ++kb)
         for (int pl = 0; pl < I8_S; ++pl)
             for (int k = 0; k < I8_KB; ++k)
-                for (int r = 0; r < I8_N; ++r) {
-                    const int8_t v = h_b[((size_t)pl * I8_N + r) * kdim + (size_t)kb * I8_KB + k];
-                    int8_t* kbase = b_img.data() + (size_t)kb * (I8_S * I8_B_TILE);
-                    if (variant >= 2)
-                        kbase[(size_t)(r / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) + (size_t)pl * (I8_B_TILE / 2) +
-                              sw(r % (I8_N / 2), k)] = v;
-                    else
-                        kbase[(size_t)pl * I8_B_TILE + sw(r, k)] = v;
-                }
-    int8_t *d_a = nullptr, *d_b = nullptr, *d_zero = nullptr;
+                for (int r = 0; r < I8_N; ++r)
+                    b_img[(size_t)kb * (I8_S * I8_B_TILE) + (size_t)pl * I8_B_TILE + sw(r, k)] =
+                        h_b[((size_t)pl * I8_N + r) * kdim + (size_t)kb * I8_KB + k];
+    int8_t *d_a = nullptr, *d_m1 = nullptr, *d_b = nullptr;
     double *d_rf = nullptr, *d_q = nullptr;
     int32_t* d_dbg = nullptr;
-    const size_t n_dbg = (size_t)I8_S * rows * I8_N;
+    const size_t n_dbg = (size_t)I8_S * TILE * I8_N;
     int rc = SEGP_OK;
     do {
         if ((rc = dev_alloc(&d_a, a_bytes)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_m1, m1_bytes)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_b, b_bytes)) != SEGP_OK) break;
-        if ((rc = dev_alloc(&d_zero, (size_t)I8_S * I8_A_TILE)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_rf, (size_t)kdim)) != SEGP_OK) break;
-        if ((rc = dev_alloc(&d_q, (size_t)nblk * I8_N)) != SEGP_OK) break;
+        if ((rc = dev_alloc(&d_q, (size_t)nblk * 2 * I8_N)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_dbg, n_dbg)) != SEGP_OK) break;
         std::vector<double> ones((size_t)kdim, 1.0);
         cudaError_t e = cudaMemcpy(d_a, a_img.data(), a_bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_m1, m1_img.data(), m1_bytes, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(d_b, b_img.data(), b_bytes, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemset(d_zero, 0, (size_t)I8_S * I8_A_TILE);
         if (e == cudaSuccess) e = cudaMemcpy(d_rf, ones.data(), kdim * sizeof(double), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemset(d_q, 0, (size_t)nblk * I8_N * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemset(d_q, 0, (size_t)nblk * 2 * I8_N * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemset(d_dbg, 0, n_dbg * sizeof(int32_t));
         if (e != cudaSuccess) {
             set_error("segp_i8_selftest: %s", cudaGetErrorString(e));
             rc = SEGP_ERR_CUDA;
@@ -1595,33 +2154,37 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
         }
         TriI8Args t{};
         t.wi8 = d_a;
+        t.wm1 = d_m1;
         t.rowfac = d_rf;
         t.ki8 = d_b;
         t.qpart = d_q;
         t.nblk = nblk;
         t.npanels = 1;
-        t.npanel_cap = 1;
-        t.b_cap = I8_N;
-        t.dbg = d_dbg;
-        t.zero_a = d_zero;
-        t.fix_bi = variant >= 2 ? bi0 / 2 : bi0;
-        if ((rc = (variant == 3   ? launch_tri_i8x2p(t, 1, nullptr)
-                   : variant == 2 ? launch_tri_i8x2(t, 1, nullptr)
-                                  : launch_tri_i8(t, 1, nullptr))) != SEGP_OK)
-            break;
+        t.npanel_cap = 2;
+        t.b_cap = 2 * I8_N;
+        t.digits = split ? 4 : 5;
+        t.cluster = 2;
+        if (variant == 1) {
+            t.dbg = d_dbg;
+            t.fix_bi = bi;
+            rc = launch_tri_i8(t, 1, nullptr);
+        } else {
+            t.fix_bi = -1;
+            rc = launch_tri_i8m(t, 1, nullptr);   // all block rows of the (zero elsewhere) model; row bi is checked
+        }
+        if (rc != SEGP_OK) break;
         e = cudaDeviceSynchronize();
-        if (e == cudaSuccess) e = cudaMemcpy(h_acc, d_dbg, n_dbg * sizeof(int32_t), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess)   // column sums of the block row(s): [rows / 128][96]
-            e = cudaMemcpy(h_colsum, d_q + (size_t)bi0 * I8_N, (size_t)(rows / TILE) * I8_N * sizeof(double),
-                           cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && variant == 1) e = cudaMemcpy(h_acc, d_dbg, n_dbg * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)   // column sums of the block row: [96]
+            e = cudaMemcpy(h_colsum, d_q + (size_t)bi * 2 * I8_N, (size_t)I8_N * sizeof(double), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {
             set_error("segp_i8_selftest: %s", cudaGetErrorString(e));
             rc = SEGP_ERR_CUDA;
         }
     } while (0);
     dev_free(d_a);
+    dev_free(d_m1);
     dev_free(d_b);
-    dev_free(d_zero);
     dev_free(d_rf);
     dev_free(d_q);
     dev_free(d_dbg);
@@ -1657,7 +2220,7 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_ksplit = value;
         return SEGP_OK;
     }
-    if (strcmp(name, "tri_mode") == 0 && value >= -1 && value <= 5) {
+    if (strcmp(name, "tri_mode") == 0 && (value == -1 || value == 0 || value == 1 || value == 4 || value == 5)) {
         if (value >= 1 && m->has_composite) {
             set_error("tri_mode=%ld (int8 tcgen05) is not available with composite (lin_*) kernels: float64 only", value);
             return SEGP_ERR_UNSUPPORTED;
@@ -1667,7 +2230,32 @@ int segp_set_option(segp_model* m, const char* name, long value) {
                       m->n_pad);
             return SEGP_ERR_UNSUPPORTED;
         }
+        if (value != m->opt_tri_mode) {
+            DeviceGuard guard(m->device);
+            cudaDeviceSynchronize();
+            free_graphs(m);
+        }
         m->opt_tri_mode = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "i8_digits") == 0 && (value == 0 || value == 4 || value == 5)) {
+        m->opt_i8_digits = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "guard") == 0 && (value == 0 || value == 1)) {
+        m->opt_guard = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "probe") == 0 && (value == 0 || value == 1)) {   // takes effect at the next segp_factorize
+        m->opt_probe = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "keep_fp64") == 0 && (value == 0 || value == 1)) {   // takes effect at the next segp_factorize
+        m->opt_keep_fp64 = value;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "graph") == 0 && (value == 0 || value == 1)) {
+        m->opt_graph = value;
         return SEGP_OK;
     }
     if (strcmp(name, "overlap") == 0 && (value == 0 || value == 1)) {
@@ -1681,10 +2269,6 @@ int segp_set_option(segp_model* m, const char* name, long value) {
             cudaDeviceSynchronize();
             dev_free(m->wdense);
         }
-        return SEGP_OK;
-    }
-    if (strcmp(name, "i8_ablate") == 0) {
-        m->opt_i8_ablate = value;
         return SEGP_OK;
     }
     if (strcmp(name, "i8_prof") == 0) {   // 1: allocate the counter buffer; 0: release it
@@ -1721,10 +2305,33 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "overlap") == 0) *value = m->opt_overlap;
     else if (strcmp(name, "i8_prof_ptr") == 0) *value = (long)(uintptr_t)m->i8_prof;
     else if (strcmp(name, "tri_mode_effective") == 0) *value = tri_mode(m);
+    else if (strcmp(name, "i8_digits") == 0) *value = m->opt_i8_digits;
+    else if (strcmp(name, "i8_digits_effective") == 0) *value = tri_mode(m) == 0 ? 0 : tri_digits(m);
+    else if (strcmp(name, "guard") == 0) *value = m->opt_guard;
+    else if (strcmp(name, "probe") == 0) *value = m->opt_probe;
+    else if (strcmp(name, "keep_fp64") == 0) *value = m->opt_keep_fp64;
+    else if (strcmp(name, "graph") == 0) *value = m->opt_graph;
+    else if (strcmp(name, "graphs_cached") == 0) {
+        long n = 0;
+        for (GraphEntry* e = m->graphs; e != nullptr; e = e->next) n += e->exec != nullptr;
+        *value = n;
+    }
+    else if (strcmp(name, "fp64_operand_resident") == 0) *value = m->wt != nullptr ? 1 : 0;
+    else if (strcmp(name, "fp64_operand_needed") == 0) *value = fp64_operand_needed(m) ? 1 : 0;
+    else if (strcmp(name, "factor_bytes") == 0) *value = (long)m->arena_bytes;
+    else if (strcmp(name, "fallback_panels") == 0) {
+        // panels recomputed on the 15-product digit set since the handle was created
+        DeviceGuard guard(m->device);
+        unsigned int v = 0;
+        SEGP_CUDA_CHECK(cudaDeviceSynchronize());
+        SEGP_CUDA_CHECK(cudaMemcpy(&v, m->fallback_counter, sizeof(v), cudaMemcpyDeviceToHost));
+        *value = (long)v;
+    }
     else if (strcmp(name, "tri_persistent") == 0) *value = m->last_tri_persistent ? 1 : 0;
     else if (strcmp(name, "append_incremental") == 0) *value = m->last_append_incremental ? 1 : 0;
     else if (strcmp(name, "keep_w") == 0) *value = m->opt_keep_w;
     else if (strcmp(name, "n_train") == 0) *value = m->n_train;
+    else if (strcmp(name, "factorized") == 0) *value = m->factorized ? 1 : 0;
     else if (strcmp(name, "launches") == 0) *value = m->launches;
     else if (strcmp(name, "n_train_padded") == 0) *value = m->n_pad;
     else if (strcmp(name, "workspace_bytes") == 0) *value = (long)m->workspace_bytes;
@@ -1746,6 +2353,58 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
         return SEGP_ERR_INVALID;
     }
     return SEGP_OK;
+}
+
+int segp_set_param(segp_model* m, const char* name, double value) {
+    if (m == nullptr || name == nullptr) {
+        set_error("segp_set_param: null argument");
+        return SEGP_ERR_INVALID;
+    }
+    if (strcmp(name, "guard_rtol") == 0 && value > 0.0 && value < 1.0) {
+        m->guard_rtol = value;
+        DeviceGuard guard(m->device);
+        cudaDeviceSynchronize();
+        free_graphs(m);
+        return SEGP_OK;
+    }
+    if (strcmp(name, "guard_kappa") == 0 && value >= 1.0 && value <= 100.0) {
+        m->guard_kappa = value;
+        DeviceGuard guard(m->device);
+        cudaDeviceSynchronize();
+        free_graphs(m);
+        return SEGP_OK;
+    }
+    set_error("segp_set_param: unknown parameter or bad value: %s=%g", name, value);
+    return SEGP_ERR_INVALID;
+}
+
+int segp_get_param(segp_model* m, const char* name, double* value) {
+    if (m == nullptr || name == nullptr || value == nullptr) {
+        set_error("segp_get_param: null argument");
+        return SEGP_ERR_INVALID;
+    }
+    static const struct {
+        const char* name;
+        int index;
+    } stats[] = {{"probe_ran", PS_RAN},         {"probe_frac4", PS_FRAC4},   {"probe_frac5", PS_FRAC5},
+                 {"probe_err4", PS_ERR4},       {"probe_err5", PS_ERR5},     {"probe_rel4", PS_REL4},
+                 {"probe_rel5", PS_REL5},       {"probe_ratio4", PS_RATIO4}, {"probe_ratio5", PS_RATIO5},
+                 {"probe_rho4", PS_RHO4},       {"probe_rho5", PS_RHO5},     {"probe_min_var_ratio", PS_MINVAR}};
+    if (strcmp(name, "guard_rtol") == 0) {
+        *value = m->guard_rtol;
+        return SEGP_OK;
+    }
+    if (strcmp(name, "guard_kappa") == 0) {
+        *value = m->guard_kappa;
+        return SEGP_OK;
+    }
+    for (const auto& s : stats)
+        if (strcmp(name, s.name) == 0) {
+            *value = m->probe_stat[s.index];
+            return SEGP_OK;
+        }
+    set_error("segp_get_param: unknown parameter %s", name);
+    return SEGP_ERR_INVALID;
 }
 
 }  // extern "C"

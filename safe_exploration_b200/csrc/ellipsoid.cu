@@ -161,6 +161,11 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
                 for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
                 mu[d] = m;
                 var[d] = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;
+                if (a.epart != nullptr) {   // int8 contraction: a-posteriori error estimate against the variance
+                    float e2 = 0.f;
+                    for (int i = 0; i < a.nblk; ++i) e2 += a.epart[((long)d * a.nblk + i) * a.b_cap + b];
+                    if (a.guard_gs * (double)e2 > var[d] * var[d]) status |= SEGP_STATUS_LOW_PRECISION;
+                }
             } else {
                 mu[d] = a.mu_d[b * n_s + d];
                 var[d] = a.var_d[b * n_s + d];
@@ -388,11 +393,13 @@ int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
     }
     const int threads = 64;
     const unsigned grid = (unsigned)((a.n_batch - a.b0 + threads - 1) / threads);
-    if (a.n_s == 2 && a.n_u == 1)
+    // the specialised instances hold a Jacobian row in NS + NU registers: a lifting input transform (n_in > n_s) does
+    // not fit and takes the generic instance
+    if (a.n_s == 2 && a.n_u == 1 && a.n_in <= 2)
         ellipsoid_step_kernel<2, 1><<<grid, threads, 0, st>>>(a);
-    else if (a.n_s == 4 && a.n_u == 1)
+    else if (a.n_s == 4 && a.n_u == 1 && a.n_in <= 4)
         ellipsoid_step_kernel<4, 1><<<grid, threads, 0, st>>>(a);
-    else if (a.n_s <= 4 && a.n_u <= 2)
+    else if (a.n_s <= 4 && a.n_u <= 2 && a.n_in <= 4)
         ellipsoid_step_kernel<4, 2><<<grid, threads, 0, st>>>(a);
     else
         ellipsoid_step_kernel<SEGP_MAX_NS, SEGP_MAX_NU><<<grid, threads, 0, st>>>(a);

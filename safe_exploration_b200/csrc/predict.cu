@@ -440,13 +440,21 @@ int launch_tri_sumsq(const TriArgs& a, int n_s, cudaStream_t st) {
 __global__ void finalize_predict_kernel(const FinalizeArgs a) {
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.n_batch) return;
+    int32_t status = 0;
     for (int d = 0; d < a.n_s; ++d) {
         double mu = 0.0;
         for (int s = 0; s < a.nsplit; ++s) mu += a.mu_part[((long)s * a.n_s + d) * a.b_cap + b];
         double qf = 0.0;
         for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
         a.mu[b * a.n_s + d] = mu;
-        a.var[b * a.n_s + d] = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;
+        const double var = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;
+        a.var[b * a.n_s + d] = var;
+        if (!(var > 0.0)) status |= SEGP_STATUS_BAD_VARIANCE;
+        if (a.epart != nullptr) {
+            float e2 = 0.f;
+            for (int i = 0; i < a.nblk; ++i) e2 += a.epart[((long)d * a.nblk + i) * a.b_cap + b];
+            if (a.guard_gs * (double)e2 > var * var) status |= SEGP_STATUS_LOW_PRECISION;
+        }
         if (a.jac != nullptr) {
             for (int j = 0; j < a.dim; ++j) {
                 double acc = 0.0, add = 0.0;
@@ -459,6 +467,7 @@ __global__ void finalize_predict_kernel(const FinalizeArgs a) {
             }
         }
     }
+    if (a.status != nullptr) a.status[b] = status;
 }
 
 int launch_finalize_predict(const FinalizeArgs& a, cudaStream_t st) {

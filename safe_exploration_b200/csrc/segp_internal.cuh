@@ -95,6 +95,7 @@ int tri_sumsq_init();   // sets the dynamic shared memory attribute once per dev
 // TMEM accumulator per diagonal a+c; the epilogue recombines the diagonals exactly in int64 (Horner, base 254),
 // converts once to float64, squares and column-sums.  See DESIGN.md section 4.
 constexpr int I8_S = 5;        // digit planes per operand  -> 15 int8 products, ~2^-39 relative resolution
+constexpr int I8_SS = 4;       // digit planes of the diagonal-split set of W -> 10 products (+ the diagonal's extra digit)
 constexpr int I8_N = 96;       // trajectories per panel (UMMA N); I8_S * I8_N = 480 <= 512 TMEM columns
 constexpr int I8_KB = 64;      // bytes (= training points) per k-block row: one SWIZZLE_64B atom
 constexpr int I8_A_TILE = TILE * I8_KB;    // 8192 B: 128 rows of W x 64 k, one digit plane, swizzled smem image
@@ -105,45 +106,65 @@ constexpr double I8_BASE = 254.0;          // following digits
 
 struct KstarI8Args {
     KstarArgs k;            // model, inputs and mean/Jacobian partial outputs (k.ks unused)
-    int8_t* ki8;            // [n_s][npanel_cap][n_pad/64][I8_S][I8_B_TILE]           (split_halves == 0)
-                            // [n_s][npanel_cap][n_pad/64][2][I8_S][I8_B_TILE / 2]    (split_halves == 1: the two
-                            //   48-trajectory halves a CTA pair loads separately for cta_group::2 MMAs)
+    int8_t* ki8;            // [n_s][npanel_cap][n_pad/64][I8_S][I8_B_TILE]
     long npanel_cap;
-    int split_halves;
     int panel0;             // first panel of this launch (blockIdx.x counts from it): sub-chunk pipelining
     int resident_ctas;      // > 0: run as a resident grid of this many small CTAs looping over the work items
 };
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st);
 
 struct TriI8Args {
-    const int8_t* wi8;      // [n_s][nblk (nblk+1) k-blocks][I8_S][I8_A_TILE]   (block row bi starts at bi (bi+1))
+    const int8_t* wi8;      // classic set [n_s][nblk (nblk+1) k-blocks][I8_S][I8_A_TILE]   (block row bi starts at bi (bi+1))
     const double* rowfac;   // [n_s][n_pad]   rowmax_i * var_d / (127^2 254^(S-1))
     const int8_t* ki8;      // as above
-    double* qpart;          // [n_s][nblk][b_cap]
+    double* qpart;          // [n_s][nblk][b_cap]   column sums of v^2 per block row
+    float* epart;           // [n_s][nblk][b_cap]   column sums of w_i v_i^2 (error-model variance, see pack_w_i8); may be NULL
+    const float* werr;      // [n_s][n_pad] variance weights w_i of the digit set in use (NULL with epart)
+    // diagonal-split set (digits == 4): wi8 = [n_s][nblk (nblk+1)][I8_SS][I8_A_TILE], rowfac = its row factors,
+    const int8_t* wm1;      // [n_s][nblk][2][I8_A_TILE] leading digit of the diagonal entries (diagonal k-blocks only)
+    int digits;             // 5 = classic set, 15 products; 4 = diagonal-split set, 10 products
+    const int32_t* pflag;   // optional [npanel_cap]: only panels with a non-zero flag are computed (precision fallback)
     int nblk, npanels;      // npanels = END of the panel range of this launch, panel0 its begin (tri_i8m only; else 0)
     int panel0;
     int pgroup;             // tri_i8m / tri_i8mp: panels per L2 group (even; 0 = 24)
     int cluster;            // tri_i8m: CTAs per cluster sharing one W stage by multicast (2 or 4; 0 = 2)
     long npanel_cap, b_cap;
-    int32_t* dbg;           // optional raw accumulators [I8_S][128 (256 for the pair kernel)][I8_N] of one tile
-    int fix_bi;             // >= 0: single-tile self-test mode (block row, or block-row pair for the pair kernel)
+    int32_t* dbg;           // optional raw accumulators [I8_S][128][I8_N] of one tile (tri_i8 self-test)
+    int fix_bi;             // >= 0: single-tile self-test mode (block row)
     long long* prof;        // profiling only (persistent kernel): [cluster][8] clock64 counters of the MMA thread
-    int ablate;             // profiling only (pair kernel): 1 = no bulk copies, 2 = no MMAs, 4 = no epilogue math
-    const int8_t* zero_a;   // pair kernel: I8_S * I8_A_TILE zero bytes (k-blocks right of the upper block row's diagonal)
 };
+// reference kernel (one CTA per tile, classic set only): self-test and cross-check of the production kernels
 int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);
-// CTA-pair variant: cta_group::2 MMAs, M = 256 (two block rows), each CTA stages its own A rows and half of B
-int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st);
 // single-CTA MMAs, two CTAs per cluster share one block row of W through multicast bulk copies
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st);
 // persistent tri_i8m: one resident cluster per TPC walks a static list of folded (equal-length) tiles
 // leave_room: 4 epilogue warps instead of 12, so that two resident K* CTAs fit next to it on every SM
 int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_room = false);
-// persistent CTA-pair variant: one resident pair per TPC walks a static tile list
-int launch_tri_i8x2p(const TriI8Args& a, int n_s, cudaStream_t st);
 int tri_i8_init();
-// W (n_pad x n_pad fp64, lower) -> digit planes + row factors for output dimension d
-int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int n_pad, cudaStream_t st);
+// precision guard of the 10-product digit set (tri_i8.cu)
+struct GuardArgs {
+    const double* qpart;    // [n_s][nblk][b_cap]
+    const float* epart;     // [n_s][nblk][b_cap]
+    const double* gp_var;   // [n_s] prior variances k**
+    int nblk, n_s, panel0;
+    long b_cap, n_batch;    // n_batch = END of the trajectory range
+    double gs;              // (2 kappa / rtol)^2
+    int32_t* pflag;         // [npanel_cap] out
+    unsigned int* counter;  // optional: number of flagged panels (accumulates)
+};
+int launch_i8_guard(const GuardArgs& a, cudaStream_t st);
+int launch_scale_f32(float* x, long n, float f, cudaStream_t st);
+// W (n_pad x n_pad fp64, lower) -> both digit-plane sets, row factors and error-model weights of output dimension d
+struct PackI8Out {
+    int8_t* wi8;        // [nblk (nblk+1)][I8_S][I8_A_TILE]
+    double* rowfac;     // [n_pad]
+    int8_t* wi8s;       // [nblk (nblk+1)][I8_SS][I8_A_TILE]
+    int8_t* wm1;        // [nblk][2][I8_A_TILE]
+    double* rowfac_s;   // [n_pad]
+    float* werr5;       // [n_pad]
+    float* werr4;       // [n_pad]
+};
+int pack_w_i8(const double* w, const PackI8Out& o, double var, int n_pad, int n_train, cudaStream_t st);
 int i8_peak(int umma_n, int iters, int pattern, double* tops);
 
 // ---------------------------------------------------------------- posterior finalise / ellipsoid step
@@ -156,6 +177,8 @@ struct StepArgs {
     const double* invls;    // [n_s][D]
     const double* jac2_part;   // composite kernels: additive Jacobian partials (else NULL)
     const double* kss;         // composite kernels: per-trajectory prior variance [n_s][b_cap] (else NULL: gp_var)
+    const float* epart;        // int8 contraction: error-model variance partials [n_s][nblk][b_cap] (else NULL)
+    double guard_gs;           // (2 kappa / rtol)^2: SEGP_STATUS_LOW_PRECISION when guard_gs * e2 > sigma^4
     int nsplit, nblk;
     long b_cap;
     // ... or given directly (foreign state-space model): [B x n_s], [B x n_s], [B x n_s x D]
@@ -193,6 +216,9 @@ struct FinalizeArgs {
     const double* invls;
     const double* jac2_part;   // composite kernels only (else NULL)
     const double* kss;
+    const float* epart;        // as StepArgs
+    double guard_gs;
+    int32_t* status;           // [B] or NULL: SEGP_STATUS_BAD_VARIANCE / SEGP_STATUS_LOW_PRECISION per input
     int nsplit, nblk, n_s, dim;
     long b_cap, n_batch;
     double* mu;    // [B x n_s]

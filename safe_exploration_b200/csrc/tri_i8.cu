@@ -71,42 +71,97 @@ __host__ __device__ __forceinline__ int sw64_offset(int row, int k) {
 }
 
 // =========================================================================================== pack_w_i8
-__global__ void w_rowmax_kernel(const double* __restrict__ w, double* __restrict__ rowmax, int n_pad) {
-    __shared__ double s[256];
+// Two digit-plane sets of W = L^-1, both stored as SWIZZLE_64B shared-memory images:
+//   classic  rows scaled by their max-abs, 5 digits                                   (15 products, tri digits = 5)
+//   split    rows scaled by the max-abs of their OFF-diagonal entries, 4 digits; the diagonal entry 1/L_ii, which
+//            dominates every row of L^-1 (median 15 x the largest off-diagonal entry at C4) and would waste the
+//            leading plane, keeps an extra leading digit d_-1 (weight 254) in a plane of its own that is non-zero on
+//            the diagonal only and is multiplied in the two diagonal k-blocks of a block row only (10 products)
+// plus, per row, the factor that turns the recombined integer into v_i and the variance weight of the statistical
+// error model (see i8_err_weight): the epilogue column-sums w_i v_i^2 next to v_i^2, which is the a-posteriori error
+// estimate of |v|^2 behind the precision guard.
+struct RowStat {
+    double maxall, maxoff, sqall, sqoff, diag;
+};
+__global__ void w_rowstat_kernel(const double* __restrict__ w, RowStat* __restrict__ rs, int n_pad) {
+    __shared__ double s0[256], s1[256], s2[256], s3[256];
     const int i = blockIdx.x;
-    double m = 0.0;
-    for (int j = threadIdx.x; j <= i; j += 256) m = fmax(m, fabs(w[(long)i * n_pad + j]));
-    s[threadIdx.x] = m;
+    double m = 0.0, mo = 0.0, q = 0.0, qo = 0.0;
+    for (int j = threadIdx.x; j <= i; j += 256) {
+        const double v = w[(long)i * n_pad + j];
+        m = fmax(m, fabs(v));
+        q = fma(v, v, q);
+        if (j < i) {
+            mo = fmax(mo, fabs(v));
+            qo = fma(v, v, qo);
+        }
+    }
+    s0[threadIdx.x] = m;
+    s1[threadIdx.x] = mo;
+    s2[threadIdx.x] = q;
+    s3[threadIdx.x] = qo;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + o]);
+        if (threadIdx.x < o) {
+            s0[threadIdx.x] = fmax(s0[threadIdx.x], s0[threadIdx.x + o]);
+            s1[threadIdx.x] = fmax(s1[threadIdx.x], s1[threadIdx.x + o]);
+            s2[threadIdx.x] += s2[threadIdx.x + o];
+            s3[threadIdx.x] += s3[threadIdx.x + o];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) rowmax[i] = s[0];
+    if (threadIdx.x == 0) rs[i] = RowStat{s0[0], s1[0], s2[0], s3[0], w[(long)i * n_pad + i]};
 }
 
-__global__ void __launch_bounds__(TILE) pack_w_i8_kernel(const double* __restrict__ w, const double* __restrict__ rowmax,
-                                                         int8_t* __restrict__ wi8, double* __restrict__ rowfac,
-                                                         double var, int n_pad) {
+// row scale of the split planes: off-diagonal max, but never so small that the diagonal's leading digit overflows
+__device__ __forceinline__ double split_scale(const RowStat& r) { return fmax(r.maxoff, fabs(r.diag) * (1.0 / 254.0)); }
+
+// Variance of the error of v_i = sum_j W_ij k*_j computed with S digits per operand and the digit pairs a + c < S,
+// digits taken as independent and uniform:  per product term, in units u = 1 / (127 254^(S-1)) of the last digit,
+//   truncation of k* against w~      w~_ij^2 / 12
+//   truncation of w~ against k~      k~_j^2 / 12          (k~ = k*/s_f^2 in [0,1]: mean square bounded by 1/2)
+//   dropped pairs a + c = S (S - 1 of them)   1 / 36 each
+// times (row scale  s_f^2  u)^2.  i8_scheme.py (scripts/experiments) checks it against the emulated scheme.
+__device__ __forceinline__ double i8_err_weight(double scale, double var, double sumsq_scaled, int n_terms, int digits) {
+    double u = 1.0 / I8_BASE0;
+    for (int a = 1; a < digits; ++a) u /= I8_BASE;
+    const double f = scale * var * u;
+    return f * f * (sumsq_scaled * (1.0 / 12.0) + (double)n_terms * (0.5 / 12.0 + (double)(digits - 1) / 36.0));
+}
+
+__global__ void __launch_bounds__(TILE) pack_w_i8_kernel(const double* __restrict__ w, const RowStat* __restrict__ rs,
+                                                         const PackI8Out o, double var, int n_pad, int n_train) {
     const int kb = blockIdx.x, bi = blockIdx.y;
     if (kb >= 2 * (bi + 1)) return;
     const int r = threadIdx.x;
     const long row = (long)bi * TILE + r;
-    const double rm = rowmax[row];
+    const RowStat st = rs[row];
+    const double rm = st.maxall;
     const double inv = rm > 0.0 ? 1.0 / rm : 0.0;
+    const double sc = split_scale(st);
+    const double inv_s = sc > 0.0 ? 1.0 / sc : 0.0;
     if (kb == 0) {
-        double f = rm * var / (I8_BASE0 * I8_BASE0);
+        double f = var / (I8_BASE0 * I8_BASE0);
 #pragma unroll
         for (int a = 1; a < I8_S; ++a) f /= I8_BASE;
-        rowfac[row] = f;
+        o.rowfac[row] = rm * f;
+        o.rowfac_s[row] = sc * f * I8_BASE;   // accumulator slots 0..4 hold the diagonals g = -1..3: one power less
+        const bool real = row < n_train;
+        o.werr5[row] = real ? (float)i8_err_weight(rm, var, st.sqall * inv * inv, (int)row + 1, 5) : 0.f;
+        o.werr4[row] = real ? (float)i8_err_weight(sc, var, st.sqoff * inv_s * inv_s, (int)row + 1, 4) : 0.f;
     }
     const double* src = w + row * n_pad + (long)kb * I8_KB;
-    int8_t* dst = wi8 + ((long)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE);
+    int8_t* dst = o.wi8 + ((long)bi * (bi + 1) + kb) * (I8_S * I8_A_TILE);
+    int8_t* dst_s = o.wi8s + ((long)bi * (bi + 1) + kb) * (I8_SS * I8_A_TILE);
+    const bool diag_kb = kb >= 2 * bi;   // the two k-blocks that hold the diagonal block
+    int8_t* dst_m1 = o.wm1 + ((long)bi * 2 + (kb - 2 * bi)) * I8_A_TILE;
 #pragma unroll 1
     for (int c = 0; c < I8_KB / 16; ++c) {
-        uint32_t pk[I8_S][4];
+        uint32_t pk[I8_S][4], ps[I8_SS + 1][4];
 #pragma unroll
         for (int a = 0; a < I8_S; ++a) pk[a][0] = pk[a][1] = pk[a][2] = pk[a][3] = 0u;
+#pragma unroll
+        for (int a = 0; a <= I8_SS; ++a) ps[a][0] = ps[a][1] = ps[a][2] = ps[a][3] = 0u;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const long col = (long)kb * I8_KB + c * 16 + j;
@@ -115,23 +170,40 @@ __global__ void __launch_bounds__(TILE) pack_w_i8_kernel(const double* __restric
             split_digits(v * inv, dg);
 #pragma unroll
             for (int a = 0; a < I8_S; ++a) pk[a][j >> 2] |= (uint32_t)(dg[a] & 0xff) << ((j & 3) * 8);
+            // split set: off-diagonal entries v / sc in [-1, 1] -> digits 0..3; the diagonal v / (254 sc) in [-1, 1]
+            // -> digits -1..3 (one level up); slot 0 of ps is the d_-1 plane
+            int ds[I8_S];
+            if (col == row) {
+                split_digits(v * inv_s * (1.0 / I8_BASE), ds);
+#pragma unroll
+                for (int a = 0; a <= I8_SS; ++a) ps[a][j >> 2] |= (uint32_t)(ds[a] & 0xff) << ((j & 3) * 8);
+            } else {
+                split_digits(v * inv_s, ds);
+#pragma unroll
+                for (int a = 0; a < I8_SS; ++a) ps[a + 1][j >> 2] |= (uint32_t)(ds[a] & 0xff) << ((j & 3) * 8);
+            }
         }
         const int off = sw64_offset(r, c * 16);
 #pragma unroll
         for (int a = 0; a < I8_S; ++a)
             *reinterpret_cast<uint4*>(dst + (long)a * I8_A_TILE + off) = make_uint4(pk[a][0], pk[a][1], pk[a][2], pk[a][3]);
+#pragma unroll
+        for (int a = 0; a < I8_SS; ++a)
+            *reinterpret_cast<uint4*>(dst_s + (long)a * I8_A_TILE + off) =
+                make_uint4(ps[a + 1][0], ps[a + 1][1], ps[a + 1][2], ps[a + 1][3]);
+        if (diag_kb) *reinterpret_cast<uint4*>(dst_m1 + off) = make_uint4(ps[0][0], ps[0][1], ps[0][2], ps[0][3]);
     }
 }
 
-int pack_w_i8(const double* w, int8_t* wi8_d, double* rowfac_d, double var, int n_pad, cudaStream_t st) {
+int pack_w_i8(const double* w, const PackI8Out& o, double var, int n_pad, int n_train, cudaStream_t st) {
     const int nblk = n_pad / TILE;
-    double* rowmax = nullptr;
-    SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rowmax), (size_t)n_pad * sizeof(double), st));
-    w_rowmax_kernel<<<n_pad, 256, 0, st>>>(w, rowmax, n_pad);
+    RowStat* rs = nullptr;
+    SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rs), (size_t)n_pad * sizeof(RowStat), st));
+    w_rowstat_kernel<<<n_pad, 256, 0, st>>>(w, rs, n_pad);
     dim3 grid((unsigned)(2 * nblk), (unsigned)nblk);
-    pack_w_i8_kernel<<<grid, TILE, 0, st>>>(w, rowmax, wi8_d, rowfac_d, var, n_pad);
+    pack_w_i8_kernel<<<grid, TILE, 0, st>>>(w, rs, o, var, n_pad, n_train);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(rowmax, st);
+    cudaFreeAsync(rs, st);
     SEGP_CUDA_CHECK(e);
     return SEGP_OK;
 }
@@ -284,9 +356,9 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
     int8_t* panel_base = aa.ki8 + (((long)d * aa.npanel_cap + panel) * nkb) * (long)(I8_S * I8_B_TILE);
 
     // destination of this trajectory's bytes inside a k-block image
-    const int rowp = aa.split_halves ? trow % (I8_N / 2) : trow;
-    const long half_off = aa.split_halves ? (long)(trow / (I8_N / 2)) * (I8_S * (I8_B_TILE / 2)) : 0;
-    const long plane_stride = aa.split_halves ? I8_B_TILE / 2 : I8_B_TILE;
+    const int rowp = trow;
+    const long half_off = 0;
+    const long plane_stride = I8_B_TILE;
 
     if (STAGE == 0) {
         // no staging: every thread reads the training points straight through L1 (uniform addresses: one request per
@@ -577,7 +649,9 @@ __device__ __forceinline__ double i8_epilogue_chunk(uint32_t tmem_quadrant_base,
 __device__ __forceinline__ double i8_cvt_s32(uint32_t x) {
     return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
 }
-__device__ __forceinline__ double i8_epilogue_chunk_fast(uint32_t tmem_quadrant_base, int col0, double rf, int lane) {
+// `werr` >= 0: also returns in `esum` this lane's column sum of werr_row * v^2 (float32: it is an error estimate).
+__device__ __forceinline__ double i8_epilogue_chunk_fast(uint32_t tmem_quadrant_base, int col0, double rf, int lane,
+                                                         float werr, float& esum) {
     static_assert(I8_S == 5, "recombination below is written for 5 diagonals");
     uint32_t v[32];
     double acc[32];
@@ -594,6 +668,22 @@ __device__ __forceinline__ double i8_epilogue_chunk_fast(uint32_t tmem_quadrant_
     for (int j = 0; j < 32; ++j) {
         const double x = acc[j] * rf;
         acc[j] = x * x;
+    }
+    if (werr >= 0.f) {
+        float ef[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ef[j] = (float)acc[j] * werr;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+                const float keep = up ? ef[j + off] : ef[j];
+                const float give = up ? ef[j] : ef[j + off];
+                ef[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+            }
+        }
+        esum = ef[0];
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -758,19 +848,7 @@ int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st) {
     return SEGP_OK;
 }
 
-// =========================================================================================== tri_i8x2 (CTA pair)
-// Two CTAs on one TPC (cluster of 2) compute two adjacent block rows (2 bp, 2 bp + 1) x one 96-trajectory panel with
-// tcgen05.mma.cta_group::2, M = 256: every CTA stages its OWN 128 rows of W (5 planes, 40 KB per k-block) and only
-// HALF of the K* panel (48 trajectories, 15 KB); the tensor cores of the pair read both halves.  Against the
-// single-CTA kernel this cuts the shared-memory operand traffic per MMA from 7 KB to 5.5 KB per SM (below the
-// 128 B/clk that capped the N = 96 shape at 84 % of the int8 peak) and the L2 -> SM fill from 70 to 55 KB per k-block.
-// The upper block row's k-range is one diagonal block (two k-blocks) shorter; it reads zero tiles there (2.4 % extra
-// MMA work at N = 5000).  Barriers: local full (own bulk copies) + relay of the peer's full barrier to the leader,
-// empty / tmem_full by multicast tcgen05.commit to both CTAs.
-constexpr int X2_STAGES = 4;
-constexpr int X2_STAGE_BYTES = I8_S * (I8_A_TILE + I8_B_TILE / 2);   // 56320
-constexpr size_t X2_SMEM = (size_t)X2_STAGES * X2_STAGE_BYTES + 1024 + 4 * I8_N * 8 + 256;
-
+// =========================================================================================== cluster helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -804,182 +882,22 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) tri_i8x2_kernel(const TriI8Args a) {
-    const uint32_t rank = cluster_ctarank();
-    const int npairs = (a.nblk + 1) / 2;
-    // ---- tile decode (per cluster): (d, panel group) outer, pair descending (heavy first), panel inner
-    int d, bp, panel;
-    bool skip = false;
-    if (a.fix_bi >= 0) {
-        d = 0;
-        bp = a.fix_bi;
-        panel = 0;
-    } else {
-        const int cid = blockIdx.x >> 1;
-        const int tiles_per_group = I8_PANEL_GROUP * npairs;
-        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
-        const int gid = cid / tiles_per_group;
-        const int r = cid % tiles_per_group;
-        d = gid / npg;
-        const int pg = gid % npg;
-        bp = npairs - 1 - r / I8_PANEL_GROUP;
-        panel = pg * I8_PANEL_GROUP + r % I8_PANEL_GROUP;
-        skip = panel >= a.npanels;
-    }
-    if (skip) return;   // both CTAs of the cluster take the same decision
-    const int bi = 2 * bp + (int)rank;             // this CTA's block row
-    const bool has_rows = bi < a.nblk;             // odd nblk: the last pair's second CTA only feeds its B half
-    const int bi_hi = min(2 * bp + 1, a.nblk - 1);
-    const int nk = 2 * (bi_hi + 1);                // k-blocks of the pair
-    const int nk_own = has_rows ? 2 * (bi + 1) : 0;   // beyond: zero tiles
-
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t raw = smem_addr(smem_raw);
-    const uint32_t stage0 = (raw + 1023u) & ~1023u;
-    unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)X2_STAGES * X2_STAGE_BYTES;
-    double* s_col = reinterpret_cast<double*>(tail);                   // [4][I8_N]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 4 * I8_N);     // full[4], peer_full[4], empty[4], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * X2_STAGES + 1);
-    const uint32_t bar0 = smem_addr(bars);
-    auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto peer_full_bar = [&](int s) { return bar0 + 8u * (X2_STAGES + s); };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * X2_STAGES + s); };
-    const uint32_t tmem_full_bar = bar0 + 8u * (3 * X2_STAGES);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < X2_STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(peer_full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
-                     "n"(I8_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    cluster_sync_all();   // barriers of both CTAs initialised, TMEM of both allocated
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ producer: own W rows + own half of K*
-        if (lane == 0) {
-            const int8_t* wsrc = a.wi8 + ((long)d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (I8_S * I8_A_TILE);
-            const int8_t* ksrc = a.ki8 + (((long)d * a.npanel_cap + panel) * (a.nblk * 2)) * (long)(I8_S * I8_B_TILE) +
-                                 (long)rank * (I8_S * (I8_B_TILE / 2));
-            for (int it = 0; it < nk; ++it) {
-                const int s = it % X2_STAGES;
-                if (it >= X2_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((it / X2_STAGES - 1) & 1));
-                const uint32_t dst = stage0 + (uint32_t)s * X2_STAGE_BYTES;
-                if (a.ablate & 1) {
-                    mbar_expect_tx(full_bar(s), 0);
-                    continue;
-                }
-                mbar_expect_tx(full_bar(s), X2_STAGE_BYTES);
-                const int8_t* asrc = it < nk_own ? wsrc + (long)it * (I8_S * I8_A_TILE) : a.zero_a;
-                bulk_g2s(dst, asrc, I8_S * I8_A_TILE, full_bar(s));
-                bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * (I8_B_TILE / 2), full_bar(s));
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            if (rank == 1) {
-                // -------------------------------------------------------------- relay: my stage landed -> tell the leader
-                for (int it = 0; it < nk; ++it) {
-                    const int s = it % X2_STAGES;
-                    mbar_wait(full_bar(s), (uint32_t)((it / X2_STAGES) & 1));
-                    mbar_arrive_remote(peer_full_bar(s), 0u);
-                }
-            } else {
-                // -------------------------------------------------------------- MMA issuer of the pair
-                constexpr uint32_t idesc = make_i8_idesc(2 * TILE, I8_N);
-                for (int it = 0; it < nk; ++it) {
-                    const int s = it % X2_STAGES;
-                    const uint32_t par = (uint32_t)((it / X2_STAGES) & 1);
-                    mbar_wait(full_bar(s), par);
-                    mbar_wait_cluster(peer_full_bar(s), par);
-                    tc_fence_after();
-                    const uint32_t sa = stage0 + (uint32_t)s * X2_STAGE_BYTES;
-                    const uint32_t sb = sa + I8_S * I8_A_TILE;
-#pragma unroll
-                    for (int ks = 0; ks < I8_KB / 32; ++ks) {
-                        if (a.ablate & 2) break;
-#pragma unroll
-                        for (int pa = 0; pa < I8_S; ++pa) {
-                            const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
-#pragma unroll
-                            for (int pc = 0; pc < I8_S - pa; ++pc) {
-                                const uint64_t bdesc = make_sw64_desc(sb + pc * (I8_B_TILE / 2) + ks * 32);
-                                tc_mma_i8_pair(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, idesc,
-                                               (uint32_t)((it | ks | pa) != 0));
-                            }
-                        }
-                    }
-                    tc_commit_pair(empty_bar(s));
-                }
-                tc_commit_pair(tmem_full_bar);
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue: own 128 rows, as in tri_i8
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const double rf = has_rows ? a.rowfac[((long)d * a.nblk + bi) * TILE + row] : 0.0;
-        mbar_wait_cluster(tmem_full_bar, 0u);
-        tc_fence_after();
-        int32_t* dbg_row = a.dbg != nullptr ? a.dbg + ((long)rank * TILE + row) * I8_N : nullptr;
-#pragma unroll 1
-        for (int chunk = 0; chunk < ((a.ablate & 4) ? 0 : I8_N / 32); ++chunk)
-            s_col[q * I8_N + chunk * 32 + lane] = i8_epilogue_chunk(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf,
-                                                                    lane, dbg_row, (long)2 * TILE * I8_N);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int c = threadIdx.x - 64;
-        if (c < I8_N && has_rows) {
-            const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
-            const long bcol = (long)panel * I8_N + c;
-            if (bcol < a.b_cap) a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();   // the peer may still read this CTA's shared memory / signal its barriers until here
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
-                     : "memory");
-    }
-}
 
 // =========================================================================================== tri_i8m (multicast)
 // The single-CTA tile of tri_i8 (M = 128, N = 96: 58.6 clocks per MMA, bound by the 4 KB + 3 KB shared-memory operand
 // read at ~122 B/clk, see segp_i8_peak_pattern) with the L2 -> SM fill cut from 70 to 50 KB per k-block: two CTAs of a
-// cluster work on the SAME block row of W and adjacent trajectory panels, each fetches half of the 40 KB W stage and
-// multicasts it into both shared memories, and its own 30 KB K* stage.  (The cta_group::2 pair kernel needs only
-// 55 KB per k-block as well, but its MMAs take ~71 clocks: every MMA pulls the peer's half of K* across the SM pair.)
-// Barriers: full (own expect_tx of the whole 70 KB; bytes arrive from both producers), empty with 2 arrivals (both
-// MMA threads commit with the cluster multicast mask: a stage is rewritten only when both CTAs have consumed it).
+// cluster work on the SAME block row of W and adjacent trajectory panels, each fetches half of the W stage and
+// multicasts it into both shared memories, and its own K* stage.
+// Barriers: full (own expect_tx of the whole stage; bytes arrive from both producers), empty with CL arrivals (all
+// MMA threads commit with the cluster multicast mask: a stage is rewritten only when every CTA has consumed it).
+//
+// SPLIT = false: classic digit set, 5 x 5 planes, pairs a + c < 5 (15 products, 9 MMAs per k-step).
+// SPLIT = true : diagonal-split set (pack_w_i8): 4 W planes x 4 K* planes, pairs a + c < 4 (10 products, 6 MMAs per
+//                k-step); in the two diagonal k-blocks of the block row additionally the plane of the diagonal's
+//                leading digit d_-1 against all 5 K* planes (3 MMAs).  Accumulator slot s holds the diagonal
+//                g = s - 1, so the epilogue (Horner over 5 slots) is the same code with another row factor.
+// Stage layout (71680 B in both modes): [W planes: 5 x 8 KB | 4 x 8 KB + d_-1 tile 8 KB][K* planes 5 x 6 KB]; the split
+// mode copies the d_-1 tile and the fifth K* plane in diagonal k-blocks only (57344 B otherwise).
 __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
                                                    uint16_t mask) {
     asm volatile(
@@ -996,10 +914,86 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask)
 
 constexpr int I8M_EPI_WARPS = 4 * (I8_N / 32);            // one warp per (TMEM lane quadrant, 32-column chunk)
 constexpr int I8M_THREADS = 64 + 32 * I8M_EPI_WARPS;      // producer, MMA issuer, 12 epilogue warps = 448
+constexpr uint32_t I8M_SB_OFF = I8_S * I8_A_TILE;         // K* planes start here in both stage layouts
+constexpr uint32_t I8M_M1_OFF = I8_SS * I8_A_TILE;        // split mode: the d_-1 tile of a diagonal k-block
+
+// Bulk copies of k-block `kb` of a block row into one stage.  wsrc: this block row's W planes (set in use), already
+// advanced by rank * (this CTA's share) -- every CTA of the cluster fetches 1/CL of the W bytes and multicasts them.
+// diag: 0 / 1 = first / second diagonal k-block of the block row (split mode: d_-1 tile + fifth K* plane), else -1.
+template <bool SPLIT, int CL>
+__device__ __forceinline__ void i8m_produce(uint32_t dst, uint32_t full_bar, const int8_t* wsrc, const int8_t* m1src,
+                                            const int8_t* ksrc, int kb, int diag, uint32_t rank) {
+    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+    if (!SPLIT) {
+        constexpr uint32_t A_PART = I8_S * I8_A_TILE / CL;
+        mbar_expect_tx(full_bar, I8_STAGE_BYTES);
+        bulk_g2s_multicast(dst + rank * A_PART, wsrc + (long)kb * (I8_S * I8_A_TILE), A_PART, full_bar, MASK);
+        bulk_g2s(dst + I8M_SB_OFF, ksrc + (long)kb * (I8_S * I8_B_TILE), I8_S * I8_B_TILE, full_bar);
+    } else {
+        constexpr uint32_t A_PART = I8_SS * I8_A_TILE / CL;
+        constexpr uint32_t M1_PART = I8_A_TILE / CL;
+        const uint32_t kbytes = (diag >= 0 ? I8_S : I8_SS) * I8_B_TILE;
+        mbar_expect_tx(full_bar, I8_SS * I8_A_TILE + kbytes + (diag >= 0 ? I8_A_TILE : 0));
+        bulk_g2s_multicast(dst + rank * A_PART, wsrc + (long)kb * (I8_SS * I8_A_TILE), A_PART, full_bar, MASK);
+        if (diag >= 0)
+            bulk_g2s_multicast(dst + I8M_M1_OFF + rank * M1_PART, m1src + (long)diag * I8_A_TILE + rank * M1_PART, M1_PART,
+                               full_bar, MASK);
+        bulk_g2s(dst + I8M_SB_OFF, ksrc + (long)kb * (I8_S * I8_B_TILE), kbytes, full_bar);
+    }
+}
+
+// All MMAs of one k-block (two k-steps of 32).  Two K* planes per instruction where possible: planes pc and pc+1 are
+// adjacent in the stage (2 x 96 rows) and their products with one W plane belong to adjacent accumulators, so ONE
+// N = 192 MMA does both; an N = 192 instruction runs at the full pipe rate (100 clocks) instead of the
+// operand-read-bound 58.6 of N = 96.  first: first k-block of the tile (accumulators are overwritten, not added to).
+template <bool SPLIT>
+__device__ __forceinline__ void i8m_issue(uint32_t tmem_base, uint32_t sa, bool first, int diag) {
+    constexpr uint32_t idesc1 = make_i8_idesc(TILE, I8_N);
+    constexpr uint32_t idesc2 = make_i8_idesc(TILE, 2 * I8_N);
+    const uint32_t sb = sa + I8M_SB_OFF;
+#pragma unroll
+    for (int ks = 0; ks < I8_KB / 32; ++ks) {
+        if (!SPLIT) {
+#pragma unroll
+            for (int pa = 0; pa < I8_S; ++pa) {
+                const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
+                const uint32_t acc = (uint32_t)(!first || ks != 0 || pa != 0);
+#pragma unroll
+                for (int pc = 0; pc < I8_S - pa; pc += 2) {
+                    const uint64_t bdesc = make_sw64_desc(sb + pc * I8_B_TILE + ks * 32);
+                    const bool two = pc + 1 < I8_S - pa;
+                    tc_mma_i8(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, two ? idesc2 : idesc1, acc);
+                }
+            }
+        } else {
+            // diagonals g = pa + pc in 0..3 live in slots 1..4; W plane 0 writes all four first
+#pragma unroll
+            for (int pa = 0; pa < I8_SS; ++pa) {
+                const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
+                const uint32_t acc = (uint32_t)(!first || ks != 0 || pa != 0);
+#pragma unroll
+                for (int pc = 0; pc < I8_SS - pa; pc += 2) {
+                    const uint64_t bdesc = make_sw64_desc(sb + pc * I8_B_TILE + ks * 32);
+                    const bool two = pc + 1 < I8_SS - pa;
+                    tc_mma_i8(tmem_base + (uint32_t)((pa + pc + 1) * I8_N), adesc, bdesc, two ? idesc2 : idesc1, acc);
+                }
+            }
+            if (diag >= 0) {
+                // d_-1 plane against K* planes 0..4 -> diagonals -1..3 = slots 0..4.  Slot 0 is touched here only: its
+                // first MMA (first k-step of the first diagonal k-block) overwrites.  Issued after the regular MMAs so
+                // that slots 1..4 are initialised even when the diagonal k-block is the tile's first (block row 0).
+                const uint64_t adesc = make_sw64_desc(sa + I8M_M1_OFF + ks * 32);
+                tc_mma_i8(tmem_base, adesc, make_sw64_desc(sb + ks * 32), idesc1, (uint32_t)(diag != 0 || ks != 0));
+                tc_mma_i8(tmem_base + (uint32_t)(1 * I8_N), adesc, make_sw64_desc(sb + 1 * I8_B_TILE + ks * 32), idesc2, 1u);
+                tc_mma_i8(tmem_base + (uint32_t)(3 * I8_N), adesc, make_sw64_desc(sb + 3 * I8_B_TILE + ks * 32), idesc2, 1u);
+            }
+        }
+    }
+}
 
 // CL = CTAs per cluster (2 or 4): the cluster works on CL adjacent panels of one block row; every CTA fetches 1/CL of
-// the W stage and multicasts it to all, so the L2 -> SM fill per CTA and k-block is 40/CL + 30 KB.
-template <int CL>
+// the W stage and multicasts it to all, so the L2 -> SM fill per CTA and k-block is 40/CL + 30 KB (32/CL + 24 KB).
+template <int CL, bool SPLIT>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8m_kernel(const TriI8Args a) {
     static_assert(CL == 2 || CL == 4, "cluster of 2 or 4 CTAs");
     const uint32_t rank = cluster_ctarank();
@@ -1017,6 +1011,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri
         bi = a.nblk - 1 - r / PG2;
         panel = a.panel0 + pg * pgroup + CL * (r % PG2) + (int)rank;
         if (panel - (int)rank >= a.npanels) return;   // the whole cluster is past the last panel
+        if (a.pflag != nullptr) {                     // precision fallback: only clusters with a flagged panel run
+            int any = 0;
+            for (int r2 = 0; r2 < CL; ++r2) {
+                const int p2 = panel - (int)rank + r2;
+                if (p2 < a.npanels) any |= a.pflag[p2];
+            }
+            if (any == 0) return;
+        }
     }
     const bool valid = panel < a.npanels;             // ragged panel count: the last cluster's spare CTAs only help loading
     const int panel_ld = valid ? panel : a.npanels - 1;
@@ -1026,7 +1028,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri
     const uint32_t stage0 = (raw + 1023u) & ~1023u;
     unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)I8_STAGES * I8_STAGE_BYTES;
     double* s_col = reinterpret_cast<double*>(tail);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 4 * I8_N);
+    float* s_ecol = reinterpret_cast<float*>(s_col + 4 * I8_N);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ecol + 4 * I8_N);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 1);
     const uint32_t bar0 = smem_addr(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -1056,54 +1059,29 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri
 
     const int nk = 2 * (bi + 1);
     const int nkb_total = a.nblk * 2;
-    constexpr uint32_t A_HALF = I8_S * I8_A_TILE / CL;   // this CTA's share of the W stage: 20480 / 10240 B
+    constexpr int NA = SPLIT ? I8_SS : I8_S;
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
 
     if (warp == 0) {
         if (lane == 0) {
-            const int8_t* wsrc = a.wi8 + ((long)d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (I8_S * I8_A_TILE) +
-                                 (long)rank * A_HALF;
+            const int8_t* wsrc = a.wi8 + ((long)d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (NA * I8_A_TILE) +
+                                 (long)rank * (NA * I8_A_TILE / CL);
+            const int8_t* m1src = SPLIT ? a.wm1 + ((long)d * a.nblk + bi) * (2 * I8_A_TILE) : nullptr;
             const int8_t* ksrc = a.ki8 + (((long)d * a.npanel_cap + panel_ld) * nkb_total) * (long)(I8_S * I8_B_TILE);
             for (int it = 0; it < nk; ++it) {
                 const int s = it % I8_STAGES;
                 if (it >= I8_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((it / I8_STAGES - 1) & 1));
-                const uint32_t dst = stage0 + (uint32_t)s * I8_STAGE_BYTES;
-                mbar_expect_tx(full_bar(s), I8_STAGE_BYTES);
-                bulk_g2s_multicast(dst + rank * A_HALF, wsrc + (long)it * (I8_S * I8_A_TILE), A_HALF, full_bar(s),
-                                   CL_MASK);
-                bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * I8_B_TILE, full_bar(s));
+                i8m_produce<SPLIT, CL>(stage0 + (uint32_t)s * I8_STAGE_BYTES, full_bar(s), wsrc, m1src, ksrc, it,
+                                       it - (nk - 2), rank);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // Two K* planes per instruction: planes pc and pc+1 are adjacent in the stage (2 x 96 rows) and their
-            // products with W plane pa belong to the adjacent accumulators pa+pc and pa+pc+1, so ONE N = 192 MMA does
-            // both.  9 MMAs instead of 15 per k-step, the 4 KB W operand is read 9 instead of 15 times, and an N = 192
-            // instruction runs at the full pipe rate (100 clocks) instead of the operand-read-bound 58.6 of N = 96.
-            // (One logical product of width 96 (5 - pa) per W plane, cut into N <= 256 pieces -- 8 MMAs -- measured
-            // no faster: 4.15 against 4.04 ms at C4.)
-            constexpr uint32_t idesc1 = make_i8_idesc(TILE, I8_N);
-            constexpr uint32_t idesc2 = make_i8_idesc(TILE, 2 * I8_N);
             for (int it = 0; it < nk; ++it) {
                 const int s = it % I8_STAGES;
                 mbar_wait_cluster(full_bar(s), (uint32_t)((it / I8_STAGES) & 1));
                 tc_fence_after();
-                const uint32_t sa = stage0 + (uint32_t)s * I8_STAGE_BYTES;
-                const uint32_t sb = sa + I8_S * I8_A_TILE;
-#pragma unroll
-                for (int ks = 0; ks < I8_KB / 32; ++ks) {
-#pragma unroll
-                    for (int pa = 0; pa < I8_S; ++pa) {
-                        const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
-                        const uint32_t acc = (uint32_t)((it | ks | pa) != 0);
-#pragma unroll
-                        for (int pc = 0; pc < I8_S - pa; pc += 2) {
-                            const uint64_t bdesc = make_sw64_desc(sb + pc * I8_B_TILE + ks * 32);
-                            const bool two = pc + 1 < I8_S - pa;
-                            tc_mma_i8(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, two ? idesc2 : idesc1, acc);
-                        }
-                    }
-                }
+                i8m_issue<SPLIT>(tmem_base, stage0 + (uint32_t)s * I8_STAGE_BYTES, it == 0, it - (nk - 2));
                 tc_commit_multicast(empty_bar(s), CL_MASK);   // one of the CL arrivals on EVERY CTA's empty barrier
             }
             tc_commit(tmem_full_bar);
@@ -1115,17 +1093,26 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri
         const int q = warp & 3;
         const int chunk = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        const double rf = a.rowfac[((long)d * a.nblk + bi) * TILE + row];
+        const long grow = ((long)d * a.nblk + bi) * TILE + row;
+        const double rf = a.rowfac[grow];
+        const float we = a.epart != nullptr ? a.werr[grow] : -1.f;
         mbar_wait(tmem_full_bar, 0u);
         tc_fence_after();
+        float es = 0.f;
         s_col[q * I8_N + chunk * 32 + lane] =
-            i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+            i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane, we, es);
+        s_ecol[q * I8_N + chunk * 32 + lane] = es;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * I8M_EPI_WARPS) : "memory");
         const int c = threadIdx.x - 64;
         if (c < I8_N && valid) {
             const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
             const long bcol = (long)panel * I8_N + c;
-            if (bcol < a.b_cap) a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
+            if (bcol < a.b_cap) {
+                a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
+                if (a.epart != nullptr)
+                    a.epart[((long)d * a.nblk + bi) * a.b_cap + bcol] =
+                        (s_ecol[c] + s_ecol[I8_N + c]) + (s_ecol[2 * I8_N + c] + s_ecol[3 * I8_N + c]);
+            }
         }
     }
     tc_fence_before();
@@ -1135,6 +1122,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri
                      : "memory");
     }
 }
+
+constexpr size_t I8M_SMEM = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 /* alignment slack */ + 4 * I8_N * 12 + 128;
 
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
     const int cl = a.cluster == 4 ? 4 : 2;
@@ -1149,10 +1138,18 @@ int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
         set_error("tri_i8m: grid of %ld cluster tiles out of range", nclusters);
         return SEGP_ERR_INVALID;
     }
-    if (cl == 4)
-        tri_i8m_kernel<4><<<(unsigned)(4 * nclusters), I8M_THREADS, I8_SMEM, st>>>(a);
-    else
-        tri_i8m_kernel<2><<<(unsigned)(2 * nclusters), I8M_THREADS, I8_SMEM, st>>>(a);
+    const bool split = a.digits == 4;
+    if (cl == 4) {
+        if (split)
+            tri_i8m_kernel<4, true><<<(unsigned)(4 * nclusters), I8M_THREADS, I8M_SMEM, st>>>(a);
+        else
+            tri_i8m_kernel<4, false><<<(unsigned)(4 * nclusters), I8M_THREADS, I8M_SMEM, st>>>(a);
+    } else {
+        if (split)
+            tri_i8m_kernel<2, true><<<(unsigned)(2 * nclusters), I8M_THREADS, I8M_SMEM, st>>>(a);
+        else
+            tri_i8m_kernel<2, false><<<(unsigned)(2 * nclusters), I8M_THREADS, I8M_SMEM, st>>>(a);
+    }
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }
@@ -1160,12 +1157,11 @@ int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st) {
 // =========================================================================================== tri_i8mp (persistent tri_i8m)
 // Same tiles, same arithmetic, same barriers as tri_i8m, but ONE resident cluster per TPC walks a static list of
 // FOLDED tiles: a tile is (d, panel pair, fold f) and covers block rows nblk-1-f and f one after the other, so every
-// tile holds exactly 2 (nblk + 1) k-blocks and a static round-robin assignment is balanced (the persistent pair
-// kernel tri_i8x2p lost 8 % to its unequal tiles).  TMEM allocation, barrier initialisation and the cluster
-// handshakes happen once per kernel; the producer runs ahead into the next block row while the epilogue of the
-// current one drains TMEM, so the pipeline refill overlaps the (exposed) epilogue.  One more barrier: tmem_empty
-// (12 arrivals, one per epilogue warp) gates the first MMA of the next block row.  What this buys is per-tile
-// overhead: most at small N (C3: nblk = 16), little at C4/C5 where the board's power cap sets the pace.
+// tile holds exactly 2 (nblk + 1) k-blocks and a static round-robin assignment is balanced.  TMEM allocation, barrier
+// initialisation and the cluster handshakes happen once per kernel; the producer runs ahead into the next block row
+// while the epilogue of the current one drains TMEM, so the pipeline refill overlaps the (exposed) epilogue.  One
+// more barrier: tmem_empty (one arrival per epilogue warp) gates the first MMA of the next block row.  What this buys
+// is per-tile overhead: most at small N (C3: nblk = 16), little at C4/C5 where the board's power cap sets the pace.
 struct MpSub {
     int d, bi, panel, panel_ld;
     bool valid;
@@ -1194,7 +1190,7 @@ __device__ __forceinline__ void mp_decode(long v, int nfold, int npairs, int PG2
 // EPI_WARPS = 12: one 32-column chunk per epilogue warp (448 threads, 128 registers: fills the register file);
 // EPI_WARPS = 4: one warp per TMEM lane quadrant walks the three chunks (192 threads): leaves registers and threads for
 // two resident K* CTAs per SM (kstar_i8_resident_kernel), used by the pipelined driver.
-template <int EPI_WARPS>
+template <int EPI_WARPS, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1) tri_i8mp_kernel(const TriI8Args a) {
     static_assert(EPI_WARPS == 4 || EPI_WARPS == I8M_EPI_WARPS, "4 or 12 epilogue warps");
     const uint32_t rank = cluster_ctarank();
@@ -1209,7 +1205,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
     const uint32_t stage0 = (raw + 1023u) & ~1023u;
     unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)I8_STAGES * I8_STAGE_BYTES;
     double* s_col = reinterpret_cast<double*>(tail);                        // [2][4][I8_N]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 2 * 4 * I8_N);
+    float* s_ecol = reinterpret_cast<float*>(s_col + 2 * 4 * I8_N);         // [2][4][I8_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ecol + 2 * 4 * I8_N);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 2);
     const uint32_t bar0 = smem_addr(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -1239,7 +1236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nkb_total = a.nblk * 2;
-    constexpr uint32_t A_HALF = I8_S * I8_A_TILE / 2;
+    constexpr int NA = SPLIT ? I8_SS : I8_S;
 
     // the block rows of this cluster, in order; every role walks the same sequence
     auto sub_of = [&](long v, int which, MpSub& out) -> bool {
@@ -1263,26 +1260,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
                     if (!sub_of(v, which, t)) continue;
                     const int nk = 2 * (t.bi + 1);
                     const int8_t* wsrc = a.wi8 +
-                                         ((long)t.d * a.nblk * (a.nblk + 1) + (long)t.bi * (t.bi + 1)) * (I8_S * I8_A_TILE) +
-                                         (long)rank * A_HALF;
+                                         ((long)t.d * a.nblk * (a.nblk + 1) + (long)t.bi * (t.bi + 1)) * (NA * I8_A_TILE) +
+                                         (long)rank * (NA * I8_A_TILE / 2);
+                    const int8_t* m1src = SPLIT ? a.wm1 + ((long)t.d * a.nblk + t.bi) * (2 * I8_A_TILE) : nullptr;
                     const int8_t* ksrc =
                         a.ki8 + (((long)t.d * a.npanel_cap + t.panel_ld) * nkb_total) * (long)(I8_S * I8_B_TILE);
                     for (int kb = 0; kb < nk; ++kb, ++it) {
                         const int s = (int)(it % I8_STAGES);
                         if (it >= I8_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((it / I8_STAGES - 1) & 1));
-                        const uint32_t dst = stage0 + (uint32_t)s * I8_STAGE_BYTES;
-                        mbar_expect_tx(full_bar(s), I8_STAGE_BYTES);
-                        bulk_g2s_multicast(dst + rank * A_HALF, wsrc + (long)kb * (I8_S * I8_A_TILE), A_HALF, full_bar(s),
-                                           (uint16_t)3);
-                        bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)kb * (I8_S * I8_B_TILE), I8_S * I8_B_TILE,
-                                 full_bar(s));
+                        i8m_produce<SPLIT, 2>(stage0 + (uint32_t)s * I8_STAGE_BYTES, full_bar(s), wsrc, m1src, ksrc, kb,
+                                              kb - (nk - 2), rank);
                     }
                 }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc1 = make_i8_idesc(TILE, I8_N);
-            constexpr uint32_t idesc2 = make_i8_idesc(TILE, 2 * I8_N);
             long it = 0;
             uint32_t nsub = 0;
             for (long v = cluster; v < ntiles; v += nclusters)
@@ -1298,23 +1290,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
                         const int s = (int)(it % I8_STAGES);
                         mbar_wait_cluster(full_bar(s), (uint32_t)((it / I8_STAGES) & 1));
                         tc_fence_after();
-                        const uint32_t sa = stage0 + (uint32_t)s * I8_STAGE_BYTES;
-                        const uint32_t sb = sa + I8_S * I8_A_TILE;
-#pragma unroll
-                        for (int ks = 0; ks < I8_KB / 32; ++ks) {
-#pragma unroll
-                            for (int pa = 0; pa < I8_S; ++pa) {
-                                const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
-                                const uint32_t acc = (uint32_t)((kb | ks | pa) != 0);
-#pragma unroll
-                                for (int pc = 0; pc < I8_S - pa; pc += 2) {
-                                    const uint64_t bdesc = make_sw64_desc(sb + pc * I8_B_TILE + ks * 32);
-                                    const bool two = pc + 1 < I8_S - pa;
-                                    tc_mma_i8(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, two ? idesc2 : idesc1,
-                                              acc);
-                                }
-                            }
-                        }
+                        i8m_issue<SPLIT>(tmem_base, stage0 + (uint32_t)s * I8_STAGE_BYTES, kb == 0, kb - (nk - 2));
                         tc_commit_multicast(empty_bar(s), (uint16_t)3);
                     }
                     tc_commit(tmem_full_bar);
@@ -1329,7 +1305,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
             for (int which = 0; which < 2; ++which) {
                 MpSub t;
                 if (!sub_of(v, which, t)) continue;
-                const double rf = a.rowfac[((long)t.d * a.nblk + t.bi) * TILE + row];
+                const long grow = ((long)t.d * a.nblk + t.bi) * TILE + row;
+                const double rf = a.rowfac[grow];
+                const float we = a.epart != nullptr ? a.werr[grow] : -1.f;
                 if (EPI_WARPS == 4) {   // next to resident K* CTAs: sleep between polls instead of spinning on the barrier
                     while (!mbar_test(tmem_full_bar, nsub & 1u)) __nanosleep(512);
                 } else {
@@ -1337,16 +1315,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
                 }
                 tc_fence_after();
                 double* col = s_col + (nsub & 1u) * (4 * I8_N);   // double-buffered: the next block row's epilogue may
-                                                                  // start while slow threads still read this one
+                float* ecol = s_ecol + (nsub & 1u) * (4 * I8_N);  // start while slow threads still read this one
                 if (EPI_WARPS == I8M_EPI_WARPS) {
                     const int chunk = (warp - 2) >> 2;
+                    float es = 0.f;
                     col[q * I8_N + chunk * 32 + lane] =
-                        i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+                        i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane, we, es);
+                    ecol[q * I8_N + chunk * 32 + lane] = es;
                 } else {
 #pragma unroll 1
-                    for (int chunk = 0; chunk < I8_N / 32; ++chunk)
+                    for (int chunk = 0; chunk < I8_N / 32; ++chunk) {
+                        float es = 0.f;
                         col[q * I8_N + chunk * 32 + lane] =
-                            i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane);
+                            i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane, we, es);
+                        ecol[q * I8_N + chunk * 32 + lane] = es;
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1356,7 +1339,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
                 if (c < I8_N && t.valid) {
                     const double sum = (col[c] + col[I8_N + c]) + (col[2 * I8_N + c] + col[3 * I8_N + c]);
                     const long bcol = (long)t.panel * I8_N + c;
-                    if (bcol < a.b_cap) a.qpart[((long)t.d * a.nblk + t.bi) * a.b_cap + bcol] = sum;
+                    if (bcol < a.b_cap) {
+                        a.qpart[((long)t.d * a.nblk + t.bi) * a.b_cap + bcol] = sum;
+                        if (a.epart != nullptr)
+                            a.epart[((long)t.d * a.nblk + t.bi) * a.b_cap + bcol] =
+                                (ecol[c] + ecol[I8_N + c]) + (ecol[2 * I8_N + c] + ecol[3 * I8_N + c]);
+                    }
                 }
                 ++nsub;
             }
@@ -1369,7 +1357,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
     }
 }
 
-constexpr size_t I8MP_SMEM = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 /* alignment slack */ + 2 * 4 * I8_N * 8 + 128;
+constexpr size_t I8MP_SMEM = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 /* alignment slack */ + 2 * 4 * I8_N * 12 + 128;
 
 int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_room) {
     const int nfold = (a.nblk + 1) / 2;
@@ -1377,6 +1365,10 @@ int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_roo
     const long ntiles = (long)n_s * nfold * npairs;
     if (ntiles <= 0) {
         set_error("tri_i8mp: empty tile list");
+        return SEGP_ERR_INVALID;
+    }
+    if (a.pflag != nullptr) {
+        set_error("tri_i8mp: the per-panel precision fallback runs on tri_i8m");
         return SEGP_ERR_INVALID;
     }
     static int n_sm = 0;
@@ -1388,299 +1380,94 @@ int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_roo
     const long nclusters = std::min<long>(ntiles, std::max(1, n_sm / 2));
     TriI8Args b = a;
     b.fix_bi = n_s;   // fix_bi (self-test tile selector of the other kernels) carries n_s into this one
-    if (leave_room)
-        tri_i8mp_kernel<4><<<(unsigned)(2 * nclusters), 64 + 32 * 4, I8MP_SMEM, st>>>(b);
-    else
-        tri_i8mp_kernel<I8M_EPI_WARPS><<<(unsigned)(2 * nclusters), I8M_THREADS, I8MP_SMEM, st>>>(b);
-    SEGP_CUDA_CHECK(cudaGetLastError());
-    return SEGP_OK;
-}
-
-// =========================================================================================== tri_i8x2p (persistent)
-// Same tiles, same arithmetic, same barriers as tri_i8x2, but ONE resident CTA pair per TPC walks a static list of
-// tiles (heavy-first order, boustrophedon over the clusters so every cluster gets the same mix of long and short
-// tiles): TMEM allocation, barrier initialisation and the cluster handshakes happen once per kernel instead of once per
-// tile, the producer runs ahead into the next tile while the epilogue of the current one drains TMEM, and no cluster
-// launch latency sits between tiles (the per-tile overhead of tri_i8x2 was ~14k clocks, 18 % of the MMA time at C4).
-// One more barrier: tmem_empty (leader CTA, 2 arrivals = the epilogues of both CTAs) gates the first MMA of the next tile.
-struct X2Tile {
-    int d, bp, panel;
-};
-__device__ __forceinline__ bool x2_decode_tile(const TriI8Args& a, long t, int npairs, X2Tile& out) {
-    if (a.fix_bi >= 0) {
-        out.d = 0;
-        out.bp = a.fix_bi;
-        out.panel = 0;
-        return t == 0;
-    }
-    const int tiles_per_group = I8_PANEL_GROUP * npairs;
-    const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
-    const long gid = t / tiles_per_group;
-    const int r = (int)(t % tiles_per_group);
-    out.d = (int)(gid / npg);
-    const int pg = (int)(gid % npg);
-    out.bp = npairs - 1 - r / I8_PANEL_GROUP;
-    out.panel = pg * I8_PANEL_GROUP + r % I8_PANEL_GROUP;
-    return out.panel < a.npanels;
-}
-// tile index of round `rr` for cluster `c` of `nc`: even rounds left to right, odd rounds right to left
-__device__ __forceinline__ long x2_tile_of_round(long rr, int c, int nc) {
-    return rr * nc + ((rr & 1) ? (nc - 1 - c) : c);
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
-    tri_i8x2p_kernel(const TriI8Args a, const long n_tiles) {
-    const uint32_t rank = cluster_ctarank();
-    const int npairs = (a.nblk + 1) / 2;
-    const int cluster = blockIdx.x >> 1;
-    const int nclusters = gridDim.x >> 1;
-
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t raw = smem_addr(smem_raw);
-    const uint32_t stage0 = (raw + 1023u) & ~1023u;
-    unsigned char* tail = smem_raw + (stage0 - raw) + (size_t)X2_STAGES * X2_STAGE_BYTES;
-    double* s_col = reinterpret_cast<double*>(tail);                   // [4][I8_N]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + 4 * I8_N);     // full[4], peer_full[4], empty[4], tmem_full, tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * X2_STAGES + 2);
-    const uint32_t bar0 = smem_addr(bars);
-    auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto peer_full_bar = [&](int s) { return bar0 + 8u * (X2_STAGES + s); };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * X2_STAGES + s); };
-    const uint32_t tmem_full_bar = bar0 + 8u * (3 * X2_STAGES);
-    const uint32_t tmem_empty_bar = bar0 + 8u * (3 * X2_STAGES + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < X2_STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(peer_full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, 2);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
-                     "n"(I8_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            long g = 0;   // running k-block counter: ring stage g % 4, phase (g / 4) & 1
-            for (long rr = 0;; ++rr) {
-                const long t = x2_tile_of_round(rr, cluster, nclusters);
-                if (rr * nclusters >= n_tiles) break;
-                X2Tile tl;
-                if (t >= n_tiles || !x2_decode_tile(a, t, npairs, tl)) continue;
-                const int bi = 2 * tl.bp + (int)rank;
-                const bool has_rows = bi < a.nblk;
-                const int bi_hi = min(2 * tl.bp + 1, a.nblk - 1);
-                const int nk = 2 * (bi_hi + 1);
-                const int nk_own = has_rows ? 2 * (bi + 1) : 0;
-                const int8_t* wsrc =
-                    a.wi8 + ((long)tl.d * a.nblk * (a.nblk + 1) + (long)bi * (bi + 1)) * (I8_S * I8_A_TILE);
-                const int8_t* ksrc = a.ki8 +
-                                     (((long)tl.d * a.npanel_cap + tl.panel) * (a.nblk * 2)) * (long)(I8_S * I8_B_TILE) +
-                                     (long)rank * (I8_S * (I8_B_TILE / 2));
-                for (int it = 0; it < nk; ++it, ++g) {
-                    const int s = (int)(g % X2_STAGES);
-                    if (g >= X2_STAGES) mbar_wait_cluster(empty_bar(s), (uint32_t)((g / X2_STAGES - 1) & 1));
-                    const uint32_t dst = stage0 + (uint32_t)s * X2_STAGE_BYTES;
-                    if (a.ablate & 1) {
-                        mbar_expect_tx(full_bar(s), 0);
-                        continue;
-                    }
-                    mbar_expect_tx(full_bar(s), X2_STAGE_BYTES);
-                    const int8_t* asrc = it < nk_own ? wsrc + (long)it * (I8_S * I8_A_TILE) : a.zero_a;
-                    bulk_g2s(dst, asrc, I8_S * I8_A_TILE, full_bar(s));
-                    bulk_g2s(dst + I8_S * I8_A_TILE, ksrc + (long)it * (I8_S * I8_B_TILE), I8_S * (I8_B_TILE / 2),
-                             full_bar(s));
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            long g = 0;
-            long ti = 0;   // tiles done by this cluster: phase of the tmem barriers
-            constexpr uint32_t idesc = make_i8_idesc(2 * TILE, I8_N);
-            const bool prof = a.prof != nullptr && rank == 0;
-            long long t_start = 0, t_full = 0, t_peer = 0, t_tmem = 0, c0 = 0;
-            if (prof) t_start = clock64();
-            for (long rr = 0;; ++rr) {
-                const long t = x2_tile_of_round(rr, cluster, nclusters);
-                if (rr * nclusters >= n_tiles) break;
-                X2Tile tl;
-                if (t >= n_tiles || !x2_decode_tile(a, t, npairs, tl)) continue;
-                const int bi_hi = min(2 * tl.bp + 1, a.nblk - 1);
-                const int nk = 2 * (bi_hi + 1);
-                if (rank == 1) {
-                    // ---------------------------------------------------------- relay my full barriers to the leader
-                    for (int it = 0; it < nk; ++it, ++g) {
-                        const int s = (int)(g % X2_STAGES);
-                        mbar_wait(full_bar(s), (uint32_t)((g / X2_STAGES) & 1));
-                        mbar_arrive_remote(peer_full_bar(s), 0u);
-                    }
-                    continue;
-                }
-                // -------------------------------------------------------------- MMA issuer of the pair
-                if (ti > 0) {   // both epilogues have drained the accumulators of the previous tile
-                    if (prof) c0 = clock64();
-                    mbar_wait_cluster(tmem_empty_bar, (uint32_t)((ti - 1) & 1));
-                    if (prof) t_tmem += clock64() - c0;
-                    tc_fence_after();
-                }
-                for (int it = 0; it < nk; ++it, ++g) {
-                    const int s = (int)(g % X2_STAGES);
-                    const uint32_t par = (uint32_t)((g / X2_STAGES) & 1);
-                    if (prof) c0 = clock64();
-                    mbar_wait(full_bar(s), par);
-                    if (prof) {
-                        const long long c1 = clock64();
-                        t_full += c1 - c0;
-                        c0 = c1;
-                    }
-                    mbar_wait_cluster(peer_full_bar(s), par);
-                    if (prof) t_peer += clock64() - c0;
-                    tc_fence_after();
-                    const uint32_t sa = stage0 + (uint32_t)s * X2_STAGE_BYTES;
-                    const uint32_t sb = sa + I8_S * I8_A_TILE;
-#pragma unroll
-                    for (int ks = 0; ks < I8_KB / 32; ++ks) {
-                        if (a.ablate & 2) break;
-#pragma unroll
-                        for (int pa = 0; pa < I8_S; ++pa) {
-                            const uint64_t adesc = make_sw64_desc(sa + pa * I8_A_TILE + ks * 32);
-#pragma unroll
-                            for (int pc = 0; pc < I8_S - pa; ++pc) {
-                                const uint64_t bdesc = make_sw64_desc(sb + pc * (I8_B_TILE / 2) + ks * 32);
-                                tc_mma_i8_pair(tmem_base + (uint32_t)((pa + pc) * I8_N), adesc, bdesc, idesc,
-                                               (uint32_t)((it | ks | pa) != 0));
-                            }
-                        }
-                    }
-                    tc_commit_pair(empty_bar(s));
-                }
-                tc_commit_pair(tmem_full_bar);
-                ++ti;
-            }
-            if (prof) {
-                long long* o = a.prof + (long)cluster * 8;
-                uint32_t smid;
-                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                o[0] = clock64() - t_start;
-                o[1] = t_full;
-                o[2] = t_peer;
-                o[3] = t_tmem;
-                o[4] = ti;
-                o[5] = g;
-                o[6] = (long long)smid;
-                o[7] = 0;
-            }
-        }
+    const bool split = a.digits == 4;
+    const unsigned grid = (unsigned)(2 * nclusters);
+    if (leave_room) {
+        if (split)
+            tri_i8mp_kernel<4, true><<<grid, 64 + 32 * 4, I8MP_SMEM, st>>>(b);
+        else
+            tri_i8mp_kernel<4, false><<<grid, 64 + 32 * 4, I8MP_SMEM, st>>>(b);
     } else {
-        // ------------------------------------------------------------------ epilogue
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        long ti = 0;
-        for (long rr = 0;; ++rr) {
-            const long t = x2_tile_of_round(rr, cluster, nclusters);
-            if (rr * nclusters >= n_tiles) break;
-            X2Tile tl;
-            if (t >= n_tiles || !x2_decode_tile(a, t, npairs, tl)) continue;
-            const int bi = 2 * tl.bp + (int)rank;
-            const bool has_rows = bi < a.nblk;
-            const double rf = has_rows ? a.rowfac[((long)tl.d * a.nblk + bi) * TILE + row] : 0.0;
-            mbar_wait_cluster(tmem_full_bar, (uint32_t)(ti & 1));
-            tc_fence_after();
-            int32_t* dbg_row = a.dbg != nullptr ? a.dbg + ((long)rank * TILE + row) * I8_N : nullptr;
-#pragma unroll 1
-            for (int chunk = 0; chunk < ((a.ablate & 4) ? 0 : I8_N / 32); ++chunk)
-                s_col[q * I8_N + chunk * 32 + lane] = i8_epilogue_chunk(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32,
-                                                                        rf, lane, dbg_row, (long)2 * TILE * I8_N);
-            tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // all four quadrants read: TMEM may be overwritten
-            if (threadIdx.x == 64) {
-                if (rank == 0)
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar) : "memory");
-                else
-                    mbar_arrive_remote(tmem_empty_bar, 0u);
-            }
-            const int c = threadIdx.x - 64;
-            if (c < I8_N && has_rows) {
-                const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
-                const long bcol = (long)tl.panel * I8_N + c;
-                if (bcol < a.b_cap) a.qpart[((long)tl.d * a.nblk + bi) * a.b_cap + bcol] = sum;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // s_col is free for the next tile
-            ++ti;
-        }
+        if (split)
+            tri_i8mp_kernel<I8M_EPI_WARPS, true><<<grid, I8M_THREADS, I8MP_SMEM, st>>>(b);
+        else
+            tri_i8mp_kernel<I8M_EPI_WARPS, false><<<grid, I8M_THREADS, I8MP_SMEM, st>>>(b);
     }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(I8_TMEM_COLS)
-                     : "memory");
-    }
-}
-
-int launch_tri_i8x2p(const TriI8Args& a, int n_s, cudaStream_t st) {
-    long n_tiles = 1;
-    if (a.fix_bi < 0) {
-        const int npairs = (a.nblk + 1) / 2;
-        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
-        n_tiles = (long)n_s * npg * I8_PANEL_GROUP * npairs;
-    }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        SEGP_CUDA_CHECK(cudaGetDevice(&dev));
-        SEGP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (n_tiles <= 0) {
-        set_error("tri_i8x2p: no tiles");
-        return SEGP_ERR_INVALID;
-    }
-    const long nclusters = std::min<long>(std::max(sms / 2, 1), n_tiles);
-    tri_i8x2p_kernel<<<(unsigned)(2 * nclusters), I8_THREADS, X2_SMEM, st>>>(a, n_tiles);
-    SEGP_CUDA_CHECK(cudaGetLastError());
-    return SEGP_OK;
-}
-
-int launch_tri_i8x2(const TriI8Args& a, int n_s, cudaStream_t st) {
-    long nclusters = 1;
-    if (a.fix_bi < 0) {
-        const int npairs = (a.nblk + 1) / 2;
-        const int npg = (a.npanels + I8_PANEL_GROUP - 1) / I8_PANEL_GROUP;
-        nclusters = (long)n_s * npg * I8_PANEL_GROUP * npairs;
-    }
-    if (nclusters <= 0 || 2 * nclusters > 2147483647L) {
-        set_error("tri_i8x2: grid of %ld cluster tiles out of range", nclusters);
-        return SEGP_ERR_INVALID;
-    }
-    tri_i8x2_kernel<<<(unsigned)(2 * nclusters), I8_THREADS, X2_SMEM, st>>>(a);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }
 
 int tri_i8_init() {
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8x2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8m_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel<I8M_EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)I8MP_SMEM));
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(tri_i8mp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8MP_SMEM));
+#define SEGP_I8_ATTR(K, BYTES) SEGP_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)))
+    SEGP_I8_ATTR((tri_i8m_kernel<2, false>), I8M_SMEM);
+    SEGP_I8_ATTR((tri_i8m_kernel<2, true>), I8M_SMEM);
+    SEGP_I8_ATTR((tri_i8m_kernel<4, false>), I8M_SMEM);
+    SEGP_I8_ATTR((tri_i8m_kernel<4, true>), I8M_SMEM);
+    SEGP_I8_ATTR((tri_i8mp_kernel<I8M_EPI_WARPS, false>), I8MP_SMEM);
+    SEGP_I8_ATTR((tri_i8mp_kernel<I8M_EPI_WARPS, true>), I8MP_SMEM);
+    SEGP_I8_ATTR((tri_i8mp_kernel<4, false>), I8MP_SMEM);
+    SEGP_I8_ATTR((tri_i8mp_kernel<4, true>), I8MP_SMEM);
+#undef SEGP_I8_ATTR
     exp2_tab_kernel<<<1, 64>>>();   // the device's exp2, as the shared-memory tables of the other K* kernels: same bits
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+// =========================================================================================== precision guard
+// After a contraction on the 10-product digit set: per trajectory and output dimension,
+//   sigma^2 = k** - sum_bi qpart,   e2 = sum_bi epart  (error-model variance of the |v|^2 just computed),
+// a panel is flagged when  (2 kappa)^2 e2 > (rtol sigma^2)^2  for any of its trajectories (or sigma^2 <= 0): the
+// 15-product kernel then recomputes the flagged panels (TriI8Args::pflag).  One block per 96-trajectory panel,
+// blockDim.y = 4 splits the block rows; the flag needs no particular summation order.
+__global__ void __launch_bounds__(4 * I8_N) i8_guard_kernel(const GuardArgs a) {
+    __shared__ double s_q[4][I8_N];
+    __shared__ float s_e[4][I8_N];
+    const int panel = a.panel0 + (int)blockIdx.x;
+    const long b = (long)panel * I8_N + threadIdx.x;
+    int flag = 0;
+    for (int d = 0; d < a.n_s; ++d) {
+        double q = 0.0;
+        float e = 0.f;
+        if (b < a.n_batch) {
+            for (int i = threadIdx.y; i < a.nblk; i += 4) {
+                const long idx = ((long)d * a.nblk + i) * a.b_cap + b;
+                q += a.qpart[idx];
+                e += a.epart[idx];
+            }
+        }
+        s_q[threadIdx.y][threadIdx.x] = q;
+        s_e[threadIdx.y][threadIdx.x] = e;
+        __syncthreads();
+        if (threadIdx.y == 0 && b < a.n_batch) {
+            const double qs = (s_q[0][threadIdx.x] + s_q[1][threadIdx.x]) + (s_q[2][threadIdx.x] + s_q[3][threadIdx.x]);
+            const double es = (double)((s_e[0][threadIdx.x] + s_e[1][threadIdx.x]) + (s_e[2][threadIdx.x] + s_e[3][threadIdx.x]));
+            const double s2 = a.gp_var[d] - qs;
+            if (!(s2 > 0.0) || a.gs * es > s2 * s2) flag = 1;
+        }
+        __syncthreads();
+    }
+    const int any = __syncthreads_or(flag);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        a.pflag[panel] = any;
+        if (any && a.counter != nullptr) atomicAdd(a.counter, 1u);
+    }
+}
+
+int launch_i8_guard(const GuardArgs& a, cudaStream_t st) {
+    const int npanels = (int)((a.n_batch + I8_N - 1) / I8_N) - a.panel0;
+    if (npanels <= 0) return SEGP_OK;
+    i8_guard_kernel<<<(unsigned)npanels, dim3(I8_N, 4), 0, st>>>(a);
+    SEGP_CUDA_CHECK(cudaGetLastError());
+    return SEGP_OK;
+}
+
+__global__ void scale_f32_kernel(float* __restrict__ x, long n, float f) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= f;
+}
+int launch_scale_f32(float* x, long n, float f, cudaStream_t st) {
+    scale_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, f);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }

@@ -68,12 +68,38 @@ def broadcast_factor(gp, src=0, group=None):
     from .ssm import _tensor_from_ptr
     torch = gp._torch
     rank = dist.get_rank(group)
-    views = [_tensor_from_ptr(torch, ptr, nbytes, gp.device) for ptr, nbytes in gp.factor_buffers()]
+    # ONE broadcast: buffer 0 is the whole factorised state of the int8 path (a single device allocation).  Only a
+    # model that runs the float64 contraction has a second buffer (the DMMA operand); whether it does is a property
+    # of the configuration every rank shares ("fp64_operand_needed": composite kernels, N_pad > 16384, tri_mode 0)
+    # or, for a probe-triggered float64 fallback, known after buffer 0 has arrived.
+    bufs = gp.factor_buffers()
+    views = [_tensor_from_ptr(torch, bufs[0][0], bufs[0][1], gp.device)]
     torch.cuda.synchronize(gp.device)
     broadcast_buffers(views, src, group)
     torch.cuda.synchronize(gp.device)
     if rank != src:
-        gp.mark_factorized()
+        try:
+            gp.mark_factorized()
+            need = False
+        except ValueError:
+            need = True
+    else:
+        need = len(bufs) > 1 and bool(gp.get_option("fp64_operand_needed"))
+    flag = torch.tensor([1 if need else 0], dtype=torch.int32, device=gp.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()):
+        if rank != src:
+            gp.alloc_fp64_operand()
+        bufs = gp.factor_buffers()
+        if len(bufs) < 2:
+            raise RuntimeError("the factorising rank did not keep the float64 operand (set tri_mode / keep_fp64 "
+                               "before training)")
+        v1 = _tensor_from_ptr(torch, bufs[1][0], bufs[1][1], gp.device)
+        broadcast_buffers([v1], src, group)
+        torch.cuda.synchronize(gp.device)
+        views.append(v1)
+        if rank != src:
+            gp.mark_factorized()
     return sum(v.numel() for v in views)
 
 

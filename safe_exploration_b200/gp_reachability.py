@@ -73,7 +73,9 @@ def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safe
     on the device (segp_multistep, asynchronous on the current stream) and return tensors.
     propagation  0 ellipsoid reachability (default); 1 / 2: q_all holds Gaussian covariances propagated by the
               first-order Taylor / mean-equivalent scheme (see uncertainty_propagation.py); l_mu, l_sigma, c_safety unused
-    out       optional RolloutResult of host arrays to write into (host path only; see pinned_result)
+    out       optional RolloutResult to write into: host arrays on the host path (see pinned_result), CUDA tensors on
+              the device path.  Re-using the same buffers lets the library replay the call as a CUDA graph (one
+              handle serves one call at a time: calls on the same model must not overlap on different streams)
     Returns RolloutResult(p_all (B,H,n_s), q_all (B,H,n_s,n_s), var_all (B,H,n_s) | None, status (B,) int32).
     """
     if not isinstance(gp, BatchedGPSSM):
@@ -101,15 +103,38 @@ def rollout(gp, p_0, k_ff, k_fb, l_mu, l_sigma, q_0=None, k_fb_init=None, c_safe
         q0_d = prep(q_0)
         kfb_d = prep(k_fb) if hor > 1 else None
         kfbi_d = prep(k_fb_init)
-        p0_stride = 0 if p0_d.numel() == n_s else n_s
-        q0_stride = 0 if (q0_d is None or q0_d.numel() == n_s * n_s) else n_s * n_s
         per = max(hor - 1, 0) * n_u * n_s
+        # the kernels derive every address from these sizes: a mis-shaped tensor must fail here, not read out of bounds
+        if p0_d.numel() not in (n_s, bsz * n_s):
+            raise ValueError("p_0 must be (n_s,), (n_s,1) or (B,n_s)")
+        if q0_d is not None and q0_d.numel() not in (n_s * n_s, bsz * n_s * n_s):
+            raise ValueError("q_0 must be (n_s,n_s) or (B,n_s,n_s)")
+        if hor > 1 and kfb_d is None:
+            raise ValueError("k_fb is required for H > 1")
+        if kfb_d is not None and kfb_d.numel() not in (per, bsz * per):
+            raise ValueError("k_fb must be (H-1,n_u,n_s) or (B,H-1,n_u,n_s)")
+        if kfbi_d is not None and kfbi_d.numel() not in (n_u * n_s, bsz * n_u * n_s):
+            raise ValueError("k_fb_init must be (n_u,n_s) or (B,n_u,n_s)")
+        if q0_d is not None and kfbi_d is None:
+            raise ValueError("k_fb_init is required when q_0 is given")
+        p0_stride = 0 if (p0_d.numel() == n_s or bsz == 1) else n_s
+        q0_stride = 0 if (q0_d is None or q0_d.numel() == n_s * n_s) else n_s * n_s
         kfb_stride = 0 if (kfb_d is None or kfb_d.numel() == per) else per
         kfbi_stride = 0 if (kfbi_d is None or kfbi_d.numel() == n_u * n_s) else n_u * n_s
-        p_all = torch.empty((bsz, hor, n_s), dtype=torch.float64, device=dev)
-        q_all = torch.empty((bsz, hor, n_s, n_s), dtype=torch.float64, device=dev)
-        var_all = torch.empty((bsz, hor, n_s), dtype=torch.float64, device=dev) if want_var else None
-        status = torch.empty((bsz,), dtype=torch.int32, device=dev)
+        if out is not None:
+            p_all, q_all, var_all, status = out.p_all, out.q_all, (out.var_all if want_var else None), out.status
+            for arr, shape, dt in ((p_all, (bsz, hor, n_s), torch.float64), (q_all, (bsz, hor, n_s, n_s), torch.float64),
+                                   (var_all, (bsz, hor, n_s), torch.float64), (status, (bsz,), torch.int32)):
+                if arr is not None and (not _is_tensor(arr) or not arr.is_cuda or tuple(arr.shape) != shape or
+                                        arr.dtype != dt or not arr.is_contiguous()):
+                    raise ValueError("out buffers must be contiguous CUDA tensors of shape {}".format(shape))
+            if want_var and var_all is None:
+                raise ValueError("out.var_all is required when want_var is true")
+        else:
+            p_all = torch.empty((bsz, hor, n_s), dtype=torch.float64, device=dev)
+            q_all = torch.empty((bsz, hor, n_s, n_s), dtype=torch.float64, device=dev)
+            var_all = torch.empty((bsz, hor, n_s), dtype=torch.float64, device=dev) if want_var else None
+            status = torch.empty((bsz,), dtype=torch.int32, device=dev)
         _lib.check(lib.segp_multistep(gp._handle, bsz, hor, _lib.dev_ptr(p0_d), p0_stride, _lib.dev_ptr(q0_d),
                                       q0_stride, _lib.dev_ptr(k_ff_d), _lib.dev_ptr(kfb_d), kfb_stride,
                                       _lib.dev_ptr(kfbi_d), kfbi_stride, prm, _lib.dev_ptr(p_all),

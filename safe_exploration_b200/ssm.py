@@ -33,11 +33,12 @@ from . import _lib
 __all__ = ["BatchedGPSSM"]
 
 # Which tensor pipe runs the variance contraction of new models (include/segp.h, option "tri_mode"):
-# -1 automatic (int8 digit planes on tcgen05 when the padded training size allows, else fp64 DMMA), 0 fp64 DMMA,
-# 1..5 the tcgen05 kernels (4, the default: single-CTA MMAs over two K* planes, W multicast over a CTA pair; 5: the
-# same as a persistent kernel over folded tiles).  All
-# are products of this package and all meet the rtol 1e-4 gate; tests run every one.
+# -1 automatic (int8 digit planes on tcgen05 when the padded training size allows and the factorize-time probe finds
+# them precise enough, else fp64 DMMA), 0 fp64 DMMA, 1 the int8 reference kernel (test cross-check), 4 / 5 the
+# production tcgen05 kernels (one cluster per tile / persistent).  "i8_digits": 0 automatic, 5 = 15 int8 products,
+# 4 = 10 products (diagonal-split digit set), guarded by the a-posteriori error estimate.
 DEFAULT_TRI_MODE = int(os.environ.get("SEGP_TRI_MODE", "-1"))
+DEFAULT_I8_DIGITS = int(os.environ.get("SEGP_I8_DIGITS", "0"))
 
 _GPY_JITTER = 1e-8        # ExactGaussianInference adds 1e-8 to the diagonal of K
 _GPY_DEFAULT_NOISE = 1.0  # GPRegression default Gaussian_noise.variance
@@ -118,7 +119,8 @@ class BatchedGPSSM(object):
     has_reverse = False
 
     def __init__(self, n_s_out, n_s_in, n_u, X=None, y=None, m=None, kern_types=None, hyp=None, train=True,
-                 Z=None, device=None, noise_diag=1e-5, tri_mode=None, composite_semantics="casadi"):
+                 Z=None, device=None, noise_diag=1e-5, tri_mode=None, composite_semantics="casadi", i8_digits=None,
+                 guard_rtol=None):
         torch = _lib.require_cuda()
         self._torch = torch
         self._lib = _lib.load()
@@ -157,6 +159,11 @@ class BatchedGPSSM(object):
         if tri_mode is None:
             tri_mode = 0 if self.has_composite else DEFAULT_TRI_MODE
         self.set_option("tri_mode", tri_mode)
+        if not self.has_composite:
+            self.set_option("i8_digits", DEFAULT_I8_DIGITS if i8_digits is None else i8_digits)
+        if guard_rtol is not None:
+            self.set_param("guard_rtol", guard_rtol)
+        self.last_predict_status = None
         if X is not None and y is not None and train:
             self.train(X, y)
 
@@ -296,8 +303,14 @@ class BatchedGPSSM(object):
         if self.m is not None:      # subset-of-data models re-select from the whole set
             return self.train(np.vstack((self.x_train, x_h)), np.vstack((self.y_train, y_h)))
         with self._torch.cuda.device(self.device):
-            _lib.check(self._lib.segp_append(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
-                                             _lib.current_stream(self.device)))
+            try:
+                _lib.check(self._lib.segp_append(self._handle, x_h.shape[0], _lib.dbl_ptr(x_h), _lib.dbl_ptr(y_h),
+                                                 _lib.current_stream(self.device)))
+            except Exception:
+                # the library restores the previous model when an update fails; if even that failed the handle is
+                # unfactorised and says so
+                self.gp_trained = bool(self.get_option("factorized"))
+                raise
         self.x_train = np.vstack((self.x_train, x_h))
         self.y_train = np.vstack((self.y_train, y_h))
         self.z = self.x_train
@@ -321,6 +334,10 @@ class BatchedGPSSM(object):
         self._upload(x_h, y_h)
         self.x_train, self.y_train, self.z = x_h, y_h, x_h
         self.gp_trained = False
+
+    def alloc_fp64_operand(self):
+        """Allocate the float64 DMMA operand (factor buffer 1) on a rank that receives it by broadcast."""
+        _lib.check(self._lib.segp_alloc_fp64_operand(self._handle))
 
     def mark_factorized(self):
         _lib.check(self._lib.segp_mark_factorized(self._handle))
@@ -354,8 +371,11 @@ class BatchedGPSSM(object):
         mu = torch.empty((t, self.n_s_out), dtype=torch.float64, device=self.device)
         var = torch.empty((t, self.n_s_out), dtype=torch.float64, device=self.device)
         jac = torch.empty((t, self.n_s_out, self.dim_in), dtype=torch.float64, device=self.device) if jacobians else None
-        _lib.check(self._lib.segp_predict(self._handle, t, _lib.dev_ptr(z), _lib.dev_ptr(mu), _lib.dev_ptr(var),
-                                          _lib.dev_ptr(jac), _lib.current_stream(self.device)))
+        status = torch.empty((t,), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.segp_predict_ex(self._handle, t, _lib.dev_ptr(z), _lib.dev_ptr(mu), _lib.dev_ptr(var),
+                                             _lib.dev_ptr(jac), _lib.dev_ptr(status), _lib.current_stream(self.device)))
+        # per-input bits (_lib.STATUS_BAD_VARIANCE, _lib.STATUS_LOW_PRECISION) of the last call, a CUDA int32 tensor
+        self.last_predict_status = status
         return (mu, var, jac) if jacobians else (mu, var)
 
     def predict(self, states, actions=None, jacobians=False, full_cov=False, quantiles=None,
@@ -410,12 +430,10 @@ class BatchedGPSSM(object):
         """(N, n_s_out) = K^-1 y per output dimension (posterior.woodbury_vector)."""
         if not self.gp_trained:
             return None
-        ptr, nbytes = self.factor_buffers()[1]
-        n_pad = nbytes // 8 // self.n_s_out
-        host = np.empty((self.n_s_out, n_pad))
+        host = np.empty((self.n_s_out, self.z.shape[0]))
         self._torch.cuda.synchronize(self.device)
-        _cudart_memcpy_d2h(self._torch, host, ptr, nbytes, self.device)
-        return np.ascontiguousarray(host[:, :self.z.shape[0]].T)
+        _lib.check(self._lib.segp_beta(self._handle, _lib.dbl_ptr(host)))
+        return np.ascontiguousarray(host.T)
 
     def log_det_k(self):
         """log det (K_d + noise_d I) per output dimension, from the Cholesky factor."""
@@ -515,6 +533,27 @@ class BatchedGPSSM(object):
         v = ctypes.c_long()
         _lib.check(self._lib.segp_get_option(self._handle, name.encode(), ctypes.byref(v)))
         return v.value
+
+    def set_param(self, name, value):
+        """Real-valued parameters of the precision guard (include/segp.h: "guard_rtol", "guard_kappa")."""
+        _lib.check(self._lib.segp_set_param(self._handle, name.encode(), float(value)))
+
+    def get_param(self, name):
+        v = ctypes.c_double()
+        _lib.check(self._lib.segp_get_param(self._handle, name.encode(), ctypes.byref(v)))
+        return v.value
+
+    def precision_report(self):
+        """What the factorize-time probe measured and decided: digit set of the first
+        contraction pass, whether automatic mode runs float64, and the probe statistics."""
+        names = ("probe_ran", "probe_frac4", "probe_frac5", "probe_err4", "probe_err5", "probe_rel4", "probe_rel5",
+                 "probe_ratio4", "probe_ratio5", "probe_rho4", "probe_rho5", "probe_min_var_ratio", "guard_rtol",
+                 "guard_kappa")
+        out = {n: self.get_param(n) for n in names}
+        out["tri_mode_effective"] = self.get_option("tri_mode_effective")
+        out["i8_digits_effective"] = self.get_option("i8_digits_effective")
+        out["fallback_panels"] = self.get_option("fallback_panels")
+        return out
 
 
 def _cudart_memcpy_d2h(torch, host, dev_ptr, nbytes, device):

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_ctypes_table_matches_header(lib):
     from safe_exploration_b200 import _lib
     assert sorted(_lib.PROTOTYPES) == _declared_functions()
-    assert lib.segp_abi_version() == 1
+    assert lib.segp_abi_version() == 2
 
 
 def test_no_cpp_or_torch_types_cross_the_boundary():

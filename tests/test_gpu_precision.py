@@ -1,0 +1,281 @@
+"""GPU tests of the precision management of the int8 tensor-core path, through the C ABI:
+
+* the factorize-time probe: what it measures, which digit set it picks, that the float64 operand is dropped when
+  automatic mode does not need it and comes back when asked for;
+* the a-posteriori guard: a noise sweep from the benchmark's 1e-2 down to the reference's bare noise_diag
+  (ssm_gpy/gaussian_process.py:188, 252-253: 1e-5, + GPy's 1e-8 jitter) at N = 2000 and N = 5000 -- automatic mode
+  must stay within rtol 1e-4 of float64 or say so in the status word;
+* the recomputation of flagged panels on the 15-product set (bit-identical to running that set directly);
+* BASELINE configs C4 (N = 5000, H = 20) and C5 (N = 10000, H = 30) at FULL model size and horizon against the
+  float64 CPU oracle on 256 rollouts;
+* the CUDA-graph replay of a rollout, a lifting GP-input transform (n_in > n_s), a failed append.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+EPS = np.finfo(np.float64).eps
+
+
+@pytest.fixture(scope="module")
+def se():
+    import safe_exploration_b200 as pkg
+    pkg._lib.load()
+    return pkg
+
+
+def _data(n, n_s, n_u, seed):
+    rng = np.random.default_rng(seed)
+    dim = n_s + n_u
+    x = rng.uniform(-1.0, 1.0, size=(n, dim))
+    y = np.sin(x @ rng.standard_normal((dim, n_s))) + 0.1 * rng.standard_normal((n, n_s))
+    ls = rng.uniform(0.8, 2.0, size=(n_s, dim))
+    var = rng.uniform(0.5, 1.5, size=n_s)
+    return rng, x, y, ls, var
+
+
+def test_probe_picks_the_10_product_set_on_a_benchmark_sized_model(se):
+    """BASELINE C3's model (cart-pole, Matern-5/2, N = 2000): sigma^2 / k** ~ 2e-3, the 10-product set resolves it to
+    ~3e-6 and the probe selects it; the float64 operand is dropped and comes back on request."""
+    from oracle.gp_oracle import GPOracle
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C3", batch=1)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp, tri_mode=-1)
+    rep = gp.precision_report()
+    print(rep)
+    assert rep["probe_ran"] == 1.0
+    assert rep["tri_mode_effective"] == 4 and rep["i8_digits_effective"] == 4
+    assert rep["probe_frac4"] == 0.0 and rep["probe_frac5"] == 0.0
+    assert rep["probe_rel4"] < 2e-5 and rep["probe_rel5"] < 1e-6
+    assert rep["probe_err5"] < rep["probe_err4"]
+    assert 0.5 < rep["probe_ratio4"] < 6.0 and 0.5 < rep["probe_ratio5"] < 6.0      # the error model holds: the max over
+    assert rep["probe_rho4"] == 1.0 and rep["probe_rho5"] == 1.0                      # 4 x 1024 probes is 3-4 sigma
+    assert gp.get_option("fp64_operand_resident") == 0        # not needed: dropped (420 MB at C4, 4.1 GB at C5)
+    rng = np.random.default_rng(0)
+    z = rng.uniform(-0.7, 0.7, size=(700, 5))
+    mu, v4 = gp.predict(z)
+    st = gp.last_predict_status.cpu().numpy()
+    assert np.all(st == 0)
+    ora = GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
+                   [h["variance"] for h in w.hyp], gp.total_noise())
+    _, var_o, _ = ora.predict_batch(z)
+    assert float(np.max(np.abs(v4 - var_o) / var_o)) < 2e-5
+    # asking for float64 afterwards brings the operand back (one more factorisation) and agrees to float64 accuracy
+    gp.set_option("tri_mode", 0)
+    _, v0 = gp.predict(z)
+    assert gp.get_option("fp64_operand_resident") == 1
+    assert float(np.max(np.abs(v0 - var_o) / var_o)) < 1e-6
+    gp.close()
+
+
+def test_probe_keeps_the_15_product_set_where_the_variance_is_too_small(se):
+    """3-D inputs, N = 2000: the data are dense, sigma^2 / k** drops to 5e-5 and the 10-product set's error estimate
+    exceeds rtol x sigma^2 on half of the probes: the model must start on the 15-product set."""
+    rng, x, y, ls, var = _data(2000, 2, 1, 3)
+    hyp = [{"lengthscale": ls[d], "variance": float(var[d]), "noise": 1e-2} for d in range(2)]
+    gp = se.BatchedGPSSM(2, 2, 1, x, y, kern_types=["rbf", "mat52"], hyp=hyp, tri_mode=-1)
+    rep = gp.precision_report()
+    print(rep)
+    assert rep["probe_frac4"] > 0.1 and rep["probe_frac5"] == 0.0
+    assert rep["tri_mode_effective"] == 4 and rep["i8_digits_effective"] == 5
+    assert rep["probe_rel5"] < 2e-6
+    gp.close()
+
+
+@pytest.mark.parametrize("n", [2000, 5000])
+@pytest.mark.parametrize("noise", [1e-2, 1e-3, 1e-4, 0.0])
+def test_guard_noise_sweep(se, n, noise):
+    """hyp noise 0 leaves the reference's noise_diag 1e-5 + jitter 1e-8 on the diagonal: cond(K) ~ 1e8."""
+    from oracle.gp_oracle import GPOracle
+    rng, x, y, ls, var = _data(n, 2, 1, 11 + n)
+    kerns = ["rbf", "mat52"]
+    hyp = [{"lengthscale": ls[d], "variance": float(var[d]), "noise": noise} for d in range(2)]
+    z = np.vstack((rng.uniform(-0.7, 0.7, size=(600, 3)), 0.05 * rng.standard_normal((360, 3)), x[:192] + 1e-3))
+    gp = se.BatchedGPSSM(2, 2, 1, x, y, kern_types=kerns, hyp=hyp, tri_mode=-1)
+    rep = gp.precision_report()
+    mu, v = gp.predict(z)
+    st = gp.last_predict_status.cpu().numpy()
+    fb = gp.get_option("fallback_panels")
+    gp.close()
+    gp0 = se.BatchedGPSSM(2, 2, 1, x, y, kern_types=kerns, hyp=hyp, tri_mode=0)
+    mu0, v0 = gp0.predict(z)
+    total_noise = gp0.total_noise()
+    gp0.close()
+    flagged = (st & (se._lib.STATUS_LOW_PRECISION | se._lib.STATUS_BAD_VARIANCE)) != 0
+    rel64 = np.max(np.abs(v - v0) / np.abs(v0), axis=1)
+    print("N=%d noise %.0e: mode %d digits %d; probe frac4 %.3f frac5 %.3f rel4 %.1e rel5 %.1e; flagged %d/%d, "
+          "recomputed panels %d; max rel dev from the float64 pipe (unflagged) %.2e; min var/k** %.1e" % (
+              n, noise, rep["tri_mode_effective"], rep["i8_digits_effective"], rep["probe_frac4"], rep["probe_frac5"],
+              rep["probe_rel4"], rep["probe_rel5"], int(flagged.sum()), flagged.size, fb,
+              float(rel64[~flagged].max()) if (~flagged).any() else 0.0, float(np.min(v0 / var[None, :]))))
+    # (a) against the float64 pipe on the same factor: within the tolerance, or flagged
+    assert np.all((rel64 <= RTOL) | flagged)
+    assert np.allclose(mu, mu0, rtol=1e-9, atol=1e-12)
+    # (b) against the CPU oracle wherever a float64 computation can resolve the variance at all: both sides factorise
+    # a matrix of condition ~ N s_f^2 / noise in float64, which leaves ~ eps * cond * k** of noise on |L^-1 k*|^2
+    ora = GPOracle(x, y, kerns, ls, var, total_noise)
+    _, var_o, _ = ora.predict_batch(z)
+    cond = n * var / total_noise
+    resolvable = np.all(var_o > 1e5 * EPS * cond[None, :] * var[None, :], axis=1)
+    relo = np.max(np.abs(v - var_o) / np.abs(var_o), axis=1)
+    assert np.all((relo <= RTOL) | flagged | ~resolvable)
+    if noise >= 1e-3:
+        assert resolvable.all() and not flagged.any()      # the benchmark regime needs no flag at all
+        assert rep["tri_mode_effective"] == 4
+
+
+def test_flagged_panels_are_recomputed_on_the_15_product_set(se):
+    from safe_exploration_b200 import workloads
+    rng, x, y, ls, var = _data(1500, 2, 1, 5)
+    hyp = [{"lengthscale": ls[d], "variance": float(var[d]), "noise": 1e-2} for d in range(2)]
+    kw = dict(kern_types=["rbf", "rbf"], hyp=hyp, tri_mode=4)
+    # 4 panels near the data (small variance), 3 far outside (variance ~ k**: never flagged)
+    z = np.vstack((rng.uniform(-0.5, 0.5, size=(4 * 96, 3)), rng.uniform(2.5, 3.0, size=(3 * 96 - 7, 3))))
+    gp5 = se.BatchedGPSSM(2, 2, 1, x, y, i8_digits=5, **kw)
+    _, v5 = gp5.predict(z)
+    gp4 = se.BatchedGPSSM(2, 2, 1, x, y, i8_digits=4, **kw)
+    gp4.set_option("guard", 0)
+    _, v4 = gp4.predict(z)
+    gp4.set_option("guard", 1)
+    assert not np.array_equal(v4, v5)
+    err = np.abs(v4 - v5) / v5
+    print("10- vs 15-product set: max rel diff %.2e near the data, %.2e far away" % (err[:384].max(), err[384:].max()))
+    # default tolerance: nothing to recompute
+    n0 = gp4.get_option("fallback_panels")
+    _, v = gp4.predict(z)
+    assert np.array_equal(v, v4) and gp4.get_option("fallback_panels") == n0
+    assert np.all(gp4.last_predict_status.cpu().numpy() == 0)
+    # a tolerance the 10-product set cannot meet near the data but meets far away: exactly those panels are recomputed
+    gp4.set_param("guard_rtol", 2e-6)
+    _, v = gp4.predict(z)
+    assert gp4.get_option("fallback_panels") - n0 == 4
+    assert np.array_equal(v[:384], v5[:384]) and np.array_equal(v[384:], v4[384:])
+    # a tolerance nothing meets: every panel is recomputed, and the status word says the result is still short of it
+    gp4.set_param("guard_rtol", 1e-12)
+    _, v = gp4.predict(z)
+    assert np.array_equal(v, v5)
+    st = gp4.last_predict_status.cpu().numpy()
+    assert np.all(st[:384] & se._lib.STATUS_LOW_PRECISION)
+    # the same through a rollout (status bits are OR-ed over the steps)
+    w = workloads.make("C2", batch=300, horizon=4)
+    args = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    r = se.rollout(gp4, w.p0, w.k_ff, w.k_fb, *args)
+    r5 = se.rollout(gp5, w.p0, w.k_ff, w.k_fb, *args)
+    assert np.array_equal(r.var_all, r5.var_all) and np.array_equal(r.q_all, r5.q_all)
+    assert np.all(r.status & se._lib.STATUS_LOW_PRECISION) and np.all(r5.status == 0)
+    gp4.close()
+    gp5.close()
+
+
+@pytest.mark.parametrize("name,batch", [("C4", 256), ("C5", 256)])
+def test_full_size_full_horizon_parity(se, name, batch):
+    """C4: N = 5000, H = 20, n_s = 4; C5: N = 10000, H = 30, n_s = 10 -- the sizes BASELINE.json quotes, every step of
+    256 rollouts against the float64 batch oracle, automatic mode (the probe's digit set + guard)."""
+    from oracle import reach_oracle
+    from oracle.gp_oracle import GPOracle
+    from safe_exploration_b200 import workloads
+    w = workloads.make(name, batch=batch)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp, tri_mode=-1)
+    rep = gp.precision_report()
+    res = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+    ora = GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
+                   [h["variance"] for h in w.hyp], gp.total_noise())
+    p_o, q_o, v_o = reach_oracle.multistep_batch(w.p0, ora, w.k_fb, w.k_ff, w.l_mu, w.l_sigma, None, w.c_safety, w.a, w.b)
+    ev = float(np.max(np.abs(res.var_all - v_o) / np.abs(v_o)))
+    ep = float(np.max(np.abs(res.p_all - p_o) / (np.abs(p_o) + 1e-5 * np.abs(p_o).max())))
+    eq = float(np.max(np.abs(res.q_all - q_o) / (np.abs(q_o) + 1e-5 * np.abs(q_o).max())))
+    print("%s full size: digits %d, probe rel4 %.1e; max rel err var %.2e  p %.2e  Q %.2e; min var/k** %.1e" % (
+        name, rep["i8_digits_effective"], rep["probe_rel4"], ev, ep, eq,
+        float(np.min(v_o / np.array([h["variance"] for h in w.hyp])[None, None, :]))))
+    assert np.all(res.status == 0) and np.all(np.isfinite(q_o))
+    assert rep["i8_digits_effective"] == 4
+    assert ev < RTOL and ep < RTOL and eq < RTOL
+    gp.close()
+
+
+def test_cuda_graph_replay_is_bit_identical(se):
+    import torch
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C2", batch=1000)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp, tri_mode=-1)
+    dev = gp.device
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    p0, kff, kfb = t(w.p0), t(w.k_ff), t(w.k_fb)
+    args = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
+
+    def buffers():
+        return se.RolloutResult(torch.empty((1000, w.horizon, 2), dtype=torch.float64, device=dev),
+                                torch.empty((1000, w.horizon, 2, 2), dtype=torch.float64, device=dev),
+                                torch.empty((1000, w.horizon, 2), dtype=torch.float64, device=dev),
+                                torch.empty((1000,), dtype=torch.int32, device=dev))
+    out = buffers()
+    gp.set_option("graph", 0)
+    ref = se.rollout(gp, p0, kff, kfb, *args, out=buffers())
+    ref = [x.clone() for x in ref]
+    gp.set_option("graph", 1)
+    n0 = gp.get_option("launches")
+    per_call = None
+    for i in range(4):
+        for x in out:
+            x.zero_()
+        r = se.rollout(gp, p0, kff, kfb, *args, out=out)
+        torch.cuda.synchronize()
+        n1 = gp.get_option("launches")
+        per_call = per_call or (n1 - n0)
+        assert n1 - n0 == per_call          # the launch counter counts the kernels inside a replayed graph too
+        n0 = n1
+        assert gp.get_option("graphs_cached") == (1 if i >= 1 else 0)     # first sight direct, second captured
+        for a, b in zip(r, ref):
+            assert torch.equal(a, b)
+    assert per_call == 3 * w.horizon
+    gp.close()
+
+
+def test_lifting_input_transform(se):
+    """t_z_gp with more GP inputs than states (n_in = 3 > n_s = 2): the specialised ellipsoid kernels hold a Jacobian
+    row of n_s + n_u entries, so this shape has to take the generic instance (round-1 advisor finding)."""
+    from oracle import reach_oracle
+    from oracle.gp_oracle import GPOracle
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C2", batch=130, n_train=200, horizon=5)
+    t = np.array([[1.0, 0.0], [0.0, 1.0], [0.6, -0.4]])
+    x = np.hstack((w.x_train[:, :2] @ t.T, w.x_train[:, 2:]))
+    rng = np.random.default_rng(2)
+    ls = rng.uniform(0.8, 1.6, size=(2, 4))
+    hyp = [{"lengthscale": ls[d], "variance": 1.0, "noise": 1e-2} for d in range(2)]
+    for mode in (0, 4):
+        gp = se.BatchedGPSSM(2, 3, 1, x, w.y_train, kern_types=["rbf", "mat52"], hyp=hyp, tri_mode=mode)
+        ora = GPOracle(x, w.y_train, ["rbf", "mat52"], ls, [1.0, 1.0], gp.total_noise())
+        q0 = np.diag([1e-4, 2e-4])
+        res = se.rollout(gp, w.p0, w.k_ff, w.k_fb, w.l_mu, w.l_sigma, q0, w.k_fb[0], w.c_safety, w.a, w.b, t)
+        p_o, q_o, v_o = reach_oracle.multistep_batch(w.p0, ora, w.k_fb, w.k_ff, w.l_mu, w.l_sigma, q0, w.c_safety, w.a,
+                                                     w.b, w.k_fb[0], t)
+        assert np.all(res.status == 0)
+        assert np.allclose(res.var_all, v_o, rtol=1e-6, atol=0) and np.allclose(res.p_all, p_o, rtol=1e-7, atol=1e-12)
+        assert np.allclose(res.q_all, q_o, rtol=1e-6, atol=1e-6 * np.abs(q_o).max() * 1e-3)
+        gp.close()
+
+
+def test_failed_append_restores_the_previous_model(se):
+    rng, x, y, ls, var = _data(300, 2, 1, 8)
+    hyp = [{"lengthscale": ls[d], "variance": float(var[d]), "noise": 1e-2} for d in range(2)]
+    gp = se.BatchedGPSSM(2, 2, 1, x[:200], y[:200], kern_types=["rbf", "rbf"], hyp=hyp)
+    gp.update_model(x[200:210], y[200:210], replace_old=False)       # switches dense-W keeping on
+    z = rng.uniform(-1, 1, (50, 3))
+    before = gp.predict(z, compute_gradients=True)
+    bad_x = x[210:212].copy()
+    bad_x[1, 0] = np.nan
+    with pytest.raises((np.linalg.LinAlgError, RuntimeError, ValueError)):
+        gp.update_model(bad_x, y[210:212], replace_old=False)
+    assert gp.gp_trained and gp.get_option("n_train") == 210 and gp.x_train.shape[0] == 210
+    after = gp.predict(z, compute_gradients=True)
+    for a, b in zip(before, after):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-12)
+    gp.update_model(x[210:230], y[210:230], replace_old=False)       # and the handle still takes valid appends
+    ref = se.BatchedGPSSM(2, 2, 1, x[:230], y[:230], kern_types=["rbf", "rbf"], hyp=hyp)
+    for a, b in zip(gp.predict(z), ref.predict(z)):
+        assert np.allclose(a, b, rtol=1e-7, atol=1e-10)
+    gp.close()
+    ref.close()
