@@ -144,14 +144,19 @@ def parity_against_oracle(res, oracle_out):
     p_o, q_o, v_o = oracle_out
     n = p_o.shape[0]
 
-    def err(got, want):
+    def err(got, want, atol_scale):
         got = got[:n].cpu().numpy()
-        scale = 1e-9 * max(1.0, float(np.max(np.abs(want))))
+        scale = atol_scale * max(1.0, float(np.max(np.abs(want))))
         return float(np.max(np.abs(got - want) / (np.abs(want) + scale / 1e-4)))
 
-    e = {"p_all": err(res.p_all, p_o), "q_all": err(res.q_all, q_o), "var_all": err(res.var_all, v_o)}
+    pairs = (("p_all", res.p_all, p_o), ("q_all", res.q_all, q_o), ("var_all", res.var_all, v_o))
+    # strict: absolute floor 1e-9 x scale (round 1's figure: entries down to 1e-5 of the largest count fully);
+    # gate: SURVEY.md section 8d, np.allclose(rtol = 1e-4, atol = 1e-6 x scale)
+    e = {k: err(g, o, 1e-9) for k, g, o in pairs}
+    e_gate = {k: err(g, o, 1e-6) for k, g, o in pairs}
     return {"checked_rollouts": int(n), "against": "float64 oracle (oracle/reach_oracle.multistep_batch) at full model size",
-            "max_rel_err": e, "rtol_gate": 1e-4, "ok": bool(max(e.values()) < 1e-4)}
+            "max_rel_err": e, "max_rel_err_gate_atol_1e-6_scale": e_gate, "rtol_gate": 1e-4,
+            "ok": bool(max(e_gate.values()) < 1e-4), "ok_strict": bool(max(e.values()) < 1e-4)}
 
 
 def _set_blas_threads(n):
@@ -307,6 +312,8 @@ def run_product(args, rank, world, local_rank):
                              torch.empty((bsz_d,), dtype=torch.int32, device=dev))
     if args.no_graph:
         gp.set_option("graph", 0)
+    if args.guard_kappa > 0:
+        gp.set_param("guard_kappa", args.guard_kappa)
 
     def step_device():
         # the result buffers are re-used, as a sampling-MPC loop would: from the second call on the library replays the
@@ -534,6 +541,7 @@ def main():
                     help="digit set of the int8 contraction: 0 automatic (factorize-time probe), 4 = 10 products, "
                          "5 = 15 products")
     ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA-graph replay")
+    ap.add_argument("--guard-kappa", type=float, default=0.0, help="override the precision guard's kappa (0 = library default)")
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -256,6 +256,10 @@ typedef struct segp_score_params {
     const double* h_wu;        /* [n_u x n_u]                                                                      */
     const double* h_x_ref;     /* [n_s] or NULL (origin)                                                           */
     int layout;                /* SEGP_SCORE_SAFEMPC (0, everything above) or SEGP_SCORE_CAUTIOUS                  */
+    const double* h_q0;        /* [n_s x n_s] initial shape matrix shared by all candidates, or NULL: with it (the
+                                  solver's init_uncertainty mode, safempc_simple.py:181-199, 350) the bound on u_0
+                                  carries the support term of K_fb_0 Q_0 K_fb_0^T like every later control          */
+    const double* h_k_fb_0;    /* [n_u x n_s] feedback gain of step 0; required with h_q0                           */
 } segp_score_params;
 
 /* constraint layouts */
@@ -324,8 +328,9 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
  * "i8_digits": digit set of the first contraction pass: 0 = automatic (the probe's choice, read-only
  *   "i8_digits_effective"), 5 = classic set, 15 int8 products, 4 = diagonal-split set, 10 products;
  * "guard": 1 (default) = a-posteriori precision guard: on the 10-product set, panels whose error estimate exceeds
- *   guard_rtol x sigma^2 are recomputed on the 15-product set (read-only "fallback_panels" counts them); whatever still
- *   exceeds it gets SEGP_STATUS_LOW_PRECISION;  "probe": 1 (default) = calibrate the error model at segp_factorize;
+ *   guard_rtol x sigma^2 are recomputed on the 15-product set (read-only "fallback_panels" counts them; when more than
+ *   a third of a rollout call's panel contractions were recomputed, automatic mode starts on the 15-product set from the
+ *   next call on: read-only "demoted"); whatever still exceeds it gets SEGP_STATUS_LOW_PRECISION;  "probe": 1 (default) = calibrate the error model at segp_factorize;
  * "keep_fp64": keep the float64 operand resident after segp_factorize (else it is dropped unless needed, and a later
  *   tri_mode 0 factorises again); read-only "fp64_operand_resident", "fp64_operand_needed", "factor_bytes";
  * "graph": 1 (default) = replay the launches of a segp_multistep call as a CUDA graph from the second call with the
@@ -338,7 +343,8 @@ int segp_set_option(segp_model* m, const char* name, long value);
 int segp_get_option(segp_model* m, const char* name, long* value);
 
 /* Real-valued parameters: "guard_rtol" (1e-4: the tolerance the precision guard protects; BASELINE.json's rtol),
- * "guard_kappa" (6: standard deviations of the error model that must fit inside it); read-only statistics of the
+ * "guard_kappa" (5: standard deviations of the error model that must fit inside it -- an unflagged variance misses the
+ * tolerance with probability < 6e-7 per evaluation, and far less away from the threshold); read-only statistics of the
  * factorize-time probe (1024 uniform inputs over the training box against the float64 contraction, worst output
  * dimension): "probe_ran", "probe_frac4" / "probe_frac5" (fraction the guard flags on the 10- / 15-product set),
  * "probe_err4/5" (max abs error of |L^-1 k*|^2), "probe_rel4/5" (max error / sigma^2), "probe_ratio4/5" (max error in

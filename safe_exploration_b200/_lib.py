@@ -50,7 +50,8 @@ class ScoreParams(ctypes.Structure):
     _fields_ = [("h_u_min", _c_double_p), ("h_u_max", _c_double_p), ("m_obs", _int), ("h_mat_obs", _c_double_p),
                 ("h_obs", _c_double_p), ("m_safe", _int), ("h_mat_safe", _c_double_p), ("h_safe", _c_double_p),
                 ("c_safety", _dbl), ("eps_constraints", _dbl), ("cost_type", _int), ("eps_noise", _dbl),
-                ("h_wx", _c_double_p), ("h_wu", _c_double_p), ("h_x_ref", _c_double_p), ("layout", _int)]
+                ("h_wx", _c_double_p), ("h_wu", _c_double_p), ("h_x_ref", _c_double_p), ("layout", _int),
+                ("h_q0", _c_double_p), ("h_k_fb_0", _c_double_p)]
 
 
 COST_EXPLORATION = 0

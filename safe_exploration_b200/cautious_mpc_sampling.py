@@ -174,7 +174,8 @@ class SamplingCautiousMPC(object):
         for _ in range(max(self.n_iter, 1)):
             cand = mean[None] + std[None] * self._rng.standard_normal((self.n_samples, self.T, self.n_u))
             cand[0] = mean
-            cand[:, 0] = np.clip(cand[:, 0], lo, hi)      # u_0 is applied at a point: plain bounds (:363-367)
+            if self.has_ctrl_bounds:                      # u_0 is applied at a point: plain bounds (:363-367); without
+                cand[:, 0] = np.clip(cand[:, 0], lo, hi)  # control bounds the reference leaves it free: no clipping
             res = self._propagate(mu_0, cand, k_fb_0)
             sc = self._score(res, cand, k_fb_0)
             if self.cost_func is not None:

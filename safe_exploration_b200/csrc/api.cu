@@ -124,10 +124,14 @@ struct segp_model {
     long opt_guard = 1;        // run the a-posteriori precision guard (flag + 15-product recomputation of flagged panels)
     long opt_probe = 1;        // calibrate the error model at factorize time (PROBE_N random inputs against float64)
     long opt_keep_fp64 = 0;    // keep the float64 operand after factorising even when automatic mode does not need it
-    double guard_rtol = 1e-4, guard_kappa = 6.0;
+    double guard_rtol = 1e-4, guard_kappa = 5.0;
     double probe_stat[PROBE_STATS] = {0};
     int force_mode = -2, force_digits = 0;   // probe only: overrides of the kernel selection
     unsigned int* fallback_counter = nullptr;   // device: panels recomputed on the 15-product set so far
+    unsigned int* h_fallback = nullptr;         // pinned host mirror, refreshed (asynchronously) after every rollout call
+    unsigned int fallback_seen = 0;             // value of the mirror when the previous call was issued
+    long panels_prev_call = 0;                  // panel contractions the previous guarded call issued
+    bool demoted = false;                       // automatic mode fell back to the 15-product first pass at run time
     // workspace
     long b_cap = 0;
     int nsplit = 1, blocks_per_split = 1;
@@ -249,7 +253,7 @@ static int tri_digits(const segp_model* m) {
     if (m->force_digits != 0) return m->force_digits;
     if (tri_mode(m) == 1) return 5;
     if (m->opt_i8_digits != 0) return (int)m->opt_i8_digits;
-    return m->i8_primary;
+    return m->demoted ? 5 : m->i8_primary;
 }
 static double guard_gs(const segp_model* m) {
     const double r = 2.0 * m->guard_kappa / m->guard_rtol;
@@ -571,12 +575,15 @@ int segp_create(segp_model** out, int device, int n_s_out, int n_s_in, int n_u, 
         if (kern_is_composite(kern_type[d])) m->has_composite = true;
     }
     if (dev_alloc(&m->d_sp, 1) != SEGP_OK || dev_alloc(&m->fallback_counter, 1) != SEGP_OK ||
-        cudaMemset(m->fallback_counter, 0, sizeof(unsigned int)) != cudaSuccess) {
+        cudaMemset(m->fallback_counter, 0, sizeof(unsigned int)) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&m->h_fallback), sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess) {
         dev_free(m->d_sp);
         dev_free(m->fallback_counter);
         delete m;
+        set_error("segp_create: allocation failed");
         return SEGP_ERR_CUDA;
     }
+    *m->h_fallback = 0;
     *out = m;
     return SEGP_OK;
 }
@@ -590,6 +597,7 @@ int segp_destroy(segp_model* m) {
     dev_free(m->d_sp);
     dev_free(m->i8_prof);
     dev_free(m->fallback_counter);
+    if (m->h_fallback != nullptr) cudaFreeHost(m->h_fallback);
     if (m->s_host != nullptr) cudaStreamDestroy(m->s_host);
     if (m->s_cap != nullptr) cudaStreamDestroy(m->s_cap);
     if (m->s_copy != nullptr) cudaStreamDestroy(m->s_copy);
@@ -876,9 +884,9 @@ static int apply_calibration(segp_model* m, cudaStream_t st) {
 // uniformly from the bounding box of the training inputs run through the float64 contraction (reference), the
 // 15-product and the 10-product kernels.  Per output dimension the measured error of |v|^2 is compared with the
 // model's a-posteriori estimate 2 sqrt(sum_i w_i v_i^2): if any probe exceeds 4.5 predicted standard deviations the
-// weights of that digit set are inflated (rho); the digit set of the first pass is the 10-product one only when the
-// guard flags none of the probes on it (and the model is large enough for the extra launches to pay); when the guard
-// would flag more than a quarter of the probes even on the 15-product set, automatic mode runs float64.
+// weights of that digit set are inflated (rho); the digit set of the first pass is the 10-product one when the guard
+// flags at most a quarter of the probes on it (and the model is large enough for the extra launches to pay); when the
+// guard would flag more than a quarter of the probes even on the 15-product set, automatic mode runs float64.
 static int probe_pass(segp_model* m, const double* d_z, long np, int mode, int digits, cudaStream_t st,
                       std::vector<double>& q, std::vector<double>& e) {
     m->force_mode = mode;
@@ -1000,8 +1008,13 @@ static int run_probe(segp_model* m, cudaStream_t st) {
     }
     ps[PS_FRAC4] = (double)n4 / (double)np;
     ps[PS_FRAC5] = (double)n5 / (double)np;
-    m->i8_primary = (n4 == 0 && m->n_pad >= 1024) ? 4 : 5;
+    // 10-product first pass + recomputation of a flagged fraction g of the panels costs (10 + 15 g) / 15 of the
+    // 15-product kernel: it pays while g < 1/3.  The probes are spread over the whole training box, a rollout batch
+    // sits in one place, so the probe fraction only says whether typical inputs pass; the run-time demotion in
+    // segp_multistep (fallback_rate) catches a batch that lives where they do not.
+    m->i8_primary = (ps[PS_FRAC4] <= 0.25 && m->n_pad >= 1024) ? 4 : 5;
     m->auto_fp64 = ps[PS_FRAC5] > 0.25;
+    m->demoted = false;
     SEGP_CHECK(apply_calibration(m, st));
     SEGP_CUDA_CHECK(cudaStreamSynchronize(st));
     return SEGP_OK;
@@ -1399,6 +1412,16 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
     SEGP_CHECK(fill_step_params(&sp, params, m->n_s, m->n_in, m->n_u));
     DeviceGuard guard(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Run-time demotion of automatic mode: the previous guarded call mirrored the recomputation counter to the host
+    // (asynchronously; it has landed by the time a caller that consumed that call's results is back here).  When more
+    // than a third of its panel contractions were redone on the 15-product set, the 10-product first pass costs more
+    // than it saves for this batch: start on the 15-product set from now on (until the next factorisation).
+    if (m->panels_prev_call > 0 && !m->demoted && m->opt_i8_digits == 0) {
+        const unsigned int now = *reinterpret_cast<volatile unsigned int*>(m->h_fallback);
+        if ((double)(now - m->fallback_seen) > (double)m->panels_prev_call / 3.0) m->demoted = true;
+        m->fallback_seen = now;
+    }
+    m->panels_prev_call = 0;
     SEGP_CHECK(ensure_fp64_operand(m, stream));
     SEGP_CHECK(ensure_workspace(m, n_batch));
     // pageable source: staged by the runtime before the call returns, and outside any captured graph
@@ -1467,6 +1490,7 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
     const int npanels_first = (int)((std::min<long>(m->b_cap, n_batch) + I8_N - 1) / I8_N);
     const bool pipelined_any = m->ws_mode != 0 && tri_mode(m) >= 4 && m->opt_overlap != 0 && npanels_first >= 48 &&
                                m->n_pad >= 1024;
+    const bool guarded = m->ws_mode != 0 && tri_mode(m) >= 4 && tri_digits(m) == 4 && m->opt_guard != 0;
     // The serial schedule: per chunk and step kstar -> contraction (+ guard + recomputation) -> ellipsoid step, every
     // launch asynchronous on one stream.
     auto issue_serial = [&](cudaStream_t s1) -> int {
@@ -1480,8 +1504,12 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
                 m->launches += 3;
             }
         }
+        if (guarded)
+            SEGP_CUDA_CHECK(cudaMemcpyAsync(m->h_fallback, m->fallback_counter, sizeof(unsigned int),
+                                            cudaMemcpyDeviceToHost, s1));
         return SEGP_OK;
     };
+    if (guarded) m->panels_prev_call = (long)horizon * ((n_batch + I8_N - 1) / I8_N);
     if (!pipelined_any) {
         // K5: the 3 H launches of a call are replayed as ONE CUDA graph from the second call with the same
         // arguments on (a sampling-MPC loop re-uses its buffers); sizes where a launch costs as much as a kernel
@@ -1955,6 +1983,15 @@ static int fill_score_params(ScoreParams* sp, const segp_score_params* prm, int 
     }
     sp->layout = prm->layout;
     if (sp->layout == SEGP_SCORE_CAUTIOUS) sp->m_safe = 0;
+    if ((prm->h_q0 == nullptr) != (prm->h_k_fb_0 == nullptr)) {
+        set_error("score params: h_q0 and h_k_fb_0 go together");
+        return SEGP_ERR_INVALID;
+    }
+    sp->has_q0 = prm->h_q0 != nullptr;
+    if (sp->has_q0) {
+        for (int i = 0; i < n_s * n_s; ++i) sp->q0[i] = prm->h_q0[i];
+        for (int i = 0; i < n_u * n_s; ++i) sp->kfb0[i] = prm->h_k_fb_0[i];
+    }
     if (prm->cost_type == SEGP_COST_QUADRATIC) {
         if (prm->h_wx == nullptr || prm->h_wu == nullptr) {
             set_error("score params: the quadratic cost needs h_wx and h_wu");
@@ -2316,6 +2353,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
         for (GraphEntry* e = m->graphs; e != nullptr; e = e->next) n += e->exec != nullptr;
         *value = n;
     }
+    else if (strcmp(name, "demoted") == 0) *value = m->demoted ? 1 : 0;
     else if (strcmp(name, "fp64_operand_resident") == 0) *value = m->wt != nullptr ? 1 : 0;
     else if (strcmp(name, "fp64_operand_needed") == 0) *value = fp64_operand_needed(m) ? 1 : 0;
     else if (strcmp(name, "factor_bytes") == 0) *value = (long)m->arena_bytes;

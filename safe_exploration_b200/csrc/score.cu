@@ -1,6 +1,7 @@
 // Scoring of B rolled-out candidates: the constraint and cost assembly of the reference's SafeMPC, per candidate.
 //   control constraints   SimpleSafeMPC._generate_control_constraint (safempc_simple.py:488-532):
-//                         step 0: u_min <= u_0 <= u_max (the start is a point, no feedback term);
+//                         step 0: u_min <= u_0 <= u_max (the start is a point, no feedback term; with an initial
+//                         ellipsoid Q_0, K_fb_0 -- init_uncertainty -- the same support term as the later steps);
 //                         step i+1: lin_ellipsoid_safety_distance(k_ff[i+1], K_fb[i] Q[i] K_fb[i]^T, [I;-I], [u_max;-u_min])
 //   state constraints     generate_safety_constraints (:317-392): obstacle polytope on ellipsoids 0..H-2,
 //                         terminal safe-set polytope on ellipsoid H-1, both through
@@ -40,8 +41,21 @@ __global__ void score_kernel(const ScoreArgs a) {
     const double c_ctrl = cautious ? sp.c_safety : 1.0;
     // ---- control constraints
     if (sp.has_ctrl) {
-        for (int j = 0; j < n_u; ++j) emit(kff[j] - sp.u_max[j]);
-        for (int j = 0; j < n_u; ++j) emit(sp.u_min[j] - kff[j]);
+        // step 0: the start is a point (no feedback term) unless an initial ellipsoid Q_0 with its gain K_fb_0 is given
+        // (init_uncertainty, safempc_simple.py:350: _generate_control_constraint(u_0, q_0, k_fb_0))
+        double sd0[SEGP_MAX_NU];
+        for (int j = 0; j < n_u; ++j) {
+            double acc = 0.0;
+            if (sp.has_q0)
+                for (int r = 0; r < n_s; ++r) {
+                    double t = 0.0;
+                    for (int c = 0; c < n_s; ++c) t = fma(sp.q0[r * n_s + c], sp.kfb0[j * n_s + c], t);
+                    acc = fma(sp.kfb0[j * n_s + r], t, acc);
+                }
+            sd0[j] = c_ctrl * sqrt(acc);
+        }
+        for (int j = 0; j < n_u; ++j) emit(kff[j] + sd0[j] - sp.u_max[j]);
+        for (int j = 0; j < n_u; ++j) emit(sp.u_min[j] - kff[j] + sd0[j]);
         for (int i = 0; i + 1 < hor; ++i) {
             const double* q = q_all + (long)i * n_s * n_s;
             const double* kfb = a.kfb + b * a.kfb_stride + (long)i * n_u * n_s;

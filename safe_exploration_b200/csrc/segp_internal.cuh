@@ -242,7 +242,8 @@ struct ScoreParams {
     double h_mat_safe[SEGP_MAX_CONSTR * SEGP_MAX_NS], h_safe[SEGP_MAX_CONSTR];
     double wx[SEGP_MAX_NS * SEGP_MAX_NS], wu[SEGP_MAX_NU * SEGP_MAX_NU], x_ref[SEGP_MAX_NS];
     double c_safety, eps_constraints, eps_noise;
-    int has_ctrl, m_obs, m_safe, cost_type, layout;
+    double q0[SEGP_MAX_NS * SEGP_MAX_NS], kfb0[SEGP_MAX_NU * SEGP_MAX_NS];   // init_uncertainty: shared Q_0, K_fb_0
+    int has_ctrl, m_obs, m_safe, cost_type, layout, has_q0;
 };
 struct ScoreArgs {
     const double* p_all;      // [B][H][n_s]

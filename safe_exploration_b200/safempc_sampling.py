@@ -32,6 +32,8 @@ __all__ = ["score_rollouts", "best_candidate", "SamplingSafeMPC", "ScoreResult"]
 
 ScoreResult = collections.namedtuple("ScoreResult", ["cost", "feasible", "violation", "g"])
 
+ATTR_NAMES_PERF = ['type_perf_traj', 'n_perf', 'r', 'perf_has_fb']                # safempc_simple.py:18-20
+DEFAULT_OPT_PERF = {'type_perf_traj': 'mean_equivalent', 'n_perf': 5, 'r': 1, 'perf_has_fb': True}
 ATTR_NAMES_ENV = ['l_mu', 'l_sigma', 'h_mat_safe', 'h_safe', 'lin_model', 'ctrl_bounds', 'safe_policy',
                   'h_mat_obs', 'h_obs']                                           # safempc_simple.py:22-23
 DEFAULT_OPT_ENV = {'ctrl_bounds': None, 'safe_policy': None, 'lin_model': None, 'h_mat_obs': None,
@@ -39,7 +41,7 @@ DEFAULT_OPT_ENV = {'ctrl_bounds': None, 'safe_policy': None, 'lin_model': None, 
 
 
 def _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, cost, wx, wu, x_ref,
-                  eps_constraints, eps_noise, c_safety, layout="safempc"):
+                  eps_constraints, eps_noise, c_safety, layout="safempc", q_0=None, k_fb_0=None):
     keep = []
 
     def hp(x, shape):
@@ -66,13 +68,14 @@ def _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, c
         _lib.COST_EXPLORATION if cost == "exploration" else _lib.COST_QUADRATIC, float(eps_noise),
         hp(wx, (n_s, n_s)) if cost == "quadratic" else None, hp(wu, (n_u, n_u)) if cost == "quadratic" else None,
         hp(x_ref, (n_s,)) if (cost == "quadratic" and x_ref is not None) else None,
-        _lib.SCORE_CAUTIOUS if layout == "cautious" else _lib.SCORE_SAFEMPC)
+        _lib.SCORE_CAUTIOUS if layout == "cautious" else _lib.SCORE_SAFEMPC,
+        hp(q_0, (n_s, n_s)) if q_0 is not None else None, hp(k_fb_0, (n_u, n_s)) if q_0 is not None else None)
     return prm, keep
 
 
 def score_rollouts(res, k_ff, k_fb, h_mat_safe, h_safe, ctrl_bounds=None, h_mat_obs=None, h_obs=None,
                    cost="exploration", wx=None, wu=None, x_ref=None, eps_constraints=1e-5, eps_noise=0.0,
-                   c_safety=1.0, want_g=False, layout="safempc"):
+                   c_safety=1.0, want_g=False, layout="safempc", q_0=None, k_fb_0=None):
     """Score the candidates of a RolloutResult (device tensors or NumPy arrays; the result has the same kind).
 
     res        RolloutResult of ``rollout`` for k_ff (B,H,n_u) and k_fb ((H-1),n_u,n_s) or (B,H-1,n_u,n_s)
@@ -83,6 +86,8 @@ def score_rollouts(res, k_ff, k_fb, h_mat_safe, h_safe, ctrl_bounds=None, h_mat_
     layout="cautious" (CautiousMPC.generate_safety_constraints, cautious_mpc.py:337-442): the same control constraints
     with c_safety on their support term, then the obstacle distances of ALL H states; no terminal set
     (h_mat_safe / h_safe may be None).  q_all then holds the propagated covariances.
+    q_0 (n_s,n_s) with k_fb_0 (n_u,n_s): the rollout started from an ellipsoid (init_uncertainty,
+    safempc_simple.py:181-199): the bound on u_0 then carries the support term of K_fb_0 Q_0 K_fb_0^T (:350).
     """
     torch = _lib.require_cuda()
     lib = _lib.load()
@@ -106,8 +111,10 @@ def score_rollouts(res, k_ff, k_fb, h_mat_safe, h_safe, ctrl_bounds=None, h_mat_
         status = torch.as_tensor(status, device=dev).to(torch.int32).contiguous()
     if cost == "exploration" and var_all is None:
         raise ValueError("the exploration cost needs the predictive variances (rollout(..., want_var=True))")
+    if (q_0 is None) != (k_fb_0 is None):
+        raise ValueError("q_0 and k_fb_0 go together")
     prm, keep = _score_params(n_s, n_u, ctrl_bounds, h_mat_obs, h_obs, h_mat_safe, h_safe, cost, wx, wu, x_ref,
-                              eps_constraints, eps_noise, c_safety, layout)
+                              eps_constraints, eps_noise, c_safety, layout, q_0, k_fb_0)
     n_g = lib.segp_score_num_constraints(hor, n_u, ctypes.byref(prm))
     cost_d = torch.empty((bsz,), dtype=torch.float64, device=dev)
     feas_d = torch.empty((bsz,), dtype=torch.int32, device=dev)
@@ -173,15 +180,22 @@ class SamplingSafeMPC(object):
     """SimpleSafeMPC with the IPOPT solve replaced by GPU sampling (safempc_simple.py:28-161 constructor).
 
     Parameters as the reference: ``n_safe, ssm, opt_env, wx_cost, wu_cost, beta_safety=2.5, rhc=True,
-    safe_policy=None, lin_trafo_gp_input=None, verbosity=0``; ``ssm`` must be a BatchedGPSSM.  Sampler options:
+    safe_policy=None, opt_perf_trajectory={}, lin_trafo_gp_input=None, verbosity=0``; ``ssm`` must be a BatchedGPSSM.
+    ``opt_perf_trajectory`` as the reference (:18-20, 153-155): ``type_perf_traj`` "mean_equivalent" | "taylor",
+    ``n_perf`` (default 5; <= 1 switches the performance trajectory off), ``r`` (1: the trajectories share u_0
+    only, the reference's tested case), ``perf_has_fb``.  With n_perf > 1 every candidate carries its own
+    performance controls k_ff_perf (n_perf - r, n_u); both trajectories are rolled out on the GPU (the performance
+    one as a Gaussian propagation, SEGP_PROP_*), the cost is the reference's default (:295-303): deviation of the
+    two mean trajectories over their common steps plus the exploration term on the PERFORMANCE trajectory.
+    Sampler options:
     ``n_samples`` candidates per iteration, ``n_iter`` refinement iterations (the sampling distribution is refit to
     the ``n_elite`` best feasible candidates), ``sigma0`` initial standard deviation of the control noise in units
     of the control range, ``seed``.  ``cost`` is "exploration" (the reference's default cost) or "quadratic".
     """
 
     def __init__(self, n_safe, ssm, opt_env, wx_cost, wu_cost, beta_safety=2.5, rhc=True, safe_policy=None,
-                 lin_trafo_gp_input=None, verbosity=0, n_samples=4096, n_iter=2, n_elite=64, sigma0=0.25,
-                 cost="exploration", x_ref=None, seed=0):
+                 opt_perf_trajectory={}, lin_trafo_gp_input=None, opts_solver=None, verbosity=0, n_samples=4096,
+                 n_iter=2, n_elite=64, sigma0=0.25, cost="exploration", x_ref=None, seed=0, sigma_x0=0.05):
         if not isinstance(ssm, BatchedGPSSM):
             raise TypeError("SamplingSafeMPC needs a BatchedGPSSM")
         self.rhc = rhc
@@ -200,6 +214,15 @@ class SamplingSafeMPC(object):
                 raise ValueError("Mandatory attribute {} missing in opt_env".format(name))
         if safe_policy is not None:
             self.safe_policy = safe_policy
+        for name in ATTR_NAMES_PERF:       # _set_attributes_from_dict(ATTR_NAMES_PERF, ...), safempc_simple.py:153-154
+            setattr(self, name, (opt_perf_trajectory or {}).get(name, DEFAULT_OPT_PERF[name]))
+        if self.type_perf_traj not in ("mean_equivalent", "taylor"):      # _set_perf_trajectory, :1018-1025
+            raise NotImplementedError("Unknown uncertainty propagation method")
+        self.n_perf, self.r = int(self.n_perf), int(self.r)
+        if self.n_perf > 1 and self.r != 1:
+            raise NotImplementedError("coupling the performance and safety trajectories for more than one step "
+                                      "(r > 1) is untested in the reference (safempc_simple.py:424-426) and not on "
+                                      "the sampling path")
         self.lin_trafo_gp_input = lin_trafo_gp_input
         self.m_obs = 0 if self.h_mat_obs is None else np.shape(self.h_mat_obs)[0]
         if self.h_mat_obs is not None:
@@ -232,9 +255,14 @@ class SamplingSafeMPC(object):
             warnings.warn("No SafePolicy!")
         self.n_samples, self.n_iter, self.n_elite = int(n_samples), int(n_iter), int(n_elite)
         self.sigma0 = float(sigma0)
+        self.sigma_x0 = float(sigma_x0)    # opt_x0: standard deviation of the sampled initial states
         self.cost = cost
         self.x_ref = x_ref
         self._rng = np.random.default_rng(seed)
+        self.cost_func = None
+        self.opt_x0 = False
+        self.init_uncertainty = False
+        self.k_ff_perf = None              # (n_perf - r, n_u) of the last feasible solution
         self.solver_initialized = True     # nothing to build: kept for callers that check it
         self.k_ff_safe = None              # (n_safe-1, n_u) of the last feasible solution
         self.k_fb_safe_all = None          # (n_safe-1, n_u*n_s)
@@ -243,9 +271,22 @@ class SamplingSafeMPC(object):
 
     # ------------------------------------------------------------------ reference helpers
     def init_solver(self, cost_func=None, opt_x0=False, init_uncertainty=False):
-        """Nothing to compile on this path (safempc_simple.py:163-284 builds the NLP here)."""
-        if cost_func is not None or opt_x0 or init_uncertainty:
-            raise NotImplementedError("custom cost functions, opt_x0 and init_uncertainty are not on the sampling path")
+        """safempc_simple.py:163-284 builds the NLP here; on this path there is nothing to compile, the three options
+        are remembered:
+
+        cost_func         replaces the default cost.  Called ONCE per iteration on the whole candidate batch with the
+                          reference's argument order (:306-313) and a leading candidate axis B on every array:
+                          ``cost_func(p_0 (B,n_s), u_0 (B,n_u), p_all (B,n_safe,n_s), q_all (B,n_safe,n_s,n_s),
+                          k_ff_safe (B,n_safe-1,n_u), k_fb_safe (n_safe-1,n_u,n_s), sigma_safe (B,n_safe,n_s)
+                          [, mu_perf (B,n_perf,n_s), sigma_perf (B,n_perf,n_s,n_s), gp_pred_sigma_perf (B,n_perf,n_s),
+                          k_fb_perf, k_ff_perf (B,n_perf-1,n_u)])`` -> (B,) costs (NumPy).
+        opt_x0            the initial state is a decision variable (:247-249): candidates sample it around the p_0
+                          handed to ``solve`` (standard deviation ``sigma_x0``) and the best candidate's is returned.
+        init_uncertainty  ``solve`` takes ``q_0`` / ``k_fb_0`` (:181-199): the rollout starts from the ellipsoid
+                          (p_0, q_0) and the bound on u_0 carries its feedback term (:350)."""
+        self.cost_func = cost_func
+        self.opt_x0 = bool(opt_x0)
+        self.init_uncertainty = bool(init_uncertainty)
         self.solver_initialized = True
 
     def get_lqr_feedback(self, x_0=None, u_0=None):
@@ -258,25 +299,45 @@ class SamplingSafeMPC(object):
         """safempc_simple.py:552-566"""
         return np.dot(state, self.a.T) + np.dot(action, self.b.T)
 
-    def _rollout(self, p_0, k_ff, k_fb):
-        return rollout(self.ssm, p_0, k_ff, k_fb, self.l_mu, self.l_sigma, None, None, self.beta_safety, self.a,
+    def _rollout(self, p_0, k_ff, k_fb, q_0=None, k_fb_0=None):
+        return rollout(self.ssm, p_0, k_ff, k_fb, self.l_mu, self.l_sigma, q_0, k_fb_0, self.beta_safety, self.a,
                        self.b, self.lin_trafo_gp_input)
 
-    def _score(self, res, k_ff, k_fb, want_g=False):
+    def _rollout_perf(self, p_0, k_ff_perf_traj, k_fb_perf):
+        """The performance trajectory of every candidate: mean_equivalent_multistep / multi_step_taylor_symbolic
+        (uncertainty_propagation_casadi.py:90-207) from the point p_0, controls [u_0; k_ff_perf], one feedback gain
+        k_fb_perf for all steps (safempc_simple.py:430-441).  Returns the Gaussian-propagation RolloutResult:
+        p_all = mu_perf (B,n_perf,n_s), q_all = sigma_perf, var_all = gp_pred_sigma_perf."""
+        prop = _lib.PROP_MEAN_EQUIVALENT if self.type_perf_traj == "mean_equivalent" else _lib.PROP_TAYLOR
+        zeros = np.zeros(self.n_s)
+        k_fb = np.tile(np.reshape(k_fb_perf, (1, self.n_u, self.n_s)), (self.n_perf - 1, 1, 1))
+        return rollout(self.ssm, p_0, k_ff_perf_traj, k_fb, zeros, zeros, None, None, 1.0, self.a, self.b,
+                       self.lin_trafo_gp_input, propagation=prop)
+
+    def _perf_cost(self, res, res_perf, eps_noise=0.0):
+        """Default cost with a performance trajectory (generate_cost_function, safempc_simple.py:292-303)."""
+        n_dev = min(self.n_perf, self.n_safe)
+        d = res_perf.p_all[:, 1:n_dev] - res.p_all[:, 1:n_dev]
+        cost = np.einsum("bti,ij,btj->b", d, 0.1 * self.wx_cost, d)
+        return cost - np.sum(np.sqrt(np.sum(res_perf.var_all + eps_noise, axis=2)), axis=1)
+
+    def _score(self, res, k_ff, k_fb, want_g=False, q_0=None, k_fb_0=None):
         return score_rollouts(res, k_ff, k_fb, self.h_mat_safe, self.h_safe, self.ctrl_bounds, self.h_mat_obs,
                               self.h_obs, cost=self.cost, wx=self.wx_cost, wu=self.wu_cost, x_ref=self.x_ref,
-                              want_g=want_g)
+                              want_g=want_g, q_0=q_0, k_fb_0=k_fb_0)
 
     def get_safety_trajectory_openloop(self, x_0, u_0, k_fb=None, k_ff=None, q_0=None, k_fb_0=None):
         """safempc_simple.py:599-637 for one control sequence -> (p_all, q_all, var_all)."""
-        if q_0 is not None:
-            raise NotImplementedError("init_uncertainty is not on the sampling path")
         k_fb = self.k_fb_safe_all if k_fb is None else k_fb
         k_ff = self.k_ff_safe if k_ff is None else k_ff
         if k_fb is None or k_ff is None:
             return None, None, None
+        if q_0 is not None and k_fb_0 is None:
+            k_fb_0 = self.get_lqr_feedback()
         seq = np.vstack((np.reshape(u_0, (1, self.n_u)), np.reshape(k_ff, (self.n_safe - 1, self.n_u))))
-        res = self._rollout(np.reshape(x_0, (self.n_s,)), seq[None], np.reshape(k_fb, (self.n_safe - 1, self.n_u, self.n_s)))
+        res = self._rollout(np.reshape(x_0, (self.n_s,)), seq[None], np.reshape(k_fb, (self.n_safe - 1, self.n_u, self.n_s)),
+                            None if q_0 is None else np.reshape(q_0, (self.n_s, self.n_s)),
+                            None if q_0 is None else np.reshape(k_fb_0, (self.n_u, self.n_s)))
         return res.p_all[0], res.q_all[0], res.var_all[0]
 
     def eval_safety_constraints(self, p_all, q_all, ubg_term=0., lbg_term=-np.inf, ubg_interm=0.,
@@ -310,13 +371,22 @@ class SamplingSafeMPC(object):
             k_fb = np.tile(k_fb_lqr, (max(self.n_safe - 1, 1), 1))[:self.n_safe - 1]
         return mean, k_fb
 
-    def solve(self, p_0, u_0=None, k_ff_all_0=None, k_fb_safe=None, sol_verbose=False):
+    def solve(self, p_0, u_0=None, k_ff_all_0=None, k_fb_safe=None, u_perf_0=None, k_fb_perf_0=None,
+              sol_verbose=False, q_0=None, k_fb_0=None):
         """One MPC step (safempc_simple.py:672-742, 742-909): sample, roll out, score, rank, fall back.
 
         Returns ``(x_0, u_apply, success)`` or, with sol_verbose, ``(x_0, u_apply, feasible, success,
         k_fb_safe, k_ff_all, p_safe, q_safe)`` like the reference (without the CasADi solution object).
+        ``u_perf_0`` (n_perf - r, n_u) / ``k_fb_perf_0`` (n_u, n_s): initial performance controls and the feedback
+        gain of the performance trajectory (default: zeros / the LQR gain, or zeros without ``perf_has_fb``);
+        ``q_0`` / ``k_fb_0``: initial ellipsoid and its gain (needs ``init_solver(init_uncertainty=True)``).
         """
         p_0 = np.reshape(np.asarray(p_0, dtype=np.float64), (self.n_s,))
+        if q_0 is not None and not self.init_uncertainty:
+            raise ValueError("q_0 given but the solver was not initialised with init_uncertainty=True")
+        if q_0 is not None:
+            q_0 = np.reshape(np.asarray(q_0, dtype=np.float64), (self.n_s, self.n_s))
+            k_fb_0 = np.reshape(self.get_lqr_feedback() if k_fb_0 is None else k_fb_0, (self.n_u, self.n_s))
         mean, k_fb_init = self._init_controls()
         if u_0 is not None:
             mean[0] = np.reshape(u_0, (self.n_u,))
@@ -327,29 +397,79 @@ class SamplingSafeMPC(object):
         if self.has_ctrl_bounds:
             lo, hi = self.ctrl_bounds[:, 0], self.ctrl_bounds[:, 1]
         else:
-            lo, hi = -np.ones(self.n_u), np.ones(self.n_u)
+            lo, hi = -np.ones(self.n_u), np.ones(self.n_u)      # only the scale of the sampling noise
         std = np.tile(self.sigma0 * (hi - lo), (self.n_safe, 1))
+        has_perf = self.n_perf > 1
+        n_pf = self.n_perf - self.r if has_perf else 0
+        if has_perf:
+            mean_perf = np.zeros((n_pf, self.n_u))
+            if u_perf_0 is not None:
+                mean_perf = np.reshape(np.asarray(u_perf_0, dtype=np.float64), (n_pf, self.n_u)).copy()
+            elif self.n_fail == 0 and self.k_ff_perf is not None and n_pf > 0:
+                mean_perf = np.vstack((self.k_ff_perf[1:], self.k_ff_perf[-1:]))      # shifted previous solution
+            std_perf = np.tile(self.sigma0 * (hi - lo), (n_pf, 1))
+            if k_fb_perf_0 is None:
+                k_fb_perf_0 = self.get_lqr_feedback() if (self.perf_has_fb and self.lin_prior) else \
+                    np.zeros((self.n_u, self.n_s))
+            k_fb_perf = np.reshape(k_fb_perf_0, (self.n_u, self.n_s))
+        mean_x, std_x = p_0.copy(), np.full(self.n_s, self.sigma_x0)
         best = None
         for _ in range(max(self.n_iter, 1)):
             cand = mean[None] + std[None] * self._rng.standard_normal((self.n_samples, self.n_safe, self.n_u))
             cand[0] = mean                                      # the current mean is always a candidate
             # u_0 is applied at a point (no feedback term), so clipping it to the bounds loses nothing; the later
-            # feed-forward terms need head-room for the feedback part and are left to the constraint check
-            cand[:, 0] = np.clip(cand[:, 0], lo, hi)
-            res = self._rollout(p_0, cand, k_fb3)
-            sc = self._score(res, cand, k_fb3)
+            # feed-forward terms need head-room for the feedback part and are left to the constraint check.  Without
+            # control bounds nothing is clipped (the reference leaves u_0 free then).
+            if self.has_ctrl_bounds and q_0 is None:
+                cand[:, 0] = np.clip(cand[:, 0], lo, hi)
+            if self.opt_x0:
+                x_cand = mean_x[None] + std_x[None] * self._rng.standard_normal((self.n_samples, self.n_s))
+                x_cand[0] = mean_x
+            else:
+                x_cand = p_0
+            res = self._rollout(x_cand, cand, k_fb3, q_0, k_fb_0)
+            sc = self._score(res, cand, k_fb3, q_0=q_0, k_fb_0=k_fb_0)
+            cost_v = sc.cost
+            res_perf = cand_perf = None
+            if has_perf:
+                cand_perf = mean_perf[None] + std_perf[None] * self._rng.standard_normal((self.n_samples, n_pf, self.n_u))
+                cand_perf[0] = mean_perf
+                if self.has_ctrl_bounds:      # plain bounds, no feedback term (safempc_simple.py:476-483)
+                    cand_perf = np.clip(cand_perf, lo, hi)
+                seq_perf = np.concatenate((cand[:, :1], cand_perf), axis=1)          # [u_0; k_ff_perf], r = 1
+                res_perf = self._rollout_perf(x_cand, seq_perf, k_fb_perf)
+                cost_v = self._perf_cost(res, res_perf)
+                ok = np.all(np.isfinite(res_perf.p_all.reshape(self.n_samples, -1)), axis=1) & (res_perf.status == 0)
+                sc = ScoreResult(cost_v, sc.feasible * ok.astype(sc.feasible.dtype), sc.violation, sc.g)
+            if self.cost_func is not None:
+                x_b = x_cand if self.opt_x0 else np.tile(p_0[None], (self.n_samples, 1))
+                args = [x_b, cand[:, 0], res.p_all, res.q_all, cand[:, 1:], k_fb3, res.var_all]
+                if has_perf:
+                    args += [res_perf.p_all, res_perf.q_all, res_perf.var_all, k_fb_perf, seq_perf[:, 1:]]
+                cost_v = np.asarray(self.cost_func(*args), dtype=np.float64).reshape(self.n_samples)
+                sc = ScoreResult(cost_v, sc.feasible * np.isfinite(cost_v).astype(sc.feasible.dtype), sc.violation, sc.g)
             idx, cost, viol, feas = best_candidate(sc)
             if idx >= 0 and (best is None or (feas, -cost if feas else -viol) > (best[3], -best[1] if best[3] else -best[2])):
-                best = (cand[idx].copy(), cost, viol, feas, res.p_all[idx].copy(), res.q_all[idx].copy())
+                best = (cand[idx].copy(), cost, viol, feas, res.p_all[idx].copy(), res.q_all[idx].copy(),
+                        None if cand_perf is None else cand_perf[idx].copy(),
+                        x_cand[idx].copy() if self.opt_x0 else p_0)
             order = np.lexsort((np.where(sc.feasible > 0, sc.cost, sc.violation), -sc.feasible))
-            elite = cand[order[:min(self.n_elite, self.n_samples)]]
+            top = order[:min(self.n_elite, self.n_samples)]
+            elite = cand[top]
             mean = elite.mean(axis=0)
             std = np.maximum(elite.std(axis=0), 1e-3 * (hi - lo))
+            if has_perf and n_pf > 0:
+                mean_perf = cand_perf[top].mean(axis=0)
+                std_perf = np.maximum(cand_perf[top].std(axis=0), 1e-3 * (hi - lo))
+            if self.opt_x0:
+                mean_x = x_cand[top].mean(axis=0)
+                std_x = np.maximum(x_cand[top].std(axis=0), 1e-3 * self.sigma_x0)
         feasible = bool(best is not None and best[3])
         success = True
         k_ff_all = p_safe = q_safe = k_fb_out = None
+        x_0 = p_0
         if feasible:
-            seq, _, _, _, p_safe, q_safe = best
+            seq, _, _, _, p_safe, q_safe, k_ff_perf, x_0 = best
             u_apply = seq[0].copy()
             k_ff_all = seq[1:].copy()
             k_fb_out = np.copy(k_fb)
@@ -359,6 +479,7 @@ class SamplingSafeMPC(object):
                 self.p_safe = p_safe
                 self.k_fb_safe_all = k_fb_out
                 self.u_apply = u_apply
+                self.k_ff_perf = k_ff_perf
         else:
             self.n_fail += 1
             if self.n_fail >= self.n_safe:
@@ -369,8 +490,8 @@ class SamplingSafeMPC(object):
                 u_apply = np.reshape(self.get_old_solution(p_0), (self.n_u,))
                 k_ff_all = u_apply
         if sol_verbose:
-            return p_0[:, None], u_apply, feasible, success, k_fb_out, k_ff_all, p_safe, q_safe
-        return p_0[:, None], u_apply, success
+            return np.reshape(x_0, (self.n_s, 1)), u_apply, feasible, success, k_fb_out, k_ff_all, p_safe, q_safe
+        return np.reshape(x_0, (self.n_s, 1)), u_apply, success
 
     def get_action(self, x0_mu, lqr_only=False, sol_verbose=False):
         """safempc_simple.py:639-670"""

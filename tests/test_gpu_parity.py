@@ -39,8 +39,9 @@ def _tri_mode(request, se):
 
 
 def _tight(gp, tight):
-    """Regression tolerance: `tight` on the float64 / 15-product paths, 3e-5 where the 10-product set runs."""
-    return 3e-5 if gp.get_option("i8_digits_effective") == 4 else tight
+    """Regression tolerance: `tight` on the float64 / 15-product paths, the gate itself where the 10-product set runs
+    (its variance error is a few 1e-6 .. 1e-5 of sigma^2 by design)."""
+    return RTOL if gp.get_option("i8_digits_effective") == 4 else tight
 
 
 def _make_models(se, x, y, n_s_in, n_u, kern_types, ls, var, noise_total):
@@ -469,7 +470,10 @@ def test_factor_buffer_transplant_equals_own_factorisation(se, kerns):
     gp2.set_data_only(x, y)
     with pytest.raises(RuntimeError):
         gp2.predict(x[:3])
-    b1, b2 = gp1.factor_buffers(), gp2.factor_buffers()
+    b1 = gp1.factor_buffers()
+    if len(b1) == 2:        # float64 contraction (tri_mode 0 / composite kernels): the DMMA operand travels too
+        gp2.alloc_fp64_operand()
+    b2 = gp2.factor_buffers()
     assert [nb for _, nb in b1] == [nb for _, nb in b2]
     for (p1, nb), (p2, _) in zip(b1, b2):
         _tensor_from_ptr(torch, p2, nb, gp2.device).copy_(_tensor_from_ptr(torch, p1, nb, gp1.device))

@@ -104,6 +104,7 @@ def _pendulum_mpc(se, n_safe=4, h_safe_bound=0.5, **kw):
     opt_env = {"l_mu": w.l_mu, "l_sigma": w.l_sigma, "h_mat_safe": w.h_mat,
                "h_safe": h_safe_bound * np.ones((2 * w.n_s, 1)), "lin_model": (w.a, w.b),
                "ctrl_bounds": np.array([[-1.0, 1.0]])}
+    kw.setdefault("opt_perf_trajectory", {"n_perf": 1})       # no performance trajectory unless a test asks for one
     mpc = se.SamplingSafeMPC(n_safe, gp, opt_env, np.eye(w.n_s), np.eye(w.n_u), beta_safety=2.0, n_samples=512,
                              n_iter=2, n_elite=32, seed=1, **kw)
     return w, gp, mpc
@@ -155,6 +156,99 @@ def test_sampling_mpc_falls_back_like_the_reference(se):
     for _ in range(3):
         u_k, feasible_k, *_ = mpc.get_action(x1, sol_verbose=True)
     assert mpc.n_fail == 4 and np.allclose(u_k, mpc.safe_policy(x1))
+    gp.close()
+
+
+@pytest.mark.parametrize("perf", ["mean_equivalent", "taylor"])
+def test_sampling_mpc_performance_trajectory(se, perf):
+    """n_perf > 1 (the reference's default, safempc_simple.py:19-20): every candidate carries performance controls;
+    the cost is the reference's default with a performance trajectory (:292-303), recomputed here from the returned
+    plan with the oracle's Gaussian propagation."""
+    from oracle import uprop_oracle
+    from oracle.gp_oracle import GPOracle
+    w, gp, mpc = _pendulum_mpc(se, opt_perf_trajectory={"n_perf": 5, "type_perf_traj": perf})
+    assert mpc.n_perf == 5 and mpc.r == 1 and mpc.perf_has_fb
+    x0 = np.array([0.02, -0.03])
+    u, feasible, success, k_fb, k_ff_all, p_safe, q_safe = mpc.get_action(x0, sol_verbose=True)
+    assert feasible and success and mpc.k_ff_perf.shape == (4, w.n_u)
+    assert np.all(np.abs(mpc.k_ff_perf) <= 1.0 + 1e-12)
+    # the cost of the returned plan, by the oracle
+    ora = GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
+                   [h["variance"] for h in w.hyp], gp.total_noise())
+    seq_perf = np.vstack((u[None], mpc.k_ff_perf))
+    k_fb_perf = mpc.get_lqr_feedback().reshape(w.n_u, w.n_s)
+    res_p = mpc._rollout_perf(x0, seq_perf[None], k_fb_perf)
+    mu_o, sig_o, var_o = uprop_oracle.multistep_batch(x0, ora, seq_perf[None], np.tile(k_fb_perf[None], (4, 1, 1)), w.a,
+                                                      w.b, None, perf == "taylor")
+    mu_o, sig_o, var_o = mu_o[0], sig_o[0], var_o[0]
+    assert np.allclose(res_p.p_all[0], mu_o, rtol=1e-6, atol=1e-9) and np.allclose(res_p.var_all[0], var_o, rtol=1e-5)
+    assert np.allclose(res_p.q_all[0], sig_o, rtol=1e-5, atol=1e-12)
+    d = mu_o[1:4] - p_safe[1:4]
+    want = float(np.einsum("ti,ij,tj->", d, 0.1 * mpc.wx_cost, d) - np.sum(np.sqrt(np.sum(var_o, axis=1))))
+    res_s = mpc._rollout(x0, np.vstack((u[None], k_ff_all))[None], k_fb.reshape(3, w.n_u, w.n_s))
+    got = float(mpc._perf_cost(res_s, res_p)[0])
+    assert abs(got - want) <= 1e-6 * abs(want)
+    # receding horizon keeps the shifted performance controls as the next mean
+    u2, success2 = mpc.get_action(p_safe[0])
+    assert success2 and mpc.n_fail == 0
+    with pytest.raises(NotImplementedError):
+        se.SamplingSafeMPC(4, gp, {"l_mu": w.l_mu, "l_sigma": w.l_sigma, "h_mat_safe": w.h_mat,
+                                   "h_safe": np.ones((4, 1)), "lin_model": (w.a, w.b)}, np.eye(2), np.eye(1),
+                           opt_perf_trajectory={"r": 2})
+    gp.close()
+
+
+def test_sampling_mpc_init_uncertainty_custom_cost_and_opt_x0(se):
+    from oracle import reach_oracle, score_oracle
+    from oracle.gp_oracle import GPOracle
+    w, gp, mpc = _pendulum_mpc(se)
+    x0 = np.array([0.02, -0.03])
+    q0 = np.diag([2e-4, 1e-4])
+    with pytest.raises(ValueError):
+        mpc.solve(x0, q_0=q0)                       # not initialised for it (safempc_simple.py:181-199)
+    mpc.init_solver(init_uncertainty=True)
+    _, u, feasible, success, k_fb, k_ff_all, p_safe, q_safe = mpc.solve(x0, q_0=q0, sol_verbose=True)
+    assert feasible and success
+    # certificate by the oracle, from the ellipsoid (x0, q0) with the LQR gain on step 0
+    ora = GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
+                   [h["variance"] for h in w.hyp], gp.total_noise())
+    k0 = mpc.get_lqr_feedback().reshape(w.n_u, w.n_s)
+    seq = np.vstack((u[None], k_ff_all))
+    p_o, q_o, _ = reach_oracle.multistep_batch(x0, ora, k_fb.reshape(3, w.n_u, w.n_s), seq[None], w.l_mu, w.l_sigma, q0,
+                                               2.0, w.a, w.b, k0)
+    assert np.allclose(p_o[0], p_safe, rtol=1e-6, atol=1e-9) and np.allclose(q_o[0], q_safe, rtol=1e-6, atol=1e-9)
+    # the bound on u_0 carries the feedback term of (q0, k0): value by value against the reference's formula
+    res = mpc._rollout(x0, seq[None], k_fb.reshape(3, w.n_u, w.n_s), q0, k0)
+    sc = se.score_rollouts(res, seq[None], k_fb.reshape(3, w.n_u, w.n_s), mpc.h_mat_safe, mpc.h_safe, mpc.ctrl_bounds,
+                           want_g=True, q_0=q0, k_fb_0=k0)
+    sd0 = np.sqrt(np.diag(k0 @ q0 @ k0.T))
+    assert np.allclose(sc.g[0, :2], [u[0] + sd0[0] - 1.0, -1.0 - u[0] + sd0[0]], rtol=1e-12, atol=1e-14)
+    g_rest = score_oracle.constraints_one(p_o[0], q_o[0], seq, k_fb.reshape(3, w.n_u, w.n_s), mpc.ctrl_bounds, None, None,
+                                          mpc.h_mat_safe, mpc.h_safe)
+    assert np.allclose(sc.g[0, 2:], g_rest[2:], rtol=1e-6, atol=1e-9)
+    # a custom cost with the reference's argument order picks the plan it asks for
+    mpc.init_solver(cost_func=lambda p_0, u_0, p_all, q_all, k_ff, k_fb_, sig: np.sum((u_0 - 0.25) ** 2, axis=1))
+    _, u_c, ok = mpc.solve(x0)
+    assert ok and abs(u_c[0] - 0.25) < 0.1
+    # opt_x0: the initial state is a decision variable; a cost that rewards x_0[0] pulls it there
+    mpc.init_solver(cost_func=lambda p_0, u_0, *rest: -p_0[:, 0], opt_x0=True)
+    mpc.n_iter = 3
+    x_opt, u_o, ok = mpc.solve(x0)
+    assert ok and x_opt.shape == (w.n_s, 1) and x_opt[0, 0] > x0[0] + 0.02
+    gp.close()
+
+
+def test_sampling_mpc_without_control_bounds_does_not_clip_u0(se):
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C2", batch=8, n_train=200, horizon=2)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
+    opt_env = {"l_mu": w.l_mu, "l_sigma": w.l_sigma, "h_mat_safe": w.h_mat, "h_safe": 1e3 * np.ones((2 * w.n_s, 1)),
+               "lin_model": (w.a, w.b)}
+    mpc = se.SamplingSafeMPC(2, gp, opt_env, np.eye(w.n_s), np.eye(w.n_u), beta_safety=2.0, n_samples=256, n_iter=1,
+                             n_elite=16, seed=3, opt_perf_trajectory={"n_perf": 1}, sigma0=1e-3)
+    mpc.init_solver(cost_func=lambda p_0, u_0, *rest: np.sum((u_0 - 1.3) ** 2, axis=1))
+    _, u, feasible, *_ = mpc.solve(np.array([0.0, 0.0]), u_0=np.array([1.3]), sol_verbose=True)
+    assert feasible and abs(u[0] - 1.3) < 0.05        # a warm start outside [-1, 1] survives: there are no bounds
     gp.close()
 
 
