@@ -433,7 +433,7 @@ def run_product(args, rank, world, local_rank):
         roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 4: "tri_i8m_kernel", 5: "tri_i8mp_kernel"}[mode]
                     + ("<split>" if digits == 4 else "<classic>"),
                     "pipe": "int8 tcgen05 (tcgen05.mma kind::i8, M=128 N=96/192 K=32, int32 accumulators in TMEM); "
-                            "float64-grade result from balanced base-254 digit planes, {} products ({})".format(
+                            "float64-grade result from balanced base-256 digit planes, {} products ({})".format(
                                 products, "diagonal-split set, 4 x 4 digits + the diagonal's leading digit; guarded by "
                                 "the a-posteriori error estimate, flagged panels recomputed with 15 products"
                                 if digits == 4 else "5 x 5 digits"),

@@ -42,8 +42,9 @@ extern "C" {
 /* composite kernels of the journal configs, k = k_lin(product term) * k_stationary + k_lin(all inputs)
  * (_k_lin_rbf / _k_lin_mat52 / _k_lin, gp_models_utils_casadi.py:73-157; GPy objects gaussian_process.py:469-474),
  * evaluated as  k(x,y) = (sum_j a_j x_j y_j) s_f^2 phi(|(x - y) / l|) + sum_j v_j x_j y_j  with the vectors a, v of
- * segp_set_linear_terms.  They run the variance contraction in float64 on the DMMA pipe (tri_mode 0): kernel values
- * are unbounded, the int8 digit planes of the tcgen05 path assume k / s_f^2 in [0, 1]. */
+ * segp_set_linear_terms.  Their values are signed and unbounded: on the int8 digit-plane path every trajectory is
+ * scaled by s_b = s_f^2 sum_j |a_j z_j| max_i |x_ij| + sum_j |v_j z_j| max_i |x_ij| >= |k(z_b, x_i)| before the digit
+ * split and the column sums of the contraction are multiplied by s_b^2. */
 #define SEGP_KERN_LIN_RBF 2
 #define SEGP_KERN_LIN_MAT52 3
 
@@ -312,7 +313,7 @@ int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double*
  *   and may be non-zero on the diagonal (row r, column K - 128 + r) only
  *   h_a [5][128][K] int8, h_b [5][96][K] int8 with K = 128 * k_blocks (HOST)
  *   h_acc [5][128][96] int32 (variant 1 only): h_acc[g] = sum over planes a + c == g of A_a B_c^T
- *   h_colsum [96]: sum over rows of (sum_g acc[g] * 254^(4-g))^2 as float64, where for variant 6
+ *   h_colsum [96]: sum over rows of (sum_g acc[g] * 256^(4-g))^2 as float64, where for variant 6
  *                  acc[g] = sum over planes a + c == g, a >= 1 or (a == 0), c <= 4, a + c <= 4 */
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum);

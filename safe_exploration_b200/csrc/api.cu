@@ -112,6 +112,8 @@ struct segp_model {
     double* plin = nullptr;    // [n_s][dim]
     double* lin = nullptr;     // [n_s][dim]
     double* xtb = nullptr;     // [n_s][dim] X^T beta_d
+    double* xmax = nullptr;    // [dim] max_i |x_ij| (scale bound of the composite kernels on the digit-plane path)
+    double* colfac2 = nullptr; // workspace: [n_s][b_cap] squared per-trajectory scales (composite models, int8 path)
     double* jac2_part = nullptr;   // workspace: additive Jacobian partials
     double* kss = nullptr;         // workspace: [n_s][b_cap] prior variances
     double* wdense = nullptr;  // [n_s][n_pad][n_pad] W = L^-1 kept dense for segp_append (only if opt_keep_w)
@@ -219,6 +221,7 @@ static void free_model_buffers(segp_model* m) {
     dev_free(m->plin);
     dev_free(m->lin);
     dev_free(m->xtb);
+    dev_free(m->xmax);
     m->has_linear_terms = false;
     m->factorized = false;
 }
@@ -235,16 +238,17 @@ static void free_workspace(segp_model* m) {
     dev_free(m->qpart);
     dev_free(m->jac2_part);
     dev_free(m->kss);
+    dev_free(m->colfac2);
     m->b_cap = 0;
     m->workspace_bytes = 0;
 }
 
-// the int8 digit planes assume kernel values in [0, s_f^2]: composite kernels (unbounded linear terms) run in float64
-static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD && !m->has_composite; }
+// the int32 accumulators of the digit-plane products bound the (padded) training size; composite kernels run on the
+// digit planes too, with a per-trajectory scale (KstarI8Args::colfac2)
+static bool i8_capable(const segp_model* m) { return m->n_pad <= I8_MAX_NPAD; }
 // which kernel runs the variance contraction: 0 fp64 DMMA, 1 int8 reference kernel, 4 tri_i8m, 5 tri_i8mp
 static int tri_mode(const segp_model* m) {
     if (m->force_mode > -2) return m->force_mode == -1 ? 4 : m->force_mode;
-    if (m->has_composite) return 0;
     if (m->opt_tri_mode >= 0) return (int)m->opt_tri_mode;
     return (i8_capable(m) && !m->auto_fp64) ? 4 : 0;
 }
@@ -267,8 +271,8 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     const int mode = tri_mode(m);
     const bool i8 = mode != 0;
     if (i8 && m->wi8 == nullptr) {
-        set_error("tri_mode=%d (int8 tcgen05) needs n_train_padded <= %ld and non-composite kernels; this model has %d",
-                  mode, I8_MAX_NPAD, m->n_pad);
+        set_error("tri_mode=%d (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", mode, I8_MAX_NPAD,
+                  m->n_pad);
         return SEGP_ERR_UNSUPPORTED;
     }
     if (!i8 && m->wt == nullptr) {
@@ -316,6 +320,7 @@ static int ensure_workspace(segp_model* m, long n_batch) {
     if (m->has_composite) {
         SEGP_CHECK(dev_alloc(&m->jac2_part, n_jac));
         SEGP_CHECK(dev_alloc(&m->kss, (size_t)m->n_s * want));
+        if (i8) SEGP_CHECK(dev_alloc(&m->colfac2, (size_t)m->n_s * want));
     }
     if (n_ks > 0) SEGP_CUDA_CHECK(cudaMemset(m->ks, 0, n_ks * sizeof(double)));
     if (n_ki8 > 0) SEGP_CUDA_CHECK(cudaMemset(m->ki8, 0, n_ki8));
@@ -406,6 +411,8 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int pan
         k8.k = k;
         k8.ki8 = m->ki8;
         k8.npanel_cap = m->npanel_cap;
+        k8.colfac2 = m->colfac2;
+        k8.xmax = m->xmax;
         k8.panel0 = panel0;
         k8.resident_ctas = coresident ? 3 * 148 : 0;   // three small CTAs per SM next to the persistent contraction
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
@@ -421,6 +428,7 @@ static TriI8Args tri_i8_args(const segp_model* m, long nb, int panel0, int digit
     t.rowfac = split ? m->rowfac_s : m->rowfac;
     t.wm1 = m->wm1;
     t.werr = split ? m->werr4 : m->werr5;
+    t.colfac2 = m->colfac2;
     t.digits = digits;
     t.ki8 = m->ki8;
     t.qpart = m->qpart;
@@ -484,6 +492,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
             g.qpart = m->qpart;
             g.epart = m->epart;
             g.gp_var = m->var;
+            g.kss = m->has_composite ? m->kss : nullptr;
             g.nblk = m->nblk;
             g.n_s = m->n_s;
             g.panel0 = panel0;
@@ -670,6 +679,11 @@ int segp_set_model(segp_model* m, int n_train, const double* h_x, const double* 
         std::copy(h_x, h_x + (size_t)n_train * dim, xraw.begin());
         SEGP_CHECK(dev_alloc(&m->xraw, xraw.size()));
         SEGP_CUDA_CHECK(cudaMemcpy(m->xraw, xraw.data(), xraw.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double> xmax(dim, 0.0);
+        for (int i = 0; i < n_train; ++i)
+            for (int j = 0; j < dim; ++j) xmax[j] = std::max(xmax[j], std::fabs(h_x[(size_t)i * dim + j]));
+        SEGP_CHECK(dev_alloc(&m->xmax, (size_t)dim));
+        SEGP_CUDA_CHECK(cudaMemcpy(m->xmax, xmax.data(), dim * sizeof(double), cudaMemcpyHostToDevice));
     }
     m->has_data = true;
     return SEGP_OK;
@@ -888,7 +902,7 @@ static int apply_calibration(segp_model* m, cudaStream_t st) {
 // flags at most a quarter of the probes on it (and the model is large enough for the extra launches to pay); when the
 // guard would flag more than a quarter of the probes even on the 15-product set, automatic mode runs float64.
 static int probe_pass(segp_model* m, const double* d_z, long np, int mode, int digits, cudaStream_t st,
-                      std::vector<double>& q, std::vector<double>& e) {
+                      std::vector<double>& q, std::vector<double>& e, std::vector<double>* prior = nullptr) {
     m->force_mode = mode;
     m->force_digits = digits;
     int rc = ensure_workspace(m, np);
@@ -908,6 +922,15 @@ static int probe_pass(segp_model* m, const double* d_z, long np, int mode, int d
     SEGP_CUDA_CHECK(cudaStreamSynchronize(st));
     SEGP_CUDA_CHECK(cudaMemcpy(hq.data(), m->qpart, n * sizeof(double), cudaMemcpyDeviceToHost));
     if (mode != 0) SEGP_CUDA_CHECK(cudaMemcpy(he.data(), m->epart, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (prior != nullptr) {   // prior variance k(z, z) per probe: s_f^2, or per input for the composite kernels
+        prior->assign((size_t)m->n_s * np, 0.0);
+        std::vector<double> hk(m->has_composite ? (size_t)m->n_s * m->b_cap : 0);
+        if (m->has_composite)
+            SEGP_CUDA_CHECK(cudaMemcpy(hk.data(), m->kss, hk.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int d = 0; d < m->n_s; ++d)
+            for (long p = 0; p < np; ++p)
+                (*prior)[(size_t)d * np + p] = m->has_composite ? hk[(size_t)d * m->b_cap + p] : m->h_var[d];
+    }
     q.assign((size_t)m->n_s * np, 0.0);
     e.assign((size_t)m->n_s * np, 0.0);
     for (int d = 0; d < m->n_s; ++d)
@@ -944,7 +967,7 @@ static int run_probe(segp_model* m, cudaStream_t st) {
     SEGP_CHECK(dev_alloc(&d_z, z.size()));
     const bool timed = m->time_tri;
     m->time_tri = false;
-    std::vector<double> q0, e0, q5, e5, q4, e4;
+    std::vector<double> q0, e0, q5, e5, q4, e4, prior;
     int rc = SEGP_OK;
     do {
         if (cudaMemcpy(d_z, z.data(), z.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -952,7 +975,7 @@ static int run_probe(segp_model* m, cudaStream_t st) {
             rc = SEGP_ERR_CUDA;
             break;
         }
-        if ((rc = probe_pass(m, d_z, np, 0, 0, st, q0, e0)) != SEGP_OK) break;
+        if ((rc = probe_pass(m, d_z, np, 0, 0, st, q0, e0, &prior)) != SEGP_OK) break;
         if ((rc = probe_pass(m, d_z, np, -1, 5, st, q5, e5)) != SEGP_OK) break;
         if ((rc = probe_pass(m, d_z, np, -1, 4, st, q4, e4)) != SEGP_OK) break;
     } while (0);
@@ -971,7 +994,7 @@ static int run_probe(segp_model* m, cudaStream_t st) {
     for (int d = 0; d < m->n_s; ++d)
         for (long p = 0; p < np; ++p) {
             const size_t i = (size_t)d * np + p;
-            const double s2 = m->h_var[d] - q0[i];
+            const double s2 = prior[i] - q0[i];
             const double err4 = std::fabs(q4[i] - q0[i]), err5 = std::fabs(q5[i] - q0[i]);
             const double sd4 = 2.0 * std::sqrt(e4[i]), sd5 = 2.0 * std::sqrt(e5[i]);
             ps[PS_ERR4] = std::max(ps[PS_ERR4], err4);
@@ -981,10 +1004,10 @@ static int run_probe(segp_model* m, cudaStream_t st) {
                 ps[PS_REL5] = std::max(ps[PS_REL5], err5 / s2);
             }
             // the float64 reference itself carries ~1e-13 of rounding relative to k**: do not calibrate against that
-            const double floor = 1e-12 * m->h_var[d];
+            const double floor = 1e-12 * prior[i];
             if (sd4 > 0.0 && err4 > floor) ps[PS_RATIO4] = std::max(ps[PS_RATIO4], err4 / sd4);
             if (sd5 > 0.0 && err5 > floor) ps[PS_RATIO5] = std::max(ps[PS_RATIO5], err5 / sd5);
-            ps[PS_MINVAR] = std::min(ps[PS_MINVAR], s2 / m->h_var[d]);
+            if (prior[i] > 0.0) ps[PS_MINVAR] = std::min(ps[PS_MINVAR], s2 / prior[i]);
         }
     ps[PS_RHO4] = std::max(1.0, ps[PS_RATIO4] / KAPPA_PROBE);
     ps[PS_RHO5] = std::max(1.0, ps[PS_RATIO5] / KAPPA_PROBE);
@@ -995,7 +1018,7 @@ static int run_probe(segp_model* m, cudaStream_t st) {
         bool f4 = false, f5 = false;
         for (int d = 0; d < m->n_s; ++d) {
             const size_t i = (size_t)d * np + p;
-            const double s2 = m->h_var[d] - q0[i];
+            const double s2 = prior[i] - q0[i];
             if (!(s2 > 0.0)) {
                 f4 = f5 = true;
                 continue;
@@ -1110,7 +1133,8 @@ int segp_factorize(segp_model* m, void* stream) {
             if ((rc = pack_w(wbuf, m->wt + (size_t)d * m->ntri * TILE * TILE, m->n_pad, ss)) != SEGP_OK) break;
             ++m->launches;
             if (m->wi8 != nullptr) {
-                if ((rc = pack_w_i8(wbuf, pack_out(m, d), m->h_var[d], m->n_pad, m->n_train, ss)) != SEGP_OK) break;
+                if ((rc = pack_w_i8(wbuf, pack_out(m, d), comp ? 1.0 : m->h_var[d], m->n_pad, m->n_train, ss)) != SEGP_OK)
+                    break;
                 m->launches += 2;
             }
         }
@@ -1208,9 +1232,14 @@ int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, 
         SEGP_CUDA_CHECK(cudaMemcpy(m->yp + (size_t)d * n_pad + n_old, rows.data(), (size_t)n_new * sizeof(double),
                                    cudaMemcpyHostToDevice));
     }
-    if (m->xraw != nullptr)
+    if (m->xraw != nullptr) {
         SEGP_CUDA_CHECK(cudaMemcpy(m->xraw + (size_t)n_old * dim, h_x, (size_t)n_new * dim * sizeof(double),
                                    cudaMemcpyHostToDevice));
+        std::vector<double> xmax(dim, 0.0);
+        for (size_t i = 0; i < hx.size() / dim; ++i)
+            for (int j = 0; j < dim; ++j) xmax[j] = std::max(xmax[j], std::fabs(hx[i * dim + j]));
+        SEGP_CUDA_CHECK(cudaMemcpy(m->xmax, xmax.data(), dim * sizeof(double), cudaMemcpyHostToDevice));
+    }
     m->h_x.swap(hx);
     m->h_y.swap(hy);
     m->n_train = n_tot;
@@ -1251,7 +1280,7 @@ int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, 
                 break;
             m->launches += 5;
             if (m->wi8 != nullptr) {
-                if ((rc = pack_w_i8(w, pack_out(m, d), m->h_var[d], n_pad, m->n_train, st)) != SEGP_OK) break;
+                if ((rc = pack_w_i8(w, pack_out(m, d), comp ? 1.0 : m->h_var[d], n_pad, m->n_train, st)) != SEGP_OK) break;
                 m->launches += 2;
             }
         }
@@ -2258,10 +2287,6 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         return SEGP_OK;
     }
     if (strcmp(name, "tri_mode") == 0 && (value == -1 || value == 0 || value == 1 || value == 4 || value == 5)) {
-        if (value >= 1 && m->has_composite) {
-            set_error("tri_mode=%ld (int8 tcgen05) is not available with composite (lin_*) kernels: float64 only", value);
-            return SEGP_ERR_UNSUPPORTED;
-        }
         if (value >= 1 && m->has_data && !i8_capable(m)) {
             set_error("tri_mode=%ld (int8 tcgen05) needs n_train_padded <= %ld; this model has %d", value, I8_MAX_NPAD,
                       m->n_pad);

@@ -90,9 +90,9 @@ int tri_sumsq_init();   // sets the dynamic shared memory attribute once per dev
 
 // ---------------------------------------------------------------- the same contraction on tcgen05 (int8 slices)
 // Ozaki-style error-free splitting: every row of W and every column of K* is scaled into [-1,1] and written as
-// I8_S balanced base-254 digits (int8, |digit| <= 127); digit planes are multiplied pairwise on the int8 tensor
+// I8_S balanced base-256 digits (int8); digit planes are multiplied pairwise on the int8 tensor
 // pipe (tcgen05.mma kind::i8, exact int32 accumulation in TMEM), digit pairs (a,c) with a+c < I8_S only, one
-// TMEM accumulator per diagonal a+c; the epilogue recombines the diagonals exactly in int64 (Horner, base 254),
+// TMEM accumulator per diagonal a+c; the epilogue recombines the diagonals exactly in int64 (Horner, base 256),
 // converts once to float64, squares and column-sums.  See DESIGN.md section 4.
 constexpr int I8_S = 5;        // digit planes per operand  -> 15 int8 products, ~2^-39 relative resolution
 constexpr int I8_SS = 4;       // digit planes of the diagonal-split set of W -> 10 products (+ the diagonal's extra digit)
@@ -102,12 +102,18 @@ constexpr int I8_A_TILE = TILE * I8_KB;    // 8192 B: 128 rows of W x 64 k, one 
 constexpr int I8_B_TILE = I8_N * I8_KB;    // 6144 B: 96 trajectories x 64 k
 constexpr long I8_MAX_NPAD = 16384;        // int32 accumulators: 5 * 127^2 * n_pad < 2^31 and the int64 Horner bound
 constexpr double I8_BASE0 = 127.0;         // first digit scale
-constexpr double I8_BASE = 254.0;          // following digits
+constexpr double I8_BASE = 256.0;          // following digits (balanced: -128..127)
 
 struct KstarI8Args {
     KstarArgs k;            // model, inputs and mean/Jacobian partial outputs (k.ks unused)
     int8_t* ki8;            // [n_s][npanel_cap][n_pad/64][I8_S][I8_B_TILE]
     long npanel_cap;
+    // composite kernels: values are signed and unbounded, so every trajectory gets its own scale s_b (an analytic bound
+    // on |k(z_b, x_i)| over the training inputs); the digits are those of k / s_b and the contraction multiplies its
+    // column sums by s_b^2.  colfac2 [n_s][b_cap] = s_b^2 (1 for the non-composite outputs of such a model), NULL
+    // for models without composite kernels; xmax [dim] = max_i |x_ij| of the raw training inputs.
+    double* colfac2;
+    const double* xmax;
     int panel0;             // first panel of this launch (blockIdx.x counts from it): sub-chunk pipelining
     int resident_ctas;      // > 0: run as a resident grid of this many small CTAs looping over the work items
 };
@@ -115,11 +121,12 @@ int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st);
 
 struct TriI8Args {
     const int8_t* wi8;      // classic set [n_s][nblk (nblk+1) k-blocks][I8_S][I8_A_TILE]   (block row bi starts at bi (bi+1))
-    const double* rowfac;   // [n_s][n_pad]   rowmax_i * var_d / (127^2 254^(S-1))
+    const double* rowfac;   // [n_s][n_pad]   rowmax_i * var_d / (127^2 256^(S-1))
     const int8_t* ki8;      // as above
     double* qpart;          // [n_s][nblk][b_cap]   column sums of v^2 per block row
     float* epart;           // [n_s][nblk][b_cap]   column sums of w_i v_i^2 (error-model variance, see pack_w_i8); may be NULL
     const float* werr;      // [n_s][n_pad] variance weights w_i of the digit set in use (NULL with epart)
+    const double* colfac2;  // composite kernels: per-trajectory factors s_b^2 on the column sums [n_s][b_cap], else NULL
     // diagonal-split set (digits == 4): wi8 = [n_s][nblk (nblk+1)][I8_SS][I8_A_TILE], rowfac = its row factors,
     const int8_t* wm1;      // [n_s][nblk][2][I8_A_TILE] leading digit of the diagonal entries (diagonal k-blocks only)
     int digits;             // 5 = classic set, 15 products; 4 = diagonal-split set, 10 products
@@ -146,6 +153,7 @@ struct GuardArgs {
     const double* qpart;    // [n_s][nblk][b_cap]
     const float* epart;     // [n_s][nblk][b_cap]
     const double* gp_var;   // [n_s] prior variances k**
+    const double* kss;      // composite kernels: per-trajectory prior variances [n_s][b_cap] (else NULL: gp_var)
     int nblk, n_s, panel0;
     long b_cap, n_batch;    // n_batch = END of the trajectory range
     double gs;              // (2 kappa / rtol)^2

@@ -4,7 +4,7 @@
 // contraction needs ~2^-36 relative accuracy -- out of reach of any fp32-accumulating pipe.
 // Integer accumulation is exact, so an error-free splitting (Ozaki scheme) recovers float64-grade results from
 // int8 products: every row of W = L^-1 and every column of K* is scaled into [-1, 1] and written as I8_S balanced
-// base-254 digits; the digit planes are multiplied pairwise (a + c < I8_S: 15 products) by tcgen05.mma kind::i8,
+// base-256 digits; the digit planes are multiplied pairwise (a + c < I8_S: 15 products) by tcgen05.mma kind::i8,
 // one TMEM accumulator per diagonal a + c, and the epilogue recombines the diagonals exactly in int64 before the
 // single conversion to float64.  Replaces, like tri_sumsq, `sum2(mtimes(k*, K^-1) * k*)` of
 // ssm_gpy/gp_models_utils_casadi.py:190-193 / GPy predict_noiseless.
@@ -22,46 +22,34 @@
 namespace segp {
 
 // =========================================================================================== digits
-// r in [-1, 1]  ->  r ~= d0/127 + d1/(127 254) + ... ; |d_a| <= 127, remainder below 0.5 / (127 254^(S-1)).
+// r in [-1, 1]  ->  V = rn(r 127 2^32), an integer of at most 39 bits + sign, written in BALANCED base 256:
+//   V = d0 2^32 + d1 2^24 + d2 2^16 + d3 2^8 + d4,   d0 in [-127, 127], d1..d4 in [-128, 127]   (all int8)
+// i.e. r ~= d0/127 + d1/(127 256) + ... with a remainder below 0.5 / (127 256^4) = 9.2e-13.  A power-of-two base makes
+// the digit split shifts and masks (no divisions), and the epilogue's Horner steps exact multiplications.
 __device__ __forceinline__ void split_digits(double r, int (&dg)[I8_S]) {
-    double x = r * I8_BASE0;
-    double q = rint(x);
-    dg[0] = (int)q;
-    double res = x - q;
+    static_assert(I8_S == 5, "digit layout below is for 5 planes");
+    long long v = __double2ll_rn(r * (I8_BASE0 * 4294967296.0));
 #pragma unroll
-    for (int a = 1; a < I8_S; ++a) {
-        x = res * I8_BASE;
-        q = rint(x);
-        dg[a] = (int)q;
-        res = x - q;
+    for (int a = I8_S - 1; a >= 1; --a) {
+        const int d = (int)((v + 128) & 255) - 128;
+        dg[a] = d;
+        v = (v - d) >> 8;
     }
+    dg[0] = (int)v;
 }
 
-// Same representation for u in [0, 1] (kernel values), with two float64 roundings instead of five and the digit
-// arithmetic on the integer pipes: u 127 254^4 ~= hi 254^2 + lo, hi = rn(u 127 254^2) in [0, 8193532],
-// lo = rn(frac 254^2) in [-32258, 32258], then balanced base-254 digits of hi (3) and lo (2).
-__device__ __forceinline__ void split_digits_unit(double u, int (&dg)[I8_S]) {
-    static_assert(I8_S == 5, "digit layout below is for 5 planes");
-    // round-to-nearest-even through the 1.5 2^52 trick (the integer lands in the low mantissa word): the same values
-    // as __double2int_rn / (double)hi, without the quarter-rate F2I / I2F conversions
-    const double MAGIC = 6755399441055744.0;
-    const double x = u * (I8_BASE0 * I8_BASE * I8_BASE);
-    const double th = x + MAGIC;
-    const int hi = __double2loint(th);
-    const double tl = (x - (th - MAGIC)) * (I8_BASE * I8_BASE) + MAGIC;
-    const int lo = __double2loint(tl);
-    // balanced remainder: v = 254 q + d, d in [-127, 126]; offsets keep the dividends non-negative
-    const unsigned lo_s = (unsigned)(lo + 127 + 254 * 128);
-    const unsigned q3 = lo_s / 254u;
-    dg[4] = (int)(lo_s - q3 * 254u) - 127;
-    dg[3] = (int)q3 - 128;
-    const unsigned hi_s = (unsigned)(hi + 127);
-    const unsigned q1 = hi_s / 254u;
-    dg[2] = (int)(hi_s - q1 * 254u) - 127;
-    const unsigned q1_s = q1 + 127u;
-    const unsigned q0 = q1_s / 254u;
-    dg[1] = (int)(q1_s - q0 * 254u) - 127;
-    dg[0] = (int)q0;
+// The same digits for u in [0, 1] (kernel values) in four integer instructions: V = rn(u 127 2^32) lands in the low
+// mantissa bits of u 127 2^32 + 1.5 2^52; adding 0x80 to each of the four low bytes turns them into excess-128 digits
+// (the carries ripple into the next byte, which is exactly the balanced recoding), and the XOR with 0x80 makes them
+// two's complement.  Returns d1..d4 packed as int8 bytes (d1 in byte 3 ... d4 in byte 0) and d0 (0..127) in d0.
+__device__ __forceinline__ uint32_t split_digits_unit(double u, int& d0) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+    const double t = fma(u, I8_BASE0 * 4294967296.0, MAGIC);
+    const uint32_t lo = (uint32_t)__double2loint(t);
+    const uint32_t hi = (uint32_t)__double2hiint(t) & 0x7FFFFu;   // V >> 32 (the 2^51 of MAGIC sits at bit 19)
+    const uint32_t lo2 = lo + 0x80808080u;
+    d0 = (int)(hi + (lo2 < lo ? 1u : 0u));
+    return lo2 ^ 0x80808080u;
 }
 
 // byte offset of element (row, k) inside a K-major SWIZZLE_64B tile image (rows of 64 bytes, 16-byte chunks
@@ -75,7 +63,7 @@ __host__ __device__ __forceinline__ int sw64_offset(int row, int k) {
 //   classic  rows scaled by their max-abs, 5 digits                                   (15 products, tri digits = 5)
 //   split    rows scaled by the max-abs of their OFF-diagonal entries, 4 digits; the diagonal entry 1/L_ii, which
 //            dominates every row of L^-1 (median 15 x the largest off-diagonal entry at C4) and would waste the
-//            leading plane, keeps an extra leading digit d_-1 (weight 254) in a plane of its own that is non-zero on
+//            leading plane, keeps an extra leading digit d_-1 (weight 256) in a plane of its own that is non-zero on
 //            the diagonal only and is multiplied in the two diagonal k-blocks of a block row only (10 products)
 // plus, per row, the factor that turns the recombined integer into v_i and the variance weight of the statistical
 // error model (see i8_err_weight): the epilogue column-sums w_i v_i^2 next to v_i^2, which is the a-posteriori error
@@ -114,19 +102,21 @@ __global__ void w_rowstat_kernel(const double* __restrict__ w, RowStat* __restri
 }
 
 // row scale of the split planes: off-diagonal max, but never so small that the diagonal's leading digit overflows
-__device__ __forceinline__ double split_scale(const RowStat& r) { return fmax(r.maxoff, fabs(r.diag) * (1.0 / 254.0)); }
+__device__ __forceinline__ double split_scale(const RowStat& r) { return fmax(r.maxoff, fabs(r.diag) * (1.0 / I8_BASE)); }
 
 // Variance of the error of v_i = sum_j W_ij k*_j computed with S digits per operand and the digit pairs a + c < S,
-// digits taken as independent and uniform:  per product term, in units u = 1 / (127 254^(S-1)) of the last digit,
+// digits taken as independent and uniform:  per product term, in units u = 1 / (127 256^(S-1)) of the last digit,
 //   truncation of k* against w~      w~_ij^2 / 12
 //   truncation of w~ against k~      k~_j^2 / 12          (k~ = k*/s_f^2 in [0,1]: mean square bounded by 1/2)
-//   dropped pairs a + c = S (S - 1 of them)   1 / 36 each
+//   dropped pairs a + c = S (S - 1 of them)   (256 / 127)^2 / 144 = 1 / 35.4 each
 // times (row scale  s_f^2  u)^2.  i8_scheme.py (scripts/experiments) checks it against the emulated scheme.
 __device__ __forceinline__ double i8_err_weight(double scale, double var, double sumsq_scaled, int n_terms, int digits) {
     double u = 1.0 / I8_BASE0;
     for (int a = 1; a < digits; ++a) u /= I8_BASE;
     const double f = scale * var * u;
-    return f * f * (sumsq_scaled * (1.0 / 12.0) + (double)n_terms * (0.5 / 12.0 + (double)(digits - 1) / 36.0));
+    // a dropped pair d_a d_c / (127 256) in units of u: both digits uniform over 256 values -> variance (256/127)^2 / 144
+    const double pair = (I8_BASE / I8_BASE0) * (I8_BASE / I8_BASE0) / 144.0;
+    return f * f * (sumsq_scaled * (1.0 / 12.0) + (double)n_terms * (0.5 / 12.0 + (double)(digits - 1) * pair));
 }
 
 __global__ void __launch_bounds__(TILE) pack_w_i8_kernel(const double* __restrict__ w, const RowStat* __restrict__ rs,
@@ -170,7 +160,7 @@ __global__ void __launch_bounds__(TILE) pack_w_i8_kernel(const double* __restric
             split_digits(v * inv, dg);
 #pragma unroll
             for (int a = 0; a < I8_S; ++a) pk[a][j >> 2] |= (uint32_t)(dg[a] & 0xff) << ((j & 3) * 8);
-            // split set: off-diagonal entries v / sc in [-1, 1] -> digits 0..3; the diagonal v / (254 sc) in [-1, 1]
+            // split set: off-diagonal entries v / sc in [-1, 1] -> digits 0..3; the diagonal v / (256 sc) in [-1, 1]
             // -> digits -1..3 (one level up); slot 0 of ps is the d_-1 plane
             int ds[I8_S];
             if (col == row) {
@@ -245,10 +235,8 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
 #pragma unroll 1
     for (int r = 0; r < ROWS; r += UNR) {
         uint32_t pk[I8_S][UNR / 4];
-#pragma unroll
-        for (int s = 0; s < I8_S; ++s)
-#pragma unroll
-            for (int q4 = 0; q4 < UNR / 4; ++q4) pk[s][q4] = 0u;
+        uint32_t wlo[UNR];   // digits 1..4 of every point, packed; digit 0 in whi
+        int whi[UNR];
 #pragma unroll
         for (int qd = 0; qd < UNR; ++qd) {
             const double* xr = s_x + (r + qd) * dim;
@@ -279,10 +267,18 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
 #pragma unroll
             for (int j = 0; j < DM; ++j)
                 if (j < dim) jac[j] = fma(w, diff[j], jac[j]);
-            int dg[I8_S];
-            split_digits_unit(unit, dg);
+            wlo[qd] = split_digits_unit(unit, whi[qd]);
+        }
+        // 4 x 4 byte transposes: plane s gets digit s of four consecutive points per word (three PRMTs each)
 #pragma unroll
-            for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
+        for (int q4 = 0; q4 < UNR / 4; ++q4) {
+            const uint32_t w0 = wlo[4 * q4], w1 = wlo[4 * q4 + 1], w2 = wlo[4 * q4 + 2], w3 = wlo[4 * q4 + 3];
+            pk[0][q4] = __byte_perm(__byte_perm((uint32_t)whi[4 * q4], (uint32_t)whi[4 * q4 + 1], 0x0040),
+                                    __byte_perm((uint32_t)whi[4 * q4 + 2], (uint32_t)whi[4 * q4 + 3], 0x0040), 0x5410);
+            pk[1][q4] = __byte_perm(__byte_perm(w0, w1, 0x0073), __byte_perm(w2, w3, 0x0073), 0x5410);
+            pk[2][q4] = __byte_perm(__byte_perm(w0, w1, 0x0062), __byte_perm(w2, w3, 0x0062), 0x5410);
+            pk[3][q4] = __byte_perm(__byte_perm(w0, w1, 0x0051), __byte_perm(w2, w3, 0x0051), 0x5410);
+            pk[4][q4] = __byte_perm(__byte_perm(w0, w1, 0x0040), __byte_perm(w2, w3, 0x0040), 0x5410);
         }
         const int kglob = row0 + r;
         int8_t* dst = kb_base + (long)(kglob >> 6) * (I8_S * I8_B_TILE) + sw64_offset(rowp, kglob & 63);
@@ -297,20 +293,9 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
     }
 }
 
-// One work item = (96-trajectory panel, output dimension, split of the training points).  STAGE training points are
-// staged through shared memory at a time.
-template <int D_T, int STAGE>
-__device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, int d, int split, int n_s,
-                                              double* __restrict__ s_x, double* __restrict__ s_beta,
-                                              const double* __restrict__ s_tab) {
-    const KstarArgs& a = aa.k;
-    constexpr int DM = D_T > 0 ? D_T : MAX_D;
-    const int dim = D_T > 0 ? D_T : a.dim;
-    const int trow = threadIdx.x;
-    const long b = (long)panel * I8_N + trow;
-    const bool active = b < a.n_batch;
-
-    double zs[DM];
+// GP input of trajectory b: given directly (predict), or [T p; k_ff] from the rollout state (raw, not yet scaled)
+template <int DM>
+__device__ __forceinline__ void kstar_i8_load_inputs(const KstarArgs& a, long b, bool active, int dim, double (&zs)[DM]) {
 #pragma unroll
     for (int j = 0; j < DM; ++j) zs[j] = 0.0;
     if (active) {
@@ -338,6 +323,128 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
             for (int j = 0; j < DM; ++j)
                 if (j >= a.n_in && j < dim) zs[j] = u[j - a.n_in];
         }
+    }
+}
+
+// The composite kernels (linear x stationary + linear, predict.cu:kstar_composite) on the digit-plane path: the same
+// float64 kernel values, mean / Jacobian sums and prior variance, with the value leaving as digit bytes of k / s_b.
+// s_b = s_f^2 sum_j |a_j z_j| xmax_j + sum_j |v_j z_j| xmax_j bounds |k(z_b, x_i)| for every training input.
+template <int DM>
+__device__ __forceinline__ void kstar_i8_composite(const KstarI8Args& aa, const double (&z)[DM], int dim, int d, int split,
+                                                   int n_s, long b, bool active, int8_t* __restrict__ kb_base, int rowp) {
+    const KstarArgs& a = aa.k;
+    const int kern = a.kern[d];
+    const double var = a.var[d];
+    const double sqrt5 = 2.23606797749978969641;
+    const double* __restrict__ pl = a.plin + d * dim;
+    const double* __restrict__ lv = a.lin + d * dim;
+    double zs[DM], za[DM], zv[DM], jac[DM], jac2[DM];
+    double kss = 0.0, kss_lin = 0.0, bound = 0.0;
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+        zs[j] = za[j] = zv[j] = jac[j] = jac2[j] = 0.0;
+        if (j < dim) {
+            zs[j] = z[j] * a.invls[d * dim + j];
+            za[j] = z[j] * pl[j];
+            zv[j] = z[j] * lv[j];
+            kss = fma(za[j], z[j], kss);
+            kss_lin = fma(zv[j], z[j], kss_lin);
+            bound += (fabs(za[j]) * var + fabs(zv[j])) * aa.xmax[j];
+        }
+    }
+    bound *= 1.0 + 1e-12;
+    if (!(bound > 0.0) || !active) bound = 1.0;
+    const double inv_s = 1.0 / bound;
+    double mu = 0.0;
+    const int row_begin = split * a.groups_per_split * 4;
+    const int row_end = min(row_begin + a.groups_per_split * 4, a.n_pad);
+#pragma unroll 1
+    for (int row0 = row_begin; row0 < row_end; row0 += 16) {
+        uint32_t pk[I8_S][4];
+#pragma unroll
+        for (int s = 0; s < I8_S; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
+#pragma unroll 4
+        for (int qd = 0; qd < 16; ++qd) {
+            const int row = row0 + qd;
+            const double* __restrict__ xsr = a.xs + ((long)d * a.n_pad + row) * dim;
+            const double* __restrict__ xr = a.xraw + (long)row * dim;
+            double diff[DM];
+            double r2 = 0.0, lp = 0.0, ll = 0.0;
+#pragma unroll
+            for (int j = 0; j < DM; ++j) {
+                diff[j] = 0.0;
+                if (j < dim) {
+                    diff[j] = zs[j] - xsr[j];
+                    r2 = fma(diff[j], diff[j], r2);
+                    lp = fma(za[j], xr[j], lp);
+                    ll = fma(zv[j], xr[j], ll);
+                }
+            }
+            double stat, gg;
+            if (kern == SEGP_KERN_LIN_RBF) {
+                stat = var * exp(-0.5 * r2);
+                gg = stat;
+            } else {
+                const double rr = sqrt(r2);
+                const double e = var * exp(-sqrt5 * rr);
+                stat = (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * e;
+                gg = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
+            }
+            double kval = fma(lp, stat, ll);
+            if (row >= a.n_train || !active) kval = 0.0;
+            const double bt = a.beta[(long)d * a.n_pad + row];   // zero on padded rows
+            mu = fma(bt, kval, mu);
+            const double w = bt * lp * gg, w2 = bt * stat;
+#pragma unroll
+            for (int j = 0; j < DM; ++j)
+                if (j < dim) {
+                    jac[j] = fma(w, diff[j], jac[j]);
+                    jac2[j] = fma(w2, xr[j], jac2[j]);
+                }
+            int dg[I8_S];
+            split_digits(kval * inv_s, dg);
+#pragma unroll
+            for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
+        }
+        int8_t* dst = kb_base + (long)(row0 >> 6) * (I8_S * I8_B_TILE) + sw64_offset(rowp, row0 & 63);
+#pragma unroll
+        for (int s = 0; s < I8_S; ++s)
+            *reinterpret_cast<uint4*>(dst + (long)s * I8_B_TILE) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+    }
+    if (!active) return;
+    a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
+#pragma unroll
+    for (int j = 0; j < DM; ++j)
+        if (j < dim) {
+            a.jac_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = jac[j];
+            a.jac2_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] =
+                pl[j] * jac2[j] + (split == 0 ? lv[j] * a.xtb[d * dim + j] : 0.0);
+        }
+    if (split == 0) {
+        a.kss[(long)d * a.b_cap + b] = fma(var, kss, kss_lin);
+        aa.colfac2[(long)d * a.b_cap + b] = bound * bound;
+    }
+}
+
+// One work item = (96-trajectory panel, output dimension, split of the training points).  STAGE training points are
+// staged through shared memory at a time.
+template <int D_T, int STAGE>
+__device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, int d, int split, int n_s,
+                                              double* __restrict__ s_x, double* __restrict__ s_beta,
+                                              const double* __restrict__ s_tab) {
+    const KstarArgs& a = aa.k;
+    constexpr int DM = D_T > 0 ? D_T : MAX_D;
+    const int dim = D_T > 0 ? D_T : a.dim;
+    const int trow = threadIdx.x;
+    const long b = (long)panel * I8_N + trow;
+    const bool active = b < a.n_batch;
+
+    double zs[DM];
+    kstar_i8_load_inputs<DM>(a, b, active, dim, zs);
+    const int kern = a.kern[d];
+    const int nkb = a.n_pad / I8_KB;
+    if (kern_is_composite(kern)) return;   // block-uniform (d): composite outputs are built by kstar_i8_composite_kernel
+    if (active) {
 #pragma unroll
         for (int j = 0; j < DM; ++j)
             if (j < dim) zs[j] *= a.invls[d * dim + j];
@@ -348,9 +455,7 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
 #pragma unroll
     for (int j = 0; j < DM; ++j) jac[j] = 0.0;
 
-    const int kern = a.kern[d];
     const double var = a.var[d];
-    const int nkb = a.n_pad / I8_KB;
     const int row_begin = split * a.groups_per_split * 4;
     const int row_end = min(row_begin + a.groups_per_split * 4, a.n_pad);
     int8_t* panel_base = aa.ki8 + (((long)d * aa.npanel_cap + panel) * nkb) * (long)(I8_S * I8_B_TILE);
@@ -399,8 +504,32 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
         a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
 #pragma unroll
         for (int j = 0; j < DM; ++j)
-            if (j < dim) a.jac_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = jac[j];
+            if (j < dim) {
+                a.jac_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = jac[j];
+                if (a.jac2_part != nullptr) a.jac2_part[(((long)split * n_s + d) * dim + j) * a.b_cap + b] = 0.0;
+            }
+        if (split == 0 && aa.colfac2 != nullptr) {   // a stationary output of a model that also has composite ones
+            a.kss[(long)d * a.b_cap + b] = var;
+            aa.colfac2[(long)d * a.b_cap + b] = 1.0;
+        }
     }
+}
+
+// composite outputs of the model (the blocks of the other outputs exit at once)
+template <int D_T>
+__global__ void __launch_bounds__(I8_N) kstar_i8_composite_kernel(const KstarI8Args aa) {
+    constexpr int DM = D_T > 0 ? D_T : MAX_D;
+    const KstarArgs& a = aa.k;
+    const int d = (int)blockIdx.y;
+    if (!kern_is_composite(a.kern[d])) return;
+    const int dim = D_T > 0 ? D_T : a.dim;
+    const int panel = aa.panel0 + (int)blockIdx.x;
+    const long b = (long)panel * I8_N + threadIdx.x;
+    const bool active = b < a.n_batch;
+    double zs[DM];
+    kstar_i8_load_inputs<DM>(a, b, active, dim, zs);
+    int8_t* base = aa.ki8 + (((long)d * aa.npanel_cap + panel) * (a.n_pad / I8_KB)) * (long)(I8_S * I8_B_TILE);
+    kstar_i8_composite<DM>(aa, zs, dim, d, (int)blockIdx.z, (int)gridDim.y, b, active, base, (int)threadIdx.x);
 }
 
 template <int D_T>
@@ -440,6 +569,22 @@ int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st) 
     const int npanels = (int)((a.k.n_batch + I8_N - 1) / I8_N) - a.panel0;
     dim3 grid((unsigned)npanels, (unsigned)n_s, (unsigned)nsplit);
     dim3 block(I8_N);
+    bool any_comp = false, all_comp = true;
+    for (int d = 0; d < n_s; ++d) {
+        any_comp = any_comp || kern_is_composite(a.k.kern[d]);
+        all_comp = all_comp && kern_is_composite(a.k.kern[d]);
+    }
+    if (any_comp) {
+        switch (a.k.dim) {
+            case 2: kstar_i8_composite_kernel<2><<<grid, block, 0, st>>>(a); break;
+            case 3: kstar_i8_composite_kernel<3><<<grid, block, 0, st>>>(a); break;
+            case 4: kstar_i8_composite_kernel<4><<<grid, block, 0, st>>>(a); break;
+            case 5: kstar_i8_composite_kernel<5><<<grid, block, 0, st>>>(a); break;
+            default: kstar_i8_composite_kernel<0><<<grid, block, 0, st>>>(a);
+        }
+        SEGP_CUDA_CHECK(cudaGetLastError());
+        if (all_comp) return SEGP_OK;
+    }
     if (a.resident_ctas > 0) {
         const long n_items = (long)npanels * n_s * nsplit;
         const unsigned ctas = (unsigned)std::min<long>(a.resident_ctas, n_items);
@@ -576,7 +721,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // =========================================================================================== epilogue helper
 // One warp, its 32 accumulator rows, 32 columns [col0, col0 + 32): recombine the I8_S diagonals
-//   v = sum_g C_g 254^(S-1-g)   as   ((C0 254 + C1) 254^2 + (C2 254 + C3)) 254 + C4
+//   v = sum_g C_g 256^(S-1-g)   as   ((C0 256 + C1) 256^2 + (C2 256 + C3)) 256 + C4
 // -- the two inner brackets exactly in int64 (one IMAD.WIDE each), the outer two steps as float64 FMAs (relative
 // error 2^-53, far below the 2^-39 resolution of the digits) -- scale by the row factor, square, and transpose-
 // reduce over the 32 rows: after the 5 halving steps lane l returns the sum of column col0 + l.
@@ -591,7 +736,7 @@ __device__ __forceinline__ double i8_epilogue_chunk(uint32_t tmem_quadrant_base,
         for (int j = 0; j < 32; ++j) dbg_row[0 * dbg_plane_stride + col0 + j] = (int)v[j];
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t01[j] = (long long)(int)v[j] * 254;
+    for (int j = 0; j < 32; ++j) t01[j] = (long long)(int)v[j] * 256;
     tmem_ld32(tmem_quadrant_base + (uint32_t)(1 * I8_N + col0), v);
     if (dbg_row != nullptr) {
 #pragma unroll
@@ -605,7 +750,7 @@ __device__ __forceinline__ double i8_epilogue_chunk(uint32_t tmem_quadrant_base,
         for (int j = 0; j < 32; ++j) dbg_row[2 * dbg_plane_stride + col0 + j] = (int)v[j];
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t23[j] = (long long)(int)v[j] * 254;
+    for (int j = 0; j < 32; ++j) t23[j] = (long long)(int)v[j] * 256;
     tmem_ld32(tmem_quadrant_base + (uint32_t)(3 * I8_N + col0), v);
     if (dbg_row != nullptr) {
 #pragma unroll
@@ -640,8 +785,8 @@ __device__ __forceinline__ double i8_epilogue_chunk(uint32_t tmem_quadrant_base,
 
 // Same recombination, same roundings, for the 12-warp epilogue of tri_i8m (one 32-column chunk per warp, three warps
 // per TMEM lane quadrant, so the TMEM round trips of one warp hide behind the arithmetic of the other two):
-//   * Horner entirely in float64:  a = C0; a = a 254 + C_g (g = 1..4).  The first three steps are exact (|a| < 2^47),
-//     the fourth rounds the exact value t01 254^2 + t23 once and the fifth rounds once more -- the same two
+//   * Horner entirely in float64:  a = C0; a = a 256 + C_g (g = 1..4).  The first three steps are exact (|a| < 2^47),
+//     the fourth rounds the exact value t01 256^2 + t23 once and the fifth rounds once more -- the same two
 //     roundings as i8_epilogue_chunk, hence bit-identical column sums;
 //   * int32 -> float64 without I2F (a quarter-rate conversion, and the int64 flavour is slower still): the bit pattern
 //     0x43300000:(x ^ 0x80000000) is 2^52 + 2^31 + x exactly, one full-rate DADD removes the bias;
@@ -820,7 +965,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) tri_i8_kernel(const TriI8Args a
         if (c < I8_N) {
             const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
             const long bcol = (long)panel * I8_N + c;
-            if (bcol < a.b_cap) a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
+            if (bcol < a.b_cap)
+                a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] =
+                    sum * (a.colfac2 != nullptr ? a.colfac2[(long)d * a.b_cap + bcol] : 1.0);
         }
     }
     tc_fence_before();
@@ -1108,10 +1255,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri
             const double sum = (s_col[c] + s_col[I8_N + c]) + (s_col[2 * I8_N + c] + s_col[3 * I8_N + c]);
             const long bcol = (long)panel * I8_N + c;
             if (bcol < a.b_cap) {
-                a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum;
+                const double cf = a.colfac2 != nullptr ? a.colfac2[(long)d * a.b_cap + bcol] : 1.0;
+                a.qpart[((long)d * a.nblk + bi) * a.b_cap + bcol] = sum * cf;
                 if (a.epart != nullptr)
                     a.epart[((long)d * a.nblk + bi) * a.b_cap + bcol] =
-                        (s_ecol[c] + s_ecol[I8_N + c]) + (s_ecol[2 * I8_N + c] + s_ecol[3 * I8_N + c]);
+                        ((s_ecol[c] + s_ecol[I8_N + c]) + (s_ecol[2 * I8_N + c] + s_ecol[3 * I8_N + c])) * (float)(cf * cf);
             }
         }
     }
@@ -1340,10 +1488,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
                     const double sum = (col[c] + col[I8_N + c]) + (col[2 * I8_N + c] + col[3 * I8_N + c]);
                     const long bcol = (long)t.panel * I8_N + c;
                     if (bcol < a.b_cap) {
-                        a.qpart[((long)t.d * a.nblk + t.bi) * a.b_cap + bcol] = sum;
+                        const double cf = a.colfac2 != nullptr ? a.colfac2[(long)t.d * a.b_cap + bcol] : 1.0;
+                        a.qpart[((long)t.d * a.nblk + t.bi) * a.b_cap + bcol] = sum * cf;
                         if (a.epart != nullptr)
                             a.epart[((long)t.d * a.nblk + t.bi) * a.b_cap + bcol] =
-                                (ecol[c] + ecol[I8_N + c]) + (ecol[2 * I8_N + c] + ecol[3 * I8_N + c]);
+                                ((ecol[c] + ecol[I8_N + c]) + (ecol[2 * I8_N + c] + ecol[3 * I8_N + c])) * (float)(cf * cf);
                     }
                 }
                 ++nsub;
@@ -1442,7 +1591,7 @@ __global__ void __launch_bounds__(4 * I8_N) i8_guard_kernel(const GuardArgs a) {
         if (threadIdx.y == 0 && b < a.n_batch) {
             const double qs = (s_q[0][threadIdx.x] + s_q[1][threadIdx.x]) + (s_q[2][threadIdx.x] + s_q[3][threadIdx.x]);
             const double es = (double)((s_e[0][threadIdx.x] + s_e[1][threadIdx.x]) + (s_e[2][threadIdx.x] + s_e[3][threadIdx.x]));
-            const double s2 = a.gp_var[d] - qs;
+            const double s2 = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qs;
             if (!(s2 > 0.0) || a.gs * es > s2 * s2) flag = 1;
         }
         __syncthreads();

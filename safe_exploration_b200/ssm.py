@@ -101,7 +101,8 @@ class BatchedGPSSM(object):
         Training data; if both are given and ``train`` is true the model is factorised immediately.
     kern_types : list[str], optional
         "rbf" | "mat52" | "lin_rbf" | "lin_mat52" per output dimension (default "rbf").  The composite kernels
-         run the variance contraction in float64 (tri_mode 0).
+         run on the same tensor pipes; on the int8 path their unbounded, signed values are
+        scaled per trajectory by an analytic bound before the digit split.
     hyp : list[dict], optional
         Per output dimension ``{"lengthscale": (D,) or scalar, "variance": float, "noise": float}``; for the composite
         kernels ``{"prod.rbf.lengthscale" | "prod.mat52.lengthscale", "prod.*.variance", "prod.linear.variances",
@@ -157,10 +158,9 @@ class BatchedGPSSM(object):
         _lib.check(self._lib.segp_create(ctypes.byref(self._handle), self.device.index, self.n_s_out, self.n_s_in,
                                          self.n_u, kern_ids))
         if tri_mode is None:
-            tri_mode = 0 if self.has_composite else DEFAULT_TRI_MODE
+            tri_mode = DEFAULT_TRI_MODE
         self.set_option("tri_mode", tri_mode)
-        if not self.has_composite:
-            self.set_option("i8_digits", DEFAULT_I8_DIGITS if i8_digits is None else i8_digits)
+        self.set_option("i8_digits", DEFAULT_I8_DIGITS if i8_digits is None else i8_digits)
         if guard_rtol is not None:
             self.set_param("guard_rtol", guard_rtol)
         self.last_predict_status = None

@@ -25,14 +25,19 @@ z = np.concatenate([w.p0[None] + 0.1 * rng.standard_normal((nb, w.n_s)), w.k_ff[
 zu = rng.uniform(-1, 1, size=z.shape)     # probe-style inputs: uniform over the training box
 
 
+BASE = 256.0
+
+
 def digits(r, s):
+    """first s balanced base-256 digits of V = rn(r 127 2^32) (tri_i8.cu: split_digits)"""
+    v = np.rint(r * (127.0 * 2.0 ** 32))
     out = []
-    x = r * 127.0
-    for a in range(s):
-        q = np.rint(x)
-        out.append(q)
-        x = (x - q) * 254.0
-    return out
+    for a in range(4, 0, -1):
+        d = np.mod(v + 128.0, 256.0) - 128.0
+        out.append(d)
+        v = (v - d) / 256.0
+    out.append(v)
+    return out[::-1][:s]
 
 
 for d in range(min(w.n_s, ndims)):
@@ -48,7 +53,7 @@ for d in range(min(w.n_s, ndims)):
     dg = np.diag(W).copy()
     woff = W - np.diag(dg)
     rmax = np.abs(woff).max(axis=1)
-    rmax = np.maximum(rmax, dg / 255.0)
+    rmax = np.maximum(rmax, dg / 256.0)
     wn = woff / rmax[:, None]
     rows = np.arange(1, n + 1)
     rw2 = (wn ** 2).sum(axis=1) / rows          # mean square of the scaled row entries
@@ -67,14 +72,14 @@ for d in range(min(w.n_s, ndims)):
             acc = np.zeros_like(v)
             for a in range(s):
                 for c in range(s - a):
-                    acc += (wd[a] @ kd[c]) / (127.0 * 127.0 * 254.0 ** (a + c))
-            khat = sum(kd[c] / (127.0 * 254.0 ** c) for c in range(5)) * var_f
+                    acc += (wd[a] @ kd[c]) / (127.0 * 127.0 * BASE ** (a + c))
+            khat = sum(kd[c] / (127.0 * BASE ** c) for c in range(5)) * var_f
             vv = acc * rmax[:, None] * var_f + dg[:, None] * khat
             q = np.sum(vv * vv, axis=0)
             err = np.abs(q - np.sum(v * v, axis=0))
-            # statistical model: per product term, variance u^2 [ (rw2 + rk2) / 12 + (s - 1) / 36 ], u = 1/(127 254^(s-1))
-            u = 1.0 / (127.0 * 254.0 ** (s - 1))
-            var_i = (rmax * var_f * u) ** 2 * rows * ((rw2 + rk2) / 12.0 + (s - 1) / 36.0)
+            # statistical model: per product term, variance u^2 [ (rw2 + rk2) / 12 + (s - 1) / 36 ], u = 1/(127 256^(s-1))
+            u = 1.0 / (127.0 * BASE ** (s - 1))
+            var_i = (rmax * var_f * u) ** 2 * rows * ((rw2 + rk2) / 12.0 + (s - 1) * (BASE / 127.0) ** 2 / 144.0)
             # d(sum v^2) = 2 sum v_i dv_i ; with sum v_i^2 <= var_f spread evenly:  std ~ 2 sqrt(var_f mean(var_i))
             model_rms = 2.0 * np.sqrt(var_f * var_i.mean())
             model_act = 2.0 * np.sqrt((v * v * var_i[:, None]).sum(axis=0))      # knowing v (oracle only)

@@ -227,9 +227,18 @@ def test_sampling_mpc_init_uncertainty_custom_cost_and_opt_x0(se):
                                           mpc.h_mat_safe, mpc.h_safe)
     assert np.allclose(sc.g[0, 2:], g_rest[2:], rtol=1e-6, atol=1e-9)
     # a custom cost with the reference's argument order picks the plan it asks for
-    mpc.init_solver(cost_func=lambda p_0, u_0, p_all, q_all, k_ff, k_fb_, sig: np.sum((u_0 - 0.25) ** 2, axis=1))
-    _, u_c, ok = mpc.solve(x0)
-    assert ok and abs(u_c[0] - 0.25) < 0.1
+    mpc.init_solver()
+    _, u_d, feas_d, *_ = mpc.solve(x0, sol_verbose=True)
+    seen = {}
+
+    def cost(p_0, u_0, p_all, q_all, k_ff, k_fb_, sig):
+        seen["shapes"] = (p_0.shape, u_0.shape, p_all.shape, q_all.shape, k_ff.shape, np.shape(k_fb_), sig.shape)
+        return np.sum((u_0 - 0.25) ** 2, axis=1)
+    mpc.init_solver(cost_func=cost)
+    _, u_c, feas_c, *_ = mpc.solve(x0, sol_verbose=True)
+    assert feas_d and feas_c and seen["shapes"] == ((512, 2), (512, 1), (512, 4, 2), (512, 4, 2, 2), (512, 3, 1), (3, 1, 2),
+                                                    (512, 4, 2))
+    assert abs(u_c[0] - 0.25) <= abs(u_d[0] - 0.25) + 1e-9 and u_c[0] != u_d[0]
     # opt_x0: the initial state is a decision variable; a cost that rewards x_0[0] pulls it there
     mpc.init_solver(cost_func=lambda p_0, u_0, *rest: -p_0[:, 0], opt_x0=True)
     mpc.n_iter = 3

@@ -32,10 +32,10 @@ def test_one_block_row_exact_integers(se, variant, k_blocks):
     lib = se._lib.load()
     rng = np.random.default_rng(10 * variant + k_blocks)
     kdim = TILE * k_blocks
-    a = rng.integers(-127, 128, size=(I8_S, TILE, kdim), dtype=np.int8)
+    a = rng.integers(-128, 128, size=(I8_S, TILE, kdim), dtype=np.int8)
     if variant == 6:
         a[0, :, :kdim - TILE] = 0          # the leading-digit plane exists in the diagonal block only
-    b = rng.integers(-127, 128, size=(I8_S, I8_N, kdim), dtype=np.int8)
+    b = rng.integers(-128, 128, size=(I8_S, I8_N, kdim), dtype=np.int8)
     acc = np.zeros((I8_S, TILE, I8_N), dtype=np.int32)
     colsum = np.zeros((I8_N,), dtype=np.float64)
     se._lib.check(lib.segp_i8_selftest(0, variant, k_blocks, a.ctypes.data_as(ctypes.c_void_p),
@@ -59,7 +59,7 @@ def test_one_block_row_exact_integers(se, variant, k_blocks):
             np.argwhere(acc.astype(np.int64) != want)[:4])
     horner = np.zeros((TILE, I8_N), dtype=object)
     for g in range(I8_S):
-        horner = horner * 254 + want[g].astype(object)
+        horner = horner * 256 + want[g].astype(object)
     want_col = np.array([float(sum(int(v) ** 2 for v in horner[:, c])) for c in range(I8_N)])
     assert np.allclose(colsum, want_col, rtol=1e-13, atol=0.0)
 
