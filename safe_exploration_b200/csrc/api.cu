@@ -502,10 +502,12 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
             g.pflag = m->pflag;
             g.counter = m->fallback_counter;
             SEGP_CHECK(launch_i8_guard(g, st));
+            // recomputation on the 15-product set as a RESIDENT grid (one cluster per TPC walking the tile list and
+            // skipping unflagged panel pairs): when nothing is flagged it costs one wave of CTAs that exit at once,
+            // not n_s x nblk x npanels launches of empty 220 KB CTAs
             TriI8Args t5 = tri_i8_args(m, nb, panel0, 5);
             t5.pflag = m->pflag;
-            t5.cluster = 2;
-            SEGP_CHECK(launch_tri_i8m(t5, m->n_s, st));
+            SEGP_CHECK(launch_tri_i8mp(t5, m->n_s, st, false));
             m->launches += 2;
         }
         return SEGP_OK;

@@ -155,14 +155,19 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
         var[d] = 0.0;
         if (d < n_s) {
             if (a.mu_part != nullptr) {
+                // partial sums in fixed order; the loads of 8 iterations are issued together (they do not depend on the
+                // running sum), which is what this latency-bound kernel is short of
                 double m = 0.0;
+#pragma unroll 8
                 for (int s = 0; s < a.nsplit; ++s) m += a.mu_part[((long)s * n_s + d) * a.b_cap + b];
                 double qf = 0.0;
+#pragma unroll 8
                 for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
                 mu[d] = m;
                 var[d] = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;
                 if (a.epart != nullptr) {   // int8 contraction: a-posteriori error estimate against the variance
                     float e2 = 0.f;
+#pragma unroll 8
                     for (int i = 0; i < a.nblk; ++i) e2 += a.epart[((long)d * a.nblk + i) * a.b_cap + b];
                     if (a.guard_gs * (double)e2 > var[d] * var[d]) status |= SEGP_STATUS_LOW_PRECISION;
                 }
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
                     if (j < dim) {
                         if (a.mu_part != nullptr) {
                             double acc = 0.0;
+#pragma unroll 8
                             for (int s = 0; s < a.nsplit; ++s)
                                 acc += a.jac_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
                             jrow[j] = -acc * a.invls[d * dim + j];

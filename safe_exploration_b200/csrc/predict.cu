@@ -443,8 +443,10 @@ __global__ void finalize_predict_kernel(const FinalizeArgs a) {
     int32_t status = 0;
     for (int d = 0; d < a.n_s; ++d) {
         double mu = 0.0;
+#pragma unroll 8
         for (int s = 0; s < a.nsplit; ++s) mu += a.mu_part[((long)s * a.n_s + d) * a.b_cap + b];
         double qf = 0.0;
+#pragma unroll 8
         for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
         a.mu[b * a.n_s + d] = mu;
         const double var = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;

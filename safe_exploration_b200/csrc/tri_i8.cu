@@ -1396,6 +1396,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         out.panel = a.panel0 + 2 * pair + (int)rank;
         out.valid = out.panel < a.npanels;            // odd panel count: the second CTA of the last pair only helps loading
         out.panel_ld = out.valid ? out.panel : out.panel - 1;
+        if (a.pflag != nullptr) {                     // precision fallback: only pairs with a flagged panel are computed
+            const int p0 = a.panel0 + 2 * pair;       // (the same answer in every role and in both CTAs of the pair)
+            if ((a.pflag[p0] | (p0 + 1 < a.npanels ? a.pflag[p0 + 1] : 0)) == 0) return false;
+        }
         return true;
     };
 
@@ -1514,10 +1518,6 @@ int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_roo
     const long ntiles = (long)n_s * nfold * npairs;
     if (ntiles <= 0) {
         set_error("tri_i8mp: empty tile list");
-        return SEGP_ERR_INVALID;
-    }
-    if (a.pflag != nullptr) {
-        set_error("tri_i8mp: the per-panel precision fallback runs on tri_i8m");
         return SEGP_ERR_INVALID;
     }
     static int n_sm = 0;

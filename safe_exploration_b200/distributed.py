@@ -62,21 +62,29 @@ def broadcast_buffers(tensors, src=0, group=None):
 
 
 def broadcast_factor(gp, src=0, group=None):
-    """Broadcast the factorised state of a BatchedGPSSM (packed L^-1 tiles, beta, logdet) from `src`.
-    Rank `src` must have trained the model; the others must have called ``set_data_only``."""
+    """Broadcast the factorised state of a BatchedGPSSM from `src`.  Rank `src` must have trained the model; the
+    others must have called ``set_data_only``.
+
+    ONE broadcast: buffer 0 is the whole factorised state of the int8 path (a single device allocation: beta,
+    log-determinants, digit planes, row factors, error-model weights, the probe's decisions).  Only a model that runs
+    the float64 contraction has a second buffer (the DMMA operand); whether it does is known to every rank once
+    buffer 0 has arrived (``mark_factorized`` refuses a model that still misses it), so the ranks agree on it with a
+    one-integer MAX all-reduce and, only then, broadcast buffer 1.
+
+    `gp` needs ``factor_views()`` (uint8 tensors aliasing the buffers), ``alloc_fp64_operand()``, ``mark_factorized()``
+    and ``get_option("fp64_operand_needed")`` -- BatchedGPSSM, or a stand-in in the CPU tests."""
+    import torch
     import torch.distributed as dist
-    from .ssm import _tensor_from_ptr
-    torch = gp._torch
     rank = dist.get_rank(group)
-    # ONE broadcast: buffer 0 is the whole factorised state of the int8 path (a single device allocation).  Only a
-    # model that runs the float64 contraction has a second buffer (the DMMA operand); whether it does is a property
-    # of the configuration every rank shares ("fp64_operand_needed": composite kernels, N_pad > 16384, tri_mode 0)
-    # or, for a probe-triggered float64 fallback, known after buffer 0 has arrived.
-    bufs = gp.factor_buffers()
-    views = [_tensor_from_ptr(torch, bufs[0][0], bufs[0][1], gp.device)]
-    torch.cuda.synchronize(gp.device)
-    broadcast_buffers(views, src, group)
-    torch.cuda.synchronize(gp.device)
+
+    def sync():
+        if gp.device.type == "cuda":
+            torch.cuda.synchronize(gp.device)
+
+    views = gp.factor_views()
+    sync()
+    broadcast_buffers(views[:1], src, group)
+    sync()
     if rank != src:
         try:
             gp.mark_factorized()
@@ -84,23 +92,23 @@ def broadcast_factor(gp, src=0, group=None):
         except ValueError:
             need = True
     else:
-        need = len(bufs) > 1 and bool(gp.get_option("fp64_operand_needed"))
+        need = len(views) > 1 and bool(gp.get_option("fp64_operand_needed"))
     flag = torch.tensor([1 if need else 0], dtype=torch.int32, device=gp.device)
     dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    sent = [views[0]]
     if int(flag.item()):
         if rank != src:
             gp.alloc_fp64_operand()
-        bufs = gp.factor_buffers()
-        if len(bufs) < 2:
+        views = gp.factor_views()
+        if len(views) < 2:
             raise RuntimeError("the factorising rank did not keep the float64 operand (set tri_mode / keep_fp64 "
                                "before training)")
-        v1 = _tensor_from_ptr(torch, bufs[1][0], bufs[1][1], gp.device)
-        broadcast_buffers([v1], src, group)
-        torch.cuda.synchronize(gp.device)
-        views.append(v1)
+        broadcast_buffers(views[1:2], src, group)
+        sync()
+        sent.append(views[1])
         if rank != src:
             gp.mark_factorized()
-    return sum(v.numel() for v in views)
+    return sum(v.numel() for v in sent)
 
 
 def build_replicated_model(n_s_out, n_s_in, n_u, x, y, kern_types, hyp, rank, world_size, src=0, device=None,

@@ -327,6 +327,10 @@ class BatchedGPSSM(object):
             out.append((ptr.value, nbytes.value))
         return out
 
+    def factor_views(self):
+        """``factor_buffers`` as uint8 CUDA tensors aliasing the device memory (what a broadcast writes into)."""
+        return [_tensor_from_ptr(self._torch, ptr, nbytes, self.device) for ptr, nbytes in self.factor_buffers()]
+
     def set_data_only(self, X, y):
         """Upload data + hyper-parameters without factorising (non-root ranks before the broadcast)."""
         x_h = _lib.host_f64(X)

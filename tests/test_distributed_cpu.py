@@ -96,3 +96,61 @@ def test_best_candidate_across_ranks_world_size_2(tmp_path):
     assert res1 == (8197, 7.0, -0.1, True)
     assert res2 == (10, 2.0, -0.5, True)
     assert res3[0] == -1 and res3[3] is False
+
+
+class _FakeModel(object):
+    """Stand-in for BatchedGPSSM on CPU tensors: the factor arena, optionally a float64 operand, and the
+    mark_factorized contract of the library (refuses while a needed second buffer is missing)."""
+
+    def __init__(self, rank, need_fp64):
+        self.device = torch.device("cpu")
+        self.rank = rank
+        rng = np.random.RandomState(5)
+        self.truth = [rng.randint(0, 255, 4096).astype(np.uint8), rng.randint(0, 255, 1024).astype(np.uint8)]
+        self.arena = torch.from_numpy(self.truth[0].copy()) if rank == 0 else torch.zeros(4096, dtype=torch.uint8)
+        self.need = need_fp64                # on non-root ranks this is "known" only after the arena has arrived
+        self.wt = torch.from_numpy(self.truth[1].copy()) if (rank == 0 and need_fp64) else None
+        self.marked = 0
+
+    def factor_views(self):
+        return [self.arena] + ([self.wt] if self.wt is not None else [])
+
+    def alloc_fp64_operand(self):
+        if self.wt is None:
+            self.wt = torch.zeros(1024, dtype=torch.uint8)
+
+    def get_option(self, name):
+        assert name == "fp64_operand_needed"
+        return 1 if self.need else 0
+
+    def mark_factorized(self):
+        assert np.array_equal(self.arena.numpy(), self.truth[0])        # only ever called after buffer 0 arrived
+        if self.need and (self.wt is None or not np.array_equal(self.wt.numpy(), self.truth[1])):
+            raise ValueError("float64 operand missing")
+        self.marked += 1
+
+
+def _factor_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sd.init_from_env(backend="gloo")
+    ok = True
+    for need in (False, True):
+        gp = _FakeModel(rank, need)
+        nbytes = sd.broadcast_factor(gp, src=0)
+        ok = ok and nbytes == (4096 + 1024 if need else 4096)          # ONE buffer unless float64 is in play
+        ok = ok and np.array_equal(gp.arena.numpy(), gp.truth[0])
+        ok = ok and (gp.marked == (1 if rank != 0 else 0))
+        if need:
+            ok = ok and np.array_equal(gp.wt.numpy(), gp.truth[1])
+    dist.barrier()
+    with open(os.path.join(out_dir, "factor_ok%d" % rank), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_factor_broadcast_is_one_collective_unless_float64_world_size_2(tmp_path):
+    port = _free_port()
+    mp.spawn(_factor_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(str(tmp_path), "factor_ok%d" % r)).read() == "1"

@@ -510,9 +510,12 @@ def _rollout_vs_oracle(se, w, t_z_gp=None, q0=None, k_fb_init=None, per_traj_kfb
     _assert_close(res.var_all, v_o, RTOL, atol_scale=1e-6, what="variance (gate)")
     _assert_close(res.p_all, p_o, RTOL, atol_scale=1e-5, what="p_all (gate)")
     _assert_close(res.q_all, q_o, RTOL, atol_scale=1e-5, what="q_all (gate)")
+    # regression bounds far inside the gate; where the 10-product digit set runs (variance error a few 1e-6 of sigma^2
+    # by design, amplified on the small entries of Q over the horizon) the bound is the gate with SURVEY 8d's atol
+    ten = gp.get_option("i8_digits_effective") == 4
     _assert_close(res.var_all, v_o, _tight(gp, 1e-6), atol_scale=1e-10, what="variance (tight)")
     _assert_close(res.p_all, p_o, _tight(gp, rtol), what="p_all (tight)")
-    _assert_close(res.q_all, q_o, _tight(gp, rtol), what="q_all (tight)")
+    _assert_close(res.q_all, q_o, _tight(gp, rtol), atol_scale=1e-6 if ten else 1e-9, what="q_all (tight)")
     return gp, res
 
 
