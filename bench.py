@@ -109,9 +109,13 @@ class ClockSampler(object):
 
 
 def _oracle_model(w):
-    from oracle.gp_oracle import GPOracle
-    return GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
-                    [h["variance"] for h in w.hyp], [h["noise"] + 1e-5 + 1e-8 for h in w.hyp])
+    from oracle import gp_oracle
+    noise = [h["noise"] + 1e-5 + 1e-8 for h in w.hyp]
+    if any(k.startswith("lin_") for k in w.kern_types):
+        ls, var, pl, lin = gp_oracle.vectors_from_reference_hyp(w.kern_types, w.hyp, w.n_s + w.n_u, semantics="casadi")
+        return gp_oracle.GPOracle(w.x_train, w.y_train, w.kern_types, ls, var, noise, prod_linear=pl, linear=lin)
+    return gp_oracle.GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
+                              [h["variance"] for h in w.hyp], noise)
 
 
 def cpu_baseline(w, seconds_target=15.0):
@@ -184,7 +188,7 @@ def run_reference(args, rank, world):
     from oracle import reach_oracle, ref_loader
     from safe_exploration_b200 import workloads
     per_step = max(1, args.ref_rollouts)
-    w = workloads.make(args.config, batch=per_step * (args.steps + args.warmup))
+    w = workloads.make(args.config, batch=per_step * (args.steps + args.warmup), kern=args.kern or None)
     ora = _oracle_model(w)
     ora._ensure_inv()
     kind = "port"
@@ -282,7 +286,7 @@ def run_product(args, rank, world, local_rank):
         b_per_gpu = max(1, cfg[5] // world)          # the quoted configuration's B, whatever the GPU count
     else:
         b_per_gpu = max(1, cfg[5] // cfg[6])         # the per-GPU shard of the quoted configuration
-    w = workloads.make(args.config, batch=b_per_gpu * world, n_train=args.n_train or None)
+    w = workloads.make(args.config, batch=b_per_gpu * world, n_train=args.n_train or None, kern=args.kern or None)
     s0, s1 = sd.shard_range(b_per_gpu * world, rank, world)
     k_ff_shard = np.ascontiguousarray(w.k_ff[s0:s1])
 
@@ -540,6 +544,9 @@ def main():
     ap.add_argument("--i8-digits", type=int, default=0, choices=[0, 4, 5],
                     help="digit set of the int8 contraction: 0 automatic (factorize-time probe), 4 = 10 products, "
                          "5 = 15 products")
+    ap.add_argument("--kern", default="", choices=["", "rbf", "mat52", "lin_rbf", "lin_mat52"],
+                    help="swap the configuration's kernel (lin_*: the composite kernels of the reference's journal "
+                         "configs; the line is then not a BASELINE configuration)")
     ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA-graph replay")
     ap.add_argument("--guard-kappa", type=float, default=0.0, help="override the precision guard's kappa (0 = library default)")
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")

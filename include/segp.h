@@ -349,7 +349,9 @@ int segp_get_option(segp_model* m, const char* name, long* value);
  * factorize-time probe (1024 uniform inputs over the training box against the float64 contraction, worst output
  * dimension): "probe_ran", "probe_frac4" / "probe_frac5" (fraction the guard flags on the 10- / 15-product set),
  * "probe_err4/5" (max abs error of |L^-1 k*|^2), "probe_rel4/5" (max error / sigma^2), "probe_ratio4/5" (max error in
- * predicted standard deviations), "probe_rho4/5" (calibration factors applied), "probe_min_var_ratio". */
+ * predicted standard deviations), "probe_rho4/5" (calibration factors applied), "probe_min_var_ratio", "probe_margin4" (largest kappa x estimated
+ * error of the 10-product set relative to guard_rtol x sigma^2 over the probes: at most 0.25 means the first pass runs
+ * without guard / recomputation launches, read-only option "unguarded"). */
 int segp_set_param(segp_model* m, const char* name, double value);
 int segp_get_param(segp_model* m, const char* name, double* value);
 

@@ -68,6 +68,7 @@ enum {
     PS_RHO4,      // calibration factor applied to the model's standard deviation (>= 1)
     PS_RHO5,
     PS_MINVAR,    // smallest sigma^2 / k** over the probe inputs
+    PS_MARGIN4,   // largest (kappa x estimated error) / (rtol sigma^2) of the 10-product set over the probes (1 = at the guard)
     PROBE_STATS
 };
 }  // namespace segp
@@ -134,6 +135,8 @@ struct segp_model {
     unsigned int fallback_seen = 0;             // value of the mirror when the previous call was issued
     long panels_prev_call = 0;                  // panel contractions the previous guarded call issued
     bool demoted = false;                       // automatic mode fell back to the 15-product first pass at run time
+    bool unguarded = false;                     // the probe found the 10-product set at least 4x inside the tolerance
+                                                // everywhere: no guard / recomputation launches (status flags stay)
     // workspace
     long b_cap = 0;
     int nsplit = 1, blocks_per_split = 1;
@@ -487,7 +490,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
             SEGP_CHECK(persistent ? launch_tri_i8mp(t, m->n_s, st, coresident) : launch_tri_i8m(t, m->n_s, st));
         }
         if (e1 != nullptr) SEGP_CUDA_CHECK(cudaEventRecord(e1, st));
-        if (digits == 4 && m->opt_guard != 0 && m->force_digits == 0) {
+        if (digits == 4 && m->opt_guard != 0 && m->force_digits == 0 && !(m->unguarded && m->opt_i8_digits == 0)) {
             GuardArgs g{};
             g.qpart = m->qpart;
             g.epart = m->epart;
@@ -788,6 +791,7 @@ static int write_meta(segp_model* m) {
     h[0] = (double)m->i8_primary;
     h[1] = m->auto_fp64 ? 1.0 : 0.0;
     h[2] = m->wt != nullptr ? 1.0 : 0.0;
+    h[3] = m->unguarded ? 1.0 : 0.0;
     for (int i = 0; i < PROBE_STATS; ++i) h[4 + i] = m->probe_stat[i];
     SEGP_CUDA_CHECK(cudaMemcpy(m->meta, h, sizeof(h), cudaMemcpyHostToDevice));
     return SEGP_OK;
@@ -799,6 +803,7 @@ static int read_meta(segp_model* m, bool* root_has_fp64) {
     m->i8_primary = h[0] == 4.0 ? 4 : 5;
     m->auto_fp64 = h[1] != 0.0;
     if (root_has_fp64 != nullptr) *root_has_fp64 = h[2] != 0.0;
+    m->unguarded = h[3] != 0.0;
     for (int i = 0; i < PROBE_STATS; ++i) m->probe_stat[i] = h[4 + i];
     return SEGP_OK;
 }
@@ -1026,6 +1031,7 @@ static int run_probe(segp_model* m, cudaStream_t st) {
                 continue;
             }
             if (gs * ps[PS_RHO4] * ps[PS_RHO4] * e4[i] > s2 * s2) f4 = true;
+            ps[PS_MARGIN4] = std::max(ps[PS_MARGIN4], std::sqrt(gs * e4[i]) * ps[PS_RHO4] / s2);
             if (gs * ps[PS_RHO5] * ps[PS_RHO5] * e5[i] > s2 * s2) f5 = true;
         }
         n4 += f4;
@@ -1037,7 +1043,11 @@ static int run_probe(segp_model* m, cudaStream_t st) {
     // 15-product kernel: it pays while g < 1/3.  The probes are spread over the whole training box, a rollout batch
     // sits in one place, so the probe fraction only says whether typical inputs pass; the run-time demotion in
     // segp_multistep (fallback_rate) catches a batch that lives where they do not.
-    m->i8_primary = (ps[PS_FRAC4] <= 0.25 && m->n_pad >= 1024) ? 4 : 5;
+    // Where the estimate stays 4x inside the tolerance on every probe the first pass runs unguarded: no guard and no
+    // recomputation launch per step (the ellipsoid step still raises SEGP_STATUS_LOW_PRECISION on whatever exceeds the
+    // tolerance), which is what lets launch-bound small models use the 10-product set at all.
+    m->unguarded = ps[PS_MARGIN4] <= 0.25;
+    m->i8_primary = (m->unguarded || (ps[PS_FRAC4] <= 0.25 && m->n_pad >= 1024)) ? 4 : 5;
     m->auto_fp64 = ps[PS_FRAC5] > 0.25;
     m->demoted = false;
     SEGP_CHECK(apply_calibration(m, st));
@@ -1065,6 +1075,8 @@ int segp_factorize(segp_model* m, void* stream) {
     m->i8_primary = 5;
     m->auto_fp64 = false;
     for (double& v : m->probe_stat) v = 0.0;
+    m->unguarded = false;
+    m->demoted = false;
     const size_t nn = (size_t)m->n_pad * m->n_pad;
     const int nb64 = m->n_pad / NBLK;
     // The output dimensions are independent factorisations and each is a chain of ~270 launches, many of them one
@@ -1521,7 +1533,8 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
     const int npanels_first = (int)((std::min<long>(m->b_cap, n_batch) + I8_N - 1) / I8_N);
     const bool pipelined_any = m->ws_mode != 0 && tri_mode(m) >= 4 && m->opt_overlap != 0 && npanels_first >= 48 &&
                                m->n_pad >= 1024;
-    const bool guarded = m->ws_mode != 0 && tri_mode(m) >= 4 && tri_digits(m) == 4 && m->opt_guard != 0;
+    const bool guarded = m->ws_mode != 0 && tri_mode(m) >= 4 && tri_digits(m) == 4 && m->opt_guard != 0 &&
+                         !(m->unguarded && m->opt_i8_digits == 0);
     // The serial schedule: per chunk and step kstar -> contraction (+ guard + recomputation) -> ellipsoid step, every
     // launch asynchronous on one stream.
     auto issue_serial = [&](cudaStream_t s1) -> int {
@@ -2381,6 +2394,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
         *value = n;
     }
     else if (strcmp(name, "demoted") == 0) *value = m->demoted ? 1 : 0;
+    else if (strcmp(name, "unguarded") == 0) *value = m->unguarded ? 1 : 0;
     else if (strcmp(name, "fp64_operand_resident") == 0) *value = m->wt != nullptr ? 1 : 0;
     else if (strcmp(name, "fp64_operand_needed") == 0) *value = fp64_operand_needed(m) ? 1 : 0;
     else if (strcmp(name, "factor_bytes") == 0) *value = (long)m->arena_bytes;
@@ -2454,7 +2468,8 @@ int segp_get_param(segp_model* m, const char* name, double* value) {
     } stats[] = {{"probe_ran", PS_RAN},         {"probe_frac4", PS_FRAC4},   {"probe_frac5", PS_FRAC5},
                  {"probe_err4", PS_ERR4},       {"probe_err5", PS_ERR5},     {"probe_rel4", PS_REL4},
                  {"probe_rel5", PS_REL5},       {"probe_ratio4", PS_RATIO4}, {"probe_ratio5", PS_RATIO5},
-                 {"probe_rho4", PS_RHO4},       {"probe_rho5", PS_RHO5},     {"probe_min_var_ratio", PS_MINVAR}};
+                 {"probe_rho4", PS_RHO4},       {"probe_rho5", PS_RHO5},     {"probe_min_var_ratio", PS_MINVAR},
+                 {"probe_margin4", PS_MARGIN4}};
     if (strcmp(name, "guard_rtol") == 0) {
         *value = m->guard_rtol;
         return SEGP_OK;

@@ -551,12 +551,14 @@ class BatchedGPSSM(object):
         """What the factorize-time probe measured and decided: digit set of the first
         contraction pass, whether automatic mode runs float64, and the probe statistics."""
         names = ("probe_ran", "probe_frac4", "probe_frac5", "probe_err4", "probe_err5", "probe_rel4", "probe_rel5",
-                 "probe_ratio4", "probe_ratio5", "probe_rho4", "probe_rho5", "probe_min_var_ratio", "guard_rtol",
-                 "guard_kappa")
+                 "probe_ratio4", "probe_ratio5", "probe_rho4", "probe_rho5", "probe_min_var_ratio", "probe_margin4",
+                 "guard_rtol", "guard_kappa")
         out = {n: self.get_param(n) for n in names}
         out["tri_mode_effective"] = self.get_option("tri_mode_effective")
         out["i8_digits_effective"] = self.get_option("i8_digits_effective")
         out["fallback_panels"] = self.get_option("fallback_panels")
+        out["unguarded"] = self.get_option("unguarded")
+        out["demoted"] = self.get_option("demoted")
         return out
 
 

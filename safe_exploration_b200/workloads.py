@@ -78,10 +78,14 @@ def lqr_gain(a, b, q=None, r=None):
     return -k
 
 
-def make(name, batch=None, n_train=None, horizon=None, seed_offset=0):
+def make(name, batch=None, n_train=None, horizon=None, seed_offset=0, kern=None):
     """Build workload `name` (C1..C5).  `batch` overrides the number of candidate sequences (per-GPU shards,
-    small parity cases); `n_train` / `horizon` shrink the model for CPU-sized parity tests."""
-    system, n_s, n_u, n_cfg, h_cfg, b_cfg, _, kern = CONFIGS[name]
+    small parity cases); `n_train` / `horizon` shrink the model for CPU-sized parity tests; `kern` swaps the kernel
+    ("lin_rbf" / "lin_mat52": the composite kernels of the reference's journal configs,
+    experiments/journal_experiment_configs/defaultconfig_episode.py:39, with hyper-parameters in the reference's own
+    key layout)."""
+    system, n_s, n_u, n_cfg, h_cfg, b_cfg, _, kern_cfg = CONFIGS[name]
+    kern = kern or kern_cfg
     n = int(n_train or n_cfg)
     hor = int(horizon or h_cfg)
     bsz = int(batch or b_cfg)
@@ -132,6 +136,11 @@ def make(name, batch=None, n_train=None, horizon=None, seed_offset=0):
         # (test/test_gp_reachability_casadi.py:55-56).
         l_mu = np.full(n_s, lipschitz)
         l_sigma = np.full(n_s, lipschitz)
+    if kern in ("lin_rbf", "lin_mat52"):
+        st = kern[4:]
+        hyp = [{"prod.%s.lengthscale" % st: np.array([float(np.mean(h["lengthscale"]))]),
+                "prod.%s.variance" % st: float(h["variance"]), "prod.linear.variances": np.array([1.0]),
+                "linear.variances": np.full(dim, 0.05), "noise": h["noise"]} for h in hyp]
     k_gain = lqr_gain(a, b, r=lqr_r * np.eye(n_u))
     k_fb = np.tile(k_gain[None], (max(hor - 1, 1), 1, 1))[:max(hor - 1, 0)]
     p0 = 0.05 * rng2.standard_normal(n_s)
