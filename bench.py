@@ -318,6 +318,8 @@ def run_product(args, rank, world, local_rank):
         gp.set_option("graph", 0)
     if args.guard_kappa > 0:
         gp.set_param("guard_kappa", args.guard_kappa)
+    if args.substreams >= 0:
+        gp.set_option("substreams", args.substreams)
 
     def step_device():
         # the result buffers are re-used, as a sampling-MPC loop would: from the second call on the library replays the
@@ -548,6 +550,7 @@ def main():
                     help="swap the configuration's kernel (lin_*: the composite kernels of the reference's journal "
                          "configs; the line is then not a BASELINE configuration)")
     ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA-graph replay")
+    ap.add_argument("--substreams", type=int, default=-1, help="sub-batch streams of small models (-1 = library default)")
     ap.add_argument("--guard-kappa", type=float, default=0.0, help="override the precision guard's kappa (0 = library default)")
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

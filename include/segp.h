@@ -336,6 +336,8 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
  *   tri_mode 0 factorises again); read-only "fp64_operand_resident", "fp64_operand_needed", "factor_bytes";
  * "graph": 1 (default) = replay the launches of a segp_multistep call as a CUDA graph from the second call with the
  *   same arguments on (read-only "graphs_cached");
+ * "substreams": small models (<= 8 block rows of 128 training points) run a chunk as independent sub-batches on internal
+ *   streams, because there every kernel is latency-bound and leaves most SMs idle (-1 automatic: 2; 0 off; n <= 4);
  * "overlap": 1 = run a chunk as two half-chunks software-pipelined over two internal streams (tri_mode 4/5);
  * "time_tri": 1 = bracket every contraction launch with a CUDA-event pair on its stream (resets the counters);
  * read-only: "launches" = kernels launched by this handle so far, "n_train_padded", "workspace_bytes",

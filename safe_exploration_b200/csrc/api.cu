@@ -157,6 +157,9 @@ struct segp_model {
     cudaStream_t s_host = nullptr;   // stream of the host entry points
     cudaStream_t s_cap = nullptr;    // capture stream of the CUDA-graph path
     cudaStream_t s_copy = nullptr;   // device-to-host result copies of the host entry points
+    cudaStream_t s_sub[3] = {nullptr, nullptr, nullptr};   // sub-batch chains of small models (segp_multistep)
+    cudaEvent_t ev_sub[3] = {nullptr, nullptr, nullptr}, ev_sub_fork = nullptr;
+    long opt_substreams = -1;        // -1 automatic (2 for models of <= 8 block rows), 0 off, n = at most n (<= 4)
     cudaEvent_t ev_chunk = nullptr;
     // options
     long opt_chunk = 8192;
@@ -615,6 +618,11 @@ int segp_destroy(segp_model* m) {
     if (m->s_host != nullptr) cudaStreamDestroy(m->s_host);
     if (m->s_cap != nullptr) cudaStreamDestroy(m->s_cap);
     if (m->s_copy != nullptr) cudaStreamDestroy(m->s_copy);
+    for (int i = 0; i < 3; ++i) {
+        if (m->s_sub[i] != nullptr) cudaStreamDestroy(m->s_sub[i]);
+        if (m->ev_sub[i] != nullptr) cudaEventDestroy(m->ev_sub[i]);
+    }
+    if (m->ev_sub_fork != nullptr) cudaEventDestroy(m->ev_sub_fork);
     if (m->ev_chunk != nullptr) cudaEventDestroy(m->ev_chunk);
     for (cudaEvent_t e : m->tri_events) cudaEventDestroy(e);
     for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_ks[0], m->ev_ks[1], m->ev_tri[0], m->ev_tri[1]})
@@ -1537,15 +1545,59 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
                          !(m->unguarded && m->opt_i8_digits == 0);
     // The serial schedule: per chunk and step kstar -> contraction (+ guard + recomputation) -> ellipsoid step, every
     // launch asynchronous on one stream.
+    // Small models (few block rows): every kernel of a step is latency-bound and leaves most SMs idle (C2: ~30 us each
+    // for 4096 trajectories).  The candidates are independent, so the chunk is cut into sub-batches of whole panel
+    // pairs whose H-step chains run on their own internal streams and overlap on the device: same kernels, same
+    // arithmetic per trajectory, disjoint parts of the workspace -- bit-identical results.  Measured at C2: 2 chains
+    // 0.75 ms per call against 0.83 (one) and 0.82 (four: the contraction CTAs take a whole SM's shared memory each, so
+    // more chains mostly queue) -- automatic mode uses two.  (Large models fill the GPU with every launch; there
+    // co-resident kernels only get in each other's way, see `overlap`.)
+    auto sub_batches = [&](long nb) -> int {
+        if (m->opt_substreams == 0 || m->ws_mode == 0 || m->nblk > 8) return 1;
+        const long np = (nb + I8_N - 1) / I8_N;
+        const long want = m->opt_substreams > 0 ? m->opt_substreams : 2;
+        return (int)std::max<long>(1, std::min<long>(want, np / 8));
+    };
     auto issue_serial = [&](cudaStream_t s1) -> int {
         if (d_status != nullptr) SEGP_CUDA_CHECK(cudaMemsetAsync(d_status, 0, n_batch * sizeof(int32_t), s1));
         for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
             const long nb = std::min<long>(m->b_cap, n_batch - c0);
-            for (int t = 0; t < horizon; ++t) {
-                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, nb), s1));
-                SEGP_CHECK(run_tri(m, nb, s1));
-                SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t, 0, nb), s1));
-                m->launches += 3;
+            const int nsub = sub_batches(nb);
+            if (nsub == 1) {
+                for (int t = 0; t < horizon; ++t) {
+                    SEGP_CHECK(run_kstar(m, kstar_args(c0, t, nb), s1));
+                    SEGP_CHECK(run_tri(m, nb, s1));
+                    SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t, 0, nb), s1));
+                    m->launches += 3;
+                }
+                continue;
+            }
+            if (m->s_sub[0] == nullptr) {
+                for (int i = 0; i < 3; ++i) {
+                    SEGP_CUDA_CHECK(cudaStreamCreateWithFlags(&m->s_sub[i], cudaStreamNonBlocking));
+                    SEGP_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_sub[i], cudaEventDisableTiming));
+                }
+                SEGP_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_sub_fork, cudaEventDisableTiming));
+            }
+            const long np = (nb + I8_N - 1) / I8_N;
+            const long q = 2 * ((np + 2 * nsub - 1) / (2 * nsub));   // panels per sub-batch: even (cluster pairs stay whole)
+            SEGP_CUDA_CHECK(cudaEventRecord(m->ev_sub_fork, s1));
+            for (int i = 0; i < nsub; ++i) {
+                const long p0 = (long)i * q, p1 = std::min<long>(p0 + q, np);
+                if (p0 >= p1) continue;
+                cudaStream_t ss = i == 0 ? s1 : m->s_sub[i - 1];
+                if (i > 0) SEGP_CUDA_CHECK(cudaStreamWaitEvent(ss, m->ev_sub_fork, 0));
+                const long b0 = p0 * I8_N, b1 = std::min<long>(p1 * I8_N, nb);
+                for (int t = 0; t < horizon; ++t) {
+                    SEGP_CHECK(run_kstar(m, kstar_args(c0, t, b1), ss, (int)p0));
+                    SEGP_CHECK(run_tri(m, b1, ss, (int)p0));
+                    SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t, b0, b1), ss));
+                    m->launches += 3;
+                }
+                if (i > 0) {
+                    SEGP_CUDA_CHECK(cudaEventRecord(m->ev_sub[i - 1], ss));
+                    SEGP_CUDA_CHECK(cudaStreamWaitEvent(s1, m->ev_sub[i - 1], 0));
+                }
             }
         }
         if (guarded)
@@ -1563,7 +1615,7 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         struct Key {
             long n_batch, p0_stride, q0_stride, kfb_stride, kfb_init_stride, b_cap, events_at;
             const void *p0, *q0, *kff, *kfb, *kfbi, *p_all, *q_all, *var_all, *status;
-            int horizon, mode, digits, guard, nsplit, timed, pgroup, cluster;
+            int horizon, mode, digits, guard, nsplit, timed, pgroup, cluster, substreams;
         } key;
         memset(&key, 0, sizeof(key));
         key.n_batch = n_batch;
@@ -1590,6 +1642,7 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         key.timed = m->time_tri ? 1 : 0;
         key.pgroup = (int)m->opt_i8_panel_group;
         key.cluster = (int)m->opt_i8_cluster;
+        key.substreams = (int)m->opt_substreams;
         const unsigned char* kb = reinterpret_cast<const unsigned char*>(&key);
         GraphEntry* g = nullptr;
         int n_entries = 0;
@@ -2335,6 +2388,13 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_graph = value;
         return SEGP_OK;
     }
+    if (strcmp(name, "substreams") == 0 && value >= -1 && value <= 4) {
+        DeviceGuard guard(m->device);
+        cudaDeviceSynchronize();
+        free_graphs(m);
+        m->opt_substreams = value;
+        return SEGP_OK;
+    }
     if (strcmp(name, "overlap") == 0 && (value == 0 || value == 1)) {
         m->opt_overlap = value;
         return SEGP_OK;
@@ -2388,6 +2448,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "probe") == 0) *value = m->opt_probe;
     else if (strcmp(name, "keep_fp64") == 0) *value = m->opt_keep_fp64;
     else if (strcmp(name, "graph") == 0) *value = m->opt_graph;
+    else if (strcmp(name, "substreams") == 0) *value = m->opt_substreams;
     else if (strcmp(name, "graphs_cached") == 0) {
         long n = 0;
         for (GraphEntry* e = m->graphs; e != nullptr; e = e->next) n += e->exec != nullptr;

@@ -28,10 +28,10 @@ bench_all)
   $B --config C5 --scaling weak --steps 3 --warmup 3 --cpu-seconds 10 > gpurun_out/bench_c5_n1.json 2> gpurun_out/bench_c5_n1.err
   $B --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err ;;
 small)
-  for m in 4 5; do for dg in 0 5; do $B --config C2 --tri-mode $m --i8-digits $dg --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_n1_m${m}_d${dg}.json 2> gpurun_out/bench_c2_n1_m${m}_d${dg}.err; done; done
-  $B --config C3 --kern lin_mat52 --steps 5 --warmup 3 > gpurun_out/bench_c3_n1_lin_mat52.json 2> gpurun_out/bench_c3_n1_lin_mat52.err
-  $B --config C3 --kern lin_mat52 --tri-mode 0 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3_n1_lin_mat52_fp64.json 2> gpurun_out/bench_c3_n1_lin_mat52_fp64.err
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'tri_|kstar|ellipsoid_step|i8_guard' -c 300 --csv --log-file gpurun_out/launches_c2.csv $B --config C2 --steps 2 --warmup 2 --e2e-steps 1 --no-cpu-baseline --no-graph > gpurun_out/ncu_launches_c2.log 2>&1 ;;
+  for ss in 0 2 4; do $B --config C2 --substreams $ss --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_n1_ss${ss}.json 2> gpurun_out/bench_c2_n1_ss${ss}.err; done
+  SEGP_ELL_THREADS=32 $B --config C2 --substreams 4 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_n1_ss4_e32.json 2> gpurun_out/bench_c2_n1_ss4_e32.err
+  SEGP_ELL_THREADS=32 $B --config C2 --substreams 0 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_n1_ss0_e32.json 2> gpurun_out/bench_c2_n1_ss0_e32.err
+  timeout 600 python -m pytest tests/test_gpu_precision.py -m gpu -q -k "substream or graph" > gpurun_out/pytest_small.log 2>&1; tail -3 gpurun_out/pytest_small.log ;;
 ncu)
   NB="$B --scaling weak --steps 1 --warmup 2 --e2e-steps 1 --no-cpu-baseline --no-graph"
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'tri_|kstar|ellipsoid_step|i8_guard' -c 400 --csv --log-file gpurun_out/launches_c4.csv $NB > gpurun_out/ncu_launches.log 2>&1
