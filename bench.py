@@ -295,7 +295,6 @@ def run_product(args, rank, world, local_rank):
                                    src=0, device=local_rank, redundant=args.redundant_factor)
     torch.cuda.synchronize(dev)
     t_setup = time.perf_counter() - t_setup0
-    gp.set_option("overlap", 1 if args.overlap else 0)
     if args.ksplit > 0:
         gp.set_option("ksplit", args.ksplit)
     if args.i8_panel_group > 0:
@@ -471,7 +470,7 @@ def run_product(args, rank, world, local_rank):
                     "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
                     "algorithmic_flop_per_launch": flop_launch, "traffic": _traffic(args.config, mode, 0)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "tri_mode": {0: "fp64 DMMA", 1: "int8 digit planes on tcgen05 (single CTA), float64 recombination",
                          2: "int8 digit planes on tcgen05 (CTA pairs), float64 recombination",
@@ -494,8 +493,8 @@ def run_product(args, rank, world, local_rank):
                           "panels_recomputed_with_15_products": int(rep["fallback_panels"]),
                           "low_precision_flags": int((res.status & 8 != 0).sum().item())},
             "cuda_graph": {"enabled": bool(gp.get_option("graph")), "graphs_cached": int(gp.get_option("graphs_cached"))},
-            "schedule": ("two half-chunks software-pipelined over two streams (K*/ellipsoid kernels of one half under "
-                         "the contraction of the other)" if gp.get_option("overlap") and mode in (4, 5) else "serial"),
+            "schedule": "serial per chunk ({} sub-batch chain(s)), replayed as a CUDA graph".format(
+                2 if (gp.get_option("substreams") != 0 and gp.get_option("n_train_padded") <= 1024) else 1),
             "clocks": sampler.summary(t_wall0, t_wall1),
             "setup_s": t_setup, "bad_status": status_bad, "all_finite": finite}
     if world == 1 and not args.no_cpu_baseline:
@@ -555,9 +554,6 @@ def main():
     ap.add_argument("--ref-rollouts", type=int, default=2, help="rollouts per step of the reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", action="store_true",
-                    help="two-stream half-chunk pipeline instead of the serial kstar -> tri -> ellipsoid schedule "
-                         "(bit-identical; measured no faster, see DESIGN.md)")
     ap.add_argument("--tri-mode", type=int, default=-1, choices=[-1, 0, 1, 4, 5],
                     help="variance contraction pipe: -1 auto (int8 tcgen05 when possible), 0 fp64 DMMA, 1 int8 tcgen05 "
                          "reference kernel (one CTA per tile), 4 single-CTA MMAs over merged K* planes, W multicast "

@@ -338,7 +338,6 @@ int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, c
  *   same arguments on (read-only "graphs_cached");
  * "substreams": small models (<= 8 block rows of 128 training points) run a chunk as independent sub-batches on internal
  *   streams, because there every kernel is latency-bound and leaves most SMs idle (-1 automatic: 2; 0 off; n <= 4);
- * "overlap": 1 = run a chunk as two half-chunks software-pipelined over two internal streams (tri_mode 4/5);
  * "time_tri": 1 = bracket every contraction launch with a CUDA-event pair on its stream (resets the counters);
  * read-only: "launches" = kernels launched by this handle so far, "n_train_padded", "workspace_bytes",
  * "tri_launches" / "tri_ns" = number and total device nanoseconds of the timed contraction launches). */

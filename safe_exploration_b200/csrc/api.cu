@@ -171,14 +171,6 @@ struct segp_model {
                               // the probe did not ask for float64; else 0), 0 = fp64 DMMA, 1 = int8 reference kernel (one
                               // CTA per tile, classic set; test cross-check), 4 = tri_i8m (single-CTA MMAs over two K*
                               // planes at once, W multicast over a CTA pair), 5 = tri_i8mp (the same, persistent)
-    long opt_overlap = 0;     // 1 = software-pipeline two half-chunks over two internal streams (tri_mode 4 / 5): the
-                              // FP64-bound K* kernel of one half runs as a resident grid of small CTAs NEXT TO the
-                              // persistent contraction (tri_i8mp<4>) of the other.  Bit-identical.  The kernels do
-                              // share the SMs, but the co-resident K* kernel runs ~7x slower than alone and becomes the
-                              // critical path: 6 % slower than the serial schedule at C4, off by default
-                              // (profiles/round1/overlap_pipeline_c3_c4_c5.txt)
-    cudaStream_t s_hi = nullptr, s_lo = nullptr;   // internal streams of the pipelined driver (created on first use)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ks[2] = {nullptr, nullptr}, ev_tri[2] = {nullptr, nullptr};
     long long* i8_prof = nullptr;   // profiling only: [128][8] counters of the persistent kernel's MMA threads
     bool last_tri_persistent = false;   // which tcgen05 kernel the last contraction launch used (automatic mode)
     int last_tri_digits = 0;
@@ -411,7 +403,7 @@ static KstarArgs base_kstar_args(const segp_model* m) {
 }
 
 // K* block (+ mean / Jacobian partials) in the operand format of the active contraction kernel
-static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int panel0 = 0, bool coresident = false) {
+static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int panel0 = 0) {
     if (m->ws_mode != 0) {
         KstarI8Args k8{};
         k8.k = k;
@@ -420,7 +412,6 @@ static int run_kstar(segp_model* m, const KstarArgs& k, cudaStream_t st, int pan
         k8.colfac2 = m->colfac2;
         k8.xmax = m->xmax;
         k8.panel0 = panel0;
-        k8.resident_ctas = coresident ? 3 * 148 : 0;   // three small CTAs per SM next to the persistent contraction
         return launch_kstar_i8(k8, m->n_s, m->nsplit, st);
     }
     return launch_kstar(k, m->n_s, m->nsplit, st);
@@ -441,7 +432,7 @@ static TriI8Args tri_i8_args(const segp_model* m, long nb, int panel0, int digit
     t.epart = m->epart;
     t.nblk = m->nblk;
     t.npanels = (int)((nb + I8_N - 1) / I8_N);
-    t.panel0 = panel0;   // != 0 only from the pipelined driver
+    t.panel0 = panel0;   // != 0 for the sub-batch chains of small models
     // panels per L2 group of tri_i8m / tri_i8mp (0 = 24): a sweep over 8..24 at C4 and C5 moved the launch time by
     // less than 0.5 %, so there is no automatic choice
     t.pgroup = (int)m->opt_i8_panel_group;
@@ -457,7 +448,7 @@ static TriI8Args tri_i8_args(const segp_model* m, long nb, int panel0, int digit
 // tcgen05 kernels on the selected digit set followed -- for the 10-product set -- by the precision guard and the
 // recomputation of the flagged panels on the 15-product set.  Optionally bracketed by a CUDA-event pair on the
 // launching stream (bench.py: the pair spans the first pass only, the kernel the roofline is quoted for).
-static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool coresident = false) {
+static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->time_tri) {
         while (m->tri_events.size() < m->tri_events_used + 2) {
@@ -482,7 +473,6 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
             const long ntiles = (long)m->n_s * ((m->nblk + 1) / 2) * ((t.npanels + 1) / 2);
             persistent = m->nblk <= 32 && ntiles >= 4 * 74;
         }
-        if (coresident) persistent = true;   // the pipelined driver needs a resident contraction grid
         m->last_tri_persistent = persistent;
         m->last_tri_digits = digits;
         if (mode == 1) {
@@ -490,7 +480,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
             SEGP_CUDA_CHECK(cudaMemsetAsync(m->epart, 0, (size_t)m->n_s * m->nblk * m->b_cap * sizeof(float), st));
             SEGP_CHECK(launch_tri_i8(t, m->n_s, st));
         } else {
-            SEGP_CHECK(persistent ? launch_tri_i8mp(t, m->n_s, st, coresident) : launch_tri_i8m(t, m->n_s, st));
+            SEGP_CHECK(persistent ? launch_tri_i8mp(t, m->n_s, st) : launch_tri_i8m(t, m->n_s, st));
         }
         if (e1 != nullptr) SEGP_CUDA_CHECK(cudaEventRecord(e1, st));
         if (digits == 4 && m->opt_guard != 0 && m->force_digits == 0 && !(m->unguarded && m->opt_i8_digits == 0)) {
@@ -513,7 +503,7 @@ static int run_tri(segp_model* m, long nb, cudaStream_t st, int panel0 = 0, bool
             // not n_s x nblk x npanels launches of empty 220 KB CTAs
             TriI8Args t5 = tri_i8_args(m, nb, panel0, 5);
             t5.pflag = m->pflag;
-            SEGP_CHECK(launch_tri_i8mp(t5, m->n_s, st, false));
+            SEGP_CHECK(launch_tri_i8mp(t5, m->n_s, st));
             m->launches += 2;
         }
         return SEGP_OK;
@@ -625,10 +615,6 @@ int segp_destroy(segp_model* m) {
     if (m->ev_sub_fork != nullptr) cudaEventDestroy(m->ev_sub_fork);
     if (m->ev_chunk != nullptr) cudaEventDestroy(m->ev_chunk);
     for (cudaEvent_t e : m->tri_events) cudaEventDestroy(e);
-    for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_ks[0], m->ev_ks[1], m->ev_tri[0], m->ev_tri[1]})
-        if (e != nullptr) cudaEventDestroy(e);
-    if (m->s_hi != nullptr) cudaStreamDestroy(m->s_hi);
-    if (m->s_lo != nullptr) cudaStreamDestroy(m->s_lo);
     if (m->stage != nullptr) cudaFree(m->stage);
     delete m;
     return SEGP_OK;
@@ -1538,9 +1524,6 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         return s;
     };
 
-    const int npanels_first = (int)((std::min<long>(m->b_cap, n_batch) + I8_N - 1) / I8_N);
-    const bool pipelined_any = m->ws_mode != 0 && tri_mode(m) >= 4 && m->opt_overlap != 0 && npanels_first >= 48 &&
-                               m->n_pad >= 1024;
     const bool guarded = m->ws_mode != 0 && tri_mode(m) >= 4 && tri_digits(m) == 4 && m->opt_guard != 0 &&
                          !(m->unguarded && m->opt_i8_digits == 0);
     // The serial schedule: per chunk and step kstar -> contraction (+ guard + recomputation) -> ellipsoid step, every
@@ -1551,7 +1534,8 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
     // arithmetic per trajectory, disjoint parts of the workspace -- bit-identical results.  Measured at C2: 2 chains
     // 0.75 ms per call against 0.83 (one) and 0.82 (four: the contraction CTAs take a whole SM's shared memory each, so
     // more chains mostly queue) -- automatic mode uses two.  (Large models fill the GPU with every launch; there
-    // co-resident kernels only get in each other's way, see `overlap`.)
+    // co-resident kernels only get in each other's way: round 1's two-stream half-chunk pipeline ran the K* kernel 7x
+    // slower next to the contraction, profiles/round1/overlap_pipeline_c3_c4_c5.txt, and was retired.)
     auto sub_batches = [&](long nb) -> int {
         if (m->opt_substreams == 0 || m->ws_mode == 0 || m->nblk > 8) return 1;
         const long np = (nb + I8_N - 1) / I8_N;
@@ -1606,7 +1590,7 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         return SEGP_OK;
     };
     if (guarded) m->panels_prev_call = (long)horizon * ((n_batch + I8_N - 1) / I8_N);
-    if (!pipelined_any) {
+    {
         // K5: the 3 H launches of a call are replayed as ONE CUDA graph from the second call with the same
         // arguments on (a sampling-MPC loop re-uses its buffers); sizes where a launch costs as much as a kernel
         // (C2: 30 launches of ~10 us of work) are otherwise launch-bound.  First sight of an argument set: direct
@@ -1703,110 +1687,6 @@ int segp_multistep(segp_model* m, long n_batch, int horizon, const double* d_p0,
         return SEGP_OK;
     }
 
-    if (d_status != nullptr) SEGP_CUDA_CHECK(cudaMemsetAsync(d_status, 0, n_batch * sizeof(int32_t), st));
-    bool forked = false;
-    for (long c0 = 0; c0 < n_batch; c0 += m->b_cap) {
-        const long nb = std::min<long>(m->b_cap, n_batch - c0);
-        const int npanels = (int)((nb + I8_N - 1) / I8_N);
-        // Two half-chunks, software-pipelined over two internal streams: all contractions on the high-priority
-        // stream, back to back (tensor pipe), the K* / ellipsoid kernels of the OTHER half under them on the
-        // low-priority stream (FP64 pipe).  Within a half the order kstar -> tri -> ellipsoid -> kstar(t+1) is kept by
-        // events; the halves touch disjoint panel ranges of the workspace.  Same kernels, same arithmetic, same
-        // fixed-order reductions: results are bit-identical to the serial schedule.
-        const bool pipelined = npanels >= 48;
-        if (!pipelined) {
-            cudaStream_t s1 = forked ? m->s_lo : st;
-            for (int t = 0; t < horizon; ++t) {
-                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, nb), s1));
-                SEGP_CHECK(run_tri(m, nb, s1));
-                SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t, 0, nb), s1));
-                m->launches += 3;
-            }
-            continue;
-        }
-        if (m->s_hi == nullptr) {
-            int least = 0, greatest = 0;
-            SEGP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-            SEGP_CUDA_CHECK(cudaStreamCreateWithPriority(&m->s_hi, cudaStreamNonBlocking, greatest));
-            SEGP_CUDA_CHECK(cudaStreamCreateWithPriority(&m->s_lo, cudaStreamNonBlocking, least));
-            for (cudaEvent_t* e : {&m->ev_fork, &m->ev_join, &m->ev_ks[0], &m->ev_ks[1], &m->ev_tri[0], &m->ev_tri[1]})
-                SEGP_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        }
-        if (!forked) {
-            SEGP_CUDA_CHECK(cudaEventRecord(m->ev_fork, st));
-            SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_hi, m->ev_fork, 0));
-            SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_lo, m->ev_fork, 0));
-            forked = true;
-        }
-        // debugging aid (SEGP_TIMELINE=1): device timestamps of every launch of the first pipelined steps, on stderr
-        static const bool timeline = getenv("SEGP_TIMELINE") != nullptr;
-        struct Mark {
-            const char* what;
-            int t, h;
-            cudaEvent_t e0, e1;
-        };
-        std::vector<Mark> marks;
-        cudaEvent_t tl_base = nullptr;
-        auto mark_begin = [&](const char* what, int t, int h, cudaStream_t s) {
-            if (!timeline || t > 2) return;
-            Mark mk{what, t, h, nullptr, nullptr};
-            cudaEventCreate(&mk.e0);
-            cudaEventCreate(&mk.e1);
-            cudaEventRecord(mk.e0, s);
-            marks.push_back(mk);
-        };
-        auto mark_end = [&](int t, cudaStream_t s) {
-            if (!timeline || t > 2) return;
-            cudaEventRecord(marks.back().e1, s);
-        };
-        if (timeline) {
-            cudaEventCreate(&tl_base);
-            cudaEventRecord(tl_base, m->s_lo);
-        }
-        const int pa = ((npanels / 2 + 1) / 2) * 2;   // even, so the cluster pairs of the first half are complete
-        const int p_begin[2] = {0, pa}, p_end[2] = {pa, npanels};
-        const long b_begin[2] = {0, (long)pa * I8_N}, b_end[2] = {std::min<long>((long)pa * I8_N, nb), nb};
-        for (int t = 0; t <= horizon; ++t) {
-            for (int h = 0; h < 2; ++h) {
-                if (t > 0) {
-                    SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_lo, m->ev_tri[h], 0));
-                    mark_begin("ell", t - 1, h, m->s_lo);
-                    SEGP_CHECK(launch_ellipsoid_step(step_args(c0, t - 1, b_begin[h], b_end[h]), m->s_lo));
-                    mark_end(t - 1, m->s_lo);
-                    ++m->launches;
-                }
-                if (t == horizon) continue;
-                mark_begin("kstar", t, h, m->s_lo);
-                SEGP_CHECK(run_kstar(m, kstar_args(c0, t, b_end[h]), m->s_lo, p_begin[h], true));
-                mark_end(t, m->s_lo);
-                SEGP_CUDA_CHECK(cudaEventRecord(m->ev_ks[h], m->s_lo));
-                SEGP_CUDA_CHECK(cudaStreamWaitEvent(m->s_hi, m->ev_ks[h], 0));
-                mark_begin("tri", t, h, m->s_hi);
-                SEGP_CHECK(run_tri(m, (long)p_end[h] * I8_N, m->s_hi, p_begin[h], true));
-                mark_end(t, m->s_hi);
-                SEGP_CUDA_CHECK(cudaEventRecord(m->ev_tri[h], m->s_hi));
-                m->launches += 2;
-            }
-        }
-        if (timeline) {
-            cudaDeviceSynchronize();
-            for (const Mark& mk : marks) {
-                float t0 = 0.f, t1 = 0.f;
-                cudaEventElapsedTime(&t0, tl_base, mk.e0);
-                cudaEventElapsedTime(&t1, tl_base, mk.e1);
-                fprintf(stderr, "[segp timeline] %-5s step %d half %d: %8.3f -> %8.3f ms (%.3f)\n", mk.what, mk.t, mk.h, t0,
-                        t1, t1 - t0);
-                cudaEventDestroy(mk.e0);
-                cudaEventDestroy(mk.e1);
-            }
-            cudaEventDestroy(tl_base);
-        }
-    }
-    if (forked) {   // everything issued on s_hi has been waited for by s_lo
-        SEGP_CUDA_CHECK(cudaEventRecord(m->ev_join, m->s_lo));
-        SEGP_CUDA_CHECK(cudaStreamWaitEvent(st, m->ev_join, 0));
-    }
-    return SEGP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- host entry
@@ -2395,10 +2275,6 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_substreams = value;
         return SEGP_OK;
     }
-    if (strcmp(name, "overlap") == 0 && (value == 0 || value == 1)) {
-        m->opt_overlap = value;
-        return SEGP_OK;
-    }
     if (strcmp(name, "keep_w") == 0 && (value == 0 || value == 1)) {   // takes effect at the next segp_factorize
         m->opt_keep_w = value;
         if (value == 0) {
@@ -2439,7 +2315,6 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "i8_panel_group") == 0) *value = m->opt_i8_panel_group;
     else if (strcmp(name, "i8_cluster") == 0) *value = m->opt_i8_cluster;
     else if (strcmp(name, "tri_mode") == 0) *value = m->opt_tri_mode;
-    else if (strcmp(name, "overlap") == 0) *value = m->opt_overlap;
     else if (strcmp(name, "i8_prof_ptr") == 0) *value = (long)(uintptr_t)m->i8_prof;
     else if (strcmp(name, "tri_mode_effective") == 0) *value = tri_mode(m);
     else if (strcmp(name, "i8_digits") == 0) *value = m->opt_i8_digits;

@@ -115,7 +115,6 @@ struct KstarI8Args {
     double* colfac2;
     const double* xmax;
     int panel0;             // first panel of this launch (blockIdx.x counts from it): sub-chunk pipelining
-    int resident_ctas;      // > 0: run as a resident grid of this many small CTAs looping over the work items
 };
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st);
 
@@ -145,8 +144,7 @@ int launch_tri_i8(const TriI8Args& a, int n_s, cudaStream_t st);
 // single-CTA MMAs, two CTAs per cluster share one block row of W through multicast bulk copies
 int launch_tri_i8m(const TriI8Args& a, int n_s, cudaStream_t st);
 // persistent tri_i8m: one resident cluster per TPC walks a static list of folded (equal-length) tiles
-// leave_room: 4 epilogue warps instead of 12, so that two resident K* CTAs fit next to it on every SM
-int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_room = false);
+int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st);
 int tri_i8_init();
 // precision guard of the 10-product digit set (tri_i8.cu)
 struct GuardArgs {

@@ -223,7 +223,7 @@ __device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict
 }
 
 // 128 staged training points against one trajectory: kernel values -> digit bytes, mean / Jacobian sums.
-template <int DM, int KERN, int UNR, int ROWS, bool DIRECT = false>
+template <int DM, int KERN, int UNR, int ROWS>
 __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, const double* __restrict__ s_beta,
                                               const double* __restrict__ s_tab,
                                               const double (&zs)[DM], int dim, double var, int row0, int n_train,
@@ -261,7 +261,7 @@ __device__ __forceinline__ void kstar_i8_rows(const double* __restrict__ s_x, co
                 g = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
             }
             if (row0 + r + qd >= n_train || !active) unit = 0.0;   // padded rows / columns: zero digits
-            const double bt = DIRECT ? s_beta[r + qd] * var : s_beta[r + qd];   // beta_i sigma_f^2 (staged: multiplied once)
+            const double bt = s_beta[r + qd];   // beta_i sigma_f^2 (multiplied once when staged)
             mu = fma(bt, unit, mu);
             const double w = bt * g;
 #pragma unroll
@@ -465,23 +465,7 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
     const long half_off = 0;
     const long plane_stride = I8_B_TILE;
 
-    if (STAGE == 0) {
-        // no staging: every thread reads the training points straight through L1 (uniform addresses: one request per
-        // warp; the CTAs of an SM work on the same rows) -- no shared memory, no block barriers, loads of 16 points in
-        // flight per warp.  For the resident variant, whose global loads see long latencies next to the contraction.
-        for (int row0 = row_begin; row0 < row_end; row0 += TILE) {
-            const double* gx = a.xs + ((long)d * a.n_pad + row0) * dim;
-            const double* gb = a.beta + (long)d * a.n_pad + row0;
-            int8_t* kb_base = panel_base + half_off;
-            if (kern == SEGP_KERN_RBF)
-                kstar_i8_rows<DM, SEGP_KERN_RBF, 16, TILE, true>(gx, gb, s_tab, zs, dim, var, row0, a.n_train, active,
-                                                                 kb_base, rowp, plane_stride, mu, jac);
-            else
-                kstar_i8_rows<DM, SEGP_KERN_MAT52, 8, TILE, true>(gx, gb, s_tab, zs, dim, var, row0, a.n_train, active,
-                                                                  kb_base, rowp, plane_stride, mu, jac);
-        }
-    }
-    for (int row0 = row_begin; STAGE > 0 && row0 < row_end; row0 += (STAGE > 0 ? STAGE : TILE)) {
+    for (int row0 = row_begin; row0 < row_end; row0 += STAGE) {
         __syncthreads();
         const double* src = a.xs + ((long)d * a.n_pad + row0) * dim;
         for (int idx = threadIdx.x; idx < STAGE * dim; idx += I8_N) s_x[idx] = src[idx];
@@ -492,11 +476,11 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
         // instruction fetch (ncu: no_instruction 1.1 per issue).  16 independent points per iteration are needed
         // to cover the FP64 latency (a 4-point body ran 40 % slower).
         if (kern == SEGP_KERN_RBF)
-            kstar_i8_rows<DM, SEGP_KERN_RBF, 16, (STAGE > 0 ? STAGE : TILE)>(s_x, s_beta, s_tab, zs, dim, var, row0,
+            kstar_i8_rows<DM, SEGP_KERN_RBF, 16, STAGE>(s_x, s_beta, s_tab, zs, dim, var, row0,
                                                                              a.n_train, active, kb_base, rowp,
                                                                              plane_stride, mu, jac);
         else
-            kstar_i8_rows<DM, SEGP_KERN_MAT52, 8, (STAGE > 0 ? STAGE : TILE)>(s_x, s_beta, s_tab, zs, dim, var, row0,
+            kstar_i8_rows<DM, SEGP_KERN_MAT52, 8, STAGE>(s_x, s_beta, s_tab, zs, dim, var, row0,
                                                                               a.n_train, active, kb_base, rowp,
                                                                               plane_stride, mu, jac);
     }
@@ -544,26 +528,6 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
                              s_beta, s_tab);
 }
 
-// The same work as a RESIDENT grid (a few small CTAs per SM looping over the items) for the pipelined driver: without
-// staging a CTA needs no shared memory and 96 x 88 registers, so three of them fit on an SM NEXT TO a persistent
-// contraction CTA (tri_i8mp<4>: 223 KB, 192 threads) and run beside it; a resident grid leaves no pending blocks that
-// could take an SM's shared memory in the gap between two contraction kernels.
-__device__ double g_exp2_tab[64];   // 2^(j/64), filled by tri_i8_init: the resident variant reads it through L1 instead of
-                                    // spending 512 B of the ~9 KB of shared memory the contraction CTA leaves per SM
-__global__ void exp2_tab_kernel() { g_exp2_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0)); }
-template <int D_T>
-__global__ void __maxnreg__(88) kstar_i8_resident_kernel(const KstarI8Args aa, int n_s, int nsplit, int npanels) {
-    static_assert(D_T > 0, "resident variant is instantiated for compile-time input dimensions only");
-    const double* s_tab = g_exp2_tab;
-    const long n_items = (long)npanels * n_s * nsplit;
-    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int p = (int)(item % npanels);
-        const int d = (int)((item / npanels) % n_s);
-        const int split = (int)(item / ((long)npanels * n_s));
-        kstar_i8_item<D_T, 0>(aa, aa.panel0 + p, d, split, n_s, nullptr, nullptr, s_tab);
-    }
-}
-
 int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st) {
     // panels [panel0, ceil(n_batch / 96)): n_batch is the END of the trajectory range
     const int npanels = (int)((a.k.n_batch + I8_N - 1) / I8_N) - a.panel0;
@@ -584,37 +548,6 @@ int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st) 
         }
         SEGP_CUDA_CHECK(cudaGetLastError());
         if (all_comp) return SEGP_OK;
-    }
-    if (a.resident_ctas > 0) {
-        const long n_items = (long)npanels * n_s * nsplit;
-        const unsigned ctas = (unsigned)std::min<long>(a.resident_ctas, n_items);
-        switch (a.k.dim) {
-        // The contraction CTA it has to sit next to runs with the maximum shared-memory carve-out: ask for the same one,
-        // a kernel that prefers another L1 / shared split is not scheduled onto an SM until that SM drains.
-#define SEGP_KS8R_CASE(D) \
-    case D: {             \
-        static bool carveout_set = false;                                                                        \
-        if (!carveout_set) {                                                                                     \
-            SEGP_CUDA_CHECK(cudaFuncSetAttribute(kstar_i8_resident_kernel<D>,                                     \
-                                                 cudaFuncAttributePreferredSharedMemoryCarveout,                 \
-                                                 (int)cudaSharedmemCarveoutMaxShared));                          \
-            carveout_set = true;                                                                                 \
-        }                                                                                                        \
-        kstar_i8_resident_kernel<D><<<ctas, block, 0, st>>>(a, n_s, nsplit, npanels);                             \
-        SEGP_CUDA_CHECK(cudaGetLastError());                                                                     \
-        return SEGP_OK;                                                                                          \
-    }
-            SEGP_KS8R_CASE(2)
-            SEGP_KS8R_CASE(3)
-            SEGP_KS8R_CASE(4)
-            SEGP_KS8R_CASE(5)
-            SEGP_KS8R_CASE(6)
-            SEGP_KS8R_CASE(7)
-            SEGP_KS8R_CASE(8)
-#undef SEGP_KS8R_CASE
-            default:
-                break;   // other input dimensions: the ordinary grid below
-        }
     }
     switch (a.k.dim) {
 #define SEGP_KS8_CASE(D) \
@@ -1335,12 +1268,10 @@ __device__ __forceinline__ void mp_decode(long v, int nfold, int npairs, int PG2
     }
 }
 
-// EPI_WARPS = 12: one 32-column chunk per epilogue warp (448 threads, 128 registers: fills the register file);
-// EPI_WARPS = 4: one warp per TMEM lane quadrant walks the three chunks (192 threads): leaves registers and threads for
-// two resident K* CTAs per SM (kstar_i8_resident_kernel), used by the pipelined driver.
-template <int EPI_WARPS, bool SPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1) tri_i8mp_kernel(const TriI8Args a) {
-    static_assert(EPI_WARPS == 4 || EPI_WARPS == I8M_EPI_WARPS, "4 or 12 epilogue warps");
+// 12 epilogue warps: one 32-column chunk each (448 threads, 128 registers: fills the register file).
+template <bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_i8mp_kernel(const TriI8Args a) {
+    constexpr int EPI_WARPS = I8M_EPI_WARPS;
     const uint32_t rank = cluster_ctarank();
     const int cluster = blockIdx.x >> 1;
     const int nclusters = gridDim.x >> 1;
@@ -1460,28 +1391,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
                 const long grow = ((long)t.d * a.nblk + t.bi) * TILE + row;
                 const double rf = a.rowfac[grow];
                 const float we = a.epart != nullptr ? a.werr[grow] : -1.f;
-                if (EPI_WARPS == 4) {   // next to resident K* CTAs: sleep between polls instead of spinning on the barrier
-                    while (!mbar_test(tmem_full_bar, nsub & 1u)) __nanosleep(512);
-                } else {
-                    mbar_wait(tmem_full_bar, nsub & 1u);
-                }
+                mbar_wait(tmem_full_bar, nsub & 1u);
                 tc_fence_after();
                 double* col = s_col + (nsub & 1u) * (4 * I8_N);   // double-buffered: the next block row's epilogue may
                 float* ecol = s_ecol + (nsub & 1u) * (4 * I8_N);  // start while slow threads still read this one
-                if (EPI_WARPS == I8M_EPI_WARPS) {
+                {
                     const int chunk = (warp - 2) >> 2;
                     float es = 0.f;
                     col[q * I8_N + chunk * 32 + lane] =
                         i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane, we, es);
                     ecol[q * I8_N + chunk * 32 + lane] = es;
-                } else {
-#pragma unroll 1
-                    for (int chunk = 0; chunk < I8_N / 32; ++chunk) {
-                        float es = 0.f;
-                        col[q * I8_N + chunk * 32 + lane] =
-                            i8_epilogue_chunk_fast(tmem_base + ((uint32_t)(q * 32) << 16), chunk * 32, rf, lane, we, es);
-                        ecol[q * I8_N + chunk * 32 + lane] = es;
-                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1512,7 +1431,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
 
 constexpr size_t I8MP_SMEM = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 /* alignment slack */ + 2 * 4 * I8_N * 12 + 128;
 
-int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_room) {
+int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st) {
     const int nfold = (a.nblk + 1) / 2;
     const int npairs = (a.npanels - a.panel0 + 1) / 2;
     const long ntiles = (long)n_s * nfold * npairs;
@@ -1531,17 +1450,10 @@ int launch_tri_i8mp(const TriI8Args& a, int n_s, cudaStream_t st, bool leave_roo
     b.fix_bi = n_s;   // fix_bi (self-test tile selector of the other kernels) carries n_s into this one
     const bool split = a.digits == 4;
     const unsigned grid = (unsigned)(2 * nclusters);
-    if (leave_room) {
-        if (split)
-            tri_i8mp_kernel<4, true><<<grid, 64 + 32 * 4, I8MP_SMEM, st>>>(b);
-        else
-            tri_i8mp_kernel<4, false><<<grid, 64 + 32 * 4, I8MP_SMEM, st>>>(b);
-    } else {
-        if (split)
-            tri_i8mp_kernel<I8M_EPI_WARPS, true><<<grid, I8M_THREADS, I8MP_SMEM, st>>>(b);
-        else
-            tri_i8mp_kernel<I8M_EPI_WARPS, false><<<grid, I8M_THREADS, I8MP_SMEM, st>>>(b);
-    }
+    if (split)
+        tri_i8mp_kernel<true><<<grid, I8M_THREADS, I8MP_SMEM, st>>>(b);
+    else
+        tri_i8mp_kernel<false><<<grid, I8M_THREADS, I8MP_SMEM, st>>>(b);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }
@@ -1553,13 +1465,9 @@ int tri_i8_init() {
     SEGP_I8_ATTR((tri_i8m_kernel<2, true>), I8M_SMEM);
     SEGP_I8_ATTR((tri_i8m_kernel<4, false>), I8M_SMEM);
     SEGP_I8_ATTR((tri_i8m_kernel<4, true>), I8M_SMEM);
-    SEGP_I8_ATTR((tri_i8mp_kernel<I8M_EPI_WARPS, false>), I8MP_SMEM);
-    SEGP_I8_ATTR((tri_i8mp_kernel<I8M_EPI_WARPS, true>), I8MP_SMEM);
-    SEGP_I8_ATTR((tri_i8mp_kernel<4, false>), I8MP_SMEM);
-    SEGP_I8_ATTR((tri_i8mp_kernel<4, true>), I8MP_SMEM);
+    SEGP_I8_ATTR((tri_i8mp_kernel<false>), I8MP_SMEM);
+    SEGP_I8_ATTR((tri_i8mp_kernel<true>), I8MP_SMEM);
 #undef SEGP_I8_ATTR
-    exp2_tab_kernel<<<1, 64>>>();   // the device's exp2, as the shared-memory tables of the other K* kernels: same bits
-    SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }
 

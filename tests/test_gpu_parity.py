@@ -585,47 +585,6 @@ def test_rollout_is_deterministic_chunk_and_order_invariant(se):
     gp.close()
 
 
-def test_pipelined_half_chunk_schedule_is_bit_identical_to_serial(se, _tri_mode):
-    """The two-stream half-chunk pipeline of segp_multistep (option "overlap", tri_mode 4 only: K* and ellipsoid
-    kernels of one half under the contraction of the other) runs the same kernels on disjoint panel ranges: results
-    must equal the serial schedule bit for bit -- for an odd panel count, a ragged last panel, several chunks with
-    a short (serial) tail chunk -- and a subset must match the oracle."""
-    from oracle import reach_oracle
-    from oracle.gp_oracle import GPOracle
-    from safe_exploration_b200 import workloads
-    if _tri_mode != 4:
-        pytest.skip("the pipelined schedule exists for the tcgen05 path only")
-    batch = 51 * 96 + 17 + 700          # chunk 4992 = 52 panels (pipelined: 26 + 26), then a 621-trajectory tail (serial)
-    w = workloads.make("C3", batch=batch, n_train=1100, horizon=4)
-    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, w.x_train, w.y_train, kern_types=w.kern_types, hyp=w.hyp)
-    args = (w.l_mu, w.l_sigma, None, None, w.c_safety, w.a, w.b)
-    gp.set_option("chunk", 4992)
-    gp.set_option("overlap", 1)
-    gp.set_option("i8_digits", 5)       # no guard / recomputation launches: the launch arithmetic below counts 3 per step
-    n0 = gp.get_option("launches")
-    r1 = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
-    n1 = gp.get_option("launches")
-    gp.set_option("overlap", 0)
-    r0 = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
-    n2 = gp.get_option("launches")
-    assert n1 - n0 == 2 * 3 * w.horizon + 3 * w.horizon and n2 - n1 == 2 * 3 * w.horizon   # halves really ran
-    for name in ("p_all", "q_all", "var_all", "status"):
-        assert np.array_equal(getattr(r0, name), getattr(r1, name)), name
-    gp.set_option("overlap", 1)
-    gp.set_option("chunk", 8192)        # one chunk of 59 panels: 30 + 29
-    r2 = se.rollout(gp, w.p0, w.k_ff, w.k_fb, *args)
-    assert np.array_equal(r2.q_all, r0.q_all) and np.array_equal(r2.p_all, r0.p_all)
-    sel = np.r_[0:40, 26 * 96 - 20:26 * 96 + 20, 4992 - 20:4992 + 20, batch - 40:batch]
-    ora = GPOracle(w.x_train, w.y_train, w.kern_types, np.stack([h["lengthscale"] for h in w.hyp]),
-                   [h["variance"] for h in w.hyp], gp.total_noise())
-    p_o, q_o, v_o = reach_oracle.multistep_batch(w.p0, ora, w.k_fb, w.k_ff[sel], w.l_mu, w.l_sigma, None, w.c_safety,
-                                                 w.a, w.b)
-    _assert_close(r1.var_all[sel], v_o, 1e-6, atol_scale=1e-10, what="variance")
-    _assert_close(r1.q_all[sel], q_o, 1e-6, what="q_all")
-    _assert_close(r1.p_all[sel], p_o, 1e-6, what="p_all")
-    gp.close()
-
-
 def test_multistep_first_step_equals_onestep_and_horizon_prefix(se):
     """Structural property at any size: the first H' steps of an H-step rollout equal an H'-step rollout, and
     step t+1 equals onestep_reachability applied to step t's ellipsoid."""
