@@ -1039,9 +1039,10 @@ static int run_probe(segp_model* m, cudaStream_t st) {
     // segp_multistep (fallback_rate) catches a batch that lives where they do not.
     // Where the estimate stays 4x inside the tolerance on every probe the first pass runs unguarded: no guard and no
     // recomputation launch per step (the ellipsoid step still raises SEGP_STATUS_LOW_PRECISION on whatever exceeds the
-    // tolerance), which is what lets launch-bound small models use the 10-product set at all.
+    // tolerance).  Models below 1024 padded points stay on the 15-product set: their steps are launch-latency-bound
+    // (the contraction of C2 is 33 us whatever the digit set), so there is nothing to buy with the coarser digits.
     m->unguarded = ps[PS_MARGIN4] <= 0.25;
-    m->i8_primary = (m->unguarded || (ps[PS_FRAC4] <= 0.25 && m->n_pad >= 1024)) ? 4 : 5;
+    m->i8_primary = (ps[PS_FRAC4] <= 0.25 && m->n_pad >= 1024) ? 4 : 5;
     m->auto_fp64 = ps[PS_FRAC5] > 0.25;
     m->demoted = false;
     SEGP_CHECK(apply_calibration(m, st));
