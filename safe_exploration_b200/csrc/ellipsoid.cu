@@ -1,14 +1,18 @@
-// Per-trajectory ellipsoid calculus, one thread per trajectory, float64 in registers:
+// Per-trajectory ellipsoid calculus in float64:
 //   ellipsoid_step   body of onestep_reachability after the ssm(...) call (gp_reachability.py:75-88 point branch,
 //                    :102-156 set branch), with compute_remainder_overapproximations (utils.py:108-144),
 //                    ellipsoid_from_rectangle (utils_ellipsoid.py:197-233) and both sum_two_ellipsoids
 //                    (utils_ellipsoid.py:63-94) fused; optional GP-input transform (gp_reachability_casadi.py:60-98).
 //                    In the fused path it also finishes the GP posterior: fixed-order reduction of the mean /
-//                    Jacobian / |L^-1 k*|^2 partials written by kstar_mean_jac and tri_sumsq.
+//                    Jacobian / |L^-1 k*|^2 partials written by the K* and contraction kernels.
+//                    Two phases per block of 32 trajectories: (A) the partial sums, one warp per (output dimension,
+//                    quantity) with the trajectory index across the lanes (coalesced 256-byte rows, eight loads in
+//                    flight per lane), results parked in shared memory; (B) the algebra, one trajectory per lane of
+//                    warp 0, everything in registers.
 //   remainder, sum_two, from_rectangle, safety_distance : the batched leaves behind the Python mirrors of
 //                    utils.py / utils_ellipsoid.py / gp_reachability.py:215-250.
 // The reference takes max eig(Q (I + K^T K)) with a general eigen-solver (utils.py:133-134); Q B is similar to the
-// symmetric C^T Q C with B = C C^T, so a cyclic Jacobi iteration on that gives the same spectrum.
+// symmetric C^T Q C with B = C C^T, so a Jacobi iteration on that gives the same spectrum (n_s = 2: closed form).
 #include <math.h>
 
 #include "segp_internal.cuh"
@@ -18,6 +22,54 @@ namespace segp {
 // Small state dimensions are fully unrolled into registers; larger ones keep rolled loops over local-memory arrays
 // (the ellipsoid algebra is O(n_s^3) per trajectory-step against O(n_s N^2) for the GP, so it never matters).
 __host__ __device__ constexpr int unroll_factor(int n) { return n <= 4 ? 32 : 1; }
+
+// Branch-free reciprocal / reciprocal square root for the Jacobi rotations (MUFU seed, two Newton steps: ~1 ulp).
+// The IEEE division and square root of the compiler are 4x longer dependent chains with a slow-path branch each,
+// and the rotation parameters sit on the critical path of a latency-bound kernel; a rotation only has to be
+// orthogonal to rounding error, not correctly rounded.  Arguments here are positive and far from the subnormals.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+// Jacobi rotation annihilating m_pr: t = sgn(alpha) beta / (|alpha| + sqrt(alpha^2 + beta^2)), alpha = (m_rr - m_pp) / 2,
+// beta = m_pr (the textbook t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) without forming theta = alpha / beta).
+__device__ __forceinline__ void jacobi_cs(double app, double arr, double apr, double& cs, double& sn) {
+    const double alpha = 0.5 * (arr - app);
+    const double h2 = fma(alpha, alpha, apr * apr);
+    const double hyp = h2 * rsqrt_fast(h2);
+    double t = (alpha >= 0.0 ? apr : -apr) * rcp_fast(fabs(alpha) + hyp);
+    if (apr == 0.0) t = 0.0;   // nothing to annihilate (also alpha == beta == 0, where the line above is NaN)
+    cs = rsqrt_fast(fma(t, t, 1.0));
+    sn = t * cs;
+}
+template <int N>
+__device__ __forceinline__ void jacobi_apply(double (&m)[N][N], int p, int r, double cs, double sn) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double akp = m[k][p], akr = m[k][r];
+        m[k][p] = cs * akp - sn * akr;
+        m[k][r] = sn * akp + cs * akr;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double apk = m[p][k], ark = m[r][k];
+        m[p][k] = cs * apk - sn * ark;
+        m[r][k] = sn * apk + cs * ark;
+    }
+}
 
 // largest eigenvalue of Q (I + K^T K), Q symmetric positive semi-definite (n x n), K (n_u x n)
 template <int N, int NU>
@@ -89,6 +141,37 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
 #pragma unroll UF
         for (int j = 0; j < N; ++j)
             if (j < i) m[i][j] = m[j][i];
+    if constexpr (N == 2) {
+        // closed form: the larger root of the 2 x 2 characteristic polynomial (stable: both terms are >= 0)
+        const double hm = 0.5 * (m[0][0] + m[N - 1][N - 1]), hd = 0.5 * (m[0][0] - m[N - 1][N - 1]);
+        return hm + sqrt(fma(hd, hd, m[0][N - 1] * m[0][N - 1]));
+    }
+    if constexpr (N == 4) {
+        // Jacobi in the round-robin ordering: the two rotations of a round touch disjoint index pairs, so their
+        // parameters are computed side by side (two independent dependent chains in flight) and a sweep is three
+        // rounds deep instead of six rotations; padded rows / columns (n < 4) are zero and rotate as no-ops.
+        for (int sweep = 0; sweep < 30; ++sweep) {
+            double off = 0.0, dg = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                dg = fma(m[i][i], m[i][i], dg);
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    if (j > i) off = fma(m[i][j], m[i][j], off);
+            }
+            if (!(off > 1e-26 * dg)) break;   // relative off-diagonal norm < 1e-13; also exits on NaN / all-zero
+#pragma unroll
+            for (int round = 0; round < 3; ++round) {
+                const int p0 = 0, r0 = round + 1;
+                const int p1 = round == 0 ? 2 : 1, r1 = round == 2 ? 2 : 3;
+                double c0, s0, c1, s1;
+                jacobi_cs(m[p0][p0], m[r0][r0], m[p0][r0], c0, s0);
+                jacobi_cs(m[p1][p1], m[r1][r1], m[p1][r1], c1, s1);
+                jacobi_apply<N>(m, p0, r0, c0, s0);
+                jacobi_apply<N>(m, p1, r1, c1, s1);
+            }
+        }
+    } else {
     // cyclic Jacobi on the symmetric M (eigenvalues only)
     for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0, dg = 0.0;
@@ -107,10 +190,8 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
                 if (r > p && r < n) {
                     const double apq = m[p][r];
                     if (apq != 0.0) {
-                        const double theta = (m[r][r] - m[p][p]) / (2.0 * apq);
-                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-                        const double cs = 1.0 / sqrt(fma(tt, tt, 1.0));
-                        const double sn = tt * cs;
+                        double cs, sn;
+                        jacobi_cs(m[p][p], m[r][r], apq, cs, sn);
 #pragma unroll UF
                         for (int k = 0; k < N; ++k) {
                             const double akp = m[k][p], akr = m[k][r];
@@ -128,6 +209,7 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
             }
         }
     }
+    }
     double lam = m[0][0];
 #pragma unroll UF
     for (int i = 1; i < N; ++i)
@@ -137,40 +219,84 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
 
 // =========================================================================================== ellipsoid_step
 // NS/NU are compile-time capacities; n_s/n_u the run-time sizes (equal for the specialised instances).
+constexpr int ELL_TB = 32;      // trajectories per block: one per lane
+constexpr int ELL_WARPS = 8;    // warps of phase A
+
 template <int NS, int NU>
-__global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(const StepArgs a) {
     constexpr int UF = unroll_factor(NS);
-    const long b = a.b0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.n_batch) return;
+    extern __shared__ double ell_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long b = a.b0 + (long)blockIdx.x * ELL_TB + lane;
+    const bool live = b < a.n_batch;
     const int n_s = a.n_s, n_u = a.n_u, n_in = a.n_in;
     const int dim = n_in + n_u;
+    const bool fused = a.mu_part != nullptr;
+    double* s_mu = ell_smem;                  // [n_s][32]
+    double* s_qf = s_mu + n_s * ELL_TB;       // [n_s][32]  |L^-1 k*|^2
+    double* s_e2 = s_qf + n_s * ELL_TB;       // [n_s][32]  error-model variance of it (int8 contraction)
+    double* s_jac = s_e2 + n_s * ELL_TB;      // [n_s][dim][32]  final Jacobian entries (set branch only)
+
+    // ---- phase A (fused path): fixed-order sums of the partials, one warp per (d, quantity); a lane's loads do not
+    // depend on its running sum, so eight are in flight at a time
+    if (fused) {
+        const int per_d = 3 + (a.q != nullptr ? dim : 0);
+        for (int item = warp; item < n_s * per_d; item += ELL_WARPS) {
+            const int d = item / per_d, kind = item - d * per_d;
+            double acc = 0.0;
+            if (live) {
+                if (kind == 0) {
+#pragma unroll 8
+                    for (int s = 0; s < a.nsplit; ++s) acc += a.mu_part[((long)s * n_s + d) * a.b_cap + b];
+                } else if (kind == 1) {
+#pragma unroll 8
+                    for (int i = 0; i < a.nblk; ++i) acc += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
+                } else if (kind == 2) {
+                    if (a.epart != nullptr) {
+                        float e2 = 0.f;
+#pragma unroll 8
+                        for (int i = 0; i < a.nblk; ++i) e2 += a.epart[((long)d * a.nblk + i) * a.b_cap + b];
+                        acc = (double)e2;
+                    }
+                } else {
+                    const int j = kind - 3;
+                    double sum = 0.0;
+#pragma unroll 8
+                    for (int s = 0; s < a.nsplit; ++s) sum += a.jac_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
+                    acc = -sum * a.invls[d * dim + j];
+                    if (a.jac2_part != nullptr) {   // composite kernels: additive terms, final form
+                        double add = 0.0;
+#pragma unroll 8
+                        for (int s = 0; s < a.nsplit; ++s)
+                            add += a.jac2_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
+                        acc += add;
+                    }
+                }
+            }
+            double* dst = kind == 0 ? s_mu + d * ELL_TB
+                                    : kind == 1 ? s_qf + d * ELL_TB
+                                                : kind == 2 ? s_e2 + d * ELL_TB : s_jac + (d * dim + kind - 3) * ELL_TB;
+            dst[lane] = acc;
+        }
+        __syncthreads();
+    }
+    if (warp != 0 || !live) return;
+
+    // ---- phase B: one trajectory per lane
     const StepParams* __restrict__ sp = a.sp;
     int32_t status = 0;
-
-    // ---- GP posterior at the centre
     double mu[NS], var[NS];
 #pragma unroll UF
     for (int d = 0; d < NS; ++d) {
         mu[d] = 0.0;
         var[d] = 0.0;
         if (d < n_s) {
-            if (a.mu_part != nullptr) {
-                // partial sums in fixed order; the loads of 8 iterations are issued together (they do not depend on the
-                // running sum), which is what this latency-bound kernel is short of
-                double m = 0.0;
-#pragma unroll 8
-                for (int s = 0; s < a.nsplit; ++s) m += a.mu_part[((long)s * n_s + d) * a.b_cap + b];
-                double qf = 0.0;
-#pragma unroll 8
-                for (int i = 0; i < a.nblk; ++i) qf += a.qpart[((long)d * a.nblk + i) * a.b_cap + b];
-                mu[d] = m;
-                var[d] = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - qf;
-                if (a.epart != nullptr) {   // int8 contraction: a-posteriori error estimate against the variance
-                    float e2 = 0.f;
-#pragma unroll 8
-                    for (int i = 0; i < a.nblk; ++i) e2 += a.epart[((long)d * a.nblk + i) * a.b_cap + b];
-                    if (a.guard_gs * (double)e2 > var[d] * var[d]) status |= SEGP_STATUS_LOW_PRECISION;
-                }
+            if (fused) {
+                mu[d] = s_mu[d * ELL_TB + lane];
+                var[d] = (a.kss != nullptr ? a.kss[(long)d * a.b_cap + b] : a.gp_var[d]) - s_qf[d * ELL_TB + lane];
+                // int8 contraction: a-posteriori error estimate against the variance
+                if (a.epart != nullptr && a.guard_gs * s_e2[d * ELL_TB + lane] > var[d] * var[d])
+                    status |= SEGP_STATUS_LOW_PRECISION;
             } else {
                 mu[d] = a.mu_d[b * n_s + d];
                 var[d] = a.var_d[b * n_s + d];
@@ -246,24 +372,8 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
 #pragma unroll UF
                 for (int j = 0; j < NS + NU; ++j) {
                     jrow[j] = 0.0;
-                    if (j < dim) {
-                        if (a.mu_part != nullptr) {
-                            double acc = 0.0;
-#pragma unroll 8
-                            for (int s = 0; s < a.nsplit; ++s)
-                                acc += a.jac_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
-                            jrow[j] = -acc * a.invls[d * dim + j];
-                            if (a.jac2_part != nullptr) {   // composite kernels: additive terms, final form
-                                double add = 0.0;
-                                for (int s = 0; s < a.nsplit; ++s)
-                                    add += a.jac2_part[(((long)s * n_s + d) * dim + j) * a.b_cap + b];
-                                jrow[j] += add;
-                            }
-                        } else {
-                            jrow[j] = a.jac_d[(b * n_s + d) * dim + j];
-                        }
-                        if (mode == SEGP_PROP_MEAN_EQUIVALENT) jrow[j] = 0.0;   // no linearisation term
-                    }
+                    if (j < dim && mode != SEGP_PROP_MEAN_EQUIVALENT)   // mean equivalent: no linearisation term
+                        jrow[j] = fused ? s_jac[(d * dim + j) * ELL_TB + lane] : a.jac_d[(b * n_s + d) * dim + j];
                 }
 #pragma unroll UF
                 for (int j = 0; j < NS; ++j) {
@@ -386,31 +496,31 @@ __global__ void __launch_bounds__(64) ellipsoid_step_kernel(const StepArgs a) {
 }
 
 int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
-    // same shared-memory carve-out preference as the contraction kernels it may run next to (pipelined driver)
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        const int mx = (int)cudaSharedmemCarveoutMaxShared;
-        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    // shared memory of phase A: n_s (3 + dim) rows of 32 doubles (C4: 8 KB; the largest supported model: 108 KB)
+    constexpr int kMaxSmem = SEGP_MAX_NS * (3 + MAX_D) * ELL_TB * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<SEGP_MAX_NS, SEGP_MAX_NU>,
-                                             cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-        carveout_set = true;
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set = true;
     }
-    // latency-bound (a long dependent chain per trajectory, one trajectory per thread); one warp per block for small
-    // batches measured no faster (C2: 0.84 vs 0.83 ms per call)
-    const int threads = 64;
-    const unsigned grid = (unsigned)((a.n_batch - a.b0 + threads - 1) / threads);
+    if (a.n_batch <= a.b0) return SEGP_OK;
+    const int threads = ELL_TB * ELL_WARPS;
+    const unsigned grid = (unsigned)((a.n_batch - a.b0 + ELL_TB - 1) / ELL_TB);
+    const size_t smem = (size_t)a.n_s * (3 + a.n_in + a.n_u) * ELL_TB * sizeof(double);
     // the specialised instances hold a Jacobian row in NS + NU registers: a lifting input transform (n_in > n_s) does
     // not fit and takes the generic instance
     if (a.n_s == 2 && a.n_u == 1 && a.n_in <= 2)
-        ellipsoid_step_kernel<2, 1><<<grid, threads, 0, st>>>(a);
+        ellipsoid_step_kernel<2, 1><<<grid, threads, smem, st>>>(a);
     else if (a.n_s == 4 && a.n_u == 1 && a.n_in <= 4)
-        ellipsoid_step_kernel<4, 1><<<grid, threads, 0, st>>>(a);
+        ellipsoid_step_kernel<4, 1><<<grid, threads, smem, st>>>(a);
     else if (a.n_s <= 4 && a.n_u <= 2 && a.n_in <= 4)
-        ellipsoid_step_kernel<4, 2><<<grid, threads, 0, st>>>(a);
+        ellipsoid_step_kernel<4, 2><<<grid, threads, smem, st>>>(a);
     else
-        ellipsoid_step_kernel<SEGP_MAX_NS, SEGP_MAX_NU><<<grid, threads, 0, st>>>(a);
+        ellipsoid_step_kernel<SEGP_MAX_NS, SEGP_MAX_NU><<<grid, threads, smem, st>>>(a);
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
 }

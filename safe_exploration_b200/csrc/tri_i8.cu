@@ -516,8 +516,11 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_composite_kernel(const KstarI8A
     kstar_i8_composite<DM>(aa, zs, dim, d, (int)blockIdx.z, (int)gridDim.y, b, active, base, (int)threadIdx.x);
 }
 
+#ifndef SEGP_KS_MINB
+#define SEGP_KS_MINB 1   // tuning experiments: minimum resident blocks per SM (caps the registers)
+#endif
 template <int D_T>
-__global__ void __launch_bounds__(I8_N) kstar_i8_kernel(const KstarI8Args aa) {
+__global__ void __launch_bounds__(I8_N, SEGP_KS_MINB) kstar_i8_kernel(const KstarI8Args aa) {
     constexpr int DM = D_T > 0 ? D_T : MAX_D;
     __shared__ double s_x[TILE * DM];
     __shared__ double s_beta[TILE];
@@ -1278,6 +1281,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8M_THREADS, 1) tri_
     const int nfold = (a.nblk + 1) / 2;
     const int npairs = (a.npanels - a.panel0 + 1) / 2;
     const long ntiles = (long)a.fix_bi * nfold * npairs;    // fix_bi carries n_s (launch_tri_i8mp)
+
+    if (a.pflag != nullptr) {
+        // Precision fallback: the usual case is that the guard flagged nothing.  Every CTA reads the whole flag array
+        // once (<= a few hundred ints, coalesced) and leaves before TMEM allocation, barrier set-up and the cluster
+        // handshake; both CTAs of a cluster see the same flags, so they leave together.  Without this every role of
+        // every cluster walked its tile list with one dependent L2 read per tile pair (~0.1 ms per step at C4).
+        int any = 0;
+        for (int i = a.panel0 + (int)threadIdx.x; i < a.npanels; i += (int)blockDim.x) any |= a.pflag[i];
+        if (__syncthreads_or(any) == 0) return;
+    }
 
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_addr(smem_raw);
