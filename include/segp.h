@@ -318,6 +318,14 @@ int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double*
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum);
 
+/* Diagnostic: the float64-grade GEMM of the factorisation on tcgen05 (7 int8 digit planes per operand, 28 products;
+ * csrc/fact_i8.cu) on host matrices: C = alpha A op(B) + beta C, A m x k, B n x k (trans_b != 0) or k x n, C m x n, all
+ * row-major; m, n multiples of 128, k a multiple of 64; flags: 1 = A lower-triangular, 2 = B (k x n) lower-triangular,
+ * 4 = only tiles on or below the diagonal.  Used by the tests to pin the kernel against NumPy (the reference does
+ * these products inside LAPACK: GPy's Cholesky / woodbury_inv, ssm_gpy/gaussian_process.py:238-263). */
+int segp_i8_gemm_selftest(int device, int m, int n, int k, const double* h_a, const double* h_b, double* h_c, double alpha,
+                          double beta, int trans_b, int flags);
+
 /* Tuning knobs / introspection ("chunk": trajectories per workspace chunk, "panel_group", "ksplit",
  * "tri_mode": which kernel runs the variance contraction: -1 = automatic (default: int8 digit planes on tcgen05 when
  *   the padded training size is <= 16384, the kernels are not composite and the factorize-time probe did not find the

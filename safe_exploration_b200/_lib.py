@@ -100,6 +100,7 @@ PROTOTYPES = {
     "segp_i8_peak": (_int, [_int, _int, _int, ctypes.POINTER(_dbl)]),
     "segp_i8_peak_pattern": (_int, [_int, _int, _int, _int, ctypes.POINTER(_dbl)]),
     "segp_i8_selftest": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
+    "segp_i8_gemm_selftest": (_int, [_int, _int, _int, _int, _vp, _vp, _vp, _dbl, _dbl, _int, _int]),
     "segp_set_option": (_int, [_vp, ctypes.c_char_p, _long]),
     "segp_get_option": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_long)]),
     "segp_set_param": (_int, [_vp, ctypes.c_char_p, _dbl]),

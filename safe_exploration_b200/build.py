@@ -18,7 +18,7 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libsegp.so")
 
-SOURCES = ["api.cu", "predict.cu", "setup.cu", "ellipsoid.cu", "diag.cu", "tri_i8.cu", "score.cu", "select.cu"]
+SOURCES = ["api.cu", "predict.cu", "setup.cu", "ellipsoid.cu", "diag.cu", "tri_i8.cu", "fact_i8.cu", "score.cu", "select.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -56,7 +56,7 @@ def build_library(force=False, verbose=True):
     """Compile every .cu under csrc/ for sm_100a and link libsegp.so.  Returns the library path."""
     nvcc = _nvcc()
     os.makedirs(BUILD_DIR, exist_ok=True)
-    headers = [os.path.join(INCLUDE, "segp.h"), os.path.join(CSRC, "segp_internal.cuh")]
+    headers = [os.path.join(INCLUDE, "segp.h"), os.path.join(CSRC, "segp_internal.cuh"), os.path.join(CSRC, "tc_i8.cuh")]
     jobs = []
     objs = []
     for s in _sources():

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <new>
+#include <chrono>
 #include <vector>
 
 #include "segp_internal.cuh"
@@ -119,6 +120,8 @@ struct segp_model {
     double* kss = nullptr;         // workspace: [n_s][b_cap] prior variances
     double* wdense = nullptr;  // [n_s][n_pad][n_pad] W = L^-1 kept dense for segp_append (only if opt_keep_w)
     long opt_keep_w = 0;       // keep wdense after factorising (set by the first segp_append)
+    long opt_fact_i8 = -1;     // factorisation GEMMs on tcgen05 digit planes: -1 automatic (n_pad >= 1024), 0 off, 1 on
+    bool last_fact_i8 = false; // the last segp_factorize ran them there
     bool last_append_incremental = false;
     // precision management of the int8 path
     int i8_primary = 5;        // digit set of the first contraction pass: 4 (10 products) or 5 (15 products)
@@ -1064,6 +1067,18 @@ int segp_factorize(segp_model* m, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     m->factorized = false;
     free_graphs(m);
+    // host-side phase timer (SEGP_FACT_TIMING=1 prints it): where a factorisation's wall time goes
+    const bool timing = getenv("SEGP_FACT_TIMING") != nullptr;
+    auto now_ms = []() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    double t_phase = now_ms();
+    auto phase = [&](const char* what) {
+        if (!timing) return;
+        const double t = now_ms();
+        fprintf(stderr, "[segp_factorize] %-28s %8.2f ms\n", what, t - t_phase);
+        t_phase = t;
+    };
     SEGP_CHECK(alloc_arena(m));
     // the float64 operand: the probe's reference, and the contraction itself where the int8 path cannot run
     SEGP_CHECK(segp_alloc_fp64_operand(m));
@@ -1080,11 +1095,18 @@ int segp_factorize(segp_model* m, void* stream) {
     constexpr int FACT_SLOTS = 4;
     struct Slot {
         double *kbuf = nullptr, *wbuf = nullptr, *tmp = nullptr, *diag_inv = nullptr, *u_tmp = nullptr;
+        F7Scratch f7{nullptr, nullptr, nullptr, nullptr};
         cudaStream_t s = nullptr;
         cudaEvent_t done = nullptr;
     };
-    const int nslots = std::min(m->n_s, FACT_SLOTS);
+    int nslots = std::min(m->n_s, FACT_SLOTS);
+    if (const char* e = getenv("SEGP_FACT_SLOTS")) nslots = std::max(1, std::min(nslots, atoi(e)));   // tuning experiments
     Slot slots[FACT_SLOTS];
+    // dense GEMMs of potrf / trtri on the tensor cores (fact_i8.cu) where the model is large enough for the splits to
+    // pay (below ~1000 points the chain of 64 x 64 diagonal blocks sets the time, not the GEMMs)
+    const bool use_f7 = m->n_pad >= 512 && m->n_pad <= I8_MAX_NPAD &&
+                        (m->opt_fact_i8 == 1 || (m->opt_fact_i8 < 0 && m->n_pad >= 1024));
+    m->last_fact_i8 = use_f7;
     cudaEvent_t fork = nullptr;
     int* d_fail = nullptr;
     int rc = SEGP_OK;
@@ -1106,6 +1128,13 @@ int segp_factorize(segp_model* m, void* stream) {
             if ((rc = dev_alloc(&sl.tmp, nn)) != SEGP_OK) break;
             if ((rc = dev_alloc(&sl.diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
             if ((rc = dev_alloc(&sl.u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
+            if (use_f7) {
+                const size_t pb = f7_scratch_plane_bytes(m->n_pad);
+                if ((rc = dev_alloc(&sl.f7.ap, pb)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.f7.bp, pb)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.f7.as, (size_t)m->n_pad)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.f7.bs, (size_t)m->n_pad)) != SEGP_OK) break;
+            }
             if (cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess ||
                 cudaStreamWaitEvent(sl.s, fork, 0) != cudaSuccess) {
@@ -1114,6 +1143,7 @@ int segp_factorize(segp_model* m, void* stream) {
             }
         }
         if (rc != SEGP_OK) break;
+        phase("arena + scratch allocation");
         SetupDims sd{m->n_train, m->n_pad, m->dim};
         for (int d = 0; d < m->n_s && rc == SEGP_OK; ++d) {
             Slot& sl = slots[d % nslots];   // a slot's buffers are reused in stream order
@@ -1126,7 +1156,8 @@ int segp_factorize(segp_model* m, void* stream) {
                                   comp ? m->lin + (size_t)d * m->dim : nullptr, ss)) != SEGP_OK)
                 break;
             ++m->launches;
-            if ((rc = potrf_lower(sl.kbuf, m->n_pad, sl.diag_inv, d_fail + d, ss, &m->launches)) != SEGP_OK) break;
+            if ((rc = potrf_lower(sl.kbuf, m->n_pad, sl.diag_inv, d_fail + d, ss, &m->launches, use_f7 ? &sl.f7 : nullptr)) != SEGP_OK)
+                break;
             if ((rc = logdet_from_chol(sl.kbuf, m->n_train, m->n_pad, m->logdet + d, ss)) != SEGP_OK) break;
             ++m->launches;
             if (cudaMemsetAsync(wbuf, 0, nn * sizeof(double), ss) != cudaSuccess) {
@@ -1134,7 +1165,8 @@ int segp_factorize(segp_model* m, void* stream) {
                 rc = SEGP_ERR_CUDA;
                 break;
             }
-            if ((rc = trtri_lower(sl.kbuf, wbuf, m->n_pad, sl.diag_inv, sl.tmp, ss, &m->launches)) != SEGP_OK) break;
+            if ((rc = trtri_lower(sl.kbuf, wbuf, m->n_pad, sl.diag_inv, sl.tmp, ss, &m->launches, use_f7 ? &sl.f7 : nullptr)) != SEGP_OK)
+                break;
             if ((rc = solve_beta(wbuf, m->yp + (size_t)d * m->n_pad, sl.u_tmp, m->beta + (size_t)d * m->n_pad, m->n_pad,
                                  ss)) != SEGP_OK)
                 break;
@@ -1148,6 +1180,7 @@ int segp_factorize(segp_model* m, void* stream) {
             }
         }
         if (rc != SEGP_OK) break;
+        phase("enqueue (host)");
         for (int i = 0; i < nslots; ++i) {   // join
             if (cudaEventRecord(slots[i].done, slots[i].s) != cudaSuccess ||
                 cudaStreamWaitEvent(st, slots[i].done, 0) != cudaSuccess) {
@@ -1159,6 +1192,7 @@ int segp_factorize(segp_model* m, void* stream) {
         if (rc != SEGP_OK) break;
         if (m->has_composite && (rc = compute_xtb(m, st)) != SEGP_OK) break;
         cudaError_t e = cudaStreamSynchronize(st);
+        phase("wait for the GPU");
         if (e == cudaSuccess)
             e = cudaMemcpy(fails.data(), d_fail, m->n_s * sizeof(int), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {
@@ -1182,11 +1216,16 @@ int segp_factorize(segp_model* m, void* stream) {
         dev_free(sl.tmp);
         dev_free(sl.diag_inv);
         dev_free(sl.u_tmp);
+        dev_free(sl.f7.ap);
+        dev_free(sl.f7.bp);
+        dev_free(sl.f7.as);
+        dev_free(sl.f7.bs);
         if (sl.done != nullptr) cudaEventDestroy(sl.done);
         if (sl.s != nullptr) cudaStreamDestroy(sl.s);
     }
     if (fork != nullptr) cudaEventDestroy(fork);
     dev_free(d_fail);
+    phase("free scratch");
     if (rc != SEGP_OK) return rc;
     m->factorized = true;
     // calibrate the int8 error model and choose the digit set (needs the float64 operand as the reference)
@@ -1197,8 +1236,11 @@ int segp_factorize(segp_model* m, void* stream) {
             return rc;
         }
     }
+    phase("probe");
     if (!fp64_operand_needed(m)) dev_free(m->wt);
-    return write_meta(m);
+    const int rc_meta = write_meta(m);
+    phase("free fp64 operand + meta");
+    return rc_meta;
 }
 
 int segp_append(segp_model* m, int n_new, const double* h_x, const double* h_y, void* stream) {
@@ -2098,6 +2140,20 @@ int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double*
     return i8_peak(umma_n, iters, pattern, tops);
 }
 
+int segp_i8_gemm_selftest(int device, int m, int n, int k, const double* h_a, const double* h_b, double* h_c, double alpha,
+                          double beta, int trans_b, int flags) {
+    if (m < 1 || n < 1 || k < 1 || h_a == nullptr || h_b == nullptr || h_c == nullptr) {
+        set_error("segp_i8_gemm_selftest: bad argument");
+        return SEGP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("segp_i8_gemm_selftest: cudaSetDevice(%d) failed", device);
+        return SEGP_ERR_CUDA;
+    }
+    return gemm_i8x7_selftest(m, n, k, h_a, h_b, h_c, alpha, beta, trans_b, flags);
+}
+
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum) {
     // variant 1: reference kernel tri_i8; 4: tri_i8m on the classic set; 6: tri_i8m on the diagonal-split set -- all on
@@ -2276,6 +2332,10 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_substreams = value;
         return SEGP_OK;
     }
+    if (strcmp(name, "fact_i8") == 0 && value >= -1 && value <= 1) {   // takes effect at the next segp_factorize
+        m->opt_fact_i8 = value;
+        return SEGP_OK;
+    }
     if (strcmp(name, "keep_w") == 0 && (value == 0 || value == 1)) {   // takes effect at the next segp_factorize
         m->opt_keep_w = value;
         if (value == 0) {
@@ -2346,6 +2406,8 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "tri_persistent") == 0) *value = m->last_tri_persistent ? 1 : 0;
     else if (strcmp(name, "append_incremental") == 0) *value = m->last_append_incremental ? 1 : 0;
     else if (strcmp(name, "keep_w") == 0) *value = m->opt_keep_w;
+    else if (strcmp(name, "fact_i8") == 0) *value = m->opt_fact_i8;
+    else if (strcmp(name, "fact_i8_effective") == 0) *value = m->last_fact_i8 ? 1 : 0;
     else if (strcmp(name, "n_train") == 0) *value = m->n_train;
     else if (strcmp(name, "factorized") == 0) *value = m->factorized ? 1 : 0;
     else if (strcmp(name, "launches") == 0) *value = m->launches;

@@ -9,6 +9,8 @@
 // The factorisation must be float64: cond(K + noise I) ~ N s_f^2 / noise ~ 1e6..1e8 at the benchmark sizes.
 #include <math.h>
 
+#include <algorithm>
+
 #include "segp_internal.cuh"
 
 namespace segp {
@@ -101,9 +103,6 @@ int launch_xtb(const double* xraw, const double* beta, double* xtb, int n_pad, i
 //   batch  blockIdx.z: every pointer advances by z * zstride elements; M_z = min(M, m_total - z * zrows).
 // 64x64 tile, 4 warps (2x2) of 32x32 = 4x4 DMMA m8n8k4 tiles; operands staged in shared memory in fragment order
 // [k/4][row][k%4] so every fragment is one conflict-free LDS.64; global loads are register-prefetched one chunk ahead.
-constexpr int GEMM_A_LOWER = 1;
-constexpr int GEMM_B_LOWER = 2;
-constexpr int GEMM_C_LOWER = 4;
 constexpr int GT = 64;    // tile edge
 constexpr int GK = 16;    // k chunk
 
@@ -346,9 +345,15 @@ __global__ void __launch_bounds__(256) panel_trsm_kernel(double* __restrict__ a,
     }
 }
 
-int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_t st, long* launches) {
+// Two-level right-looking blocking when the tensor-core GEMM is available (f7 != NULL): 64-wide blocks are factorised
+// as before (potf2_inv, panel_trsm) but their float64 DMMA updates stay inside the current 256-wide panel; the rest of
+// the trailing matrix is updated once per panel, A22 -= P P^T with K = 256, on tcgen05 from digit planes of P
+// (fact_i8.cu): ~1 - 1.5 * 256 / n_pad of the factorisation's flops run on the tensor cores.
+int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_t st, long* launches,
+                const F7Scratch* f7) {
     const int nb = n_pad / NBLK;
     constexpr int kBlockSmem = 2 * NBLK * (NBLK + 1) * (int)sizeof(double);
+    constexpr int PANEL = 256;
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmem));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmem));
     SEGP_CUDA_CHECK(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
@@ -359,22 +364,48 @@ int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_
         if (rem <= 0) break;
         panel_trsm_kernel<<<rem, 256, kBlockSmem, st>>>(a, n_pad, kb, diag_inv);
         ++*launches;
-        // trailing update: A22 -= A21 A21^T (lower tiles only)
+        // trailing update: A22 -= A21 A21^T (lower tiles only); with f7 only up to the end of the 256-wide panel
         GemmArgs g{};
         const long off = ((long)kb + 1) * NBLK;
+        const long panel_end = std::min<long>(((long)kb * NBLK / PANEL + 1) * PANEL, n_pad);
         g.a = a + off * n_pad + (long)kb * NBLK;
         g.b = g.a;
         g.c = a + off * n_pad + off;
         g.lda = g.ldb = g.ldc = n_pad;
-        g.m = g.n = rem * NBLK;
+        g.m = rem * NBLK;
+        g.n = f7 != nullptr ? (int)(panel_end - off) : g.m;
         g.k = NBLK;
         g.alpha = -1.0;
         g.beta = 1.0;
         g.flags = GEMM_C_LOWER;
         g.m_total = g.m;
         g.zrows = 0;
-        SEGP_CHECK(launch_gemm64(g, true, 1, st));
-        ++*launches;
+        if (g.n > 0) {
+            SEGP_CHECK(launch_gemm64(g, true, 1, st));
+            ++*launches;
+        }
+        if (f7 != nullptr && off == panel_end && off < n_pad) {
+            // the panel [p0, off) is final below row off: digit planes of P = A[off:, p0:off], then the K = pw update
+            const long p0 = panel_end - PANEL < 0 ? 0 : ((long)kb * NBLK / PANEL) * PANEL;
+            const int pw = (int)(off - p0);
+            const int rows = (int)(n_pad - off);
+            SEGP_CHECK(f7_split(a + off * n_pad + p0, n_pad, 0, rows, pw, 0, 0, 0, 0, 0, 1, f7->as, f7->ap, st));
+            GemmI8Args t{};
+            t.ap = t.bp = f7->ap;
+            t.as = t.bs = f7->as;
+            t.a_kb = t.b_kb = pw / NBLK;
+            t.c = a + off * n_pad + off;
+            t.ldc = n_pad;
+            t.m = t.n = rows;
+            t.k = pw;
+            t.alpha = -1.0;
+            t.beta = 1.0;
+            t.flags = GEMM_C_LOWER;
+            t.m_total = rows;
+            t.zrows = 0;
+            SEGP_CHECK(launch_gemm_i8x7(t, 1, st));
+            *launches += 4;
+        }
     }
     SEGP_CUDA_CHECK(cudaGetLastError());
     return SEGP_OK;
@@ -389,7 +420,7 @@ __global__ void copy_diag_inv_kernel(double* __restrict__ w, int n_pad, const do
 }
 
 int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, double* tmp, cudaStream_t st,
-                long* launches) {
+                long* launches, const F7Scratch* f7) {
     const int nb = n_pad / NBLK;
     copy_diag_inv_kernel<<<nb, 256, 0, st>>>(w, n_pad, diag_inv);
     ++*launches;
@@ -398,6 +429,44 @@ int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, d
     //   W21 = -W22 T       (W22 lower)
     for (long s = NBLK; s < n_pad; s *= 2) {
         const int pairs = (int)((n_pad - s + 2 * s - 1) / (2 * s));   // pairs whose second block is non-empty
+        if (f7 != nullptr && s >= 256) {
+            // the same two products from digit planes on tcgen05 (fact_i8.cu); every operand is split with the exact
+            // max-abs of its rows over this level's k range as the scale
+            const long zs = 2 * s * ((long)n_pad + 1);
+            const int lim = (int)(n_pad - s), zr = (int)(2 * s), si = (int)s;
+            const long zplanes = (long)f7_plane_bytes(si, si, 1);
+            GemmI8Args t{};
+            t.ap = f7->ap;
+            t.as = f7->as;
+            t.bp = f7->bp;
+            t.bs = f7->bs;
+            t.a_kb = t.b_kb = si / NBLK;
+            t.ldc = n_pad;
+            t.m = t.n = t.k = si;
+            t.z_ap = t.z_bp = zplanes;
+            t.z_as = t.z_bs = s;
+            t.z_c = zs;
+            t.m_total = lim;
+            t.zrows = zr;
+            // T = L21 * W11: A = L21 (rows clipped in the last pair), B^T = W11^T (zero for k < n)
+            SEGP_CHECK(f7_split(l + s * n_pad, n_pad, zs, si, si, 0, 0, 1, lim, zr, pairs, f7->as, f7->ap, st));
+            SEGP_CHECK(f7_split(w, n_pad, zs, si, si, 1, 2, 0, 0, 0, pairs, f7->bs, f7->bp, st));
+            t.c = tmp + s * n_pad;
+            t.alpha = 1.0;
+            t.beta = 0.0;
+            t.flags = GEMM_B_LOWER;
+            SEGP_CHECK(launch_gemm_i8x7(t, pairs, st));
+            // W21 = -W22 * T: A = W22 (lower; rows and k clipped), B^T = T^T (k clipped)
+            SEGP_CHECK(f7_split(w + s * n_pad + s, n_pad, zs, si, si, 0, 1, 3, lim, zr, pairs, f7->as, f7->ap, st));
+            SEGP_CHECK(f7_split(tmp + s * n_pad, n_pad, zs, si, si, 1, 0, 2, lim, zr, pairs, f7->bs, f7->bp, st));
+            t.c = w + s * n_pad;
+            t.alpha = -1.0;
+            t.beta = 0.0;
+            t.flags = GEMM_A_LOWER;
+            SEGP_CHECK(launch_gemm_i8x7(t, pairs, st));
+            *launches += 14;
+            continue;
+        }
         GemmArgs g{};
         g.lda = g.ldb = g.ldc = n_pad;
         g.m = (int)s;

@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "segp_internal.cuh"
+#include "tc_i8.cuh"
 
 namespace segp {
 
@@ -50,12 +51,6 @@ __device__ __forceinline__ uint32_t split_digits_unit(double u, int& d0) {
     const uint32_t lo2 = lo + 0x80808080u;
     d0 = (int)(hi + (lo2 < lo ? 1u : 0u));
     return lo2 ^ 0x80808080u;
-}
-
-// byte offset of element (row, k) inside a K-major SWIZZLE_64B tile image (rows of 64 bytes, 16-byte chunks
-// XOR-ed with address bits [7,9) = (row >> 1) & 3)
-__host__ __device__ __forceinline__ int sw64_offset(int row, int k) {
-    return row * I8_KB + ((((k >> 4) ^ ((row >> 1) & 3)) << 4) | (k & 15));
 }
 
 // =========================================================================================== pack_w_i8
@@ -573,88 +568,6 @@ int launch_kstar_i8(const KstarI8Args& a, int n_s, int nsplit, cudaStream_t st) 
     return SEGP_OK;
 }
 
-// =========================================================================================== PTX helpers
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "I8_WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra I8_WAIT_DONE;\n"
-        "bra I8_WAIT_LOOP;\n"
-        "I8_WAIT_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// all prior tcgen05.mma of this thread complete -> one arrival on the mbarrier
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = 128, N from idesc, K = 32
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major SWIZZLE_64B operand descriptor: start address >> 4, LBO unused (0), SBO = 8 rows x 64 B = 512 B,
-// descriptor version 1 (sm_100), layout type 4 (SWIZZLE_64B)
-__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
-// instruction descriptor, kind::i8: D = s32, A = B = signed int8, both K-major, dense, no saturation
-__host__ __device__ constexpr uint32_t make_i8_idesc(int m, int n) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-// 32 lanes x 32 consecutive 32-bit columns of this warp's TMEM quadrant -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // =========================================================================================== epilogue helper
 // One warp, its 32 accumulator rows, 32 columns [col0, col0 + 32): recombine the I8_S diagonals
 //   v = sum_g C_g 256^(S-1-g)   as   ((C0 256 + C1) 256^2 + (C2 256 + C3)) 256 + C4
@@ -727,9 +640,6 @@ __device__ __forceinline__ double i8_epilogue_chunk(uint32_t tmem_quadrant_base,
 //   * int32 -> float64 without I2F (a quarter-rate conversion, and the int64 flavour is slower still): the bit pattern
 //     0x43300000:(x ^ 0x80000000) is 2^52 + 2^31 + x exactly, one full-rate DADD removes the bias;
 //   * 64 + 32 live registers instead of 192, which is what lets 448 threads fit the register file.
-__device__ __forceinline__ double i8_cvt_s32(uint32_t x) {
-    return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
-}
 // `werr` >= 0: also returns in `esum` this lane's column sum of werr_row * v^2 (float32: it is an error estimate).
 __device__ __forceinline__ double i8_epilogue_chunk_fast(uint32_t tmem_quadrant_base, int col0, double rf, int lane,
                                                          float werr, float& esum) {
