@@ -122,6 +122,17 @@ struct segp_model {
     long opt_keep_w = 0;       // keep wdense after factorising (set by the first segp_append)
     long opt_fact_i8 = -1;     // factorisation GEMMs on tcgen05 digit planes: -1 automatic (n_pad >= 1024), 0 off, 1 on
     bool last_fact_i8 = false; // the last segp_factorize ran them there
+    // scratch of segp_factorize kept between calls (an MPC loop refits the same-size model every step; allocating and
+    // freeing ~3 GB costs as much as the factorisation itself): up to 4 slots; option "scratch_cache" -1 = keep when
+    // it is <= 4 GB, 0 = never, 1 = always
+    struct FactScratch {
+        double *kbuf = nullptr, *wbuf = nullptr, *tmp = nullptr, *diag_inv = nullptr, *u_tmp = nullptr;
+        F7Scratch f7{nullptr, nullptr, nullptr, nullptr};
+    };
+    FactScratch fact_cache[4];
+    int fact_cache_npad = 0, fact_cache_slots = 0;
+    bool fact_cache_f7 = false, fact_cache_w = false;
+    long opt_scratch_cache = -1;
     bool last_append_incremental = false;
     // precision management of the int8 path
     int i8_primary = 5;        // digit set of the first contraction pass: 4 (10 products) or 5 (15 products)
@@ -225,6 +236,21 @@ static void free_model_buffers(segp_model* m) {
     dev_free(m->xmax);
     m->has_linear_terms = false;
     m->factorized = false;
+}
+
+static void free_fact_cache(segp_model* m) {
+    for (auto& c : m->fact_cache) {
+        dev_free(c.kbuf);
+        dev_free(c.wbuf);
+        dev_free(c.tmp);
+        dev_free(c.diag_inv);
+        dev_free(c.u_tmp);
+        dev_free(c.f7.ap);
+        dev_free(c.f7.bp);
+        dev_free(c.f7.as);
+        dev_free(c.f7.bs);
+    }
+    m->fact_cache_npad = m->fact_cache_slots = 0;
 }
 
 static void free_workspace(segp_model* m) {
@@ -604,6 +630,7 @@ int segp_destroy(segp_model* m) {
     cudaDeviceSynchronize();
     free_model_buffers(m);
     free_workspace(m);
+    free_fact_cache(m);
     dev_free(m->d_sp);
     dev_free(m->i8_prof);
     dev_free(m->fallback_counter);
@@ -1093,9 +1120,7 @@ int segp_factorize(segp_model* m, void* stream) {
     // block wide (the 64 x 64 diagonal blocks): up to FACT_SLOTS of them run concurrently on their own streams, each
     // with its own scratch, so the latency-bound launches of one overlap the GEMMs of the others.
     constexpr int FACT_SLOTS = 4;
-    struct Slot {
-        double *kbuf = nullptr, *wbuf = nullptr, *tmp = nullptr, *diag_inv = nullptr, *u_tmp = nullptr;
-        F7Scratch f7{nullptr, nullptr, nullptr, nullptr};
+    struct Slot : segp_model::FactScratch {
         cudaStream_t s = nullptr;
         cudaEvent_t done = nullptr;
     };
@@ -1111,6 +1136,20 @@ int segp_factorize(segp_model* m, void* stream) {
     int* d_fail = nullptr;
     int rc = SEGP_OK;
     std::vector<int> fails(m->n_s, 0);
+    // scratch kept from the previous factorisation of a same-size model
+    const bool need_w = !m->opt_keep_w;
+    const bool cache_hit = m->fact_cache_npad == m->n_pad && m->fact_cache_slots >= nslots && m->fact_cache_f7 == use_f7 &&
+                           m->fact_cache_w == need_w;
+    if (cache_hit) {
+        for (int i = 0; i < nslots; ++i) {
+            static_cast<segp_model::FactScratch&>(slots[i]) = m->fact_cache[i];
+            m->fact_cache[i] = segp_model::FactScratch();
+        }
+    }
+    if (!cache_hit || m->fact_cache_slots > nslots) free_fact_cache(m);
+    m->fact_cache_npad = m->fact_cache_slots = 0;
+    const size_t slot_bytes = (3 * nn + (size_t)nb64 * NBLK * NBLK + 33 * (size_t)m->n_pad) * sizeof(double) +
+                              (use_f7 ? 2 * f7_scratch_plane_bytes(m->n_pad) + 2 * m->n_pad * sizeof(double) : 0);
     do {
         if (m->opt_keep_w && m->wdense == nullptr && (rc = dev_alloc(&m->wdense, (size_t)m->n_s * nn)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_fail, (size_t)m->n_s)) != SEGP_OK) break;
@@ -1123,12 +1162,14 @@ int segp_factorize(segp_model* m, void* stream) {
         }
         for (int i = 0; i < nslots && rc == SEGP_OK; ++i) {
             Slot& sl = slots[i];
+            if (!cache_hit) {
             if ((rc = dev_alloc(&sl.kbuf, nn)) != SEGP_OK) break;
-            if (!m->opt_keep_w && (rc = dev_alloc(&sl.wbuf, nn)) != SEGP_OK) break;
+            if (need_w && (rc = dev_alloc(&sl.wbuf, nn)) != SEGP_OK) break;
             if ((rc = dev_alloc(&sl.tmp, nn)) != SEGP_OK) break;
             if ((rc = dev_alloc(&sl.diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
             if ((rc = dev_alloc(&sl.u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
-            if (use_f7) {
+            }
+            if (use_f7 && !cache_hit) {
                 const size_t pb = f7_scratch_plane_bytes(m->n_pad);
                 if ((rc = dev_alloc(&sl.f7.ap, pb)) != SEGP_OK) break;
                 if ((rc = dev_alloc(&sl.f7.bp, pb)) != SEGP_OK) break;
@@ -1209,6 +1250,18 @@ int segp_factorize(segp_model* m, void* stream) {
             }
     } while (0);
     cudaDeviceSynchronize();
+    const bool keep_scratch = rc == SEGP_OK && (m->opt_scratch_cache == 1 ||
+                                                (m->opt_scratch_cache < 0 && (size_t)nslots * slot_bytes <= ((size_t)4 << 30)));
+    if (keep_scratch) {
+        for (int i = 0; i < nslots; ++i) {
+            m->fact_cache[i] = static_cast<segp_model::FactScratch&>(slots[i]);
+            static_cast<segp_model::FactScratch&>(slots[i]) = segp_model::FactScratch();
+        }
+        m->fact_cache_npad = m->n_pad;
+        m->fact_cache_slots = nslots;
+        m->fact_cache_f7 = use_f7;
+        m->fact_cache_w = need_w;
+    }
     for (int i = 0; i < FACT_SLOTS; ++i) {
         Slot& sl = slots[i];
         dev_free(sl.kbuf);
@@ -2332,6 +2385,15 @@ int segp_set_option(segp_model* m, const char* name, long value) {
         m->opt_substreams = value;
         return SEGP_OK;
     }
+    if (strcmp(name, "scratch_cache") == 0 && value >= -1 && value <= 1) {
+        m->opt_scratch_cache = value;
+        if (value == 0) {
+            DeviceGuard guard(m->device);
+            cudaDeviceSynchronize();
+            free_fact_cache(m);
+        }
+        return SEGP_OK;
+    }
     if (strcmp(name, "fact_i8") == 0 && value >= -1 && value <= 1) {   // takes effect at the next segp_factorize
         m->opt_fact_i8 = value;
         return SEGP_OK;
@@ -2407,6 +2469,16 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
     else if (strcmp(name, "append_incremental") == 0) *value = m->last_append_incremental ? 1 : 0;
     else if (strcmp(name, "keep_w") == 0) *value = m->opt_keep_w;
     else if (strcmp(name, "fact_i8") == 0) *value = m->opt_fact_i8;
+    else if (strcmp(name, "scratch_cache") == 0) *value = m->opt_scratch_cache;
+    else if (strcmp(name, "scratch_cached_bytes") == 0) {
+        *value = 0;
+        if (m->fact_cache_slots > 0) {
+            const size_t nn = (size_t)m->fact_cache_npad * m->fact_cache_npad;
+            size_t b = ((m->fact_cache_w ? 3 : 2) * nn + nn / NBLK * NBLK + 33 * (size_t)m->fact_cache_npad) * sizeof(double);
+            if (m->fact_cache_f7) b += 2 * f7_scratch_plane_bytes(m->fact_cache_npad) + 2 * m->fact_cache_npad * sizeof(double);
+            *value = (long)(b * m->fact_cache_slots);
+        }
+    }
     else if (strcmp(name, "fact_i8_effective") == 0) *value = m->last_fact_i8 ? 1 : 0;
     else if (strcmp(name, "n_train") == 0) *value = m->n_train;
     else if (strcmp(name, "factorized") == 0) *value = m->factorized ? 1 : 0;

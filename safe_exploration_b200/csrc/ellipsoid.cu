@@ -23,27 +23,6 @@ namespace segp {
 // (the ellipsoid algebra is O(n_s^3) per trajectory-step against O(n_s N^2) for the GP, so it never matters).
 __host__ __device__ constexpr int unroll_factor(int n) { return n <= 4 ? 32 : 1; }
 
-// Branch-free reciprocal / reciprocal square root for the Jacobi rotations (MUFU seed, two Newton steps: ~1 ulp).
-// The IEEE division and square root of the compiler are 4x longer dependent chains with a slow-path branch each,
-// and the rotation parameters sit on the critical path of a latency-bound kernel; a rotation only has to be
-// orthogonal to rounding error, not correctly rounded.  Arguments here are positive and far from the subnormals.
-__device__ __forceinline__ double rcp_fast(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
-__device__ __forceinline__ double rsqrt_fast(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 0.5 * x;
-    double e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
-    return fma(y, e, y);
-}
 // Jacobi rotation annihilating m_pr: t = sgn(alpha) beta / (|alpha| + sqrt(alpha^2 + beta^2)), alpha = (m_rr - m_pp) / 2,
 // beta = m_pr (the textbook t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) without forming theta = alpha / beta).
 __device__ __forceinline__ void jacobi_cs(double app, double arr, double apr, double& cs, double& sn) {

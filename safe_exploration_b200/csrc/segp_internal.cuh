@@ -44,6 +44,31 @@ struct StepParams {
     int prop_mode;   // SEGP_PROP_*
 };
 
+#ifdef __CUDACC__
+// Branch-free reciprocal / reciprocal square root (MUFU seed, two Newton steps: ~1 ulp) for the latency-bound chains:
+// the Jacobi rotations of the ellipsoid step and the pivots of the 64 x 64 diagonal-block Cholesky.
+// The IEEE division and square root of the compiler are 4x longer dependent chains with a slow-path branch each,
+// and the rotation parameters sit on the critical path of a latency-bound kernel; a rotation only has to be
+// orthogonal to rounding error, not correctly rounded.  Arguments here are positive and far from the subnormals.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+#endif
+
 // ---------------------------------------------------------------- kernel-matrix block + mean/Jacobian partials
 struct KstarArgs {
     const double* xs;       // [n_s][Np][D]  training inputs scaled by 1/lengthscale_d

@@ -265,12 +265,21 @@ static int launch_gemm64(const GemmArgs& g, bool trans_b, int batch, cudaStream_
 }
 
 // =========================================================================================== potrf
-// Diagonal block: unblocked Cholesky of the 64x64 block in shared memory + its explicit inverse.
+// Diagonal block: Cholesky of the 64 x 64 block in shared memory + its explicit inverse.  This kernel is one CTA on the
+// critical path of the whole factorisation (n_pad / 64 of them in a row), so it is written for latency:
+//   factor   right-looking, ONE barrier per column: the pivot's reciprocal square root is computed redundantly by
+//            every thread (MUFU + two Newton steps), the scaled column goes to a second array (nobody waits for it),
+//            the rank-1 update reads the unscaled column;
+//   inverse  the two 32 x 32 diagonal blocks side by side (row by row, 4 lanes per entry + shuffle reduction), then
+//            X21 = -X22 (L21 X11) as two 32^3 products over all 256 threads.
+// (round 1: 77 us per block, three barriers per column and a one-thread-per-column substitution.)
 __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ a, int n_pad, int kb,
                                                         double* __restrict__ diag_inv, int* __restrict__ fail) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    double(*s)[NBLK + 1] = reinterpret_cast<double(*)[NBLK + 1]>(dyn_smem);
-    double(*x)[NBLK + 1] = s + NBLK;
+    double(*s)[NBLK + 1] = reinterpret_cast<double(*)[NBLK + 1]>(dyn_smem);   // A, updated in place; later T
+    double(*l)[NBLK + 1] = s + NBLK;                                          // L
+    double(*x)[NBLK + 1] = l + NBLK;                                          // L^-1
+    __shared__ double s_dinv[NBLK];
     __shared__ int s_fail;
     const int tid = threadIdx.x;
     double* blk = a + ((long)kb * NBLK) * n_pad + (long)kb * NBLK;
@@ -278,43 +287,58 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ a, 
     for (int idx = tid; idx < NBLK * NBLK; idx += 256) {
         const int r = idx / NBLK, c = idx % NBLK;
         s[r][c] = (c <= r) ? blk[(long)r * n_pad + c] : 0.0;
+        l[r][c] = 0.0;
+        x[r][c] = 0.0;
     }
     __syncthreads();
     const int row = tid & 63, part = tid >> 6;
     for (int j = 0; j < NBLK; ++j) {
-        if (tid == 0) {
-            const double d = s[j][j];
-            if (!(d > 0.0)) {
-                s_fail = kb * NBLK + j + 1;
-                s[j][j] = 1.0;
-            } else {
-                s[j][j] = sqrt(d);
+        const double d = s[j][j];
+        const bool bad = !(d > 0.0);
+        if (bad && tid == 0) s_fail = kb * NBLK + j + 1;
+        const double rinv = bad ? 1.0 : rsqrt_fast(d);
+        if (row >= j) {
+            const double lij = (row == j) ? (bad ? 1.0 : d * rinv) : s[row][j] * rinv;
+            if (part == 0) {
+                l[row][j] = lij;
+                if (row == j) s_dinv[j] = rinv;
             }
-        }
-        __syncthreads();
-        if (tid > j && tid < NBLK) s[tid][j] /= s[j][j];
-        __syncthreads();
-        if (row > j) {
-            const double lij = s[row][j];
-            for (int k = j + 1 + part; k <= row; k += 4) s[row][k] = fma(-lij, s[k][j], s[row][k]);
+            for (int k = j + 1 + part; k <= row; k += 4) s[row][k] = fma(-lij, s[k][j] * rinv, s[row][k]);
         }
         __syncthreads();
     }
-    // inverse, one column per thread (forward substitution)
-    if (tid < NBLK) {
-        const int c = tid;
-        for (int i = 0; i < c; ++i) x[i][c] = 0.0;
-        x[c][c] = 1.0 / s[c][c];
-        for (int i = c + 1; i < NBLK; ++i) {
+    // inverse of the two diagonal 32 x 32 blocks: group g = tid / 128, lane quad = 4 partial sums of one column
+    {
+        const int g = tid >> 7, t = tid & 127;
+        const int c = t >> 2, p4 = t & 3;            // column within the block, partial-sum index
+        const int o = g * 32;
+        for (int i = 0; i < 32; ++i) {
             double acc = 0.0;
-            for (int k = c; k < i; ++k) acc = fma(s[i][k], x[k][c], acc);
-            x[i][c] = -acc / s[i][i];
+            for (int k = c + p4; k < i; k += 4) acc = fma(l[o + i][o + k], x[o + k][o + c], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (p4 == 0 && c <= i) x[o + i][o + c] = (c == i) ? s_dinv[o + i] : -acc * s_dinv[o + i];
+            __syncthreads();
         }
+    }
+    // T = L21 X11 (X11 lower: k >= c) into s[0..31][0..31]; then X21 = -X22 T (X22 lower: k <= r)
+    for (int idx = tid; idx < 32 * 32; idx += 256) {
+        const int r = idx >> 5, c = idx & 31;
+        double acc = 0.0;
+        for (int k = c; k < 32; ++k) acc = fma(l[32 + r][k], x[k][c], acc);
+        s[r][c] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 32 * 32; idx += 256) {
+        const int r = idx >> 5, c = idx & 31;
+        double acc = 0.0;
+        for (int k = 0; k <= r; ++k) acc = fma(x[32 + r][32 + k], s[k][c], acc);
+        x[32 + r][c] = -acc;
     }
     __syncthreads();
     for (int idx = tid; idx < NBLK * NBLK; idx += 256) {
         const int r = idx / NBLK, c = idx % NBLK;
-        if (c <= r) blk[(long)r * n_pad + c] = s[r][c];
+        if (c <= r) blk[(long)r * n_pad + c] = l[r][c];
         diag_inv[(long)kb * NBLK * NBLK + idx] = x[r][c];
     }
     if (tid == 0 && s_fail != 0) atomicCAS(fail, 0, s_fail);
@@ -353,12 +377,13 @@ int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_
                 const F7Scratch* f7) {
     const int nb = n_pad / NBLK;
     constexpr int kBlockSmem = 2 * NBLK * (NBLK + 1) * (int)sizeof(double);
+    constexpr int kPotf2Smem = 3 * NBLK * (NBLK + 1) * (int)sizeof(double);
     constexpr int PANEL = 256;
-    SEGP_CUDA_CHECK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmem));
+    SEGP_CUDA_CHECK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotf2Smem));
     SEGP_CUDA_CHECK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmem));
     SEGP_CUDA_CHECK(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
     for (int kb = 0; kb < nb; ++kb) {
-        potf2_inv_kernel<<<1, 256, kBlockSmem, st>>>(a, n_pad, kb, diag_inv, d_fail);
+        potf2_inv_kernel<<<1, 256, kPotf2Smem, st>>>(a, n_pad, kb, diag_inv, d_fail);
         ++*launches;
         const int rem = nb - kb - 1;
         if (rem <= 0) break;
