@@ -318,7 +318,7 @@ int segp_i8_peak_pattern(int device, int umma_n, int pattern, int iters, double*
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
                      double* h_colsum);
 
-/* Diagnostic: the float64-grade GEMM of the factorisation on tcgen05 (7 int8 digit planes per operand, 28 products;
+/* Diagnostic: the float64-grade GEMM of the factorisation on tcgen05 (8 int8 digit planes per operand, 36 products;
  * csrc/fact_i8.cu) on host matrices: C = alpha A op(B) + beta C, A m x k, B n x k (trans_b != 0) or k x n, C m x n, all
  * row-major; m, n multiples of 128, k a multiple of 64; flags: 1 = A lower-triangular, 2 = B (k x n) lower-triangular,
  * 4 = only tiles on or below the diagonal.  Used by the tests to pin the kernel against NumPy (the reference does
@@ -346,6 +346,13 @@ int segp_i8_gemm_selftest(int device, int m, int n, int k, const double* h_a, co
  *   same arguments on (read-only "graphs_cached");
  * "substreams": small models (<= 8 block rows of 128 training points) run a chunk as independent sub-batches on internal
  *   streams, because there every kernel is latency-bound and leaves most SMs idle (-1 automatic: 2; 0 off; n <= 4);
+ * "fact_i8": the dense GEMMs of segp_factorize (trailing updates of potrf with K = 256, the block products of trtri from
+ *   256-row blocks up) on tcgen05 from 8-digit int8 planes (csrc/fact_i8.cu): -1 = automatic (default: models of >= 1024
+ *   padded points), 0 = float64 DMMA only, 1 = on from 512 points; read-only "fact_i8_effective";
+ * "scratch_cache": keep the scratch of segp_factorize (K, L^-1, a temporary and the digit planes: ~0.9 GB per concurrent
+ *   output dimension at N = 5000) between calls, so that a loop that refits a same-size model every step does not pay
+ *   for allocating and freeing it: -1 = automatic (default: keep when it is <= 4 GB), 0 = never (frees it now), 1 =
+ *   always; read-only "scratch_cached_bytes";
  * "time_tri": 1 = bracket every contraction launch with a CUDA-event pair on its stream (resets the counters);
  * read-only: "launches" = kernels launched by this handle so far, "n_train_padded", "workspace_bytes",
  * "tri_launches" / "tri_ns" = number and total device nanoseconds of the timed contraction launches). */

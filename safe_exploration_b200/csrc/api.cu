@@ -127,11 +127,11 @@ struct segp_model {
     // it is <= 4 GB, 0 = never, 1 = always
     struct FactScratch {
         double *kbuf = nullptr, *wbuf = nullptr, *tmp = nullptr, *diag_inv = nullptr, *u_tmp = nullptr;
-        F7Scratch f7{nullptr, nullptr, nullptr, nullptr};
+        FdScratch fd{nullptr, nullptr, nullptr, nullptr};
     };
     FactScratch fact_cache[4];
     int fact_cache_npad = 0, fact_cache_slots = 0;
-    bool fact_cache_f7 = false, fact_cache_w = false;
+    bool fact_cache_fd = false, fact_cache_w = false;
     long opt_scratch_cache = -1;
     bool last_append_incremental = false;
     // precision management of the int8 path
@@ -245,10 +245,10 @@ static void free_fact_cache(segp_model* m) {
         dev_free(c.tmp);
         dev_free(c.diag_inv);
         dev_free(c.u_tmp);
-        dev_free(c.f7.ap);
-        dev_free(c.f7.bp);
-        dev_free(c.f7.as);
-        dev_free(c.f7.bs);
+        dev_free(c.fd.ap);
+        dev_free(c.fd.bp);
+        dev_free(c.fd.as);
+        dev_free(c.fd.bs);
     }
     m->fact_cache_npad = m->fact_cache_slots = 0;
 }
@@ -1129,16 +1129,16 @@ int segp_factorize(segp_model* m, void* stream) {
     Slot slots[FACT_SLOTS];
     // dense GEMMs of potrf / trtri on the tensor cores (fact_i8.cu) where the model is large enough for the splits to
     // pay (below ~1000 points the chain of 64 x 64 diagonal blocks sets the time, not the GEMMs)
-    const bool use_f7 = m->n_pad >= 512 && m->n_pad <= I8_MAX_NPAD &&
+    const bool use_fd = m->n_pad >= 512 && m->n_pad <= I8_MAX_NPAD &&
                         (m->opt_fact_i8 == 1 || (m->opt_fact_i8 < 0 && m->n_pad >= 1024));
-    m->last_fact_i8 = use_f7;
+    m->last_fact_i8 = use_fd;
     cudaEvent_t fork = nullptr;
     int* d_fail = nullptr;
     int rc = SEGP_OK;
     std::vector<int> fails(m->n_s, 0);
     // scratch kept from the previous factorisation of a same-size model
     const bool need_w = !m->opt_keep_w;
-    const bool cache_hit = m->fact_cache_npad == m->n_pad && m->fact_cache_slots >= nslots && m->fact_cache_f7 == use_f7 &&
+    const bool cache_hit = m->fact_cache_npad == m->n_pad && m->fact_cache_slots >= nslots && m->fact_cache_fd == use_fd &&
                            m->fact_cache_w == need_w;
     if (cache_hit) {
         for (int i = 0; i < nslots; ++i) {
@@ -1149,7 +1149,7 @@ int segp_factorize(segp_model* m, void* stream) {
     if (!cache_hit || m->fact_cache_slots > nslots) free_fact_cache(m);
     m->fact_cache_npad = m->fact_cache_slots = 0;
     const size_t slot_bytes = (3 * nn + (size_t)nb64 * NBLK * NBLK + 33 * (size_t)m->n_pad) * sizeof(double) +
-                              (use_f7 ? 2 * f7_scratch_plane_bytes(m->n_pad) + 2 * m->n_pad * sizeof(double) : 0);
+                              (use_fd ? 2 * fd_scratch_plane_bytes(m->n_pad) + 2 * m->n_pad * sizeof(double) : 0);
     do {
         if (m->opt_keep_w && m->wdense == nullptr && (rc = dev_alloc(&m->wdense, (size_t)m->n_s * nn)) != SEGP_OK) break;
         if ((rc = dev_alloc(&d_fail, (size_t)m->n_s)) != SEGP_OK) break;
@@ -1169,12 +1169,12 @@ int segp_factorize(segp_model* m, void* stream) {
             if ((rc = dev_alloc(&sl.diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
             if ((rc = dev_alloc(&sl.u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
             }
-            if (use_f7 && !cache_hit) {
-                const size_t pb = f7_scratch_plane_bytes(m->n_pad);
-                if ((rc = dev_alloc(&sl.f7.ap, pb)) != SEGP_OK) break;
-                if ((rc = dev_alloc(&sl.f7.bp, pb)) != SEGP_OK) break;
-                if ((rc = dev_alloc(&sl.f7.as, (size_t)m->n_pad)) != SEGP_OK) break;
-                if ((rc = dev_alloc(&sl.f7.bs, (size_t)m->n_pad)) != SEGP_OK) break;
+            if (use_fd && !cache_hit) {
+                const size_t pb = fd_scratch_plane_bytes(m->n_pad);
+                if ((rc = dev_alloc(&sl.fd.ap, pb)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.fd.bp, pb)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.fd.as, (size_t)m->n_pad)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.fd.bs, (size_t)m->n_pad)) != SEGP_OK) break;
             }
             if (cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess ||
@@ -1197,7 +1197,7 @@ int segp_factorize(segp_model* m, void* stream) {
                                   comp ? m->lin + (size_t)d * m->dim : nullptr, ss)) != SEGP_OK)
                 break;
             ++m->launches;
-            if ((rc = potrf_lower(sl.kbuf, m->n_pad, sl.diag_inv, d_fail + d, ss, &m->launches, use_f7 ? &sl.f7 : nullptr)) != SEGP_OK)
+            if ((rc = potrf_lower(sl.kbuf, m->n_pad, sl.diag_inv, d_fail + d, ss, &m->launches, use_fd ? &sl.fd : nullptr)) != SEGP_OK)
                 break;
             if ((rc = logdet_from_chol(sl.kbuf, m->n_train, m->n_pad, m->logdet + d, ss)) != SEGP_OK) break;
             ++m->launches;
@@ -1206,7 +1206,7 @@ int segp_factorize(segp_model* m, void* stream) {
                 rc = SEGP_ERR_CUDA;
                 break;
             }
-            if ((rc = trtri_lower(sl.kbuf, wbuf, m->n_pad, sl.diag_inv, sl.tmp, ss, &m->launches, use_f7 ? &sl.f7 : nullptr)) != SEGP_OK)
+            if ((rc = trtri_lower(sl.kbuf, wbuf, m->n_pad, sl.diag_inv, sl.tmp, ss, &m->launches, use_fd ? &sl.fd : nullptr)) != SEGP_OK)
                 break;
             if ((rc = solve_beta(wbuf, m->yp + (size_t)d * m->n_pad, sl.u_tmp, m->beta + (size_t)d * m->n_pad, m->n_pad,
                                  ss)) != SEGP_OK)
@@ -1259,7 +1259,7 @@ int segp_factorize(segp_model* m, void* stream) {
         }
         m->fact_cache_npad = m->n_pad;
         m->fact_cache_slots = nslots;
-        m->fact_cache_f7 = use_f7;
+        m->fact_cache_fd = use_fd;
         m->fact_cache_w = need_w;
     }
     for (int i = 0; i < FACT_SLOTS; ++i) {
@@ -1269,10 +1269,10 @@ int segp_factorize(segp_model* m, void* stream) {
         dev_free(sl.tmp);
         dev_free(sl.diag_inv);
         dev_free(sl.u_tmp);
-        dev_free(sl.f7.ap);
-        dev_free(sl.f7.bp);
-        dev_free(sl.f7.as);
-        dev_free(sl.f7.bs);
+        dev_free(sl.fd.ap);
+        dev_free(sl.fd.bp);
+        dev_free(sl.fd.as);
+        dev_free(sl.fd.bs);
         if (sl.done != nullptr) cudaEventDestroy(sl.done);
         if (sl.s != nullptr) cudaStreamDestroy(sl.s);
     }
@@ -2204,7 +2204,7 @@ int segp_i8_gemm_selftest(int device, int m, int n, int k, const double* h_a, co
         set_error("segp_i8_gemm_selftest: cudaSetDevice(%d) failed", device);
         return SEGP_ERR_CUDA;
     }
-    return gemm_i8x7_selftest(m, n, k, h_a, h_b, h_c, alpha, beta, trans_b, flags);
+    return gemm_i8d_selftest(m, n, k, h_a, h_b, h_c, alpha, beta, trans_b, flags);
 }
 
 int segp_i8_selftest(int device, int variant, int k_blocks, const int8_t* h_a, const int8_t* h_b, int32_t* h_acc,
@@ -2475,7 +2475,7 @@ int segp_get_option(segp_model* m, const char* name, long* value) {
         if (m->fact_cache_slots > 0) {
             const size_t nn = (size_t)m->fact_cache_npad * m->fact_cache_npad;
             size_t b = ((m->fact_cache_w ? 3 : 2) * nn + nn / NBLK * NBLK + 33 * (size_t)m->fact_cache_npad) * sizeof(double);
-            if (m->fact_cache_f7) b += 2 * f7_scratch_plane_bytes(m->fact_cache_npad) + 2 * m->fact_cache_npad * sizeof(double);
+            if (m->fact_cache_fd) b += 2 * fd_scratch_plane_bytes(m->fact_cache_npad) + 2 * m->fact_cache_npad * sizeof(double);
             *value = (long)(b * m->fact_cache_slots);
         }
     }

@@ -303,13 +303,13 @@ int launch_argbest(long n, const double* cost, const int32_t* feasible, const do
                    cudaStream_t st);
 
 // ---------------------------------------------------------------- factorisation GEMMs
-// flags shared by gemm64 (float64 DMMA, setup.cu) and gemm_i8x7 (tcgen05 digit planes, fact_i8.cu)
+// flags shared by gemm64 (float64 DMMA, setup.cu) and gemm_i8d (tcgen05 digit planes, fact_i8.cu)
 constexpr int GEMM_A_LOWER = 1;   // A[i,k] == 0 for k > i   -> the k loop stops at the row tile's end
 constexpr int GEMM_B_LOWER = 2;   // B[k,n] == 0 for k < n   -> the k loop starts at the column tile's start
 constexpr int GEMM_C_LOWER = 4;   // only tiles on or below the diagonal are computed (syrk)
 
-// C[z] (M_z x N) = alpha A[z] B[z]^T + beta C[z] from digit planes (f7_split): planes [row tile of 128][k-block of
-// 64][7][8 KB] + one scale per operand row; M_z = min(m, m_total - z * zrows) as GemmArgs.
+// C[z] (M_z x N) = alpha A[z] B[z]^T + beta C[z] from digit planes (fd_split): planes [row tile of 128][k-block of
+// 64][8][8 KB] + one scale per operand row; M_z = min(m, m_total - z * zrows) as GemmArgs.
 struct GemmI8Args {
     const int8_t* ap;
     const double* as;
@@ -326,20 +326,20 @@ struct GemmI8Args {
     int m_total, zrows;
 };
 // scratch of one factorisation stream: two operand plane sets + their row scales
-struct F7Scratch {
+struct FdScratch {
     int8_t* ap;
     int8_t* bp;
     double* as;
     double* bs;
 };
-size_t f7_scratch_plane_bytes(int n_pad);          // bytes per operand plane set for a model of n_pad points
-size_t f7_plane_bytes(int rows, int cols, int batch);
+size_t fd_scratch_plane_bytes(int n_pad);          // bytes per operand plane set for a model of n_pad points
+size_t fd_plane_bytes(int rows, int cols, int batch);
 // operand O[r][k] = transposed ? X[k ld + r] : X[r ld + k]; tri 1: zero for k > r, 2: zero for k < r; clip bit 0 / 1:
 // the ragged last batch entry bounds the rows / the k range by min(nominal, lim_total - z zrows)
-int f7_split(const double* x, long ld, long zstride, int rows, int cols, int transposed, int tri, int clip, int lim_total,
+int fd_split(const double* x, long ld, long zstride, int rows, int cols, int transposed, int tri, int clip, int lim_total,
              int zrows, int batch, double* scale, int8_t* planes, cudaStream_t st);
-int launch_gemm_i8x7(const GemmI8Args& g, int batch, cudaStream_t st);
-int gemm_i8x7_selftest(int m, int n, int k, const double* h_a, const double* h_b, double* h_c, double alpha, double beta,
+int launch_gemm_i8d(const GemmI8Args& g, int batch, cudaStream_t st);
+int gemm_i8d_selftest(int m, int n, int k, const double* h_a, const double* h_b, double* h_c, double alpha, double beta,
                        int trans_b, int flags);
 
 // ---------------------------------------------------------------- setup (factorisation), all float64 on device
@@ -361,13 +361,13 @@ int logdet_from_winv(const double* w, int n_train, int n_pad, double* d_out, cud
 int launch_xtb(const double* xraw, const double* beta, double* xtb, int n_pad, int dim, cudaStream_t st);
 // in-place blocked Cholesky (lower) of a (n_pad x n_pad); diag_inv gets the inverses of the 64x64 diagonal blocks;
 // *d_fail (device int) is set to 1+pivot index on a non-positive pivot.
-// f7 != NULL: the K = 256 trailing updates (two-level blocking) run on the tcgen05 digit-plane GEMM (fact_i8.cu).
+// fd != NULL: the K = 256 trailing updates (two-level blocking) run on the tcgen05 digit-plane GEMM (fact_i8.cu).
 int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_t st, long* launches,
-                const F7Scratch* f7 = nullptr);
+                const FdScratch* fd = nullptr);
 // w (zero-initialised n_pad x n_pad) = inverse of the lower factor l; tmp is n_pad x n_pad scratch.
-// f7 != NULL: the levels with blocks of >= 256 rows run on the tcgen05 digit-plane GEMM.
+// fd != NULL: the levels with blocks of >= 256 rows run on the tcgen05 digit-plane GEMM.
 int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, double* tmp, cudaStream_t st,
-                long* launches, const F7Scratch* f7 = nullptr);
+                long* launches, const FdScratch* fd = nullptr);
 // beta = W^T (W y)
 int solve_beta(const double* w, const double* y, double* u_tmp, double* beta, int n_pad, cudaStream_t st);
 // pack W into [ntri][32][128][4] tiles

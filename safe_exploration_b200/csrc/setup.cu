@@ -369,12 +369,12 @@ __global__ void __launch_bounds__(256) panel_trsm_kernel(double* __restrict__ a,
     }
 }
 
-// Two-level right-looking blocking when the tensor-core GEMM is available (f7 != NULL): 64-wide blocks are factorised
+// Two-level right-looking blocking when the tensor-core GEMM is available (fd != NULL): 64-wide blocks are factorised
 // as before (potf2_inv, panel_trsm) but their float64 DMMA updates stay inside the current 256-wide panel; the rest of
 // the trailing matrix is updated once per panel, A22 -= P P^T with K = 256, on tcgen05 from digit planes of P
 // (fact_i8.cu): ~1 - 1.5 * 256 / n_pad of the factorisation's flops run on the tensor cores.
 int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_t st, long* launches,
-                const F7Scratch* f7) {
+                const FdScratch* fd) {
     const int nb = n_pad / NBLK;
     constexpr int kBlockSmem = 2 * NBLK * (NBLK + 1) * (int)sizeof(double);
     constexpr int kPotf2Smem = 3 * NBLK * (NBLK + 1) * (int)sizeof(double);
@@ -389,7 +389,7 @@ int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_
         if (rem <= 0) break;
         panel_trsm_kernel<<<rem, 256, kBlockSmem, st>>>(a, n_pad, kb, diag_inv);
         ++*launches;
-        // trailing update: A22 -= A21 A21^T (lower tiles only); with f7 only up to the end of the 256-wide panel
+        // trailing update: A22 -= A21 A21^T (lower tiles only); with fd only up to the end of the 256-wide panel
         GemmArgs g{};
         const long off = ((long)kb + 1) * NBLK;
         const long panel_end = std::min<long>(((long)kb * NBLK / PANEL + 1) * PANEL, n_pad);
@@ -398,7 +398,7 @@ int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_
         g.c = a + off * n_pad + off;
         g.lda = g.ldb = g.ldc = n_pad;
         g.m = rem * NBLK;
-        g.n = f7 != nullptr ? (int)(panel_end - off) : g.m;
+        g.n = fd != nullptr ? (int)(panel_end - off) : g.m;
         g.k = NBLK;
         g.alpha = -1.0;
         g.beta = 1.0;
@@ -409,15 +409,15 @@ int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_
             SEGP_CHECK(launch_gemm64(g, true, 1, st));
             ++*launches;
         }
-        if (f7 != nullptr && off == panel_end && off < n_pad) {
+        if (fd != nullptr && off == panel_end && off < n_pad) {
             // the panel [p0, off) is final below row off: digit planes of P = A[off:, p0:off], then the K = pw update
             const long p0 = panel_end - PANEL < 0 ? 0 : ((long)kb * NBLK / PANEL) * PANEL;
             const int pw = (int)(off - p0);
             const int rows = (int)(n_pad - off);
-            SEGP_CHECK(f7_split(a + off * n_pad + p0, n_pad, 0, rows, pw, 0, 0, 0, 0, 0, 1, f7->as, f7->ap, st));
+            SEGP_CHECK(fd_split(a + off * n_pad + p0, n_pad, 0, rows, pw, 0, 0, 0, 0, 0, 1, fd->as, fd->ap, st));
             GemmI8Args t{};
-            t.ap = t.bp = f7->ap;
-            t.as = t.bs = f7->as;
+            t.ap = t.bp = fd->ap;
+            t.as = t.bs = fd->as;
             t.a_kb = t.b_kb = pw / NBLK;
             t.c = a + off * n_pad + off;
             t.ldc = n_pad;
@@ -428,7 +428,7 @@ int potrf_lower(double* a, int n_pad, double* diag_inv, int* d_fail, cudaStream_
             t.flags = GEMM_C_LOWER;
             t.m_total = rows;
             t.zrows = 0;
-            SEGP_CHECK(launch_gemm_i8x7(t, 1, st));
+            SEGP_CHECK(launch_gemm_i8d(t, 1, st));
             *launches += 4;
         }
     }
@@ -445,7 +445,7 @@ __global__ void copy_diag_inv_kernel(double* __restrict__ w, int n_pad, const do
 }
 
 int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, double* tmp, cudaStream_t st,
-                long* launches, const F7Scratch* f7) {
+                long* launches, const FdScratch* fd) {
     const int nb = n_pad / NBLK;
     copy_diag_inv_kernel<<<nb, 256, 0, st>>>(w, n_pad, diag_inv);
     ++*launches;
@@ -454,17 +454,17 @@ int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, d
     //   W21 = -W22 T       (W22 lower)
     for (long s = NBLK; s < n_pad; s *= 2) {
         const int pairs = (int)((n_pad - s + 2 * s - 1) / (2 * s));   // pairs whose second block is non-empty
-        if (f7 != nullptr && s >= 256) {
+        if (fd != nullptr && s >= 256) {
             // the same two products from digit planes on tcgen05 (fact_i8.cu); every operand is split with the exact
             // max-abs of its rows over this level's k range as the scale
             const long zs = 2 * s * ((long)n_pad + 1);
             const int lim = (int)(n_pad - s), zr = (int)(2 * s), si = (int)s;
-            const long zplanes = (long)f7_plane_bytes(si, si, 1);
+            const long zplanes = (long)fd_plane_bytes(si, si, 1);
             GemmI8Args t{};
-            t.ap = f7->ap;
-            t.as = f7->as;
-            t.bp = f7->bp;
-            t.bs = f7->bs;
+            t.ap = fd->ap;
+            t.as = fd->as;
+            t.bp = fd->bp;
+            t.bs = fd->bs;
             t.a_kb = t.b_kb = si / NBLK;
             t.ldc = n_pad;
             t.m = t.n = t.k = si;
@@ -474,21 +474,21 @@ int trtri_lower(const double* l, double* w, int n_pad, const double* diag_inv, d
             t.m_total = lim;
             t.zrows = zr;
             // T = L21 * W11: A = L21 (rows clipped in the last pair), B^T = W11^T (zero for k < n)
-            SEGP_CHECK(f7_split(l + s * n_pad, n_pad, zs, si, si, 0, 0, 1, lim, zr, pairs, f7->as, f7->ap, st));
-            SEGP_CHECK(f7_split(w, n_pad, zs, si, si, 1, 2, 0, 0, 0, pairs, f7->bs, f7->bp, st));
+            SEGP_CHECK(fd_split(l + s * n_pad, n_pad, zs, si, si, 0, 0, 1, lim, zr, pairs, fd->as, fd->ap, st));
+            SEGP_CHECK(fd_split(w, n_pad, zs, si, si, 1, 2, 0, 0, 0, pairs, fd->bs, fd->bp, st));
             t.c = tmp + s * n_pad;
             t.alpha = 1.0;
             t.beta = 0.0;
             t.flags = GEMM_B_LOWER;
-            SEGP_CHECK(launch_gemm_i8x7(t, pairs, st));
+            SEGP_CHECK(launch_gemm_i8d(t, pairs, st));
             // W21 = -W22 * T: A = W22 (lower; rows and k clipped), B^T = T^T (k clipped)
-            SEGP_CHECK(f7_split(w + s * n_pad + s, n_pad, zs, si, si, 0, 1, 3, lim, zr, pairs, f7->as, f7->ap, st));
-            SEGP_CHECK(f7_split(tmp + s * n_pad, n_pad, zs, si, si, 1, 0, 2, lim, zr, pairs, f7->bs, f7->bp, st));
+            SEGP_CHECK(fd_split(w + s * n_pad + s, n_pad, zs, si, si, 0, 1, 3, lim, zr, pairs, fd->as, fd->ap, st));
+            SEGP_CHECK(fd_split(tmp + s * n_pad, n_pad, zs, si, si, 1, 0, 2, lim, zr, pairs, fd->bs, fd->bp, st));
             t.c = w + s * n_pad;
             t.alpha = -1.0;
             t.beta = 0.0;
             t.flags = GEMM_A_LOWER;
-            SEGP_CHECK(launch_gemm_i8x7(t, pairs, st));
+            SEGP_CHECK(launch_gemm_i8d(t, pairs, st));
             *launches += 14;
             continue;
         }

@@ -2,7 +2,8 @@
 # One GPU measurement pass (1 x B200) under gpurun: which parts run is chosen by the words on the command line.
 #   tests    pytest -m gpu (all)          smoke   __graft_entry__.smoke()
 #   bench    bench.py for C4 (quoted configuration, B = 65536) + C4 weak shard (B = 8192) + C2 / C3 / C5
-#   ncu      launch list of a C4 step + ncu --set full of the three rollout kernels
+#   ncu      launch lists (C4 / C3 / C2 steps, C4 factorisation) + ncu --set full of the rollout kernels and the factorisation GEMM
+#   setup    factorisation wall times and host-side phase breakdown, tensor-core GEMMs off / on
 # Outputs under gpurun_out/ (scratch); scripts/collect_profiles.py copies the judged summaries to profiles/round2/.
 mkdir -p gpurun_out
 B="python bench.py"
@@ -27,17 +28,21 @@ bench_all)
   $B --config C2 --steps 20 --warmup 5 --no-graph --no-cpu-baseline > gpurun_out/bench_c2_n1_nograph.json 2> gpurun_out/bench_c2_n1_nograph.err
   $B --config C5 --scaling weak --steps 3 --warmup 3 --cpu-seconds 10 > gpurun_out/bench_c5_n1.json 2> gpurun_out/bench_c5_n1.err
   $B --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err ;;
-small)
-  for ss in 0 2 4; do $B --config C2 --substreams $ss --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_n1_ss${ss}.json 2> gpurun_out/bench_c2_n1_ss${ss}.err; done
-  SEGP_ELL_THREADS=32 $B --config C2 --substreams 4 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_n1_ss4_e32.json 2> gpurun_out/bench_c2_n1_ss4_e32.err
-  SEGP_ELL_THREADS=32 $B --config C2 --substreams 0 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_n1_ss0_e32.json 2> gpurun_out/bench_c2_n1_ss0_e32.err
-  timeout 600 python -m pytest tests/test_gpu_precision.py -m gpu -q -k "substream or graph" > gpurun_out/pytest_small.log 2>&1; tail -3 gpurun_out/pytest_small.log ;;
 ncu)
   NB="$B --scaling weak --steps 1 --warmup 2 --e2e-steps 1 --no-cpu-baseline --no-graph"
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'tri_|kstar|ellipsoid_step|i8_guard' -c 400 --csv --log-file gpurun_out/launches_c4.csv $NB > gpurun_out/ncu_launches.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:tri_i8m -s 4 -c 1 -o gpurun_out/prof_tri_i8m_c4 -f $NB > gpurun_out/ncu_full_tri.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:kstar_i8 -s 4 -c 1 -o gpurun_out/prof_kstar_i8_c4 -f $NB > gpurun_out/ncu_full_kstar.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:ellipsoid_step -s 4 -c 1 -o gpurun_out/prof_ellipsoid_c4 -f $NB > gpurun_out/ncu_full_ell.log 2>&1 ;;
+  ncu --set full --clock-control none --import-source on -k regex:ellipsoid_step -s 4 -c 1 -o gpurun_out/prof_ellipsoid_c4 -f $NB > gpurun_out/ncu_full_ell.log 2>&1
+  for c in C2 C3; do
+    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'tri_|kstar|ellipsoid_step|i8_guard' -c 300 --csv --log-file gpurun_out/launches_${c,,}.csv $B --config $c --steps 1 --warmup 2 --e2e-steps 1 --no-cpu-baseline --no-graph > gpurun_out/ncu_launches_${c,,}.log 2>&1
+  done
+  SEGP_FACT_I8=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_setup_c4.csv python scripts/profile_setup.py C4 0 > gpurun_out/ncu_setup.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:gemm_i8d -s 2 -c 1 -o gpurun_out/prof_gemm_i8d_c4 -f python scripts/profile_setup.py C4 0 > gpurun_out/ncu_full_gemm.log 2>&1 ;;
+setup)
+  for cfg in C3 C4 C5; do for mode in 0 1; do
+    SEGP_FACT_TIMING=1 SEGP_FACT_I8=$mode python scripts/profile_setup.py $cfg 3 > gpurun_out/setup_${cfg,,}_fact_i8_$mode.log 2>&1; tail -1 gpurun_out/setup_${cfg,,}_fact_i8_$mode.log
+  done; done ;;
 esac
 done
 ls -la gpurun_out | tail -30

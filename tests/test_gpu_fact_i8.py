@@ -1,4 +1,4 @@
-"""GPU tests of the factorisation GEMMs on tcgen05 (csrc/fact_i8.cu: 7 int8 digit planes per operand, 28 products),
+"""GPU tests of the factorisation GEMMs on tcgen05 (csrc/fact_i8.cu: 8 int8 digit planes per operand, 36 products),
 through the C ABI.
 
 * the split + GEMM kernel against NumPy float64 on host matrices (every flag combination the factorisation uses),
@@ -17,14 +17,15 @@ A_LOWER, B_LOWER, C_LOWER = 1, 2, 4
 
 
 def _tol(a, b_nk, extra=0.0):
-    """Error bound of the digit-plane product, entry (i, j): every operand row is fixed-point with 55 bits below its own
-    max-abs, and the digit pairs a + c >= 7 are dropped, so the absolute error is bounded NORM-wise by
-    ~ 2^-53 K max|a_i| max|b_j| (not by |a_i|^T |b_j| as for a float64 dot product); plus float64 rounding of the
-    NumPy reference itself."""
+    """Error bound of the digit-plane product, entry (i, j): every operand row is fixed-point with 63 bits below its own
+    max-abs (each element first rounded to 53 bits), and the digit pairs a + c >= 8 are dropped, so next to the
+    float64-level term relative to |a_i|^T |b_j| (scaling by 1 / max, rounding to the digit grid and the epilogue's three
+    multiplications: <= 1e-15 in the worst case, far below the K * 1.1e-16 of a float64 dot product) there is a NORM-wise
+    one, ~ 2^-61 K max|a_i| max|b_j|."""
     k = a.shape[1]
     amax = np.abs(a).max(axis=1)[:, None]
     bmax = np.abs(b_nk).max(axis=1)[None, :]
-    return 2.0 ** -53 * k * amax * bmax + 4e-16 * (np.abs(a) @ np.abs(b_nk).T + extra)
+    return 2.0 ** -61 * k * amax * bmax + 2e-15 * (np.abs(a) @ np.abs(b_nk).T + extra)
 
 
 @pytest.fixture(scope="module")
