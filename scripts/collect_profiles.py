@@ -52,11 +52,20 @@ def dram_bytes(summary_path):
     return int(float(rd[2]) * scale[rd[1].strip()] + float(wr[2]) * scale[wr[1].strip()])
 
 
+# gpurun_out/ also holds files of earlier rounds: only what was written after this round began is collected
+ROUND_START = 1792231200.0   # 2026-10-17 10:00 UTC
+
+
+def fresh(path):
+    return os.path.getmtime(path) >= ROUND_START
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else ""
     os.makedirs(DST, exist_ok=True)
     for fn in sorted(os.listdir(SRC)):
-        if fn.startswith("bench_") and fn.endswith(".json") and os.path.getsize(os.path.join(SRC, fn)) > 0:
+        if (fn.startswith("bench_") and fn.endswith(".json") and os.path.getsize(os.path.join(SRC, fn)) > 0
+                and fresh(os.path.join(SRC, fn))):
             shutil.copy(os.path.join(SRC, fn), os.path.join(DST, fn.replace(".json", tag + ".json")))
     lc = os.path.join(SRC, "launches_c4.csv")
     if os.path.exists(lc):
@@ -64,6 +73,25 @@ if __name__ == "__main__":
         launches(lc, os.path.join(DST, "launches_c4_summary%s.txt" % tag),
                  "ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --scaling weak --steps 1 --warmup 2 "
                  "--no-graph (C4 shard, B=8192, automatic digit set), rollout kernels only")
+    for c in ("c2", "c3"):
+        lc = os.path.join(SRC, "launches_%s.csv" % c)
+        if os.path.exists(lc):
+            launches(lc, os.path.join(DST, "launches_%s_summary%s.txt" % (c, tag)),
+                     "ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --config %s --steps 1 --warmup 2 "
+                     "--no-graph, rollout kernels only" % c.upper())
+    lc = os.path.join(SRC, "launches_setup_c4.csv")
+    if os.path.exists(lc):
+        launches(lc, os.path.join(DST, "launches_setup_c4_summary%s.txt" % tag),
+                 "ncu --metrics gpu__time_duration.sum --clock-control none; scripts/profile_setup.py C4 0 with "
+                 "SEGP_FACT_I8=1: ONE segp_factorize of the C4 model (4 output dimensions; serialised by ncu) + its probe")
+    for fn in sorted(os.listdir(SRC)):
+        if fn.startswith("setup_c") and "fact_i8" in fn and fn.endswith(".log"):
+            shutil.copy(os.path.join(SRC, fn), os.path.join(DST, fn.replace(".log", tag + ".txt")))
+    rep = os.path.join(SRC, "prof_gemm_i8d_c4.ncu-rep")
+    if os.path.exists(rep):
+        ncu_summary(rep, "ncu --set full --clock-control none --import-source on -k regex:gemm_i8d -s 2 -c 1 "
+                    "(scripts/profile_setup.py C4 0: a trailing update of the C4 factorisation)",
+                    os.path.join(DST, "gemm_i8d_c4_ncu_full%s.txt" % tag))
     cmd = ("ncu --set full --clock-control none --import-source on -k regex:%s -s 4 -c 1 "
            "(bench.py --scaling weak: C4 shard, B=8192, N=5000, n_s=4, automatic digit set)")
     for rep, pat, out in (("prof_tri_i8m_c4.ncu-rep", "tri_i8m", "tri_i8m_c4_ncu_full%s.txt" % tag),
