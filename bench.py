@@ -496,7 +496,8 @@ def run_product(args, rank, world, local_rank):
             "schedule": "serial per chunk ({} sub-batch chain(s)), replayed as a CUDA graph".format(
                 2 if (gp.get_option("substreams") != 0 and gp.get_option("n_train_padded") <= 1024) else 1),
             "clocks": sampler.summary(t_wall0, t_wall1),
-            "setup_s": t_setup, "bad_status": status_bad, "all_finite": finite}
+            "setup_s": t_setup, "factorize_gemms_on_tcgen05": bool(gp.get_option("fact_i8_effective")),
+            "bad_status": status_bad, "all_finite": finite}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], oracle_out = cpu_baseline(w, args.cpu_seconds)
         line["parity"] = parity_against_oracle(res, oracle_out)

@@ -136,3 +136,25 @@ def test_factorize_on_tensor_cores_matches_dmma_path(se, n_train, kern):
     mu_o, var_o, _ = ora.predict_batch(z)
     assert np.allclose(mu1, mu_o, rtol=1e-6, atol=1e-9 * np.abs(mu_o).max())
     assert np.allclose(var1, var_o, rtol=1e-6, atol=0)
+
+
+def test_scratch_cache_reuses_and_frees(se):
+    """segp_factorize keeps its scratch for the next same-size factorisation (option scratch_cache): same bits, and the
+    memory goes back when the option is switched off."""
+    from safe_exploration_b200 import workloads
+    w = workloads.make("C3", batch=96, n_train=700)
+    gp = se.BatchedGPSSM(w.n_s, w.n_s, w.n_u, None, None, kern_types=w.kern_types, hyp=w.hyp, device=0)
+    gp.set_option("fact_i8", 1)
+    gp.train(w.x_train, w.y_train)
+    beta = gp.beta.copy()
+    assert gp.get_option("scratch_cached_bytes") > 0
+    gp.train(w.x_train, w.y_train)                       # from the cache
+    assert np.array_equal(beta, gp.beta)
+    gp.set_option("scratch_cache", 0)
+    assert gp.get_option("scratch_cached_bytes") == 0
+    gp.train(w.x_train, w.y_train)                       # fresh allocations, freed again
+    assert gp.get_option("scratch_cached_bytes") == 0 and np.array_equal(beta, gp.beta)
+    gp.set_option("fact_i8", 0)
+    gp.train(w.x_train, w.y_train)                       # float64 DMMA path: same factor to rounding
+    assert np.abs(gp.beta - beta).max() <= 1e-10 * np.abs(beta).max()
+    gp.close()
