@@ -265,25 +265,30 @@ static int launch_gemm64(const GemmArgs& g, bool trans_b, int batch, cudaStream_
 }
 
 // =========================================================================================== potrf
-// Diagonal block: Cholesky of the 64 x 64 block in shared memory + its explicit inverse.  This kernel is one CTA on the
-// critical path of the whole factorisation (n_pad / 64 of them in a row), so it is written for latency:
-//   factor   right-looking, ONE barrier per column: the pivot's reciprocal square root is computed redundantly by
-//            every thread (MUFU + two Newton steps), the scaled column goes to a second array (nobody waits for it),
-//            the rank-1 update reads the unscaled column;
+// Diagonal block: Cholesky of the 64 x 64 block + its explicit inverse.  This kernel is one CTA on the critical path
+// of the whole factorisation (n_pad / 64 of them in a row), so it is written for latency:
+//   factor   right-looking with the matrix in REGISTERS: thread (row, part) owns the entries (row, 4 i + part), i < 16,
+//            of its row; per column j two barriers -- the owner of (j, j) publishes the pivot; every thread takes its
+//            reciprocal square root (MUFU + two Newton steps), the owners of column j publish the scaled column; then
+//            16 independent FMAs per thread against broadcast shared-memory reads.  The column loop is fully unrolled
+//            so that the register indices are static.
 //   inverse  the two 32 x 32 diagonal blocks side by side (row by row, 4 lanes per entry + shuffle reduction), then
 //            X21 = -X22 (L21 X11) as two 32^3 products over all 256 threads.
-// (round 1: 77 us per block, three barriers per column and a one-thread-per-column substitution.)
+// (round 1: 77 us per block -- three barriers per column around shared-memory updates, one-thread-per-column
+// substitution; the shared-memory version of this layout with one barrier: 61 us.)
 __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ a, int n_pad, int kb,
                                                         double* __restrict__ diag_inv, int* __restrict__ fail) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    double(*s)[NBLK + 1] = reinterpret_cast<double(*)[NBLK + 1]>(dyn_smem);   // A, updated in place; later T
+    double(*s)[NBLK + 1] = reinterpret_cast<double(*)[NBLK + 1]>(dyn_smem);   // T of the inverse
     double(*l)[NBLK + 1] = s + NBLK;                                          // L
     double(*x)[NBLK + 1] = l + NBLK;                                          // L^-1
-    __shared__ double s_dinv[NBLK];
+    __shared__ double s_dinv[NBLK], s_lcol[NBLK], s_piv;
     __shared__ int s_fail;
     const int tid = threadIdx.x;
+    const int row = tid & 63, part = tid >> 6;
     double* blk = a + ((long)kb * NBLK) * n_pad + (long)kb * NBLK;
     if (tid == 0) s_fail = 0;
+    // coalesced load through shared memory, then each thread takes its 16 entries
     for (int idx = tid; idx < NBLK * NBLK; idx += 256) {
         const int r = idx / NBLK, c = idx % NBLK;
         s[r][c] = (c <= r) ? blk[(long)r * n_pad + c] : 0.0;
@@ -291,22 +296,36 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ a, 
         x[r][c] = 0.0;
     }
     __syncthreads();
-    const int row = tid & 63, part = tid >> 6;
+    double av[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) av[i] = s[row][4 * i + part];
+    if (tid == 0) s_piv = s[0][0];
+#pragma unroll
     for (int j = 0; j < NBLK; ++j) {
-        const double d = s[j][j];
+        const int pj = j & 3, ij = j >> 2;
+        __syncthreads();                              // pivot (j, j) published
+        const double d = s_piv;
         const bool bad = !(d > 0.0);
         if (bad && tid == 0) s_fail = kb * NBLK + j + 1;
         const double rinv = bad ? 1.0 : rsqrt_fast(d);
-        if (row >= j) {
-            const double lij = (row == j) ? (bad ? 1.0 : d * rinv) : s[row][j] * rinv;
-            if (part == 0) {
-                l[row][j] = lij;
-                if (row == j) s_dinv[j] = rinv;
-            }
-            for (int k = j + 1 + part; k <= row; k += 4) s[row][k] = fma(-lij, s[k][j] * rinv, s[row][k]);
+        if (part == pj && row >= j) {
+            const double lij = (row == j) ? (bad ? 1.0 : d * rinv) : av[ij] * rinv;
+            s_lcol[row] = lij;
+            l[row][j] = lij;
+            if (row == j) s_dinv[j] = rinv;
         }
-        __syncthreads();
+        __syncthreads();                              // scaled column j published
+        if (row > j) {
+            const double lrow = s_lcol[row];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = 4 * i + part;
+                if (k > j && k <= row) av[i] = fma(-lrow, s_lcol[k], av[i]);
+            }
+            if (j + 1 < NBLK && row == j + 1 && part == ((j + 1) & 3)) s_piv = av[(j + 1) >> 2];
+        }
     }
+    __syncthreads();
     // inverse of the two diagonal 32 x 32 blocks: group g = tid / 128, lane quad = 4 partial sums of one column
     {
         const int g = tid >> 7, t = tid & 127;
@@ -344,7 +363,8 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ a, 
     if (tid == 0 && s_fail != 0) atomicCAS(fail, 0, s_fail);
 }
 
-// Panel: A[i,k] <- A[i,k] * Linv_kk^T for the row blocks i > k (64 rows per CTA).
+// Panel: A[i,k] <- A[i,k] * Linv_kk^T for the row blocks i > k (64 rows per CTA).  Thread (c, rg) computes column c of
+// the rows rg * 16 .. + 16, eight rows at a time: eight independent accumulators against one broadcast row of Linv.
 __global__ void __launch_bounds__(256) panel_trsm_kernel(double* __restrict__ a, int n_pad, int kb,
                                                          const double* __restrict__ diag_inv) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -361,11 +381,20 @@ __global__ void __launch_bounds__(256) panel_trsm_kernel(double* __restrict__ a,
     }
     __syncthreads();
     // out[r][c] = sum_{m <= c} A[r][m] * Linv[c][m]
-    const int c = tid & 63;
-    for (int r = tid >> 6; r < NBLK; r += 4) {
-        double acc = 0.0;
-        for (int m = 0; m <= c; ++m) acc = fma(s_a[r][m], s_l[c][m], acc);
-        blk[(long)r * n_pad + c] = acc;
+    const int c = tid & 63, rg = tid >> 6;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int r0 = rg * 16 + half * 8;
+        double acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+        for (int m = 0; m <= c; ++m) {
+            const double lv = s_l[c][m];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fma(s_a[r0 + i][m], lv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) blk[(long)(r0 + i) * n_pad + c] = acc[i];
     }
 }
 
