@@ -1006,9 +1006,23 @@ static int run_probe(segp_model* m, cudaStream_t st) {
             rc = SEGP_ERR_CUDA;
             break;
         }
+        const bool timing = getenv("SEGP_FACT_TIMING") != nullptr;
+        auto now_ms = []() {
+            return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        };
+        double t0 = now_ms();
+        auto lap = [&](const char* what) {
+            if (!timing) return;
+            const double t = now_ms();
+            fprintf(stderr, "[probe] %-24s %8.2f ms\n", what, t - t0);
+            t0 = t;
+        };
         if ((rc = probe_pass(m, d_z, np, 0, 0, st, q0, e0, &prior)) != SEGP_OK) break;
+        lap("float64 pass");
         if ((rc = probe_pass(m, d_z, np, -1, 5, st, q5, e5)) != SEGP_OK) break;
+        lap("15-product pass");
         if ((rc = probe_pass(m, d_z, np, -1, 4, st, q4, e4)) != SEGP_OK) break;
+        lap("10-product pass");
     } while (0);
     m->time_tri = timed;
     dev_free(d_z);
