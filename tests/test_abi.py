@@ -62,6 +62,20 @@ def test_library_is_sm100a_sass_with_tcgen05_dmma_and_bulk_copies():
     assert "UTCIMMA" in out.stdout and "LDTM" in out.stdout
     assert "DMMA" in out.stdout
     assert "UBLKCP" in out.stdout and "SYNCS" in out.stdout
+    # per kernel: the contraction AND the factorisation GEMM issue tcgen05 MMAs and read TMEM
+    per, cur = {}, None
+    for line in out.stdout.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = ""
+        elif cur is not None:
+            per[cur] += line
+    for frag in ("tri_i8m_kernel", "tri_i8mp_kernel", "gemm_i8d_kernel"):
+        hits = [k for k in per if frag in k]
+        assert hits, frag
+        for k in hits:
+            assert "UTCIMMA" in per[k] and "LDTM" in per[k] and "UBLKCP" in per[k], k
 
 
 def test_product_fails_loudly_without_a_gpu(lib):
