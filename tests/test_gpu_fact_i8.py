@@ -99,7 +99,7 @@ def test_gemm_triangular_operands(se):
     assert np.all(np.abs(got - want) <= _tol(w22, t_want.T))
 
 
-@pytest.mark.parametrize("n_train,kern", [(1500, "rbf"), (2000, "mat52"), (1100, "rbf")])
+@pytest.mark.parametrize("n_train,kern", [(1500, "rbf"), (2000, "mat52"), (1100, "rbf"), (5000, "rbf")])
 def test_factorize_on_tensor_cores_matches_dmma_path(se, n_train, kern):
     import torch
     from oracle.gp_oracle import GPOracle
