@@ -434,6 +434,7 @@ def run_product(args, rank, world, local_rank):
         kblocks = nblk * (nblk + 1) // 2
         executed = 2.0 * products * w.n_s * (128 * 128 * kblocks) * panels * 96
         i8_96, i8_256 = _i8_peak(gp, local_rank, 96), _i8_peak(gp, local_rank, 256)
+        dmma = _dmma_peak(gp, local_rank)   # the only native pipe that produces float64 products (mma.sync m8n8k4.f64)
         pipe_tops = executed / tri_avg_s / 1e12 if tri_avg_s > 0 else None
         roofline = {"bound": "tensor", "kernel": {1: "tri_i8_kernel", 4: "tri_i8m_kernel", 5: "tri_i8mp_kernel"}[mode]
                     + ("<split>" if digits == 4 else "<classic>"),
@@ -453,6 +454,8 @@ def run_product(args, rank, world, local_rank):
                     "pipe_frac_of_n96_peak": (pipe_tops / i8_96) if (pipe_tops and i8_96) else None,
                     "pipe_frac_of_n256_peak": (pipe_tops / i8_256) if (pipe_tops and i8_256) else None,
                     "pipe_frac_of_2x_bf16_peak": (pipe_tops / (2.0 * bf16_peak)) if pipe_tops else None,
+                    "fp64_dmma_peak_tflops": dmma,
+                    "achieved_over_fp64_dmma_peak": (achieved / dmma) if (achieved and dmma) else None,
                     "avg_launch_ms": tri_avg_s * 1e3, "launches_timed": tri_count, "share_of_step": share,
                     "algorithmic_flop_per_launch": flop_launch,
                     "traffic": _traffic(args.config, mode, digits),
