@@ -1177,11 +1177,11 @@ int segp_factorize(segp_model* m, void* stream) {
         for (int i = 0; i < nslots && rc == SEGP_OK; ++i) {
             Slot& sl = slots[i];
             if (!cache_hit) {
-            if ((rc = dev_alloc(&sl.kbuf, nn)) != SEGP_OK) break;
-            if (need_w && (rc = dev_alloc(&sl.wbuf, nn)) != SEGP_OK) break;
-            if ((rc = dev_alloc(&sl.tmp, nn)) != SEGP_OK) break;
-            if ((rc = dev_alloc(&sl.diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
-            if ((rc = dev_alloc(&sl.u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.kbuf, nn)) != SEGP_OK) break;
+                if (need_w && (rc = dev_alloc(&sl.wbuf, nn)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.tmp, nn)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.diag_inv, (size_t)nb64 * NBLK * NBLK)) != SEGP_OK) break;
+                if ((rc = dev_alloc(&sl.u_tmp, (size_t)33 * m->n_pad)) != SEGP_OK) break;
             }
             if (use_fd && !cache_hit) {
                 const size_t pb = fd_scratch_plane_bytes(m->n_pad);

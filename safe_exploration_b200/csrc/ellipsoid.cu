@@ -477,14 +477,13 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
 int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
     // shared memory of phase A: n_s (3 + dim) rows of 32 doubles (C4: 8 KB; the largest supported model: 108 KB)
     constexpr int kMaxSmem = SEGP_MAX_NS * (3 + MAX_D) * ELL_TB * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_call_on_device(attr_set)) {
         SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<SEGP_MAX_NS, SEGP_MAX_NU>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_set = true;
     }
     if (a.n_batch <= a.b0) return SEGP_OK;
     const int threads = ELL_TB * ELL_WARPS;

@@ -32,6 +32,16 @@ void set_error(const char* fmt, ...);
         if (rc__ != SEGP_OK) return rc__; \
     } while (0)
 
+// true the first time it is called on the current device with this flag array: function attributes
+// (cudaFuncSetAttribute) are per device, a process may drive several
+inline bool first_call_on_device(bool (&seen)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+
 // Shared reachability parameters, resident in device memory (uploaded once per call).
 struct StepParams {
     double a[SEGP_MAX_NS * SEGP_MAX_NS];     // row-major n_s x n_s
@@ -319,7 +329,7 @@ struct GemmI8Args {
     int b_kb;
     double* c;
     long ldc;
-    int m, n, k;         // multiples of 128, 64, 64
+    int m, n, k;         // multiples of 128, 128, 64
     double alpha, beta;
     int flags;
     long z_ap, z_as, z_bp, z_bs, z_c;   // batch strides: bytes (planes), elements (scales, C)
