@@ -22,6 +22,9 @@ namespace segp {
 // Small state dimensions are fully unrolled into registers; larger ones keep rolled loops over local-memory arrays
 // (the ellipsoid algebra is O(n_s^3) per trajectory-step against O(n_s N^2) for the GP, so it never matters).
 __host__ __device__ constexpr int unroll_factor(int n) { return n <= 4 ? 32 : 1; }
+// innermost loops of the generic instance: four iterations in flight (their loads hit local memory; rolled one by one
+// every iteration waits out the full load latency)
+__host__ __device__ constexpr int unroll_inner(int n) { return n <= 4 ? 32 : 4; }
 
 // Jacobi rotation annihilating m_pr: t = sgn(alpha) beta / (|alpha| + sqrt(alpha^2 + beta^2)), alpha = (m_rr - m_pp) / 2,
 // beta = m_pr (the textbook t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) without forming theta = alpha / beta).
@@ -50,40 +53,45 @@ __device__ __forceinline__ void jacobi_apply(double (&m)[N][N], int p, int r, do
     }
 }
 
-// largest eigenvalue of Q (I + K^T K), Q symmetric positive semi-definite (n x n), K (n_u x n)
+// M = C^T Q C with B = I + K^T K = C C^T: symmetric, same spectrum as Q B.  Q symmetric positive semi-definite (n x n),
+// K (n_u x n)
 template <int N, int NU>
-__device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const double (&kfb)[NU][N], int n, int nu) {
-    constexpr int UF = unroll_factor(N);
+__device__ __forceinline__ void build_similar(const double (&q)[N][N], const double (&kfb)[NU][N], int n, int nu,
+                                              double (&m)[N][N]) {
+    constexpr int UF = unroll_factor(N), UI = unroll_inner(N);
+    // loop bounds: the compile-time capacity for the register-resident instances (fully unrolled), the run-time size
+    // for the generic one (rolled loops over local-memory arrays: 16^3 -> n^3 work)
+    const int NL = (N > 4) ? n : N, NUL = (N > 4) ? nu : NU;
     double bm[N][N];
 #pragma unroll UF
-    for (int i = 0; i < N; ++i)
+    for (int i = 0; i < NL; ++i)
 #pragma unroll UF
-        for (int j = 0; j < N; ++j) {
+        for (int j = 0; j < NL; ++j) {
             double acc = (i == j) ? 1.0 : 0.0;
             if (i < n && j < n) {
 #pragma unroll UF
-                for (int u = 0; u < NU; ++u)
+                for (int u = 0; u < NUL; ++u)
                     if (u < nu) acc = fma(kfb[u][i], kfb[u][j], acc);
             }
             bm[i][j] = acc;
         }
     // Cholesky B = C C^T (B >= I, always positive definite), in place, lower
 #pragma unroll UF
-    for (int j = 0; j < N; ++j) {
+    for (int j = 0; j < NL; ++j) {
         if (j < n) {
             double d = bm[j][j];
-#pragma unroll UF
-            for (int k = 0; k < N; ++k)
+#pragma unroll UI
+            for (int k = 0; k < NL; ++k)
                 if (k < j) d = fma(-bm[j][k], bm[j][k], d);
             d = sqrt(d);
             bm[j][j] = d;
             const double inv = 1.0 / d;
 #pragma unroll UF
-            for (int i = 0; i < N; ++i) {
+            for (int i = 0; i < NL; ++i) {
                 if (i > j && i < n) {
                     double s = bm[i][j];
-#pragma unroll UF
-                    for (int k = 0; k < N; ++k)
+#pragma unroll UI
+                    for (int k = 0; k < NL; ++k)
                         if (k < j) s = fma(-bm[i][k], bm[j][k], s);
                     bm[i][j] = s * inv;
                 }
@@ -93,33 +101,41 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
     // M = C^T Q C ; first T = Q C (T[i][j] = sum_{k>=j} Q[i][k] C[k][j])
     double t[N][N];
 #pragma unroll UF
-    for (int i = 0; i < N; ++i)
+    for (int i = 0; i < NL; ++i)
 #pragma unroll UF
-        for (int j = 0; j < N; ++j) {
+        for (int j = 0; j < NL; ++j) {
             double acc = 0.0;
-#pragma unroll UF
-            for (int k = 0; k < N; ++k)
+#pragma unroll UI
+            for (int k = 0; k < NL; ++k)
                 if (k >= j && k < n && i < n) acc = fma(0.5 * (q[i][k] + q[k][i]), bm[k][j], acc);
             t[i][j] = acc;
         }
-    double m[N][N];
 #pragma unroll UF
-    for (int i = 0; i < N; ++i)
+    for (int i = 0; i < NL; ++i)
 #pragma unroll UF
-        for (int j = 0; j < N; ++j) {
+        for (int j = 0; j < NL; ++j) {
             double acc = 0.0;
             if (j >= i) {
-#pragma unroll UF
-                for (int k = 0; k < N; ++k)
+#pragma unroll UI
+                for (int k = 0; k < NL; ++k)
                     if (k >= i && k < n) acc = fma(bm[k][i], t[k][j], acc);
             }
             m[i][j] = acc;
         }
 #pragma unroll UF
-    for (int i = 0; i < N; ++i)
+    for (int i = 0; i < NL; ++i)
 #pragma unroll UF
-        for (int j = 0; j < N; ++j)
+        for (int j = 0; j < NL; ++j)
             if (j < i) m[i][j] = m[j][i];
+}
+
+// largest eigenvalue of Q (I + K^T K)
+template <int N, int NU>
+__device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const double (&kfb)[NU][N], int n, int nu) {
+    constexpr int UF = unroll_factor(N), UI = unroll_inner(N);
+    const int NL = (N > 4) ? n : N;
+    double m[N][N];
+    build_similar<N, NU>(q, kfb, n, nu, m);
     if constexpr (N == 2) {
         // closed form: the larger root of the 2 x 2 characteristic polynomial (stable: both terms are >= 0)
         const double hm = 0.5 * (m[0][0] + m[N - 1][N - 1]), hd = 0.5 * (m[0][0] - m[N - 1][N - 1]);
@@ -155,30 +171,30 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
     for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0, dg = 0.0;
 #pragma unroll UF
-        for (int i = 0; i < N; ++i) {
+        for (int i = 0; i < NL; ++i) {
             dg = fma(m[i][i], m[i][i], dg);
 #pragma unroll UF
-            for (int j = 0; j < N; ++j)
+            for (int j = 0; j < NL; ++j)
                 if (j > i) off = fma(m[i][j], m[i][j], off);
         }
         if (!(off > 1e-26 * dg)) break;   // relative off-diagonal norm < 1e-13; also exits on NaN / all-zero
 #pragma unroll UF
-        for (int p = 0; p < N; ++p) {
+        for (int p = 0; p < NL; ++p) {
 #pragma unroll UF
-            for (int r = 0; r < N; ++r) {
+            for (int r = 0; r < NL; ++r) {
                 if (r > p && r < n) {
                     const double apq = m[p][r];
                     if (apq != 0.0) {
                         double cs, sn;
                         jacobi_cs(m[p][p], m[r][r], apq, cs, sn);
-#pragma unroll UF
-                        for (int k = 0; k < N; ++k) {
+#pragma unroll UI
+                        for (int k = 0; k < NL; ++k) {
                             const double akp = m[k][p], akr = m[k][r];
                             m[k][p] = cs * akp - sn * akr;
                             m[k][r] = sn * akp + cs * akr;
                         }
-#pragma unroll UF
-                        for (int k = 0; k < N; ++k) {
+#pragma unroll UI
+                        for (int k = 0; k < NL; ++k) {
                             const double apk = m[p][k], ark = m[r][k];
                             m[p][k] = cs * apk - sn * ark;
                             m[r][k] = sn * apk + cs * ark;
@@ -191,19 +207,81 @@ __device__ __forceinline__ double lambda_max_qb(const double (&q)[N][N], const d
     }
     double lam = m[0][0];
 #pragma unroll UF
-    for (int i = 1; i < N; ++i)
+    for (int i = 1; i < NL; ++i)
         if (i < n) lam = fmax(lam, m[i][i]);
     return lam;
 }
 
+constexpr int ELL_TB = 32;      // trajectories per block: one per lane
+constexpr int ELL_WARPS = 8;    // warps of phase A (and of the cooperative Jacobi)
+static_assert(2 * ELL_WARPS >= SEGP_MAX_NS, "one warp per disjoint rotation of a round");
+
+// Cooperative Jacobi for the generic instance (n_s > 4): the matrices of the block's 32 trajectories sit in shared
+// memory (element (i, j) of lane l at sm[(i n + j) 32 + l]) and the ceil(n / 2) disjoint rotations of a round of the
+// round-robin ordering run on one warp each (n <= 16 -> at most 8 pairs = ELL_WARPS); lane = trajectory throughout.
+// One thread per trajectory with the matrix in local memory is a dependent chain of ~360 rotations x 2 n element
+// updates per trajectory (C5: 1.8 ms for 8192 trajectories, 5 % of a step).  A lane whose matrix has converged
+// rotates by the identity (exact no-op), so a trajectory's result does not depend on its neighbours.  On return
+// (block-synchronised) the eigenvalues are on the diagonal.
+__device__ __forceinline__ void jacobi_coop(double* __restrict__ sm, int* __restrict__ s_flag, int n, int warp, int lane) {
+    const int np = n + (n & 1);      // players of the tournament (a dummy for odd n)
+    const int rounds = np - 1;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        if (warp == 0) {
+            double off = 0.0, dg = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double d = sm[(i * n + i) * 32 + lane];
+                dg = fma(d, d, dg);
+                for (int j = i + 1; j < n; ++j) {
+                    const double o = sm[(i * n + j) * 32 + lane];
+                    off = fma(o, o, off);
+                }
+            }
+            s_flag[lane] = !(off > 1e-26 * dg);   // relative off-diagonal norm < 1e-13; also NaN / all-zero
+        }
+        __syncthreads();
+        const bool done = s_flag[lane] != 0;
+        if (__syncthreads_and(done ? 1 : 0)) break;
+        for (int r = 0; r < rounds; ++r) {
+            // pair of this warp in round r (circle method: player np - 1 stays, the others rotate)
+            int p = -1, q = -1;
+            if (warp < np / 2) {
+                const int x = warp == 0 ? np - 1 : (r + warp) % (np - 1);
+                const int y = warp == 0 ? r : (r - warp + (np - 1)) % (np - 1);
+                p = min(x, y);
+                q = max(x, y);
+                if (q >= n) p = -1;      // the dummy's partner rests
+            }
+            double cs = 1.0, sn = 0.0;
+            if (p >= 0) {
+                if (!done) jacobi_cs(sm[(p * n + p) * 32 + lane], sm[(q * n + q) * 32 + lane], sm[(p * n + q) * 32 + lane], cs, sn);
+#pragma unroll 4
+                for (int k = 0; k < n; ++k) {     // columns p, q (disjoint from every other pair's)
+                    const double akp = sm[(k * n + p) * 32 + lane], akq = sm[(k * n + q) * 32 + lane];
+                    sm[(k * n + p) * 32 + lane] = cs * akp - sn * akq;
+                    sm[(k * n + q) * 32 + lane] = sn * akp + cs * akq;
+                }
+            }
+            __syncthreads();
+            if (p >= 0) {
+#pragma unroll 4
+                for (int k = 0; k < n; ++k) {     // rows p, q
+                    const double apk = sm[(p * n + k) * 32 + lane], aqk = sm[(q * n + k) * 32 + lane];
+                    sm[(p * n + k) * 32 + lane] = cs * apk - sn * aqk;
+                    sm[(q * n + k) * 32 + lane] = sn * apk + cs * aqk;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // =========================================================================================== ellipsoid_step
 // NS/NU are compile-time capacities; n_s/n_u the run-time sizes (equal for the specialised instances).
-constexpr int ELL_TB = 32;      // trajectories per block: one per lane
-constexpr int ELL_WARPS = 8;    // warps of phase A
 
 template <int NS, int NU>
 __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(const StepArgs a) {
-    constexpr int UF = unroll_factor(NS);
+    constexpr int UF = unroll_factor(NS), UI = unroll_inner(NS);
     extern __shared__ double ell_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long b = a.b0 + (long)blockIdx.x * ELL_TB + lane;
@@ -259,14 +337,39 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
         }
         __syncthreads();
     }
+    // ---- generic instance, set branch of the reachability step: lambda_max(Q (I + K^T K)) depends on the state only,
+    // not on the GP, and is found by all warps together (jacobi_coop) before warp 0 goes on alone
+    double* s_m = s_jac + n_s * dim * ELL_TB;                           // [n_s n_s][32]
+    int* s_flag = reinterpret_cast<int*>(s_m + n_s * n_s * ELL_TB);     // [32]
+    double q[NS][NS], kfb[NU][NS];   // shape matrix and feedback gain of the set branch
+    bool coop = false;
+    if constexpr (NS > 4) {
+        coop = a.q != nullptr && a.sp->prop_mode == SEGP_PROP_ELLIPSOID;
+        if (coop) {
+            if (warp == 0) {
+                double m[NS][NS];
+                for (int i = 0; i < n_s; ++i)
+                    for (int j = 0; j < n_s; ++j) q[i][j] = live ? a.q[b * a.q_stride + i * n_s + j] : 0.0;
+                for (int i = 0; i < n_u; ++i)
+                    for (int j = 0; j < n_s; ++j) kfb[i][j] = live ? a.kfb[b * a.kfb_stride + i * n_s + j] : 0.0;
+                build_similar<NS, NU>(q, kfb, n_s, n_u, m);
+                for (int i = 0; i < n_s; ++i)
+                    for (int j = 0; j < n_s; ++j) s_m[(i * n_s + j) * ELL_TB + lane] = m[i][j];
+            }
+            __syncthreads();
+            jacobi_coop(s_m, s_flag, n_s, warp, lane);
+        }
+    }
     if (warp != 0 || !live) return;
 
-    // ---- phase B: one trajectory per lane
+    // ---- phase B: one trajectory per lane.  Loop bounds: compile-time capacities for the register-resident instances,
+    // run-time sizes for the generic one (see lambda_max_qb)
+    const int NSL = (NS > 4) ? n_s : NS, NUL = (NS > 4) ? n_u : NU, NDL = (NS > 4) ? dim : NS + NU;
     const StepParams* __restrict__ sp = a.sp;
     int32_t status = 0;
     double mu[NS], var[NS];
 #pragma unroll UF
-    for (int d = 0; d < NS; ++d) {
+    for (int d = 0; d < NSL; ++d) {
         mu[d] = 0.0;
         var[d] = 0.0;
         if (d < n_s) {
@@ -287,21 +390,21 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
 
     double p[NS], u[NU];
 #pragma unroll UF
-    for (int i = 0; i < NS; ++i) p[i] = (i < n_s) ? a.p[b * a.p_stride + i] : 0.0;
+    for (int i = 0; i < NSL; ++i) p[i] = (i < n_s) ? a.p[b * a.p_stride + i] : 0.0;
 #pragma unroll UF
-    for (int i = 0; i < NU; ++i) u[i] = (i < n_u) ? a.kff[b * a.kff_stride + i] : 0.0;
+    for (int i = 0; i < NUL; ++i) u[i] = (i < n_u) ? a.kff[b * a.kff_stride + i] : 0.0;
 
     // p_lin = mu + A p + B k_ff   (gp_reachability.py:82-83, :115)
     double p1[NS];
 #pragma unroll UF
-    for (int i = 0; i < NS; ++i) {
+    for (int i = 0; i < NSL; ++i) {
         double acc = mu[i];
         if (i < n_s) {
 #pragma unroll UF
-            for (int k = 0; k < NS; ++k)
+            for (int k = 0; k < NSL; ++k)
                 if (k < n_s) acc = fma(sp->a[i * n_s + k], p[k], acc);
 #pragma unroll UF
-            for (int k = 0; k < NU; ++k)
+            for (int k = 0; k < NUL; ++k)
                 if (k < n_u) acc = fma(sp->b[i * n_u + k], u[k], acc);
         }
         p1[i] = acc;
@@ -314,11 +417,11 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
         // ---- point branch (gp_reachability.py:65-88): Q1 = diag(n_s (c sigma_d)^2);
         //      Gaussian propagation (uncertainty_propagation_casadi.py:52-57, 256-261): Sigma1 = diag(sigma_d^2)
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i)
+        for (int i = 0; i < NSL; ++i)
 #pragma unroll UF
-            for (int j = 0; j < NS; ++j) q1[i][j] = 0.0;
+            for (int j = 0; j < NSL; ++j) q1[i][j] = 0.0;
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i)
+        for (int i = 0; i < NSL; ++i)
             if (i < n_s) {
                 if (mode != SEGP_PROP_ELLIPSOID) {
                     q1[i][i] = var[i];
@@ -330,39 +433,38 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
             }
     } else {
         // ---- set branch (gp_reachability.py:89-156)
-        double q[NS][NS], kfb[NU][NS];
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i)
+        for (int i = 0; i < NSL; ++i)
 #pragma unroll UF
-            for (int j = 0; j < NS; ++j) q[i][j] = (i < n_s && j < n_s) ? a.q[b * a.q_stride + i * n_s + j] : 0.0;
+            for (int j = 0; j < NSL; ++j) q[i][j] = (i < n_s && j < n_s) ? a.q[b * a.q_stride + i * n_s + j] : 0.0;
 #pragma unroll UF
-        for (int i = 0; i < NU; ++i)
+        for (int i = 0; i < NUL; ++i)
 #pragma unroll UF
-            for (int j = 0; j < NS; ++j)
+            for (int j = 0; j < NSL; ++j)
                 kfb[i][j] = (i < n_u && j < n_s) ? a.kfb[b * a.kfb_stride + i * n_s + j] : 0.0;
 
         // H = A + A_mu + (B_mu + B) K_fb ; A_mu = J[:, :n_in] (T), B_mu = J[:, n_in:]
         double h[NS][NS];
 #pragma unroll UF
-        for (int d = 0; d < NS; ++d) {
+        for (int d = 0; d < NSL; ++d) {
             if (d < n_s) {
                 // Jacobian row d: jrow[j], j < dim
                 double jrow[NS + NU];
 #pragma unroll UF
-                for (int j = 0; j < NS + NU; ++j) {
+                for (int j = 0; j < NDL; ++j) {
                     jrow[j] = 0.0;
                     if (j < dim && mode != SEGP_PROP_MEAN_EQUIVALENT)   // mean equivalent: no linearisation term
                         jrow[j] = fused ? s_jac[(d * dim + j) * ELL_TB + lane] : a.jac_d[(b * n_s + d) * dim + j];
                 }
 #pragma unroll UF
-                for (int j = 0; j < NS; ++j) {
+                for (int j = 0; j < NSL; ++j) {
                     if (j < n_s) {
                         double acc = sp->a[d * n_s + j];
                         if (sp->has_t) {
                             for (int i = 0; i < n_in; ++i) {
                                 double ji = 0.0;
 #pragma unroll UF
-                                for (int jj = 0; jj < NS + NU; ++jj)
+                                for (int jj = 0; jj < NDL; ++jj)
                                     if (jj == i) ji = jrow[jj];
                                 acc = fma(ji, sp->t[i * n_s + j], acc);
                             }
@@ -370,11 +472,11 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
                             acc += jrow[j];
                         }
 #pragma unroll UF
-                        for (int k = 0; k < NU; ++k) {
+                        for (int k = 0; k < NUL; ++k) {
                             if (k < n_u) {
                                 double jb = 0.0;
 #pragma unroll UF
-                                for (int jj = 0; jj < NS + NU; ++jj)
+                                for (int jj = 0; jj < NDL; ++jj)
                                     if (jj == n_in + k) jb = jrow[jj];
                                 acc = fma(jb + sp->b[d * n_u + k], kfb[k][j], acc);
                             }
@@ -386,28 +488,28 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
                 }
             } else {
 #pragma unroll UF
-                for (int j = 0; j < NS; ++j) h[d][j] = 0.0;
+                for (int j = 0; j < NSL; ++j) h[d][j] = 0.0;
             }
         }
         // Q0 = H Q H^T
         double hq[NS][NS];
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i)
+        for (int i = 0; i < NSL; ++i)
 #pragma unroll UF
-            for (int j = 0; j < NS; ++j) {
+            for (int j = 0; j < NSL; ++j) {
                 double acc = 0.0;
-#pragma unroll UF
-                for (int k = 0; k < NS; ++k) acc = fma(h[i][k], q[k][j], acc);
+#pragma unroll UI
+                for (int k = 0; k < NSL; ++k) acc = fma(h[i][k], q[k][j], acc);
                 hq[i][j] = acc;
             }
         double tr0 = 0.0;
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i)
+        for (int i = 0; i < NSL; ++i)
 #pragma unroll UF
-            for (int j = 0; j < NS; ++j) {
+            for (int j = 0; j < NSL; ++j) {
                 double acc = 0.0;
-#pragma unroll UF
-                for (int k = 0; k < NS; ++k) acc = fma(hq[i][k], h[j][k], acc);
+#pragma unroll UI
+                for (int k = 0; k < NSL; ++k) acc = fma(hq[i][k], h[j][k], acc);
                 q1[i][j] = acc;
                 if (i == j) tr0 += acc;
             }
@@ -417,16 +519,22 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
             // (H = A + B K for the mean-equivalent variant): with F = [I; K], Sigma_z = F Sigma F^T and
             // Sigma_zg = Sigma_z J^T, so every block carries the factor F Sigma F^T.
 #pragma unroll UF
-            for (int i = 0; i < NS; ++i)
+            for (int i = 0; i < NSL; ++i)
                 if (i < n_s) q1[i][i] += var[i];
         } else {
         // remainder boxes (utils.py:129-142)
-        const double r2 = lambda_max_qb<NS, NU>(q, kfb, n_s, n_u);
+        double r2;
+        if constexpr (NS > 4) {      // found by the whole block above: the eigenvalues are on the diagonal
+            r2 = s_m[lane];
+            for (int i = 1; i < n_s; ++i) r2 = fmax(r2, s_m[(i * n_s + i) * ELL_TB + lane]);
+        } else {
+            r2 = lambda_max_qb<NS, NU>(q, kfb, n_s, n_u);
+        }
         const double r1 = sqrt(r2);
         double tr_sig = 0.0, tr_mu = 0.0;
         double d_sig[NS], d_mu[NS];
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i) {
+        for (int i = 0; i < NSL; ++i) {
             d_sig[i] = d_mu[i] = 0.0;
             if (i < n_s) {
                 const double ub_mu = sp->l_mu[i] * r2;
@@ -443,27 +551,27 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
         const double c1 = sqrt(tr_sig / tr_mu);
         double tr_l = 0.0;
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i) {
+        for (int i = 0; i < NSL; ++i) {
             d_sig[i] = (1.0 + 1.0 / c1) * d_sig[i] + (1.0 + c1) * d_mu[i];
             tr_l += d_sig[i];
         }
         const double c2 = sqrt(tr_l / tr0);
         const double f_l = 1.0 + 1.0 / c2, f_0 = 1.0 + c2;
 #pragma unroll UF
-        for (int i = 0; i < NS; ++i)
+        for (int i = 0; i < NSL; ++i)
 #pragma unroll UF
-            for (int j = 0; j < NS; ++j) q1[i][j] = f_0 * q1[i][j] + ((i == j) ? f_l * d_sig[i] : 0.0);
+            for (int j = 0; j < NSL; ++j) q1[i][j] = f_0 * q1[i][j] + ((i == j) ? f_l * d_sig[i] : 0.0);
         }
     }
 
     bool finite = true;
 #pragma unroll UF
-    for (int i = 0; i < NS; ++i) {
+    for (int i = 0; i < NSL; ++i) {
         if (i < n_s) {
             a.p_out[b * a.p_out_stride + i] = p1[i];
             finite = finite && isfinite(p1[i]);
 #pragma unroll UF
-            for (int j = 0; j < NS; ++j)
+            for (int j = 0; j < NSL; ++j)
                 if (j < n_s) {
                     a.q_out[b * a.q_out_stride + i * n_s + j] = q1[i][j];
                     finite = finite && isfinite(q1[i][j]);
@@ -475,8 +583,9 @@ __global__ void __launch_bounds__(ELL_TB * ELL_WARPS) ellipsoid_step_kernel(cons
 }
 
 int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
-    // shared memory of phase A: n_s (3 + dim) rows of 32 doubles (C4: 8 KB; the largest supported model: 108 KB)
-    constexpr int kMaxSmem = SEGP_MAX_NS * (3 + MAX_D) * ELL_TB * (int)sizeof(double);
+    // shared memory: phase A, n_s (3 + dim) rows of 32 doubles (C4: 8 KB; the largest supported model: 108 KB); the
+    // generic instance adds the n_s x n_s matrices of the cooperative Jacobi (n_s = 16: 64 KB) and 32 flags
+    constexpr int kMaxSmem = SEGP_MAX_NS * (3 + MAX_D + SEGP_MAX_NS) * ELL_TB * (int)sizeof(double) + 128;
     static bool attr_set[64] = {};
     if (first_call_on_device(attr_set)) {
         SEGP_CUDA_CHECK(cudaFuncSetAttribute(ellipsoid_step_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -488,7 +597,9 @@ int launch_ellipsoid_step(const StepArgs& a, cudaStream_t st) {
     if (a.n_batch <= a.b0) return SEGP_OK;
     const int threads = ELL_TB * ELL_WARPS;
     const unsigned grid = (unsigned)((a.n_batch - a.b0 + ELL_TB - 1) / ELL_TB);
-    const size_t smem = (size_t)a.n_s * (3 + a.n_in + a.n_u) * ELL_TB * sizeof(double);
+    const bool generic = !((a.n_s == 2 && a.n_u == 1 && a.n_in <= 2) || (a.n_s <= 4 && a.n_u <= 2 && a.n_in <= 4));
+    const size_t smem = (size_t)a.n_s * (3 + a.n_in + a.n_u + (generic ? a.n_s : 0)) * ELL_TB * sizeof(double) +
+                        (generic ? 128 : 0);
     // the specialised instances hold a Jacobian row in NS + NU registers: a lifting input transform (n_in > n_s) does
     // not fit and takes the generic instance
     if (a.n_s == 2 && a.n_u == 1 && a.n_in <= 2)
@@ -511,15 +622,16 @@ __global__ void remainder_kernel(long n_batch, int n_s, int n_u, const double* _
     constexpr int UF = unroll_factor(NS);
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batch) return;
+    const int NSL = (NS > 4) ? n_s : NS, NUL = (NS > 4) ? n_u : NU;
     double qm[NS][NS], k[NU][NS];
 #pragma unroll UF
-    for (int i = 0; i < NS; ++i)
+    for (int i = 0; i < NSL; ++i)
 #pragma unroll UF
-        for (int j = 0; j < NS; ++j) qm[i][j] = (i < n_s && j < n_s) ? q[b * n_s * n_s + i * n_s + j] : 0.0;
+        for (int j = 0; j < NSL; ++j) qm[i][j] = (i < n_s && j < n_s) ? q[b * n_s * n_s + i * n_s + j] : 0.0;
 #pragma unroll UF
-    for (int i = 0; i < NU; ++i)
+    for (int i = 0; i < NUL; ++i)
 #pragma unroll UF
-        for (int j = 0; j < NS; ++j) k[i][j] = (i < n_u && j < n_s) ? kfb[b * kfb_stride + i * n_s + j] : 0.0;
+        for (int j = 0; j < NSL; ++j) k[i][j] = (i < n_u && j < n_s) ? kfb[b * kfb_stride + i * n_s + j] : 0.0;
     const double r2 = lambda_max_qb<NS, NU>(qm, k, n_s, n_u);
     const double r1 = sqrt(r2);
     for (int i = 0; i < n_s; ++i) {

@@ -636,6 +636,45 @@ def test_foreign_ssm_uses_ellipsoid_step(se):
     _assert_close(qa, qa_o, 1e-10)
 
 
+@pytest.mark.parametrize("n_s,n_u", [(5, 2), (7, 3), (8, 1), (10, 3), (16, 8)])
+def test_generic_step_kernel_sizes(se, n_s, n_u):
+    """State dimensions beyond the register-resident instances (n_s > 4) take the generic step kernel, whose
+    lambda_max(Q (I + K^T K)) is a Jacobi iteration spread over the block's warps (round-robin ordering; odd n_s plays
+    with a dummy): multi-step rollouts of a foreign model against the oracle, batched so that several lanes iterate on
+    different matrices."""
+    from oracle import reach_oracle
+    from oracle.gp_oracle import GPOracle
+    rng = np.random.RandomState(10 * n_s + n_u)
+    n = 30
+    x = rng.uniform(-1, 1, size=(n, n_s + n_u))
+    y = np.tanh(x @ rng.randn(n_s + n_u, n_s))
+    ora = GPOracle(x, y, ["rbf"] * n_s, rng.uniform(0.7, 2, size=(n_s, n_s + n_u)),
+                   rng.uniform(0.5, 1.5, size=n_s), rng.uniform(0.01, 0.05, size=n_s))
+    a = 0.7 * np.eye(n_s) + 0.05 * rng.randn(n_s, n_s)
+    b = 0.3 * rng.randn(n_s, n_u)
+    l_mu = rng.uniform(1e-3, 1e-2, n_s)
+    l_sig = rng.uniform(1e-3, 1e-2, n_s)
+    hor = 4
+    kfb = 0.3 * rng.randn(hor - 1, n_u, n_s)
+    for trial in range(3):
+        p = 0.1 * rng.randn(n_s, 1)
+        kff = 0.2 * rng.randn(hor, n_u)
+        _, _, pa, qa = se.multistep_reachability(p, ora, kfb, kff, l_mu, l_sig, None, 2.0, 0, a, b, None)
+        _, _, pa_o, qa_o = reach_oracle.multistep_reachability(p, ora, kfb, kff, l_mu, l_sig, None, 2.0, 0, a, b, None)
+        _assert_close(pa, pa_o, 1e-10)
+        _assert_close(qa, qa_o, 1e-9)
+    # one step from a given ellipsoid, including a rank-deficient shape matrix (zero rotations must be no-ops)
+    m = rng.randn(n_s, n_s)
+    for q in (0.05 * (m @ m.T + 0.1 * np.eye(n_s)), 0.05 * np.outer(m[0], m[0]) + 1e-9 * np.eye(n_s)):
+        p = 0.1 * rng.randn(n_s, 1)
+        k1 = 0.5 * rng.randn(n_u, n_s)
+        kf = 0.2 * rng.randn(n_u, 1)
+        p1, q1 = se.onestep_reachability(p, ora, kf, l_mu, l_sig, q, k1, 1.7, 0, a, b)
+        po, qo = reach_oracle.onestep_reachability(p, ora, kf, l_mu, l_sig, q, k1, 1.7, 0, a, b)
+        _assert_close(p1, po, 1e-12)
+        _assert_close(q1, qo, 1e-10)
+
+
 # =========================================================================== error behaviour
 def test_error_mapping_and_status_flags(se):
     from safe_exploration_b200 import workloads
