@@ -73,12 +73,12 @@ if __name__ == "__main__":
         launches(lc, os.path.join(DST, "launches_c4_summary%s.txt" % tag),
                  "ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --scaling weak --steps 1 --warmup 2 "
                  "--no-graph (C4 shard, B=8192, automatic digit set), rollout kernels only")
-    for c in ("c2", "c3"):
+    for c in ("c2", "c3", "c5"):
         lc = os.path.join(SRC, "launches_%s.csv" % c)
         if os.path.exists(lc):
             launches(lc, os.path.join(DST, "launches_%s_summary%s.txt" % (c, tag)),
-                     "ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --config %s --steps 1 --warmup 2 "
-                     "--no-graph, rollout kernels only" % c.upper())
+                     "ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --config %s --steps 1 --no-graph "
+                     "(C5: --scaling weak --batch 8192), rollout kernels only" % c.upper())
     lc = os.path.join(SRC, "launches_setup_c4.csv")
     if os.path.exists(lc):
         launches(lc, os.path.join(DST, "launches_setup_c4_summary%s.txt" % tag),
