@@ -53,6 +53,18 @@ __device__ __forceinline__ uint32_t split_digits_unit(double u, int& d0) {
     return lo2 ^ 0x80808080u;
 }
 
+// The same for r in [-1, 1] (composite kernel values scaled by the per-trajectory bound): the mantissa of
+// r 127 2^32 + 1.5 2^52 holds 2^51 + V in two's complement, so bits 32..50 are V >> 32 modulo 2^19 -- sign-extend them.
+__device__ __forceinline__ uint32_t split_digits_signed(double r, int& d0) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+    const double t = fma(r, I8_BASE0 * 4294967296.0, MAGIC);
+    const uint32_t lo = (uint32_t)__double2loint(t);
+    const int hi = ((int)((uint32_t)__double2hiint(t) << 13)) >> 13;   // sign-extended 19 bits
+    const uint32_t lo2 = lo + 0x80808080u;
+    d0 = hi + (lo2 < lo ? 1 : 0);
+    return lo2 ^ 0x80808080u;
+}
+
 // =========================================================================================== pack_w_i8
 // Two digit-plane sets of W = L^-1, both stored as SWIZZLE_64B shared-memory images:
 //   classic  rows scaled by their max-abs, 5 digits                                   (15 products, tri digits = 5)
@@ -324,13 +336,91 @@ __device__ __forceinline__ void kstar_i8_load_inputs(const KstarArgs& a, long b,
 // The composite kernels (linear x stationary + linear, predict.cu:kstar_composite) on the digit-plane path: the same
 // float64 kernel values, mean / Jacobian sums and prior variance, with the value leaving as digit bytes of k / s_b.
 // s_b = s_f^2 sum_j |a_j z_j| xmax_j + sum_j |v_j z_j| xmax_j bounds |k(z_b, x_i)| for every training input.
+// Same structure as the stationary kernels' kstar_i8_rows: 128 training points staged through shared memory (scaled
+// and raw coordinates, beta), the table exponential, 8 independent points per iteration, three PRMTs per plane word.
+// training points staged at a time: scaled + raw coordinates must fit the 48 KB of static shared memory
+__host__ __device__ constexpr int comp_stage_rows(int dm) { return dm > 12 ? 64 : TILE; }
+
+template <int DM, int KERN, int ROWS>
+__device__ __forceinline__ void kstar_i8_rows_composite(const double* __restrict__ s_x, const double* __restrict__ s_xr,
+                                                        const double* __restrict__ s_beta, const double* __restrict__ s_tab,
+                                                        const double (&zs)[DM], const double (&za)[DM],
+                                                        const double (&zv)[DM], int dim, double var, double inv_s, int row0,
+                                                        int n_train, bool active, int8_t* __restrict__ kb_base, int rowp,
+                                                        double& mu, double (&jac)[DM], double (&jac2)[DM]) {
+    constexpr int UNR = 8;
+    const double sqrt5 = 2.23606797749978969641;
+#pragma unroll 1
+    for (int r = 0; r < ROWS; r += UNR) {
+        uint32_t pk[I8_S][UNR / 4];
+        uint32_t wlo[UNR];
+        int whi[UNR];
+#pragma unroll
+        for (int qd = 0; qd < UNR; ++qd) {
+            const double* xsr = s_x + (r + qd) * dim;
+            const double* xr = s_xr + (r + qd) * dim;
+            double diff[DM];
+            double r2 = 0.0, lp = 0.0, ll = 0.0;
+#pragma unroll
+            for (int j = 0; j < DM; ++j) {
+                diff[j] = 0.0;
+                if (j < dim) {
+                    diff[j] = zs[j] - xsr[j];
+                    r2 = fma(diff[j], diff[j], r2);
+                    lp = fma(za[j], xr[j], lp);
+                    ll = fma(zv[j], xr[j], ll);
+                }
+            }
+            double stat, gg;
+            if (KERN == SEGP_KERN_LIN_RBF) {
+                stat = var * exp_neg_tab(-0.5 * r2, s_tab);
+                gg = stat;
+            } else {
+                const double rr = sqrt(r2);
+                const double e = var * exp_neg_tab(-sqrt5 * rr, s_tab);
+                stat = (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * e;
+                gg = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
+            }
+            double kval = fma(lp, stat, ll);
+            if (row0 + r + qd >= n_train || !active) kval = 0.0;
+            const double bt = s_beta[r + qd];   // zero on padded rows
+            mu = fma(bt, kval, mu);
+            const double w = bt * lp * gg, w2 = bt * stat;
+#pragma unroll
+            for (int j = 0; j < DM; ++j)
+                if (j < dim) {
+                    jac[j] = fma(w, diff[j], jac[j]);
+                    jac2[j] = fma(w2, xr[j], jac2[j]);
+                }
+            // |kval| <= s_b up to rounding: clamp so the leading digit stays within +-127
+            wlo[qd] = split_digits_signed(fmax(-1.0, fmin(1.0, kval * inv_s)), whi[qd]);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < UNR / 4; ++q4) {
+            const uint32_t w0 = wlo[4 * q4], w1 = wlo[4 * q4 + 1], w2 = wlo[4 * q4 + 2], w3 = wlo[4 * q4 + 3];
+            pk[0][q4] = __byte_perm(__byte_perm((uint32_t)whi[4 * q4], (uint32_t)whi[4 * q4 + 1], 0x0040),
+                                    __byte_perm((uint32_t)whi[4 * q4 + 2], (uint32_t)whi[4 * q4 + 3], 0x0040), 0x5410);
+            pk[1][q4] = __byte_perm(__byte_perm(w0, w1, 0x0073), __byte_perm(w2, w3, 0x0073), 0x5410);
+            pk[2][q4] = __byte_perm(__byte_perm(w0, w1, 0x0062), __byte_perm(w2, w3, 0x0062), 0x5410);
+            pk[3][q4] = __byte_perm(__byte_perm(w0, w1, 0x0051), __byte_perm(w2, w3, 0x0051), 0x5410);
+            pk[4][q4] = __byte_perm(__byte_perm(w0, w1, 0x0040), __byte_perm(w2, w3, 0x0040), 0x5410);
+        }
+        const int kglob = row0 + r;
+        int8_t* dst = kb_base + (long)(kglob >> 6) * (I8_S * I8_B_TILE) + sw64_offset(rowp, kglob & 63);
+#pragma unroll
+        for (int pl = 0; pl < I8_S; ++pl)
+            *reinterpret_cast<uint2*>(dst + (long)pl * I8_B_TILE) = make_uint2(pk[pl][0], pk[pl][1]);
+    }
+}
+
 template <int DM>
 __device__ __forceinline__ void kstar_i8_composite(const KstarI8Args& aa, const double (&z)[DM], int dim, int d, int split,
-                                                   int n_s, long b, bool active, int8_t* __restrict__ kb_base, int rowp) {
+                                                   int n_s, long b, bool active, int8_t* __restrict__ kb_base, int rowp,
+                                                   double* __restrict__ s_x, double* __restrict__ s_xr,
+                                                   double* __restrict__ s_beta, const double* __restrict__ s_tab) {
     const KstarArgs& a = aa.k;
     const int kern = a.kern[d];
     const double var = a.var[d];
-    const double sqrt5 = 2.23606797749978969641;
     const double* __restrict__ pl = a.plin + d * dim;
     const double* __restrict__ lv = a.lin + d * dim;
     double zs[DM], za[DM], zv[DM], jac[DM], jac2[DM];
@@ -351,60 +441,25 @@ __device__ __forceinline__ void kstar_i8_composite(const KstarI8Args& aa, const 
     if (!(bound > 0.0) || !active) bound = 1.0;
     const double inv_s = 1.0 / bound;
     double mu = 0.0;
+    constexpr int STAGE = comp_stage_rows(DM);
     const int row_begin = split * a.groups_per_split * 4;
     const int row_end = min(row_begin + a.groups_per_split * 4, a.n_pad);
-#pragma unroll 1
-    for (int row0 = row_begin; row0 < row_end; row0 += 16) {
-        uint32_t pk[I8_S][4];
-#pragma unroll
-        for (int s = 0; s < I8_S; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
-#pragma unroll 4
-        for (int qd = 0; qd < 16; ++qd) {
-            const int row = row0 + qd;
-            const double* __restrict__ xsr = a.xs + ((long)d * a.n_pad + row) * dim;
-            const double* __restrict__ xr = a.xraw + (long)row * dim;
-            double diff[DM];
-            double r2 = 0.0, lp = 0.0, ll = 0.0;
-#pragma unroll
-            for (int j = 0; j < DM; ++j) {
-                diff[j] = 0.0;
-                if (j < dim) {
-                    diff[j] = zs[j] - xsr[j];
-                    r2 = fma(diff[j], diff[j], r2);
-                    lp = fma(za[j], xr[j], lp);
-                    ll = fma(zv[j], xr[j], ll);
-                }
-            }
-            double stat, gg;
-            if (kern == SEGP_KERN_LIN_RBF) {
-                stat = var * exp(-0.5 * r2);
-                gg = stat;
-            } else {
-                const double rr = sqrt(r2);
-                const double e = var * exp(-sqrt5 * rr);
-                stat = (1.0 + sqrt5 * rr + (5.0 / 3.0) * r2) * e;
-                gg = (5.0 / 3.0) * (1.0 + sqrt5 * rr) * e;
-            }
-            double kval = fma(lp, stat, ll);
-            if (row >= a.n_train || !active) kval = 0.0;
-            const double bt = a.beta[(long)d * a.n_pad + row];   // zero on padded rows
-            mu = fma(bt, kval, mu);
-            const double w = bt * lp * gg, w2 = bt * stat;
-#pragma unroll
-            for (int j = 0; j < DM; ++j)
-                if (j < dim) {
-                    jac[j] = fma(w, diff[j], jac[j]);
-                    jac2[j] = fma(w2, xr[j], jac2[j]);
-                }
-            int dg[I8_S];
-            split_digits(kval * inv_s, dg);
-#pragma unroll
-            for (int s = 0; s < I8_S; ++s) pk[s][qd >> 2] |= (uint32_t)(dg[s] & 0xff) << ((qd & 3) * 8);
+    for (int row0 = row_begin; row0 < row_end; row0 += STAGE) {
+        __syncthreads();
+        const double* src = a.xs + ((long)d * a.n_pad + row0) * dim;
+        const double* srcr = a.xraw + (long)row0 * dim;
+        for (int idx = threadIdx.x; idx < STAGE * dim; idx += I8_N) {
+            s_x[idx] = src[idx];
+            s_xr[idx] = srcr[idx];
         }
-        int8_t* dst = kb_base + (long)(row0 >> 6) * (I8_S * I8_B_TILE) + sw64_offset(rowp, row0 & 63);
-#pragma unroll
-        for (int s = 0; s < I8_S; ++s)
-            *reinterpret_cast<uint4*>(dst + (long)s * I8_B_TILE) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+        for (int idx = threadIdx.x; idx < STAGE; idx += I8_N) s_beta[idx] = a.beta[(long)d * a.n_pad + row0 + idx];
+        __syncthreads();
+        if (kern == SEGP_KERN_LIN_RBF)
+            kstar_i8_rows_composite<DM, SEGP_KERN_LIN_RBF, STAGE>(s_x, s_xr, s_beta, s_tab, zs, za, zv, dim, var, inv_s, row0,
+                                                                  a.n_train, active, kb_base, rowp, mu, jac, jac2);
+        else
+            kstar_i8_rows_composite<DM, SEGP_KERN_LIN_MAT52, STAGE>(s_x, s_xr, s_beta, s_tab, zs, za, zv, dim, var, inv_s, row0,
+                                                                    a.n_train, active, kb_base, rowp, mu, jac, jac2);
     }
     if (!active) return;
     a.mu_part[((long)split * n_s + d) * a.b_cap + b] = mu;
@@ -498,9 +553,15 @@ __device__ __forceinline__ void kstar_i8_item(const KstarI8Args& aa, int panel, 
 template <int D_T>
 __global__ void __launch_bounds__(I8_N) kstar_i8_composite_kernel(const KstarI8Args aa) {
     constexpr int DM = D_T > 0 ? D_T : MAX_D;
+    __shared__ double s_x[comp_stage_rows(DM) * DM];
+    __shared__ double s_xr[comp_stage_rows(DM) * DM];
+    __shared__ double s_beta[TILE];
+    __shared__ double s_tab[64];
     const KstarArgs& a = aa.k;
     const int d = (int)blockIdx.y;
     if (!kern_is_composite(a.kern[d])) return;
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));   // visible after the first
+                                                                                           // __syncthreads of the stage loop
     const int dim = D_T > 0 ? D_T : a.dim;
     const int panel = aa.panel0 + (int)blockIdx.x;
     const long b = (long)panel * I8_N + threadIdx.x;
@@ -508,7 +569,8 @@ __global__ void __launch_bounds__(I8_N) kstar_i8_composite_kernel(const KstarI8A
     double zs[DM];
     kstar_i8_load_inputs<DM>(a, b, active, dim, zs);
     int8_t* base = aa.ki8 + (((long)d * aa.npanel_cap + panel) * (a.n_pad / I8_KB)) * (long)(I8_S * I8_B_TILE);
-    kstar_i8_composite<DM>(aa, zs, dim, d, (int)blockIdx.z, (int)gridDim.y, b, active, base, (int)threadIdx.x);
+    kstar_i8_composite<DM>(aa, zs, dim, d, (int)blockIdx.z, (int)gridDim.y, b, active, base, (int)threadIdx.x, s_x, s_xr,
+                           s_beta, s_tab);
 }
 
 #ifndef SEGP_KS_MINB
