@@ -47,6 +47,26 @@ static void dev_free(T*& p) {
     p = nullptr;
 }
 
+// The handle-free entry points (scoring, arg-best, stand-alone ellipsoid step, safety distance) take their few hundred
+// bytes of device-side parameters from the stream-ordered allocator.  With the default release threshold of 0 the
+// pool gives everything back to the driver at the next synchronisation and the following cudaMallocAsync pays for a
+// fresh reservation: measured 2-6 ms per call inside a sampling-MPC iteration whose kernels take 0.5 ms.  Let the
+// device's default pool keep up to 64 MB (once per device).
+static void retain_small_async_allocations() {
+    static bool seen[64] = {};
+    if (!first_call_on_device(seen)) return;
+    int dev = 0;
+    cudaMemPool_t pool = nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    uint64_t cur = 0, want = 64ull << 20;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < want)
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+    cudaGetLastError();
+}
+
 }  // namespace segp
 
 using namespace segp;
@@ -1900,6 +1920,7 @@ struct TempParams {
     cudaStream_t st;
     explicit TempParams(cudaStream_t s) : st(s) {}
     int upload(const StepParams& sp) {
+        retain_small_async_allocations();
         SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d), sizeof(StepParams), st));
         SEGP_CUDA_CHECK(cudaMemcpyAsync(d, &sp, sizeof(sp), cudaMemcpyHostToDevice, st));
         return SEGP_OK;
@@ -2016,6 +2037,7 @@ int segp_safety_distance(int device, long n_items, int n_s, int m, const double*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* d_h = nullptr;
     const size_t n_h = (size_t)m * n_s + m;
+    retain_small_async_allocations();
     SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_h), n_h * sizeof(double), st));
     cudaError_t e = cudaMemcpyAsync(d_h, h_h_mat, (size_t)m * n_s * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
@@ -2118,6 +2140,7 @@ int segp_score_rollouts(int device, long n_batch, int horizon, int n_s, int n_u,
     DeviceGuard guard(device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ScoreParams* d_sp = nullptr;
+    retain_small_async_allocations();
     SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_sp), sizeof(ScoreParams), st));
     cudaError_t e = cudaMemcpyAsync(d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, st);
     int rc = SEGP_OK;
@@ -2167,6 +2190,7 @@ int segp_argbest(int device, long n_batch, const double* d_cost, const int32_t* 
     DeviceGuard guard(device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     BestCandidate* d_out = nullptr;
+    retain_small_async_allocations();
     SEGP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&d_out), sizeof(BestCandidate), st));
     int rc = launch_argbest(n_batch, d_cost, d_feasible, d_violation, d_out, st);
     BestCandidate out{};

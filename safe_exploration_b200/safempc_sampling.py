@@ -25,7 +25,7 @@ import warnings
 import numpy as np
 
 from . import _lib
-from .gp_reachability import rollout
+from .gp_reachability import RolloutResult, rollout
 from .ssm import BatchedGPSSM
 
 __all__ = ["score_rollouts", "best_candidate", "SamplingSafeMPC", "ScoreResult"]
@@ -293,7 +293,14 @@ class SamplingSafeMPC(object):
         """safempc_simple.py:569-597: k_fb = -dlqr(a, b, wx_feedback, wu_feedback), as a (1, n_s*n_u) row."""
         if not self.lin_prior:
             raise NotImplementedError("Cannot compute feed-back matrices without prior model")
-        return (-_dlqr(self.a, self.b, self.wx_feedback, self.wu_feedback)).reshape((1, self.n_s * self.n_u))
+        # the linear prior and the weights are fixed after construction: solve the Riccati equation once per value
+        key = (self.a.tobytes(), self.b.tobytes(), np.asarray(self.wx_feedback).tobytes(),
+               np.asarray(self.wu_feedback).tobytes())
+        if getattr(self, "_lqr_key", None) != key:
+            self._lqr_key = key
+            self._lqr_gain = (-_dlqr(self.a, self.b, self.wx_feedback, self.wu_feedback)).reshape(
+                (1, self.n_s * self.n_u))
+        return self._lqr_gain.copy()
 
     def eval_prior(self, state, action):
         """safempc_simple.py:552-566"""
@@ -302,6 +309,33 @@ class SamplingSafeMPC(object):
     def _rollout(self, p_0, k_ff, k_fb, q_0=None, k_fb_0=None):
         return rollout(self.ssm, p_0, k_ff, k_fb, self.l_mu, self.l_sigma, q_0, k_fb_0, self.beta_safety, self.a,
                        self.b, self.lin_trafo_gp_input)
+
+    def _rollout_device(self, p_0, k_ff, k_fb, q_0=None, k_fb_0=None):
+        """The same rollout with everything resident on the device: the candidates are copied into persistent CUDA
+        tensors (same addresses every call, so segp_multistep replays its launches as a CUDA graph) and the result
+        stays there for the scoring kernel.  Returns (RolloutResult of CUDA tensors, candidate tensor)."""
+        torch = self.ssm._torch
+        dev = self.ssm.device
+        bsz, hor = int(k_ff.shape[0]), int(k_ff.shape[1])
+        p_0 = np.asarray(p_0, dtype=np.float64)
+        key = (bsz, hor, p_0.size, k_fb.shape)
+        d = getattr(self, "_dev", None)
+        if d is None or d["key"] != key:
+            f64 = dict(dtype=torch.float64, device=dev)
+            d = {"key": key, "k_ff": torch.empty((bsz, hor, self.n_u), **f64), "p_0": torch.empty((p_0.size,), **f64),
+                 "k_fb": torch.empty(tuple(k_fb.shape), **f64),
+                 "out": RolloutResult(torch.empty((bsz, hor, self.n_s), **f64),
+                                      torch.empty((bsz, hor, self.n_s, self.n_s), **f64),
+                                      torch.empty((bsz, hor, self.n_s), **f64),
+                                      torch.empty((bsz,), dtype=torch.int32, device=dev))}
+            self._dev = d
+        d["k_ff"].copy_(torch.from_numpy(np.ascontiguousarray(k_ff)))
+        d["p_0"].copy_(torch.from_numpy(np.ascontiguousarray(p_0.reshape(-1))))
+        d["k_fb"].copy_(torch.from_numpy(np.ascontiguousarray(k_fb)))
+        p_arg = d["p_0"] if p_0.size == self.n_s else d["p_0"].reshape(bsz, self.n_s)
+        res = rollout(self.ssm, p_arg, d["k_ff"], d["k_fb"], self.l_mu, self.l_sigma, q_0, k_fb_0, self.beta_safety,
+                      self.a, self.b, self.lin_trafo_gp_input, out=d["out"])
+        return res, d["k_ff"]
 
     def _rollout_perf(self, p_0, k_ff_perf_traj, k_fb_perf):
         """The performance trajectory of every candidate: mean_equivalent_multistep / multi_step_taylor_symbolic
@@ -427,8 +461,18 @@ class SamplingSafeMPC(object):
                 x_cand[0] = mean_x
             else:
                 x_cand = p_0
-            res = self._rollout(x_cand, cand, k_fb3, q_0, k_fb_0)
-            sc = self._score(res, cand, k_fb3, q_0=q_0, k_fb_0=k_fb_0)
+            # Default problem (no performance trajectory, no Python cost function): candidates, rollout results and
+            # scores stay on the device -- persistent buffers, so the rollout replays as one CUDA graph -- and only
+            # the three (B,) score vectors and the best candidate's trajectory come back to the host.
+            on_dev = not has_perf and self.cost_func is None
+            if on_dev:
+                res, cand_d = self._rollout_device(x_cand, cand, k_fb3, q_0, k_fb_0)
+                sc_d = self._score(res, cand_d, self._dev["k_fb"], q_0=q_0, k_fb_0=k_fb_0)
+                sc = ScoreResult(sc_d.cost.cpu().numpy(), sc_d.feasible.cpu().numpy(), sc_d.violation.cpu().numpy(), None)
+            else:
+                sc_d = None
+                res = self._rollout(x_cand, cand, k_fb3, q_0, k_fb_0)
+                sc = self._score(res, cand, k_fb3, q_0=q_0, k_fb_0=k_fb_0)
             cost_v = sc.cost
             res_perf = cand_perf = None
             if has_perf:
@@ -448,9 +492,11 @@ class SamplingSafeMPC(object):
                     args += [res_perf.p_all, res_perf.q_all, res_perf.var_all, k_fb_perf, seq_perf[:, 1:]]
                 cost_v = np.asarray(self.cost_func(*args), dtype=np.float64).reshape(self.n_samples)
                 sc = ScoreResult(cost_v, sc.feasible * np.isfinite(cost_v).astype(sc.feasible.dtype), sc.violation, sc.g)
-            idx, cost, viol, feas = best_candidate(sc)
+            idx, cost, viol, feas = best_candidate(sc_d if on_dev else sc)   # arg-best on the device-resident scores
             if idx >= 0 and (best is None or (feas, -cost if feas else -viol) > (best[3], -best[1] if best[3] else -best[2])):
-                best = (cand[idx].copy(), cost, viol, feas, res.p_all[idx].copy(), res.q_all[idx].copy(),
+                p_best = res.p_all[idx].cpu().numpy() if on_dev else res.p_all[idx].copy()
+                q_best = res.q_all[idx].cpu().numpy() if on_dev else res.q_all[idx].copy()
+                best = (cand[idx].copy(), cost, viol, feas, p_best, q_best,
                         None if cand_perf is None else cand_perf[idx].copy(),
                         x_cand[idx].copy() if self.opt_x0 else p_0)
             order = np.lexsort((np.where(sc.feasible > 0, sc.cost, sc.violation), -sc.feasible))
