@@ -24,7 +24,7 @@ import warnings
 
 import numpy as np
 
-from .gp_reachability import rollout
+from .gp_reachability import RolloutResult, rollout
 from .safempc_sampling import ScoreResult, best_candidate, score_rollouts
 from .ssm import BatchedGPSSM
 
@@ -132,6 +132,31 @@ class SamplingCautiousMPC(object):
         return rollout(self.gp, mu_0, k_ff, k_fb_all, zeros, zeros, None, None, 1.0, self.a, self.b,
                        self.lin_trafo_gp_input, True, self._prop_mode)
 
+    def _propagate_device(self, mu_0, k_ff, k_fb):
+        """_propagate with the candidates copied into persistent CUDA tensors and the result left on the device for the
+        scoring kernel (same addresses every call: the launches replay as a CUDA graph).  Returns (result, k_ff tensor)."""
+        torch = self.gp._torch
+        dev = self.gp.device
+        bsz = int(k_ff.shape[0])
+        d = getattr(self, "_dev", None)
+        if d is None or d["key"] != bsz:
+            f64 = dict(dtype=torch.float64, device=dev)
+            d = {"key": bsz, "k_ff": torch.empty((bsz, self.T, self.n_u), **f64), "mu_0": torch.empty((self.n_s,), **f64),
+                 "k_fb": torch.empty((max(self.T - 1, 0), self.n_u, self.n_s), **f64),
+                 "out": RolloutResult(torch.empty((bsz, self.T, self.n_s), **f64),
+                                      torch.empty((bsz, self.T, self.n_s, self.n_s), **f64),
+                                      torch.empty((bsz, self.T, self.n_s), **f64),
+                                      torch.empty((bsz,), dtype=torch.int32, device=dev))}
+            self._dev = d
+        k_fb_all = np.tile(np.reshape(k_fb, (1, self.n_u, self.n_s)), (max(self.T - 1, 1), 1, 1))[:self.T - 1]
+        d["k_ff"].copy_(torch.from_numpy(np.ascontiguousarray(k_ff)))
+        d["mu_0"].copy_(torch.from_numpy(np.ascontiguousarray(np.reshape(mu_0, (self.n_s,)))))
+        d["k_fb"].copy_(torch.from_numpy(np.ascontiguousarray(k_fb_all)))
+        zeros = np.zeros(self.n_s)
+        res = rollout(self.gp, d["mu_0"], d["k_ff"], d["k_fb"], zeros, zeros, None, None, 1.0, self.a, self.b,
+                      self.lin_trafo_gp_input, True, self._prop_mode, out=d["out"])
+        return res, d["k_ff"]
+
     def generate_safety_constraints(self, p_all, q_all, u_0, k_fb, k_ff):
         """cautious_mpc.py:337-395 evaluated numerically for a batch: p_all (B,T,n_s), q_all (B,T,n_s,n_s), u_0 (B,n_u),
         k_fb (n_u,n_s), k_ff (B,T-1,n_u) -> ScoreResult with g (B,n_g) in the reference's order and the feasibility
@@ -176,16 +201,26 @@ class SamplingCautiousMPC(object):
             cand[0] = mean
             if self.has_ctrl_bounds:                      # u_0 is applied at a point: plain bounds (:363-367); without
                 cand[:, 0] = np.clip(cand[:, 0], lo, hi)  # control bounds the reference leaves it free: no clipping
-            res = self._propagate(mu_0, cand, k_fb_0)
-            sc = self._score(res, cand, k_fb_0)
-            if self.cost_func is not None:
+            # default cost: candidates, propagated trajectories and scores stay on the device; only the three (B,) score
+            # vectors and the best candidate's trajectory come back (a Python cost function needs host arrays)
+            on_dev = self.cost_func is None
+            if on_dev:
+                res, cand_d = self._propagate_device(mu_0, cand, k_fb_0)
+                sc_d = self._score(res, cand_d, k_fb_0)
+                sc = ScoreResult(sc_d.cost.cpu().numpy(), sc_d.feasible.cpu().numpy(), sc_d.violation.cpu().numpy(), None)
+            else:
+                sc_d = None
+                res = self._propagate(mu_0, cand, k_fb_0)
+                sc = self._score(res, cand, k_fb_0)
                 cost = np.asarray(self.cost_func(mu_0, cand[:, 0], res.p_all, res.q_all, cand[:, 1:], k_fb_0,
                                                  res.var_all), dtype=np.float64).reshape(-1)
                 sc = ScoreResult(cost, sc.feasible, sc.violation, sc.g)
-            idx, cost_b, viol_b, feas_b = best_candidate(sc)
+            idx, cost_b, viol_b, feas_b = best_candidate(sc_d if on_dev else sc)
             if idx >= 0 and (best is None or (feas_b, -cost_b if feas_b else -viol_b) >
                              (best[3], -best[1] if best[3] else -best[2])):
-                best = (cand[idx].copy(), cost_b, viol_b, feas_b, res.p_all[idx].copy(), res.q_all[idx].copy())
+                p_best = res.p_all[idx].cpu().numpy() if on_dev else res.p_all[idx].copy()
+                q_best = res.q_all[idx].cpu().numpy() if on_dev else res.q_all[idx].copy()
+                best = (cand[idx].copy(), cost_b, viol_b, feas_b, p_best, q_best)
             order = np.lexsort((np.where(sc.feasible > 0, sc.cost, sc.violation), -sc.feasible))
             elite = cand[order[:min(self.n_elite, self.n_samples)]]
             mean = elite.mean(axis=0)
